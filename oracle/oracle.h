@@ -1,0 +1,131 @@
+/* ORACLE — TEST INFRASTRUCTURE ONLY (see oracle.cpp header). C interface for ctypes. */
+#ifndef LEGOLOAM_ORACLE_H_
+#define LEGOLOAM_ORACLE_H_
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Packed point: x, y, z, intensity (16 B). The reference's pcl::PointXYZI is the same four
+ * floats at byte 0/4/8/16 of a 32-byte struct (utility.h:45); tests repack. */
+typedef struct { float x, y, z, i; } orc_p4;
+
+/* Hot-path knobs; defaults = the reference's hard-coded values. */
+typedef struct {
+  float corner_leaf;      /* 0.2  mapOptmization.cpp:92 */
+  float surf_leaf;        /* 0.4  mapOptmization.cpp:93 */
+  float max_sq_dist;      /* 1.0  :1279 / :1389 */
+  float eig_ratio;        /* 3    :1325 */
+  double plane_tol;       /* 0.2  :1416  (double literal in the reference: float is promoted) */
+  double weight_k;        /* 0.9  :1363 / :1425  (double literal) */
+  double min_weight;      /* 0.1  :1370 / :1435  (double literal) */
+  int   min_residuals;    /* 50   :1453 */
+  float eig_thresh;       /* 100  :1519 */
+  int   iter_count_thres; /* 200  loam_config.yaml:35 */
+  float step_size;        /* 1.0  loam_config.yaml:32, used at :1500 */
+  float stop_thres;       /* 0.05 loam_config.yaml:33, used at :1554 */
+  int   apply_update;     /* 0 = as shipped (:1539-1545 commented out), 1 = upstream */
+  int   eigen_mode;       /* 0 = as shipped (row 0 / row-masked V), 1 = upstream semantics */
+  int   map_downsample;   /* 1 = VoxelGrid on the surrounding maps (:1225-1231) */
+  int   min_corner_map;   /* 10   :1573 */
+  int   min_surf_map;     /* 100  :1573 */
+} orc_params;
+
+/* State that persists across scans in the reference (members of MapOptimization). */
+typedef struct {
+  int   is_degenerate;    /* mapOptimization.h: isDegenerate */
+  float matP[36];         /* row-major 6x6 */
+  float min_lambda;
+  float cf_mean;
+} orc_state;
+
+typedef struct {
+  int   status;           /* 0 = optimised, 1 = skipped by the map-size guard (:1573) */
+  int   iter_num;
+  float min_lambda;
+  float cf_mean;
+  int   is_degenerate;
+  int   converged;
+  int   sel_num;          /* laserCloudSelNum of the last iteration */
+  float pose[6];          /* transformTobeMapped after the loop */
+  float last_x[6];        /* matX of the last iteration (after the degeneracy projection) */
+} orc_result;
+
+void orc_default_params(orc_params* p);
+void orc_init_state(orc_state* s);
+
+/* k-NN backend: 0 = brute force (canonical, ties by index), 1 = own uniform grid (same
+ * canonical result), 2 = external (the reference's vendored nanoflann via oracle/_ref). */
+typedef void* (*orc_ext_build_fn)(const orc_p4* pts, int n);
+typedef void  (*orc_ext_knn5_fn)(void* tree, const float q[3], int* idx5, float* d2_5);
+typedef void  (*orc_ext_free_fn)(void* tree);
+void orc_set_knn_backend(int kind);
+void orc_set_ext_knn(orc_ext_build_fn b, orc_ext_knn5_fn q, orc_ext_free_fn f);
+
+/* a2  transformPointCloud  mapOptmization.cpp:637-667; pose6 = [rx ry rz tx ty tz]. */
+void orc_transform_cloud(const orc_p4* in, int n, const float pose6[6], orc_p4* out);
+
+/* a3  pcl::VoxelGrid<PointXYZI>::filter. member[i] = output slot of input point i (or -1 for
+ * non-finite points); returns 0, or 1 when the int32 voxel index would overflow (PCL then
+ * passes the input through unchanged; so do we). */
+int orc_voxel_downsample(const orc_p4* in, int n, float leaf, orc_p4* out, int* n_out, int* member);
+
+/* a5  exact 5-NN. idx/d2 are [nq][5], ascending by (d2, idx). Missing neighbours: idx -1. */
+void orc_knn5(const orc_p4* map, int n, const orc_p4* q, int nq, int* idx, float* d2, int backend);
+
+/* a6  pointAssociateToMap  :606-620 */
+void orc_point_associate_to_map(const orc_p4* in, int n, const float pose6[6], orc_p4* out);
+
+/* a7 / a8. Per query (original order): mask[i]=1 if the residual is kept, coeff[i] = the
+ * 4-float record, knn_idx[i][5] / knn_d2[i][5], accept[i] = (d2_5 < max_sq_dist). */
+void orc_corner_residuals(const orc_p4* map, int n, const orc_p4* q, int nq, const float pose6[6],
+                          const orc_params* prm, float* coeff, int* mask, int* accept,
+                          int* knn_idx, float* knn_d2);
+void orc_surf_residuals(const orc_p4* map, int n, const orc_p4* q, int nq, const float pose6[6],
+                        const orc_params* prm, float* coeff, int* mask, int* accept,
+                        int* knn_idx, float* knn_d2);
+
+/* a9  LMOptimization(iterCount). ori/coeff are the compacted residual records. Outputs the
+ * 6x6 AtA (row-major), Atb, x; updates pose (if apply_update) and state. Returns 1 when the
+ * iteration reports convergence, 0 otherwise, -1 when skipped (n < min_residuals). */
+int orc_lm_step(const orc_p4* ori, const float* coeff, int n, int iter, float pose6[6],
+                const orc_params* prm, orc_state* st, float* AtA36, float* Atb6, float* x6,
+                float* deltaR, float* deltaT);
+
+/* a10 scan2MapOptimization on already-downsampled maps. */
+void orc_scan2map(const orc_p4* corner_map, int nc, const orc_p4* surf_map, int ns,
+                  const orc_p4* corner_q, int nqc, const orc_p4* surf_q, int nqs,
+                  float pose6[6], const orc_params* prm, orc_state* st, orc_result* res);
+
+/* a1  extractSurroundingKeyFrames tail: concatenate the selected keyframes (corner | surf then
+ * outlier per keyframe, cache order = ids order), transformed by their poses, then VoxelGrid.
+ * Clouds are given as one packed array + offsets (n_kf + 1 entries each). */
+void orc_build_local_map(int n_kf, const float* poses6, const orc_p4* corner, const int* corner_off,
+                         const orc_p4* surf, const int* surf_off, const orc_p4* outlier,
+                         const int* outlier_off, const orc_params* prm, orc_p4* corner_ds,
+                         int* n_corner_ds, orc_p4* surf_ds, int* n_surf_ds, int* n_corner_raw,
+                         int* n_surf_raw);
+
+/* Prior: transformAssociateToMap  mapOptmization.cpp:458-581 */
+void orc_transform_associate_to_map(const float sum[6], const float bef[6], const float aft[6],
+                                    float tobe[6]);
+
+/* Replay harness (config 2): the per-scan body of MapOptimization::run (:1878-1888) with
+ * loop closure on (sliding window of the last `window` keyframes, :1101-1151) and the pose
+ * graph as pass-through. */
+typedef struct orc_replay orc_replay;
+orc_replay* orc_replay_create(const orc_params* prm, int window);
+void orc_replay_destroy(orc_replay* r);
+/* One frame: clouds as the reference receives them after downsampleCurrentScan
+ * (corner_scan raw = keyframe corner cloud, corner_scan_ds = corner queries, surf_last_ds and
+ * outlier_last_ds = keyframe surf/outlier clouds, surf_total_ds = surf queries). odom = transformSum. */
+void orc_replay_step(orc_replay* r, const float odom6[6], const orc_p4* corner_scan, int n_cs,
+                     const orc_p4* corner_scan_ds, int n_csd, const orc_p4* surf_last_ds, int n_sl,
+                     const orc_p4* outlier_last_ds, int n_ol, const orc_p4* surf_total_ds, int n_st,
+                     orc_result* res, int* n_corner_map_ds, int* n_surf_map_ds);
+void orc_replay_get_map(orc_replay* r, int which, orc_p4* out, int cap, int* n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

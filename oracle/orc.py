@@ -1,0 +1,251 @@
+"""ORACLE — TEST INFRASTRUCTURE ONLY.
+
+ctypes wrapper over oracle/_build/liboracle.so (the CPU restatement of the reference's scan-to-map
+path, oracle.cpp) and, when present, oracle/_ref/libnanoflann_ref.so (the reference's own vendored
+nanoflann compiled from /root/reference in place). Only tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference legs may import this module; the product package
+(lego-loam-sr_b200/) never does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "_build", "liboracle.so")
+_REF = os.path.join(_HERE, "_ref", "libnanoflann_ref.so")
+
+KNN_BRUTE, KNN_GRID, KNN_NANOFLANN = 0, 1, 2
+
+
+class Params(C.Structure):
+    _fields_ = [
+        ("corner_leaf", C.c_float), ("surf_leaf", C.c_float), ("max_sq_dist", C.c_float),
+        ("eig_ratio", C.c_float), ("plane_tol", C.c_double), ("weight_k", C.c_double),
+        ("min_weight", C.c_double), ("min_residuals", C.c_int), ("eig_thresh", C.c_float),
+        ("iter_count_thres", C.c_int), ("step_size", C.c_float), ("stop_thres", C.c_float),
+        ("apply_update", C.c_int), ("eigen_mode", C.c_int), ("map_downsample", C.c_int),
+        ("min_corner_map", C.c_int), ("min_surf_map", C.c_int),
+    ]
+
+
+class State(C.Structure):
+    _fields_ = [("is_degenerate", C.c_int), ("matP", C.c_float * 36), ("min_lambda", C.c_float),
+                ("cf_mean", C.c_float)]
+
+
+class Result(C.Structure):
+    _fields_ = [("status", C.c_int), ("iter_num", C.c_int), ("min_lambda", C.c_float),
+                ("cf_mean", C.c_float), ("is_degenerate", C.c_int), ("converged", C.c_int),
+                ("sel_num", C.c_int), ("pose", C.c_float * 6), ("last_x", C.c_float * 6)]
+
+
+def build(force=False):
+    """Compile the restatement (always) and the nanoflann shim (when /root/reference exists)."""
+    if force or not os.path.exists(_LIB) or any(
+            os.path.getmtime(os.path.join(_HERE, f)) > os.path.getmtime(_LIB)
+            for f in ("oracle.cpp", "oracle.h", "eigen_restate.hpp")):
+        subprocess.check_call(["make", "-C", _HERE, "all"], stdout=subprocess.DEVNULL)
+    if os.path.isdir("/root/reference/LeGO-LOAM/include/lego_loam") and (force or not os.path.exists(_REF)):
+        subprocess.check_call(["make", "-C", _HERE, "ref"], stdout=subprocess.DEVNULL)
+
+
+_lib = None
+_ref = None
+_keep = []
+
+
+def _p4(a):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    assert a.ndim == 2 and a.shape[1] == 4, a.shape
+    return a
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def lib():
+    global _lib, _ref
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_LIB)
+        _lib.orc_replay_create.restype = C.c_void_p
+        _lib.orc_lm_step.restype = C.c_int
+        _lib.orc_voxel_downsample.restype = C.c_int
+        if os.path.exists(_REF):
+            _ref = C.CDLL(_REF)
+            _ref.ref_kdtree_build.restype = C.c_void_p
+            _lib.orc_set_ext_knn(C.cast(_ref.ref_kdtree_build, C.c_void_p),
+                                 C.cast(_ref.ref_kdtree_knn5, C.c_void_p),
+                                 C.cast(_ref.ref_kdtree_free, C.c_void_p))
+    return _lib
+
+
+def have_ref():
+    lib()
+    return _ref is not None
+
+
+def default_params(**kw):
+    p = Params()
+    lib().orc_default_params(C.byref(p))
+    for k, v in kw.items():
+        assert hasattr(p, k), k
+        setattr(p, k, v)
+    return p
+
+
+def new_state():
+    s = State()
+    lib().orc_init_state(C.byref(s))
+    return s
+
+
+def set_knn_backend(kind):
+    if kind == KNN_NANOFLANN and not have_ref():
+        raise RuntimeError("oracle/_ref/libnanoflann_ref.so is not built")
+    lib().orc_set_knn_backend(C.c_int(kind))
+
+
+def transform_cloud(pts, pose6):
+    pts = _p4(pts)
+    out = np.empty_like(pts)
+    pose = np.ascontiguousarray(pose6, dtype=np.float32)
+    lib().orc_transform_cloud(_ptr(pts), C.c_int(len(pts)), _ptr(pose), _ptr(out))
+    return out
+
+
+def voxel_downsample(pts, leaf):
+    pts = _p4(pts)
+    n = len(pts)
+    out = np.empty((max(n, 1), 4), np.float32)
+    member = np.empty(max(n, 1), np.int32)
+    n_out = C.c_int(0)
+    flag = lib().orc_voxel_downsample(_ptr(pts), C.c_int(n), C.c_float(leaf), _ptr(out), C.byref(n_out),
+                                      _ptr(member))
+    return out[:n_out.value].copy(), member[:n], flag
+
+
+def knn5(map_pts, q, backend=KNN_GRID):
+    map_pts, q = _p4(map_pts), _p4(q)
+    if backend == KNN_NANOFLANN and not have_ref():
+        raise RuntimeError("oracle/_ref/libnanoflann_ref.so is not built")
+    idx = np.empty((len(q), 5), np.int32)
+    d2 = np.empty((len(q), 5), np.float32)
+    lib().orc_knn5(_ptr(map_pts), C.c_int(len(map_pts)), _ptr(q), C.c_int(len(q)), _ptr(idx), _ptr(d2),
+                   C.c_int(backend))
+    return idx, d2
+
+
+def _residuals(fn, map_pts, q, pose6, prm):
+    map_pts, q = _p4(map_pts), _p4(q)
+    nq = len(q)
+    pose = np.ascontiguousarray(pose6, dtype=np.float32)
+    coeff = np.zeros((nq, 4), np.float32)
+    mask = np.zeros(nq, np.int32)
+    accept = np.zeros(nq, np.int32)
+    idx = np.zeros((nq, 5), np.int32)
+    d2 = np.zeros((nq, 5), np.float32)
+    fn(_ptr(map_pts), C.c_int(len(map_pts)), _ptr(q), C.c_int(nq), _ptr(pose), C.byref(prm), _ptr(coeff),
+       _ptr(mask), _ptr(accept), _ptr(idx), _ptr(d2))
+    return dict(coeff=coeff, mask=mask, accept=accept, knn_idx=idx, knn_d2=d2)
+
+
+def corner_residuals(map_pts, q, pose6, prm):
+    return _residuals(lib().orc_corner_residuals, map_pts, q, pose6, prm)
+
+
+def surf_residuals(map_pts, q, pose6, prm):
+    return _residuals(lib().orc_surf_residuals, map_pts, q, pose6, prm)
+
+
+def lm_step(ori, coeff, it, pose6, prm, st):
+    ori = _p4(ori)
+    coeff = _p4(coeff)
+    pose = np.array(pose6, dtype=np.float32)
+    AtA = np.zeros((6, 6), np.float32)
+    Atb = np.zeros(6, np.float32)
+    x = np.zeros(6, np.float32)
+    dR, dT = C.c_float(0), C.c_float(0)
+    r = lib().orc_lm_step(_ptr(ori), _ptr(coeff), C.c_int(len(ori)), C.c_int(it), _ptr(pose), C.byref(prm),
+                          C.byref(st), _ptr(AtA), _ptr(Atb), _ptr(x), C.byref(dR), C.byref(dT))
+    return dict(ret=r, pose=pose, AtA=AtA, Atb=Atb, x=x, deltaR=dR.value, deltaT=dT.value)
+
+
+def scan2map(corner_map, surf_map, corner_q, surf_q, pose6, prm, st=None):
+    corner_map, surf_map, corner_q, surf_q = map(_p4, (corner_map, surf_map, corner_q, surf_q))
+    pose = np.array(pose6, dtype=np.float32)
+    st = st if st is not None else new_state()
+    res = Result()
+    lib().orc_scan2map(_ptr(corner_map), C.c_int(len(corner_map)), _ptr(surf_map), C.c_int(len(surf_map)),
+                       _ptr(corner_q), C.c_int(len(corner_q)), _ptr(surf_q), C.c_int(len(surf_q)), _ptr(pose),
+                       C.byref(prm), C.byref(st), C.byref(res))
+    return res, pose, st
+
+
+def _pack_clouds(clouds):
+    off = np.zeros(len(clouds) + 1, np.int32)
+    for i, c in enumerate(clouds):
+        off[i + 1] = off[i] + len(c)
+    if off[-1] == 0:
+        return np.zeros((1, 4), np.float32), off
+    return np.ascontiguousarray(np.concatenate([_p4(c) for c in clouds if len(c)]), np.float32), off
+
+
+def build_local_map(poses6, corner, surf, outlier, prm):
+    """poses6: [n_kf, 6]; corner/surf/outlier: lists of [n,4] clouds in the sensor frame."""
+    n_kf = len(poses6)
+    poses = np.ascontiguousarray(poses6, np.float32).reshape(-1)
+    c, co = _pack_clouds(corner)
+    s, so = _pack_clouds(surf)
+    o, oo = _pack_clouds(outlier)
+    cap_c = max(int(co[-1]), 1)
+    cap_s = max(int(so[-1] + oo[-1]), 1)
+    cds = np.empty((cap_c, 4), np.float32)
+    sds = np.empty((cap_s, 4), np.float32)
+    ncd, nsd, ncr, nsr = C.c_int(0), C.c_int(0), C.c_int(0), C.c_int(0)
+    lib().orc_build_local_map(C.c_int(n_kf), _ptr(poses), _ptr(c), _ptr(co), _ptr(s), _ptr(so), _ptr(o), _ptr(oo),
+                              C.byref(prm), _ptr(cds), C.byref(ncd), _ptr(sds), C.byref(nsd), C.byref(ncr),
+                              C.byref(nsr))
+    return cds[:ncd.value].copy(), sds[:nsd.value].copy(), ncr.value, nsr.value
+
+
+def transform_associate_to_map(tsum, bef, aft):
+    a = [np.ascontiguousarray(v, np.float32) for v in (tsum, bef, aft)]
+    out = np.zeros(6, np.float32)
+    lib().orc_transform_associate_to_map(_ptr(a[0]), _ptr(a[1]), _ptr(a[2]), _ptr(out))
+    return out
+
+
+class Replay:
+    def __init__(self, prm, window=50):
+        self._h = C.c_void_p(lib().orc_replay_create(C.byref(prm), C.c_int(window)))
+
+    def step(self, odom6, corner_scan, corner_scan_ds, surf_last_ds, outlier_last_ds, surf_total_ds):
+        a = [_p4(v) for v in (corner_scan, corner_scan_ds, surf_last_ds, outlier_last_ds, surf_total_ds)]
+        odom = np.ascontiguousarray(odom6, np.float32)
+        res = Result()
+        nc, ns = C.c_int(0), C.c_int(0)
+        lib().orc_replay_step(self._h, _ptr(odom), _ptr(a[0]), C.c_int(len(a[0])), _ptr(a[1]), C.c_int(len(a[1])),
+                              _ptr(a[2]), C.c_int(len(a[2])), _ptr(a[3]), C.c_int(len(a[3])), _ptr(a[4]),
+                              C.c_int(len(a[4])), C.byref(res), C.byref(nc), C.byref(ns))
+        return res, nc.value, ns.value
+
+    def get_map(self, which, cap=4_000_000):
+        out = np.empty((cap, 4), np.float32)
+        n = C.c_int(0)
+        lib().orc_replay_get_map(self._h, C.c_int(which), _ptr(out), C.c_int(cap), C.byref(n))
+        return out[:n.value].copy()
+
+    def close(self):
+        if self._h:
+            lib().orc_replay_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
