@@ -1,0 +1,1066 @@
+// Host side of the C ABI declared in include/legoloam_b200.h: handle, device memory, launch
+// sequences. Everything numerical runs in the kernels of map_build.cuh / radix_sort.cuh / lm.cuh /
+// fit.cuh; this file only marshals, launches and copies. There is no CPU fallback: a call that cannot
+// reach the GPU fails with LL_ERR_CUDA and ll_last_error_string() says why.
+#include "../../include/legoloam_b200.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "common.cuh"
+#include "fit.cuh"
+#include "lm.cuh"
+#include "map_build.cuh"
+#include "normal_eq.cuh"
+#include "radix_sort.cuh"
+
+using namespace ll;
+
+namespace {
+
+constexpr size_t kArenaChunk = 64ull << 20;  // keyframe store grows in 64 MiB slabs
+constexpr int kCellCap = 1 << 24;            // 16.7 M one-metre cells per search grid (<= 24 key bits: 3 sort passes)
+constexpr int kGridPasses = 3;
+constexpr int kFirstChunk = 12;              // LM iterations enqueued before the first look at `done`
+constexpr int kNextChunk = 16;
+
+struct Keyframe {
+  float4* d[3] = {nullptr, nullptr, nullptr};  // corner, surf, outlier (device, packed float4, sensor frame)
+  int n[3] = {0, 0, 0};
+  float pose[6] = {0, 0, 0, 0, 0, 0};
+};
+
+// One map's worth of device buffers. Slots 0 / 1 are the corner / surf surrounding maps; slot 2 serves
+// the stand-alone VoxelGrid entry point so that it never disturbs the local map.
+struct MapSlot {
+  size_t cap = 0;  // points
+  float4 *raw = nullptr, *ds = nullptr, *sorted = nullptr;
+  uint32_t *keys[2] = {nullptr, nullptr}, *vals[2] = {nullptr, nullptr};
+  int2* cells = nullptr;
+  uint8_t* scratch = nullptr;  // [MapState | ghist | tile counters | head status | look-back status], zeroed per build
+  size_t scratch_bytes = 0;
+  int max_tiles = 0, max_head_tiles = 0;
+  int* member = nullptr;
+  int n_raw = 0;
+  MapState* st() const { return reinterpret_cast<MapState*>(scratch); }
+  uint32_t* ghist() const { return reinterpret_cast<uint32_t*>(scratch + 256); }
+  uint32_t* tile_counter() const { return ghist() + RS_MAX_PASSES * RS_RADIX; }
+  uint32_t* head_status() const { return tile_counter() + 8; }
+  uint32_t* status() const { return head_status() + max_head_tiles; }
+};
+static_assert(sizeof(MapState) <= 256, "MapState must fit the first 256 bytes of the scratch block");
+
+}  // namespace
+
+struct ll_handle_s {
+  ll_params prm;
+  int device = 0;
+  int num_sms = kNumSMsHint;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  uint64_t launches = 0;
+
+  std::vector<void*> arena;
+  size_t arena_off = 0, arena_cap = 0;
+  std::unordered_map<int, Keyframe> kfs;
+
+  uint8_t* pinned = nullptr;
+  size_t pinned_bytes = 0;
+  cudaEvent_t pinned_evt = nullptr;
+
+  MapSlot slot[3];
+  bool map_ready = false;
+  bool cells_given_up = false;
+
+  Segment* d_segs = nullptr;
+  BlockJob* d_jobs = nullptr;
+  size_t segs_cap = 0, jobs_cap = 0;
+
+  float4* dq[2] = {nullptr, nullptr};
+  size_t dq_cap[2] = {0, 0};
+  const float4* q_ptr[2] = {nullptr, nullptr};
+  int nq[2] = {0, 0};
+
+  LMState* d_state = nullptr;
+  LMState* h_state = nullptr;  // pinned mirror
+  float* d_partials = nullptr;
+  int partial_blocks = 0;
+  bool scan_pending = false;
+  int iters_enqueued = 0;
+  int lm_blocks = 0;
+
+  void* d_tmp[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // emit / stage scratch
+
+  // optional per-kernel-class timing with CUDA events on the launching stream (bench.py roofline)
+  bool prof_on = false;
+  int prof_pending = -1;
+  cudaEvent_t prof_a = nullptr;
+  std::vector<cudaEvent_t> prof_pool;
+  size_t prof_used = 0;
+  struct ProfRec { int cls; cudaEvent_t a, b; };
+  std::vector<ProfRec> prof_recs;
+  size_t tmp_bytes[6] = {0, 0, 0, 0, 0, 0};
+};
+
+namespace {
+
+int fail(ll_handle h, int code, const std::string& msg) {
+  if (h) h->err = msg;
+  return code;
+}
+
+cudaEvent_t prof_event(ll_handle h) {
+  if (h->prof_used == h->prof_pool.size()) {
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    h->prof_pool.push_back(e);
+  }
+  return h->prof_pool[h->prof_used++];
+}
+void prof_begin(ll_handle h, int cls) {
+  h->prof_a = prof_event(h);
+  cudaEventRecord(h->prof_a, h->stream);
+  h->prof_pending = cls;
+}
+void prof_end(ll_handle h) {
+  cudaEvent_t b = prof_event(h);
+  cudaEventRecord(b, h->stream);
+  h->prof_recs.push_back({h->prof_pending, h->prof_a, b});
+  h->prof_pending = -1;
+}
+
+#define LL_CUDA(h, expr)                                                                     \
+  do {                                                                                       \
+    cudaError_t _e = (expr);                                                                 \
+    if (_e != cudaSuccess) {                                                                 \
+      return fail(h, LL_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));      \
+    }                                                                                        \
+  } while (0)
+
+#define LL_TRY(expr)            \
+  do {                          \
+    int _r = (expr);            \
+    if (_r != LL_OK) return _r; \
+  } while (0)
+
+#define LL_PROF(h, cls)                 \
+  do {                                  \
+    if ((h)->prof_on) prof_begin(h, cls); \
+  } while (0)
+
+#define LL_LAUNCHED(h)                                                                         \
+  do {                                                                                         \
+    (h)->launches++;                                                                           \
+    if ((h)->prof_pending >= 0) prof_end(h);                                                   \
+    cudaError_t _e = cudaPeekAtLastError();                                                    \
+    if (_e != cudaSuccess) return fail(h, LL_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(_e)); \
+  } while (0)
+
+int ensure_bytes(ll_handle h, void** p, size_t* cap, size_t need) {
+  if (*cap >= need && *p) return LL_OK;
+  LL_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (*p) LL_CUDA(h, cudaFree(*p));
+  *p = nullptr;
+  size_t newcap = need + need / 2 + 256;
+  cudaError_t e = cudaMalloc(p, newcap);
+  if (e != cudaSuccess) return fail(h, LL_ERR_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+  *cap = newcap;
+  return LL_OK;
+}
+
+int ensure_pinned(ll_handle h, size_t need) {
+  if (h->pinned_bytes >= need) return LL_OK;
+  LL_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (h->pinned) LL_CUDA(h, cudaFreeHost(h->pinned));
+  h->pinned = nullptr;
+  size_t newcap = need + need / 2 + 4096;
+  cudaError_t e = cudaMallocHost(reinterpret_cast<void**>(&h->pinned), newcap);
+  if (e != cudaSuccess) return fail(h, LL_ERR_NOMEM, std::string("cudaMallocHost: ") + cudaGetErrorString(e));
+  h->pinned_bytes = newcap;
+  return LL_OK;
+}
+
+// The staging buffer is reused by consecutive uploads: wait until the previous copy has drained it.
+int pinned_acquire(ll_handle h, size_t need) {
+  LL_CUDA(h, cudaEventSynchronize(h->pinned_evt));
+  return ensure_pinned(h, need);
+}
+int pinned_release(ll_handle h) {
+  LL_CUDA(h, cudaEventRecord(h->pinned_evt, h->stream));
+  return LL_OK;
+}
+
+// pcl::PointXYZI -> packed float4. stride 16: {x,y,z,intensity}; otherwise intensity sits at byte 16.
+inline void pack_points(float4* dst, const void* src, size_t n, size_t stride) {
+  const uint8_t* b = static_cast<const uint8_t*>(src);
+  const size_t ioff = stride == 16 ? 12 : 16;
+  for (size_t i = 0; i < n; ++i) {
+    const float* f = reinterpret_cast<const float*>(b + i * stride);
+    float w;
+    std::memcpy(&w, b + i * stride + ioff, 4);
+    dst[i] = make_float4(f[0], f[1], f[2], w);
+  }
+}
+inline void unpack_points(void* dst, const float4* src, size_t n, size_t stride) {
+  uint8_t* b = static_cast<uint8_t*>(dst);
+  if (stride == 16) {
+    std::memcpy(dst, src, n * 16);
+    return;
+  }
+  for (size_t i = 0; i < n; ++i) {
+    std::memset(b + i * stride, 0, stride);
+    const float v[4] = {src[i].x, src[i].y, src[i].z, 1.0f};  // PCL_ADD_POINT4D pads with 1
+    std::memcpy(b + i * stride, v, 16);
+    std::memcpy(b + i * stride + 16, &src[i].w, 4);
+  }
+}
+
+bool stride_ok(size_t s) { return s == 16 || (s >= 20 && s % 4 == 0); }
+
+int upload_points(ll_handle h, float4* d_dst, const void* src, size_t n, size_t stride) {
+  if (n == 0) return LL_OK;
+  LL_TRY(pinned_acquire(h, n * sizeof(float4)));
+  pack_points(reinterpret_cast<float4*>(h->pinned), src, n, stride);
+  LL_CUDA(h, cudaMemcpyAsync(d_dst, h->pinned, n * sizeof(float4), cudaMemcpyHostToDevice, h->stream));
+  return pinned_release(h);
+}
+
+int arena_alloc(ll_handle h, size_t bytes, void** out) {
+  bytes = (bytes + 255) & ~size_t(255);
+  if (bytes == 0) bytes = 256;
+  if (h->arena.empty() || h->arena_off + bytes > h->arena_cap) {
+    size_t chunk = bytes > kArenaChunk ? bytes : kArenaChunk;
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, chunk);
+    if (e != cudaSuccess) return fail(h, LL_ERR_NOMEM, std::string("cudaMalloc(keyframe arena): ") + cudaGetErrorString(e));
+    h->arena.push_back(p);
+    h->arena_off = 0;
+    h->arena_cap = chunk;
+  }
+  *out = static_cast<uint8_t*>(h->arena.back()) + h->arena_off;
+  h->arena_off += bytes;
+  return LL_OK;
+}
+
+int ensure_slot(ll_handle h, int s, size_t need_pts, bool need_grid) {
+  MapSlot& S = h->slot[s];
+  if (need_pts < 1) need_pts = 1;
+  if (S.cap < need_pts) {
+    LL_CUDA(h, cudaStreamSynchronize(h->stream));
+    void* ptrs[] = {S.raw, S.ds, S.sorted, S.keys[0], S.keys[1], S.vals[0], S.vals[1], S.scratch, S.member};
+    for (void* p : ptrs)
+      if (p) LL_CUDA(h, cudaFree(p));
+    size_t cap = need_pts + need_pts / 4 + 4096;
+    S.raw = S.ds = S.sorted = nullptr;
+    S.member = nullptr;
+    S.cap = 0;
+    auto A = [&](void** p, size_t bytes) -> int {
+      cudaError_t e = cudaMalloc(p, bytes);
+      if (e != cudaSuccess) return fail(h, LL_ERR_NOMEM, std::string("cudaMalloc(map slot): ") + cudaGetErrorString(e));
+      return LL_OK;
+    };
+    LL_TRY(A(reinterpret_cast<void**>(&S.raw), cap * 16));
+    LL_TRY(A(reinterpret_cast<void**>(&S.ds), cap * 16));
+    LL_TRY(A(reinterpret_cast<void**>(&S.sorted), cap * 16));
+    for (int k = 0; k < 2; ++k) {
+      LL_TRY(A(reinterpret_cast<void**>(&S.keys[k]), cap * 4));
+      LL_TRY(A(reinterpret_cast<void**>(&S.vals[k]), cap * 4));
+    }
+    LL_TRY(A(reinterpret_cast<void**>(&S.member), cap * 4));
+    S.max_tiles = (int)((cap + RS_TILE - 1) / RS_TILE) + 1;
+    S.max_head_tiles = (int)((cap + MB_TILE - 1) / MB_TILE) + 1;
+    S.scratch_bytes = 256 + sizeof(uint32_t) * (size_t)(RS_MAX_PASSES * RS_RADIX + 8 + S.max_head_tiles +
+                                                        (size_t)RS_MAX_PASSES * S.max_tiles * RS_RADIX);
+    LL_TRY(A(reinterpret_cast<void**>(&S.scratch), S.scratch_bytes));
+    S.cap = cap;
+  }
+  if (need_grid && !S.cells) {
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&S.cells), sizeof(int2) * (size_t)kCellCap);
+    if (e != cudaSuccess) return fail(h, LL_ERR_NOMEM, std::string("cudaMalloc(cell table): ") + cudaGetErrorString(e));
+  }
+  return LL_OK;
+}
+
+MapBuffers slot_buffers(const ll_handle h, int s, float leaf, int downsample, bool want_member) {
+  const MapSlot& S = h->slot[s];
+  MapBuffers M;
+  M.raw = S.raw;
+  M.ds = downsample ? S.ds : S.raw;
+  M.sorted = S.sorted;
+  M.cells = S.cells;
+  M.st = S.st();
+  M.head_status = S.head_status();
+  M.member = want_member ? S.member : nullptr;
+  M.n_raw = S.n_raw;
+  M.cell_cap = kCellCap;
+  M.inv_leaf = 1.0f / leaf;
+  M.downsample = downsample;
+  return M;
+}
+
+SortProblem slot_sort(const ll_handle h, int s, bool grid_phase) {
+  const MapSlot& S = h->slot[s];
+  SortProblem P;
+  P.keys[0] = S.keys[0]; P.keys[1] = S.keys[1];
+  P.vals[0] = S.vals[0]; P.vals[1] = S.vals[1];
+  P.n = grid_phase ? &S.st()->n_ds : &S.st()->n_raw;
+  P.bits = grid_phase ? &S.st()->grid_bits : &S.st()->voxel_bits;
+  P.ghist = S.ghist();
+  P.status = S.status();
+  P.tile_counter = S.tile_counter();
+  P.max_tiles = S.max_tiles;
+  return P;
+}
+
+// Segments + block jobs for transform_minmax_kernel, staged through pinned memory.
+struct SegList {
+  std::vector<Segment> segs;
+  std::vector<BlockJob> jobs;
+  void add(const float4* src, int count, int dst_off, int map, const float pose6[6]) {
+    if (count <= 0) return;
+    Segment s;
+    std::memset(&s, 0, sizeof(s));
+    s.src = src;
+    s.count = count;
+    s.dst_off = dst_off;
+    s.map = map;
+    if (pose6) {
+      // updateTransformPointCloudSinCos (mapOptmization.cpp:622-635): double trig rounded to float
+      s.t.cr = (float)std::cos((double)pose6[0]); s.t.sr = (float)std::sin((double)pose6[0]);
+      s.t.cp = (float)std::cos((double)pose6[1]); s.t.sp = (float)std::sin((double)pose6[1]);
+      s.t.cy = (float)std::cos((double)pose6[2]); s.t.sy = (float)std::sin((double)pose6[2]);
+      s.t.tx = pose6[3]; s.t.ty = pose6[4]; s.t.tz = pose6[5];
+      s.identity = 0;
+    } else {
+      s.identity = 1;
+    }
+    const int si = (int)segs.size();
+    segs.push_back(s);
+    for (int st = 0; st < count; st += MB_TILE) jobs.push_back(BlockJob{si, st});
+  }
+};
+
+int upload_seglist(ll_handle h, const SegList& L) {
+  const size_t sb = L.segs.size() * sizeof(Segment), jb = L.jobs.size() * sizeof(BlockJob);
+  if (sb == 0) return LL_OK;
+  LL_TRY(ensure_bytes(h, reinterpret_cast<void**>(&h->d_segs), &h->segs_cap, sb));
+  LL_TRY(ensure_bytes(h, reinterpret_cast<void**>(&h->d_jobs), &h->jobs_cap, jb));
+  LL_TRY(pinned_acquire(h, sb + jb));
+  std::memcpy(h->pinned, L.segs.data(), sb);
+  std::memcpy(h->pinned + sb, L.jobs.data(), jb);
+  LL_CUDA(h, cudaMemcpyAsync(h->d_segs, h->pinned, sb, cudaMemcpyHostToDevice, h->stream));
+  LL_CUDA(h, cudaMemcpyAsync(h->d_jobs, h->pinned + sb, jb, cudaMemcpyHostToDevice, h->stream));
+  return pinned_release(h);
+}
+
+// Run the map pipeline on slots (sa, sb) (sb < 0: single problem). The raw clouds are described by L.
+int run_map_pipeline(ll_handle h, int sa, int sb, const SegList& L, float leaf_a, float leaf_b, int ds_a, int ds_b,
+                     bool build_grid, bool want_member) {
+  const int ny = sb >= 0 ? 2 : 1;
+  MapBatch B;
+  std::memset(&B, 0, sizeof(B));
+  B.m[0] = slot_buffers(h, sa, leaf_a, ds_a, want_member);
+  B.sort[0] = slot_sort(h, sa, false);
+  if (sb >= 0) {
+    B.m[1] = slot_buffers(h, sb, leaf_b, ds_b, false);
+    B.sort[1] = slot_sort(h, sb, false);
+  } else {
+    B.m[1] = B.m[0];
+    B.m[1].n_raw = 0;
+    B.sort[1] = B.sort[0];
+  }
+  B.count = ny;
+  const int slots[2] = {sa, sb};
+  int maxn = 0;
+  for (int k = 0; k < ny; ++k) {
+    MapSlot& S = h->slot[slots[k]];
+    LL_CUDA(h, cudaMemsetAsync(S.scratch, 0, S.scratch_bytes, h->stream));
+    maxn = std::max(maxn, S.n_raw);
+  }
+  LL_TRY(upload_seglist(h, L));
+  if (!L.jobs.empty()) {
+    LL_PROF(h, 0);
+    transform_minmax_kernel<<<(unsigned)L.jobs.size(), MB_THREADS, 0, h->stream>>>(B, h->d_segs, h->d_jobs);
+    LL_LAUNCHED(h);
+  }
+  if (maxn == 0) return LL_OK;
+  const unsigned gx_pts = (unsigned)((maxn + MB_TILE - 1) / MB_TILE);
+  const unsigned gx_sort = (unsigned)((maxn + RS_TILE - 1) / RS_TILE);
+  if (ds_a || (sb >= 0 && ds_b)) {
+    LL_PROF(h, 1);
+    voxel_keys_kernel<<<dim3(gx_pts, ny), MB_THREADS, 0, h->stream>>>(B);
+    LL_LAUNCHED(h);
+    SortBatch SB;
+    SB.p[0] = B.sort[0];
+    SB.p[1] = B.sort[1];
+    for (int pass = 0; pass < RS_MAX_PASSES; ++pass) {
+      LL_PROF(h, 2);
+      rs_onesweep_kernel<<<dim3(gx_sort, ny), RS_THREADS, 0, h->stream>>>(SB, pass);
+      LL_LAUNCHED(h);
+    }
+    LL_PROF(h, 3);
+    voxel_reduce_kernel<<<dim3(gx_pts, ny), MB_THREADS, 0, h->stream>>>(B);
+    LL_LAUNCHED(h);
+  }
+  if (!build_grid) return LL_OK;
+  for (int k = 0; k < ny; ++k) {  // re-arm the sort scratch (everything behind MapState) for the cell sort
+    MapSlot& S = h->slot[slots[k]];
+    LL_CUDA(h, cudaMemsetAsync(S.scratch + 256, 0, S.scratch_bytes - 256, h->stream));
+  }
+  B.sort[0] = slot_sort(h, sa, true);
+  if (sb >= 0) B.sort[1] = slot_sort(h, sb, true);
+  const unsigned gx_grid = std::max(gx_pts, (unsigned)(2 * h->num_sms));
+  LL_PROF(h, 4);
+  grid_keys_kernel<<<dim3(gx_grid, ny), MB_THREADS, 0, h->stream>>>(B);
+  LL_LAUNCHED(h);
+  SortBatch SB;
+  SB.p[0] = B.sort[0];
+  SB.p[1] = B.sort[1];
+  for (int pass = 0; pass < kGridPasses; ++pass) {
+    LL_PROF(h, 5);
+    rs_onesweep_kernel<<<dim3(gx_sort, ny), RS_THREADS, 0, h->stream>>>(SB, pass);
+    LL_LAUNCHED(h);
+  }
+  LL_PROF(h, 6);
+  grid_finalize_kernel<<<dim3(gx_pts, ny), MB_THREADS, 0, h->stream>>>(B);
+  LL_LAUNCHED(h);
+  return LL_OK;
+}
+
+LMParams make_lm_params(const ll_params& p) {
+  LMParams q;
+  q.fit.max_sq_dist = p.max_sq_dist;
+  q.fit.eig_ratio = p.eig_ratio;
+  q.fit.plane_tol = p.plane_tol;
+  q.fit.weight_k = p.weight_k;
+  q.fit.min_weight = p.min_weight;
+  q.fit.eigen_mode = p.eigen_mode;
+  q.min_residuals = p.min_residuals;
+  q.eig_thresh = p.eig_thresh;
+  q.iter_count_thres = p.iter_count_thres;
+  q.step_size = p.step_size;
+  q.stop_thres = p.stop_thres;
+  q.apply_update = p.apply_update;
+  q.min_corner_map = p.min_corner_map;
+  q.min_surf_map = p.min_surf_map;
+  return q;
+}
+
+int validate_params(ll_handle h, const ll_params* p) {
+  if (!p) return fail(h, LL_ERR_INVALID_ARG, "params is NULL");
+  if (!(p->corner_leaf > 0.f) || !(p->surf_leaf > 0.f)) return fail(h, LL_ERR_INVALID_ARG, "leaf sizes must be > 0");
+  if (!(p->max_sq_dist > 0.f) || p->max_sq_dist > 1.0f)
+    return fail(h, LL_ERR_INVALID_ARG, "max_sq_dist must be in (0, 1]: the 1 m search grid is exact only up to 1 m");
+  if (p->eigen_mode != 0 && p->eigen_mode != 1) return fail(h, LL_ERR_INVALID_ARG, "eigen_mode must be 0 or 1");
+  return LL_OK;
+}
+
+LMArgs make_lm_args(ll_handle h, int mode) {
+  LMArgs A;
+  std::memset(&A, 0, sizeof(A));
+  for (int m = 0; m < 2; ++m) {
+    A.sorted[m] = h->slot[m].sorted;
+    A.cells[m] = h->slot[m].cells;
+    A.mst[m] = h->slot[m].st();
+    A.q[m] = h->q_ptr[m];
+    A.nq[m] = h->nq[m];
+  }
+  A.prm = make_lm_params(h->prm);
+  A.st = h->d_state;
+  A.partials = h->d_partials;
+  A.mode = mode;
+  return A;
+}
+
+int lm_grid_blocks(ll_handle h, int nq) {
+  int blocks = (nq + LM_WARPS - 1) / LM_WARPS;
+  const int cap = h->num_sms * 4;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return blocks;
+}
+
+int ensure_partials(ll_handle h, int blocks) {
+  if (h->partial_blocks >= blocks) return LL_OK;
+  LL_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (h->d_partials) LL_CUDA(h, cudaFree(h->d_partials));
+  h->d_partials = nullptr;
+  const int cap = std::max(blocks, h->num_sms * 4);
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&h->d_partials), sizeof(float) * 32 * (size_t)cap);
+  if (e != cudaSuccess) return fail(h, LL_ERR_NOMEM, std::string("cudaMalloc(partials): ") + cudaGetErrorString(e));
+  h->partial_blocks = cap;
+  return LL_OK;
+}
+
+int set_queries_host(ll_handle h, int m, const void* pts, size_t n, size_t stride) {
+  size_t bytes = std::max<size_t>(n, 1) * sizeof(float4);
+  LL_TRY(ensure_bytes(h, reinterpret_cast<void**>(&h->dq[m]), &h->dq_cap[m], bytes));
+  LL_TRY(upload_points(h, h->dq[m], pts, n, stride));
+  h->q_ptr[m] = h->dq[m];
+  h->nq[m] = (int)n;
+  return LL_OK;
+}
+
+int enqueue_iterations(ll_handle h, int count) {
+  LMArgs A = make_lm_args(h, 0);
+  for (int i = 0; i < count; ++i) {
+    LL_PROF(h, 8);
+    lm_iter_kernel<<<h->lm_blocks, LM_THREADS, 0, h->stream>>>(A);
+    LL_LAUNCHED(h);
+  }
+  h->iters_enqueued += count;
+  LL_CUDA(h, cudaMemcpyAsync(h->h_state, h->d_state, sizeof(LMState), cudaMemcpyDeviceToHost, h->stream));
+  return LL_OK;
+}
+
+int scan2map_enqueue(ll_handle h, const float pose6[6]) {
+  if (!h->map_ready) return fail(h, LL_ERR_STATE, "scan2map called before ll_build_local_map / ll_set_local_map_raw");
+  if (!pose6) return fail(h, LL_ERR_INVALID_ARG, "pose6 is NULL");
+  const int nq = h->nq[0] + h->nq[1];
+  h->lm_blocks = lm_grid_blocks(h, nq);
+  LL_TRY(ensure_partials(h, h->lm_blocks));
+  LL_PROF(h, 7);
+  lm_begin_kernel<<<1, 32, 0, h->stream>>>(h->d_state, h->slot[0].st(), h->slot[1].st(), make_lm_params(h->prm),
+                                           pose6[0], pose6[1], pose6[2], pose6[3], pose6[4], pose6[5]);
+  LL_LAUNCHED(h);
+  h->iters_enqueued = 0;
+  const int first = std::min(std::max(h->prm.iter_count_thres, 0), kFirstChunk);
+  LL_TRY(enqueue_iterations(h, first));
+  h->scan_pending = true;
+  return LL_OK;
+}
+
+void fill_result(const LMState& s, ll_result* r) {
+  r->status = s.status;
+  r->iter_num = s.iter_num;
+  r->min_lambda = s.min_lambda;
+  r->cf_mean = s.cf_mean;
+  r->is_degenerate = s.is_degenerate;
+  r->converged = s.converged;
+  r->sel_num = s.sel_num;
+  r->flags = s.flags;
+  r->corner_map_ds = s.corner_map_ds;
+  r->surf_map_ds = s.surf_map_ds;
+  std::memcpy(r->pose, s.pose, sizeof(r->pose));
+  std::memcpy(r->last_x, s.last_x, sizeof(r->last_x));
+}
+
+int scan2map_collect(ll_handle h, float pose6_out[6], ll_result* res) {
+  if (!h->scan_pending) return fail(h, LL_ERR_STATE, "no scan2map in flight");
+  while (true) {
+    LL_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (h->h_state->done || h->iters_enqueued >= h->prm.iter_count_thres) break;
+    const int more = std::min(h->prm.iter_count_thres - h->iters_enqueued, kNextChunk);
+    LL_TRY(enqueue_iterations(h, more));
+  }
+  h->scan_pending = false;
+  if (pose6_out) std::memcpy(pose6_out, h->h_state->pose, 6 * sizeof(float));
+  if (res) fill_result(*h->h_state, res);
+  return LL_OK;
+}
+
+int ensure_tmp(ll_handle h, int k, size_t bytes) {
+  return ensure_bytes(h, &h->d_tmp[k], &h->tmp_bytes[k], std::max<size_t>(bytes, 16));
+}
+
+// Shared body of ll_corner_residuals / ll_surf_residuals / ll_knn5.
+int emit_queries(ll_handle h, int which, int mode, const void* queries, size_t nq, size_t stride, const float pose6[6],
+                 float* coeff4, int* mask, int* accept, int* idx5, float* d2_5) {
+  if (!h) return LL_ERR_INVALID_ARG;
+  if (!h->map_ready) return fail(h, LL_ERR_STATE, "no local map: call ll_build_local_map / ll_set_local_map_raw first");
+  if (which != 0 && which != 1) return fail(h, LL_ERR_INVALID_ARG, "which must be 0 (corner) or 1 (surf)");
+  if (nq && (!queries || !stride_ok(stride))) return fail(h, LL_ERR_INVALID_ARG, "bad query cloud / stride");
+  if (nq == 0) return LL_OK;
+  LL_TRY(set_queries_host(h, which, queries, nq, stride));
+  h->nq[1 - which] = 0;
+  h->q_ptr[1 - which] = h->dq[which];
+  LL_TRY(ensure_tmp(h, 0, nq * 16));
+  LL_TRY(ensure_tmp(h, 1, nq * 4));
+  LL_TRY(ensure_tmp(h, 2, nq * 4));
+  LL_TRY(ensure_tmp(h, 3, nq * 20));
+  LL_TRY(ensure_tmp(h, 4, nq * 20));
+  const float ident[6] = {0, 0, 0, 0, 0, 0};
+  const float* ps = pose6 ? pose6 : ident;
+  lm_begin_kernel<<<1, 32, 0, h->stream>>>(h->d_state, h->slot[0].st(), h->slot[1].st(), make_lm_params(h->prm), ps[0],
+                                           ps[1], ps[2], ps[3], ps[4], ps[5]);
+  LL_LAUNCHED(h);
+  LMArgs A = make_lm_args(h, mode);
+  A.e_coeff = static_cast<float*>(h->d_tmp[0]);
+  A.e_mask = static_cast<int*>(h->d_tmp[1]);
+  A.e_accept = static_cast<int*>(h->d_tmp[2]);
+  A.e_idx = static_cast<int*>(h->d_tmp[3]);
+  A.e_d2 = static_cast<float*>(h->d_tmp[4]);
+  const int blocks = lm_grid_blocks(h, (int)nq);
+  lm_iter_kernel<<<blocks, LM_THREADS, 0, h->stream>>>(A);
+  LL_LAUNCHED(h);
+  if (coeff4) LL_CUDA(h, cudaMemcpyAsync(coeff4, h->d_tmp[0], nq * 16, cudaMemcpyDeviceToHost, h->stream));
+  if (mask) LL_CUDA(h, cudaMemcpyAsync(mask, h->d_tmp[1], nq * 4, cudaMemcpyDeviceToHost, h->stream));
+  if (accept) LL_CUDA(h, cudaMemcpyAsync(accept, h->d_tmp[2], nq * 4, cudaMemcpyDeviceToHost, h->stream));
+  if (idx5) LL_CUDA(h, cudaMemcpyAsync(idx5, h->d_tmp[3], nq * 20, cudaMemcpyDeviceToHost, h->stream));
+  if (d2_5) LL_CUDA(h, cudaMemcpyAsync(d2_5, h->d_tmp[4], nq * 20, cudaMemcpyDeviceToHost, h->stream));
+  LL_CUDA(h, cudaStreamSynchronize(h->stream));
+  return LL_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ll_default_params(ll_params* p) {
+  if (!p) return LL_ERR_INVALID_ARG;
+  p->corner_leaf = 0.2f;
+  p->surf_leaf = 0.4f;
+  p->max_sq_dist = 1.0f;
+  p->eig_ratio = 3.0f;
+  p->plane_tol = 0.2;
+  p->weight_k = 0.9;
+  p->min_weight = 0.1;
+  p->min_residuals = 50;
+  p->eig_thresh = 100.0f;
+  p->iter_count_thres = 200;
+  p->step_size = 1.0f;
+  p->stop_thres = 0.05f;
+  p->apply_update = 0;
+  p->eigen_mode = 0;
+  p->map_downsample = 1;
+  p->min_corner_map = 10;
+  p->min_surf_map = 100;
+  return LL_OK;
+}
+
+int ll_create(const ll_params* p, int device_id, ll_handle* out) {
+  if (!out) return LL_ERR_INVALID_ARG;
+  *out = nullptr;
+  ll_params def;
+  ll_default_params(&def);
+  const ll_params* use = p ? p : &def;
+  if (validate_params(nullptr, use) != LL_OK) return LL_ERR_INVALID_ARG;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device_id < 0 || device_id >= ndev) return LL_ERR_CUDA;
+  if (cudaSetDevice(device_id) != cudaSuccess) return LL_ERR_CUDA;
+  ll_handle h = new (std::nothrow) ll_handle_s();
+  if (!h) return LL_ERR_NOMEM;
+  h->prm = *use;
+  h->device = device_id;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device_id) == cudaSuccess) h->num_sms = prop.multiProcessorCount;
+  bool ok = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaEventCreateWithFlags(&h->pinned_evt, cudaEventDisableTiming) == cudaSuccess &&
+            cudaMalloc(reinterpret_cast<void**>(&h->d_state), sizeof(LMState)) == cudaSuccess &&
+            cudaMallocHost(reinterpret_cast<void**>(&h->h_state), sizeof(LMState)) == cudaSuccess &&
+            cudaMemsetAsync(h->d_state, 0, sizeof(LMState), h->stream) == cudaSuccess &&
+            cudaStreamSynchronize(h->stream) == cudaSuccess;
+  if (!ok) {
+    ll_destroy(h);
+    return LL_ERR_CUDA;
+  }
+  std::memset(h->h_state, 0, sizeof(LMState));
+  *out = h;
+  return LL_OK;
+}
+
+int ll_destroy(ll_handle h) {
+  if (!h) return LL_OK;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  for (void* p : h->arena) cudaFree(p);
+  for (MapSlot& S : h->slot) {
+    void* ptrs[] = {S.raw, S.ds, S.sorted, S.keys[0], S.keys[1], S.vals[0], S.vals[1], S.scratch, S.member, S.cells};
+    for (void* p : ptrs)
+      if (p) cudaFree(p);
+  }
+  void* ptrs[] = {h->d_segs, h->d_jobs, h->dq[0], h->dq[1], h->d_state, h->d_partials,
+                  h->d_tmp[0], h->d_tmp[1], h->d_tmp[2], h->d_tmp[3], h->d_tmp[4], h->d_tmp[5]};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  if (h->pinned) cudaFreeHost(h->pinned);
+  if (h->h_state) cudaFreeHost(h->h_state);
+  if (h->pinned_evt) cudaEventDestroy(h->pinned_evt);
+  for (cudaEvent_t e : h->prof_pool) cudaEventDestroy(e);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return LL_OK;
+}
+
+int ll_set_params(ll_handle h, const ll_params* p) {
+  if (!h) return LL_ERR_INVALID_ARG;
+  LL_TRY(validate_params(h, p));
+  h->prm = *p;
+  return LL_OK;
+}
+
+const char* ll_last_error_string(ll_handle h) { return h ? h->err.c_str() : "invalid handle"; }
+
+int ll_get_stream(ll_handle h, void** stream) {
+  if (!h || !stream) return LL_ERR_INVALID_ARG;
+  *stream = reinterpret_cast<void*>(h->stream);
+  return LL_OK;
+}
+
+int ll_get_launch_count(ll_handle h, uint64_t* n) {
+  if (!h || !n) return LL_ERR_INVALID_ARG;
+  *n = h->launches;
+  return LL_OK;
+}
+
+static int add_keyframe_impl(ll_handle h, int id, const void* c[3], const size_t n[3], size_t stride, bool dev,
+                             const float pose6[6]) {
+  if (!h) return LL_ERR_INVALID_ARG;
+  if (!pose6) return fail(h, LL_ERR_INVALID_ARG, "pose6 is NULL");
+  if (!dev && !stride_ok(stride)) return fail(h, LL_ERR_INVALID_ARG, "stride_bytes must be 16 or >= 20 and a multiple of 4");
+  for (int k = 0; k < 3; ++k)
+    if (n[k] && !c[k]) return fail(h, LL_ERR_INVALID_ARG, "NULL cloud with non-zero count");
+  LL_CUDA(h, cudaSetDevice(h->device));
+  Keyframe kf;
+  std::memcpy(kf.pose, pose6, sizeof(kf.pose));
+  for (int k = 0; k < 3; ++k) {
+    kf.n[k] = (int)n[k];
+    void* p = nullptr;
+    LL_TRY(arena_alloc(h, n[k] * sizeof(float4), &p));
+    kf.d[k] = static_cast<float4*>(p);
+    if (n[k] == 0) continue;
+    if (dev) {
+      LL_CUDA(h, cudaMemcpyAsync(kf.d[k], c[k], n[k] * sizeof(float4), cudaMemcpyDeviceToDevice, h->stream));
+    } else {
+      LL_TRY(upload_points(h, kf.d[k], c[k], n[k], stride));
+    }
+  }
+  h->kfs[id] = kf;  // re-adding an id replaces the entry (the old slab space is not reclaimed)
+  return LL_OK;
+}
+
+int ll_add_keyframe(ll_handle h, int id, const void* corner, size_t n_corner, const void* surf, size_t n_surf,
+                    const void* outlier, size_t n_outlier, size_t stride_bytes, const float pose6[6]) {
+  const void* c[3] = {corner, surf, outlier};
+  const size_t n[3] = {n_corner, n_surf, n_outlier};
+  return add_keyframe_impl(h, id, c, n, stride_bytes, false, pose6);
+}
+
+int ll_add_keyframe_dev(ll_handle h, int id, const void* d_corner, size_t n_corner, const void* d_surf, size_t n_surf,
+                        const void* d_outlier, size_t n_outlier, const float pose6[6]) {
+  const void* c[3] = {d_corner, d_surf, d_outlier};
+  const size_t n[3] = {n_corner, n_surf, n_outlier};
+  return add_keyframe_impl(h, id, c, n, 16, true, pose6);
+}
+
+int ll_set_keyframe_pose(ll_handle h, int id, const float pose6[6]) {
+  if (!h || !pose6) return LL_ERR_INVALID_ARG;
+  auto it = h->kfs.find(id);
+  if (it == h->kfs.end()) return fail(h, LL_ERR_NOT_FOUND, "unknown keyframe id " + std::to_string(id));
+  std::memcpy(it->second.pose, pose6, 6 * sizeof(float));
+  return LL_OK;
+}
+
+int ll_build_local_map(ll_handle h, const int* ids, int n_ids) {
+  if (!h || n_ids < 0 || (n_ids && !ids)) return LL_ERR_INVALID_ARG;
+  if (h->scan_pending) return fail(h, LL_ERR_STATE, "a scan2map is still in flight: call ll_scan2map_wait first");
+  LL_CUDA(h, cudaSetDevice(h->device));
+  size_t nc = 0, ns = 0;
+  for (int i = 0; i < n_ids; ++i) {
+    auto it = h->kfs.find(ids[i]);
+    if (it == h->kfs.end()) return fail(h, LL_ERR_NOT_FOUND, "unknown keyframe id " + std::to_string(ids[i]));
+    nc += it->second.n[0];
+    ns += (size_t)it->second.n[1] + it->second.n[2];
+  }
+  if (nc > 0x3fffffff || ns > 0x3fffffff) return fail(h, LL_ERR_INVALID_ARG, "surrounding cloud too large");
+  LL_TRY(ensure_slot(h, 0, nc, true));
+  LL_TRY(ensure_slot(h, 1, ns, true));
+  SegList L;
+  int oc = 0, os = 0;
+  for (int i = 0; i < n_ids; ++i) {  // cache order = ids order; per keyframe corner | surf, outlier (:1147-1151)
+    const Keyframe& kf = h->kfs[ids[i]];
+    L.add(kf.d[0], kf.n[0], oc, 0, kf.pose); oc += kf.n[0];
+    L.add(kf.d[1], kf.n[1], os, 1, kf.pose); os += kf.n[1];
+    L.add(kf.d[2], kf.n[2], os, 1, kf.pose); os += kf.n[2];
+  }
+  h->slot[0].n_raw = (int)nc;
+  h->slot[1].n_raw = (int)ns;
+  const int ds = h->prm.map_downsample ? 1 : 0;
+  LL_TRY(run_map_pipeline(h, 0, 1, L, h->prm.corner_leaf, h->prm.surf_leaf, ds, ds, true, false));
+  h->map_ready = true;
+  return LL_OK;
+}
+
+int ll_set_local_map_raw(ll_handle h, const void* corner, size_t n_corner, const void* surf, size_t n_surf,
+                         size_t stride_bytes) {
+  if (!h) return LL_ERR_INVALID_ARG;
+  if (!stride_ok(stride_bytes) || (n_corner && !corner) || (n_surf && !surf))
+    return fail(h, LL_ERR_INVALID_ARG, "bad cloud / stride");
+  if (h->scan_pending) return fail(h, LL_ERR_STATE, "a scan2map is still in flight: call ll_scan2map_wait first");
+  LL_CUDA(h, cudaSetDevice(h->device));
+  LL_TRY(ensure_slot(h, 0, n_corner, true));
+  LL_TRY(ensure_slot(h, 1, n_surf, true));
+  // stage the two clouds in the `sorted` buffers (free until grid_finalize), then run the pipeline with
+  // identity segments
+  LL_TRY(upload_points(h, h->slot[0].sorted, corner, n_corner, stride_bytes));
+  LL_TRY(upload_points(h, h->slot[1].sorted, surf, n_surf, stride_bytes));
+  SegList L;
+  L.add(h->slot[0].sorted, (int)n_corner, 0, 0, nullptr);
+  L.add(h->slot[1].sorted, (int)n_surf, 0, 1, nullptr);
+  h->slot[0].n_raw = (int)n_corner;
+  h->slot[1].n_raw = (int)n_surf;
+  const int ds = h->prm.map_downsample ? 1 : 0;
+  LL_TRY(run_map_pipeline(h, 0, 1, L, h->prm.corner_leaf, h->prm.surf_leaf, ds, ds, true, false));
+  h->map_ready = true;
+  return LL_OK;
+}
+
+int ll_get_map_ds(ll_handle h, int which, void* out, size_t cap_points, size_t stride_bytes, size_t* n) {
+  if (!h || !n || (which != 0 && which != 1)) return LL_ERR_INVALID_ARG;
+  if (!h->map_ready) return fail(h, LL_ERR_STATE, "no local map");
+  if (!stride_ok(stride_bytes)) return fail(h, LL_ERR_INVALID_ARG, "bad stride");
+  LL_CUDA(h, cudaSetDevice(h->device));
+  MapSlot& S = h->slot[which];
+  MapState st;
+  LL_CUDA(h, cudaMemcpyAsync(&st, S.st(), sizeof(st), cudaMemcpyDeviceToHost, h->stream));
+  LL_CUDA(h, cudaStreamSynchronize(h->stream));
+  *n = (size_t)st.n_ds;
+  if (!out) return LL_OK;
+  if (cap_points < (size_t)st.n_ds) return fail(h, LL_ERR_CAPACITY, "output buffer too small for the downsampled map");
+  if (st.n_ds == 0) return LL_OK;
+  const float4* src = h->prm.map_downsample ? S.ds : S.raw;
+  std::vector<float4> tmp((size_t)st.n_ds);
+  LL_CUDA(h, cudaMemcpyAsync(tmp.data(), src, tmp.size() * 16, cudaMemcpyDeviceToHost, h->stream));
+  LL_CUDA(h, cudaStreamSynchronize(h->stream));
+  unpack_points(out, tmp.data(), tmp.size(), stride_bytes);
+  return LL_OK;
+}
+
+int ll_scan2map_async(ll_handle h, const void* corner_scan_ds, size_t n_corner, const void* surf_total_ds,
+                      size_t n_surf, size_t stride_bytes, const float pose6_in[6]) {
+  if (!h) return LL_ERR_INVALID_ARG;
+  if (!stride_ok(stride_bytes) || (n_corner && !corner_scan_ds) || (n_surf && !surf_total_ds))
+    return fail(h, LL_ERR_INVALID_ARG, "bad query cloud / stride");
+  if (h->scan_pending) return fail(h, LL_ERR_STATE, "a scan2map is already in flight");
+  LL_CUDA(h, cudaSetDevice(h->device));
+  // one staging pass for both query clouds
+  const size_t nt = n_corner + n_surf;
+  LL_TRY(ensure_bytes(h, reinterpret_cast<void**>(&h->dq[0]), &h->dq_cap[0], std::max<size_t>(nt, 1) * sizeof(float4)));
+  if (nt) {
+    LL_TRY(pinned_acquire(h, nt * sizeof(float4)));
+    float4* st = reinterpret_cast<float4*>(h->pinned);
+    pack_points(st, corner_scan_ds, n_corner, stride_bytes);
+    pack_points(st + n_corner, surf_total_ds, n_surf, stride_bytes);
+    LL_CUDA(h, cudaMemcpyAsync(h->dq[0], st, nt * sizeof(float4), cudaMemcpyHostToDevice, h->stream));
+    LL_TRY(pinned_release(h));
+  }
+  h->q_ptr[0] = h->dq[0];
+  h->q_ptr[1] = h->dq[0] + n_corner;
+  h->nq[0] = (int)n_corner;
+  h->nq[1] = (int)n_surf;
+  return scan2map_enqueue(h, pose6_in);
+}
+
+int ll_scan2map_dev_async(ll_handle h, const void* d_corner_scan_ds, size_t n_corner, const void* d_surf_total_ds,
+                          size_t n_surf, const float pose6_in[6]) {
+  if (!h) return LL_ERR_INVALID_ARG;
+  if ((n_corner && !d_corner_scan_ds) || (n_surf && !d_surf_total_ds)) return fail(h, LL_ERR_INVALID_ARG, "NULL query cloud");
+  if (h->scan_pending) return fail(h, LL_ERR_STATE, "a scan2map is already in flight");
+  LL_CUDA(h, cudaSetDevice(h->device));
+  h->q_ptr[0] = static_cast<const float4*>(d_corner_scan_ds);
+  h->q_ptr[1] = static_cast<const float4*>(d_surf_total_ds);
+  if (!h->q_ptr[0]) h->q_ptr[0] = h->q_ptr[1];
+  if (!h->q_ptr[1]) h->q_ptr[1] = h->q_ptr[0];
+  h->nq[0] = (int)n_corner;
+  h->nq[1] = (int)n_surf;
+  return scan2map_enqueue(h, pose6_in);
+}
+
+int ll_scan2map_wait(ll_handle h, float pose6_out[6], ll_result* res) {
+  if (!h) return LL_ERR_INVALID_ARG;
+  LL_CUDA(h, cudaSetDevice(h->device));
+  return scan2map_collect(h, pose6_out, res);
+}
+
+int ll_scan2map(ll_handle h, const void* corner_scan_ds, size_t n_corner, const void* surf_total_ds, size_t n_surf,
+                size_t stride_bytes, float pose6_inout[6], ll_result* res) {
+  LL_TRY(ll_scan2map_async(h, corner_scan_ds, n_corner, surf_total_ds, n_surf, stride_bytes, pose6_inout));
+  return scan2map_collect(h, pose6_inout, res);
+}
+
+int ll_scan2map_dev(ll_handle h, const void* d_corner_scan_ds, size_t n_corner, const void* d_surf_total_ds,
+                    size_t n_surf, float pose6_inout[6], ll_result* res) {
+  LL_TRY(ll_scan2map_dev_async(h, d_corner_scan_ds, n_corner, d_surf_total_ds, n_surf, pose6_inout));
+  return scan2map_collect(h, pose6_inout, res);
+}
+
+int ll_voxel_downsample(ll_handle h, const void* in, size_t n, size_t stride_bytes, float leaf, void* out,
+                        size_t cap_points, size_t out_stride_bytes, size_t* n_out, int* member, int* flags) {
+  if (!h || !n_out) return LL_ERR_INVALID_ARG;
+  if (!stride_ok(stride_bytes) || !stride_ok(out_stride_bytes) || (n && !in) || !(leaf > 0.f))
+    return fail(h, LL_ERR_INVALID_ARG, "bad cloud / stride / leaf");
+  if (n > 0x3fffffff) return fail(h, LL_ERR_INVALID_ARG, "cloud too large");
+  LL_CUDA(h, cudaSetDevice(h->device));
+  *n_out = 0;
+  if (flags) *flags = 0;
+  if (n == 0) return LL_OK;
+  LL_TRY(ensure_slot(h, 2, n, false));
+  MapSlot& S = h->slot[2];
+  LL_TRY(upload_points(h, S.sorted, in, n, stride_bytes));
+  if (member) LL_CUDA(h, cudaMemsetAsync(S.member, 0xff, n * sizeof(int), h->stream));
+  SegList L;
+  L.add(S.sorted, (int)n, 0, 0, nullptr);
+  S.n_raw = (int)n;
+  LL_TRY(run_map_pipeline(h, 2, -1, L, leaf, leaf, 1, 1, false, member != nullptr));
+  MapState st;
+  LL_CUDA(h, cudaMemcpyAsync(&st, S.st(), sizeof(st), cudaMemcpyDeviceToHost, h->stream));
+  LL_CUDA(h, cudaStreamSynchronize(h->stream));
+  *n_out = (size_t)st.n_ds;
+  if (flags) *flags = st.voxel_overflow ? 1 : 0;
+  if (member) {
+    LL_CUDA(h, cudaMemcpyAsync(member, S.member, n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    LL_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
+  if (!out) return LL_OK;
+  if (cap_points < (size_t)st.n_ds) return fail(h, LL_ERR_CAPACITY, "output buffer too small");
+  std::vector<float4> tmp((size_t)st.n_ds);
+  if (!tmp.empty()) {
+    LL_CUDA(h, cudaMemcpyAsync(tmp.data(), S.ds, tmp.size() * 16, cudaMemcpyDeviceToHost, h->stream));
+    LL_CUDA(h, cudaStreamSynchronize(h->stream));
+    unpack_points(out, tmp.data(), tmp.size(), out_stride_bytes);
+  }
+  return LL_OK;
+}
+
+int ll_knn5(ll_handle h, int which, const void* queries, size_t nq, size_t stride_bytes, int* idx5, float* d2_5,
+            int* accept) {
+  if (!h) return LL_ERR_INVALID_ARG;
+  LL_CUDA(h, cudaSetDevice(h->device));
+  return emit_queries(h, which, 2, queries, nq, stride_bytes, nullptr, nullptr, nullptr, accept, idx5, d2_5);
+}
+
+int ll_corner_residuals(ll_handle h, const void* queries, size_t nq, size_t stride_bytes, const float pose6[6],
+                        float* coeff4, int* mask, int* accept, int* knn_idx5, float* knn_d2_5) {
+  if (!h || !pose6) return LL_ERR_INVALID_ARG;
+  LL_CUDA(h, cudaSetDevice(h->device));
+  return emit_queries(h, 0, 1, queries, nq, stride_bytes, pose6, coeff4, mask, accept, knn_idx5, knn_d2_5);
+}
+
+int ll_surf_residuals(ll_handle h, const void* queries, size_t nq, size_t stride_bytes, const float pose6[6],
+                      float* coeff4, int* mask, int* accept, int* knn_idx5, float* knn_d2_5) {
+  if (!h || !pose6) return LL_ERR_INVALID_ARG;
+  LL_CUDA(h, cudaSetDevice(h->device));
+  return emit_queries(h, 1, 1, queries, nq, stride_bytes, pose6, coeff4, mask, accept, knn_idx5, knn_d2_5);
+}
+
+// Set pose / iteration index for the stage-level a9 entry (one thread).
+__global__ void lm_stage_setup_kernel(LMState* S, int iter, float p0, float p1, float p2, float p3, float p4, float p5) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  S->pose[0] = p0; S->pose[1] = p1; S->pose[2] = p2; S->pose[3] = p3; S->pose[4] = p4; S->pose[5] = p5;
+  set_trig(S);
+  S->iter = iter;
+  S->ticket = 0;
+  S->lm_ret = 0;
+}
+
+int ll_lm_step(ll_handle h, const void* ori, const float* coeff4, size_t n, size_t stride_bytes, int iter,
+               float pose6_inout[6], float* AtA36, float* Atb6, float* x6, float* deltaR, float* deltaT, int* ret) {
+  if (!h || !pose6_inout) return LL_ERR_INVALID_ARG;
+  if (!stride_ok(stride_bytes) || (n && (!ori || !coeff4))) return fail(h, LL_ERR_INVALID_ARG, "bad records / stride");
+  LL_CUDA(h, cudaSetDevice(h->device));
+  LL_TRY(ensure_tmp(h, 0, n * 16));
+  LL_TRY(ensure_tmp(h, 5, n * 16));
+  LL_TRY(upload_points(h, static_cast<float4*>(h->d_tmp[5]), ori, n, stride_bytes));
+  if (n) LL_CUDA(h, cudaMemcpyAsync(h->d_tmp[0], coeff4, n * 16, cudaMemcpyHostToDevice, h->stream));
+  int blocks = (int)((n + LM_THREADS - 1) / LM_THREADS);
+  blocks = std::max(1, std::min(blocks, h->num_sms * 2));
+  LL_TRY(ensure_partials(h, blocks));
+  lm_stage_setup_kernel<<<1, 32, 0, h->stream>>>(h->d_state, iter, pose6_inout[0], pose6_inout[1], pose6_inout[2],
+                                                 pose6_inout[3], pose6_inout[4], pose6_inout[5]);
+  LL_LAUNCHED(h);
+  lm_rows_kernel<<<blocks, LM_THREADS, 0, h->stream>>>(static_cast<const float4*>(h->d_tmp[5]),
+                                                       static_cast<const float4*>(h->d_tmp[0]), (int)n,
+                                                       make_lm_params(h->prm), h->d_state, h->d_partials);
+  LL_LAUNCHED(h);
+  LL_CUDA(h, cudaMemcpyAsync(h->h_state, h->d_state, sizeof(LMState), cudaMemcpyDeviceToHost, h->stream));
+  LL_CUDA(h, cudaStreamSynchronize(h->stream));
+  const LMState& s = *h->h_state;
+  std::memcpy(pose6_inout, s.pose, 6 * sizeof(float));
+  if (AtA36) std::memcpy(AtA36, s.AtA, sizeof(s.AtA));
+  if (Atb6) std::memcpy(Atb6, s.Atb, sizeof(s.Atb));
+  if (x6) std::memcpy(x6, s.last_x, sizeof(s.last_x));
+  if (deltaR) *deltaR = s.deltaR;
+  if (deltaT) *deltaT = s.deltaT;
+  if (ret) *ret = s.lm_ret;
+  return LL_OK;
+}
+
+int ll_get_degeneracy(ll_handle h, int* is_degenerate, float* matP36) {
+  if (!h) return LL_ERR_INVALID_ARG;
+  LL_CUDA(h, cudaSetDevice(h->device));
+  LL_CUDA(h, cudaMemcpyAsync(h->h_state, h->d_state, sizeof(LMState), cudaMemcpyDeviceToHost, h->stream));
+  LL_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (is_degenerate) *is_degenerate = h->h_state->is_degenerate;
+  if (matP36) std::memcpy(matP36, h->h_state->matP, sizeof(h->h_state->matP));
+  return LL_OK;
+}
+
+int ll_solve_normal_eq(ll_handle h, const float* rows6, const float* b, size_t n, int dof_mask, int iter,
+                       float eig_thresh, float* x_out, float* matP_inout, int* is_degenerate_inout) {
+  if (!h) return LL_ERR_INVALID_ARG;
+  int m = 0;
+  for (int k = 0; k < 6; ++k) m += (dof_mask >> k) & 1;
+  if (m == 0 || (dof_mask & ~63) || !x_out || !matP_inout || !is_degenerate_inout || (n && (!rows6 || !b)))
+    return fail(h, LL_ERR_INVALID_ARG, "bad dof_mask / NULL argument");
+  LL_CUDA(h, cudaSetDevice(h->device));
+  LL_TRY(ensure_tmp(h, 0, n * 24));
+  LL_TRY(ensure_tmp(h, 1, n * 4));
+  LL_TRY(ensure_tmp(h, 2, 256));
+  uint8_t* small = static_cast<uint8_t*>(h->d_tmp[2]);
+  float* d_x = reinterpret_cast<float*>(small);
+  float* d_P = reinterpret_cast<float*>(small + 32);
+  int* d_deg = reinterpret_cast<int*>(small + 32 + 144);
+  if (n) {
+    LL_CUDA(h, cudaMemcpyAsync(h->d_tmp[0], rows6, n * 24, cudaMemcpyHostToDevice, h->stream));
+    LL_CUDA(h, cudaMemcpyAsync(h->d_tmp[1], b, n * 4, cudaMemcpyHostToDevice, h->stream));
+  }
+  LL_CUDA(h, cudaMemcpyAsync(d_P, matP_inout, sizeof(float) * m * m, cudaMemcpyHostToDevice, h->stream));
+  LL_CUDA(h, cudaMemcpyAsync(d_deg, is_degenerate_inout, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  normal_eq_kernel<<<1, LM_THREADS, 0, h->stream>>>(static_cast<const float*>(h->d_tmp[0]),
+                                                    static_cast<const float*>(h->d_tmp[1]), (int)n, dof_mask, iter,
+                                                    eig_thresh, h->prm.eigen_mode, d_x, d_P, d_deg);
+  LL_LAUNCHED(h);
+  LL_CUDA(h, cudaMemcpyAsync(x_out, d_x, sizeof(float) * m, cudaMemcpyDeviceToHost, h->stream));
+  LL_CUDA(h, cudaMemcpyAsync(matP_inout, d_P, sizeof(float) * m * m, cudaMemcpyDeviceToHost, h->stream));
+  LL_CUDA(h, cudaMemcpyAsync(is_degenerate_inout, d_deg, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  LL_CUDA(h, cudaStreamSynchronize(h->stream));
+  return LL_OK;
+}
+
+int ll_profile_enable(ll_handle h, int on) {
+  if (!h) return LL_ERR_INVALID_ARG;
+  h->prof_on = on != 0;
+  return LL_OK;
+}
+
+int ll_profile_read(ll_handle h, double* ms_per_class, uint64_t* launches_per_class, int n_classes) {
+  if (!h || !ms_per_class || !launches_per_class || n_classes <= 0) return LL_ERR_INVALID_ARG;
+  LL_CUDA(h, cudaSetDevice(h->device));
+  LL_CUDA(h, cudaStreamSynchronize(h->stream));
+  for (int i = 0; i < n_classes; ++i) { ms_per_class[i] = 0.0; launches_per_class[i] = 0; }
+  for (const auto& r : h->prof_recs) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) != cudaSuccess) continue;
+    if (r.cls >= 0 && r.cls < n_classes) { ms_per_class[r.cls] += ms; launches_per_class[r.cls]++; }
+  }
+  h->prof_recs.clear();
+  h->prof_used = 0;
+  return LL_OK;
+}
+
+int ll_reset_state(ll_handle h) {
+  if (!h) return LL_ERR_INVALID_ARG;
+  LL_CUDA(h, cudaSetDevice(h->device));
+  LL_CUDA(h, cudaMemsetAsync(h->d_state, 0, sizeof(LMState), h->stream));
+  LL_CUDA(h, cudaStreamSynchronize(h->stream));
+  std::memset(h->h_state, 0, sizeof(LMState));
+  h->scan_pending = false;
+  return LL_OK;
+}
+
+}  // extern "C"

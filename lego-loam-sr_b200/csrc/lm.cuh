@@ -1,0 +1,809 @@
+// The Levenberg-Marquardt loop of scan2MapOptimization (mapOptmization.cpp:1572-1610) on the device.
+//
+// One launch of lm_iter_kernel = one iteration of the reference's loop body:
+//   cornerOptimization (a7) + surfOptimization (a8): one warp per query point —
+//     pointAssociateToMap (a6) -> 5-NN in the 3x3x3 cells of the 1 m grid (a5; candidates of a row of
+//     three x-adjacent cells are contiguous in the cell-sorted array, so lanes read consecutive float4s)
+//     -> warp-level top-5 by (d2, map index) with redux.sync -> line / plane fit in registers (fit.cuh)
+//     -> Jacobian row -> 29 running sums (21 AtA + 6 Atb + sum|d| + count), lane L owning sum L;
+//   LMOptimization (a9): the block partials are written to global memory and the LAST block to
+//     finish (atomic ticket) adds them in a fixed order, solves the 6x6 system, applies the
+//     degeneracy projector, updates the pose and its sin/cos, and evaluates the stop test.
+// Iterations are separate launches on one stream (the kernel boundary is the grid-wide barrier);
+// the host never reads anything back between them.
+#pragma once
+#include "common.cuh"
+#include "fit.cuh"
+#include "map_build.cuh"
+
+namespace ll {
+
+constexpr int LM_THREADS = 256;
+constexpr int LM_WARPS = LM_THREADS / 32;
+constexpr int LM_NSUM = 29;
+constexpr uint32_t LM_EMPTY_D2 = 0x7f800000u;  // +inf: "no candidate"
+
+struct LMParams {
+  FitParams fit;
+  int min_residuals;
+  float eig_thresh;
+  int iter_count_thres;
+  float step_size;
+  float stop_thres;
+  int apply_update;
+  int min_corner_map;
+  int min_surf_map;
+};
+
+// Persistent per-handle state; the members of MapOptimization the hot path reads and writes
+// (mapOptimization.h:245-253, :279-281) plus loop bookkeeping.
+struct LMState {
+  float pose[6];  // transformTobeMapped
+  Trig trig;      // its cached sin / cos (updatePointAssociateToMapSinCos)
+  RotTrig rtrig;  // the six values LMOptimization recomputes (:1445-1450)
+  int iter;       // iterCount of the next launch
+  int done;       // loop has ended (break, threshold, or nothing can change any more)
+  int status;     // 0 optimised, 1 skipped by the map-size guard
+  int iter_num;
+  int converged;
+  int sel_num;
+  int flags;
+  int lm_ret;     // return value of the last LMOptimization: 1 true, 0 false, -1 "< 50 residuals"
+  int is_degenerate;
+  float matP[36];  // row-major
+  float min_lambda;
+  float cf_mean;
+  float last_x[6];
+  float AtA[36];   // row-major, of the last executed iteration
+  float Atb[6];
+  float deltaR, deltaT;
+  unsigned int ticket;
+  int corner_map_ds, surf_map_ds;
+};
+
+struct LMArgs {
+  const float4* sorted[2];
+  const int2* cells[2];
+  const MapState* mst[2];
+  const float4* q[2];  // corner queries, surf queries (sensor frame)
+  int nq[2];
+  LMParams prm;
+  LMState* st;
+  float* partials;  // [gridDim.x][32]
+  int mode;         // 0 = LM iteration; 1 = residuals only (emit); 2 = k-NN only (emit, queries in map frame)
+  // emit targets (mode != 0), indexed by query (corner queries first)
+  float* e_coeff;
+  int* e_mask;
+  int* e_accept;
+  int* e_idx;
+  float* e_d2;
+};
+
+// ---- 6x6 dense helpers (one thread; column-major like Eigen) -------------------------------------------
+struct Mat6 {
+  float d[36];
+  __device__ float& operator()(int r, int c) { return d[c * 6 + r]; }
+  __device__ float operator()(int r, int c) const { return d[c * 6 + r]; }
+};
+
+// Eigen 3.3.7 Householder.h makeHouseholderInPlace on v[0..n)
+__device__ inline void make_householder(float* v, int n, float& tau, float& beta) {
+  float tailSq = 0.f;
+  for (int i = 1; i < n; ++i) tailSq += v[i] * v[i];
+  const float c0 = v[0];
+  if (n == 1 || tailSq <= FLT_MIN) {
+    tau = 0.f;
+    beta = c0;
+    for (int i = 1; i < n; ++i) v[i] = 0.f;
+  } else {
+    beta = sqrtf(c0 * c0 + tailSq);
+    if (c0 >= 0.f) beta = -beta;
+    const float denom = c0 - beta;
+    for (int i = 1; i < n; ++i) v[i] = v[i] / denom;
+    tau = (beta - c0) / beta;
+  }
+}
+
+// matAtA.colPivHouseholderQr().solve(matAtB) (mapOptmization.cpp:1505) for an n x n system, n <= 6.
+// Same step sequence as Eigen 3.3.7 ColPivHouseholderQR::computeInPlace + _solve_impl.
+__device__ void colpiv_qr_solve_n(const float* Ain /* col-major n x n */, const float* b, float* x, int n) {
+  float qr[36], hC[6], nU[6], nD[6], c[6], col[6];
+  int transp[6], perm[6];
+  for (int i = 0; i < n * n; ++i) qr[i] = Ain[i];
+#define QR(r, cc) qr[(cc) * n + (r)]
+  for (int k = 0; k < n; ++k) {
+    float s = 0.f;
+    for (int r = 0; r < n; ++r) s += QR(r, k) * QR(r, k);
+    nD[k] = sqrtf(s);
+    nU[k] = nD[k];
+  }
+  float maxNorm = nU[0];
+  for (int k = 1; k < n; ++k) maxNorm = fmaxf(maxNorm, nU[k]);
+  const float thr = (maxNorm * FLT_EPSILON) * (maxNorm * FLT_EPSILON) / (float)n;
+  const float ndt = sqrtf(FLT_EPSILON);
+  int nonzero = n;
+  for (int k = 0; k < n; ++k) {
+    int big = k;
+    float bigv = nU[k];
+    for (int j = k + 1; j < n; ++j)
+      if (nU[j] > bigv) { bigv = nU[j]; big = j; }
+    if (nonzero == n && bigv * bigv < thr * (float)(n - k)) nonzero = k;
+    transp[k] = big;
+    if (k != big) {
+      for (int r = 0; r < n; ++r) { float t = QR(r, k); QR(r, k) = QR(r, big); QR(r, big) = t; }
+      float t = nU[k]; nU[k] = nU[big]; nU[big] = t;
+      t = nD[k]; nD[k] = nD[big]; nD[big] = t;
+    }
+    const int m = n - k;
+    for (int r = 0; r < m; ++r) col[r] = QR(k + r, k);
+    float tau, beta;
+    make_householder(col, m, tau, beta);
+    for (int r = 1; r < m; ++r) QR(k + r, k) = col[r];
+    QR(k, k) = beta;
+    hC[k] = tau;
+    if (m == 1) {
+      for (int cc = k + 1; cc < n; ++cc) QR(k, cc) *= (1.f - tau);
+    } else if (tau != 0.f) {
+      for (int cc = k + 1; cc < n; ++cc) {
+        float tmp = 0.f;
+        for (int r = 1; r < m; ++r) tmp += col[r] * QR(k + r, cc);
+        tmp += QR(k, cc);
+        QR(k, cc) -= tau * tmp;
+        for (int r = 1; r < m; ++r) QR(k + r, cc) -= tau * col[r] * tmp;
+      }
+    }
+    for (int j = k + 1; j < n; ++j) {
+      if (nU[j] != 0.f) {
+        float temp = fabsf(QR(k, j)) / nU[j];
+        temp = (1.f + temp) * (1.f - temp);
+        temp = temp < 0.f ? 0.f : temp;
+        const float ratio = nU[j] / nD[j];
+        const float temp2 = temp * (ratio * ratio);
+        if (temp2 <= ndt) {
+          float s = 0.f;
+          for (int r = k + 1; r < n; ++r) s += QR(r, j) * QR(r, j);
+          nD[j] = sqrtf(s);
+          nU[j] = nD[j];
+        } else {
+          nU[j] *= sqrtf(temp);
+        }
+      }
+    }
+  }
+  for (int i = 0; i < n; ++i) perm[i] = i;
+  for (int k = 0; k < n; ++k) { int t = perm[k]; perm[k] = perm[transp[k]]; perm[transp[k]] = t; }
+  for (int i = 0; i < n; ++i) x[i] = 0.f;
+  if (nonzero == 0) return;
+  for (int r = 0; r < n; ++r) c[r] = b[r];
+  for (int k = 0; k < nonzero; ++k) {
+    const int m = n - k;
+    const float tau = hC[k];
+    if (m == 1) {
+      c[k] *= (1.f - tau);
+    } else if (tau != 0.f) {
+      float tmp = 0.f;
+      for (int r = 1; r < m; ++r) tmp += QR(k + r, k) * c[k + r];
+      tmp += c[k];
+      c[k] -= tau * tmp;
+      for (int r = 1; r < m; ++r) c[k + r] -= tau * QR(k + r, k) * tmp;
+    }
+  }
+  for (int i = nonzero - 1; i >= 0; --i) {
+    float s = c[i];
+    for (int j = i + 1; j < nonzero; ++j) s -= QR(i, j) * c[j];
+    c[i] = s / QR(i, i);
+  }
+  for (int i = 0; i < nonzero; ++i) x[perm[i]] = c[i];
+#undef QR
+}
+
+// Cyclic Jacobi eigen-decomposition of a symmetric n x n matrix (n <= 6) in double: eigenvalues
+// ascending in w, eigenvectors in the columns of V (col-major n x n). Used for eigen_mode = upstream,
+// where only eigenvalues and the span of the kept eigenvectors matter (sign-free projector).
+__device__ void jacobi_eig_n(const float* Ain /* col-major, symmetric */, int n, double* w, double* V) {
+  double A[36];
+  for (int i = 0; i < n * n; ++i) A[i] = (double)Ain[i];
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < n; ++j) V[j * n + i] = (i == j) ? 1.0 : 0.0;
+#define AA(r, c) A[(c) * n + (r)]
+  for (int sweep = 0; sweep < 30; ++sweep) {
+    double off = 0.0, diag = 0.0;
+    for (int i = 0; i < n; ++i) {
+      diag += AA(i, i) * AA(i, i);
+      for (int j = i + 1; j < n; ++j) off += AA(i, j) * AA(i, j);
+    }
+    if (off <= 1e-30 * diag || off == 0.0) break;
+    for (int p = 0; p < n - 1; ++p)
+      for (int q = p + 1; q < n; ++q) {
+        const double apq = AA(p, q);
+        if (apq == 0.0) continue;
+        const double theta = (AA(q, q) - AA(p, p)) / (2.0 * apq);
+        const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+        const double cth = 1.0 / sqrt(t * t + 1.0), sth = t * cth;
+        for (int k = 0; k < n; ++k) {  // A <- A J
+          const double akp = AA(k, p), akq = AA(k, q);
+          AA(k, p) = cth * akp - sth * akq;
+          AA(k, q) = sth * akp + cth * akq;
+        }
+        for (int k = 0; k < n; ++k) {  // A <- J^T A
+          const double apk = AA(p, k), aqk = AA(q, k);
+          AA(p, k) = cth * apk - sth * aqk;
+          AA(q, k) = sth * apk + cth * aqk;
+        }
+        for (int k = 0; k < n; ++k) {
+          const double vkp = V[p * n + k], vkq = V[q * n + k];
+          V[p * n + k] = cth * vkp - sth * vkq;
+          V[q * n + k] = sth * vkp + cth * vkq;
+        }
+      }
+  }
+  for (int i = 0; i < n; ++i) w[i] = AA(i, i);
+#undef AA
+  for (int i = 0; i < n - 1; ++i) {  // ascending selection sort, swapping columns
+    int k = i;
+    for (int j = i + 1; j < n; ++j)
+      if (w[j] < w[k]) k = j;
+    if (k != i) {
+      double t = w[i]; w[i] = w[k]; w[k] = t;
+      for (int r = 0; r < n; ++r) { double u = V[i * n + r]; V[i * n + r] = V[k * n + r]; V[k * n + r] = u; }
+    }
+  }
+}
+
+// Eigen-style SelfAdjointEigenSolver<Matrix<float,6,6>> (general Householder tridiagonalisation +
+// the shared QR iteration of fit.cuh) and PartialPivLU inverse, for eigen_mode = as shipped
+// (mapOptmization.cpp:1512-1530 depends on Eigen's eigenvector signs). Q col-major.
+__device__ void eig6_eigen_style(const float* Ain /* col-major symmetric */, float ev[6], float Q[36]) {
+  const int N = 6;
+  float A[36];
+#define AA(r, c) A[(c) * N + (r)]
+  float scale = 0.f;
+  for (int i = 0; i < 36; ++i) A[i] = 0.f;
+  for (int c = 0; c < N; ++c)
+    for (int r = c; r < N; ++r) {
+      AA(r, c) = Ain[c * N + r];
+      scale = fmaxf(scale, fabsf(Ain[c * N + r]));
+    }
+  if (scale == 0.f) scale = 1.f;
+  for (int c = 0; c < N; ++c)
+    for (int r = c; r < N; ++r) AA(r, c) /= scale;
+  float hC[5], p[6], col[6], diag[6], sub[5];
+  for (int i = 0; i < N - 1; ++i) {
+    const int rs = N - i - 1;
+    for (int r = 0; r < rs; ++r) col[r] = AA(i + 1 + r, i);
+    float h, beta;
+    make_householder(col, rs, h, beta);
+    col[0] = 1.f;
+    for (int r = 0; r < rs; ++r) {
+      float acc = 0.f;
+      for (int c = 0; c < rs; ++c) {
+        const float a = (r >= c) ? AA(i + 1 + r, i + 1 + c) : AA(i + 1 + c, i + 1 + r);
+        acc += a * (h * col[c]);
+      }
+      p[r] = acc;
+    }
+    float dot = 0.f;
+    for (int r = 0; r < rs; ++r) dot += p[r] * col[r];
+    const float alpha = h * -0.5f * dot;
+    for (int r = 0; r < rs; ++r) p[r] += alpha * col[r];
+    for (int c = 0; c < rs; ++c)
+      for (int r = c; r < rs; ++r) AA(i + 1 + r, i + 1 + c) -= (col[r] * p[c] + p[r] * col[c]);
+    AA(i + 1, i) = beta;
+    for (int r = 1; r < rs; ++r) AA(i + 1 + r, i) = col[r];
+    hC[i] = h;
+  }
+  for (int i = 0; i < N; ++i) diag[i] = AA(i, i);
+  for (int i = 0; i < N - 1; ++i) sub[i] = AA(i + 1, i);
+  for (int i = 0; i < 36; ++i) Q[i] = 0.f;
+  for (int i = 0; i < N; ++i) Q[i * N + i] = 1.f;
+#define QQ(r, c) Q[(c) * N + (r)]
+  for (int k = N - 2; k >= 0; --k) {
+    const int cs = N - k - 1;
+    const int off = N - cs;
+    const float tau = hC[k];
+    if (cs == 1) {
+      QQ(off, off) *= (1.f - tau);
+    } else if (tau != 0.f) {
+      for (int c = 0; c < cs; ++c) {
+        float tmp = 0.f;
+        for (int r = 1; r < cs; ++r) tmp += AA(k + 1 + r, k) * QQ(off + r, off + c);
+        tmp += QQ(off, off + c);
+        QQ(off, off + c) -= tau * tmp;
+        for (int r = 1; r < cs; ++r) QQ(off + r, off + c) -= tau * AA(k + 1 + r, k) * tmp;
+      }
+    }
+  }
+#undef QQ
+#undef AA
+  tridiagonal_eig<6>(diag, sub, Q);
+  for (int i = 0; i < N; ++i) ev[i] = diag[i] * scale;
+}
+
+__device__ void inverse_lu6(const float* Ain /* col-major */, float* inv /* col-major */) {
+  const int N = 6;
+  float lu[36];
+  int piv[6];
+  for (int i = 0; i < 36; ++i) lu[i] = Ain[i];
+#define LU(r, c) lu[(c) * N + (r)]
+  for (int k = 0; k < N; ++k) {
+    int pp = k;
+    float best = fabsf(LU(k, k));
+    for (int r = k + 1; r < N; ++r)
+      if (fabsf(LU(r, k)) > best) { best = fabsf(LU(r, k)); pp = r; }
+    piv[k] = pp;
+    if (pp != k)
+      for (int c = 0; c < N; ++c) { float t = LU(k, c); LU(k, c) = LU(pp, c); LU(pp, c) = t; }
+    if (LU(k, k) != 0.f) {
+      for (int r = k + 1; r < N; ++r) LU(r, k) /= LU(k, k);
+      for (int c = k + 1; c < N; ++c)
+        for (int r = k + 1; r < N; ++r) LU(r, c) -= LU(r, k) * LU(k, c);
+    }
+  }
+  for (int cc = 0; cc < N; ++cc) {
+    float y[6];
+    for (int r = 0; r < N; ++r) y[r] = (r == cc) ? 1.f : 0.f;
+    for (int k = 0; k < N; ++k) { float t = y[k]; y[k] = y[piv[k]]; y[piv[k]] = t; }
+    for (int r = 0; r < N; ++r)
+      for (int c = 0; c < r; ++c) y[r] -= LU(r, c) * y[c];
+    for (int r = N - 1; r >= 0; --r) {
+      for (int c = r + 1; c < N; ++c) y[r] -= LU(r, c) * y[c];
+      y[r] /= LU(r, r);
+    }
+    for (int r = 0; r < N; ++r) inv[cc * N + r] = y[r];
+  }
+#undef LU
+}
+
+__device__ inline void set_trig(LMState* S) {
+  // cos / sin of a float evaluated in double and rounded (the repo-wide convention)
+  S->trig.cr = (float)cos((double)S->pose[0]);
+  S->trig.sr = (float)sin((double)S->pose[0]);
+  S->trig.cp = (float)cos((double)S->pose[1]);
+  S->trig.sp = (float)sin((double)S->pose[1]);
+  S->trig.cy = (float)cos((double)S->pose[2]);
+  S->trig.sy = (float)sin((double)S->pose[2]);
+  S->trig.tx = S->pose[3];
+  S->trig.ty = S->pose[4];
+  S->trig.tz = S->pose[5];
+  S->rtrig.srx = S->trig.sr; S->rtrig.crx = S->trig.cr;
+  S->rtrig.sry = S->trig.sp; S->rtrig.cry = S->trig.cp;
+  S->rtrig.srz = S->trig.sy; S->rtrig.crz = S->trig.cy;
+}
+
+// LMOptimization after the rows are reduced (mapOptmization.cpp:1452-1455, :1502-1569), one thread.
+// sums: 21 upper-triangular AtA entries (row-major order), 6 Atb, sum|d|, count.
+__device__ void lm_solve(const double* sums, const LMParams& prm, LMState* S, bool stage_mode) {
+  const int n = (int)(sums[28] + 0.5);
+  const int iter = S->iter;
+  S->sel_num = n;
+  bool pose_changed = false;
+  int ret;
+  if (n < prm.min_residuals) {
+    ret = -1;  // "return false" before anything is computed (:1453)
+  } else {
+    Mat6 AtA;
+    float Atb[6], x[6];
+    int k = 0;
+    for (int r = 0; r < 6; ++r)
+      for (int c = r; c < 6; ++c) {
+        const float v = (float)sums[k++];
+        AtA(r, c) = v;
+        AtA(c, r) = v;
+      }
+    for (int r = 0; r < 6; ++r) Atb[r] = (float)sums[21 + r];
+    colpiv_qr_solve_n(AtA.d, Atb, x, 6);
+    if (iter == 0) {  // :1507-1531
+      float P[36];    // row-major
+      int degenerate = 0;
+      if (prm.fit.eigen_mode == 0) {
+        float E[6], V[36], V2[36], Vinv[36];
+        eig6_eigen_style(AtA.d, E, V);
+        S->min_lambda = E[0];
+        for (int i = 0; i < 36; ++i) V2[i] = V[i];
+        for (int i = 5; i >= 0; --i) {  // as shipped: ascending eigenvalues walked from the largest
+          if (E[i] < prm.eig_thresh) {
+            for (int j = 0; j < 6; ++j) V2[j * 6 + i] = 0.f;  // zero ROW i of the column matrix
+            degenerate = 1;
+          } else {
+            break;
+          }
+        }
+        inverse_lu6(V, Vinv);
+        for (int r = 0; r < 6; ++r)
+          for (int c = 0; c < 6; ++c) {
+            float acc = 0.f;
+            for (int kk = 0; kk < 6; ++kk) acc += Vinv[kk * 6 + r] * V2[c * 6 + kk];
+            P[r * 6 + c] = acc;
+          }
+      } else {
+        double w[6], V[36];
+        jacobi_eig_n(AtA.d, 6, w, V);
+        S->min_lambda = (float)w[0];
+        int first_kept = 0;
+        while (first_kept < 6 && (float)w[first_kept] < prm.eig_thresh) ++first_kept;
+        degenerate = first_kept > 0;
+        for (int r = 0; r < 6; ++r)
+          for (int c = 0; c < 6; ++c) {
+            double acc = 0.0;
+            for (int kk = first_kept; kk < 6; ++kk) acc += V[kk * 6 + r] * V[kk * 6 + c];
+            P[r * 6 + c] = (float)acc;
+          }
+      }
+      S->is_degenerate = degenerate;
+      for (int i = 0; i < 36; ++i) S->matP[i] = P[i];
+    }
+    if (S->is_degenerate) {  // :1533-1537
+      float x2[6];
+      for (int r = 0; r < 6; ++r) {
+        float acc = 0.f;
+        for (int c = 0; c < 6; ++c) acc += S->matP[r * 6 + c] * x[c];
+        x2[r] = acc;
+      }
+      for (int r = 0; r < 6; ++r) x[r] = x2[r];
+    }
+    if (prm.apply_update) {  // :1540-1545
+      for (int r = 0; r < 6; ++r) S->pose[r] += x[r];
+      pose_changed = true;
+    }
+    const double r0 = (double)(x[0] * 57.29578f), r1 = (double)(x[1] * 57.29578f), r2 = (double)(x[2] * 57.29578f);
+    const float deltaR = (float)sqrt(r0 * r0 + r1 * r1 + r2 * r2);
+    const double t0 = (double)(x[3] * 100.f), t1 = (double)(x[4] * 100.f), t2 = (double)(x[5] * 100.f);
+    const float deltaT = (float)sqrt(t0 * t0 + t1 * t1 + t2 * t2);
+    S->cf_mean = (float)sums[27] / (float)n;  // :1555-1568
+    for (int r = 0; r < 6; ++r) S->last_x[r] = x[r];
+    for (int r = 0; r < 6; ++r)
+      for (int c = 0; c < 6; ++c) S->AtA[r * 6 + c] = AtA(r, c);
+    for (int r = 0; r < 6; ++r) S->Atb[r] = Atb[r];
+    S->deltaR = deltaR;
+    S->deltaT = deltaT;
+    ret = (deltaR < prm.stop_thres && deltaT < prm.stop_thres) ? 1 : 0;
+  }
+  S->lm_ret = ret;
+  if (stage_mode) {
+    if (pose_changed) set_trig(S);
+    return;
+  }
+  // loop control of scan2MapOptimization (:1578-1586)
+  const int executed = iter + 1;
+  if (ret == 1) {
+    S->converged = 1;
+    S->iter_num = executed;
+    S->done = 1;
+  } else if (executed >= prm.iter_count_thres) {
+    S->iter_num = executed;
+    S->done = 1;
+  } else if (!pose_changed) {
+    // Nothing can change any more: the pose is not updated (as shipped, or fewer than 50 residuals), so
+    // every remaining iteration would recompute exactly the same numbers and fall through to the
+    // threshold. Report what the reference reports without replaying them.
+    S->iter_num = prm.iter_count_thres;
+    S->done = 1;
+  }
+  S->iter = executed;
+  if (pose_changed) set_trig(S);
+}
+
+// ---- warp-level 5-NN --------------------------------------------------------------------------------------
+struct GridGeom {
+  int ox, oy, oz, dx, dy, dz;
+};
+
+struct Knn5 {
+  uint32_t d2[5];   // float bit patterns, ascending; LM_EMPTY_D2 = missing
+  uint32_t idx[5];  // map (ds) index
+  uint32_t pos[5];  // position in the cell-sorted array
+  bool accept;
+};
+
+__device__ __forceinline__ bool pair_less(uint32_t da, uint32_t ia, uint32_t db, uint32_t ib) {
+  return da < db || (da == db && ia < ib);
+}
+
+// All 32 lanes of a warp cooperate on ONE query (sx, sy, sz) already in the map frame.
+__device__ __forceinline__ Knn5 warp_knn5(const float4* __restrict__ sorted, const int2* __restrict__ cells,
+                                          const GridGeom& g, float sx, float sy, float sz, float max_sq_dist,
+                                          int lane) {
+  const int cx = (int)floorf(sx) - g.ox, cy = (int)floorf(sy) - g.oy, cz = (int)floorf(sz) - g.oz;
+  int rs[9], rc[9];
+  int total = 0;
+  const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.dx - 1);
+#pragma unroll
+  for (int r = 0; r < 9; ++r) {
+    const int y = cy + (r % 3) - 1, z = cz + (r / 3) - 1;
+    int s = 0, c = 0;
+    if (y >= 0 && y < g.dy && z >= 0 && z < g.dz && x0 <= x1) {
+      const int base = (z * g.dy + y) * g.dx;
+      int s_ = 0x7fffffff, e_ = 0;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const int x = x0 + k;
+        if (x <= x1) {
+          const int2 ce = __ldg(&cells[base + x]);
+          if (ce.y > ce.x) { s_ = min(s_, ce.x); e_ = max(e_, ce.y); }
+        }
+      }
+      if (e_ > 0) { s = s_; c = e_ - s_; }
+    }
+    rs[r] = s;
+    rc[r] = c;
+    total += c;
+  }
+  // per-lane sorted list of the best five candidates this lane has seen
+  uint32_t ld[5], li[5], lp[5];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) { ld[k] = LM_EMPTY_D2; li[k] = 0xffffffffu; lp[k] = 0xffffffffu; }
+  const uint32_t max_bits = __float_as_uint(max_sq_dist);
+  for (int j = lane; j < total; j += 32) {
+    int base = 0, src = 0;
+#pragma unroll
+    for (int r = 0; r < 9; ++r) {
+      if (j >= base && j < base + rc[r]) src = rs[r] + (j - base);
+      base += rc[r];
+    }
+    const float4 m = __ldg(&sorted[src]);
+    // L2_Simple_Adaptor::evalMetric (nanoflann.hpp:431-439): ((dx^2) + dy^2) + dz^2, no contraction
+    float df = sx - m.x;
+    float d = df * df;
+    df = sy - m.y;
+    d += df * df;
+    df = sz - m.z;
+    d += df * df;
+    const uint32_t db = __float_as_uint(d);
+    const uint32_t ib = __float_as_uint(m.w);
+    if (db < max_bits && pair_less(db, ib, ld[4], li[4])) {
+      ld[4] = db; li[4] = ib; lp[4] = (uint32_t)src;
+#pragma unroll
+      for (int k = 4; k > 0; --k) {
+        if (pair_less(ld[k], li[k], ld[k - 1], li[k - 1])) {
+          uint32_t t = ld[k]; ld[k] = ld[k - 1]; ld[k - 1] = t;
+          t = li[k]; li[k] = li[k - 1]; li[k - 1] = t;
+          t = lp[k]; lp[k] = lp[k - 1]; lp[k - 1] = t;
+        }
+      }
+    }
+  }
+  // five rounds of warp-wide arg-min over the list heads, ties broken by the lower map index
+  Knn5 out;
+#pragma unroll
+  for (int r = 0; r < 5; ++r) {
+    const uint32_t m = __reduce_min_sync(0xffffffffu, ld[0]);
+    const uint32_t om = __reduce_min_sync(0xffffffffu, ld[0] == m ? li[0] : 0xffffffffu);
+    const bool win = (ld[0] == m) && (li[0] == om) && (m != LM_EMPTY_D2);
+    const uint32_t pw = __reduce_min_sync(0xffffffffu, win ? lp[0] : 0xffffffffu);
+    out.d2[r] = m;
+    out.idx[r] = om;
+    out.pos[r] = pw;
+    if (win) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { ld[k] = ld[k + 1]; li[k] = li[k + 1]; lp[k] = lp[k + 1]; }
+      ld[4] = LM_EMPTY_D2; li[4] = 0xffffffffu; lp[4] = 0xffffffffu;
+    }
+  }
+  out.accept = out.d2[4] != LM_EMPTY_D2;  // five neighbours, all with d2 < max_sq_dist (:1279 / :1389)
+  return out;
+}
+
+__device__ __forceinline__ void lane_sum_index(int lane, int& a, int& b) {
+  // staging vector sv: [0..5] = Jacobian row, [6] = b, [7] = |d|, [8] = 1, [9] = 0
+  if (lane < 21) {
+    int r = 0, rem = lane;
+    while (rem >= 6 - r) { rem -= 6 - r; ++r; }
+    a = r;
+    b = r + rem;
+  } else if (lane < 27) {
+    a = lane - 21;
+    b = 6;
+  } else if (lane == 27) {
+    a = 7;
+    b = 8;
+  } else if (lane == 28) {
+    a = 8;
+    b = 8;
+  } else {
+    a = 8;
+    b = 9;
+  }
+}
+
+// Sum the block partials in a fixed order (deterministic regardless of which block arrives last).
+__device__ void reduce_partials_and_solve(const float* partials, int nblocks, const LMParams& prm, LMState* S,
+                                          bool stage_mode, double* s_red /* [LM_WARPS][32] shared */) {
+  const int lane = threadIdx.x & 31, sub = threadIdx.x >> 5;
+  double acc = 0.0;
+  for (int b = sub; b < nblocks; b += LM_WARPS) acc += (double)__ldcg(&partials[b * 32 + lane]);
+  s_red[sub * 32 + lane] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < LM_WARPS; ++w) t += s_red[w * 32 + lane];
+    s_red[lane] = t;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) lm_solve(s_red, prm, S, stage_mode);
+}
+
+__global__ void __launch_bounds__(LM_THREADS) lm_iter_kernel(const __grid_constant__ LMArgs A) {
+  LMState* S = A.st;
+  if (A.mode == 0 && S->done) return;
+  __shared__ float s_sv[LM_WARPS][12];
+  __shared__ float s_wacc[LM_WARPS][32];
+  __shared__ double s_red[LM_WARPS * 32];
+  __shared__ int s_last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const Trig trig = S->trig;
+  const RotTrig rt = S->rtrig;
+  GridGeom geom[2];
+#pragma unroll
+  for (int m = 0; m < 2; ++m) {
+    const MapState* ms = A.mst[m];
+    geom[m].ox = ms->gox; geom[m].oy = ms->goy; geom[m].oz = ms->goz;
+    geom[m].dx = ms->gdx; geom[m].dy = ms->gdy; geom[m].dz = ms->gdz;
+  }
+  int ia, ib;
+  lane_sum_index(lane, ia, ib);
+  if (lane == 0) { s_sv[warp][8] = 1.f; s_sv[warp][9] = 0.f; }
+  float acc = 0.f;
+  const int nq = A.nq[0] + A.nq[1];
+  const int gwarp = blockIdx.x * LM_WARPS + warp, nwarps = gridDim.x * LM_WARPS;
+  for (int qi = gwarp; qi < nq; qi += nwarps) {
+    const int m = qi < A.nq[0] ? 0 : 1;
+    const float4 p = __ldg(&A.q[m][m ? qi - A.nq[0] : qi]);
+    const float4 sel = (A.mode == 2) ? p : rigid_transform(trig, p);
+    const Knn5 nn = warp_knn5(A.sorted[m], A.cells[m], geom[m], sel.x, sel.y, sel.z, A.prm.fit.max_sq_dist, lane);
+    float coeff[4] = {0.f, 0.f, 0.f, 0.f};
+    bool keep = false;
+    if (nn.accept && A.mode != 2) {
+      float nbx[5], nby[5], nbz[5];
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {
+        const float4 nb = __ldg(&A.sorted[m][nn.pos[k]]);
+        nbx[k] = nb.x; nby[k] = nb.y; nbz[k] = nb.z;
+      }
+      keep = m == 0 ? corner_fit(nbx, nby, nbz, sel.x, sel.y, sel.z, A.prm.fit, coeff)
+                    : surf_fit(nbx, nby, nbz, sel.x, sel.y, sel.z, A.prm.fit, coeff);
+    }
+    if (A.mode != 0) {
+      if (lane == 0) {
+        if (A.e_accept) A.e_accept[qi] = nn.accept ? 1 : 0;
+        if (A.e_mask) A.e_mask[qi] = keep ? 1 : 0;
+        if (A.e_coeff) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) A.e_coeff[4 * qi + k] = keep ? coeff[k] : 0.f;
+        }
+      }
+      if (lane < 5) {
+        uint32_t d = nn.d2[0], ix = nn.idx[0];
+#pragma unroll
+        for (int k = 1; k < 5; ++k)
+          if (lane == k) { d = nn.d2[k]; ix = nn.idx[k]; }
+        const bool have = d != LM_EMPTY_D2;
+        if (A.e_idx) A.e_idx[5 * qi + lane] = have ? (int)ix : -1;
+        if (A.e_d2) A.e_d2[5 * qi + lane] = have ? __uint_as_float(d) : FLT_MAX;
+      }
+      continue;
+    }
+    if (keep) {  // warp-uniform
+      float row[6];
+      jacobian_row(rt, p.x, p.y, p.z, coeff[0], coeff[1], coeff[2], row);
+      if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) s_sv[warp][k] = row[k];
+        s_sv[warp][6] = -A.prm.step_size * coeff[3];  // matB (:1500)
+        s_sv[warp][7] = fabsf(coeff[3]);
+      }
+      __syncwarp();
+      acc += s_sv[warp][ia] * s_sv[warp][ib];
+      __syncwarp();
+    }
+  }
+  if (A.mode != 0) return;
+  s_wacc[warp][lane] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < LM_WARPS; ++w) t += s_wacc[w][lane];
+    A.partials[blockIdx.x * 32 + lane] = t;
+    __threadfence();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicAdd(&S->ticket, 1u);
+    s_last = (t == gridDim.x - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (threadIdx.x == 0) S->ticket = 0;
+  reduce_partials_and_solve(A.partials, gridDim.x, A.prm, S, false, s_red);
+}
+
+// scan2MapOptimization prologue (:1573): the map-size guard and the loop state, one thread.
+__global__ void lm_begin_kernel(LMState* S, const MapState* corner, const MapState* surf, LMParams prm,
+                                float p0, float p1, float p2, float p3, float p4, float p5) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  S->pose[0] = p0; S->pose[1] = p1; S->pose[2] = p2; S->pose[3] = p3; S->pose[4] = p4; S->pose[5] = p5;
+  set_trig(S);
+  S->iter = 0;
+  S->iter_num = 0;
+  S->converged = 0;
+  S->sel_num = 0;
+  S->lm_ret = 0;
+  S->ticket = 0;
+  S->corner_map_ds = corner->n_ds;
+  S->surf_map_ds = surf->n_ds;
+  int flags = 0;
+  if (corner->voxel_overflow) flags |= 1;
+  if (surf->voxel_overflow) flags |= 2;
+  if (corner->grid_too_large || surf->grid_too_large) flags |= 4;
+  S->flags = flags;
+  const bool ok = corner->n_ds > prm.min_corner_map && surf->n_ds > prm.min_surf_map && !(flags & 4);
+  S->status = ok ? 0 : 1;
+  S->done = ok ? 0 : 1;
+  if (prm.iter_count_thres <= 0) S->done = 1;
+}
+
+// Stage-level a9 (ll_lm_step): rows from explicit (laserCloudOri, coeffSel) records, one thread per record.
+__global__ void __launch_bounds__(LM_THREADS) lm_rows_kernel(const float4* __restrict__ ori,
+                                                             const float4* __restrict__ coeff, int n, LMParams prm,
+                                                             LMState* S, float* partials) {
+  __shared__ float s_wacc[LM_WARPS][32];
+  __shared__ double s_red[LM_WARPS * 32];
+  __shared__ int s_last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const RotTrig rt = S->rtrig;
+  int ia, ib;
+  lane_sum_index(lane, ia, ib);
+  float acc = 0.f;
+  // each warp walks 32 records at a time; every lane computes one row, then the warp folds the 32 rows
+  // into the 29 sums in record order (lane L owns sum L)
+  for (int base = (blockIdx.x * LM_WARPS + warp) * 32; base < n; base += gridDim.x * LM_WARPS * 32) {
+    const int i = base + lane;
+    float sv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float one = 0.f;
+    if (i < n) {
+      const float4 p = ori[i];
+      const float4 c = coeff[i];
+      jacobian_row(rt, p.x, p.y, p.z, c.x, c.y, c.z, sv);
+      sv[6] = -prm.step_size * c.w;
+      sv[7] = fabsf(c.w);
+      one = 1.f;
+    }
+    for (int src = 0; src < 32; ++src) {
+      float v[10];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = __shfl_sync(0xffffffffu, sv[k], src);
+      v[8] = __shfl_sync(0xffffffffu, one, src);
+      v[9] = 0.f;
+      float va = v[0], vb = v[0];
+#pragma unroll
+      for (int k = 1; k < 10; ++k) {
+        if (ia == k) va = v[k];
+        if (ib == k) vb = v[k];
+      }
+      if (v[8] != 0.f) acc += va * vb;
+    }
+  }
+  s_wacc[warp][lane] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < LM_WARPS; ++w) t += s_wacc[w][lane];
+    partials[blockIdx.x * 32 + lane] = t;
+    __threadfence();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicAdd(&S->ticket, 1u);
+    s_last = (t == gridDim.x - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (threadIdx.x == 0) S->ticket = 0;
+  reduce_partials_and_solve(partials, gridDim.x, prm, S, true, s_red);
+}
+
+}  // namespace ll

@@ -1,0 +1,129 @@
+// C++ host mirror of the reference's MapOptimization hot-path members, written over the C ABI only
+// (include/legoloam_b200.h). Member names, call order and data flow follow
+// LeGO-LOAM/src/mapOptimization.h:311,327-333 and MapOptimization::run (mapOptmization.cpp:1854-1930)
+// so that the ROS 2 node can replace the bodies one for one. ROS, PCL, GTSAM and
+// Eigen do not appear: clouds are std::vector of a 32-byte PointXYZI with pcl's field offsets, and the
+// pose graph is a pass-through (loop closure disabled => iSAM2 returns the odometry chain).
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <deque>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "legoloam_b200.h"
+
+namespace lego_loam_b200 {
+
+// pcl::PointXYZI (utility.h:45): x,y,z at bytes 0/4/8, intensity at byte 16, 32-byte stride.
+struct alignas(16) PointXYZI {
+  float x = 0, y = 0, z = 0, data3 = 1.0f;
+  float intensity = 0, pad[3] = {0, 0, 0};
+};
+static_assert(sizeof(PointXYZI) == 32, "PointXYZI must match pcl::PointXYZI's 32-byte layout");
+using PointType = PointXYZI;
+
+struct PointCloud {
+  std::vector<PointType> points;
+  using Ptr = std::shared_ptr<PointCloud>;
+  size_t size() const { return points.size(); }
+  bool empty() const { return points.empty(); }
+  void clear() { points.clear(); }
+  void push_back(const PointType& p) { points.push_back(p); }
+  PointCloud& operator+=(const PointCloud& o) {
+    points.insert(points.end(), o.points.begin(), o.points.end());
+    return *this;
+  }
+};
+
+// PointXYZIRPYT (utility.h:118-134)
+struct PointTypePose {
+  float x = 0, y = 0, z = 0, intensity = 0, roll = 0, pitch = 0, yaw = 0;
+  double time = 0;
+};
+
+// AssociationOut (utility.h:75-83) with the odometry already converted by OdometryToTransform (utility.h:99-113).
+struct AssociationOut {
+  PointCloud::Ptr cloud_outlier_last, cloud_corner_last, cloud_surf_last, cloud_corner_scan, cloud_surf_scan;
+  float laser_odometry[6] = {0, 0, 0, 0, 0, 0};  // transformSum
+  double stamp = 0;
+};
+
+class MapOptimization {
+ public:
+  // loop_closure_enabled / surrounding_keyframe_search_* : loam_config.yaml:23,26,27
+  MapOptimization(const ll_params& params, int device_id, bool loop_closure_enabled = true,
+                  int surrounding_keyframe_search_num = 50, float surrounding_keyframe_search_radius = 50.0f);
+  ~MapOptimization();
+  MapOptimization(const MapOptimization&) = delete;
+  MapOptimization& operator=(const MapOptimization&) = delete;
+
+  // ---- the per-frame body of run() (mapOptmization.cpp:1866-1896) -----------------------------------
+  // scan_clouds_are_downsampled: the five clouds are already what downsampleCurrentScan would produce
+  // (cloud_corner_scan stays raw: it is the corner keyframe cloud, :1746; `corner_scan_ds` then carries
+  // laserCloudCornerScanDS and cloud_surf_last / cloud_outlier_last carry *LastDS, cloud_surf_scan carries
+  // laserCloudSurfTotalLastDS).
+  void processFrame(const AssociationOut& association, bool scan_clouds_are_downsampled = false,
+                    PointCloud::Ptr corner_scan_ds = nullptr);
+
+  // ---- members with the reference's names (mapOptimization.h:311,327-333 and :458,:583) ----------------
+  void transformAssociateToMap();
+  void transformUpdate();
+  void extractSurroundingKeyFrames();
+  void downsampleCurrentScan();
+  void cornerOptimization();        // stage-level: fills laserCloudOri / coeffSel for the current pose
+  void surfOptimization();          // stage-level
+  bool LMOptimization(int iterCount);  // stage-level, on laserCloudOri / coeffSel
+  void scan2MapOptimization();      // the whole loop in one ABI call
+  void saveKeyFramesAndFactor();
+  void correctPoses();
+  void clearCloud();
+
+  // ---- state with the reference's names -------------------------------------------------------------
+  float transformLast[6], transformSum[6], transformIncre[6], transformTobeMapped[6], transformBefMapped[6],
+      transformAftMapped[6];
+  PointCloud::Ptr laserCloudCornerLast, laserCloudSurfLast, laserCloudCornerScan, laserCloudSurfScan,
+      laserCloudOutlierLast;
+  PointCloud::Ptr laserCloudCornerLastDS, laserCloudSurfLastDS, laserCloudCornerScanDS, laserCloudSurfScanDS,
+      laserCloudOutlierLastDS, laserCloudSurfTotalLast, laserCloudSurfTotalLastDS;
+  PointCloud::Ptr laserCloudOri, coeffSel;
+  std::vector<PointType> cloudKeyPoses3D;
+  std::vector<PointTypePose> cloudKeyPoses6D;
+  PointType currentRobotPosPoint, previousRobotPosPoint;
+  int laserCloudCornerFromMapDSNum = 0, laserCloudSurfFromMapDSNum = 0;
+  bool isDegenerate = false;
+  float min_lambda = 0, CF_mean = 0;
+  int iter_num = 0;
+  int frame_idx = 0;
+  bool aLoopIsClosed = false;
+  std::vector<PointType> localInfo;  // (iter_num, min_lambda, CF_mean, frame_idx), :1602-1607
+  ll_result lastResult;
+
+  // laserCloud{Corner,Surf}FromMapDS on request (publishKeyPosesAndFrames reads the surf one, :746-752)
+  PointCloud::Ptr getLaserCloudCornerFromMapDS();
+  PointCloud::Ptr getLaserCloudSurfFromMapDS();
+
+  ll_handle handle() const { return h_; }
+  const std::string& lastError() const { return err_; }
+
+ private:
+  void check(int rc, const char* what);
+  PointCloud::Ptr voxel(const PointCloud& in, float leaf);
+
+  ll_handle h_ = nullptr;
+  ll_params prm_;
+  bool loop_closure_enabled_;
+  int search_num_;
+  float search_radius_;
+  std::string err_;
+  // loop-closure-on branch: ids of the keyframes in the recent deque (:1101-1151)
+  std::deque<int> recentKeyFrameIDs_;
+  int latestFrameID_ = 0;
+  // loop-closure-off branch: surroundingExistingKeyPosesID (:1171-1216)
+  std::vector<int> surroundingExistingKeyPosesID_;
+  std::vector<int> mapIds_;
+  bool mapBuilt_ = false;
+};
+
+}  // namespace lego_loam_b200

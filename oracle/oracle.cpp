@@ -699,6 +699,50 @@ void orc_transform_associate_to_map(const float sum[6], const float bef[6], cons
   tobe[5] = aft[5] - (-S(tobe[1]) * x2 + C(tobe[1]) * z2);
 }
 
+// ---- direct access to the restated Eigen pieces, for the oracle's own cross-checks -------------------
+// A: row-major n x n symmetric (n = 3 or 6); evals ascending, evecs row-major with eigenvectors in columns.
+void orc_test_self_adjoint_eig(const float* A, int n, float* evals, float* evecs) {
+  if (n == 3) {
+    Mat<3, 3> M, V;
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) M(r, c) = A[3 * r + c];
+    orc_eig::self_adjoint_eig<3>(M, evals, V);
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) evecs[3 * r + c] = V(r, c);
+  } else {
+    Mat<6, 6> M, V;
+    for (int r = 0; r < 6; ++r)
+      for (int c = 0; c < 6; ++c) M(r, c) = A[6 * r + c];
+    orc_eig::self_adjoint_eig<6>(M, evals, V);
+    for (int r = 0; r < 6; ++r)
+      for (int c = 0; c < 6; ++c) evecs[6 * r + c] = V(r, c);
+  }
+}
+
+// A: row-major (5x3 or 6x6), b: rows; x: cols.
+void orc_test_colpiv_qr_solve(const float* A, const float* b, int rows, int cols, float* x) {
+  if (rows == 5 && cols == 3) {
+    Mat<5, 3> M;
+    for (int r = 0; r < 5; ++r)
+      for (int c = 0; c < 3; ++c) M(r, c) = A[3 * r + c];
+    orc_eig::colpiv_qr_solve<5, 3>(M, b, x);
+  } else {
+    Mat<6, 6> M;
+    for (int r = 0; r < 6; ++r)
+      for (int c = 0; c < 6; ++c) M(r, c) = A[6 * r + c];
+    orc_eig::colpiv_qr_solve<6, 6>(M, b, x);
+  }
+}
+
+void orc_test_inverse6(const float* A, float* inv) {
+  Mat<6, 6> M, I;
+  for (int r = 0; r < 6; ++r)
+    for (int c = 0; c < 6; ++c) M(r, c) = A[6 * r + c];
+  orc_eig::inverse_lu<6>(M, I);
+  for (int r = 0; r < 6; ++r)
+    for (int c = 0; c < 6; ++c) inv[6 * r + c] = I(r, c);
+}
+
 orc_replay* orc_replay_create(const orc_params* prm, int window) {
   orc_replay* r = new orc_replay();
   r->prm = *prm;

@@ -219,6 +219,32 @@ def transform_associate_to_map(tsum, bef, aft):
     return out
 
 
+def self_adjoint_eig(A):
+    A = np.ascontiguousarray(A, np.float32)
+    n = A.shape[0]
+    assert A.shape == (n, n) and n in (3, 6)
+    ev = np.zeros(n, np.float32)
+    V = np.zeros((n, n), np.float32)
+    lib().orc_test_self_adjoint_eig(_ptr(A), C.c_int(n), _ptr(ev), _ptr(V))
+    return ev, V
+
+
+def colpiv_qr_solve(A, b):
+    A = np.ascontiguousarray(A, np.float32)
+    b = np.ascontiguousarray(b, np.float32)
+    assert A.shape in ((5, 3), (6, 6))
+    x = np.zeros(A.shape[1], np.float32)
+    lib().orc_test_colpiv_qr_solve(_ptr(A), _ptr(b), C.c_int(A.shape[0]), C.c_int(A.shape[1]), _ptr(x))
+    return x
+
+
+def inverse6(A):
+    A = np.ascontiguousarray(A, np.float32)
+    out = np.zeros((6, 6), np.float32)
+    lib().orc_test_inverse6(_ptr(A), _ptr(out))
+    return out
+
+
 class Replay:
     def __init__(self, prm, window=50):
         self._h = C.c_void_p(lib().orc_replay_create(C.byref(prm), C.c_int(window)))

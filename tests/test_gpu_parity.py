@@ -1,0 +1,392 @@
+"""Parity tests proper: the CUDA path, called through the C ABI, against the CPU oracle on identical
+seeded inputs (B200 box; `pytest -m gpu`).
+
+Bars (BASELINE.json north_star):
+  * voxel-downsampled map membership, output order AND coordinates: bit-exact;
+  * 5-NN accept mask and neighbour index sets (ties by index) and squared distances: bit-exact;
+  * per-point residual records: |diff| <= 2e-5 (same masks except points within float rounding of a threshold);
+  * final 6-DoF pose after 10 LM iterations: <= 1e-4 m translation, <= 1e-5 rad rotation.
+"""
+import numpy as np
+import pytest
+
+from conftest import rot_err, trans_err, upstream_params
+
+pytestmark = pytest.mark.gpu
+
+TOL_T = 1e-4   # metres, BASELINE.json
+TOL_R = 1e-5   # radians, BASELINE.json
+TOL_COEFF = 2e-5
+
+
+@pytest.fixture(scope="module")
+def abi():
+    import __graft_entry__ as ge
+    ge.build()
+    from lego_loam_sr_b200 import abi as _abi
+    return _abi
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def load_map(h, d):
+    kf = d["keyframes"]
+    for i, f in enumerate(kf):
+        h.add_keyframe(i, f["corner_scan"], f["surf_last_ds"], f["outlier_last_ds"], d["key_poses"][i])
+    h.build_local_map(list(range(len(kf))))
+
+
+# ------------------------------------------------------------------------------------------ a3 VoxelGrid
+@pytest.mark.parametrize("leaf", [0.2, 0.4, 1.0])
+def test_voxel_downsample_bit_exact(abi, orc, single_problem, leaf):
+    d = single_problem
+    pts = np.concatenate([orc.transform_cloud(f["surf_last_ds"], d["key_poses"][i]) for i, f in enumerate(d["keyframes"][:12])])
+    with abi.Handle() as h:
+        out, member, flags = h.voxel_downsample(pts, leaf)
+    o_out, o_member, o_flag = orc.voxel_downsample(pts, leaf)
+    assert flags == o_flag == 0
+    assert len(out) == len(o_out)
+    assert np.array_equal(member, o_member)            # membership + output order
+    assert np.array_equal(bits(out), bits(o_out))      # centroids, accumulated in the canonical order
+
+
+def test_voxel_downsample_edge_cases(abi, orc):
+    rng = np.random.default_rng(0)
+    with abi.Handle() as h:
+        out, member, flags = h.voxel_downsample(np.zeros((0, 4), np.float32), 0.2)
+        assert len(out) == 0
+        one = np.array([[1.5, 2.5, -3.5, 7.0]], np.float32)
+        out, member, flags = h.voxel_downsample(one, 0.2)
+        assert np.array_equal(out, one) and member.tolist() == [0]
+        same = np.tile(np.array([[1.0, 1.0, 1.0, 2.0]], np.float32), (700, 1))
+        out, member, flags = h.voxel_downsample(same, 0.2)
+        o_out, o_member, _ = orc.voxel_downsample(same, 0.2)
+        assert np.array_equal(bits(out), bits(o_out)) and np.array_equal(member, o_member)
+        # ragged sizes around tile boundaries (1024 / 2048) and a PointXYZI-strided (32-byte) input
+        for n in (1023, 1024, 1025, 2047, 2049, 5000):
+            pts = np.concatenate([rng.uniform(-8, 8, (n, 3)), rng.uniform(0, 16, (n, 1))], 1).astype(np.float32)
+            out, member, flags = h.voxel_downsample(pts, 0.4)
+            o_out, o_member, _ = orc.voxel_downsample(pts, 0.4)
+            assert np.array_equal(member, o_member) and np.array_equal(bits(out), bits(o_out)), n
+        wide = np.zeros((len(pts), 8), np.float32)
+        wide[:, :3] = pts[:, :3]
+        wide[:, 3] = 1.0
+        wide[:, 4] = pts[:, 3]
+        out32, member32, _ = h.voxel_downsample(wide, 0.4)
+        assert np.array_equal(bits(out32), bits(o_out))
+        # negative coordinates, large offsets
+        pts = np.concatenate([rng.uniform(-500, -480, (3000, 3)), rng.uniform(0, 16, (3000, 1))], 1).astype(np.float32)
+        out, member, flags = h.voxel_downsample(pts, 0.2)
+        o_out, o_member, _ = orc.voxel_downsample(pts, 0.2)
+        assert np.array_equal(member, o_member) and np.array_equal(bits(out), bits(o_out))
+        # int32 voxel index overflow: PCL passes the input through; so do the oracle and the device
+        far = np.array([[0, 0, 0, 0], [3000, 3000, 3000, 1], [10, 10, 10, 2]], np.float32)
+        out, member, flags = h.voxel_downsample(far, 0.01)
+        o_out, o_member, o_flag = orc.voxel_downsample(far, 0.01)
+        assert flags == 1 and o_flag == 1
+        assert np.array_equal(bits(out), bits(o_out)) and np.array_equal(member, o_member)
+
+
+# ------------------------------------------------------------------------------------------ a1/a2 local map
+def test_local_map_assembly_bit_exact(abi, orc, single_problem, single_maps):
+    with abi.Handle() as h:
+        load_map(h, single_problem)
+        cds, sds = h.get_map_ds(0), h.get_map_ds(1)
+    assert len(cds) == len(single_maps["corner_ds"]) and len(sds) == len(single_maps["surf_ds"])
+    assert np.array_equal(bits(cds), bits(single_maps["corner_ds"]))
+    assert np.array_equal(bits(sds), bits(single_maps["surf_ds"]))
+
+
+def test_local_map_subset_order_and_pose_update(abi, orc, single_problem):
+    """Cache order = ids order (:1218-1222); set_keyframe_pose is what correctPoses does (:1757-1785)."""
+    d = single_problem
+    kf = d["keyframes"]
+    ids = [7, 2, 11, 5]
+    poses = d["key_poses"].copy()
+    poses[2] = poses[2] + np.array([0.01, -0.02, 0.005, 0.3, -0.1, 0.2], np.float32)
+    prm = orc.default_params()
+    o_c, o_s, _, _ = orc.build_local_map(poses[ids], [kf[i]["corner_scan"] for i in ids], [kf[i]["surf_last_ds"] for i in ids],
+                                         [kf[i]["outlier_last_ds"] for i in ids], prm)
+    with abi.Handle() as h:
+        for i, f in enumerate(kf):
+            h.add_keyframe(i, f["corner_scan"], f["surf_last_ds"], f["outlier_last_ds"], d["key_poses"][i])
+        h.set_keyframe_pose(2, poses[2])
+        h.build_local_map(ids)
+        assert np.array_equal(bits(h.get_map_ds(0)), bits(o_c))
+        assert np.array_equal(bits(h.get_map_ds(1)), bits(o_s))
+        with pytest.raises(abi.LegoLoamError) as e:
+            h.build_local_map([0, 999])
+        assert e.value.code == -4
+    # map_downsample = 0 (BASELINE config 4): the raw concatenation is the map
+    prm0 = orc.default_params(map_downsample=0)
+    r_c, r_s, _, _ = orc.build_local_map(poses[ids], [kf[i]["corner_scan"] for i in ids], [kf[i]["surf_last_ds"] for i in ids],
+                                         [kf[i]["outlier_last_ds"] for i in ids], prm0)
+    with abi.Handle(abi.default_params(map_downsample=0)) as h:
+        for i in ids:
+            h.add_keyframe(i, kf[i]["corner_scan"], kf[i]["surf_last_ds"], kf[i]["outlier_last_ds"], poses[i])
+        h.build_local_map(ids)
+        assert np.array_equal(bits(h.get_map_ds(0)), bits(r_c))
+        assert np.array_equal(bits(h.get_map_ds(1)), bits(r_s))
+
+
+# ------------------------------------------------------------------------------------------ a4/a5 k-NN
+def test_knn5_bit_exact(abi, orc, single_problem, single_maps):
+    d = single_problem
+    with abi.Handle() as h:
+        h.set_local_map_raw(single_maps["corner_ds"], single_maps["surf_ds"])  # goes through VoxelGrid again
+        # a voxel-filtered map is a fixed point of the filter at the same leaf only up to rounding, so query the
+        # map the device actually holds
+        maps = [h.get_map_ds(0), h.get_map_ds(1)]
+        for which, cloud in ((0, "corner_scan_ds"), (1, "surf_total_ds")):
+            q = orc.transform_cloud(d["query"][cloud], d["gt"])
+            q = np.concatenate([q, q[:20] + np.float32(40.0)])  # some queries far outside the map
+            idx, d2, accept = h.knn5(which, q)
+            o_idx, o_d2 = orc.knn5(maps[which], q, orc.KNN_BRUTE)
+            o_accept = (o_idx[:, 4] >= 0) & (o_d2[:, 4] < 1.0)
+            assert np.array_equal(accept.astype(bool), o_accept)
+            assert o_accept.sum() > 0.5 * len(d["query"][cloud])
+            assert np.array_equal(idx[o_accept], o_idx[o_accept])
+            assert np.array_equal(bits(d2[o_accept]), bits(o_d2[o_accept]))
+            if orc.have_ref():  # and against the reference's own nanoflann
+                n_idx, n_d2 = orc.knn5(maps[which], q, orc.KNN_NANOFLANN)
+                tie_free = (np.diff(o_d2, axis=1) > 0).all(1) & o_accept
+                assert np.array_equal(idx[tie_free], n_idx[tie_free])
+
+
+def test_knn5_exact_ties_and_small_maps(abi, orc):
+    """Equal distances: the five lowest indices win, in index order. Fewer than five candidates: rejected."""
+    m = (np.array([[1, 0, 0, 0], [-1, 0, 0, 0], [0, 1, 0, 0], [0, -1, 0, 0], [0, 0, 1, 0], [0, 0, -1, 0], [1, 0, 0, 0],
+                   [0, 1, 0, 0]], np.float32) * 0.5)
+    surf = np.concatenate([np.random.default_rng(1).uniform(5, 9, (300, 3)), np.zeros((300, 1))], 1).astype(np.float32)
+    with abi.Handle(abi.default_params(map_downsample=0)) as h:
+        h.set_local_map_raw(m, surf)
+        q = np.array([[0, 0, 0, 0], [0.3, 0.2, -0.1, 0], [30, 30, 30, 0]], np.float32)
+        idx, d2, accept = h.knn5(0, q)
+        o_idx, o_d2 = orc.knn5(m, q, orc.KNN_BRUTE)
+        assert idx[0].tolist() == [0, 1, 2, 3, 4] and accept.tolist() == [1, 1, 0]
+        assert np.array_equal(idx[:2], o_idx[:2]) and np.array_equal(bits(d2[:2]), bits(o_d2[:2]))
+        h.set_local_map_raw(m[:4], surf)
+        idx, d2, accept = h.knn5(0, q)
+        assert accept.tolist() == [0, 0, 0]
+
+
+# ------------------------------------------------------------------------------------------ a6/a7/a8 residuals
+@pytest.mark.parametrize("eigen_mode", [1, 0])
+def test_residuals_parity(abi, orc, single_problem, single_maps, eigen_mode):
+    d = single_problem
+    prm = upstream_params(abi, eigen_mode=eigen_mode)
+    oprm = upstream_params(orc, eigen_mode=eigen_mode)
+    with abi.Handle(prm) as h:
+        load_map(h, d)
+        for name, fn, ofn, mp, cloud in (("corner", h.corner_residuals, orc.corner_residuals, single_maps["corner_ds"], "corner_scan_ds"),
+                                         ("surf", h.surf_residuals, orc.surf_residuals, single_maps["surf_ds"], "surf_total_ds")):
+            q = d["query"][cloud]
+            g = fn(q, d["prior"])
+            o = ofn(mp, q, d["prior"], oprm)
+            assert np.array_equal(g["accept"], o["accept"]), name
+            acc = o["accept"].astype(bool)
+            assert np.array_equal(g["knn_idx"][acc], o["knn_idx"][acc]), name
+            assert np.array_equal(bits(g["knn_d2"][acc]), bits(o["knn_d2"][acc])), name
+            mism = int((g["mask"] != o["mask"]).sum())
+            both = (g["mask"] == 1) & (o["mask"] == 1)
+            assert both.sum() > 0.3 * len(q), (name, both.sum(), len(q))
+            assert mism <= max(2, len(q) // 1000), (name, mism)  # only points sitting on a threshold may flip
+            err = np.abs(g["coeff"][both] - o["coeff"][both]).max()
+            assert err <= TOL_COEFF, (name, err)
+            nbit = int((bits(g["coeff"][both]) != bits(o["coeff"][both])).any(1).sum())
+            print("%s eigen_mode=%d: %d kept, %d mask mismatches, max |dcoeff| %.2e, %d records not bit-identical"
+                  % (name, eigen_mode, both.sum(), mism, err, nbit))
+
+
+# ------------------------------------------------------------------------------------------ a9 LM step
+@pytest.mark.parametrize("eigen_mode", [1, 0])
+def test_lm_step_parity(abi, orc, single_problem, single_maps, eigen_mode):
+    d = single_problem
+    oprm = upstream_params(orc, eigen_mode=eigen_mode)
+    rc = orc.corner_residuals(single_maps["corner_ds"], d["query"]["corner_scan_ds"], d["prior"], oprm)
+    rs = orc.surf_residuals(single_maps["surf_ds"], d["query"]["surf_total_ds"], d["prior"], oprm)
+    ori = np.concatenate([d["query"]["corner_scan_ds"][rc["mask"] == 1], d["query"]["surf_total_ds"][rs["mask"] == 1]])
+    coeff = np.concatenate([rc["coeff"][rc["mask"] == 1], rs["coeff"][rs["mask"] == 1]])
+    for eig_thresh in (100.0, 1e9):  # 1e9: every direction is "degenerate" -> exercises the projector
+        ost = orc.new_state()
+        oprm.eig_thresh = eig_thresh
+        o = orc.lm_step(ori, coeff, 0, d["prior"], oprm, ost)
+        prm = upstream_params(abi, eigen_mode=eigen_mode, eig_thresh=eig_thresh)
+        with abi.Handle(prm) as h:
+            g = h.lm_step(ori, coeff, 0, d["prior"])
+            deg, P = h.get_degeneracy()
+        assert g["ret"] == o["ret"]
+        scale = np.abs(o["AtA"]).max()
+        assert np.abs(g["AtA"] - o["AtA"]).max() <= 2e-5 * scale
+        assert np.abs(g["Atb"] - o["Atb"]).max() <= 2e-5 * np.abs(o["Atb"]).max() + 1e-6
+        assert deg == ost.is_degenerate
+        if eigen_mode == 1 or eig_thresh == 100.0:
+            assert np.abs(P - np.array(ost.matP).reshape(6, 6)).max() <= 1e-3
+        assert np.abs(g["x"] - o["x"]).max() <= 5e-5, (g["x"], o["x"])
+        assert np.abs(g["pose"] - o["pose"]).max() <= 5e-5
+        assert abs(g["deltaR"] - o["deltaR"]) <= 1e-3 * max(1.0, o["deltaR"])
+    # fewer than 50 residuals: skipped, pose untouched (:1453)
+    with abi.Handle(upstream_params(abi)) as h:
+        g = h.lm_step(ori[:20], coeff[:20], 0, d["prior"])
+    assert g["ret"] == -1 and np.array_equal(g["pose"], d["prior"])
+
+
+# ------------------------------------------------------------------------------------------ a10 full loop
+def test_scan2map_pose_within_tolerance(abi, orc, single_problem, single_maps):
+    d = single_problem
+    with abi.Handle(upstream_params(abi)) as h:
+        load_map(h, d)
+        pose, res = h.scan2map(d["query"]["corner_scan_ds"], d["query"]["surf_total_ds"], d["prior"])
+        pose2, res2 = h.scan2map(d["query"]["corner_scan_ds"], d["query"]["surf_total_ds"], d["prior"])
+    ores, opose, _ = orc.scan2map(single_maps["corner_ds"], single_maps["surf_ds"], d["query"]["corner_scan_ds"],
+                                  d["query"]["surf_total_ds"], d["prior"], upstream_params(orc))
+    assert res.status == 0 and res.iter_num == ores.iter_num == 10
+    assert res.corner_map_ds == len(single_maps["corner_ds"]) and res.surf_map_ds == len(single_maps["surf_ds"])
+    assert abs(res.sel_num - ores.sel_num) <= 3
+    assert trans_err(pose, opose) <= TOL_T, (pose, opose)
+    assert rot_err(pose, opose) <= TOL_R, (pose, opose)
+    assert abs(res.min_lambda - ores.min_lambda) <= 1e-3 * ores.min_lambda
+    assert abs(res.cf_mean - ores.cf_mean) <= 1e-5
+    assert res.is_degenerate == ores.is_degenerate
+    assert trans_err(pose, d["gt"]) < 0.02
+    assert np.array_equal(bits(pose), bits(pose2)) and res2.sel_num == res.sel_num  # deterministic reduction order
+    print("scan2map: |dt| %.2e m, |dr| %.2e rad vs oracle; sel %d vs %d" % (trans_err(pose, opose), rot_err(pose, opose), res.sel_num, ores.sel_num))
+
+
+def test_scan2map_early_exit_and_thresholds(abi, orc, single_problem, single_maps):
+    d = single_problem
+    for kw in (dict(stop_thres=0.05, iter_count_thres=30), dict(stop_thres=0.05, iter_count_thres=200),
+               dict(stop_thres=0.0, iter_count_thres=3), dict(stop_thres=0.0, iter_count_thres=25)):
+        with abi.Handle(upstream_params(abi, **kw)) as h:
+            load_map(h, d)
+            pose, res = h.scan2map(d["query"]["corner_scan_ds"], d["query"]["surf_total_ds"], d["prior"])
+        ores, opose, _ = orc.scan2map(single_maps["corner_ds"], single_maps["surf_ds"], d["query"]["corner_scan_ds"],
+                                      d["query"]["surf_total_ds"], d["prior"], upstream_params(orc, **kw))
+        assert (res.iter_num, res.converged) == (ores.iter_num, ores.converged), kw
+        assert trans_err(pose, opose) <= TOL_T and rot_err(pose, opose) <= TOL_R, kw
+
+
+def test_scan2map_as_shipped(abi, orc, single_problem, single_maps):
+    """apply_update = 0, eigen_mode = 0, 200 iterations: the reference as it ships (pose never moves)."""
+    d = single_problem
+    with abi.Handle(abi.default_params()) as h:
+        load_map(h, d)
+        pose, res = h.scan2map(d["query"]["corner_scan_ds"], d["query"]["surf_total_ds"], d["prior"])
+    ores, opose, _ = orc.scan2map(single_maps["corner_ds"], single_maps["surf_ds"], d["query"]["corner_scan_ds"],
+                                  d["query"]["surf_total_ds"], d["prior"], orc.default_params(iter_count_thres=200))
+    assert np.array_equal(pose, d["prior"]) and np.array_equal(opose, d["prior"])
+    assert (res.iter_num, res.converged, res.is_degenerate) == (ores.iter_num, ores.converged, ores.is_degenerate) == (200, 0, 0)
+    assert abs(res.sel_num - ores.sel_num) <= 3
+    assert abs(res.cf_mean - ores.cf_mean) <= 1e-5
+    assert abs(res.min_lambda - ores.min_lambda) <= 2e-3 * abs(ores.min_lambda)
+    assert np.abs(np.array(res.last_x) - np.array(ores.last_x)).max() <= 1e-4
+
+
+def test_scan2map_guards(abi, orc, single_problem, single_maps):
+    d = single_problem
+    with abi.Handle(upstream_params(abi, map_downsample=0)) as h:
+        h.set_local_map_raw(single_maps["corner_ds"][:10], single_maps["surf_ds"])
+        pose, res = h.scan2map(d["query"]["corner_scan_ds"], d["query"]["surf_total_ds"], d["prior"])
+        assert res.status == 1 and res.iter_num == 0 and np.array_equal(pose, d["prior"])  # :1573
+        h.set_local_map_raw(single_maps["corner_ds"], single_maps["surf_ds"])
+        pose, res = h.scan2map(d["query"]["corner_scan_ds"][:5], d["query"]["surf_total_ds"][:20], d["prior"])
+        assert res.status == 0 and res.iter_num == 10 and res.sel_num < 50 and np.array_equal(pose, d["prior"])  # :1453
+        pose, res = h.scan2map(np.zeros((0, 4), np.float32), np.zeros((0, 4), np.float32), d["prior"])
+        assert res.status == 0 and res.sel_num == 0 and np.array_equal(pose, d["prior"])
+    with abi.Handle(upstream_params(abi)) as h:
+        with pytest.raises(abi.LegoLoamError) as e:
+            h.scan2map(d["query"]["corner_scan_ds"], d["query"]["surf_total_ds"], d["prior"])
+        assert e.value.code == -7  # no local map yet
+
+
+# ------------------------------------------------------------------------------------------ replay (config 2 shape)
+def test_replay_matches_oracle(abi, orc, sequence):
+    """The C++ MapOptimization mirror (host/) fed frame by frame vs the oracle's replay of the same frames."""
+    from lego_loam_sr_b200 import host
+    kw = dict(iter_count_thres=10, stop_thres=0.0)
+    mo = host.MapOptimization(upstream_params(abi, **kw), loop_closure_enabled=True, search_num=50)
+    rp = orc.Replay(upstream_params(orc, **kw), window=50)
+    worst_t = worst_r = 0.0
+    for k, f in enumerate(sequence["frames"]):
+        pose, res = mo.process_frame(sequence["odom"][k], f, pre_downsampled=True)
+        ores, nc, ns = rp.step(sequence["odom"][k], f["corner_scan"], f["corner_scan_ds"], f["surf_last_ds"],
+                               f["outlier_last_ds"], f["surf_total_ds"])
+        assert res.status == ores.status, k
+        if res.status == 0:
+            # per-frame drift between the two replays stays at rounding level; it compounds through the map
+            worst_t = max(worst_t, trans_err(pose, ores.pose))
+            worst_r = max(worst_r, rot_err(pose, ores.pose))
+            assert abs(res.corner_map_ds - nc) <= max(3, nc // 500) and abs(res.surf_map_ds - ns) <= max(3, ns // 500), k
+    assert mo.num_keyframes == len(sequence["frames"])
+    assert worst_t <= 5e-4 and worst_r <= 5e-5, (worst_t, worst_r)
+    print("replay: worst |dt| %.2e m, |dr| %.2e rad over %d frames" % (worst_t, worst_r, len(sequence["frames"])))
+    mo.close()
+
+
+def test_replay_scan_side_downsample_on_device(abi, orc, synth, sequence):
+    """downsampleCurrentScan (:1234-1267) through ll_voxel_downsample: raw clouds in, same frame products."""
+    from conftest import SMALL_WORLD
+    from lego_loam_sr_b200 import host
+    world = synth.World(seed=2, **SMALL_WORLD)
+    gt = synth.trajectory(world, 4, step=0.7, seed=2)
+    mo = host.MapOptimization(upstream_params(abi), loop_closure_enabled=False, search_num=50, search_radius=50.0)
+    for k in range(4):
+        raw = synth.scan(world, gt[k], seed=2 * 100003 + k)
+        pose, res = mo.process_frame(gt[k].astype(np.float32), raw, pre_downsampled=False)
+        assert res.status == (1 if k == 0 else 0)
+        if k:
+            assert trans_err(pose, gt[k]) < 0.05
+    mo.close()
+
+
+# ------------------------------------------------------------------------------------------ full-size properties
+def test_full_size_properties(abi, orc):
+    """BASELINE config 3/4 sizes (2 M-point map, 100 k queries): too big for the brute-force oracle, so check
+    size-independent properties — membership partition, sortedness, centroid containment, idempotence of the
+    voxel stage, and k-NN against the oracle's grid index on a sample."""
+    rng = np.random.default_rng(4)
+    n = 2_000_000
+    # a few planes + clutter, ~120 m extent
+    pts = np.empty((n, 4), np.float32)
+    pts[:, 0] = rng.uniform(-60, 60, n)
+    pts[:, 2] = rng.uniform(-60, 60, n)
+    pts[:, 1] = np.where(rng.random(n) < 0.7, -1.8 + rng.normal(0, 0.02, n), rng.uniform(-1.8, 6, n))
+    pts[:, 3] = rng.uniform(0, 16, n)
+    with abi.Handle(abi.default_params(map_downsample=0)) as h:
+        out, member, flags = h.voxel_downsample(pts, 0.4)
+        assert flags == 0 and member.min() == 0 and member.max() == len(out) - 1
+        cnt = np.bincount(member, minlength=len(out))
+        assert cnt.min() >= 1 and cnt.sum() == n
+        inv = np.float32(1.0) / np.float32(0.4)
+        vox = np.floor(pts[:, :3] * inv).astype(np.int64)
+        vo = np.floor(out[:, :3] * inv).astype(np.int64)
+        # each centroid lies in (or on the rounding edge of) the voxel of its members
+        assert np.abs(vo[member] - vox).max() <= 1
+        mn = vox.min(0)
+        dd = vox.max(0) - mn + 1
+        key = (vox[:, 0] - mn[0]) + dd[0] * ((vox[:, 1] - mn[1]) + dd[1] * (vox[:, 2] - mn[2]))
+        first = np.full(len(out), -1, np.int64)
+        first[member[::-1]] = key[::-1]
+        assert (np.diff(first) > 0).all()                    # output ascends in voxel index
+        assert len(np.unique(key)) == len(out)
+        sums = np.zeros((len(out), 4))
+        np.add.at(sums, member, pts.astype(np.float64))
+        assert np.abs(sums / cnt[:, None] - out).max() < 5e-4  # centroid = mean
+        out2, member2, _ = h.voxel_downsample(out, 0.4)
+        assert abs(len(out2) - len(out)) <= len(out) // 1000   # (near-)idempotent
+        # k-NN at scale on the un-downsampled 2 M map vs the oracle grid (exact, canonical)
+        corner = pts[:200_000]
+        h.set_local_map_raw(corner, pts)
+        q = pts[rng.choice(n, 100_000, replace=False)].copy()
+        q[:, :3] += rng.normal(0, 0.05, (len(q), 3)).astype(np.float32)
+        idx, d2, accept = h.knn5(1, q)
+        assert accept.mean() > 0.9
+        sample = rng.choice(len(q), 3000, replace=False)
+        o_idx, o_d2 = orc.knn5(pts, q[sample], orc.KNN_GRID)
+        o_acc = o_d2[:, 4] < 1.0
+        assert np.array_equal(accept[sample].astype(bool), o_acc)
+        assert np.array_equal(idx[sample][o_acc], o_idx[o_acc])
+        assert np.array_equal(bits(d2[sample][o_acc]), bits(o_d2[o_acc]))
+        assert (np.diff(d2[accept == 1], axis=1) >= 0).all()
