@@ -1,0 +1,377 @@
+#!/usr/bin/env python
+"""Benchmark of the scan-to-map registration hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload replay|single|dense]
+
+Workload at N = 1 (BASELINE.json configs[1]): replay of a synthetic VLP-16 trajectory (10 Hz, ground plane +
+walls + poles) through MapOptimization's per-frame hot path with a sliding local map of the last 50
+keyframes: extractSurroundingKeyFrames (transform + concatenate + VoxelGrid 0.2/0.4 + search-grid build),
+scan2MapOptimization (10 LM iterations of 5-NN + line/plane fit + normal equations + 6x6 solve) and the
+keyframe store. One STEP = one scan registered. 50 scans are registered first to fill the window
+(untimed set-up), then W warm-up scans, then K timed scans.
+
+  value : scans/s with every input cloud already resident in HBM (device pointers through the C ABI).
+  e2e   : the same through the reference-facing C++ mirror with HOST clouds: pack + H2D of the scan's five
+          clouds and D2H of the result inside the timed region.
+  N > 1 : one process per GPU (torchrun), each rank replays its own sequence (weak scaling); poses are
+          gathered with NCCL after the loop; value = all ranks' scans / max-over-ranks device time.
+  --impl reference : the CPU path (oracle restatement + the reference's vendored nanoflann) on the host cores.
+
+Timing: CUDA events on the library's own stream around every step; L2 is flushed (256 MiB memset) before each
+timed step; SM clocks and throttle reasons are sampled with nvidia-smi during the timed region.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "oracle")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+METRIC = "scan-to-map registrations/sec (VLP-16 scan vs sliding 50-keyframe local map)"
+UNIT = "scans/s"
+BENCH_WORLD = dict(n_blocks=60, n_poles=600, half_x=80, half_z=120)
+BENCH_STEP_M = 1.0   # metres travelled per scan (10 Hz at 36 km/h) so that 50 keyframes span ~50 m
+WINDOW = 50          # surroundingKeyframeSearchNum, loam_config.yaml:27
+ITERS = 10           # LM iterations per scan (exactly 10, stop_thres = 0)
+CACHE_DIR = os.environ.get("LLB200_CACHE", "/tmp/llb200_cache")
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="replay", choices=["replay"])
+    ap.add_argument("--no-l2-flush", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=20.0, help="wall budget of the cpu_baseline sample")
+    ap.add_argument("--seed", type=int, default=2)
+    return ap.parse_args()
+
+
+def headline_params(mod):
+    return mod.default_params(apply_update=1, eigen_mode=1, iter_count_thres=ITERS, stop_thres=0.0)
+
+
+def make_data(seed, n_scans):
+    from lego_loam_sr_b200 import synth
+    return synth.make_sequence(seed=seed, n_scans=n_scans, step=BENCH_STEP_M, world_kw=BENCH_WORLD, cache_dir=CACHE_DIR)
+
+
+# ----------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[0]))
+                smax.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------- GPU arm
+def frame_bytes(f):
+    return 16 * sum(len(f[k]) for k in ("corner_scan", "corner_scan_ds", "surf_last_ds", "outlier_last_ds", "surf_total_ds"))
+
+
+def run_gpu(data, device, prefill, warmup, steps, resident, flush, profile=False):
+    """Replay prefill + warmup + steps frames; time the last `steps`. Returns a dict of measurements."""
+    import torch
+    from lego_loam_sr_b200 import abi, host
+    torch.cuda.set_device(device)
+    mo = host.MapOptimization(headline_params(abi), device=device, loop_closure_enabled=True, search_num=WINDOW)
+    ext = torch.cuda.ExternalStream(mo.stream, device=device)
+    view = mo.abi_handle()
+    frames, odom = data["frames"], data["odom"]
+    total = prefill + warmup + steps
+    dev_frames = None
+    if resident:
+        keys = ("corner_scan", "corner_scan_ds", "surf_last_ds", "outlier_last_ds", "surf_total_ds")
+        dev_frames = []
+        for f in frames[:total]:
+            ts = [torch.from_numpy(np.ascontiguousarray(f[k], np.float32)).to("cuda:%d" % device) for k in keys]
+            dev_frames.append((ts, [(t.data_ptr() if t.numel() else 0, t.shape[0]) for t in ts]))
+        torch.cuda.synchronize(device)
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda:%d" % device) if flush else None
+    step_ms, wall_ms, results, poses = [], [], [], []
+    launches0 = 0
+    for k in range(total):
+        timed = k >= prefill + warmup
+        if k == prefill + warmup:
+            launches0 = mo.launch_count
+            if profile:
+                view.profile_enable(True)
+                view.profile_read()
+        if timed:
+            if flush_buf is not None:
+                flush_buf.zero_()
+                torch.cuda.synchronize(device)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter()
+            e0.record(ext)
+        if resident:
+            pose, res = mo.process_frame_dev(odom[k], dev_frames[k][1])
+        else:
+            pose, res = mo.process_frame(odom[k], frames[k], pre_downsampled=True)
+        if timed:
+            e1.record(ext)
+            e1.synchronize()
+            wall_ms.append((time.perf_counter() - t0) * 1e3)
+            step_ms.append(e0.elapsed_time(e1))
+            results.append((res.status, res.iter_num, res.sel_num, res.corner_map_ds, res.surf_map_ds))
+            poses.append(pose.copy())
+    out = dict(step_ms=step_ms, wall_ms=wall_ms, results=results, poses=np.array(poses, np.float32),
+               launches=mo.launch_count - launches0)
+    if profile:
+        out["profile"] = view.profile_read()
+        view.profile_enable(False)
+    # raw (pre-VoxelGrid) sizes of the timed steps' local maps, for the algorithmic-bytes model
+    raw_c, raw_s = [], []
+    for k in range(prefill + warmup, total):
+        win = frames[max(0, k - WINDOW):k]
+        raw_c.append(sum(len(f["corner_scan"]) for f in win))
+        raw_s.append(sum(len(f["surf_last_ds"]) + len(f["outlier_last_ds"]) for f in win))
+    out["raw_corner"], out["raw_surf"] = raw_c, raw_s
+    out["queries"] = [len(frames[k]["corner_scan_ds"]) + len(frames[k]["surf_total_ds"]) for k in range(prefill + warmup, total)]
+    out["h2d_bytes"] = [frame_bytes(frames[k]) for k in range(prefill + warmup, total)]
+    mo.close()
+    return out
+
+
+def algorithmic_bytes(cls, n_raw, n_ds, q):
+    """Algorithmic bytes ONE launch of a kernel class moves (packed 16-byte points, 4-byte keys and
+    values). n_raw / n_ds count corner + surf points together (both maps go through the same launch)."""
+    return {
+        "transform_minmax": 32 * n_raw,             # read sensor-frame cloud, write map-frame cloud
+        "voxel_keys": 24 * n_raw,                   # read 16, write key + value
+        "voxel_sort_pass": 16 * n_raw,              # read + write (key, value)
+        "voxel_reduce": 24 * n_raw + 16 * n_ds,     # read pairs, gather points, write centroids
+        "grid_keys": 24 * n_ds,
+        "grid_sort_pass": 16 * n_ds,
+        "grid_finalize": 24 * n_ds + 16 * n_ds,
+        "lm_begin": 0,
+        "lm_iter": 96 * q,                          # SURVEY.md §8d B_iter: query + five neighbours, 16 B each
+    }[cls]
+
+
+def roofline_from_profile(prof, run, peaks):
+    n = len(run["results"])
+    n_raw = sum(run["raw_corner"]) / n + sum(run["raw_surf"]) / n
+    n_ds = sum(r[3] + r[4] for r in run["results"]) / n
+    q = sum(run["queries"]) / n
+    total_ms = sum(ms for ms, _ in prof.values()) or 1e-9
+    table = {}
+    for cls, (ms, cnt) in prof.items():
+        if not cnt:
+            continue
+        per_launch_us = ms * 1e3 / cnt
+        b = algorithmic_bytes(cls, n_raw, n_ds, q)
+        table[cls] = dict(launches_per_step=cnt / n, us_per_launch=round(per_launch_us, 3), share=round(ms / total_ms, 4),
+                          gbs=round(b / (per_launch_us * 1e-6) / 1e9, 2) if per_launch_us > 0 else None)
+    top = max(table, key=lambda c: table[c]["share"])
+    peak = peaks.get("hbm_gbs", 6650.0)
+    achieved = table[top]["gbs"]
+    roof = {"kernel": top, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "frac": round(achieved / peak, 5), "traffic": None,
+            "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if "hbm_gbs" in peaks else "fallback 6650 (B200_PROFILING.md)",
+            "algorithmic_bytes_per_launch": int(algorithmic_bytes(top, n_raw, n_ds, q)),
+            "us_per_launch": table[top]["us_per_launch"], "share_of_step": table[top]["share"],
+            "note": "one scan is latency-bound (10 dependent iterations, ~7 k queries): see DESIGN.md §5 and profiles/"}
+    return roof, table, dict(n_raw=round(n_raw), n_ds=round(n_ds), queries=round(q))
+
+
+# ----------------------------------------------------------------------------------------------- CPU arm
+def run_cpu(data, prefill, warmup, steps, budget_s):
+    """The reference's CPU path (oracle restatement; k-NN = the reference's vendored nanoflann when oracle/_ref was
+    built), single thread like the reference's _run_thread (mapOptmization.cpp:175). Times `steps` scans after
+    prefill + warmup untimed ones, or as many as fit in budget_s."""
+    import orc
+    orc.build()
+    knn = "nanoflann (reference, oracle/_ref)" if orc.have_ref() else "oracle uniform grid"
+    orc.set_knn_backend(orc.KNN_NANOFLANN if orc.have_ref() else orc.KNN_GRID)
+    rp = orc.Replay(headline_params(orc), window=WINDOW)
+    frames, odom = data["frames"], data["odom"]
+    times = []
+    t_start = time.perf_counter()
+    for k in range(min(prefill + warmup + steps, len(frames))):
+        f = frames[k]
+        t0 = time.perf_counter()
+        rp.step(odom[k], f["corner_scan"], f["corner_scan_ds"], f["surf_last_ds"], f["outlier_last_ds"], f["surf_total_ds"])
+        dt = time.perf_counter() - t0
+        if k >= prefill + warmup:
+            times.append(dt)
+            if time.perf_counter() - t_start > budget_s and len(times) >= 5:
+                break
+    orc.set_knn_backend(orc.KNN_GRID)
+    rp.close()
+    return times, knn
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    prefill = WINDOW
+    n_scans = prefill + args.warmup + args.steps
+    config = {"workload": "configs[1]: synthetic VLP-16 trajectory replay, sliding local map of the last %d keyframes, "
+                          "%d LM iterations per scan" % (WINDOW, ITERS),
+              "sensor": "VLP-16 16x1800", "metres_per_scan": BENCH_STEP_M, "window_keyframes": WINDOW,
+              "lm_iterations": ITERS, "apply_update": 1, "eigen_mode": "upstream", "prefill_scans": prefill,
+              "sequences_per_gpu": 1, "l2": "flushed before every timed step (256 MiB memset)" if not args.no_l2_flush else "not flushed"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        data = make_data(args.seed, n_scans)
+        times, knn = run_cpu(data, prefill, args.warmup, args.steps, budget_s=150.0)
+        v = len(times) / sum(times)
+        sample = "%d consecutive scans of the same replay after %d untimed scans filled the window; k-NN = %s" % (len(times), prefill + args.warmup, knn)
+        line = {"impl": "reference", "metric": METRIC, "value": round(v, 3), "unit": UNIT, "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 / v, 3), "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                "p50_ms_per_scan": round(statistics.median(times) * 1e3, 3),
+                "cpu_baseline": {"value": round(v, 3), "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
+                                 "host_cores_available": host_cores(),
+                                 "why_one_core": "one registration stream is sequential; the reference runs it on one thread (mapOptmization.cpp:175)"},
+                "e2e": {"value": round(v, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    import __graft_entry__ as ge
+    if world > 1:
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if rank == 0:
+        ge.build()
+    if world > 1:
+        dist.barrier()
+    device = local_rank
+    data = make_data(args.seed + rank, n_scans)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    flush = not args.no_l2_flush
+
+    def sync_all():
+        torch.cuda.synchronize(device)
+        if world > 1:
+            dist.barrier()
+
+    sampler = ClockSampler(device)
+    # ---- e2e leg: host clouds through the C++ mirror
+    sync_all()
+    e2e = run_gpu(data, device, prefill, args.warmup, args.steps, resident=False, flush=flush)
+    # ---- value leg: inputs resident in HBM
+    sync_all()
+    sampler.start()
+    res = run_gpu(data, device, prefill, args.warmup, args.steps, resident=True, flush=flush)
+    sync_all()
+    clocks = sampler.stop()
+    # gather per-rank device times and poses (NCCL carries results only)
+    t_res = torch.tensor([sum(res["step_ms"]), sum(e2e["step_ms"])], dtype=torch.float64, device="cuda:%d" % device)
+    if world > 1:
+        dist.all_reduce(t_res, op=dist.ReduceOp.MAX)
+        poses = torch.from_numpy(res["poses"]).to("cuda:%d" % device)
+        gathered = [torch.empty_like(poses) for _ in range(world)]
+        dist.all_gather(gathered, poses)
+    total_ms, total_e2e_ms = float(t_res[0]), float(t_res[1])
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    # ---- per-kernel timing pass (rank 0): same steps with CUDA events around every launch
+    prof_run = run_gpu(data, device, prefill, args.warmup, args.steps, resident=True, flush=flush, profile=True)
+    roof, table, sizes = roofline_from_profile(prof_run["profile"], prof_run, peaks)
+    value = world * args.steps / (total_ms * 1e-3)
+    e2e_value = world * args.steps / (total_e2e_ms * 1e-3)
+    line = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(total_ms / args.steps, 4), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+            "p50_ms_per_scan": round(statistics.median(res["step_ms"]), 4),
+            "p50_ms_per_scan_e2e": round(statistics.median(e2e["step_ms"]), 4),
+            "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": int(np.mean(e2e["h2d_bytes"])),
+                    "d2h_bytes_per_step": 484, "wall_ms_per_step": round(statistics.mean(e2e["wall_ms"]), 4)},
+            "gpu_launches": int(res["launches"]), "gpu_launches_per_step": round(res["launches"] / args.steps, 2),
+            "clocks": clocks, "roofline": roof, "kernels": table, "sizes": sizes,
+            "checks": {"all_scans_optimised": all(r[0] == 0 for r in res["results"]),
+                       "iterations_per_scan": sorted(set(r[1] for r in res["results"])),
+                       "resident_equals_e2e_pose": bool(np.array_equal(res["poses"], e2e["poses"]))}}
+    if world == 1 and not args.no_cpu_baseline:
+        times, knn = run_cpu(data, prefill, 0, args.steps, budget_s=args.cpu_seconds)
+        v = len(times) / sum(times)
+        line["cpu_baseline"] = {"value": round(v, 3), "unit": UNIT, "cores": 1, "kind": "port",
+                                "sample": "%d consecutive scans of the same replay after %d untimed scans filled the window; "
+                                          "restated PCL/Eigen pieces, k-NN = %s" % (len(times), prefill, knn),
+                                "p50_ms_per_scan": round(statistics.median(times) * 1e3, 3), "host_cores_available": host_cores()}
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

@@ -101,6 +101,16 @@ class Handle:
         if rc != LL_OK:
             raise LegoLoamError(rc, "ll_create failed (is a CUDA device visible?)")
 
+    @classmethod
+    def from_raw(cls, raw_handle, params=None):
+        """Non-owning view of an ll_handle created elsewhere (e.g. inside the C++ host mirror)."""
+        self = cls.__new__(cls)
+        self._lib = load()
+        self._h = C.c_void_p(raw_handle)
+        self.params = params
+        self._borrowed = True
+        return self
+
     # -- plumbing ------------------------------------------------------------------------------
     def _check(self, rc):
         if rc != LL_OK:
@@ -108,7 +118,8 @@ class Handle:
 
     def close(self):
         if getattr(self, "_h", None):
-            self._lib.ll_destroy(self._h)
+            if not getattr(self, "_borrowed", False):
+                self._lib.ll_destroy(self._h)
             self._h = None
 
     def __del__(self):

@@ -54,6 +54,7 @@ struct MapSlot {
   uint32_t* status() const { return head_status() + max_head_tiles; }
 };
 static_assert(sizeof(MapState) <= 256, "MapState must fit the first 256 bytes of the scratch block");
+static_assert(sizeof(LMState) == 484, "bench.py reports sizeof(LMState) as the per-scan device-to-host bytes");
 
 }  // namespace
 

@@ -82,6 +82,21 @@ class MapOptimization:
             raise RuntimeError(err.value.decode("utf-8", "replace"))
         return pose, res
 
+    def process_frame_dev(self, odom6, ptrs):
+        """ptrs: five (device_pointer, count) pairs — corner_scan, corner_scan_ds, surf_last_ds, outlier_last_ds,
+        surf_total_ds — packed float4 clouds already resident on the device."""
+        odom = np.ascontiguousarray(odom6, np.float32)
+        res = abi.Result()
+        pose = np.zeros(6, np.float32)
+        err = C.create_string_buffer(512)
+        args = []
+        for p, n in ptrs:
+            args += [C.c_void_p(p), C.c_size_t(n)]
+        rc = self._lib.llh_process_frame_dev(self._mo, _vp(odom), *args, C.byref(res), _vp(pose), err, C.c_size_t(512))
+        if rc != 0:
+            raise RuntimeError(err.value.decode("utf-8", "replace"))
+        return pose, res
+
     @property
     def num_keyframes(self):
         return self._lib.llh_num_keyframes(self._mo)
@@ -90,6 +105,16 @@ class MapOptimization:
         p = np.zeros(6, np.float32)
         self._lib.llh_get_key_pose(self._mo, C.c_int(i), _vp(p))
         return p
+
+    @property
+    def last_prior(self):
+        p = np.zeros(6, np.float32)
+        self._lib.llh_get_last_prior(self._mo, _vp(p))
+        return p
+
+    def abi_handle(self):
+        """Non-owning abi.Handle view of the ll_handle the mirror drives (for inspection in tests)."""
+        return abi.Handle.from_raw(self._lib.llh_abi_handle(self._mo), self.params)
 
     @property
     def launch_count(self):

@@ -245,11 +245,18 @@ void MapOptimization::scan2MapOptimization() {  // :1572-1610
   std::memset(&lastResult, 0, sizeof(lastResult));
   lastResult.status = 1;
   std::memcpy(lastResult.pose, transformTobeMapped, sizeof(lastResult.pose));
+  std::memcpy(lastPrior, transformTobeMapped, sizeof(lastPrior));
   if (!mapBuilt_) return;  // first frame: laserCloud*FromMapDSNum are 0, the guard at :1573 fails
-  check(ll_scan2map(h_, laserCloudCornerScanDS->points.data(), laserCloudCornerScanDS->size(),
-                    laserCloudSurfTotalLastDS->points.data(), laserCloudSurfTotalLastDS->size(), sizeof(PointType),
-                    transformTobeMapped, &lastResult),
-        "ll_scan2map");
+  if (devFrame_) {
+    check(ll_scan2map_dev(h_, devFrame_->corner_scan_ds, devFrame_->n_corner_scan_ds, devFrame_->surf_total_ds,
+                          devFrame_->n_surf_total_ds, transformTobeMapped, &lastResult),
+          "ll_scan2map_dev");
+  } else {
+    check(ll_scan2map(h_, laserCloudCornerScanDS->points.data(), laserCloudCornerScanDS->size(),
+                      laserCloudSurfTotalLastDS->points.data(), laserCloudSurfTotalLastDS->size(), sizeof(PointType),
+                      transformTobeMapped, &lastResult),
+          "ll_scan2map");
+  }
   laserCloudCornerFromMapDSNum = lastResult.corner_map_ds;
   laserCloudSurfFromMapDSNum = lastResult.surf_map_ds;
   if (lastResult.status != 0) return;
@@ -295,10 +302,35 @@ void MapOptimization::saveKeyFramesAndFactor() {  // :1612-1755, pose graph = pa
   }
   // :1744-1752: corner keyframe = un-downsampled laserCloudCornerScan, surf = laserCloudSurfLastDS,
   // outlier = laserCloudOutlierLastDS. Uploaded once; the device keeps them for the whole run.
+  if (devFrame_) {
+    check(ll_add_keyframe_dev(h_, (int)cloudKeyPoses3D.size() - 1, devFrame_->corner_scan, devFrame_->n_corner_scan,
+                              devFrame_->surf_last_ds, devFrame_->n_surf_last_ds, devFrame_->outlier_last_ds,
+                              devFrame_->n_outlier_last_ds, pose),
+          "ll_add_keyframe_dev");
+    return;
+  }
   check(ll_add_keyframe(h_, (int)cloudKeyPoses3D.size() - 1, laserCloudCornerScan->points.data(),
                         laserCloudCornerScan->size(), laserCloudSurfLastDS->points.data(), laserCloudSurfLastDS->size(),
                         laserCloudOutlierLastDS->points.data(), laserCloudOutlierLastDS->size(), sizeof(PointType), pose),
         "ll_add_keyframe");
+}
+
+void MapOptimization::processFrameDevice(const float laser_odometry[6], const DeviceFrame& frame) {
+  frame_idx++;
+  devFrame_ = &frame;
+  try {
+    for (int i = 0; i < 6; ++i) transformSum[i] = laser_odometry[i];
+    transformAssociateToMap();
+    extractSurroundingKeyFrames();
+    scan2MapOptimization();
+    saveKeyFramesAndFactor();
+    correctPoses();
+    clearCloud();
+  } catch (...) {
+    devFrame_ = nullptr;
+    throw;
+  }
+  devFrame_ = nullptr;
 }
 
 void MapOptimization::correctPoses() {  // :1757-1785
@@ -426,11 +458,39 @@ int llh_process_frame(void* mo, const float odom6[6], const float* corner_scan, 
   }
 }
 
+// One frame whose (already downsampled) clouds are resident on the device as packed float4.
+int llh_process_frame_dev(void* mo, const float odom6[6], const void* d_corner_scan, size_t n_cs,
+                          const void* d_corner_scan_ds, size_t n_csd, const void* d_surf_last_ds, size_t n_sl,
+                          const void* d_outlier_last_ds, size_t n_ol, const void* d_surf_total_ds, size_t n_st,
+                          ll_result* res, float pose_out[6], char* err, size_t err_cap) {
+  MapOptimization* M = static_cast<MapOptimization*>(mo);
+  try {
+    MapOptimization::DeviceFrame f;
+    f.corner_scan = d_corner_scan; f.n_corner_scan = n_cs;
+    f.corner_scan_ds = d_corner_scan_ds; f.n_corner_scan_ds = n_csd;
+    f.surf_last_ds = d_surf_last_ds; f.n_surf_last_ds = n_sl;
+    f.outlier_last_ds = d_outlier_last_ds; f.n_outlier_last_ds = n_ol;
+    f.surf_total_ds = d_surf_total_ds; f.n_surf_total_ds = n_st;
+    M->processFrameDevice(odom6, f);
+    if (res) *res = M->lastResult;
+    if (pose_out) std::memcpy(pose_out, M->lastResult.pose, 6 * sizeof(float));
+    return 0;
+  } catch (const std::exception& e) {
+    if (err && err_cap) std::snprintf(err, err_cap, "%s", e.what());
+    return -1;
+  }
+}
+
 int llh_num_keyframes(void* mo) { return (int)static_cast<MapOptimization*>(mo)->cloudKeyPoses3D.size(); }
 
 void llh_get_key_pose(void* mo, int i, float pose6[6]) {
   const auto& p = static_cast<MapOptimization*>(mo)->cloudKeyPoses6D[(size_t)i];
   pose6[0] = p.roll; pose6[1] = p.pitch; pose6[2] = p.yaw; pose6[3] = p.x; pose6[4] = p.y; pose6[5] = p.z;
+}
+
+// transformTobeMapped as it entered the last scan2MapOptimization (the odometry-to-map prior)
+void llh_get_last_prior(void* mo, float pose6[6]) {
+  std::memcpy(pose6, static_cast<MapOptimization*>(mo)->lastPrior, 6 * sizeof(float));
 }
 
 void* llh_abi_handle(void* mo) { return static_cast<MapOptimization*>(mo)->handle(); }

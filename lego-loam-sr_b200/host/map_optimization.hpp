@@ -67,6 +67,17 @@ class MapOptimization {
   void processFrame(const AssociationOut& association, bool scan_clouds_are_downsampled = false,
                     PointCloud::Ptr corner_scan_ds = nullptr);
 
+  // Same frame body for clouds that already live in device memory as packed float4 (already downsampled):
+  // what bench.py times as "inputs resident in HBM". Only pointers and counts cross the boundary.
+  struct DeviceFrame {
+    const void* corner_scan = nullptr;     size_t n_corner_scan = 0;      // keyframe corner cloud (:1746)
+    const void* corner_scan_ds = nullptr;  size_t n_corner_scan_ds = 0;   // laserCloudCornerScanDS
+    const void* surf_last_ds = nullptr;    size_t n_surf_last_ds = 0;     // keyframe surf cloud (:1744)
+    const void* outlier_last_ds = nullptr; size_t n_outlier_last_ds = 0;  // keyframe outlier cloud (:1745)
+    const void* surf_total_ds = nullptr;   size_t n_surf_total_ds = 0;    // laserCloudSurfTotalLastDS
+  };
+  void processFrameDevice(const float laser_odometry[6], const DeviceFrame& frame);
+
   // ---- members with the reference's names (mapOptimization.h:311,327-333 and :458,:583) ----------------
   void transformAssociateToMap();
   void transformUpdate();
@@ -99,6 +110,7 @@ class MapOptimization {
   bool aLoopIsClosed = false;
   std::vector<PointType> localInfo;  // (iter_num, min_lambda, CF_mean, frame_idx), :1602-1607
   ll_result lastResult;
+  float lastPrior[6] = {0, 0, 0, 0, 0, 0};  // transformTobeMapped on entry to the last scan2MapOptimization
 
   // laserCloud{Corner,Surf}FromMapDS on request (publishKeyPosesAndFrames reads the surf one, :746-752)
   PointCloud::Ptr getLaserCloudCornerFromMapDS();
@@ -124,6 +136,7 @@ class MapOptimization {
   std::vector<int> surroundingExistingKeyPosesID_;
   std::vector<int> mapIds_;
   bool mapBuilt_ = false;
+  const DeviceFrame* devFrame_ = nullptr;  // non-null while processFrameDevice runs
 };
 
 }  // namespace lego_loam_b200

@@ -12,9 +12,9 @@
 // Iterations are separate launches on one stream (the kernel boundary is the grid-wide barrier);
 // the host never reads anything back between them.
 #pragma once
-#include "common.cuh"
-#include "fit.cuh"
-#include "map_build.cuh"
+#include "../lego-loam-sr_b200/csrc/common.cuh"
+#include "../lego-loam-sr_b200/csrc/fit.cuh"
+#include "../lego-loam-sr_b200/csrc/map_build.cuh"
 
 namespace ll {
 
@@ -106,7 +106,7 @@ __device__ inline void make_householder(float* v, int n, float& tau, float& beta
 
 // matAtA.colPivHouseholderQr().solve(matAtB) (mapOptmization.cpp:1505) for an n x n system, n <= 6.
 // Same step sequence as Eigen 3.3.7 ColPivHouseholderQR::computeInPlace + _solve_impl.
-__device__ __noinline__ void colpiv_qr_solve_n(const float* Ain /* col-major n x n */, const float* b, float* x, int n) {
+__device__ void colpiv_qr_solve_n(const float* Ain /* col-major n x n */, const float* b, float* x, int n) {
   float qr[36], hC[6], nU[6], nD[6], c[6], col[6];
   int transp[6], perm[6];
   for (int i = 0; i < n * n; ++i) qr[i] = Ain[i];
@@ -200,7 +200,7 @@ __device__ __noinline__ void colpiv_qr_solve_n(const float* Ain /* col-major n x
 // Cyclic Jacobi eigen-decomposition of a symmetric n x n matrix (n <= 6) in double: eigenvalues
 // ascending in w, eigenvectors in the columns of V (col-major n x n). Used for eigen_mode = upstream,
 // where only eigenvalues and the span of the kept eigenvectors matter (sign-free projector).
-__device__ __noinline__ void jacobi_eig_n(const float* Ain /* col-major, symmetric */, int n, double* w, double* V) {
+__device__ void jacobi_eig_n(const float* Ain /* col-major, symmetric */, int n, double* w, double* V) {
   double A[36];
   for (int i = 0; i < n * n; ++i) A[i] = (double)Ain[i];
   for (int i = 0; i < n; ++i)
@@ -253,7 +253,7 @@ __device__ __noinline__ void jacobi_eig_n(const float* Ain /* col-major, symmetr
 // Eigen-style SelfAdjointEigenSolver<Matrix<float,6,6>> (general Householder tridiagonalisation +
 // the shared QR iteration of fit.cuh) and PartialPivLU inverse, for eigen_mode = as shipped
 // (mapOptmization.cpp:1512-1530 depends on Eigen's eigenvector signs). Q col-major.
-__device__ __noinline__ void eig6_eigen_style(const float* Ain /* col-major symmetric */, float ev[6], float Q[36]) {
+__device__ void eig6_eigen_style(const float* Ain /* col-major symmetric */, float ev[6], float Q[36]) {
   const int N = 6;
   float A[36];
 #define AA(r, c) A[(c) * N + (r)]
@@ -319,7 +319,7 @@ __device__ __noinline__ void eig6_eigen_style(const float* Ain /* col-major symm
   for (int i = 0; i < N; ++i) ev[i] = diag[i] * scale;
 }
 
-__device__ __noinline__ void inverse_lu6(const float* Ain /* col-major */, float* inv /* col-major */) {
+__device__ void inverse_lu6(const float* Ain /* col-major */, float* inv /* col-major */) {
   const int N = 6;
   float lu[36];
   int piv[6];
@@ -372,7 +372,7 @@ __device__ inline void set_trig(LMState* S) {
 
 // LMOptimization after the rows are reduced (mapOptmization.cpp:1452-1455, :1502-1569), one thread.
 // sums: 21 upper-triangular AtA entries (row-major order), 6 Atb, sum|d|, count.
-__device__ __noinline__ void lm_solve(const double* sums, const LMParams& prm, LMState* S, bool stage_mode) {
+__device__ void lm_solve(const double* sums, const LMParams& prm, LMState* S, bool stage_mode) {
   const int n = (int)(sums[28] + 0.5);
   const int iter = S->iter;
   S->sel_num = n;
@@ -392,12 +392,14 @@ __device__ __noinline__ void lm_solve(const double* sums, const LMParams& prm, L
       }
     for (int r = 0; r < 6; ++r) Atb[r] = (float)sums[21 + r];
     colpiv_qr_solve_n(AtA.d, Atb, x, 6);
+    printf("A x: %g %g %g %g %g %g\n", x[0],x[1],x[2],x[3],x[4],x[5]);
     if (iter == 0) {  // :1507-1531
       float P[36];    // row-major
       int degenerate = 0;
       if (prm.fit.eigen_mode == 0) {
         float E[6], V[36], V2[36], Vinv[36];
         eig6_eigen_style(AtA.d, E, V);
+    printf("B x: %g %g %g %g %g %g E %g %g %g %g %g %g\n", x[0],x[1],x[2],x[3],x[4],x[5],E[0],E[1],E[2],E[3],E[4],E[5]);
         S->min_lambda = E[0];
         for (int i = 0; i < 36; ++i) V2[i] = V[i];
         for (int i = 5; i >= 0; --i) {  // as shipped: ascending eigenvalues walked from the largest
@@ -409,6 +411,7 @@ __device__ __noinline__ void lm_solve(const double* sums, const LMParams& prm, L
           }
         }
         inverse_lu6(V, Vinv);
+    printf("C x: %g %g %g %g %g %g\n", x[0],x[1],x[2],x[3],x[4],x[5]);
         for (int r = 0; r < 6; ++r)
           for (int c = 0; c < 6; ++c) {
             float acc = 0.f;
@@ -432,6 +435,7 @@ __device__ __noinline__ void lm_solve(const double* sums, const LMParams& prm, L
       S->is_degenerate = degenerate;
       for (int i = 0; i < 36; ++i) S->matP[i] = P[i];
     }
+    printf("D x: %g %g %g %g %g %g deg %d\n", x[0],x[1],x[2],x[3],x[4],x[5], S->is_degenerate);
     if (S->is_degenerate) {  // :1533-1537
       float x2[6];
       for (int r = 0; r < 6; ++r) {

@@ -12,9 +12,9 @@
 // Iterations are separate launches on one stream (the kernel boundary is the grid-wide barrier);
 // the host never reads anything back between them.
 #pragma once
-#include "common.cuh"
-#include "fit.cuh"
-#include "map_build.cuh"
+#include "../lego-loam-sr_b200/csrc/common.cuh"
+#include "../lego-loam-sr_b200/csrc/fit.cuh"
+#include "../lego-loam-sr_b200/csrc/map_build.cuh"
 
 namespace ll {
 
@@ -372,7 +372,7 @@ __device__ inline void set_trig(LMState* S) {
 
 // LMOptimization after the rows are reduced (mapOptmization.cpp:1452-1455, :1502-1569), one thread.
 // sums: 21 upper-triangular AtA entries (row-major order), 6 Atb, sum|d|, count.
-__device__ __noinline__ void lm_solve(const double* sums, const LMParams& prm, LMState* S, bool stage_mode) {
+__device__ void lm_solve(const double* sums, const LMParams& prm, LMState* S, bool stage_mode) {
   const int n = (int)(sums[28] + 0.5);
   const int iter = S->iter;
   S->sel_num = n;
