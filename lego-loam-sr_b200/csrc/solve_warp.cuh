@@ -1,0 +1,232 @@
+// Warp-parallel versions of the two small dense solves at the end of every LM iteration
+// (LMOptimization, mapOptmization.cpp:1502-1531). They run in the LAST block of lm_iter_kernel, i.e. on
+// the critical path between two iterations, so they are laid out for latency: lane j owns COLUMN j of
+// the 6x6 matrix in registers, every row index is a compile-time constant after unrolling, and columns
+// meet only through shuffles.
+//
+//   qr66_warp      matAtA.colPivHouseholderQr().solve(matAtB): the same step sequence as Eigen 3.3.7
+//                  ColPivHouseholderQR (pivot search, Householder reflector, trailing update, norm
+//                  down-dating, Q^T b, back substitution) — each column's arithmetic is exactly what the
+//                  sequential algorithm does to that column, so the result is bit-identical to it.
+//   jacobi6_warp   symmetric eigen-decomposition in double with the round-robin ("tournament") parallel
+//                  ordering: 5 rounds of 3 disjoint rotations per sweep. Used for eigen_mode = upstream,
+//                  where only the eigenvalues and the span of the kept eigenvectors matter.
+#pragma once
+#include <float.h>
+#include "common.cuh"
+
+namespace ll {
+
+constexpr unsigned FULL = 0xffffffffu;
+
+// All 32 lanes must call. AtA: row-major 6x6 in shared memory (symmetric), Atb: 6 floats.
+// Returns this lane's solution component x[lane] on lanes 0..5 (0 elsewhere).
+__device__ __forceinline__ float qr66_warp(const float* AtA, const float* Atb, int lane) {
+  float a[6];
+#pragma unroll
+  for (int r = 0; r < 6; ++r) a[r] = lane < 6 ? AtA[r * 6 + lane] : 0.f;
+  float s0 = 0.f;
+#pragma unroll
+  for (int r = 0; r < 6; ++r) s0 += a[r] * a[r];
+  float nD = sqrtf(s0), nU = nD;
+  float maxNorm = nU;
+#pragma unroll
+  for (int o = 4; o > 0; o >>= 1) maxNorm = fmaxf(maxNorm, __shfl_xor_sync(FULL, maxNorm, o));
+  maxNorm = __shfl_sync(FULL, maxNorm, 0);
+  const float thr = (maxNorm * FLT_EPSILON) * (maxNorm * FLT_EPSILON) / 6.f;
+  const float ndt = sqrtf(FLT_EPSILON);
+  int nonzero = 6;
+  int cur = lane < 6 ? lane : 100;  // current position of this lane's column in the pivoted order
+  float hv[6][6];                   // hv[k][r], r > k: essential part of reflector k (same on every lane)
+  float tau[6];
+  int owner[6];                     // lane (= original column) sitting at pivot position k
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    // pivot: largest updated norm among positions k..5, lowest position on ties
+    float bestv = (cur >= k && cur < 6) ? nU : -1.f;
+    int bestp = cur;
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(FULL, bestv, o);
+      const int op = __shfl_xor_sync(FULL, bestp, o);
+      if (ov > bestv || (ov == bestv && op < bestp)) { bestv = ov; bestp = op; }
+    }
+    bestv = __shfl_sync(FULL, bestv, 0);
+    bestp = __shfl_sync(FULL, bestp, 0);
+    if (nonzero == 6 && bestv * bestv < thr * (float)(6 - k)) nonzero = k;
+    if (cur == bestp) cur = k;
+    else if (cur == k) cur = bestp;
+    const int src = __ffs(__ballot_sync(FULL, cur == k)) - 1;
+    owner[k] = src;
+    // Householder reflector of the pivot column, rows k..5 (makeHouseholderInPlace)
+    float tailSq = 0.f;
+#pragma unroll
+    for (int r = k + 1; r < 6; ++r) tailSq += a[r] * a[r];
+    const float c0 = a[k];
+    float beta, tk, ess[6];
+    if (k == 5 || tailSq <= FLT_MIN) {
+      tk = 0.f;
+      beta = c0;
+#pragma unroll
+      for (int r = k + 1; r < 6; ++r) ess[r] = 0.f;
+    } else {
+      beta = sqrtf(c0 * c0 + tailSq);
+      if (c0 >= 0.f) beta = -beta;
+      const float denom = c0 - beta;
+#pragma unroll
+      for (int r = k + 1; r < 6; ++r) ess[r] = a[r] / denom;
+      tk = (beta - c0) / beta;
+    }
+    tk = __shfl_sync(FULL, tk, src);
+    beta = __shfl_sync(FULL, beta, src);
+#pragma unroll
+    for (int r = k + 1; r < 6; ++r) ess[r] = __shfl_sync(FULL, ess[r], src);
+    tau[k] = tk;
+#pragma unroll
+    for (int r = k + 1; r < 6; ++r) hv[k][r] = ess[r];
+    if (cur == k) {
+      a[k] = beta;
+#pragma unroll
+      for (int r = k + 1; r < 6; ++r) a[r] = ess[r];
+    } else if (cur > k && cur < 6) {
+      if (k < 5 && tk != 0.f) {  // applyHouseholderOnTheLeft to a trailing column
+        float tmp = 0.f;
+#pragma unroll
+        for (int r = k + 1; r < 6; ++r) tmp += ess[r] * a[r];
+        tmp += a[k];
+        a[k] -= tk * tmp;
+#pragma unroll
+        for (int r = k + 1; r < 6; ++r) a[r] -= tk * ess[r] * tmp;
+      }
+      if (nU != 0.f) {  // column-norm down-dating
+        float temp = fabsf(a[k]) / nU;
+        temp = (1.f + temp) * (1.f - temp);
+        temp = temp < 0.f ? 0.f : temp;
+        const float ratio = nU / nD;
+        const float temp2 = temp * (ratio * ratio);
+        if (temp2 <= ndt) {
+          float s = 0.f;
+#pragma unroll
+          for (int r = k + 1; r < 6; ++r) s += a[r] * a[r];
+          nD = sqrtf(s);
+          nU = nD;
+        } else {
+          nU *= sqrtf(temp);
+        }
+      }
+    }
+  }
+  // c = Q^T b (every lane computes the same six numbers)
+  float c[6];
+#pragma unroll
+  for (int r = 0; r < 6; ++r) c[r] = Atb[r];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    if (k < nonzero && tau[k] != 0.f) {
+      float tmp = 0.f;
+#pragma unroll
+      for (int r = k + 1; r < 6; ++r) tmp += hv[k][r] * c[r];
+      tmp += c[k];
+      c[k] -= tau[k] * tmp;
+#pragma unroll
+      for (int r = k + 1; r < 6; ++r) c[r] -= tau[k] * hv[k][r] * tmp;
+    }
+  }
+  // back substitution on R: R(i, j) = element i of the column at position j
+#pragma unroll
+  for (int i = 5; i >= 0; --i) {
+    float s = c[i];
+#pragma unroll
+    for (int j = i + 1; j < 6; ++j) {
+      const float rij = __shfl_sync(FULL, a[i], owner[j]);
+      if (j < nonzero) s -= rij * c[j];
+    }
+    const float rii = __shfl_sync(FULL, a[i], owner[i]);
+    if (i < nonzero) c[i] = s / rii;
+  }
+  float x = 0.f;
+#pragma unroll
+  for (int i = 0; i < 6; ++i)
+    if (cur == i && i < nonzero) x = c[i];
+  return lane < 6 ? x : 0.f;
+}
+
+// All 32 lanes must call. A: row-major symmetric 6x6 (float, shared memory).
+// On return, lane l < 6 holds eigenvalue w and its eigenvector v[0..5] (unsorted; one eigenpair per lane).
+__device__ __forceinline__ void jacobi6_warp(const float* A, int lane, double& w, double v[6]) {
+  double a[6];
+#pragma unroll
+  for (int r = 0; r < 6; ++r) {
+    a[r] = lane < 6 ? (double)A[r * 6 + lane] : 0.0;
+    v[r] = (r == lane) ? 1.0 : 0.0;
+  }
+  // round-robin schedule: 5 rounds x 3 disjoint pairs (p < q)
+  constexpr int P[5][3] = {{0, 1, 2}, {0, 3, 1}, {0, 2, 1}, {0, 1, 4}, {0, 2, 3}};
+  constexpr int Q[5][3] = {{5, 4, 3}, {4, 5, 2}, {3, 4, 5}, {2, 3, 5}, {1, 5, 4}};
+  for (int sweep = 0; sweep < 30; ++sweep) {
+    double off = 0.0, diag = 0.0;
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+      if (r < lane && lane < 6) off += a[r] * a[r];
+      if (r == lane) diag += a[r] * a[r];
+    }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+      off += __shfl_xor_sync(FULL, off, o);
+      diag += __shfl_xor_sync(FULL, diag, o);
+    }
+    off = __shfl_sync(FULL, off, 0);
+    diag = __shfl_sync(FULL, diag, 0);
+    if (off <= 1e-30 * diag || off == 0.0) break;
+#pragma unroll
+    for (int rd = 0; rd < 5; ++rd) {
+      double cs[3], sn[3];
+      int partner = lane;
+      bool is_p = false;
+      double myc = 1.0, mys = 0.0;
+#pragma unroll
+      for (int t = 0; t < 3; ++t) {
+        const int p = P[rd][t], q = Q[rd][t];
+        // lane q owns a_pq = a[p] and a_qq = a[q]; a_pp comes from lane p
+        const double app = __shfl_sync(FULL, a[p], p);
+        const double apq = __shfl_sync(FULL, a[p], q);
+        const double aqq = __shfl_sync(FULL, a[q], q);
+        double c = 1.0, s = 0.0;
+        if (apq != 0.0) {
+          const double theta = (aqq - app) / (2.0 * apq);
+          const double tt = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+          c = 1.0 / sqrt(tt * tt + 1.0);
+          s = tt * c;
+        }
+        cs[t] = c;
+        sn[t] = s;
+        if (lane == p) { partner = q; is_p = true; myc = c; mys = s; }
+        if (lane == q) { partner = p; is_p = false; myc = c; mys = s; }
+      }
+      // A <- A J and V <- V J: column p' = c p - s q, column q' = s p + c q
+#pragma unroll
+      for (int r = 0; r < 6; ++r) {
+        const double oa = __shfl_sync(FULL, a[r], partner);
+        const double ov = __shfl_sync(FULL, v[r], partner);
+        if (lane < 6) {
+          a[r] = is_p ? (myc * a[r] - mys * oa) : (mys * oa + myc * a[r]);
+          v[r] = is_p ? (myc * v[r] - mys * ov) : (mys * ov + myc * v[r]);
+        }
+      }
+      // A <- J^T A: rows p, q of every column
+#pragma unroll
+      for (int t = 0; t < 3; ++t) {
+        const int p = P[rd][t], q = Q[rd][t];
+        const double ap = a[p], aq = a[q];
+        a[p] = cs[t] * ap - sn[t] * aq;
+        a[q] = sn[t] * ap + cs[t] * aq;
+      }
+    }
+  }
+  w = 0.0;
+#pragma unroll
+  for (int r = 0; r < 6; ++r)
+    if (r == lane) w = a[r];
+}
+
+}  // namespace ll

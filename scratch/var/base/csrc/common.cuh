@@ -1,0 +1,56 @@
+// Shared declarations for the sm_100a scan-to-map kernels.
+//
+// Numerics contract: this library is compiled with -fmad=false, so every float
+// expression below is evaluated as written, IEEE round-to-nearest, with correctly rounded division
+// and square root (nvcc defaults -prec-div=true -prec-sqrt=true). That is what makes voxel
+// membership, grid cells and neighbour distances bit-identical to the reference's x86-64 build,
+// which has no FMA contraction either (LeGO-LOAM/CMakeLists.txt:9-11: -O3, no -march).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ll {
+
+constexpr int kNumSMsHint = 148;  // B200: 2 dies x 74 SMs; actual count read at ll_create
+
+// One rigid transform, the reference's cached sin/cos members
+// (updatePointAssociateToMapSinCos mapOptmization.cpp:591-604, updateTransformPointCloudSinCos :622-635).
+struct Trig {
+  float cr, sr, cp, sp, cy, sy, tx, ty, tz;
+};
+
+// pointAssociateToMap (mapOptmization.cpp:606-620) and the body of transformPointCloud (:649-664):
+// rotate about z (rz), then x (rx), then y (ry), then translate. Operation order kept.
+__device__ __forceinline__ float4 rigid_transform(const Trig& t, const float4 p) {
+  float x1 = t.cy * p.x - t.sy * p.y;
+  float y1 = t.sy * p.x + t.cy * p.y;
+  float z1 = p.z;
+  float x2 = x1;
+  float y2 = t.cr * y1 - t.sr * z1;
+  float z2 = t.sr * y1 + t.cr * z1;
+  float4 o;
+  o.x = t.cp * x2 + t.sp * z2 + t.tx;
+  o.y = y2 + t.ty;
+  o.z = -t.sp * x2 + t.cp * z2 + t.tz;
+  o.w = p.w;
+  return o;
+}
+
+// Monotone float <-> uint mapping for atomicMin / atomicMax on floats.
+__device__ __forceinline__ uint32_t float_to_ordered(float f) {
+  uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ordered_to_float(uint32_t u) {
+  return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+__device__ __forceinline__ bool finite3(const float4 p) {
+  return isfinite(p.x) && isfinite(p.y) && isfinite(p.z);
+}
+
+// Streaming 128-bit accesses: raw clouds are read once / written once per stage.
+__device__ __forceinline__ float4 ld_stream(const float4* p) { return __ldcs(p); }
+__device__ __forceinline__ void st_stream(float4* p, float4 v) { __stcs(p, v); }
+
+}  // namespace ll

@@ -17,7 +17,6 @@
 #include "common.cuh"
 #include "fit.cuh"
 #include "map_build.cuh"
-#include "solve_warp.cuh"
 
 namespace ll {
 
@@ -27,7 +26,6 @@ constexpr int LM_MIN_BLOCKS = 1;         // resident blocks per SM the register 
 constexpr int LM_NSUM = 29;              // 21 AtA + 6 Atb + sum|d| + count
 constexpr int LM_SLOT = 21;              // floats staged per query (odd => bank-conflict-free per-thread reads)
 constexpr int LM_CHUNK = LM_THREADS;     // queries a block stages per pass
-constexpr int LM_CAND_UNROLL = 4;        // candidate loads in flight per lane during the 5-NN scan
 constexpr uint32_t LM_EMPTY_D2 = 0x7f800000u;  // +inf: "no candidate"
 
 struct LMParams {
@@ -377,71 +375,17 @@ __device__ inline void set_trig(LMState* S) {
   S->rtrig.srz = S->trig.sy; S->rtrig.crz = S->trig.cy;
 }
 
-// The part of LMOptimization after matX is known (mapOptmization.cpp:1533-1569) plus the loop control of
-// scan2MapOptimization (:1578-1586). One thread. x == nullptr means "fewer than min_residuals rows": the
-// reference returns false before computing anything (:1453).
-__device__ __noinline__ void lm_apply_and_control(float* x, int n, double sum_abs_d, const float* AtA_rm,
-                                                  const float* Atb, const LMParams& prm, LMState* S, bool stage_mode) {
-  const int iter = S->iter;
-  S->sel_num = n;
-  bool pose_changed = false;
-  int ret = -1;
-  if (x) {
-    if (S->is_degenerate) {  // :1533-1537
-      float x2[6];
-      for (int r = 0; r < 6; ++r) {
-        float acc = 0.f;
-        for (int c = 0; c < 6; ++c) acc += S->matP[r * 6 + c] * x[c];
-        x2[r] = acc;
-      }
-      for (int r = 0; r < 6; ++r) x[r] = x2[r];
-    }
-    if (prm.apply_update) {  // :1540-1545
-      for (int r = 0; r < 6; ++r) S->pose[r] += x[r];
-      pose_changed = true;
-    }
-    const double r0 = (double)(x[0] * 57.29578f), r1 = (double)(x[1] * 57.29578f), r2 = (double)(x[2] * 57.29578f);
-    const float deltaR = (float)sqrt(r0 * r0 + r1 * r1 + r2 * r2);
-    const double t0 = (double)(x[3] * 100.f), t1 = (double)(x[4] * 100.f), t2 = (double)(x[5] * 100.f);
-    const float deltaT = (float)sqrt(t0 * t0 + t1 * t1 + t2 * t2);
-    S->cf_mean = (float)sum_abs_d / (float)n;  // :1555-1568
-    for (int r = 0; r < 6; ++r) S->last_x[r] = x[r];
-    for (int i = 0; i < 36; ++i) S->AtA[i] = AtA_rm[i];
-    for (int r = 0; r < 6; ++r) S->Atb[r] = Atb[r];
-    S->deltaR = deltaR;
-    S->deltaT = deltaT;
-    ret = (deltaR < prm.stop_thres && deltaT < prm.stop_thres) ? 1 : 0;
-  }
-  S->lm_ret = ret;
-  if (stage_mode) {
-    if (pose_changed) set_trig(S);
-    return;
-  }
-  const int executed = iter + 1;
-  if (ret == 1) {
-    S->converged = 1;
-    S->iter_num = executed;
-    S->done = 1;
-  } else if (executed >= prm.iter_count_thres) {
-    S->iter_num = executed;
-    S->done = 1;
-  } else if (!pose_changed) {
-    // Nothing can change any more: the pose is not updated (as shipped, or fewer than 50 residuals), so
-    // every remaining iteration would recompute exactly the same numbers and fall through to the
-    // threshold. Report what the reference reports without replaying them.
-    S->iter_num = prm.iter_count_thres;
-    S->done = 1;
-  }
-  S->iter = executed;
-  if (pose_changed) set_trig(S);
-}
-
 // LMOptimization after the rows are reduced (mapOptmization.cpp:1452-1455, :1502-1569), one thread.
 // sums: 21 upper-triangular AtA entries (row-major order), 6 Atb, sum|d|, count.
 __device__ __noinline__ void lm_solve(const double* sums, const LMParams& prm, LMState* S, bool stage_mode) {
   const int n = (int)(sums[28] + 0.5);
   const int iter = S->iter;
-  if (n >= prm.min_residuals) {
+  S->sel_num = n;
+  bool pose_changed = false;
+  int ret;
+  if (n < prm.min_residuals) {
+    ret = -1;  // "return false" before anything is computed (:1453)
+  } else {
     Mat6 AtA;
     float Atb[6], x[6];
     int k = 0;
@@ -493,13 +437,55 @@ __device__ __noinline__ void lm_solve(const double* sums, const LMParams& prm, L
       S->is_degenerate = degenerate;
       for (int i = 0; i < 36; ++i) S->matP[i] = P[i];
     }
-    float AtA_rm[36];
+    if (S->is_degenerate) {  // :1533-1537
+      float x2[6];
+      for (int r = 0; r < 6; ++r) {
+        float acc = 0.f;
+        for (int c = 0; c < 6; ++c) acc += S->matP[r * 6 + c] * x[c];
+        x2[r] = acc;
+      }
+      for (int r = 0; r < 6; ++r) x[r] = x2[r];
+    }
+    if (prm.apply_update) {  // :1540-1545
+      for (int r = 0; r < 6; ++r) S->pose[r] += x[r];
+      pose_changed = true;
+    }
+    const double r0 = (double)(x[0] * 57.29578f), r1 = (double)(x[1] * 57.29578f), r2 = (double)(x[2] * 57.29578f);
+    const float deltaR = (float)sqrt(r0 * r0 + r1 * r1 + r2 * r2);
+    const double t0 = (double)(x[3] * 100.f), t1 = (double)(x[4] * 100.f), t2 = (double)(x[5] * 100.f);
+    const float deltaT = (float)sqrt(t0 * t0 + t1 * t1 + t2 * t2);
+    S->cf_mean = (float)sums[27] / (float)n;  // :1555-1568
+    for (int r = 0; r < 6; ++r) S->last_x[r] = x[r];
     for (int r = 0; r < 6; ++r)
-      for (int c = 0; c < 6; ++c) AtA_rm[r * 6 + c] = AtA(r, c);
-    lm_apply_and_control(x, n, sums[27], AtA_rm, Atb, prm, S, stage_mode);
+      for (int c = 0; c < 6; ++c) S->AtA[r * 6 + c] = AtA(r, c);
+    for (int r = 0; r < 6; ++r) S->Atb[r] = Atb[r];
+    S->deltaR = deltaR;
+    S->deltaT = deltaT;
+    ret = (deltaR < prm.stop_thres && deltaT < prm.stop_thres) ? 1 : 0;
+  }
+  S->lm_ret = ret;
+  if (stage_mode) {
+    if (pose_changed) set_trig(S);
     return;
   }
-  lm_apply_and_control(nullptr, n, sums[27], nullptr, nullptr, prm, S, stage_mode);
+  // loop control of scan2MapOptimization (:1578-1586)
+  const int executed = iter + 1;
+  if (ret == 1) {
+    S->converged = 1;
+    S->iter_num = executed;
+    S->done = 1;
+  } else if (executed >= prm.iter_count_thres) {
+    S->iter_num = executed;
+    S->done = 1;
+  } else if (!pose_changed) {
+    // Nothing can change any more: the pose is not updated (as shipped, or fewer than 50 residuals), so
+    // every remaining iteration would recompute exactly the same numbers and fall through to the
+    // threshold. Report what the reference reports without replaying them.
+    S->iter_num = prm.iter_count_thres;
+    S->done = 1;
+  }
+  S->iter = executed;
+  if (pose_changed) set_trig(S);
 }
 
 // ---- warp-level 5-NN --------------------------------------------------------------------------------------
@@ -554,46 +540,31 @@ __device__ __forceinline__ Knn5 warp_knn5(const float4* __restrict__ sorted, con
 #pragma unroll
   for (int k = 0; k < 5; ++k) { ld[k] = LM_EMPTY_D2; li[k] = 0xffffffffu; lp[k] = 0xffffffffu; }
   const uint32_t max_bits = __float_as_uint(max_sq_dist);
-  for (int j0 = lane; j0 < total; j0 += 32 * LM_CAND_UNROLL) {
-    // up to LM_CAND_UNROLL candidates per lane are fetched before any is consumed (one load round trip)
-    int srcs[LM_CAND_UNROLL];
-    float4 ms[LM_CAND_UNROLL];
+  for (int j = lane; j < total; j += 32) {
+    int base = 0, src = 0;
 #pragma unroll
-    for (int u = 0; u < LM_CAND_UNROLL; ++u) {
-      const int j = j0 + 32 * u;
-      int base = 0, src = -1;
-#pragma unroll
-      for (int r = 0; r < 9; ++r) {
-        if (j >= base && j < base + rc[r]) src = rs[r] + (j - base);
-        base += rc[r];
-      }
-      srcs[u] = src;  // -1 when j >= total
+    for (int r = 0; r < 9; ++r) {
+      if (j >= base && j < base + rc[r]) src = rs[r] + (j - base);
+      base += rc[r];
     }
+    const float4 m = __ldg(&sorted[src]);
+    // L2_Simple_Adaptor::evalMetric (nanoflann.hpp:431-439): ((dx^2) + dy^2) + dz^2, no contraction
+    float df = sx - m.x;
+    float d = df * df;
+    df = sy - m.y;
+    d += df * df;
+    df = sz - m.z;
+    d += df * df;
+    const uint32_t db = __float_as_uint(d);
+    const uint32_t ib = __float_as_uint(m.w);
+    if (db < max_bits && pair_less(db, ib, ld[4], li[4])) {
+      ld[4] = db; li[4] = ib; lp[4] = (uint32_t)src;
 #pragma unroll
-    for (int u = 0; u < LM_CAND_UNROLL; ++u)
-      ms[u] = srcs[u] >= 0 ? __ldg(&sorted[srcs[u]]) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-    for (int u = 0; u < LM_CAND_UNROLL; ++u) {
-      if (srcs[u] < 0) continue;
-      const float4 m = ms[u];
-      // L2_Simple_Adaptor::evalMetric (nanoflann.hpp:431-439): ((dx^2) + dy^2) + dz^2, no contraction
-      float df = sx - m.x;
-      float d = df * df;
-      df = sy - m.y;
-      d += df * df;
-      df = sz - m.z;
-      d += df * df;
-      const uint32_t db = __float_as_uint(d);
-      const uint32_t ib = __float_as_uint(m.w);
-      if (db < max_bits && pair_less(db, ib, ld[4], li[4])) {
-        ld[4] = db; li[4] = ib; lp[4] = (uint32_t)srcs[u];
-#pragma unroll
-        for (int k = 4; k > 0; --k) {
-          if (pair_less(ld[k], li[k], ld[k - 1], li[k - 1])) {
-            uint32_t t = ld[k]; ld[k] = ld[k - 1]; ld[k - 1] = t;
-            t = li[k]; li[k] = li[k - 1]; li[k - 1] = t;
-            t = lp[k]; lp[k] = lp[k - 1]; lp[k - 1] = t;
-          }
+      for (int k = 4; k > 0; --k) {
+        if (pair_less(ld[k], li[k], ld[k - 1], li[k - 1])) {
+          uint32_t t = ld[k]; ld[k] = ld[k - 1]; ld[k - 1] = t;
+          t = li[k]; li[k] = li[k - 1]; li[k - 1] = t;
+          t = lp[k]; lp[k] = lp[k - 1]; lp[k - 1] = t;
         }
       }
     }
@@ -633,161 +604,12 @@ __device__ __forceinline__ float lm_term(const float sv[8], float one, int k) {
   return one;
 }
 
-// LMOptimization on the reduced sums, executed by the whole (last) block. sums = s_red[0..28] in shared
-// memory; s_red must provide at least 64 + 64 doubles. For eigen_mode = upstream the 6x6 solve runs on warp 0
-// and, at iteration 0, the eigen-decomposition runs concurrently on warp 1 (solve_warp.cuh); everything
-// else (as shipped mode, fewer than min_residuals rows) takes the single-thread path above.
-__device__ void lm_solve_block(double* s_red, const LMParams& prm, LMState* S, bool stage_mode) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int n = (int)(s_red[28] + 0.5);
-  if (prm.fit.eigen_mode == 0 || n < prm.min_residuals) {
-    if (tid == 0) lm_solve(s_red, prm, S, stage_mode);
-    return;
-  }
-  float* sh = reinterpret_cast<float*>(s_red + 64);
-  float* AtA = sh;        // [36] row-major
-  float* Atb = sh + 36;   // [6]
-  float* xs = sh + 42;    // [6]
-  float* Ps = sh + 48;    // [36] row-major
-  float* misc = sh + 84;  // [0] = is_degenerate (as float), [1] = min_lambda
-  const int iter = S->iter;
-  if (tid < 36) {
-    const int r = tid / 6, c = tid % 6, i = r < c ? r : c, j = r < c ? c : r;
-    AtA[tid] = (float)s_red[i * 6 - (i * (i - 1)) / 2 + (j - i)];
-  } else if (tid < 42) {
-    Atb[tid - 36] = (float)s_red[21 + tid - 36];
-  }
-  __syncthreads();
-  if (warp == 0) {
-    const float x = qr66_warp(AtA, Atb, lane);  // :1505
-    if (lane < 6) xs[lane] = x;
-  } else if (warp == 1 && iter == 0) {  // :1507-1531, upstream semantics
-    double w, v[6];
-    jacobi6_warp(AtA, lane, w, v);
-    const bool below = lane < 6 && (float)w < prm.eig_thresh;
-    const unsigned mb = __ballot_sync(FULL, below);
-    double wmin = lane < 6 ? w : 1.7976931348623157e308;
-#pragma unroll
-    for (int o = 4; o > 0; o >>= 1) wmin = fmin(wmin, __shfl_xor_sync(FULL, wmin, o));
-    if (lane == 0) {
-      misc[0] = mb ? 1.f : 0.f;
-      misc[1] = (float)wmin;
-    }
-    // matP = sum over kept eigenvectors v v^T (identity when nothing is dropped)
-#pragma unroll
-    for (int r = 0; r < 6; ++r)
-#pragma unroll
-      for (int c = 0; c < 6; ++c) {
-        float pv = r == c ? 1.f : 0.f;
-        if (mb) {
-          double t = (lane < 6 && !below) ? v[r] * v[c] : 0.0;
-#pragma unroll
-          for (int o = 4; o > 0; o >>= 1) t += __shfl_xor_sync(FULL, t, o);
-          pv = (float)t;
-        }
-        if (lane == 0) Ps[r * 6 + c] = pv;
-      }
-  }
-  __syncthreads();
-  if (warp != 0) return;
-  // ---- the rest of LMOptimization (:1533-1569) and the loop control (:1578-1586) on warp 0: lane r owns
-  //      component r of matX / the pose; lanes 0..2 also own one angle's sin / cos each
-  int degenerate;
-  if (iter == 0) {
-    degenerate = misc[0] != 0.f ? 1 : 0;
-    if (lane == 0) {
-      S->is_degenerate = degenerate;
-      S->min_lambda = misc[1];
-    }
-    if (lane < 6)
-      for (int c = 0; c < 6; ++c) S->matP[lane * 6 + c] = Ps[lane * 6 + c];
-  } else {
-    degenerate = S->is_degenerate;
-    if (degenerate && lane < 6)
-      for (int c = 0; c < 6; ++c) Ps[lane * 6 + c] = S->matP[lane * 6 + c];
-  }
-  float x = lane < 6 ? xs[lane] : 0.f;
-  if (degenerate && lane < 6) {  // matX = matP * matX2
-    float acc = 0.f;
-    for (int c = 0; c < 6; ++c) acc += Ps[lane * 6 + c] * xs[c];
-    x = acc;
-  }
-  float pose = lane < 6 ? S->pose[lane] : 0.f;
-  if (prm.apply_update && lane < 6) {  // :1540-1545
-    pose += x;
-    S->pose[lane] = pose;
-  }
-  if (lane < 6) {
-    S->last_x[lane] = x;
-    S->Atb[lane] = Atb[lane];
-    for (int c = 0; c < 6; ++c) S->AtA[lane * 6 + c] = AtA[lane * 6 + c];
-  }
-  // deltaR / deltaT (:1547-1552): pcl::rad2deg(float) then pow(., 2) and sqrt in double
-  const float scaled = lane < 3 ? x * 57.29578f : x * 100.f;
-  const double sq = (double)scaled * (double)scaled;
-  const double q0 = __shfl_sync(FULL, sq, 0), q1 = __shfl_sync(FULL, sq, 1), q2 = __shfl_sync(FULL, sq, 2);
-  const double q3 = __shfl_sync(FULL, sq, 3), q4 = __shfl_sync(FULL, sq, 4), q5 = __shfl_sync(FULL, sq, 5);
-  const float deltaR = (float)sqrt(q0 + q1 + q2);
-  const float deltaT = (float)sqrt(q3 + q4 + q5);
-  const int ret = (deltaR < prm.stop_thres && deltaT < prm.stop_thres) ? 1 : 0;
-  const bool pose_changed = prm.apply_update != 0;
-  if (pose_changed) {  // updatePointAssociateToMapSinCos (:591-604) for the next iteration
-    if (lane < 3) {
-      double sn, cs;
-      sincos((double)pose, &sn, &cs);
-      const float fs = (float)sn, fc = (float)cs;
-      if (lane == 0) { S->trig.cr = fc; S->trig.sr = fs; S->rtrig.crx = fc; S->rtrig.srx = fs; }
-      if (lane == 1) { S->trig.cp = fc; S->trig.sp = fs; S->rtrig.cry = fc; S->rtrig.sry = fs; }
-      if (lane == 2) { S->trig.cy = fc; S->trig.sy = fs; S->rtrig.crz = fc; S->rtrig.srz = fs; }
-    } else if (lane == 3) {
-      S->trig.tx = pose;
-    } else if (lane == 4) {
-      S->trig.ty = pose;
-    } else if (lane == 5) {
-      S->trig.tz = pose;
-    }
-  }
-  if (lane == 0) {
-    S->sel_num = n;
-    S->cf_mean = (float)s_red[27] / (float)n;  // :1555-1568
-    S->deltaR = deltaR;
-    S->deltaT = deltaT;
-    S->lm_ret = ret;
-    if (!stage_mode) {
-      const int executed = iter + 1;
-      if (ret == 1) {
-        S->converged = 1;
-        S->iter_num = executed;
-        S->done = 1;
-      } else if (executed >= prm.iter_count_thres) {
-        S->iter_num = executed;
-        S->done = 1;
-      } else if (!pose_changed) {  // nothing can change any more (see lm_apply_and_control)
-        S->iter_num = prm.iter_count_thres;
-        S->done = 1;
-      }
-      S->iter = executed;
-    }
-  }
-}
-
 // Sum the block partials in a fixed order (deterministic regardless of which block arrives last).
 __device__ void reduce_partials_and_solve(const float* partials, int nblocks, const LMParams& prm, LMState* S,
                                           bool stage_mode, double* s_red /* [nwarps][32] shared */) {
   const int lane = threadIdx.x & 31, sub = threadIdx.x >> 5, nsub = blockDim.x >> 5;
   double acc = 0.0;
-  int b = sub;
-  for (; b + 3 * nsub < nblocks; b += 4 * nsub) {  // four loads in flight, added in the same order as a plain loop
-    const float v0 = __ldcg(&partials[b * 32 + lane]);
-    const float v1 = __ldcg(&partials[(b + nsub) * 32 + lane]);
-    const float v2 = __ldcg(&partials[(b + 2 * nsub) * 32 + lane]);
-    const float v3 = __ldcg(&partials[(b + 3 * nsub) * 32 + lane]);
-    acc += (double)v0;
-    acc += (double)v1;
-    acc += (double)v2;
-    acc += (double)v3;
-  }
-  for (; b < nblocks; b += nsub) acc += (double)__ldcg(&partials[b * 32 + lane]);
+  for (int b = sub; b < nblocks; b += nsub) acc += (double)__ldcg(&partials[b * 32 + lane]);
   s_red[sub * 32 + lane] = acc;
   __syncthreads();
   if (threadIdx.x < 32) {
@@ -796,7 +618,7 @@ __device__ void reduce_partials_and_solve(const float* partials, int nblocks, co
     s_red[lane] = t;
   }
   __syncthreads();
-  lm_solve_block(s_red, prm, S, stage_mode);
+  if (threadIdx.x == 0) lm_solve(s_red, prm, S, stage_mode);
 }
 
 // One LM iteration. Each block owns a contiguous chunk of the query list (corner queries first, then surf):
@@ -814,13 +636,6 @@ __global__ void __launch_bounds__(LM_THREADS, LM_MIN_BLOCKS) lm_iter_kernel(cons
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const Trig trig = S->trig;
   const RotTrig rt = S->rtrig;
-  GridGeom geom[2];
-#pragma unroll
-  for (int m = 0; m < 2; ++m) {
-    const MapState* ms = A.mst[m];
-    geom[m].ox = ms->gox; geom[m].oy = ms->goy; geom[m].oz = ms->goz;
-    geom[m].dx = ms->gdx; geom[m].dy = ms->gdy; geom[m].dz = ms->gdz;
-  }
   const int nq = A.nq[0] + A.nq[1];
   const int per = (nq + gridDim.x - 1) / gridDim.x;
   const int q_begin = min(nq, (int)blockIdx.x * per), q_end = min(nq, q_begin + per);
@@ -828,21 +643,17 @@ __global__ void __launch_bounds__(LM_THREADS, LM_MIN_BLOCKS) lm_iter_kernel(cons
   for (int c0 = q_begin; c0 < q_end; c0 += LM_CHUNK) {
     const int cn = min(LM_CHUNK, q_end - c0);
     // ---- phase 1: k-NN, one warp per query
-    float4 p_next = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (warp < cn) {
-      const int q0 = c0 + warp;
-      p_next = __ldg(q0 < A.nq[0] ? &A.q[0][q0] : &A.q[1][q0 - A.nq[0]]);
-    }
     for (int i = warp; i < cn; i += LM_WARPS) {
       const int qi = c0 + i;
       const int m = qi < A.nq[0] ? 0 : 1;
-      const float4 p = p_next;
-      if (i + LM_WARPS < cn) {  // the next query of this warp is in flight while this one is searched
-        const int qn = qi + LM_WARPS;
-        p_next = __ldg(qn < A.nq[0] ? &A.q[0][qn] : &A.q[1][qn - A.nq[0]]);
-      }
+      const float4 p = __ldg(&A.q[m][m ? qi - A.nq[0] : qi]);
       const float4 sel = (A.mode == 2) ? p : rigid_transform(trig, p);
-      const GridGeom g = m ? geom[1] : geom[0];
+      GridGeom g;
+      {
+        const MapState* ms = A.mst[m];
+        g.ox = ms->gox; g.oy = ms->goy; g.oz = ms->goz;
+        g.dx = ms->gdx; g.dy = ms->gdy; g.dz = ms->gdz;
+      }
       const Knn5 nn = warp_knn5(A.sorted[m], A.cells[m], g, sel.x, sel.y, sel.z, A.prm.fit.max_sq_dist, lane);
       float* slot = &s_slot[i * LM_SLOT];
       if (lane < 5) {

@@ -225,35 +225,18 @@ __global__ void __launch_bounds__(MB_THREADS) voxel_keys_kernel(const __grid_con
 }
 
 // Sorted (voxel, original index) pairs -> one centroid per voxel, written in ascending voxel index.
-// Per tile of 1024 sorted pairs:
-//   1. every thread gathers the points of its four pairs into shared memory (independent loads: one
-//      round trip) and flags segment heads (first pair of a voxel);
-//   2. block scan + single-word decoupled look-back give every head its output slot;
-//   3. the head's thread adds its segment up IN SORTED ORDER (= ascending original index, the canonical
-//      order: the float sum is the same sequence of additions the CPU performs) from shared memory —
-//      the segment length is known from the next head, so the loop is unrolled with the loads ahead of
-//      the adds; a segment that runs past the tile continues from global memory.
+// A tile flags segment heads, a block scan + single-word decoupled look-back gives every head its
+// output slot, and the head's thread walks its segment accumulating in sorted (= original) order.
 __global__ void __launch_bounds__(MB_THREADS) voxel_reduce_kernel(const __grid_constant__ MapBatch B) {
   const MapBuffers& M = B.m[blockIdx.y];
   if (!M.downsample) return;
   const SortProblem& S = B.sort[blockIdx.y];
   MapState* st = M.st;
   const int n = M.n_raw;
-  __shared__ float4 s_pts[MB_TILE];
-  __shared__ uint32_t s_val[MB_TILE];
-  __shared__ int s_head_pos[MB_TILE + 1];
   __shared__ int s_tile;
   __shared__ uint32_t s_warp_sum[MB_THREADS / 32];
   __shared__ uint32_t s_tile_excl;
-  __shared__ int s_sent_pos;  // local position of the first sentinel-keyed (non-finite) pair, if any
-  __shared__ float4 s_cross_sum;
-  __shared__ int s_cross, s_cross_cnt, s_first_miss;
-  __shared__ uint32_t s_cross_slot, s_cross_key;
-  if (threadIdx.x == 0) {
-    s_tile = (int)atomicAdd(&st->head_ticket, 1u);
-    s_sent_pos = MB_TILE;
-    s_cross = 0;
-  }
+  if (threadIdx.x == 0) s_tile = (int)atomicAdd(&st->head_ticket, 1u);
   __syncthreads();
   const int tile = s_tile;
   const int base = tile * MB_TILE;
@@ -264,30 +247,16 @@ __global__ void __launch_bounds__(MB_THREADS) voxel_reduce_kernel(const __grid_c
   const VoxelMeta v = voxel_meta(st, M.inv_leaf);
   const uint32_t sentinel = v.overflow ? (uint32_t)n : (uint32_t)v.total;
 
-  const int l0 = threadIdx.x * MB_ITEMS;  // local index of this thread's first pair
-  const int i0 = base + l0;
-  uint32_t key[MB_ITEMS], val[MB_ITEMS];
+  const int i0 = base + threadIdx.x * MB_ITEMS;
+  uint32_t key[MB_ITEMS];
   bool head[MB_ITEMS];
   uint32_t prev = (i0 > 0 && i0 < n) ? keys[i0 - 1] : 0xffffffffu;
-#pragma unroll
-  for (int k = 0; k < MB_ITEMS; ++k) {
-    const int i = i0 + k;
-    key[k] = (i < n) ? keys[i] : 0xffffffffu;
-    val[k] = (i < n) ? vals[i] : 0u;
-  }
-#pragma unroll
-  for (int k = 0; k < MB_ITEMS; ++k) {  // gather: four independent loads in flight per thread
-    const int i = i0 + k;
-    s_pts[l0 + k] = (i < n) ? M.raw[val[k]] : make_float4(0.f, 0.f, 0.f, 0.f);
-    s_val[l0 + k] = val[k];
-  }
   uint32_t cnt = 0;
 #pragma unroll
   for (int k = 0; k < MB_ITEMS; ++k) {
     const int i = i0 + k;
-    const bool boundary = (i < n) && (i == 0 || key[k] != prev);
-    head[k] = boundary && key[k] != sentinel;
-    if (boundary && key[k] == sentinel) s_sent_pos = l0 + k;  // at most one such pair per tile (sorted)
+    key[k] = (i < n) ? keys[i] : 0xffffffffu;
+    head[k] = (i < n) && key[k] != sentinel && (i == 0 || key[k] != prev);
     prev = key[k];
     cnt += head[k] ? 1u : 0u;
   }
@@ -308,127 +277,45 @@ __global__ void __launch_bounds__(MB_THREADS) voxel_reduce_kernel(const __grid_c
     if (w < warp) warp_off += c;
     tile_total += c;
   }
-  if (warp == 0) {  // warp-wide decoupled look-back: 32 predecessor tiles per round trip
+  if (threadIdx.x == 0) {
     volatile uint32_t* status = M.head_status;
     uint32_t excl = 0;
     if (tile == 0) {
-      if (lane == 0) status[0] = tile_total | RS_FLAG_PREFIX;
+      status[0] = tile_total | RS_FLAG_PREFIX;
     } else {
-      if (lane == 0) status[tile] = tile_total | RS_FLAG_AGG;
+      status[tile] = tile_total | RS_FLAG_AGG;
       int j = tile - 1;
-      bool done = false;
-      while (!done) {
-        const int idx = j - lane;
-        uint32_t w = 2u << 30;  // RS_FLAG_PREFIX: virtual empty prefix before tile 0
-        if (idx >= 0) w = status[idx];
-        const unsigned pre = __ballot_sync(0xffffffffu, (w & RS_FLAG_PREFIX) != 0);
-        const unsigned nrd = __ballot_sync(0xffffffffu, (w & (RS_FLAG_PREFIX | RS_FLAG_AGG)) == 0);
-        const int first_pre = pre ? __ffs(pre) - 1 : 32;
-        const int first_nrd = nrd ? __ffs(nrd) - 1 : 32;
-        done = first_pre < first_nrd;
-        const int stop = done ? first_pre + 1 : first_nrd;  // lanes [0, stop) contribute
-        uint32_t v = lane < stop ? (w & RS_VALUE_MASK) : 0u;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        excl += v;
-        j -= stop;
+      while (true) {
+        const uint32_t w = status[j];
+        if (w & RS_FLAG_PREFIX) { excl += w & RS_VALUE_MASK; break; }
+        else if (w & RS_FLAG_AGG) { excl += w & RS_VALUE_MASK; --j; }
       }
-      if (lane == 0) status[tile] = (excl + tile_total) | RS_FLAG_PREFIX;
+      status[tile] = (excl + tile_total) | RS_FLAG_PREFIX;
     }
-    if (lane == 0) {
-      s_tile_excl = excl;
-      if (base + MB_TILE >= n) st->n_ds = (int)(excl + tile_total);  // last tile: laserCloud*FromMapDSNum
-    }
+    s_tile_excl = excl;
+    if (base + MB_TILE >= n) st->n_ds = (int)(excl + tile_total);  // last tile: laserCloud*FromMapDSNum
   }
-  // local head positions, so that a head knows where its segment ends (the next head, or the tile end)
-  const uint32_t local0 = warp_off + (incl - cnt);
-  {
-    uint32_t ls = local0;
-#pragma unroll
-    for (int k = 0; k < MB_ITEMS; ++k)
-      if (head[k]) s_head_pos[ls++] = l0 + k;
-  }
-  const int tile_n = min(MB_TILE, n - base);
-  if (threadIdx.x == 0) s_head_pos[tile_total] = tile_n;
   __syncthreads();
-  uint32_t ls = local0;
-  const uint32_t slot0 = s_tile_excl;
+  uint32_t slot = s_tile_excl + warp_off + (incl - cnt);
 #pragma unroll
   for (int k = 0; k < MB_ITEMS; ++k) {
-    if (!head[k]) continue;
-    const int beg = l0 + k;
-    const int end = min(s_head_pos[ls + 1], s_sent_pos);  // sentinel-keyed pairs only ever trail the last head
-    const uint32_t slot = slot0 + ls;
-    ++ls;
-    float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
-    int c = 0;
-    int j = beg;
-    const uint32_t kk = key[k];
-    for (; j + 4 <= end; j += 4) {  // loads first, then the four dependent adds per component
-      const float4 p0 = s_pts[j], p1 = s_pts[j + 1], p2 = s_pts[j + 2], p3 = s_pts[j + 3];
-      sx += p0.x; sy += p0.y; sz += p0.z; si += p0.w;
-      sx += p1.x; sy += p1.y; sz += p1.z; si += p1.w;
-      sx += p2.x; sy += p2.y; sz += p2.z; si += p2.w;
-      sx += p3.x; sy += p3.y; sz += p3.z; si += p3.w;
-    }
-    for (; j < end; ++j) {
-      const float4 p = s_pts[j];
-      sx += p.x; sy += p.y; sz += p.z; si += p.w;
-    }
-    c = end - beg;
-    if (M.member)
-      for (int t = beg; t < end; ++t) M.member[s_val[t]] = (int)slot;
-    if (end == tile_n && s_sent_pos >= tile_n && base + tile_n < n) {
-      // The segment may continue in the following tiles: park the running sums; the whole block finishes it below.
-      s_cross_sum = make_float4(sx, sy, sz, si);
-      s_cross_cnt = c;
-      s_cross_slot = slot;
-      s_cross_key = kk;
-      s_cross = 1;
-      continue;
-    }
-    const float fc = (float)c;
-    M.ds[slot] = make_float4(sx / fc, sy / fc, sz / fc, si / fc);
-  }
-  __syncthreads();
-  if (!s_cross) return;
-  // Continuation of the one segment that crosses the tile end. The block finds its end and gathers its points
-  // MB_THREADS pairs at a time (coalesced key reads, independent gathers); thread 0 keeps adding in sorted order.
-  float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
-  int c = 0;
-  if (threadIdx.x == 0) {
-    sx = s_cross_sum.x; sy = s_cross_sum.y; sz = s_cross_sum.z; si = s_cross_sum.w;
-    c = s_cross_cnt;
-  }
-  const uint32_t ck = s_cross_key;
-  const uint32_t cslot = s_cross_slot;
-  for (int g0 = base + tile_n; g0 < n; g0 += MB_THREADS) {
-    const int g = g0 + threadIdx.x;
-    const bool match = g < n && keys[g] == ck;
-    if (threadIdx.x == 0) s_first_miss = MB_THREADS;
-    __syncthreads();
-    if (!match) atomicMin(&s_first_miss, (int)threadIdx.x);
-    __syncthreads();
-    const int m = s_first_miss;  // pairs [g0, g0 + m) still belong to the segment
-    if ((int)threadIdx.x < m) {
-      const uint32_t src = vals[g];
-      s_pts[threadIdx.x] = M.raw[src];
-      if (M.member) M.member[src] = (int)cslot;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      for (int t = 0; t < m; ++t) {
-        const float4 p = s_pts[t];
+    if (head[k]) {
+      float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
+      int j = i0 + k;
+      const uint32_t kk = key[k];
+      int c = 0;
+      while (j < n && keys[j] == kk) {
+        const uint32_t src = vals[j];
+        const float4 p = M.raw[src];
         sx += p.x; sy += p.y; sz += p.z; si += p.w;
+        if (M.member) M.member[src] = (int)slot;
+        ++j;
+        ++c;
       }
-      c += m;
+      const float fc = (float)c;
+      M.ds[slot] = make_float4(sx / fc, sy / fc, sz / fc, si / fc);
+      ++slot;
     }
-    __syncthreads();
-    if (m < MB_THREADS) break;
-  }
-  if (threadIdx.x == 0) {
-    const float fc = (float)c;
-    M.ds[cslot] = make_float4(sx / fc, sy / fc, sz / fc, si / fc);
   }
 }
 

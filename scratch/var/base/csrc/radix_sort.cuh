@@ -24,7 +24,6 @@ constexpr int RS_ITEMS = 8;
 constexpr int RS_TILE = RS_THREADS * RS_ITEMS;  // 2048 pairs per tile
 constexpr int RS_RADIX = 256;
 constexpr int RS_MAX_PASSES = 4;
-constexpr int RS_LOOKBACK = 8;  // predecessor tiles inspected per look-back round trip
 constexpr uint32_t RS_FLAG_AGG = 1u << 30;     // tile aggregate published
 constexpr uint32_t RS_FLAG_PREFIX = 2u << 30;  // inclusive prefix published
 constexpr uint32_t RS_VALUE_MASK = (1u << 30) - 1;
@@ -130,32 +129,17 @@ __global__ void __launch_bounds__(RS_THREADS) rs_onesweep_kernel(const __grid_co
     status[(size_t)tile * RS_RADIX + tid] = tile_count | RS_FLAG_PREFIX;
   } else {
     status[(size_t)tile * RS_RADIX + tid] = tile_count | RS_FLAG_AGG;
-    // Windowed look-back: RS_LOOKBACK predecessor words are fetched together (independent loads, one round
-    // trip) and consumed in order. When every tile of a pass is resident at once they all finish ranking at
-    // the same moment, and a one-word-at-a-time walk would serialise ~tiles/2 L2 round trips.
     int j = tile - 1;
-    bool done = false;
-    while (!done) {
-      uint32_t w[RS_LOOKBACK];
-#pragma unroll
-      for (int u = 0; u < RS_LOOKBACK; ++u) {
-        w[u] = 2u << 30;  // RS_FLAG_PREFIX: virtual empty prefix before tile 0
-        if (j - u >= 0) w[u] = status[(size_t)(j - u) * RS_RADIX + tid];
+    while (true) {
+      uint32_t w = status[(size_t)j * RS_RADIX + tid];
+      if (w & RS_FLAG_PREFIX) {
+        excl += w & RS_VALUE_MASK;
+        break;
+      } else if (w & RS_FLAG_AGG) {
+        excl += w & RS_VALUE_MASK;
+        --j;
       }
-      int consumed = 0;
-#pragma unroll
-      for (int u = 0; u < RS_LOOKBACK; ++u) {
-        if (done || consumed != u) continue;  // stopped at an unpublished tile: re-read from there
-        if (w[u] & RS_FLAG_PREFIX) {
-          excl += w[u] & RS_VALUE_MASK;
-          done = true;
-        } else if (w[u] & RS_FLAG_AGG) {
-          excl += w[u] & RS_VALUE_MASK;
-          ++consumed;
-        }
-        // else: that tile has its ticket but has not published yet; it is running, so retry
-      }
-      j -= consumed;
+      // else: that tile has its ticket but has not published yet; it is running, so spin
     }
     status[(size_t)tile * RS_RADIX + tid] = (excl + tile_count) | RS_FLAG_PREFIX;
   }

@@ -1,0 +1,176 @@
+/* legoloam_b200.h — C ABI of the B200-native scan-to-map registration path of LeGO-LOAM-SR.
+ *
+ * The reference has no plugin / FFI layer for this path: the "API" is a set of private,
+ * argument-less member functions of MapOptimization that communicate through class members
+ * (LeGO-LOAM/src/mapOptimization.h:311,327-333; only caller MapOptimization::run,
+ * mapOptmization.cpp:1882-1886). This header is the boundary those member functions call after the
+ * swap: plain pointers and sizes, no C++ or torch types, every export returns int (0 = ok,
+ * negative = ll_status). INTEGRATION.md shows the reference-side binding.
+ *
+ * Conventions
+ *  - Host point clouds are read IN PLACE as (base, count, stride_bytes): x,y,z at byte 0/4/8 and
+ *    intensity at byte 16 of each record (pcl::PointXYZI, utility.h:45, stride 32). stride 16 means
+ *    packed {x,y,z,intensity}. The library never owns or frees host memory.
+ *  - `*_dev` variants take DEVICE pointers to packed float4 {x,y,z,intensity}.
+ *  - A pose is transformTobeMapped's layout [rx, ry, rz, tx, ty, tz] (mapOptimization.h:248),
+ *    R = R_y(ry) R_x(rx) R_z(rz) (mapOptmization.cpp:606-620). A keyframe pose uses the same layout
+ *    (PointTypePose roll,pitch,yaw,x,y,z = rx,ry,rz,tx,ty,tz; mapOptmization.cpp:1700-1706).
+ *  - A handle is externally synchronised (one caller thread, like the reference's _run_thread,
+ *    mapOptmization.cpp:175) and owns one CUDA stream; different handles are independent.
+ *  - There is no CPU fallback. If no CUDA device is usable ll_create fails with LL_ERR_CUDA.
+ */
+#ifndef LEGOLOAM_B200_H_
+#define LEGOLOAM_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  LL_OK = 0,
+  LL_ERR_INVALID_ARG = -1,
+  LL_ERR_CUDA = -2,
+  LL_ERR_NOMEM = -3,
+  LL_ERR_NOT_FOUND = -4,      /* unknown keyframe id */
+  LL_ERR_CAPACITY = -5,       /* output buffer too small */
+  LL_ERR_GRID_TOO_LARGE = -6, /* the 1 m search grid over the local map exceeds the cell budget */
+  LL_ERR_STATE = -7           /* call order (e.g. scan2map before a local map exists) */
+} ll_status;
+
+typedef struct ll_handle_s* ll_handle;
+
+/* Hot-path knobs. Defaults (ll_default_params) are the reference's values. Thresholds the
+ * reference writes as double literals are doubles here so that comparisons promote the same way. */
+typedef struct {
+  float  corner_leaf;      /* 0.2  downSizeFilterCorner, mapOptmization.cpp:92 */
+  float  surf_leaf;        /* 0.4  downSizeFilterSurf,   mapOptmization.cpp:93 */
+  float  max_sq_dist;      /* 1.0  pointSearchSqDis[4] < 1.0, :1279 / :1389 (must be <= 1.0) */
+  float  eig_ratio;        /* 3    matD1[2] > 3 * matD1[1], :1325 */
+  double plane_tol;        /* 0.2  :1416 */
+  double weight_k;         /* 0.9  :1363 / :1425 */
+  double min_weight;       /* 0.1  :1370 / :1435 */
+  int    min_residuals;    /* 50   :1453 */
+  float  eig_thresh;       /* 100  :1519 */
+  int    iter_count_thres; /* 200  loam_config.yaml:35 */
+  float  step_size;        /* 1.0  loam_config.yaml:32 (used at :1500) */
+  float  stop_thres;       /* 0.05 loam_config.yaml:33 (used at :1554) */
+  int    apply_update;     /* 0 = as shipped (pose update commented out, :1539-1545); 1 = upstream */
+  int    eigen_mode;       /* 0 = as shipped (row 0 of V, row-masked V, :1329-1334,:1520-1530);
+                              1 = upstream semantics (principal eigenvector, projector sum v v^T) */
+  int    map_downsample;   /* 1 = VoxelGrid on the surrounding maps (:1225-1231); 0 = bypass */
+  int    min_corner_map;   /* 10   :1573 */
+  int    min_surf_map;     /* 100  :1573 */
+} ll_params;
+
+/* What scan2MapOptimization leaves behind (mapOptmization.cpp:1602-1607 and members). */
+typedef struct {
+  int   status;        /* 0 = optimised; 1 = skipped by the map-size guard (:1573), pose unchanged */
+  int   iter_num;      /* iterations executed (localInfo.x) */
+  float min_lambda;    /* smallest eigenvalue of AtA at iteration 0 (localInfo.y) */
+  float cf_mean;       /* mean |residual| of the last iteration (localInfo.z) */
+  int   is_degenerate; /* persists in the handle across scans, like the member */
+  int   converged;     /* LMOptimization returned true */
+  int   sel_num;       /* laserCloudSelNum of the last iteration */
+  int   flags;         /* bit 0: corner VoxelGrid index overflow (PCL pass-through reproduced);
+                          bit 1: same for surf; bit 2: search grid too large (scan skipped) */
+  int   corner_map_ds; /* laserCloudCornerFromMapDSNum */
+  int   surf_map_ds;   /* laserCloudSurfFromMapDSNum */
+  float pose[6];       /* transformTobeMapped after the loop */
+  float last_x[6];     /* matX of the last iteration */
+} ll_result;
+
+int ll_default_params(ll_params* p);
+int ll_create(const ll_params* p, int device_id, ll_handle* out);
+int ll_destroy(ll_handle h);
+int ll_set_params(ll_handle h, const ll_params* p);
+/* Text of the last failure on this handle (CUDA error strings included); never NULL. */
+const char* ll_last_error_string(ll_handle h);
+/* The handle's CUDA stream (cudaStream_t as void*), for callers that record their own events. */
+int ll_get_stream(ll_handle h, void** stream);
+/* Number of kernel launches this handle has issued so far (bench.py's gpu_launches). */
+int ll_get_launch_count(ll_handle h, uint64_t* n);
+
+/* Optional per-kernel-class timing with CUDA events on the handle's stream (bench.py's roofline). Classes:
+ * 0 transform+bbox, 1 voxel keys, 2 voxel sort pass, 3 voxel reduce, 4 grid keys, 5 grid sort pass,
+ * 6 grid finalize, 7 LM prologue, 8 LM iteration. ll_profile_read synchronises, returns the summed
+ * milliseconds and launch counts since the last read, and clears them. */
+int ll_profile_enable(ll_handle h, int on);
+int ll_profile_read(ll_handle h, double* ms_per_class, uint64_t* launches_per_class, int n_classes);
+
+/* ---- keyframe store: cornerCloudKeyFrames / surfCloudKeyFrames / outlierCloudKeyFrames
+ *      (mapOptimization.h:134-136, filled at mapOptmization.cpp:1744-1752) --------------------- */
+int ll_add_keyframe(ll_handle h, int id, const void* corner, size_t n_corner, const void* surf,
+                    size_t n_surf, const void* outlier, size_t n_outlier, size_t stride_bytes,
+                    const float pose6[6]);
+int ll_add_keyframe_dev(ll_handle h, int id, const void* d_corner, size_t n_corner, const void* d_surf,
+                        size_t n_surf, const void* d_outlier, size_t n_outlier, const float pose6[6]);
+/* correctPoses (mapOptmization.cpp:1757-1785) */
+int ll_set_keyframe_pose(ll_handle h, int id, const float pose6[6]);
+
+/* ---- a1: extractSurroundingKeyFrames tail (mapOptmization.cpp:1147-1151 / :1218-1231):
+ * transform the listed keyframes by their poses, concatenate (per keyframe corner | surf, outlier),
+ * VoxelGrid 0.2 / 0.4 (unless map_downsample = 0), then build the 1 m search grids that replace
+ * kdtreeCornerFromMap / kdtreeSurfFromMap (:1575-1576). Asynchronous on the handle's stream. */
+int ll_build_local_map(ll_handle h, const int* ids, int n_ids);
+/* Test / bench entry that skips the keyframe store: raw surrounding clouds already in the map frame. */
+int ll_set_local_map_raw(ll_handle h, const void* corner, size_t n_corner, const void* surf,
+                         size_t n_surf, size_t stride_bytes);
+/* Copy back laserCloud{Corner,Surf}FromMapDS (which = 0 corner, 1 surf). Synchronises. */
+int ll_get_map_ds(ll_handle h, int which, void* out, size_t cap_points, size_t stride_bytes, size_t* n);
+
+/* ---- a10: scan2MapOptimization (mapOptmization.cpp:1572-1610) with a7/a8/a9 inside ------------
+ * corner_scan_ds = laserCloudCornerScanDS (:1273), surf_total_ds = laserCloudSurfTotalLastDS (:1381).
+ * pose6_inout: transformTobeMapped in, refined pose out. Synchronous. */
+int ll_scan2map(ll_handle h, const void* corner_scan_ds, size_t n_corner, const void* surf_total_ds,
+                size_t n_surf, size_t stride_bytes, float pose6_inout[6], ll_result* res);
+int ll_scan2map_dev(ll_handle h, const void* d_corner_scan_ds, size_t n_corner, const void* d_surf_total_ds,
+                    size_t n_surf, float pose6_inout[6], ll_result* res);
+/* Asynchronous pair: enqueue, then collect. Between the two the caller may drive other handles. */
+int ll_scan2map_async(ll_handle h, const void* corner_scan_ds, size_t n_corner, const void* surf_total_ds,
+                      size_t n_surf, size_t stride_bytes, const float pose6_in[6]);
+int ll_scan2map_dev_async(ll_handle h, const void* d_corner_scan_ds, size_t n_corner,
+                          const void* d_surf_total_ds, size_t n_surf, const float pose6_in[6]);
+int ll_scan2map_wait(ll_handle h, float pose6_out[6], ll_result* res);
+
+/* ---- stage-level entry points (parity tests; each synchronous) --------------------------------- */
+/* a3: pcl::VoxelGrid<PointXYZI>::filter as called at mapOptmization.cpp:1225-1231 / :1236-1265.
+ * member (nullable, n ints): output slot of each input point. flags bit 0 = index overflow. */
+int ll_voxel_downsample(ll_handle h, const void* in, size_t n, size_t stride_bytes, float leaf, void* out,
+                        size_t cap_points, size_t out_stride_bytes, size_t* n_out, int* member, int* flags);
+/* a4 + a5: nearestKSearch(point, 5) against the current local map (which = 0 corner, 1 surf) for
+ * queries already in the map frame. accept[i] = (5 neighbours found with d2 < max_sq_dist); for
+ * accepted queries idx5/d2_5 are the exact 5-NN ascending by (d2, index). */
+int ll_knn5(ll_handle h, int which, const void* queries, size_t nq, size_t stride_bytes, int* idx5,
+            float* d2_5, int* accept);
+/* a6 + a7 / a8 per query, original order: coeff4 = the coeffSel record, mask = kept (s > 0.1). */
+int ll_corner_residuals(ll_handle h, const void* queries, size_t nq, size_t stride_bytes, const float pose6[6],
+                        float* coeff4, int* mask, int* accept, int* knn_idx5, float* knn_d2_5);
+int ll_surf_residuals(ll_handle h, const void* queries, size_t nq, size_t stride_bytes, const float pose6[6],
+                      float* coeff4, int* mask, int* accept, int* knn_idx5, float* knn_d2_5);
+/* a9: LMOptimization(iter) on explicit residual records (laserCloudOri, coeffSel). ret: 1 converged,
+ * 0 not, -1 skipped (n < min_residuals). AtA36 row-major. Uses and updates the handle's persistent
+ * isDegenerate / matP. */
+int ll_lm_step(ll_handle h, const void* ori, const float* coeff4, size_t n, size_t stride_bytes, int iter,
+               float pose6_inout[6], float* AtA36, float* Atb6, float* x6, float* deltaR, float* deltaT,
+               int* ret);
+/* Persistent degeneracy state (mapOptimization.h:279,281). matP36 row-major. */
+int ll_get_degeneracy(ll_handle h, int* is_degenerate, float* matP36);
+int ll_reset_state(ll_handle h);
+
+/* ---- second consumer: FeatureAssociation::calculateTransformationSurf / Corner /
+ * calculateTransformation (featureAssociation.cpp:1846-2010, :2013-2143, :2145-2289): the same
+ * normal-equation reduce + small solve + degeneracy kernel with a column mask. rows = n x 6
+ * Jacobian rows (only the masked columns are used, in mask order), b = n right-hand sides.
+ * dof_mask: bit k set = unknown k of [rx ry rz tx ty tz]. x_out gets the masked unknowns in order.
+ * On iter == 0 the eigen / degeneracy projector is recomputed into matP_inout (m x m, row-major) and
+ * *is_degenerate_inout; otherwise they are applied as given. */
+int ll_solve_normal_eq(ll_handle h, const float* rows6, const float* b, size_t n, int dof_mask, int iter,
+                       float eig_thresh, float* x_out, float* matP_inout, int* is_degenerate_inout);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LEGOLOAM_B200_H_ */

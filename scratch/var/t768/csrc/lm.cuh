@@ -21,12 +21,12 @@
 
 namespace ll {
 
-constexpr int LM_THREADS = 512;
+constexpr int LM_THREADS = 768;
 constexpr int LM_WARPS = LM_THREADS / 32;
 constexpr int LM_MIN_BLOCKS = 1;         // resident blocks per SM the register budget is sized for
 constexpr int LM_NSUM = 29;              // 21 AtA + 6 Atb + sum|d| + count
 constexpr int LM_SLOT = 21;              // floats staged per query (odd => bank-conflict-free per-thread reads)
-constexpr int LM_CHUNK = LM_THREADS;     // queries a block stages per pass
+constexpr int LM_CHUNK = 512;     // queries a block stages per pass
 constexpr int LM_CAND_UNROLL = 4;        // candidate loads in flight per lane during the 5-NN scan
 constexpr uint32_t LM_EMPTY_D2 = 0x7f800000u;  // +inf: "no candidate"
 

@@ -20,6 +20,8 @@
 #include "solve_warp.cuh"
 
 namespace ll {
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+__device__ unsigned long long g_ts[1024][8];
 
 constexpr int LM_THREADS = 512;
 constexpr int LM_WARPS = LM_THREADS / 32;
@@ -807,6 +809,7 @@ __device__ void reduce_partials_and_solve(const float* partials, int nblocks, co
 //   tail     block partial -> global; the last block to arrive adds all partials and solves.
 __global__ void __launch_bounds__(LM_THREADS, LM_MIN_BLOCKS) lm_iter_kernel(const __grid_constant__ LMArgs A) {
   LMState* S = A.st;
+  if (threadIdx.x == 0) g_ts[blockIdx.x][0] = gtime();
   if (A.mode == 0 && S->done) return;
   __shared__ __align__(16) float s_slot[LM_CHUNK * LM_SLOT];
   __shared__ float s_wacc[LM_WARPS][32];
@@ -870,6 +873,7 @@ __global__ void __launch_bounds__(LM_THREADS, LM_MIN_BLOCKS) lm_iter_kernel(cons
       }
     }
     __syncthreads();
+    if (threadIdx.x == 0) g_ts[blockIdx.x][1] = gtime();
     // ---- phase 2: fit + Jacobian row, one thread per query
     if (A.mode != 2) {
       float sv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -921,6 +925,7 @@ __global__ void __launch_bounds__(LM_THREADS, LM_MIN_BLOCKS) lm_iter_kernel(cons
     __syncthreads();
   }
   if (A.mode != 0) return;
+  if (threadIdx.x == 0) g_ts[blockIdx.x][2] = gtime();
   if (tid < 32) {
     A.partials[blockIdx.x * 32 + tid] = tid < LM_NSUM ? run_sum : 0.f;
     __threadfence();
@@ -934,7 +939,14 @@ __global__ void __launch_bounds__(LM_THREADS, LM_MIN_BLOCKS) lm_iter_kernel(cons
   if (!s_last) return;
   __threadfence();
   if (tid == 0) S->ticket = 0;
+  if (threadIdx.x == 0) g_ts[blockIdx.x][3] = gtime();
+  const int it_dbg = S->iter;
   reduce_partials_and_solve(A.partials, gridDim.x, A.prm, S, false, reinterpret_cast<double*>(s_slot));
+  if (threadIdx.x == 0) {
+    unsigned long long t5 = gtime(), t0min = ~0ull, t0max = 0, p1 = 0, p2 = 0, t2max = 0;
+    for (int b = 0; b < (int)gridDim.x; ++b) { unsigned long long a0 = *(volatile unsigned long long*)&g_ts[b][0], a1 = *(volatile unsigned long long*)&g_ts[b][1], a2 = *(volatile unsigned long long*)&g_ts[b][2]; if (a0 < t0min) t0min = a0; if (a0 > t0max) t0max = a0; if (a1 - a0 > p1) p1 = a1 - a0; if (a2 - a1 > p2) p2 = a2 - a1; if (a2 > t2max) t2max = a2; }
+    printf("iter %d: start spread %llu ns, phase1 max %llu, phase2 max %llu, all-blocks-done %llu, last-block-ticket %llu, reduce+solve %llu, total %llu\n", it_dbg, t0max - t0min, p1, p2, t2max - t0min, g_ts[blockIdx.x][3] - t0min, t5 - g_ts[blockIdx.x][3], t5 - t0min);
+  }
 }
 
 // scan2MapOptimization prologue (:1573): the map-size guard and the loop state, one thread.
