@@ -86,6 +86,9 @@ int ll_default_params(ll_params* p);
 int ll_create(const ll_params* p, int device_id, ll_handle* out);
 int ll_destroy(ll_handle h);
 int ll_set_params(ll_handle h, const ll_params* p);
+/* Pre-size the device buffers (points of the raw surrounding corner / surf clouds, query points per scan) so
+ * that no call on the per-frame path has to reallocate; buffers still grow on demand beyond this. */
+int ll_reserve(ll_handle h, size_t max_corner_raw, size_t max_surf_raw, size_t max_queries);
 /* Text of the last failure on this handle (CUDA error strings included); never NULL. */
 const char* ll_last_error_string(ll_handle h);
 /* The handle's CUDA stream (cudaStream_t as void*), for callers that record their own events. */

@@ -23,9 +23,10 @@ using namespace ll;
 
 namespace {
 
-constexpr size_t kArenaChunk = 64ull << 20;  // keyframe store grows in 64 MiB slabs
+constexpr size_t kArenaChunk = 256ull << 20;  // keyframe store grows in 256 MiB slabs (~1000 VLP-16 keyframes each)
 constexpr int kCellCap = 1 << 24;            // 16.7 M one-metre cells per search grid (<= 24 key bits: 3 sort passes)
 constexpr int kGridPasses = 3;
+constexpr int kPinSlots = 4;                 // pinned staging buffers in flight
 constexpr int kFirstChunk = 12;              // LM iterations enqueued before the first look at `done`
 constexpr int kNextChunk = 16;
 
@@ -70,9 +71,11 @@ struct ll_handle_s {
   size_t arena_off = 0, arena_cap = 0;
   std::unordered_map<int, Keyframe> kfs;
 
-  uint8_t* pinned = nullptr;
-  size_t pinned_bytes = 0;
-  cudaEvent_t pinned_evt = nullptr;
+  uint8_t* pinned = nullptr;  // the staging slot acquired last
+  uint8_t* pin_buf[kPinSlots] = {};
+  size_t pin_bytes[kPinSlots] = {};
+  cudaEvent_t pin_evt[kPinSlots] = {};
+  int pin_cur = 0;
 
   MapSlot slot[3];
   bool map_ready = false;
@@ -174,25 +177,27 @@ int ensure_bytes(ll_handle h, void** p, size_t* cap, size_t need) {
   return LL_OK;
 }
 
-int ensure_pinned(ll_handle h, size_t need) {
-  if (h->pinned_bytes >= need) return LL_OK;
-  LL_CUDA(h, cudaStreamSynchronize(h->stream));
-  if (h->pinned) LL_CUDA(h, cudaFreeHost(h->pinned));
-  h->pinned = nullptr;
-  size_t newcap = need + need / 2 + 4096;
-  cudaError_t e = cudaMallocHost(reinterpret_cast<void**>(&h->pinned), newcap);
-  if (e != cudaSuccess) return fail(h, LL_ERR_NOMEM, std::string("cudaMallocHost: ") + cudaGetErrorString(e));
-  h->pinned_bytes = newcap;
+// Host-to-device staging: a ring of kPinSlots pinned buffers, each guarded by the event of the last copy that
+// read it, so that consecutive uploads (keyframe clouds, segment table, queries) never wait for one another.
+// h->pinned always points at the slot acquired last.
+int pinned_acquire(ll_handle h, size_t need) {
+  h->pin_cur = (h->pin_cur + 1) % kPinSlots;
+  const int s = h->pin_cur;
+  LL_CUDA(h, cudaEventSynchronize(h->pin_evt[s]));
+  if (h->pin_bytes[s] < need) {
+    if (h->pin_buf[s]) LL_CUDA(h, cudaFreeHost(h->pin_buf[s]));
+    h->pin_buf[s] = nullptr;
+    h->pin_bytes[s] = 0;
+    const size_t newcap = need + need / 2 + 4096;
+    cudaError_t e = cudaMallocHost(reinterpret_cast<void**>(&h->pin_buf[s]), newcap);
+    if (e != cudaSuccess) return fail(h, LL_ERR_NOMEM, std::string("cudaMallocHost: ") + cudaGetErrorString(e));
+    h->pin_bytes[s] = newcap;
+  }
+  h->pinned = h->pin_buf[s];
   return LL_OK;
 }
-
-// The staging buffer is reused by consecutive uploads: wait until the previous copy has drained it.
-int pinned_acquire(ll_handle h, size_t need) {
-  LL_CUDA(h, cudaEventSynchronize(h->pinned_evt));
-  return ensure_pinned(h, need);
-}
 int pinned_release(ll_handle h) {
-  LL_CUDA(h, cudaEventRecord(h->pinned_evt, h->stream));
+  LL_CUDA(h, cudaEventRecord(h->pin_evt[h->pin_cur], h->stream));
   return LL_OK;
 }
 
@@ -256,7 +261,7 @@ int ensure_slot(ll_handle h, int s, size_t need_pts, bool need_grid) {
     void* ptrs[] = {S.raw, S.ds, S.sorted, S.keys[0], S.keys[1], S.vals[0], S.vals[1], S.scratch, S.member};
     for (void* p : ptrs)
       if (p) LL_CUDA(h, cudaFree(p));
-    size_t cap = need_pts + need_pts / 4 + 4096;
+    size_t cap = 2 * need_pts + 4096;  // geometric growth: reallocation is a multi-millisecond stall
     S.raw = S.ds = S.sorted = nullptr;
     S.member = nullptr;
     S.cap = 0;
@@ -652,8 +657,10 @@ int ll_create(const ll_params* p, int device_id, ll_handle* out) {
   h->device = device_id;
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device_id) == cudaSuccess) h->num_sms = prop.multiProcessorCount;
-  bool ok = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess &&
-            cudaEventCreateWithFlags(&h->pinned_evt, cudaEventDisableTiming) == cudaSuccess &&
+  bool ev_ok = true;
+  for (int i = 0; i < kPinSlots; ++i)
+    ev_ok = ev_ok && cudaEventCreateWithFlags(&h->pin_evt[i], cudaEventDisableTiming) == cudaSuccess;
+  bool ok = ev_ok && cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess &&
             cudaMalloc(reinterpret_cast<void**>(&h->d_state), sizeof(LMState)) == cudaSuccess &&
             cudaMallocHost(reinterpret_cast<void**>(&h->h_state), sizeof(LMState)) == cudaSuccess &&
             cudaMemsetAsync(h->d_state, 0, sizeof(LMState), h->stream) == cudaSuccess &&
@@ -681,12 +688,28 @@ int ll_destroy(ll_handle h) {
                   h->d_tmp[0], h->d_tmp[1], h->d_tmp[2], h->d_tmp[3], h->d_tmp[4], h->d_tmp[5]};
   for (void* p : ptrs)
     if (p) cudaFree(p);
-  if (h->pinned) cudaFreeHost(h->pinned);
+  for (int i = 0; i < kPinSlots; ++i) {
+    if (h->pin_buf[i]) cudaFreeHost(h->pin_buf[i]);
+    if (h->pin_evt[i]) cudaEventDestroy(h->pin_evt[i]);
+  }
   if (h->h_state) cudaFreeHost(h->h_state);
-  if (h->pinned_evt) cudaEventDestroy(h->pinned_evt);
   for (cudaEvent_t e : h->prof_pool) cudaEventDestroy(e);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
+  return LL_OK;
+}
+
+int ll_reserve(ll_handle h, size_t max_corner_raw, size_t max_surf_raw, size_t max_queries) {
+  if (!h) return LL_ERR_INVALID_ARG;
+  if (h->scan_pending) return fail(h, LL_ERR_STATE, "a scan2map is still in flight");
+  LL_CUDA(h, cudaSetDevice(h->device));
+  if (max_corner_raw) LL_TRY(ensure_slot(h, 0, (max_corner_raw + 1) / 2, true));  // ensure_slot doubles what it is asked for
+  if (max_surf_raw) LL_TRY(ensure_slot(h, 1, (max_surf_raw + 1) / 2, true));
+  if (max_queries) {
+    LL_TRY(ensure_bytes(h, reinterpret_cast<void**>(&h->dq[0]), &h->dq_cap[0], max_queries * sizeof(float4)));
+    for (int i = 0; i < kPinSlots; ++i) LL_TRY(pinned_acquire(h, max_queries * sizeof(float4)));
+  }
+  LL_TRY(ensure_partials(h, h->num_sms * LM_MIN_BLOCKS));
   return LL_OK;
 }
 

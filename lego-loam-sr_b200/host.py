@@ -85,6 +85,17 @@ class MapOptimization:
     def process_frame_dev(self, odom6, ptrs):
         """ptrs: five (device_pointer, count) pairs — corner_scan, corner_scan_ds, surf_last_ds, outlier_last_ds,
         surf_total_ds — packed float4 clouds already resident on the device."""
+        return self._process_view(odom6, ptrs, device=1, stride=16)
+
+    def process_frame_host(self, odom6, clouds):
+        """clouds: five numpy arrays in pcl::PointXYZI layout ([n, 8] float32, stride 32) or packed ([n, 4]),
+        read in place by the library (no intermediate PointCloud copies) — the ROS node's situation."""
+        arrs = [np.ascontiguousarray(c, np.float32) for c in clouds]
+        stride = arrs[0].shape[1] * 4 if arrs[0].ndim == 2 else 16
+        ptrs = [(a.ctypes.data if a.size else 0, a.shape[0]) for a in arrs]
+        return self._process_view(odom6, ptrs, device=0, stride=stride)
+
+    def _process_view(self, odom6, ptrs, device, stride):
         odom = np.ascontiguousarray(odom6, np.float32)
         res = abi.Result()
         pose = np.zeros(6, np.float32)
@@ -92,7 +103,8 @@ class MapOptimization:
         args = []
         for p, n in ptrs:
             args += [C.c_void_p(p), C.c_size_t(n)]
-        rc = self._lib.llh_process_frame_dev(self._mo, _vp(odom), *args, C.byref(res), _vp(pose), err, C.c_size_t(512))
+        rc = self._lib.llh_process_frame_view(self._mo, _vp(odom), *args, C.c_int(device), C.c_size_t(stride),
+                                              C.byref(res), _vp(pose), err, C.c_size_t(512))
         if rc != 0:
             raise RuntimeError(err.value.decode("utf-8", "replace"))
         return pose, res

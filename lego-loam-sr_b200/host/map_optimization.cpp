@@ -84,6 +84,8 @@ MapOptimization::MapOptimization(const ll_params& params, int device_id, bool lo
   std::memset(&lastResult, 0, sizeof(lastResult));
   const int rc = ll_create(&prm_, device_id, &h_);
   if (rc != LL_OK) throw std::runtime_error("ll_create failed (" + std::to_string(rc) + "): no usable CUDA device; there is no CPU fallback");
+  // A 50-keyframe VLP-16 window is ~0.1 M corner + ~0.3 M surf raw points; reserve well above that once.
+  check(ll_reserve(h_, 1u << 20, 1u << 21, 1u << 17), "ll_reserve");
 }
 
 MapOptimization::~MapOptimization() { ll_destroy(h_); }
@@ -247,10 +249,14 @@ void MapOptimization::scan2MapOptimization() {  // :1572-1610
   std::memcpy(lastResult.pose, transformTobeMapped, sizeof(lastResult.pose));
   std::memcpy(lastPrior, transformTobeMapped, sizeof(lastPrior));
   if (!mapBuilt_) return;  // first frame: laserCloud*FromMapDSNum are 0, the guard at :1573 fails
-  if (devFrame_) {
-    check(ll_scan2map_dev(h_, devFrame_->corner_scan_ds, devFrame_->n_corner_scan_ds, devFrame_->surf_total_ds,
-                          devFrame_->n_surf_total_ds, transformTobeMapped, &lastResult),
+  if (view_ && view_->device) {
+    check(ll_scan2map_dev(h_, view_->corner_scan_ds, view_->n_corner_scan_ds, view_->surf_total_ds,
+                          view_->n_surf_total_ds, transformTobeMapped, &lastResult),
           "ll_scan2map_dev");
+  } else if (view_) {
+    check(ll_scan2map(h_, view_->corner_scan_ds, view_->n_corner_scan_ds, view_->surf_total_ds, view_->n_surf_total_ds,
+                      view_->stride_bytes, transformTobeMapped, &lastResult),
+          "ll_scan2map");
   } else {
     check(ll_scan2map(h_, laserCloudCornerScanDS->points.data(), laserCloudCornerScanDS->size(),
                       laserCloudSurfTotalLastDS->points.data(), laserCloudSurfTotalLastDS->size(), sizeof(PointType),
@@ -302,11 +308,18 @@ void MapOptimization::saveKeyFramesAndFactor() {  // :1612-1755, pose graph = pa
   }
   // :1744-1752: corner keyframe = un-downsampled laserCloudCornerScan, surf = laserCloudSurfLastDS,
   // outlier = laserCloudOutlierLastDS. Uploaded once; the device keeps them for the whole run.
-  if (devFrame_) {
-    check(ll_add_keyframe_dev(h_, (int)cloudKeyPoses3D.size() - 1, devFrame_->corner_scan, devFrame_->n_corner_scan,
-                              devFrame_->surf_last_ds, devFrame_->n_surf_last_ds, devFrame_->outlier_last_ds,
-                              devFrame_->n_outlier_last_ds, pose),
+  if (view_ && view_->device) {
+    check(ll_add_keyframe_dev(h_, (int)cloudKeyPoses3D.size() - 1, view_->corner_scan, view_->n_corner_scan,
+                              view_->surf_last_ds, view_->n_surf_last_ds, view_->outlier_last_ds,
+                              view_->n_outlier_last_ds, pose),
           "ll_add_keyframe_dev");
+    return;
+  }
+  if (view_) {
+    check(ll_add_keyframe(h_, (int)cloudKeyPoses3D.size() - 1, view_->corner_scan, view_->n_corner_scan,
+                          view_->surf_last_ds, view_->n_surf_last_ds, view_->outlier_last_ds, view_->n_outlier_last_ds,
+                          view_->stride_bytes, pose),
+          "ll_add_keyframe");
     return;
   }
   check(ll_add_keyframe(h_, (int)cloudKeyPoses3D.size() - 1, laserCloudCornerScan->points.data(),
@@ -315,9 +328,9 @@ void MapOptimization::saveKeyFramesAndFactor() {  // :1612-1755, pose graph = pa
         "ll_add_keyframe");
 }
 
-void MapOptimization::processFrameDevice(const float laser_odometry[6], const DeviceFrame& frame) {
+void MapOptimization::processFrameView(const float laser_odometry[6], const FrameView& frame) {
   frame_idx++;
-  devFrame_ = &frame;
+  view_ = &frame;
   try {
     for (int i = 0; i < 6; ++i) transformSum[i] = laser_odometry[i];
     transformAssociateToMap();
@@ -327,10 +340,10 @@ void MapOptimization::processFrameDevice(const float laser_odometry[6], const De
     correctPoses();
     clearCloud();
   } catch (...) {
-    devFrame_ = nullptr;
+    view_ = nullptr;
     throw;
   }
-  devFrame_ = nullptr;
+  view_ = nullptr;
 }
 
 void MapOptimization::correctPoses() {  // :1757-1785
@@ -458,20 +471,23 @@ int llh_process_frame(void* mo, const float odom6[6], const float* corner_scan, 
   }
 }
 
-// One frame whose (already downsampled) clouds are resident on the device as packed float4.
-int llh_process_frame_dev(void* mo, const float odom6[6], const void* d_corner_scan, size_t n_cs,
-                          const void* d_corner_scan_ds, size_t n_csd, const void* d_surf_last_ds, size_t n_sl,
-                          const void* d_outlier_last_ds, size_t n_ol, const void* d_surf_total_ds, size_t n_st,
-                          ll_result* res, float pose_out[6], char* err, size_t err_cap) {
+// One frame on caller-owned, already downsampled clouds (no copies into PointCloud objects): device != 0 —
+// packed float4 clouds resident on the device; device == 0 — host clouds read in place with `stride` bytes per point.
+int llh_process_frame_view(void* mo, const float odom6[6], const void* corner_scan, size_t n_cs,
+                           const void* corner_scan_ds, size_t n_csd, const void* surf_last_ds, size_t n_sl,
+                           const void* outlier_last_ds, size_t n_ol, const void* surf_total_ds, size_t n_st, int device,
+                           size_t stride, ll_result* res, float pose_out[6], char* err, size_t err_cap) {
   MapOptimization* M = static_cast<MapOptimization*>(mo);
   try {
-    MapOptimization::DeviceFrame f;
-    f.corner_scan = d_corner_scan; f.n_corner_scan = n_cs;
-    f.corner_scan_ds = d_corner_scan_ds; f.n_corner_scan_ds = n_csd;
-    f.surf_last_ds = d_surf_last_ds; f.n_surf_last_ds = n_sl;
-    f.outlier_last_ds = d_outlier_last_ds; f.n_outlier_last_ds = n_ol;
-    f.surf_total_ds = d_surf_total_ds; f.n_surf_total_ds = n_st;
-    M->processFrameDevice(odom6, f);
+    MapOptimization::FrameView f;
+    f.corner_scan = corner_scan; f.n_corner_scan = n_cs;
+    f.corner_scan_ds = corner_scan_ds; f.n_corner_scan_ds = n_csd;
+    f.surf_last_ds = surf_last_ds; f.n_surf_last_ds = n_sl;
+    f.outlier_last_ds = outlier_last_ds; f.n_outlier_last_ds = n_ol;
+    f.surf_total_ds = surf_total_ds; f.n_surf_total_ds = n_st;
+    f.device = device != 0;
+    f.stride_bytes = stride;
+    M->processFrameView(odom6, f);
     if (res) *res = M->lastResult;
     if (pose_out) std::memcpy(pose_out, M->lastResult.pose, 6 * sizeof(float));
     return 0;

@@ -67,16 +67,21 @@ class MapOptimization {
   void processFrame(const AssociationOut& association, bool scan_clouds_are_downsampled = false,
                     PointCloud::Ptr corner_scan_ds = nullptr);
 
-  // Same frame body for clouds that already live in device memory as packed float4 (already downsampled):
-  // what bench.py times as "inputs resident in HBM". Only pointers and counts cross the boundary.
-  struct DeviceFrame {
+  // Same frame body on caller-owned memory, without copying into PointCloud objects: the clouds are
+  // already what downsampleCurrentScan would produce. Two uses: (a) device = true — packed float4 clouds
+  // resident in device memory (what bench.py times as "inputs resident in HBM"; only pointers and counts
+  // cross the boundary); (b) device = false — host clouds read in place with the given stride (32 for
+  // pcl::PointXYZI storage, i.e. cloud->points.data()), which is what the ROS node's clouds look like.
+  struct FrameView {
     const void* corner_scan = nullptr;     size_t n_corner_scan = 0;      // keyframe corner cloud (:1746)
     const void* corner_scan_ds = nullptr;  size_t n_corner_scan_ds = 0;   // laserCloudCornerScanDS
     const void* surf_last_ds = nullptr;    size_t n_surf_last_ds = 0;     // keyframe surf cloud (:1744)
     const void* outlier_last_ds = nullptr; size_t n_outlier_last_ds = 0;  // keyframe outlier cloud (:1745)
     const void* surf_total_ds = nullptr;   size_t n_surf_total_ds = 0;    // laserCloudSurfTotalLastDS
+    bool device = false;
+    size_t stride_bytes = 32;  // host clouds only
   };
-  void processFrameDevice(const float laser_odometry[6], const DeviceFrame& frame);
+  void processFrameView(const float laser_odometry[6], const FrameView& frame);
 
   // ---- members with the reference's names (mapOptimization.h:311,327-333 and :458,:583) ----------------
   void transformAssociateToMap();
@@ -136,7 +141,7 @@ class MapOptimization {
   std::vector<int> surroundingExistingKeyPosesID_;
   std::vector<int> mapIds_;
   bool mapBuilt_ = false;
-  const DeviceFrame* devFrame_ = nullptr;  // non-null while processFrameDevice runs
+  const FrameView* view_ = nullptr;  // non-null while processFrameView runs
 };
 
 }  // namespace lego_loam_b200

@@ -402,3 +402,28 @@ def test_full_size_properties(abi, orc):
         assert np.array_equal(idx[sample][o_acc], o_idx[o_acc])
         assert np.array_equal(bits(d2[sample][o_acc]), bits(o_d2[o_acc]))
         assert (np.diff(d2[accept == 1], axis=1) >= 0).all()
+
+
+# ------------------------------------------------------------------------------------------ batched replay (config 5 shape)
+def test_batched_replay_is_independent_of_concurrency(abi, synth):
+    """Several sequences in flight on one GPU (one handle + stream + host thread each) give bit-identical poses to
+    replaying them one after the other: handles share nothing."""
+    from lego_loam_sr_b200 import batch, host
+    small = dict(n_blocks=8, n_poles=50, half_x=25, half_z=35)
+    seqs = {s: synth.make_sequence(seed=100 + s, n_scans=6, step=0.7, world_kw=small) for s in range(4)}
+
+    def make_node():
+        return host.MapOptimization(upstream_params(abi, iter_count_thres=6), loop_closure_enabled=True, search_num=50)
+
+    def feed(node, data, k):
+        f = data["frames"][k]
+        return node.process_frame_host(data["odom"][k], [f["corner_scan"], f["corner_scan_ds"], f["surf_last_ds"],
+                                                         f["outlier_last_ds"], f["surf_total_ds"]])
+
+    seq_rec = batch.replay_sequences(seqs, make_node, feed, n_threads=1)
+    par_rec = batch.replay_sequences(seqs, make_node, feed, n_threads=4)
+    a = batch.gather_records(seq_rec, 4, 6, 1, 0)
+    b = batch.gather_records(par_rec, 4, 6, 1, 0)
+    assert np.array_equal(a, b)
+    assert (a[:, 1:, batch.RECORD_FIELDS.index("status")] == 0).all()
+    assert (a[:, 1:, batch.RECORD_FIELDS.index("iter_num")] == 6).all()
