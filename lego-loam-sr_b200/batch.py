@@ -57,12 +57,13 @@ def gather_records(local_records, n_sequences, n_scans, world_size, rank, dist=N
     return out
 
 
-def replay_sequences(sequences, make_node, feed, n_threads=None):
+def replay_sequences(sequences, make_node, feed, n_threads=None, nodes=None):
     """Replay {seq_id: data} concurrently: one node (MapOptimization mirror) and one host thread per sequence.
 
     make_node() -> node; feed(node, data, k) -> (pose, res) registers scan k. Returns {seq: [n, W] records}.
     ctypes releases the GIL inside every library call, so the threads overlap on the GPU (one CUDA stream
-    per handle).
+    per handle). `nodes` = {seq: node} created beforehand keeps handle creation (cudaMalloc, which synchronises
+    the device) out of a timed region; such nodes are left open for the caller to close.
     """
     ids = sorted(sequences)
     records = {}
@@ -71,7 +72,7 @@ def replay_sequences(sequences, make_node, feed, n_threads=None):
     def work(my_ids):
         try:
             for s in my_ids:
-                node = make_node()
+                node = nodes[s] if nodes is not None else make_node()
                 data = sequences[s]
                 n = len(data["frames"])
                 rec = np.zeros((n, RECORD_WIDTH), np.float64)
@@ -79,7 +80,8 @@ def replay_sequences(sequences, make_node, feed, n_threads=None):
                     pose, res = feed(node, data, k)
                     rec[k] = make_record(s, k, pose, res)
                 records[s] = rec
-                node.close()
+                if nodes is None:
+                    node.close()
         except Exception as e:  # surfaced to the caller below
             errors.append(e)
 

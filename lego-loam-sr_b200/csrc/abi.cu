@@ -710,6 +710,10 @@ int ll_reserve(ll_handle h, size_t max_corner_raw, size_t max_surf_raw, size_t m
     for (int i = 0; i < kPinSlots; ++i) LL_TRY(pinned_acquire(h, max_queries * sizeof(float4)));
   }
   LL_TRY(ensure_partials(h, h->num_sms * LM_MIN_BLOCKS));
+  if (h->arena.empty()) {  // first keyframe slab now rather than inside the first add_keyframe
+    void* p = nullptr;
+    LL_TRY(arena_alloc(h, 256, &p));
+  }
   return LL_OK;
 }
 
