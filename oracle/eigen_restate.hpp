@@ -402,4 +402,17 @@ inline void inverse_lu(const Mat<N, N>& Ain, Mat<N, N>& inv) {
   }
 }
 
+// --- Matrix<float,3,3>::inverse(): Eigen's fixed-size path (compute_inverse_size3_helper) = cofactors / det ---
+inline void inverse3_cofactor(const Mat<3, 3>& M, Mat<3, 3>& inv) {
+  auto cof = [&](int i, int j) {
+    const int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+    return M(i1, j1) * M(i2, j2) - M(i1, j2) * M(i2, j1);
+  };
+  const float c00 = cof(0, 0), c10 = cof(1, 0), c20 = cof(2, 0);
+  const float det = c00 * M(0, 0) + c10 * M(1, 0) + c20 * M(2, 0);
+  const float invdet = 1.f / det;
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) inv(r, c) = cof(c, r) * invdet;
+}
+
 }  // namespace orc_eig

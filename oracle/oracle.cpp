@@ -699,6 +699,94 @@ void orc_transform_associate_to_map(const float sum[6], const float bef[6], cons
   tobe[5] = aft[5] - (-S(tobe[1]) * x2 + C(tobe[1]) * z2);
 }
 
+// ---- FeatureAssociation::calculateTransformationSurf / Corner / calculateTransformation ----------------
+// (featureAssociation.cpp:1925-1997, :2068-2131, :2208-2271): rows restricted to the masked unknowns,
+// matAtA / matAtB as float products, colPivHouseholderQr solve, and on iterCount == 0 the eigen / degeneracy
+// projector with the given threshold (10 there). matP / isDegenerate are the caller's (function-local in the
+// reference). M = number of unknowns (3 or 6).
+}  // extern "C" (templates need C++ linkage)
+
+template <int M>
+static void solve_normal_eq_t(const float* rows6, const float* b, int n, const int* cols, int iter, float eig_thresh,
+                              int eigen_mode, float* x_out, float* matP, int* is_degenerate) {
+  Mat<M, M> AtA;
+  AtA.zero();
+  float Atb[M];
+  for (int k = 0; k < M; ++k) Atb[k] = 0.f;
+  for (int i = 0; i < n; ++i) {
+    float r[M];
+    for (int k = 0; k < M; ++k) r[k] = rows6[6 * i + cols[k]];
+    for (int a = 0; a < M; ++a) {
+      for (int c = 0; c < M; ++c) AtA(a, c) += r[a] * r[c];
+      Atb[a] += r[a] * b[i];
+    }
+  }
+  float x[M];
+  orc_eig::colpiv_qr_solve<M, M>(AtA, Atb, x);
+  if (iter == 0) {
+    float E[M];
+    Mat<M, M> V, V2, P;
+    orc_eig::self_adjoint_eig<M>(AtA, E, V);
+    int deg = 0;
+    if (eigen_mode == 0) {
+      V2 = V;
+      for (int i = M - 1; i >= 0; --i) {
+        if (E[i] < eig_thresh) {
+          for (int j = 0; j < M; ++j) V2(i, j) = 0.f;
+          deg = 1;
+        } else {
+          break;
+        }
+      }
+      Mat<M, M> Vinv;
+      if constexpr (M == 3) orc_eig::inverse3_cofactor(V, Vinv);
+      else orc_eig::inverse_lu<M>(V, Vinv);
+      for (int r = 0; r < M; ++r)
+        for (int c = 0; c < M; ++c) {
+          float acc = 0.f;
+          for (int k = 0; k < M; ++k) acc += Vinv(r, k) * V2(k, c);
+          P(r, c) = acc;
+        }
+    } else {
+      int first_kept = 0;
+      while (first_kept < M && E[first_kept] < eig_thresh) ++first_kept;
+      deg = first_kept > 0;
+      for (int r = 0; r < M; ++r)
+        for (int c = 0; c < M; ++c) {
+          float acc = 0.f;
+          for (int k = first_kept; k < M; ++k) acc += V(r, k) * V(c, k);
+          P(r, c) = acc;
+        }
+    }
+    *is_degenerate = deg;
+    for (int r = 0; r < M; ++r)
+      for (int c = 0; c < M; ++c) matP[M * r + c] = P(r, c);
+  }
+  if (*is_degenerate) {
+    float x2[M];
+    for (int r = 0; r < M; ++r) {
+      float acc = 0.f;
+      for (int c = 0; c < M; ++c) acc += matP[M * r + c] * x[c];
+      x2[r] = acc;
+    }
+    for (int r = 0; r < M; ++r) x[r] = x2[r];
+  }
+  for (int r = 0; r < M; ++r) x_out[r] = x[r];
+}
+
+extern "C" {
+
+int orc_solve_normal_eq(const float* rows6, const float* b, int n, int dof_mask, int iter, float eig_thresh,
+                        int eigen_mode, float* x_out, float* matP_inout, int* is_degenerate_inout) {
+  int cols[6], m = 0;
+  for (int k = 0; k < 6; ++k)
+    if (dof_mask & (1 << k)) cols[m++] = k;
+  if (m == 3) solve_normal_eq_t<3>(rows6, b, n, cols, iter, eig_thresh, eigen_mode, x_out, matP_inout, is_degenerate_inout);
+  else if (m == 6) solve_normal_eq_t<6>(rows6, b, n, cols, iter, eig_thresh, eigen_mode, x_out, matP_inout, is_degenerate_inout);
+  else return -1;
+  return 0;
+}
+
 // ---- direct access to the restated Eigen pieces, for the oracle's own cross-checks -------------------
 // A: row-major n x n symmetric (n = 3 or 6); evals ascending, evecs row-major with eigenvectors in columns.
 void orc_test_self_adjoint_eig(const float* A, int n, float* evals, float* evecs) {

@@ -125,6 +125,14 @@ void orc_replay_step(orc_replay* r, const float odom6[6], const orc_p4* corner_s
                      orc_result* res, int* n_corner_map_ds, int* n_surf_map_ds);
 void orc_replay_get_map(orc_replay* r, int which, orc_p4* out, int cap, int* n);
 
+/* f-1: FeatureAssociation's normal-equation solves (featureAssociation.cpp:1925-1997, :2068-2131, :2208-2271)
+ * with a column mask over [rx ry rz tx ty tz]; 3 or 6 unknowns. Returns 0, or -1 for other counts. */
+int orc_solve_normal_eq(const float* rows6, const float* b, int n, int dof_mask, int iter, float eig_thresh,
+                        int eigen_mode, float* x_out, float* matP_inout, int* is_degenerate_inout);
+void orc_test_self_adjoint_eig(const float* A, int n, float* evals, float* evecs);
+void orc_test_colpiv_qr_solve(const float* A, const float* b, int rows, int cols, float* x);
+void orc_test_inverse6(const float* A, float* inv);
+
 #ifdef __cplusplus
 }
 #endif

@@ -245,6 +245,20 @@ def inverse6(A):
     return out
 
 
+def solve_normal_eq(rows6, b, dof_mask, it, eig_thresh, eigen_mode, matP=None, is_degenerate=0):
+    rows = np.ascontiguousarray(rows6, np.float32).reshape(-1, 6)
+    bb = np.ascontiguousarray(b, np.float32).reshape(-1)
+    m = bin(dof_mask & 63).count("1")
+    x = np.zeros(m, np.float32)
+    P = np.zeros((m, m), np.float32) if matP is None else np.ascontiguousarray(matP, np.float32).copy()
+    deg = C.c_int(is_degenerate)
+    lib().orc_solve_normal_eq.restype = C.c_int
+    rc = lib().orc_solve_normal_eq(_ptr(rows), _ptr(bb), C.c_int(len(rows)), C.c_int(dof_mask), C.c_int(it),
+                                   C.c_float(eig_thresh), C.c_int(eigen_mode), _ptr(x), _ptr(P), C.byref(deg))
+    assert rc == 0, "oracle supports 3 or 6 unknowns"
+    return x, P, deg.value
+
+
 class Replay:
     def __init__(self, prm, window=50):
         self._h = C.c_void_p(lib().orc_replay_create(C.byref(prm), C.c_int(window)))

@@ -233,6 +233,48 @@ def test_lm_step_parity(abi, orc, single_problem, single_maps, eigen_mode):
     assert g["ret"] == -1 and np.array_equal(g["pose"], d["prior"])
 
 
+# ------------------------------------------------------------------------------------------ f-1 FeatureAssociation solves
+@pytest.mark.parametrize("eigen_mode", [0, 1])
+def test_solve_normal_eq_parity(abi, orc, eigen_mode):
+    """calculateTransformationSurf / Corner / calculateTransformation (featureAssociation.cpp:1846-2289): the same
+    reduce + small solve + degeneracy kernel with a column mask ([rx,rz,ty], [ry,tx,tz], all six), eigen threshold 10."""
+    rng = np.random.default_rng(9)
+    n = 1500
+    rows = (rng.normal(size=(n, 6)) * np.array([3.0, 2.0, 3.0, 0.6, 0.3, 0.6])).astype(np.float32)
+    x_true = np.array([0.004, -0.003, 0.002, 0.02, -0.01, 0.03])
+    b = (rows.astype(np.float64) @ x_true + rng.normal(0, 1e-3, n)).astype(np.float32)
+    with abi.Handle(abi.default_params(eigen_mode=eigen_mode)) as h:
+        for mask in (0b010101, 0b101010, 0b111111):
+            for thresh in (10.0, 1e9, 3000.0):
+                gx, gP, gdeg = h.solve_normal_eq(rows, b, mask, 0, thresh)
+                ox, oP, odeg = orc.solve_normal_eq(rows, b, mask, 0, thresh, eigen_mode)
+                assert gdeg == odeg, (mask, thresh)
+                assert np.abs(gx - ox).max() <= 2e-5 * max(1.0, np.abs(ox).max()), (mask, thresh, gx, ox)
+                assert np.abs(gP - oP).max() <= 2e-3, (mask, thresh)
+                # iteration > 0 re-uses the caller's projector (function-local matP in the reference)
+                gx1, gP1, gdeg1 = h.solve_normal_eq(rows, b, mask, 3, thresh, matP=gP, is_degenerate=gdeg)
+                ox1, oP1, odeg1 = orc.solve_normal_eq(rows, b, mask, 3, thresh, eigen_mode, matP=oP, is_degenerate=odeg)
+                assert gdeg1 == odeg1 and np.abs(gx1 - ox1).max() <= 2e-5 * max(1.0, np.abs(ox1).max())
+        # not degenerate: the solution is the least-squares one
+        gx, gP, gdeg = h.solve_normal_eq(rows, b, 0b111111, 0, 10.0)
+        assert gdeg == 0 and np.abs(gx - x_true).max() < 2e-4
+
+
+def test_voxel_downsample_skips_non_finite_points(abi, orc):
+    """pcl::VoxelGrid drops non-finite points (they are neither binned nor counted)."""
+    rng = np.random.default_rng(12)
+    pts = np.concatenate([rng.uniform(-6, 6, (3000, 3)), rng.uniform(0, 16, (3000, 1))], 1).astype(np.float32)
+    bad = rng.choice(3000, 40, replace=False)
+    pts[bad[:20], 0] = np.nan
+    pts[bad[20:30], 1] = np.inf
+    pts[bad[30:], 2] = -np.inf
+    with abi.Handle() as h:
+        out, member, flags = h.voxel_downsample(pts, 0.4)
+    o_out, o_member, _ = orc.voxel_downsample(pts, 0.4)
+    assert np.array_equal(member, o_member) and (member[bad] == -1).all()
+    assert np.array_equal(bits(out), bits(o_out))
+
+
 # ------------------------------------------------------------------------------------------ a10 full loop
 def test_scan2map_pose_within_tolerance(abi, orc, single_problem, single_maps):
     d = single_problem
