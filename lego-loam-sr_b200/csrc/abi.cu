@@ -10,6 +10,7 @@
 #include <new>
 #include <string>
 #include <unordered_map>
+#include <utility>
 #include <vector>
 
 #include "common.cuh"
@@ -164,6 +165,21 @@ void prof_end(ll_handle h) {
     cudaError_t _e = cudaPeekAtLastError();                                                    \
     if (_e != cudaSuccess) return fail(h, LL_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(_e)); \
   } while (0)
+
+// Launch with programmatic stream serialization (see pdl_entry in common.cuh).
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(cudaStream_t stream, void (*kernel)(KArgs...), dim3 grid, dim3 block, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 int ensure_bytes(ll_handle h, void** p, size_t* cap, size_t need) {
   if (*cap >= need && *p) return LL_OK;
@@ -391,7 +407,8 @@ int run_map_pipeline(ll_handle h, int sa, int sb, const SegList& L, float leaf_a
   LL_TRY(upload_seglist(h, L));
   if (!L.jobs.empty()) {
     LL_PROF(h, 0);
-    transform_minmax_kernel<<<(unsigned)L.jobs.size(), MB_THREADS, 0, h->stream>>>(B, h->d_segs, h->d_jobs);
+    LL_CUDA(h, launch_pdl(h->stream, transform_minmax_kernel, dim3((unsigned)L.jobs.size()), dim3(MB_THREADS), B,
+                          (const Segment*)h->d_segs, (const BlockJob*)h->d_jobs));
     LL_LAUNCHED(h);
   }
   if (maxn == 0) return LL_OK;
@@ -399,18 +416,18 @@ int run_map_pipeline(ll_handle h, int sa, int sb, const SegList& L, float leaf_a
   const unsigned gx_sort = (unsigned)((maxn + RS_TILE - 1) / RS_TILE);
   if (ds_a || (sb >= 0 && ds_b)) {
     LL_PROF(h, 1);
-    voxel_keys_kernel<<<dim3(gx_pts, ny), MB_THREADS, 0, h->stream>>>(B);
+    LL_CUDA(h, launch_pdl(h->stream, voxel_keys_kernel, dim3(gx_pts, ny), dim3(MB_THREADS), B));
     LL_LAUNCHED(h);
     SortBatch SB;
     SB.p[0] = B.sort[0];
     SB.p[1] = B.sort[1];
     for (int pass = 0; pass < RS_MAX_PASSES; ++pass) {
       LL_PROF(h, 2);
-      rs_onesweep_kernel<<<dim3(gx_sort, ny), RS_THREADS, 0, h->stream>>>(SB, pass);
+      LL_CUDA(h, launch_pdl(h->stream, rs_onesweep_kernel, dim3(gx_sort, ny), dim3(RS_THREADS), SB, pass));
       LL_LAUNCHED(h);
     }
     LL_PROF(h, 3);
-    voxel_reduce_kernel<<<dim3(gx_pts, ny), MB_THREADS, 0, h->stream>>>(B);
+    LL_CUDA(h, launch_pdl(h->stream, voxel_reduce_kernel, dim3(gx_pts, ny), dim3(MB_THREADS), B));
     LL_LAUNCHED(h);
   }
   if (!build_grid) return LL_OK;
@@ -422,18 +439,18 @@ int run_map_pipeline(ll_handle h, int sa, int sb, const SegList& L, float leaf_a
   if (sb >= 0) B.sort[1] = slot_sort(h, sb, true);
   const unsigned gx_grid = std::max(gx_pts, (unsigned)(2 * h->num_sms));
   LL_PROF(h, 4);
-  grid_keys_kernel<<<dim3(gx_grid, ny), MB_THREADS, 0, h->stream>>>(B);
+  LL_CUDA(h, launch_pdl(h->stream, grid_keys_kernel, dim3(gx_grid, ny), dim3(MB_THREADS), B));
   LL_LAUNCHED(h);
   SortBatch SB;
   SB.p[0] = B.sort[0];
   SB.p[1] = B.sort[1];
   for (int pass = 0; pass < kGridPasses; ++pass) {
     LL_PROF(h, 5);
-    rs_onesweep_kernel<<<dim3(gx_sort, ny), RS_THREADS, 0, h->stream>>>(SB, pass);
+    LL_CUDA(h, launch_pdl(h->stream, rs_onesweep_kernel, dim3(gx_sort, ny), dim3(RS_THREADS), SB, pass));
     LL_LAUNCHED(h);
   }
   LL_PROF(h, 6);
-  grid_finalize_kernel<<<dim3(gx_pts, ny), MB_THREADS, 0, h->stream>>>(B);
+  LL_CUDA(h, launch_pdl(h->stream, grid_finalize_kernel, dim3(gx_pts, ny), dim3(MB_THREADS), B));
   LL_LAUNCHED(h);
   return LL_OK;
 }
@@ -518,7 +535,9 @@ int enqueue_iterations(ll_handle h, int count) {
   LMArgs A = make_lm_args(h, 0);
   for (int i = 0; i < count; ++i) {
     LL_PROF(h, 8);
-    lm_iter_kernel<<<h->lm_blocks, LM_THREADS, 0, h->stream>>>(A);
+    // iteration k+1 is set up (and its blocks become resident as SMs free up) while iteration k's last block is
+    // still solving
+    LL_CUDA(h, launch_pdl(h->stream, lm_iter_kernel, dim3((unsigned)h->lm_blocks), dim3(LM_THREADS), A));
     LL_LAUNCHED(h);
   }
   h->iters_enqueued += count;
@@ -533,8 +552,9 @@ int scan2map_enqueue(ll_handle h, const float pose6[6]) {
   h->lm_blocks = lm_grid_blocks(h, nq);
   LL_TRY(ensure_partials(h, h->lm_blocks));
   LL_PROF(h, 7);
-  lm_begin_kernel<<<1, 32, 0, h->stream>>>(h->d_state, h->slot[0].st(), h->slot[1].st(), make_lm_params(h->prm),
-                                           pose6[0], pose6[1], pose6[2], pose6[3], pose6[4], pose6[5]);
+  LL_CUDA(h, launch_pdl(h->stream, lm_begin_kernel, dim3(1), dim3(32), h->d_state, (const MapState*)h->slot[0].st(),
+                        (const MapState*)h->slot[1].st(), make_lm_params(h->prm), pose6[0], pose6[1], pose6[2], pose6[3],
+                        pose6[4], pose6[5]));
   LL_LAUNCHED(h);
   h->iters_enqueued = 0;
   const int first = std::min(std::max(h->prm.iter_count_thres, 0), kFirstChunk);

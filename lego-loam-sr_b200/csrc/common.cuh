@@ -49,6 +49,16 @@ __device__ __forceinline__ bool finite3(const float4 p) {
   return isfinite(p.x) && isfinite(p.y) && isfinite(p.z);
 }
 
+// Programmatic dependent launch (PDL). Every kernel of the per-scan chain is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization and starts with pdl_entry(): it waits until the previous
+// kernel's memory is visible, then lets the next kernel begin its own launch (block scheduling, parameter
+// fetch) while this one is still running. The chain is ~25 short dependent kernels per scan, so launch-to-launch
+// latency is a first-order cost. Both instructions are no-ops under a plain launch.
+__device__ __forceinline__ void pdl_entry() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;");
+}
+
 // Streaming 128-bit accesses: raw clouds are read once / written once per stage.
 __device__ __forceinline__ float4 ld_stream(const float4* p) { return __ldcs(p); }
 __device__ __forceinline__ void st_stream(float4* p, float4 v) { __stcs(p, v); }

@@ -663,9 +663,13 @@ __device__ void lm_solve_block(double* s_red, const LMParams& prm, LMState* S, b
     if (lane < 6) xs[lane] = x;
   } else if (warp == 1 && iter == 0) {  // :1507-1531, upstream semantics
     double w, v[6];
-    jacobi6_warp(AtA, lane, w, v);
+    jacobi6_warp<false>(AtA, lane, w, v);  // eigenvalues only
+    unsigned mb = __ballot_sync(FULL, lane < 6 && (float)w < prm.eig_thresh);
+    if (mb) {  // degenerate: the projector needs the eigenvectors too
+      jacobi6_warp<true>(AtA, lane, w, v);
+      mb = __ballot_sync(FULL, lane < 6 && (float)w < prm.eig_thresh);
+    }
     const bool below = lane < 6 && (float)w < prm.eig_thresh;
-    const unsigned mb = __ballot_sync(FULL, below);
     double wmin = lane < 6 ? w : 1.7976931348623157e308;
 #pragma unroll
     for (int o = 4; o > 0; o >>= 1) wmin = fmin(wmin, __shfl_xor_sync(FULL, wmin, o));
@@ -807,6 +811,9 @@ __device__ void reduce_partials_and_solve(const float* partials, int nblocks, co
 //   tail     block partial -> global; the last block to arrive adds all partials and solves.
 __global__ void __launch_bounds__(LM_THREADS, LM_MIN_BLOCKS) lm_iter_kernel(const __grid_constant__ LMArgs A) {
   LMState* S = A.st;
+  // Programmatic dependent launch (see enqueue_iterations): wait for the previous grid's results, then let the
+  // next grid start its own launch. Both are no-ops for a plain launch.
+  pdl_entry();
   if (A.mode == 0 && S->done) return;
   __shared__ __align__(16) float s_slot[LM_CHUNK * LM_SLOT];
   __shared__ float s_wacc[LM_WARPS][32];
@@ -940,6 +947,7 @@ __global__ void __launch_bounds__(LM_THREADS, LM_MIN_BLOCKS) lm_iter_kernel(cons
 // scan2MapOptimization prologue (:1573): the map-size guard and the loop state, one thread.
 __global__ void lm_begin_kernel(LMState* S, const MapState* corner, const MapState* surf, LMParams prm,
                                 float p0, float p1, float p2, float p3, float p4, float p5) {
+  pdl_entry();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   S->pose[0] = p0; S->pose[1] = p1; S->pose[2] = p2; S->pose[3] = p3; S->pose[4] = p4; S->pose[5] = p5;
   set_trig(S);

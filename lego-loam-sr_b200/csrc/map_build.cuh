@@ -90,6 +90,7 @@ __device__ __forceinline__ float warp_max(float v) {
 __global__ void __launch_bounds__(MB_THREADS) transform_minmax_kernel(const __grid_constant__ MapBatch B,
                                                                       const Segment* __restrict__ segs,
                                                                       const BlockJob* __restrict__ jobs) {
+  pdl_entry();
   const BlockJob job = jobs[blockIdx.x];
   const Segment s = segs[job.seg];
   const MapBuffers& M = B.m[s.map];
@@ -182,6 +183,7 @@ __device__ __forceinline__ VoxelMeta voxel_meta(const MapState* st, float inv) {
 }
 
 __global__ void __launch_bounds__(MB_THREADS) voxel_keys_kernel(const __grid_constant__ MapBatch B) {
+  pdl_entry();
   const MapBuffers& M = B.m[blockIdx.y];
   if (!M.downsample) return;
   const int n = M.n_raw;
@@ -234,6 +236,7 @@ __global__ void __launch_bounds__(MB_THREADS) voxel_keys_kernel(const __grid_con
 //      the segment length is known from the next head, so the loop is unrolled with the loads ahead of
 //      the adds; a segment that runs past the tile continues from global memory.
 __global__ void __launch_bounds__(MB_THREADS) voxel_reduce_kernel(const __grid_constant__ MapBatch B) {
+  pdl_entry();
   const MapBuffers& M = B.m[blockIdx.y];
   if (!M.downsample) return;
   const SortProblem& S = B.sort[blockIdx.y];
@@ -433,6 +436,7 @@ __global__ void __launch_bounds__(MB_THREADS) voxel_reduce_kernel(const __grid_c
 }
 
 __global__ void __launch_bounds__(MB_THREADS) grid_keys_kernel(const __grid_constant__ MapBatch B) {
+  pdl_entry();
   const MapBuffers& M = B.m[blockIdx.y];
   const SortProblem& S = B.sort[blockIdx.y];
   MapState* st = M.st;
@@ -485,6 +489,7 @@ __global__ void __launch_bounds__(MB_THREADS) grid_keys_kernel(const __grid_cons
 }
 
 __global__ void __launch_bounds__(MB_THREADS) grid_finalize_kernel(const __grid_constant__ MapBatch B) {
+  pdl_entry();
   const MapBuffers& M = B.m[blockIdx.y];
   const SortProblem& S = B.sort[blockIdx.y];
   const MapState* st = M.st;

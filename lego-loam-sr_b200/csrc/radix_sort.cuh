@@ -61,6 +61,7 @@ struct SortBatch {
 };
 
 __global__ void __launch_bounds__(RS_THREADS) rs_onesweep_kernel(const __grid_constant__ SortBatch batch, int pass) {
+  pdl_entry();
   const SortProblem& P = batch.p[blockIdx.y];
   const int bits = *P.bits;
   if (pass * 8 >= bits) return;  // digit is zero for every key: the pass is the identity

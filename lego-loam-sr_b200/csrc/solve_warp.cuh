@@ -152,7 +152,11 @@ __device__ __forceinline__ float qr66_warp(const float* AtA, const float* Atb, i
 }
 
 // All 32 lanes must call. A: row-major symmetric 6x6 (float, shared memory).
-// On return, lane l < 6 holds eigenvalue w and its eigenvector v[0..5] (unsorted; one eigenpair per lane).
+// On return, lane l < 6 holds eigenvalue w and (kVectors) its eigenvector v[0..5] (unsorted; one eigenpair per
+// lane). kVectors = false skips the accumulation of V (40 % of the shuffles): the common case only needs the
+// eigenvalues (min_lambda, and "is anything below the threshold?"). Sweeps stop when the off-diagonal mass is
+// below 1e-11 of the diagonal's, far beyond what the float outputs can see.
+template <bool kVectors>
 __device__ __forceinline__ void jacobi6_warp(const float* A, int lane, double& w, double v[6]) {
   double a[6];
 #pragma unroll
@@ -177,7 +181,7 @@ __device__ __forceinline__ void jacobi6_warp(const float* A, int lane, double& w
     }
     off = __shfl_sync(FULL, off, 0);
     diag = __shfl_sync(FULL, diag, 0);
-    if (off <= 1e-30 * diag || off == 0.0) break;
+    if (off <= 1e-22 * diag || off == 0.0) break;
 #pragma unroll
     for (int rd = 0; rd < 5; ++rd) {
       double cs[3], sn[3];
@@ -207,10 +211,10 @@ __device__ __forceinline__ void jacobi6_warp(const float* A, int lane, double& w
 #pragma unroll
       for (int r = 0; r < 6; ++r) {
         const double oa = __shfl_sync(FULL, a[r], partner);
-        const double ov = __shfl_sync(FULL, v[r], partner);
-        if (lane < 6) {
-          a[r] = is_p ? (myc * a[r] - mys * oa) : (mys * oa + myc * a[r]);
-          v[r] = is_p ? (myc * v[r] - mys * ov) : (mys * ov + myc * v[r]);
+        if (lane < 6) a[r] = is_p ? (myc * a[r] - mys * oa) : (mys * oa + myc * a[r]);
+        if (kVectors) {
+          const double ov = __shfl_sync(FULL, v[r], partner);
+          if (lane < 6) v[r] = is_p ? (myc * v[r] - mys * ov) : (mys * ov + myc * v[r]);
         }
       }
       // A <- J^T A: rows p, q of every column
