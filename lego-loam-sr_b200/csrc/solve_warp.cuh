@@ -187,25 +187,31 @@ __device__ __forceinline__ void jacobi6_warp(const float* A, int lane, double& w
       double cs[3], sn[3];
       int partner = lane;
       bool is_p = false;
-      double myc = 1.0, mys = 0.0;
+      // The three rotations of a round are independent: every lane gathers the 2x2 block of ITS pair and the
+      // (c, s) of all three pairs are computed at once (one divide + sqrt + rsqrt chain per round, not three).
+      double app = 0.0, apq = 0.0, aqq = 0.0;
 #pragma unroll
       for (int t = 0; t < 3; ++t) {
         const int p = P[rd][t], q = Q[rd][t];
         // lane q owns a_pq = a[p] and a_qq = a[q]; a_pp comes from lane p
-        const double app = __shfl_sync(FULL, a[p], p);
-        const double apq = __shfl_sync(FULL, a[p], q);
-        const double aqq = __shfl_sync(FULL, a[q], q);
-        double c = 1.0, s = 0.0;
-        if (apq != 0.0) {
-          const double theta = (aqq - app) / (2.0 * apq);
-          const double tt = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-          c = 1.0 / sqrt(tt * tt + 1.0);
-          s = tt * c;
-        }
-        cs[t] = c;
-        sn[t] = s;
-        if (lane == p) { partner = q; is_p = true; myc = c; mys = s; }
-        if (lane == q) { partner = p; is_p = false; myc = c; mys = s; }
+        const double t_pp = __shfl_sync(FULL, a[p], p);
+        const double t_pq = __shfl_sync(FULL, a[p], q);
+        const double t_qq = __shfl_sync(FULL, a[q], q);
+        if (lane == p || lane == q) { app = t_pp; apq = t_pq; aqq = t_qq; }
+        if (lane == p) { partner = q; is_p = true; }
+        if (lane == q) { partner = p; is_p = false; }
+      }
+      double myc = 1.0, mys = 0.0;
+      if (apq != 0.0) {
+        const double theta = (aqq - app) / (2.0 * apq);
+        const double tt = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+        myc = 1.0 / sqrt(tt * tt + 1.0);
+        mys = tt * myc;
+      }
+#pragma unroll
+      for (int t = 0; t < 3; ++t) {
+        cs[t] = __shfl_sync(FULL, myc, P[rd][t]);
+        sn[t] = __shfl_sync(FULL, mys, P[rd][t]);
       }
       // A <- A J and V <- V J: column p' = c p - s q, column q' = s p + c q
 #pragma unroll
