@@ -64,8 +64,13 @@ def parse_args():
     return ap.parse_args()
 
 
-def headline_params(mod):
-    return mod.default_params(apply_update=1, eigen_mode=1, iter_count_thres=ITERS, stop_thres=0.0)
+def headline_params(mod, **device_kw):
+    p = mod.default_params(apply_update=1, eigen_mode=1, iter_count_thres=ITERS, stop_thres=0.0)
+    if hasattr(p, "lm_solver"):  # execution knobs of the CUDA library (the oracle has no such choice)
+        p.lm_solver = 1          # 6x6 normal equations by LDL^T in double
+        for k, v in device_kw.items():
+            setattr(p, k, v)
+    return p
 
 
 def make_data(seed, n_scans):
@@ -235,7 +240,8 @@ def run_batch(args, rank, world, device):
         seqs[sid] = d
 
     def make_node():
-        return host.MapOptimization(headline_params(abi), device=device, loop_closure_enabled=True, search_num=WINDOW)
+        # several handles share the GPU: one launch per LM iteration so that their kernels interleave
+        return host.MapOptimization(headline_params(abi, persistent_lm=0), device=device, loop_closure_enabled=True, search_num=WINDOW)
 
     def feed(node, data, k):
         return node.process_frame_host(data["odom"][k], data["host"][k])
@@ -274,7 +280,8 @@ def algorithmic_bytes(cls, n_raw, n_ds, q):
         "grid_sort_pass": 16 * n_ds,
         "grid_finalize": 24 * n_ds + 16 * n_ds,
         "lm_begin": 0,
-        "lm_iter": 96 * q,                          # SURVEY.md §8d B_iter: query + five neighbours, 16 B each
+        "lm_iter": 96 * q * ITERS,                  # SURVEY.md §8d B_iter (query + five neighbours, 16 B each) x the
+                                                    # iterations one persistent launch runs
     }[cls]
 
 
@@ -354,7 +361,7 @@ def main():
     config = {"workload": "configs[1]: synthetic VLP-16 trajectory replay, sliding local map of the last %d keyframes, "
                           "%d LM iterations per scan" % (WINDOW, ITERS),
               "sensor": "VLP-16 16x1800", "metres_per_scan": BENCH_STEP_M, "window_keyframes": WINDOW,
-              "lm_iterations": ITERS, "apply_update": 1, "eigen_mode": "upstream", "prefill_scans": prefill,
+              "lm_iterations": ITERS, "apply_update": 1, "eigen_mode": "upstream", "lm_solver": "ldlt-f64", "persistent_lm": 1, "prefill_scans": prefill,
               "sequences_per_gpu": 1, "l2": "flushed before every timed step (256 MiB memset)" if not args.no_l2_flush else "not flushed"}
 
     if args.impl == "reference":

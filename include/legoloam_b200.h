@@ -63,6 +63,12 @@ typedef struct {
   int    map_downsample;   /* 1 = VoxelGrid on the surrounding maps (:1225-1231); 0 = bypass */
   int    min_corner_map;   /* 10   :1573 */
   int    min_surf_map;     /* 100  :1573 */
+  int    lm_solver;        /* how matAtA x = matAtB is solved (:1505). 0 (default) = Eigen's ColPivHouseholderQR step
+                              sequence in float; 1 = LDL^T in double (same system solved to double accuracy; falls
+                              back to 0 when AtA is rank deficient). Pose parity holds for both (tests). */
+  int    persistent_lm;    /* 1 (default) = the whole iteration loop of scan2MapOptimization in one cooperative launch
+                              (one block per SM, grid barrier per iteration); 0 = one launch per iteration (use this
+                              when several handles share a GPU and should interleave, e.g. batched replay). */
 } ll_params;
 
 /* What scan2MapOptimization leaves behind (mapOptmization.cpp:1602-1607 and members). */

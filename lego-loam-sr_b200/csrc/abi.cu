@@ -30,6 +30,7 @@ constexpr int kGridPasses = 3;
 constexpr int kPinSlots = 4;                 // pinned staging buffers in flight
 constexpr int kFirstChunk = 12;              // LM iterations enqueued before the first look at `done`
 constexpr int kNextChunk = 16;
+constexpr int kBarrierSlots = 64;
 
 struct Keyframe {
   float4* d[3] = {nullptr, nullptr, nullptr};  // corner, surf, outlier (device, packed float4, sensor frame)
@@ -93,7 +94,9 @@ struct ll_handle_s {
 
   LMState* d_state = nullptr;
   LMState* h_state = nullptr;  // pinned mirror
-  float* d_partials = nullptr;
+  float* d_partials = nullptr;   // [2][partial_blocks][32] (double-buffered by iteration parity in the persistent kernel)
+  unsigned* d_barriers = nullptr;  // ring of kBarrierSlots grid-barrier counters, one per scan, re-armed 32 scans ahead
+  uint64_t scan_seq = 0;
   int partial_blocks = 0;
   bool scan_pending = false;
   int iters_enqueued = 0;
@@ -471,6 +474,7 @@ LMParams make_lm_params(const ll_params& p) {
   q.apply_update = p.apply_update;
   q.min_corner_map = p.min_corner_map;
   q.min_surf_map = p.min_surf_map;
+  q.lm_solver = p.lm_solver;
   return q;
 }
 
@@ -480,6 +484,8 @@ int validate_params(ll_handle h, const ll_params* p) {
   if (!(p->max_sq_dist > 0.f) || p->max_sq_dist > 1.0f)
     return fail(h, LL_ERR_INVALID_ARG, "max_sq_dist must be in (0, 1]: the 1 m search grid is exact only up to 1 m");
   if (p->eigen_mode != 0 && p->eigen_mode != 1) return fail(h, LL_ERR_INVALID_ARG, "eigen_mode must be 0 or 1");
+  if (p->lm_solver != 0 && p->lm_solver != 1) return fail(h, LL_ERR_INVALID_ARG, "lm_solver must be 0 or 1");
+  if (p->persistent_lm != 0 && p->persistent_lm != 1) return fail(h, LL_ERR_INVALID_ARG, "persistent_lm must be 0 or 1");
   return LL_OK;
 }
 
@@ -516,7 +522,7 @@ int ensure_partials(ll_handle h, int blocks) {
   if (h->d_partials) LL_CUDA(h, cudaFree(h->d_partials));
   h->d_partials = nullptr;
   const int cap = std::max(blocks, h->num_sms * 4);
-  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&h->d_partials), sizeof(float) * 32 * (size_t)cap);
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&h->d_partials), sizeof(float) * 32 * 2 * (size_t)cap);
   if (e != cudaSuccess) return fail(h, LL_ERR_NOMEM, std::string("cudaMalloc(partials): ") + cudaGetErrorString(e));
   h->partial_blocks = cap;
   return LL_OK;
@@ -551,6 +557,23 @@ int scan2map_enqueue(ll_handle h, const float pose6[6]) {
   const int nq = h->nq[0] + h->nq[1];
   h->lm_blocks = lm_grid_blocks(h, nq);
   LL_TRY(ensure_partials(h, h->lm_blocks));
+  if (h->prm.persistent_lm) {
+    // the whole loop in one cooperative launch (all blocks co-resident: lm_blocks <= number of SMs, one block per SM)
+    LMArgs A = make_lm_args(h, 0);
+    float p[6] = {pose6[0], pose6[1], pose6[2], pose6[3], pose6[4], pose6[5]};
+    unsigned* bar = h->d_barriers + (h->scan_seq % kBarrierSlots);
+    unsigned* bar_clear = h->d_barriers + ((h->scan_seq + kBarrierSlots / 2) % kBarrierSlots);
+    h->scan_seq++;
+    void* args[] = {&A, &p[0], &p[1], &p[2], &p[3], &p[4], &p[5], &bar, &bar_clear};
+    LL_PROF(h, 8);
+    LL_CUDA(h, cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(lm_persistent_kernel), dim3((unsigned)h->lm_blocks),
+                                           dim3(LM_THREADS), args, 0, h->stream));
+    LL_LAUNCHED(h);
+    h->iters_enqueued = h->prm.iter_count_thres;
+    LL_CUDA(h, cudaMemcpyAsync(h->h_state, h->d_state, sizeof(LMState), cudaMemcpyDeviceToHost, h->stream));
+    h->scan_pending = true;
+    return LL_OK;
+  }
   LL_PROF(h, 7);
   LL_CUDA(h, launch_pdl(h->stream, lm_begin_kernel, dim3(1), dim3(32), h->d_state, (const MapState*)h->slot[0].st(),
                         (const MapState*)h->slot[1].st(), make_lm_params(h->prm), pose6[0], pose6[1], pose6[2], pose6[3],
@@ -658,6 +681,8 @@ int ll_default_params(ll_params* p) {
   p->map_downsample = 1;
   p->min_corner_map = 10;
   p->min_surf_map = 100;
+  p->lm_solver = 0;
+  p->persistent_lm = 1;
   return LL_OK;
 }
 
@@ -682,6 +707,8 @@ int ll_create(const ll_params* p, int device_id, ll_handle* out) {
     ev_ok = ev_ok && cudaEventCreateWithFlags(&h->pin_evt[i], cudaEventDisableTiming) == cudaSuccess;
   bool ok = ev_ok && cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess &&
             cudaMalloc(reinterpret_cast<void**>(&h->d_state), sizeof(LMState)) == cudaSuccess &&
+            cudaMalloc(reinterpret_cast<void**>(&h->d_barriers), sizeof(unsigned) * kBarrierSlots) == cudaSuccess &&
+            cudaMemsetAsync(h->d_barriers, 0, sizeof(unsigned) * kBarrierSlots, h->stream) == cudaSuccess &&
             cudaMallocHost(reinterpret_cast<void**>(&h->h_state), sizeof(LMState)) == cudaSuccess &&
             cudaMemsetAsync(h->d_state, 0, sizeof(LMState), h->stream) == cudaSuccess &&
             cudaStreamSynchronize(h->stream) == cudaSuccess;
@@ -704,7 +731,7 @@ int ll_destroy(ll_handle h) {
     for (void* p : ptrs)
       if (p) cudaFree(p);
   }
-  void* ptrs[] = {h->d_segs, h->d_jobs, h->dq[0], h->dq[1], h->d_state, h->d_partials,
+  void* ptrs[] = {h->d_segs, h->d_jobs, h->dq[0], h->dq[1], h->d_state, h->d_partials, h->d_barriers,
                   h->d_tmp[0], h->d_tmp[1], h->d_tmp[2], h->d_tmp[3], h->d_tmp[4], h->d_tmp[5]};
   for (void* p : ptrs)
     if (p) cudaFree(p);

@@ -26,7 +26,8 @@ constexpr int LM_WARPS = LM_THREADS / 32;
 constexpr int LM_MIN_BLOCKS = 1;         // resident blocks per SM the register budget is sized for
 constexpr int LM_NSUM = 29;              // 21 AtA + 6 Atb + sum|d| + count
 constexpr int LM_SLOT = 21;              // floats staged per query (odd => bank-conflict-free per-thread reads)
-constexpr int LM_CHUNK = LM_THREADS;     // queries a block stages per pass
+constexpr int LM_CHUNK = LM_THREADS - 32;  // queries a block stages per pass (one warp of slack: corner and surf
+                                           // queries of a pass are placed in different warps, see lm_iter_kernel)
 constexpr int LM_CAND_UNROLL = 4;        // candidate loads in flight per lane during the 5-NN scan
 constexpr uint32_t LM_EMPTY_D2 = 0x7f800000u;  // +inf: "no candidate"
 
@@ -40,6 +41,7 @@ struct LMParams {
   int apply_update;
   int min_corner_map;
   int min_surf_map;
+  int lm_solver;  // 0 = Eigen's ColPivHouseholderQR step sequence (qr66_warp), 1 = LDL^T in double (ldlt6_solve)
 };
 
 // Persistent per-handle state; the members of MapOptimization the hot path reads and writes
@@ -521,10 +523,24 @@ __device__ __forceinline__ bool pair_less(uint32_t da, uint32_t ia, uint32_t db,
 // All 32 lanes of a warp cooperate on ONE query (sx, sy, sz) already in the map frame.
 //  1. lanes 0..26 each fetch one of the 27 cell descriptors (a single load round trip);
 //  2. the three x-adjacent cells of a row are contiguous in the cell-sorted array, so two shuffles merge
-//     them into 9 [start, count) ranges, which are then broadcast to every lane;
-//  3. lane l evaluates candidates l, l+32, ... of the concatenated ranges (consecutive float4s) and keeps
-//     its own best five in registers;
-//  4. five rounds of redux.sync pick the global best five by (d2, map index).
+//     them into 9 [start, count) ranges; they are broadcast centre row first (the row of the query's own
+//     cell holds the nearest points, so the running 5th-best distance is tight from the first chunk on);
+//  3. candidates are taken 128 at a time: lane l owns candidates l, l+32, l+64, l+96 of the concatenated
+//     ranges (consecutive float4s; all four loads in flight before any is consumed), sorts its four
+//     (d2, index) pairs with a 5-comparator network, and five rounds of redux.sync pop the warp-wide
+//     minimum by (d2, map index). A typical VLP-16 query has 50-110 candidates: one chunk.
+//  4. with more than 128 candidates the best five so far are carried in uniform registers, later
+//     candidates are pre-filtered against the carried 5th best, and chunks without survivors are skipped.
+// The result is the exact five smallest (d2, index) pairs with d2 < max_sq_dist, independent of the
+// order in which candidates are visited.
+#define LL_KNN_CE(a, b)                                                  \
+  {                                                                      \
+    const bool sw_ = pair_less(cd[b], ci[b], cd[a], ci[a]);              \
+    const uint32_t d_ = sw_ ? cd[b] : cd[a], i_ = sw_ ? ci[b] : ci[a], p_ = sw_ ? cp[b] : cp[a]; \
+    cd[b] = sw_ ? cd[a] : cd[b]; ci[b] = sw_ ? ci[a] : ci[b]; cp[b] = sw_ ? cp[a] : cp[b];        \
+    cd[a] = d_; ci[a] = i_; cp[a] = p_;                                  \
+  }
+
 __device__ __forceinline__ Knn5 warp_knn5(const float4* __restrict__ sorted, const int2* __restrict__ cells,
                                           const GridGeom& g, float sx, float sy, float sz, float max_sq_dist,
                                           int lane) {
@@ -541,40 +557,46 @@ __device__ __forceinline__ Knn5 warp_knn5(const float4* __restrict__ sorted, con
   s = min(s, min(s1, s2));
   e = max(e, max(e1, e2));
   const int my_start = e > 0 ? s : 0, my_count = e > 0 ? e - s : 0;  // meaningful on lanes 0, 3, ..., 24
-  int rs[9], rc[9];
+  // pr[k] = candidates before range k, bs[k] = (start of range k) - pr[k]: candidate j of the concatenation
+  // lives at sorted[j + bs[k]] for the last k with pr[k] <= j. Range order: centre row first.
+  constexpr int kRowLane[9] = {12, 3, 9, 15, 21, 0, 6, 18, 24};
+  int pr[9], bs[9];
   int total = 0;
 #pragma unroll
-  for (int r = 0; r < 9; ++r) {
-    rs[r] = __shfl_sync(0xffffffffu, my_start, 3 * r);
-    rc[r] = __shfl_sync(0xffffffffu, my_count, 3 * r);
-    total += rc[r];
+  for (int k = 0; k < 9; ++k) {
+    const int st = __shfl_sync(0xffffffffu, my_start, kRowLane[k]);
+    const int cn = __shfl_sync(0xffffffffu, my_count, kRowLane[k]);
+    pr[k] = total;
+    bs[k] = st - total;
+    total += cn;
   }
-  // per-lane sorted list of the best five candidates this lane has seen
-  uint32_t ld[5], li[5], lp[5];
-#pragma unroll
-  for (int k = 0; k < 5; ++k) { ld[k] = LM_EMPTY_D2; li[k] = 0xffffffffu; lp[k] = 0xffffffffu; }
   const uint32_t max_bits = __float_as_uint(max_sq_dist);
-  for (int j0 = lane; j0 < total; j0 += 32 * LM_CAND_UNROLL) {
-    // up to LM_CAND_UNROLL candidates per lane are fetched before any is consumed (one load round trip)
+  Knn5 K;  // best five so far (warp-uniform), ascending
+#pragma unroll
+  for (int k = 0; k < 5; ++k) { K.d2[k] = LM_EMPTY_D2; K.idx[k] = 0xffffffffu; K.pos[k] = 0xffffffffu; }
+  for (int j0 = 0; j0 < total; j0 += 32 * LM_CAND_UNROLL) {
+    const bool first = j0 == 0;
     int srcs[LM_CAND_UNROLL];
     float4 ms[LM_CAND_UNROLL];
 #pragma unroll
     for (int u = 0; u < LM_CAND_UNROLL; ++u) {
-      const int j = j0 + 32 * u;
-      int base = 0, src = -1;
+      srcs[u] = -1;
+      if (j0 + 32 * u < total) {  // warp-uniform
+        const int j = j0 + 32 * u + lane;
+        int b = bs[0];
 #pragma unroll
-      for (int r = 0; r < 9; ++r) {
-        if (j >= base && j < base + rc[r]) src = rs[r] + (j - base);
-        base += rc[r];
+        for (int k = 1; k < 9; ++k)
+          if (j >= pr[k]) b = bs[k];
+        if (j < total) srcs[u] = j + b;
       }
-      srcs[u] = src;  // -1 when j >= total
     }
 #pragma unroll
     for (int u = 0; u < LM_CAND_UNROLL; ++u)
       ms[u] = srcs[u] >= 0 ? __ldg(&sorted[srcs[u]]) : make_float4(0.f, 0.f, 0.f, 0.f);
+    uint32_t cd[LM_CAND_UNROLL], ci[LM_CAND_UNROLL], cp[LM_CAND_UNROLL];
+    bool any = false;
 #pragma unroll
     for (int u = 0; u < LM_CAND_UNROLL; ++u) {
-      if (srcs[u] < 0) continue;
       const float4 m = ms[u];
       // L2_Simple_Adaptor::evalMetric (nanoflann.hpp:431-439): ((dx^2) + dy^2) + dz^2, no contraction
       float df = sx - m.x;
@@ -585,39 +607,46 @@ __device__ __forceinline__ Knn5 warp_knn5(const float4* __restrict__ sorted, con
       d += df * df;
       const uint32_t db = __float_as_uint(d);
       const uint32_t ib = __float_as_uint(m.w);
-      if (db < max_bits && pair_less(db, ib, ld[4], li[4])) {
-        ld[4] = db; li[4] = ib; lp[4] = (uint32_t)srcs[u];
+      const bool ok = srcs[u] >= 0 && db < max_bits && (first || pair_less(db, ib, K.d2[4], K.idx[4]));
+      cd[u] = ok ? db : LM_EMPTY_D2;
+      ci[u] = ok ? ib : 0xffffffffu;
+      cp[u] = ok ? (uint32_t)srcs[u] : 0xffffffffu;
+      any = any || ok;
+    }
+    if (!first && !__any_sync(0xffffffffu, any)) continue;  // nothing in this chunk beats the carried five
+    static_assert(LM_CAND_UNROLL == 4, "the sorting network below is written for four candidates per lane");
+    LL_KNN_CE(0, 1) LL_KNN_CE(2, 3) LL_KNN_CE(0, 2) LL_KNN_CE(1, 3) LL_KNN_CE(1, 2)
+    // five rounds: warp-wide arg-min over the list heads (ties broken by the lower map index), merged with the
+    // carried list
+    Knn5 out;
 #pragma unroll
-        for (int k = 4; k > 0; --k) {
-          if (pair_less(ld[k], li[k], ld[k - 1], li[k - 1])) {
-            uint32_t t = ld[k]; ld[k] = ld[k - 1]; ld[k - 1] = t;
-            t = li[k]; li[k] = li[k - 1]; li[k - 1] = t;
-            t = lp[k]; lp[k] = lp[k - 1]; lp[k - 1] = t;
-          }
+    for (int r = 0; r < 5; ++r) {
+      const uint32_t m = __reduce_min_sync(0xffffffffu, cd[0]);
+      const uint32_t om = __reduce_min_sync(0xffffffffu, cd[0] == m ? ci[0] : 0xffffffffu);
+      const bool carried = !first && pair_less(K.d2[0], K.idx[0], m, om);  // warp-uniform
+      if (carried) {
+        out.d2[r] = K.d2[0]; out.idx[r] = K.idx[0]; out.pos[r] = K.pos[0];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { K.d2[k] = K.d2[k + 1]; K.idx[k] = K.idx[k + 1]; K.pos[k] = K.pos[k + 1]; }
+        K.d2[4] = LM_EMPTY_D2; K.idx[4] = 0xffffffffu; K.pos[4] = 0xffffffffu;
+      } else {
+        const bool win = (cd[0] == m) && (ci[0] == om) && (m != LM_EMPTY_D2);
+        const uint32_t pw = __reduce_min_sync(0xffffffffu, win ? cp[0] : 0xffffffffu);
+        out.d2[r] = m; out.idx[r] = om; out.pos[r] = pw;
+        if (win) {
+#pragma unroll
+          for (int k = 0; k < LM_CAND_UNROLL - 1; ++k) { cd[k] = cd[k + 1]; ci[k] = ci[k + 1]; cp[k] = cp[k + 1]; }
+          cd[LM_CAND_UNROLL - 1] = LM_EMPTY_D2; ci[LM_CAND_UNROLL - 1] = 0xffffffffu; cp[LM_CAND_UNROLL - 1] = 0xffffffffu;
         }
       }
     }
-  }
-  // five rounds of warp-wide arg-min over the list heads, ties broken by the lower map index
-  Knn5 out;
 #pragma unroll
-  for (int r = 0; r < 5; ++r) {
-    const uint32_t m = __reduce_min_sync(0xffffffffu, ld[0]);
-    const uint32_t om = __reduce_min_sync(0xffffffffu, ld[0] == m ? li[0] : 0xffffffffu);
-    const bool win = (ld[0] == m) && (li[0] == om) && (m != LM_EMPTY_D2);
-    const uint32_t pw = __reduce_min_sync(0xffffffffu, win ? lp[0] : 0xffffffffu);
-    out.d2[r] = m;
-    out.idx[r] = om;
-    out.pos[r] = pw;
-    if (win) {
-#pragma unroll
-      for (int k = 0; k < 4; ++k) { ld[k] = ld[k + 1]; li[k] = li[k + 1]; lp[k] = lp[k + 1]; }
-      ld[4] = LM_EMPTY_D2; li[4] = 0xffffffffu; lp[4] = 0xffffffffu;
-    }
+    for (int k = 0; k < 5; ++k) { K.d2[k] = out.d2[k]; K.idx[k] = out.idx[k]; K.pos[k] = out.pos[k]; }
   }
-  out.accept = out.d2[4] != LM_EMPTY_D2;  // five neighbours, all with d2 < max_sq_dist (:1279 / :1389)
-  return out;
+  K.accept = K.d2[4] != LM_EMPTY_D2;  // five neighbours, all with d2 < max_sq_dist (:1279 / :1389)
+  return K;
 }
+#undef LL_KNN_CE
 
 // The 29 running sums of one LM iteration in a fixed order: 21 upper-triangular AtA entries (row-major),
 // 6 Atb entries, sum |d|, count. sv = [row0..row5, b, |d|].
@@ -658,8 +687,16 @@ __device__ void lm_solve_block(double* s_red, const LMParams& prm, LMState* S, b
     Atb[tid - 36] = (float)s_red[21 + tid - 36];
   }
   __syncthreads();
-  if (warp == 0) {
-    const float x = qr66_warp(AtA, Atb, lane);  // :1505
+  if (warp == 0) {  // :1505
+    float x = 0.f;
+    float xv[6];
+    if (prm.lm_solver == 1 && ldlt6_solve(AtA, Atb, xv)) {  // every lane computes the same six numbers
+#pragma unroll
+      for (int r = 0; r < 6; ++r)
+        if (lane == r) x = xv[r];
+    } else {
+      x = qr66_warp(AtA, Atb, lane);
+    }
     if (lane < 6) xs[lane] = x;
   } else if (warp == 1 && iter == 0) {  // :1507-1531, upstream semantics
     double w, v[6];
@@ -780,18 +817,18 @@ __device__ void reduce_partials_and_solve(const float* partials, int nblocks, co
                                           bool stage_mode, double* s_red /* [nwarps][32] shared */) {
   const int lane = threadIdx.x & 31, sub = threadIdx.x >> 5, nsub = blockDim.x >> 5;
   double acc = 0.0;
-  int b = sub;
-  for (; b + 3 * nsub < nblocks; b += 4 * nsub) {  // four loads in flight, added in the same order as a plain loop
-    const float v0 = __ldcg(&partials[b * 32 + lane]);
-    const float v1 = __ldcg(&partials[(b + nsub) * 32 + lane]);
-    const float v2 = __ldcg(&partials[(b + 2 * nsub) * 32 + lane]);
-    const float v3 = __ldcg(&partials[(b + 3 * nsub) * 32 + lane]);
-    acc += (double)v0;
-    acc += (double)v1;
-    acc += (double)v2;
-    acc += (double)v3;
+  constexpr int kInFlight = 10;  // 148 blocks / 16 warps: every partial of a warp's share is fetched in one round trip
+  for (int b = sub; b < nblocks; b += kInFlight * nsub) {  // added in the same order as a plain loop
+    float v[kInFlight];
+#pragma unroll
+    for (int u = 0; u < kInFlight; ++u) {
+      const int bb = b + u * nsub;
+      v[u] = bb < nblocks ? __ldcg(&partials[bb * 32 + lane]) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < kInFlight; ++u)
+      if (b + u * nsub < nblocks) acc += (double)v[u];
   }
-  for (; b < nblocks; b += nsub) acc += (double)__ldcg(&partials[b * 32 + lane]);
   s_red[sub * 32 + lane] = acc;
   __syncthreads();
   if (threadIdx.x < 32) {
@@ -803,37 +840,25 @@ __device__ void reduce_partials_and_solve(const float* partials, int nblocks, co
   lm_solve_block(s_red, prm, S, stage_mode);
 }
 
-// One LM iteration. Each block owns a contiguous chunk of the query list (corner queries first, then surf):
+// Phases 1 and 2 of one LM iteration over queries [q_begin, q_end) of the concatenated query list (corner
+// queries first, then surf):
 //   phase 1  one warp per query: pointAssociateToMap + 5-NN; the five neighbours and the transformed query
 //            are staged in shared memory (21 floats per query, odd stride => conflict-free);
 //   phase 2  one thread per query: line / plane fit, Jacobian row, then a shuffle-tree reduction of the 29
-//            sums over the block (fixed order => bitwise repeatable);
-//   tail     block partial -> global; the last block to arrive adds all partials and solves.
-__global__ void __launch_bounds__(LM_THREADS, LM_MIN_BLOCKS) lm_iter_kernel(const __grid_constant__ LMArgs A) {
-  LMState* S = A.st;
-  // Programmatic dependent launch (see enqueue_iterations): wait for the previous grid's results, then let the
-  // next grid start its own launch. Both are no-ops for a plain launch.
-  pdl_entry();
-  if (A.mode == 0 && S->done) return;
-  __shared__ __align__(16) float s_slot[LM_CHUNK * LM_SLOT];
-  __shared__ float s_wacc[LM_WARPS][32];
-  __shared__ int s_last;
+//            sums over the block (fixed order => bitwise repeatable).
+// Returns, on threads 0..28, this block's total of sum `tid`.
+__device__ __forceinline__ float lm_block_pass(const LMArgs& A, const Trig& trig, const RotTrig& rt,
+                                               const GridGeom (&geom)[2], float* s_slot, float (*s_wacc)[32],
+                                               int q_begin, int q_end) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const Trig trig = S->trig;
-  const RotTrig rt = S->rtrig;
-  GridGeom geom[2];
-#pragma unroll
-  for (int m = 0; m < 2; ++m) {
-    const MapState* ms = A.mst[m];
-    geom[m].ox = ms->gox; geom[m].oy = ms->goy; geom[m].oz = ms->goz;
-    geom[m].dx = ms->gdx; geom[m].dy = ms->gdy; geom[m].dz = ms->gdz;
-  }
-  const int nq = A.nq[0] + A.nq[1];
-  const int per = (nq + gridDim.x - 1) / gridDim.x;
-  const int q_begin = min(nq, (int)blockIdx.x * per), q_end = min(nq, q_begin + per);
   float run_sum = 0.f;  // threads 0..28: this block's running total of sum `tid`
   for (int c0 = q_begin; c0 < q_end; c0 += LM_CHUNK) {
     const int cn = min(LM_CHUNK, q_end - c0);
+    // Staging slot of query i of this pass = the thread that fits it in phase 2. Corner queries come first; the
+    // surf queries start at the next warp boundary so that no warp runs corner_fit and surf_fit back to back.
+    const int nc = max(0, min(cn, A.nq[0] - c0));
+    const int nc_pad = (nc + 31) & ~31;
+    const int nslots = nc_pad + (cn - nc);
     // ---- phase 1: k-NN, one warp per query
     float4 p_next = make_float4(0.f, 0.f, 0.f, 0.f);
     if (warp < cn) {
@@ -851,7 +876,7 @@ __global__ void __launch_bounds__(LM_THREADS, LM_MIN_BLOCKS) lm_iter_kernel(cons
       const float4 sel = (A.mode == 2) ? p : rigid_transform(trig, p);
       const GridGeom g = m ? geom[1] : geom[0];
       const Knn5 nn = warp_knn5(A.sorted[m], A.cells[m], g, sel.x, sel.y, sel.z, A.prm.fit.max_sq_dist, lane);
-      float* slot = &s_slot[i * LM_SLOT];
+      float* slot = &s_slot[(i < nc ? i : nc_pad + (i - nc)) * LM_SLOT];
       if (lane < 5) {
         uint32_t pos = nn.pos[0], d = nn.d2[0], ix = nn.idx[0];
 #pragma unroll
@@ -881,8 +906,9 @@ __global__ void __launch_bounds__(LM_THREADS, LM_MIN_BLOCKS) lm_iter_kernel(cons
     if (A.mode != 2) {
       float sv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       float one = 0.f;
-      if (tid < cn) {
-        const int qi = c0 + tid;
+      const int my_i = tid < nc ? tid : (tid >= nc_pad && tid < nslots ? nc + (tid - nc_pad) : -1);
+      if (my_i >= 0) {
+        const int qi = c0 + my_i;
         const int m = qi < A.nq[0] ? 0 : 1;
         const float* slot = &s_slot[tid * LM_SLOT];
         float coeff[4] = {0.f, 0.f, 0.f, 0.f};
@@ -909,7 +935,7 @@ __global__ void __launch_bounds__(LM_THREADS, LM_MIN_BLOCKS) lm_iter_kernel(cons
         }
       }
       if (A.mode == 0) {
-        if (warp * 32 < cn) {  // warp-uniform
+        if (warp * 32 < nslots) {  // warp-uniform
 #pragma unroll
           for (int k = 0; k < LM_NSUM; ++k) {
             float v = lm_term(sv, one, k);
@@ -920,13 +946,46 @@ __global__ void __launch_bounds__(LM_THREADS, LM_MIN_BLOCKS) lm_iter_kernel(cons
         }
         __syncthreads();
         if (tid < LM_NSUM) {
-          const int nw = (cn + 31) >> 5;
+          const int nw = (nslots + 31) >> 5;
           for (int w = 0; w < nw; ++w) run_sum += s_wacc[w][tid];
         }
       }
     }
     __syncthreads();
   }
+  return run_sum;
+}
+
+__device__ __forceinline__ void lm_load_geom(const LMArgs& A, GridGeom (&geom)[2]) {
+#pragma unroll
+  for (int m = 0; m < 2; ++m) {
+    const MapState* ms = A.mst[m];
+    geom[m].ox = ms->gox; geom[m].oy = ms->goy; geom[m].oz = ms->goz;
+    geom[m].dx = ms->gdx; geom[m].dy = ms->gdy; geom[m].dz = ms->gdz;
+  }
+}
+
+// One LM iteration per launch (stage-level entry points, and scan2map when persistent_lm = 0). Each block owns
+// a contiguous chunk of the query list; block partial -> global; the last block to arrive adds all partials in
+// a fixed order and solves.
+__global__ void __launch_bounds__(LM_THREADS, LM_MIN_BLOCKS) lm_iter_kernel(const __grid_constant__ LMArgs A) {
+  LMState* S = A.st;
+  // Programmatic dependent launch (see enqueue_iterations): wait for the previous grid's results, then let the
+  // next grid start its own launch. Both are no-ops for a plain launch.
+  pdl_entry();
+  if (A.mode == 0 && S->done) return;
+  __shared__ __align__(16) float s_slot[LM_THREADS * LM_SLOT];
+  __shared__ float s_wacc[LM_WARPS][32];
+  __shared__ int s_last;
+  const int tid = threadIdx.x;
+  const Trig trig = S->trig;
+  const RotTrig rt = S->rtrig;
+  GridGeom geom[2];
+  lm_load_geom(A, geom);
+  const int nq = A.nq[0] + A.nq[1];
+  const int per = (nq + gridDim.x - 1) / gridDim.x;
+  const int q_begin = min(nq, (int)blockIdx.x * per), q_end = min(nq, q_begin + per);
+  const float run_sum = lm_block_pass(A, trig, rt, geom, s_slot, s_wacc, q_begin, q_end);
   if (A.mode != 0) return;
   if (tid < 32) {
     A.partials[blockIdx.x * 32 + tid] = tid < LM_NSUM ? run_sum : 0.f;
@@ -944,12 +1003,11 @@ __global__ void __launch_bounds__(LM_THREADS, LM_MIN_BLOCKS) lm_iter_kernel(cons
   reduce_partials_and_solve(A.partials, gridDim.x, A.prm, S, false, reinterpret_cast<double*>(s_slot));
 }
 
-// scan2MapOptimization prologue (:1573): the map-size guard and the loop state, one thread.
-__global__ void lm_begin_kernel(LMState* S, const MapState* corner, const MapState* surf, LMParams prm,
-                                float p0, float p1, float p2, float p3, float p4, float p5) {
-  pdl_entry();
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  S->pose[0] = p0; S->pose[1] = p1; S->pose[2] = p2; S->pose[3] = p3; S->pose[4] = p4; S->pose[5] = p5;
+// The map-size guard and loop state of scan2MapOptimization (:1573), applied to *S by one thread.
+__device__ __forceinline__ void lm_begin_state(LMState* S, const MapState* corner, const MapState* surf, const LMParams& prm,
+                                               const float pose6[6]) {
+#pragma unroll
+  for (int i = 0; i < 6; ++i) S->pose[i] = pose6[i];
   set_trig(S);
   S->iter = 0;
   S->iter_num = 0;
@@ -968,6 +1026,80 @@ __global__ void lm_begin_kernel(LMState* S, const MapState* corner, const MapSta
   S->status = ok ? 0 : 1;
   S->done = ok ? 0 : 1;
   if (prm.iter_count_thres <= 0) S->done = 1;
+}
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// The whole loop of scan2MapOptimization (:1572-1610) in ONE cooperative launch (persistent_lm = 1): one block
+// per SM, all co-resident. Every block keeps its own copy of the loop state (pose, sin/cos, matP, counters) in
+// shared memory. Per iteration: phases 1 and 2 over the block's share of the queries -> block partial to global
+// (double-buffered by iteration parity) -> grid barrier (one arrive counter, monotonically increasing within the
+// scan) -> EVERY block adds all partials in the same fixed order and runs the same 6x6 solve, so all blocks hold
+// bit-identical new poses without a publish / observe round trip, and nothing waits for a kernel boundary.
+// Block 0 writes the final state back.  barrier: this scan's arrive counter (zero on entry); barrier_clear: the
+// counter a later scan will use (ring of counters in the handle, re-armed 32 scans ahead).
+__global__ void __launch_bounds__(LM_THREADS, 1) lm_persistent_kernel(const __grid_constant__ LMArgs A, float p0, float p1,
+                                                                      float p2, float p3, float p4, float p5,
+                                                                      unsigned* barrier, unsigned* barrier_clear) {
+  __shared__ __align__(16) float s_slot[LM_THREADS * LM_SLOT];
+  __shared__ float s_wacc[LM_WARPS][32];
+  __shared__ __align__(16) LMState s_st;
+  const int tid = threadIdx.x;
+  {  // prologue: the persistent members (matP, isDegenerate, ...) come from the handle's state
+    static_assert(sizeof(LMState) % 4 == 0, "LMState is copied word by word");
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(A.st);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&s_st);
+    if (tid < (int)(sizeof(LMState) / 4)) dst[tid] = __ldcg(src + tid);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const float pose6[6] = {p0, p1, p2, p3, p4, p5};
+    lm_begin_state(&s_st, A.mst[0], A.mst[1], A.prm, pose6);
+  }
+  GridGeom geom[2];
+  lm_load_geom(A, geom);
+  const int nq = A.nq[0] + A.nq[1];
+  const int per = (nq + gridDim.x - 1) / gridDim.x;
+  const int q_begin = min(nq, (int)blockIdx.x * per), q_end = min(nq, q_begin + per);
+  for (unsigned it = 0;; ++it) {
+    __syncthreads();
+    if (s_st.done) break;  // block-uniform, and the same decision in every block
+    const Trig trig = s_st.trig;
+    const RotTrig rt = s_st.rtrig;
+    const float run_sum = lm_block_pass(A, trig, rt, geom, s_slot, s_wacc, q_begin, q_end);
+    float* part = A.partials + (size_t)(it & 1u) * gridDim.x * 32;
+    if (tid < 32) {
+      part[blockIdx.x * 32 + tid] = tid < LM_NSUM ? run_sum : 0.f;
+      __threadfence();
+    }
+    __syncthreads();
+    if (tid == 0) {
+      atomicAdd(barrier, 1u);
+      const unsigned target = (it + 1u) * gridDim.x;
+      while (ld_acquire_u32(barrier) < target) {}
+    }
+    __syncthreads();
+    reduce_partials_and_solve(part, gridDim.x, A.prm, &s_st, false, reinterpret_cast<double*>(s_slot));
+  }
+  if (blockIdx.x == 0) {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(&s_st);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(A.st);
+    if (tid < (int)(sizeof(LMState) / 4)) dst[tid] = src[tid];
+    if (tid == 0) *barrier_clear = 0u;
+  }
+}
+
+// scan2MapOptimization prologue (:1573): the map-size guard and the loop state, one thread.
+__global__ void lm_begin_kernel(LMState* S, const MapState* corner, const MapState* surf, LMParams prm,
+                                float p0, float p1, float p2, float p3, float p4, float p5) {
+  pdl_entry();
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const float pose6[6] = {p0, p1, p2, p3, p4, p5};
+  lm_begin_state(S, corner, surf, prm, pose6);
 }
 
 // Stage-level a9 (ll_lm_step): rows from explicit (laserCloudOri, coeffSel) records, one thread per record,

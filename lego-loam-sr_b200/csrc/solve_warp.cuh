@@ -43,16 +43,12 @@ __device__ __forceinline__ float qr66_warp(const float* AtA, const float* Atb, i
 #pragma unroll
   for (int k = 0; k < 6; ++k) {
     // pivot: largest updated norm among positions k..5, lowest position on ties
-    float bestv = (cur >= k && cur < 6) ? nU : -1.f;
-    int bestp = cur;
-#pragma unroll
-    for (int o = 4; o > 0; o >>= 1) {
-      const float ov = __shfl_xor_sync(FULL, bestv, o);
-      const int op = __shfl_xor_sync(FULL, bestp, o);
-      if (ov > bestv || (ov == bestv && op < bestp)) { bestv = ov; bestp = op; }
-    }
-    bestv = __shfl_sync(FULL, bestv, 0);
-    bestp = __shfl_sync(FULL, bestp, 0);
+    // (norms are >= +0, so their bit patterns order like the values: two redux.sync instead of a shuffle tree)
+    const bool act = cur >= k && cur < 6;
+    const uint32_t nbits = act ? __float_as_uint(nU) : 0u;
+    const uint32_t mbits = __reduce_max_sync(FULL, nbits);
+    const int bestp = (int)__reduce_min_sync(FULL, (act && nbits == mbits) ? (unsigned)cur : 99u);
+    const float bestv = __uint_as_float(mbits);
     if (nonzero == 6 && bestv * bestv < thr * (float)(6 - k)) nonzero = k;
     if (cur == bestp) cur = k;
     else if (cur == k) cur = bestp;
@@ -149,6 +145,60 @@ __device__ __forceinline__ float qr66_warp(const float* AtA, const float* Atb, i
   for (int i = 0; i < 6; ++i)
     if (cur == i && i < nonzero) x = c[i];
   return lane < 6 ? x : 0.f;
+}
+
+// lm_solver = 1: the same 6x6 normal equations solved by an LDL^T factorisation in double (no pivoting: AtA is
+// symmetric positive definite whenever the scan constrains all six degrees of freedom). One thread's worth of
+// work, ~60 fused multiply-adds and six divisions, so every lane simply computes it redundantly and no
+// broadcast is needed. The result is the solution of the float system to double accuracy; Eigen's float
+// ColPivHouseholderQR (qr66_warp) differs from it by its own rounding error (<= cond(AtA) * 6e-8 relative).
+// Returns false when a pivot is not safely positive (rank-deficient AtA): the caller then takes the
+// rank-revealing QR, whose behaviour in that case (zeroed components) is part of the reference's semantics.
+__device__ __forceinline__ bool ldlt6_solve(const float* AtA, const float* Atb, float x[6]) {
+  double L[6][6], W[6][6], d[6], rd[6], y[6];
+  double maxdiag = 0.0;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) maxdiag = fmax(maxdiag, (double)AtA[i * 6 + i]);
+  bool ok = maxdiag > 0.0 && maxdiag < 1.7976931348623157e308;
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    double sj = (double)AtA[j * 6 + j];
+#pragma unroll
+    for (int k = 0; k < j; ++k) sj -= L[j][k] * W[j][k];
+    d[j] = sj;
+    ok = ok && (sj > 1e-12 * maxdiag);
+    rd[j] = 1.0 / sj;
+#pragma unroll
+    for (int i = j + 1; i < 6; ++i) {
+      double t = (double)AtA[i * 6 + j];
+#pragma unroll
+      for (int k = 0; k < j; ++k) t -= L[i][k] * W[j][k];
+      W[i][j] = t;           // L(i,j) * d(j)
+      L[i][j] = t * rd[j];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {  // L y = b
+    double t = (double)Atb[i];
+#pragma unroll
+    for (int k = 0; k < i; ++k) t -= L[i][k] * y[k];
+    y[i] = t;
+  }
+#pragma unroll
+  for (int i = 0; i < 6; ++i) y[i] *= rd[i];  // D z = y
+#pragma unroll
+  for (int i = 5; i >= 0; --i) {  // L^T x = z
+    double t = y[i];
+#pragma unroll
+    for (int k = i + 1; k < 6; ++k) t -= L[k][i] * y[k];
+    y[i] = t;
+  }
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    x[i] = (float)y[i];
+    ok = ok && isfinite(x[i]);
+  }
+  return ok;
 }
 
 // All 32 lanes must call. A: row-major symmetric 6x6 (float, shared memory).

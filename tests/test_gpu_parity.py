@@ -276,9 +276,11 @@ def test_voxel_downsample_skips_non_finite_points(abi, orc):
 
 
 # ------------------------------------------------------------------------------------------ a10 full loop
-def test_scan2map_pose_within_tolerance(abi, orc, single_problem, single_maps):
+@pytest.mark.parametrize("lm_solver,persistent_lm", [(0, 1), (1, 1), (0, 0), (1, 0)])
+def test_scan2map_pose_within_tolerance(abi, orc, single_problem, single_maps, lm_solver, persistent_lm):
+    """lm_solver: Eigen-sequence QR / LDL^T in double; persistent_lm: one cooperative launch / one launch per iteration."""
     d = single_problem
-    with abi.Handle(upstream_params(abi)) as h:
+    with abi.Handle(upstream_params(abi, lm_solver=lm_solver, persistent_lm=persistent_lm)) as h:
         load_map(h, d)
         pose, res = h.scan2map(d["query"]["corner_scan_ds"], d["query"]["surf_total_ds"], d["prior"])
         pose2, res2 = h.scan2map(d["query"]["corner_scan_ds"], d["query"]["surf_total_ds"], d["prior"])
@@ -301,13 +303,14 @@ def test_scan2map_early_exit_and_thresholds(abi, orc, single_problem, single_map
     d = single_problem
     for kw in (dict(stop_thres=0.05, iter_count_thres=30), dict(stop_thres=0.05, iter_count_thres=200),
                dict(stop_thres=0.0, iter_count_thres=3), dict(stop_thres=0.0, iter_count_thres=25)):
-        with abi.Handle(upstream_params(abi, **kw)) as h:
-            load_map(h, d)
-            pose, res = h.scan2map(d["query"]["corner_scan_ds"], d["query"]["surf_total_ds"], d["prior"])
         ores, opose, _ = orc.scan2map(single_maps["corner_ds"], single_maps["surf_ds"], d["query"]["corner_scan_ds"],
                                       d["query"]["surf_total_ds"], d["prior"], upstream_params(orc, **kw))
-        assert (res.iter_num, res.converged) == (ores.iter_num, ores.converged), kw
-        assert trans_err(pose, opose) <= TOL_T and rot_err(pose, opose) <= TOL_R, kw
+        for dev_kw in (dict(lm_solver=0, persistent_lm=1), dict(lm_solver=1, persistent_lm=1), dict(lm_solver=1, persistent_lm=0)):
+            with abi.Handle(upstream_params(abi, **kw, **dev_kw)) as h:
+                load_map(h, d)
+                pose, res = h.scan2map(d["query"]["corner_scan_ds"], d["query"]["surf_total_ds"], d["prior"])
+            assert (res.iter_num, res.converged) == (ores.iter_num, ores.converged), (kw, dev_kw)
+            assert trans_err(pose, opose) <= TOL_T and rot_err(pose, opose) <= TOL_R, (kw, dev_kw)
 
 
 def test_scan2map_as_shipped(abi, orc, single_problem, single_maps):
