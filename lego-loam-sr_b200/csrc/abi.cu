@@ -6,6 +6,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -503,6 +504,13 @@ LMArgs make_lm_args(ll_handle h, int mode) {
   A.st = h->d_state;
   A.partials = h->d_partials;
   A.mode = mode;
+  // Relative per-query cost used to cut the query list into equal-weight pieces (lm_partition). Measured on B200
+  // (VLP-16 replay, 148 blocks): 1:1 wins — what matters is that no block exceeds 48 queries, i.e. one batch of
+  // three per warp; 3:2 / 2:1 / 3:1 push the surf blocks into a second batch and cost 15-20 %.
+  static const int wc = std::getenv("LLB200_WC") ? std::atoi(std::getenv("LLB200_WC")) : 1;
+  static const int ws = std::getenv("LLB200_WS") ? std::atoi(std::getenv("LLB200_WS")) : 1;
+  A.w_corner = mode == 0 ? std::max(wc, 1) : 1;
+  A.w_surf = mode == 0 ? std::max(ws, 1) : 1;
   return A;
 }
 

@@ -80,6 +80,7 @@ struct LMArgs {
   LMState* st;
   float* partials;  // [gridDim.x][32]
   int mode;         // 0 = LM iteration; 1 = residuals only (emit); 2 = k-NN only (emit, queries in map frame)
+  int w_corner, w_surf;  // relative cost of a corner / surf query (lm_partition)
   // emit targets (mode != 0), indexed by query (corner queries first)
   float* e_coeff;
   int* e_mask;
@@ -541,22 +542,10 @@ __device__ __forceinline__ bool pair_less(uint32_t da, uint32_t ia, uint32_t db,
     cd[a] = d_; ci[a] = i_; cp[a] = p_;                                  \
   }
 
-__device__ __forceinline__ Knn5 warp_knn5(const float4* __restrict__ sorted, const int2* __restrict__ cells,
-                                          const GridGeom& g, float sx, float sy, float sz, float max_sq_dist,
-                                          int lane) {
-  const int cx = (int)floorf(sx) - g.ox, cy = (int)floorf(sy) - g.oy, cz = (int)floorf(sz) - g.oz;
-  int2 ce = make_int2(0, 0);
-  if (lane < 27) {
-    const int x = cx + (lane % 3) - 1, y = cy + ((lane / 3) % 3) - 1, z = cz + (lane / 9) - 1;
-    if (x >= 0 && x < g.dx && y >= 0 && y < g.dy && z >= 0 && z < g.dz) ce = __ldg(&cells[(z * g.dy + y) * g.dx + x]);
-  }
-  int s = (ce.y > ce.x) ? ce.x : 0x7fffffff;
-  int e = (ce.y > ce.x) ? ce.y : 0;
-  const int s1 = __shfl_down_sync(0xffffffffu, s, 1), e1 = __shfl_down_sync(0xffffffffu, e, 1);
-  const int s2 = __shfl_down_sync(0xffffffffu, s, 2), e2 = __shfl_down_sync(0xffffffffu, e, 2);
-  s = min(s, min(s1, s2));
-  e = max(e, max(e1, e2));
-  const int my_start = e > 0 ? s : 0, my_count = e > 0 ? e - s : 0;  // meaningful on lanes 0, 3, ..., 24
+// Chunks j0_begin, j0_begin + 128, ... of the candidate list described by (my_start, my_count) on lanes 0, 3, ..., 24,
+// merged into K (the best five of the chunks before j0_begin; all empty when j0_begin == 0).
+__device__ __forceinline__ void knn5_chunks(const float4* __restrict__ sorted, int my_start, int my_count, float sx,
+                                            float sy, float sz, float max_sq_dist, int lane, int j0_begin, Knn5& K) {
   // pr[k] = candidates before range k, bs[k] = (start of range k) - pr[k]: candidate j of the concatenation
   // lives at sorted[j + bs[k]] for the last k with pr[k] <= j. Range order: centre row first.
   constexpr int kRowLane[9] = {12, 3, 9, 15, 21, 0, 6, 18, 24};
@@ -571,10 +560,7 @@ __device__ __forceinline__ Knn5 warp_knn5(const float4* __restrict__ sorted, con
     total += cn;
   }
   const uint32_t max_bits = __float_as_uint(max_sq_dist);
-  Knn5 K;  // best five so far (warp-uniform), ascending
-#pragma unroll
-  for (int k = 0; k < 5; ++k) { K.d2[k] = LM_EMPTY_D2; K.idx[k] = 0xffffffffu; K.pos[k] = 0xffffffffu; }
-  for (int j0 = 0; j0 < total; j0 += 32 * LM_CAND_UNROLL) {
+  for (int j0 = j0_begin; j0 < total; j0 += 32 * LM_CAND_UNROLL) {
     const bool first = j0 == 0;
     int srcs[LM_CAND_UNROLL];
     float4 ms[LM_CAND_UNROLL];
@@ -643,8 +629,174 @@ __device__ __forceinline__ Knn5 warp_knn5(const float4* __restrict__ sorted, con
 #pragma unroll
     for (int k = 0; k < 5; ++k) { K.d2[k] = out.d2[k]; K.idx[k] = out.idx[k]; K.pos[k] = out.pos[k]; }
   }
+}
+
+__device__ __forceinline__ Knn5 warp_knn5(const float4* __restrict__ sorted, const int2* __restrict__ cells,
+                                          const GridGeom& g, float sx, float sy, float sz, float max_sq_dist,
+                                          int lane) {
+  const int cx = (int)floorf(sx) - g.ox, cy = (int)floorf(sy) - g.oy, cz = (int)floorf(sz) - g.oz;
+  int2 ce = make_int2(0, 0);
+  if (lane < 27) {
+    const int x = cx + (lane % 3) - 1, y = cy + ((lane / 3) % 3) - 1, z = cz + (lane / 9) - 1;
+    if (x >= 0 && x < g.dx && y >= 0 && y < g.dy && z >= 0 && z < g.dz) ce = __ldg(&cells[(z * g.dy + y) * g.dx + x]);
+  }
+  int s = (ce.y > ce.x) ? ce.x : 0x7fffffff;
+  int e = (ce.y > ce.x) ? ce.y : 0;
+  const int s1 = __shfl_down_sync(0xffffffffu, s, 1), e1 = __shfl_down_sync(0xffffffffu, e, 1);
+  const int s2 = __shfl_down_sync(0xffffffffu, s, 2), e2 = __shfl_down_sync(0xffffffffu, e, 2);
+  s = min(s, min(s1, s2));
+  e = max(e, max(e1, e2));
+  const int my_start = e > 0 ? s : 0, my_count = e > 0 ? e - s : 0;  // meaningful on lanes 0, 3, ..., 24
+  Knn5 K;  // best five so far (warp-uniform), ascending
+#pragma unroll
+  for (int k = 0; k < 5; ++k) { K.d2[k] = LM_EMPTY_D2; K.idx[k] = 0xffffffffu; K.pos[k] = 0xffffffffu; }
+  knn5_chunks(sorted, my_start, my_count, sx, sy, sz, max_sq_dist, lane, 0, K);
   K.accept = K.d2[4] != LM_EMPTY_D2;  // five neighbours, all with d2 < max_sq_dist (:1279 / :1389)
   return K;
+}
+
+// LM_KNN_BATCH queries of one warp searched TOGETHER: the cell descriptors of all of them are fetched in one
+// round trip, then all their candidates, and the five selection rounds of the different queries are independent
+// dependency chains that the scheduler interleaves — a block's ~47 queries over 16 warps would otherwise be three
+// fully serialised search latencies per warp. Handles the first chunk (<= 128 candidates) of every query; a
+// query with more candidates is searched by warp_knn5 (same result: the exact five smallest (d2, index) pairs).
+// On return lane r < 5 holds neighbour r of query q in (od, oi, op)[q] (bit patterns as in Knn5; empty slots
+// LM_EMPTY_D2 / 0xffffffff), and acc[q] (warp-uniform) says whether five neighbours within range exist.
+constexpr int LM_KNN_BATCH = 3;
+
+__device__ __forceinline__ void warp_knn5_batch(const float4* const (&sorted)[2], const int2* const (&cells)[2],
+                                                const GridGeom (&geom)[2], const int (&mq)[LM_KNN_BATCH],
+                                                const float4 (&sel)[LM_KNN_BATCH], float max_sq_dist, int lane,
+                                                uint32_t (&od)[LM_KNN_BATCH], uint32_t (&oi)[LM_KNN_BATCH],
+                                                uint32_t (&op)[LM_KNN_BATCH], bool (&acc)[LM_KNN_BATCH]) {
+  constexpr int NB = LM_KNN_BATCH;
+  constexpr int kRowLane[9] = {12, 3, 9, 15, 21, 0, 6, 18, 24};
+  const uint32_t max_bits = __float_as_uint(max_sq_dist);
+  // ---- stage 1: the 27 cell descriptors of every query (one load per lane per query, all in flight together)
+  int2 ce[NB];
+#pragma unroll
+  for (int q = 0; q < NB; ++q) {
+    ce[q] = make_int2(0, 0);
+    if (mq[q] >= 0 && lane < 27) {
+      const GridGeom& g = mq[q] ? geom[1] : geom[0];
+      const int x = (int)floorf(sel[q].x) - g.ox + (lane % 3) - 1, y = (int)floorf(sel[q].y) - g.oy + ((lane / 3) % 3) - 1,
+                z = (int)floorf(sel[q].z) - g.oz + (lane / 9) - 1;
+      if (x >= 0 && x < g.dx && y >= 0 && y < g.dy && z >= 0 && z < g.dz)
+        ce[q] = __ldg(&cells[mq[q] ? 1 : 0][(z * g.dy + y) * g.dx + x]);
+    }
+  }
+  // ---- stage 2: ranges -> candidate addresses -> candidate loads (all queries' loads in flight together)
+  int total[NB], q_start[NB], q_count[NB];
+  int srcs[NB][LM_CAND_UNROLL];
+  float4 ms[NB][LM_CAND_UNROLL];
+#pragma unroll
+  for (int q = 0; q < NB; ++q) {
+    int s = (ce[q].y > ce[q].x) ? ce[q].x : 0x7fffffff;
+    int e = (ce[q].y > ce[q].x) ? ce[q].y : 0;
+    const int s1 = __shfl_down_sync(0xffffffffu, s, 1), e1 = __shfl_down_sync(0xffffffffu, e, 1);
+    const int s2 = __shfl_down_sync(0xffffffffu, s, 2), e2 = __shfl_down_sync(0xffffffffu, e, 2);
+    s = min(s, min(s1, s2));
+    e = max(e, max(e1, e2));
+    const int my_start = e > 0 ? s : 0, my_count = e > 0 ? e - s : 0;
+    q_start[q] = my_start;
+    q_count[q] = my_count;
+    int pr[9], bs[9];
+    int tot = 0;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      const int st = __shfl_sync(0xffffffffu, my_start, kRowLane[k]);
+      const int cn = __shfl_sync(0xffffffffu, my_count, kRowLane[k]);
+      pr[k] = tot;
+      bs[k] = st - tot;
+      tot += cn;
+    }
+    total[q] = tot;
+#pragma unroll
+    for (int u = 0; u < LM_CAND_UNROLL; ++u) {
+      srcs[q][u] = -1;
+      if (32 * u < tot) {  // warp-uniform
+        const int j = 32 * u + lane;
+        int b = bs[0];
+#pragma unroll
+        for (int k = 1; k < 9; ++k)
+          if (j >= pr[k]) b = bs[k];
+        if (j < tot) srcs[q][u] = j + b;
+      }
+      ms[q][u] = srcs[q][u] >= 0 ? __ldg(&sorted[mq[q] > 0 ? 1 : 0][srcs[q][u]]) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  // ---- stage 3: distances and the per-lane sorting network
+  uint32_t cdq[NB][LM_CAND_UNROLL], ciq[NB][LM_CAND_UNROLL], cpq[NB][LM_CAND_UNROLL];
+#pragma unroll
+  for (int q = 0; q < NB; ++q) {
+    uint32_t (&cd)[LM_CAND_UNROLL] = cdq[q];
+    uint32_t (&ci)[LM_CAND_UNROLL] = ciq[q];
+    uint32_t (&cp)[LM_CAND_UNROLL] = cpq[q];
+#pragma unroll
+    for (int u = 0; u < LM_CAND_UNROLL; ++u) {
+      const float4 m = ms[q][u];
+      float df = sel[q].x - m.x;  // evalMetric order (nanoflann.hpp:431-439), no contraction
+      float d = df * df;
+      df = sel[q].y - m.y;
+      d += df * df;
+      df = sel[q].z - m.z;
+      d += df * df;
+      const uint32_t db = __float_as_uint(d);
+      const bool ok = srcs[q][u] >= 0 && db < max_bits;
+      cd[u] = ok ? db : LM_EMPTY_D2;
+      ci[u] = ok ? __float_as_uint(m.w) : 0xffffffffu;
+      cp[u] = ok ? (uint32_t)srcs[q][u] : 0xffffffffu;
+    }
+    LL_KNN_CE(0, 1) LL_KNN_CE(2, 3) LL_KNN_CE(0, 2) LL_KNN_CE(1, 3) LL_KNN_CE(1, 2)
+  }
+  // ---- stage 4: five selection rounds, the queries' chains interleaved. One redux.sync finds the smallest d2;
+  //      a ballot names the lane(s) holding it; only an exact d2 tie between lanes needs the index redux.
+#pragma unroll
+  for (int q = 0; q < NB; ++q) { od[q] = LM_EMPTY_D2; oi[q] = 0xffffffffu; op[q] = 0xffffffffu; acc[q] = false; }
+#pragma unroll
+  for (int r = 0; r < 5; ++r) {
+#pragma unroll
+    for (int q = 0; q < NB; ++q) {
+      uint32_t (&cd)[LM_CAND_UNROLL] = cdq[q];
+      uint32_t (&ci)[LM_CAND_UNROLL] = ciq[q];
+      uint32_t (&cp)[LM_CAND_UNROLL] = cpq[q];
+      const uint32_t m = __reduce_min_sync(0xffffffffu, cd[0]);
+      unsigned bal = __ballot_sync(0xffffffffu, cd[0] == m);
+      if (m != LM_EMPTY_D2 && (bal & (bal - 1u)) != 0u) {  // warp-uniform; rare
+        const uint32_t om = __reduce_min_sync(0xffffffffu, cd[0] == m ? ci[0] : 0xffffffffu);
+        bal = __ballot_sync(0xffffffffu, cd[0] == m && ci[0] == om);
+      }
+      const int wl = __ffs(bal) - 1;
+      const uint32_t wi = __shfl_sync(0xffffffffu, ci[0], wl);
+      const uint32_t wp = __shfl_sync(0xffffffffu, cp[0], wl);
+      if (lane == r) { od[q] = m; oi[q] = wi; op[q] = wp; }
+      if (r == 4) acc[q] = m != LM_EMPTY_D2;
+      if (lane == wl && m != LM_EMPTY_D2) {
+#pragma unroll
+        for (int k = 0; k < LM_CAND_UNROLL - 1; ++k) { cd[k] = cd[k + 1]; ci[k] = ci[k + 1]; cp[k] = cp[k + 1]; }
+        cd[LM_CAND_UNROLL - 1] = LM_EMPTY_D2; ci[LM_CAND_UNROLL - 1] = 0xffffffffu; cp[LM_CAND_UNROLL - 1] = 0xffffffffu;
+      }
+    }
+  }
+  // ---- queries with more than one chunk of candidates: the remaining chunks, merged into the five found so far
+#pragma unroll
+  for (int q = 0; q < NB; ++q) {
+    if (mq[q] >= 0 && total[q] > 32 * LM_CAND_UNROLL) {  // warp-uniform
+      Knn5 K;
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {
+        K.d2[k] = __shfl_sync(0xffffffffu, od[q], k);
+        K.idx[k] = __shfl_sync(0xffffffffu, oi[q], k);
+        K.pos[k] = __shfl_sync(0xffffffffu, op[q], k);
+      }
+      knn5_chunks(sorted[mq[q] ? 1 : 0], q_start[q], q_count[q], sel[q].x, sel[q].y, sel[q].z, max_sq_dist, lane,
+                  32 * LM_CAND_UNROLL, K);
+#pragma unroll
+      for (int k = 0; k < 5; ++k)
+        if (lane == k) { od[q] = K.d2[k]; oi[q] = K.idx[k]; op[q] = K.pos[k]; }
+      acc[q] = K.d2[4] != LM_EMPTY_D2;
+    }
+  }
 }
 #undef LL_KNN_CE
 
@@ -859,46 +1011,52 @@ __device__ __forceinline__ float lm_block_pass(const LMArgs& A, const Trig& trig
     const int nc = max(0, min(cn, A.nq[0] - c0));
     const int nc_pad = (nc + 31) & ~31;
     const int nslots = nc_pad + (cn - nc);
-    // ---- phase 1: k-NN, one warp per query
-    float4 p_next = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (warp < cn) {
-      const int q0 = c0 + warp;
-      p_next = __ldg(q0 < A.nq[0] ? &A.q[0][q0] : &A.q[1][q0 - A.nq[0]]);
-    }
-    for (int i = warp; i < cn; i += LM_WARPS) {
-      const int qi = c0 + i;
-      const int m = qi < A.nq[0] ? 0 : 1;
-      const float4 p = p_next;
-      if (i + LM_WARPS < cn) {  // the next query of this warp is in flight while this one is searched
-        const int qn = qi + LM_WARPS;
-        p_next = __ldg(qn < A.nq[0] ? &A.q[0][qn] : &A.q[1][qn - A.nq[0]]);
-      }
-      const float4 sel = (A.mode == 2) ? p : rigid_transform(trig, p);
-      const GridGeom g = m ? geom[1] : geom[0];
-      const Knn5 nn = warp_knn5(A.sorted[m], A.cells[m], g, sel.x, sel.y, sel.z, A.prm.fit.max_sq_dist, lane);
-      float* slot = &s_slot[(i < nc ? i : nc_pad + (i - nc)) * LM_SLOT];
-      if (lane < 5) {
-        uint32_t pos = nn.pos[0], d = nn.d2[0], ix = nn.idx[0];
+    // ---- phase 1: k-NN, one warp per query, LM_KNN_BATCH queries of a warp at a time
+    for (int i0 = warp; i0 < cn; i0 += LM_KNN_BATCH * LM_WARPS) {
+      int mq[LM_KNN_BATCH];
+      float4 sel[LM_KNN_BATCH];
 #pragma unroll
-        for (int k = 1; k < 5; ++k)
-          if (lane == k) { pos = nn.pos[k]; d = nn.d2[k]; ix = nn.idx[k]; }
-        if (nn.accept) {
-          const float4 nb = __ldg(&A.sorted[m][pos]);
-          slot[4 + 3 * lane] = nb.x;
-          slot[5 + 3 * lane] = nb.y;
-          slot[6 + 3 * lane] = nb.z;
+      for (int b = 0; b < LM_KNN_BATCH; ++b) {
+        const int i = i0 + b * LM_WARPS;
+        mq[b] = -1;
+        sel[b] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < cn) {
+          const int qi = c0 + i;
+          mq[b] = qi < A.nq[0] ? 0 : 1;
+          sel[b] = __ldg(mq[b] ? &A.q[1][qi - A.nq[0]] : &A.q[0][qi]);
         }
-        if (A.mode != 0) {
-          const bool have = d != LM_EMPTY_D2;
-          if (A.e_idx) A.e_idx[5 * qi + lane] = have ? (int)ix : -1;
-          if (A.e_d2) A.e_d2[5 * qi + lane] = have ? __uint_as_float(d) : FLT_MAX;
+      }
+#pragma unroll
+      for (int b = 0; b < LM_KNN_BATCH; ++b)
+        if (A.mode != 2) sel[b] = rigid_transform(trig, sel[b]);
+      uint32_t od[LM_KNN_BATCH], oi[LM_KNN_BATCH], op[LM_KNN_BATCH];
+      bool acc[LM_KNN_BATCH];
+      warp_knn5_batch(A.sorted, A.cells, geom, mq, sel, A.prm.fit.max_sq_dist, lane, od, oi, op, acc);
+#pragma unroll
+      for (int b = 0; b < LM_KNN_BATCH; ++b) {
+        const int i = i0 + b * LM_WARPS;
+        if (i >= cn) continue;  // warp-uniform
+        const int qi = c0 + i;
+        float* slot = &s_slot[(i < nc ? i : nc_pad + (i - nc)) * LM_SLOT];
+        if (lane < 5) {
+          if (acc[b]) {
+            const float4 nb = __ldg(&A.sorted[mq[b]][op[b]]);
+            slot[4 + 3 * lane] = nb.x;
+            slot[5 + 3 * lane] = nb.y;
+            slot[6 + 3 * lane] = nb.z;
+          }
+          if (A.mode != 0) {
+            const bool have = od[b] != LM_EMPTY_D2;
+            if (A.e_idx) A.e_idx[5 * qi + lane] = have ? (int)oi[b] : -1;
+            if (A.e_d2) A.e_d2[5 * qi + lane] = have ? __uint_as_float(od[b]) : FLT_MAX;
+          }
+        } else if (lane == 5) {
+          slot[0] = sel[b].x;
+          slot[1] = sel[b].y;
+          slot[2] = sel[b].z;
+          slot[3] = acc[b] ? 1.f : 0.f;
+          if (A.mode != 0 && A.e_accept) A.e_accept[qi] = acc[b] ? 1 : 0;
         }
-      } else if (lane == 5) {
-        slot[0] = sel.x;
-        slot[1] = sel.y;
-        slot[2] = sel.z;
-        slot[3] = nn.accept ? 1.f : 0.f;
-        if (A.mode != 0 && A.e_accept) A.e_accept[qi] = nn.accept ? 1 : 0;
       }
     }
     __syncthreads();
@@ -956,6 +1114,20 @@ __device__ __forceinline__ float lm_block_pass(const LMArgs& A, const Trig& trig
   return run_sum;
 }
 
+// Block b's share [q_begin, q_end) of the concatenated query list. An iteration ends when the slowest block
+// arrives at the barrier, and a corner query costs more than a surf query in both phases (denser map -> more
+// candidates; eigen solve in double), so the list is cut into pieces of equal WEIGHT, not equal length.
+__device__ __forceinline__ void lm_partition(const LMArgs& A, int b, int nb, int& q_begin, int& q_end) {
+  const long long wc = A.w_corner, ws = A.w_surf;
+  const long long cw = wc * A.nq[0], W = cw + ws * A.nq[1];
+  auto cut = [&](long long k) -> int {
+    const long long pos = (W * k) / nb;
+    return pos < cw ? (int)(pos / wc) : A.nq[0] + (int)((pos - cw) / ws);
+  };
+  q_begin = cut(b);
+  q_end = (b + 1 == nb) ? A.nq[0] + A.nq[1] : cut(b + 1);
+}
+
 __device__ __forceinline__ void lm_load_geom(const LMArgs& A, GridGeom (&geom)[2]) {
 #pragma unroll
   for (int m = 0; m < 2; ++m) {
@@ -982,9 +1154,8 @@ __global__ void __launch_bounds__(LM_THREADS, LM_MIN_BLOCKS) lm_iter_kernel(cons
   const RotTrig rt = S->rtrig;
   GridGeom geom[2];
   lm_load_geom(A, geom);
-  const int nq = A.nq[0] + A.nq[1];
-  const int per = (nq + gridDim.x - 1) / gridDim.x;
-  const int q_begin = min(nq, (int)blockIdx.x * per), q_end = min(nq, q_begin + per);
+  int q_begin, q_end;
+  lm_partition(A, (int)blockIdx.x, (int)gridDim.x, q_begin, q_end);
   const float run_sum = lm_block_pass(A, trig, rt, geom, s_slot, s_wacc, q_begin, q_end);
   if (A.mode != 0) return;
   if (tid < 32) {
@@ -1062,9 +1233,8 @@ __global__ void __launch_bounds__(LM_THREADS, 1) lm_persistent_kernel(const __gr
   }
   GridGeom geom[2];
   lm_load_geom(A, geom);
-  const int nq = A.nq[0] + A.nq[1];
-  const int per = (nq + gridDim.x - 1) / gridDim.x;
-  const int q_begin = min(nq, (int)blockIdx.x * per), q_end = min(nq, q_begin + per);
+  int q_begin, q_end;
+  lm_partition(A, (int)blockIdx.x, (int)gridDim.x, q_begin, q_end);
   for (unsigned it = 0;; ++it) {
     __syncthreads();
     if (s_st.done) break;  // block-uniform, and the same decision in every block

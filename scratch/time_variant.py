@@ -8,7 +8,7 @@ if os.environ.get("LLB200_LIB"):
     abi.LIB_PATH = os.environ["LLB200_LIB"]
 WORLD = dict(n_blocks=60, n_poles=600, half_x=80, half_z=120)
 d = synth.make_single(seed=1, n_map_scans=50, step=1.0, world_kw=WORLD)
-prm = abi.default_params(apply_update=1, eigen_mode=1, iter_count_thres=10, stop_thres=0.0)
+prm = abi.default_params(apply_update=1, eigen_mode=1, iter_count_thres=10, stop_thres=0.0, lm_solver=1)
 with abi.Handle(prm) as h:
     for i, f in enumerate(d["keyframes"]):
         h.add_keyframe(i, f["corner_scan"], f["surf_last_ds"], f["outlier_last_ds"], d["key_poses"][i])
