@@ -312,6 +312,14 @@ int ensure_slot(ll_handle h, int s, size_t need_pts, bool need_grid) {
   return LL_OK;
 }
 
+// Bytes of the scratch block a build over S.n_raw points can touch: everything up to the look-back words, plus the
+// look-back words of the tiles in use (tile-major layout, radix_sort.cuh).
+size_t scratch_bytes_in_use(const MapSlot& S) {
+  const size_t tiles = (size_t)(S.n_raw + RS_TILE - 1) / RS_TILE + 1;
+  const size_t head = reinterpret_cast<const uint8_t*>(S.status()) - S.scratch;
+  return std::min(S.scratch_bytes, head + std::min(tiles, (size_t)S.max_tiles) * RS_MAX_PASSES * RS_RADIX * sizeof(uint32_t));
+}
+
 MapBuffers slot_buffers(const ll_handle h, int s, float leaf, int downsample, bool want_member) {
   const MapSlot& S = h->slot[s];
   MapBuffers M;
@@ -405,7 +413,7 @@ int run_map_pipeline(ll_handle h, int sa, int sb, const SegList& L, float leaf_a
   int maxn = 0;
   for (int k = 0; k < ny; ++k) {
     MapSlot& S = h->slot[slots[k]];
-    LL_CUDA(h, cudaMemsetAsync(S.scratch, 0, S.scratch_bytes, h->stream));
+    LL_CUDA(h, cudaMemsetAsync(S.scratch, 0, scratch_bytes_in_use(S), h->stream));
     maxn = std::max(maxn, S.n_raw);
   }
   LL_TRY(upload_seglist(h, L));
@@ -437,7 +445,7 @@ int run_map_pipeline(ll_handle h, int sa, int sb, const SegList& L, float leaf_a
   if (!build_grid) return LL_OK;
   for (int k = 0; k < ny; ++k) {  // re-arm the sort scratch (everything behind MapState) for the cell sort
     MapSlot& S = h->slot[slots[k]];
-    LL_CUDA(h, cudaMemsetAsync(S.scratch + 256, 0, S.scratch_bytes - 256, h->stream));
+    LL_CUDA(h, cudaMemsetAsync(S.scratch + 256, 0, scratch_bytes_in_use(S) - 256, h->stream));
   }
   B.sort[0] = slot_sort(h, sa, true);
   if (sb >= 0) B.sort[1] = slot_sort(h, sb, true);

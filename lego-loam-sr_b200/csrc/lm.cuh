@@ -851,17 +851,25 @@ __device__ void lm_solve_block(double* s_red, const LMParams& prm, LMState* S, b
     }
     if (lane < 6) xs[lane] = x;
   } else if (warp == 1 && iter == 0) {  // :1507-1531, upstream semantics
-    double w, v[6];
-    jacobi6_warp<false>(AtA, lane, w, v);  // eigenvalues only
-    unsigned mb = __ballot_sync(FULL, lane < 6 && (float)w < prm.eig_thresh);
-    if (mb) {  // degenerate: the projector needs the eigenvectors too
+    // min_lambda and "is any eigenvalue below the threshold" from Sturm counts (solve_warp.cuh); the full
+    // eigen-decomposition only when the projector needs eigenvectors
+    double w = 0.0, v[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    double wmin;
+    int n_below;
+    // (float)lambda < eig_thresh  <=>  lambda < the midpoint between eig_thresh and the float below it (ties round to
+    // eig_thresh's even mantissa for the default 100): the double shift that reproduces the float comparison
+    const double thr_mid = 0.5 * ((double)prm.eig_thresh + (double)nextafterf(prm.eig_thresh, -FLT_MAX));
+    min_eig6_multisection(AtA, thr_mid, lane, wmin, n_below);
+    unsigned mb = n_below > 0 ? 1u : 0u;
+    if (mb) {  // degenerate
       jacobi6_warp<true>(AtA, lane, w, v);
       mb = __ballot_sync(FULL, lane < 6 && (float)w < prm.eig_thresh);
+      double jm = lane < 6 ? w : 1.7976931348623157e308;
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) jm = fmin(jm, __shfl_xor_sync(FULL, jm, o));
+      wmin = jm;
     }
     const bool below = lane < 6 && (float)w < prm.eig_thresh;
-    double wmin = lane < 6 ? w : 1.7976931348623157e308;
-#pragma unroll
-    for (int o = 4; o > 0; o >>= 1) wmin = fmin(wmin, __shfl_xor_sync(FULL, wmin, o));
     if (lane == 0) {
       misc[0] = mb ? 1.f : 0.f;
       misc[1] = (float)wmin;

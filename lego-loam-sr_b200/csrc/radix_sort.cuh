@@ -35,7 +35,7 @@ struct SortProblem {
   const int* n;            // element count (device)
   const int* bits;         // significant key bits (device), 0..32
   uint32_t* ghist;         // [RS_MAX_PASSES][256] digit histograms of the whole input (pre-zeroed, filled by keygen)
-  uint32_t* status;        // [RS_MAX_PASSES][max_tiles][256] look-back words (pre-zeroed)
+  uint32_t* status;        // [max_tiles][RS_MAX_PASSES][256] look-back words (pre-zeroed)
   uint32_t* tile_counter;  // [RS_MAX_PASSES] dynamic tile tickets (pre-zeroed)
   int max_tiles;
 };
@@ -125,12 +125,15 @@ __global__ void __launch_bounds__(RS_THREADS) rs_onesweep_kernel(const __grid_co
     warp_hist[w][tid] = tile_count;
     tile_count += c;
   }
-  volatile uint32_t* status = P.status + ((size_t)pass * P.max_tiles) * RS_RADIX;
+  // tile-major layout [tile][pass][digit]: the words a build can touch are a prefix of the array, so the host
+  // only has to zero ceil(n / RS_TILE) tiles' worth, not the whole capacity
+  constexpr size_t kTileStride = (size_t)RS_MAX_PASSES * RS_RADIX;
+  volatile uint32_t* status = P.status + (size_t)pass * RS_RADIX;
   uint32_t excl = 0;
   if (tile == 0) {
-    status[(size_t)tile * RS_RADIX + tid] = tile_count | RS_FLAG_PREFIX;
+    status[(size_t)tile * kTileStride + tid] = tile_count | RS_FLAG_PREFIX;
   } else {
-    status[(size_t)tile * RS_RADIX + tid] = tile_count | RS_FLAG_AGG;
+    status[(size_t)tile * kTileStride + tid] = tile_count | RS_FLAG_AGG;
     // Windowed look-back: RS_LOOKBACK predecessor words are fetched together (independent loads, one round
     // trip) and consumed in order. When every tile of a pass is resident at once they all finish ranking at
     // the same moment, and a one-word-at-a-time walk would serialise ~tiles/2 L2 round trips.
@@ -141,7 +144,7 @@ __global__ void __launch_bounds__(RS_THREADS) rs_onesweep_kernel(const __grid_co
 #pragma unroll
       for (int u = 0; u < RS_LOOKBACK; ++u) {
         w[u] = 2u << 30;  // RS_FLAG_PREFIX: virtual empty prefix before tile 0
-        if (j - u >= 0) w[u] = status[(size_t)(j - u) * RS_RADIX + tid];
+        if (j - u >= 0) w[u] = status[(size_t)(j - u) * kTileStride + tid];
       }
       int consumed = 0;
 #pragma unroll
@@ -158,7 +161,7 @@ __global__ void __launch_bounds__(RS_THREADS) rs_onesweep_kernel(const __grid_co
       }
       j -= consumed;
     }
-    status[(size_t)tile * RS_RADIX + tid] = (excl + tile_count) | RS_FLAG_PREFIX;
+    status[(size_t)tile * kTileStride + tid] = (excl + tile_count) | RS_FLAG_PREFIX;
   }
   // Exclusive prefix of the global digit histogram (256 values, Hillis-Steele in shared memory).
   const uint32_t g = P.ghist[pass * RS_RADIX + tid];

@@ -201,6 +201,62 @@ __device__ __forceinline__ bool ldlt6_solve(const float* AtA, const float* Atb, 
   return ok;
 }
 
+// Number of eigenvalues of the symmetric 6x6 matrix A (row-major float) below sigma: the count of negative
+// pivots of the LDL^T factorisation of A - sigma I (Sylvester's law of inertia), in double. One thread.
+__device__ __forceinline__ int sturm_count6(const float* A, double sigma) {
+  double L[6][6], W[6][6];
+  int neg = 0;
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    double dj = (double)A[j * 6 + j] - sigma;
+#pragma unroll
+    for (int k = 0; k < j; ++k) dj -= L[j][k] * W[j][k];
+    if (dj == 0.0) dj = -1e-300;  // sigma sits on an eigenvalue of a leading block: count it as below
+    neg += dj < 0.0 ? 1 : 0;
+    const double rd = 1.0 / dj;
+#pragma unroll
+    for (int i = j + 1; i < 6; ++i) {
+      double t = (double)A[i * 6 + j];
+#pragma unroll
+      for (int k = 0; k < j; ++k) t -= L[i][k] * W[j][k];
+      W[i][j] = t;
+      L[i][j] = t * rd;
+    }
+  }
+  return neg;
+}
+
+// Smallest eigenvalue of A and the number of eigenvalues below `thresh`, by 32-way multisection on Sturm counts:
+// every lane tests its own shift, a ballot finds the sub-interval that contains the smallest eigenvalue, and
+// seven rounds narrow [-(eps) trace, min diagonal] by 33^7 ~ 4e10 — well below float resolution of the result.
+// This replaces the full Jacobi eigen-decomposition on the critical path of iteration 0 whenever no eigenvalue
+// is below the threshold (the usual case); the eigenvectors are only needed for the degenerate projector.
+// All 32 lanes must call; results are warp-uniform.
+__device__ __forceinline__ void min_eig6_multisection(const float* A, double thresh, int lane, double& min_lambda,
+                                                      int& n_below) {
+  double tr = 0.0, hi = 1.7976931348623157e308;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    tr += fabs((double)A[i * 6 + i]);
+    hi = fmin(hi, (double)A[i * 6 + i]);  // lambda_min <= every diagonal entry
+  }
+  double lo = -1e-6 * tr - 1e-30;         // AtA is positive semi-definite up to rounding
+  hi += 1e-12 * tr + 1e-30;
+  n_below = sturm_count6(A, thresh);
+#pragma unroll 1
+  for (int round = 0; round < 7; ++round) {
+    const double step = (hi - lo) / 33.0;
+    const double sigma = lo + step * (double)(lane + 1);
+    const unsigned has = __ballot_sync(FULL, sturm_count6(A, sigma) >= 1);
+    // counts are monotone in sigma: the first lane whose shift is above lambda_min
+    const int first = has ? __ffs(has) - 1 : 32;
+    const double new_lo = lo + step * (double)first;
+    hi = first < 32 ? lo + step * (double)(first + 1) : hi;
+    lo = new_lo;
+  }
+  min_lambda = 0.5 * (lo + hi);
+}
+
 // All 32 lanes must call. A: row-major symmetric 6x6 (float, shared memory).
 // On return, lane l < 6 holds eigenvalue w and (kVectors) its eigenvector v[0..5] (unsorted; one eigenpair per
 // lane). kVectors = false skips the accumulation of V (40 % of the shuffles): the common case only needs the

@@ -5,7 +5,7 @@ import numpy as np, torch
 from lego_loam_sr_b200 import synth, abi
 WORLD = dict(n_blocks=60, n_poles=600, half_x=80, half_z=120)
 d = synth.make_single(seed=1, n_map_scans=50, step=1.0, world_kw=WORLD)
-prm = abi.default_params(apply_update=1, eigen_mode=1, iter_count_thres=10, stop_thres=0.0)
+prm = abi.default_params(apply_update=1, eigen_mode=1, iter_count_thres=10, stop_thres=0.0, lm_solver=1)
 with abi.Handle(prm) as h:
     h._lib.ll_reserve(h._h, 1 << 20, 1 << 21, 1 << 17)
     for i, f in enumerate(d["keyframes"]):
