@@ -59,6 +59,7 @@ def parse_args():
     ap.add_argument("--threads", type=int, default=8, help="concurrent sequences (host threads / streams) per GPU")
     ap.add_argument("--no-l2-flush", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-at-scale", action="store_true", help="skip the configs[2]/[3]-shaped per-kernel measurements")
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="wall budget of the cpu_baseline sample")
     ap.add_argument("--seed", type=int, default=2)
     return ap.parse_args()
@@ -303,18 +304,66 @@ def roofline_from_profile(prof, run, peaks):
     peak = peaks.get("hbm_gbs", 6650.0)
     achieved = table[top]["gbs"]
     traffic = None  # dram__bytes_read + dram__bytes_write per launch from the committed ncu --set full capture
-    try:
-        cap = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_%s_full.json" % top)))
-        traffic = int(cap["traffic_bytes_per_launch"])
-    except Exception:
-        pass
-    roof = {"kernel": top, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    for name in ("r01b_ncu_lm_persistent_full.json" if top == "lm_iter" else "", "r01_ncu_%s_full.json" % top):
+        try:
+            cap = json.load(open(os.path.join(ROOT, "profiles", name)))
+            traffic = int(cap["traffic_bytes_per_launch"])
+            break
+        except Exception:
+            pass
+    roof = {"kernel": "lm_persistent_kernel (all %d LM iterations of a scan)" % ITERS if top == "lm_iter" else top, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
             "frac": round(achieved / peak, 5), "traffic": traffic,
             "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if "hbm_gbs" in peaks else "fallback 6650 (B200_PROFILING.md)",
             "algorithmic_bytes_per_launch": int(algorithmic_bytes(top, n_raw, n_ds, q)),
             "us_per_launch": table[top]["us_per_launch"], "share_of_step": table[top]["share"],
             "note": "one scan is latency-bound (10 dependent iterations, ~7 k queries): see DESIGN.md §5 and profiles/"}
     return roof, table, dict(n_raw=round(n_raw), n_ds=round(n_ds), queries=round(q))
+
+
+def run_at_scale(device, peaks):
+    """BASELINE configs[2]/[3]-shaped single problems (parity-test cases, not the headline): per-kernel-class device
+    time and achieved algorithmic GB/s at sizes where bandwidth, not launch latency, is what bounds the kernels.
+    c4: ~2.2 M surrounding-map points WITHOUT map downsampling, 20 k corner + 80 k surf queries.
+    c3: 2.5 M raw surf + 0.2 M raw corner points WITH VoxelGrid, 8 k + 32 k queries (HDL-64E-like volume)."""
+    from lego_loam_sr_b200 import abi
+    rng = np.random.default_rng(4)
+
+    def world(n):
+        p = np.empty((n, 4), np.float32)
+        p[:, 0] = rng.uniform(-70, 70, n)
+        p[:, 2] = rng.uniform(-70, 70, n)
+        p[:, 1] = np.where(rng.random(n) < 0.7, -1.8 + rng.normal(0, 0.02, n), rng.uniform(-1.8, 6, n))
+        p[:, 3] = rng.uniform(0, 16, n)
+        return p
+
+    out = {}
+    peak = peaks.get("hbm_gbs", 6650.0)
+    for name, ds, n_surf, n_corner, nqc, nqs in (("c4_dense_no_downsample", 0, 2_000_000, 200_000, 20_000, 80_000),
+                                                 ("c3_like_with_voxelgrid", 1, 2_500_000, 200_000, 8_000, 32_000)):
+        surf, corner = world(n_surf), world(n_corner)
+        prm = headline_params(abi, map_downsample=ds)
+        cq = corner[rng.choice(len(corner), nqc, replace=False)].copy()
+        sq = surf[rng.choice(len(surf), nqs, replace=False)].copy()
+        pose = np.array([0.002, -0.003, 0.002, 0.03, -0.02, 0.03], np.float32)
+        with abi.Handle(prm, device=device) as h:
+            for r in range(4):
+                if r == 1:
+                    h.profile_enable(True)
+                    h.profile_read()
+                h.set_local_map_raw(corner, surf)
+                _, res = h.scan2map(cq, sq, pose)
+            prof = h.profile_read()
+        n_raw, n_ds, q = n_surf + n_corner, res.corner_map_ds + res.surf_map_ds, nqc + nqs
+        table = {}
+        for cls, (ms, cnt) in prof.items():
+            if not cnt:
+                continue
+            us = ms * 1e3 / cnt
+            b = algorithmic_bytes(cls, n_raw, n_ds, q)
+            table[cls] = {"us_per_launch": round(us, 1), "gbs": round(b / (us * 1e-6) / 1e9, 1), "frac_of_hbm_peak": round(b / (us * 1e-6) / 1e9 / peak, 4)}
+        out[name] = {"n_raw": n_raw, "n_ds": int(n_ds), "queries": q, "iterations": int(res.iter_num), "residuals": int(res.sel_num),
+                     "kernels": table}
+    return out
 
 
 # ----------------------------------------------------------------------------------------------- CPU arm
@@ -468,6 +517,8 @@ def main():
             "checks": {"all_scans_optimised": all(r[0] == 0 for r in res["results"]),
                        "iterations_per_scan": sorted(set(r[1] for r in res["results"])),
                        "resident_equals_e2e_pose": bool(np.array_equal(res["poses"], e2e["poses"]))}}
+    if world == 1 and not args.no_at_scale:
+        line["at_scale"] = run_at_scale(device, peaks)
     if world == 1 and not args.no_cpu_baseline:
         times, knn = run_cpu(data, prefill, 0, args.steps, budget_s=args.cpu_seconds)
         v = len(times) / sum(times)

@@ -32,6 +32,7 @@ constexpr int kPinSlots = 4;                 // pinned staging buffers in flight
 constexpr int kFirstChunk = 12;              // LM iterations enqueued before the first look at `done`
 constexpr int kNextChunk = 16;
 constexpr int kBarrierSlots = 64;
+constexpr long kInlineGridMaxPoints = 1L << 20;  // raw points up to which the persistent kernel may build the grids itself
 
 struct Keyframe {
   float4* d[3] = {nullptr, nullptr, nullptr};  // corner, surf, outlier (device, packed float4, sensor frame)
@@ -82,6 +83,10 @@ struct ll_handle_s {
 
   MapSlot slot[3];
   bool map_ready = false;
+  // the search grids of the current local map are still to be built: either inside the persistent scan kernel
+  // (grid_inline.cuh) or, for any other consumer, by run_grid_build()
+  bool grid_deferred = false;
+  struct { int sa, sb; float leaf_a, leaf_b; int ds_a, ds_b; } grid_cfg = {0, 1, 0.2f, 0.4f, 1, 1};
   bool cells_given_up = false;
 
   Segment* d_segs = nullptr;
@@ -392,6 +397,27 @@ int upload_seglist(ll_handle h, const SegList& L) {
   return pinned_release(h);
 }
 
+int run_grid_build(ll_handle h);
+
+// The MapBatch of the slots in h->grid_cfg, with the sort problems of the voxel phase or of the grid phase.
+MapBatch make_map_batch(const ll_handle h, bool grid_phase) {
+  const auto& c = h->grid_cfg;
+  MapBatch B;
+  std::memset(&B, 0, sizeof(B));
+  B.m[0] = slot_buffers(h, c.sa, c.leaf_a, c.ds_a, false);
+  B.sort[0] = slot_sort(h, c.sa, grid_phase);
+  if (c.sb >= 0) {
+    B.m[1] = slot_buffers(h, c.sb, c.leaf_b, c.ds_b, false);
+    B.sort[1] = slot_sort(h, c.sb, grid_phase);
+  } else {
+    B.m[1] = B.m[0];
+    B.m[1].n_raw = 0;
+    B.sort[1] = B.sort[0];
+  }
+  B.count = c.sb >= 0 ? 2 : 1;
+  return B;
+}
+
 // Run the map pipeline on slots (sa, sb) (sb < 0: single problem). The raw clouds are described by L.
 int run_map_pipeline(ll_handle h, int sa, int sb, const SegList& L, float leaf_a, float leaf_b, int ds_a, int ds_b,
                      bool build_grid, bool want_member) {
@@ -443,12 +469,34 @@ int run_map_pipeline(ll_handle h, int sa, int sb, const SegList& L, float leaf_a
     LL_LAUNCHED(h);
   }
   if (!build_grid) return LL_OK;
+  h->grid_cfg = {sa, sb, leaf_a, leaf_b, ds_a, ds_b};
+  // the persistent kernel sorts one tile of <= 16 * 512 points per block, both maps together; its grid may be as small
+  // as one block per 16 queries, so bound the raw size (>= the downsampled size) by what the smallest useful grid holds
+  const long pts = (long)h->slot[sa].n_raw + (sb >= 0 ? (long)h->slot[sb].n_raw : 0);
+  static const bool no_inline = std::getenv("LLB200_NO_INLINE_GRID") != nullptr;  // A/B switch for measurements
+  if (!no_inline && h->prm.persistent_lm && sb >= 0 && !want_member && pts <= kInlineGridMaxPoints) {
+    h->grid_deferred = true;  // the next persistent scan kernel builds them; any other consumer calls ensure_grid()
+    return LL_OK;
+  }
+  h->grid_deferred = false;
+  return run_grid_build(h);
+}
+
+// a4 as five separate launches: cell keys, <= 3 radix passes, cell-ordered points + cell table.
+int run_grid_build(ll_handle h) {
+  const int sa = h->grid_cfg.sa, sb = h->grid_cfg.sb;
+  const int ny = sb >= 0 ? 2 : 1;
+  MapBatch B = make_map_batch(h, true);
+  const int slots[2] = {sa, sb};
+  int maxn = 0;
   for (int k = 0; k < ny; ++k) {  // re-arm the sort scratch (everything behind MapState) for the cell sort
     MapSlot& S = h->slot[slots[k]];
     LL_CUDA(h, cudaMemsetAsync(S.scratch + 256, 0, scratch_bytes_in_use(S) - 256, h->stream));
+    maxn = std::max(maxn, S.n_raw);
   }
-  B.sort[0] = slot_sort(h, sa, true);
-  if (sb >= 0) B.sort[1] = slot_sort(h, sb, true);
+  if (maxn == 0) return LL_OK;
+  const unsigned gx_pts = (unsigned)((maxn + MB_TILE - 1) / MB_TILE);
+  const unsigned gx_sort = (unsigned)((maxn + RS_TILE - 1) / RS_TILE);
   const unsigned gx_grid = std::max(gx_pts, (unsigned)(2 * h->num_sms));
   LL_PROF(h, 4);
   LL_CUDA(h, launch_pdl(h->stream, grid_keys_kernel, dim3(gx_grid, ny), dim3(MB_THREADS), B));
@@ -465,6 +513,12 @@ int run_map_pipeline(ll_handle h, int sa, int sb, const SegList& L, float leaf_a
   LL_CUDA(h, launch_pdl(h->stream, grid_finalize_kernel, dim3(gx_pts, ny), dim3(MB_THREADS), B));
   LL_LAUNCHED(h);
   return LL_OK;
+}
+
+int ensure_grid(ll_handle h) {
+  if (!h->grid_deferred) return LL_OK;
+  h->grid_deferred = false;
+  return run_grid_build(h);
 }
 
 LMParams make_lm_params(const ll_params& p) {
@@ -559,7 +613,8 @@ int enqueue_iterations(ll_handle h, int count) {
     LL_PROF(h, 8);
     // iteration k+1 is set up (and its blocks become resident as SMs free up) while iteration k's last block is
     // still solving
-    LL_CUDA(h, launch_pdl(h->stream, lm_iter_kernel, dim3((unsigned)h->lm_blocks), dim3(LM_THREADS), A));
+    LL_CUDA(h, launch_pdl(h->stream, h->prm.eigen_mode ? lm_iter_kernel<1> : lm_iter_kernel<0>, dim3((unsigned)h->lm_blocks),
+                          dim3(LM_THREADS), A));
     LL_LAUNCHED(h);
   }
   h->iters_enqueued += count;
@@ -572,7 +627,9 @@ int scan2map_enqueue(ll_handle h, const float pose6[6]) {
   if (!pose6) return fail(h, LL_ERR_INVALID_ARG, "pose6 is NULL");
   const int nq = h->nq[0] + h->nq[1];
   h->lm_blocks = lm_grid_blocks(h, nq);
+  if (h->prm.persistent_lm && h->grid_deferred) h->lm_blocks = h->num_sms;  // the grid build wants every SM (one tile per block)
   LL_TRY(ensure_partials(h, h->lm_blocks));
+  if (!h->prm.persistent_lm) LL_TRY(ensure_grid(h));
   if (h->prm.persistent_lm) {
     // the whole loop in one cooperative launch (all blocks co-resident: lm_blocks <= number of SMs, one block per SM)
     LMArgs A = make_lm_args(h, 0);
@@ -580,9 +637,14 @@ int scan2map_enqueue(ll_handle h, const float pose6[6]) {
     unsigned* bar = h->d_barriers + (h->scan_seq % kBarrierSlots);
     unsigned* bar_clear = h->d_barriers + ((h->scan_seq + kBarrierSlots / 2) % kBarrierSlots);
     h->scan_seq++;
-    void* args[] = {&A, &p[0], &p[1], &p[2], &p[3], &p[4], &p[5], &bar, &bar_clear};
+    MapBatch GB = make_map_batch(h, true);
+    int build_grid = h->grid_deferred ? 1 : 0;
+    h->grid_deferred = false;
+    void* args[] = {&A, &p[0], &p[1], &p[2], &p[3], &p[4], &p[5], &bar, &bar_clear, &GB, &build_grid};
     LL_PROF(h, 8);
-    LL_CUDA(h, cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(lm_persistent_kernel), dim3((unsigned)h->lm_blocks),
+    LL_CUDA(h, cudaLaunchCooperativeKernel(h->prm.eigen_mode ? reinterpret_cast<const void*>(lm_persistent_kernel<1>)
+                                                             : reinterpret_cast<const void*>(lm_persistent_kernel<0>),
+                                           dim3((unsigned)h->lm_blocks),
                                            dim3(LM_THREADS), args, 0, h->stream));
     LL_LAUNCHED(h);
     h->iters_enqueued = h->prm.iter_count_thres;
@@ -643,6 +705,7 @@ int emit_queries(ll_handle h, int which, int mode, const void* queries, size_t n
   if (which != 0 && which != 1) return fail(h, LL_ERR_INVALID_ARG, "which must be 0 (corner) or 1 (surf)");
   if (nq && (!queries || !stride_ok(stride))) return fail(h, LL_ERR_INVALID_ARG, "bad query cloud / stride");
   if (nq == 0) return LL_OK;
+  LL_TRY(ensure_grid(h));
   LL_TRY(set_queries_host(h, which, queries, nq, stride));
   h->nq[1 - which] = 0;
   h->q_ptr[1 - which] = h->dq[which];
@@ -663,7 +726,8 @@ int emit_queries(ll_handle h, int which, int mode, const void* queries, size_t n
   A.e_idx = static_cast<int*>(h->d_tmp[3]);
   A.e_d2 = static_cast<float*>(h->d_tmp[4]);
   const int blocks = lm_grid_blocks(h, (int)nq);
-  lm_iter_kernel<<<blocks, LM_THREADS, 0, h->stream>>>(A);
+  if (h->prm.eigen_mode) lm_iter_kernel<1><<<blocks, LM_THREADS, 0, h->stream>>>(A);
+  else lm_iter_kernel<0><<<blocks, LM_THREADS, 0, h->stream>>>(A);
   LL_LAUNCHED(h);
   if (coeff4) LL_CUDA(h, cudaMemcpyAsync(coeff4, h->d_tmp[0], nq * 16, cudaMemcpyDeviceToHost, h->stream));
   if (mask) LL_CUDA(h, cudaMemcpyAsync(mask, h->d_tmp[1], nq * 4, cudaMemcpyDeviceToHost, h->stream));

@@ -59,6 +59,26 @@ __device__ __forceinline__ void pdl_entry() {
   asm volatile("griddepcontrol.launch_dependents;");
 }
 
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// Barrier across a co-resident grid (cooperative launch): `counter` starts at zero and only grows during the
+// launch; `epoch` counts the barriers this thread has passed (the same in every thread of the grid).
+__device__ __forceinline__ void coop_barrier(unsigned* counter, unsigned& epoch) {
+  ++epoch;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();  // cumulative: orders the block's earlier writes (observed through bar.sync) before the arrive
+    atomicAdd(counter, 1u);
+    const unsigned target = epoch * gridDim.x;
+    while (ld_acquire_u32(counter) < target) {}
+  }
+  __syncthreads();
+}
+
 // Streaming 128-bit accesses: raw clouds are read once / written once per stage.
 __device__ __forceinline__ float4 ld_stream(const float4* p) { return __ldcs(p); }
 __device__ __forceinline__ void st_stream(float4* p, float4 v) { __stcs(p, v); }

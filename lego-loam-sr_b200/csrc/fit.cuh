@@ -204,6 +204,9 @@ __device__ void eig3_eigen_style(float a11, float a12, float a13, float a22, flo
 // ---- a7: corner residual ------------------------------------------------------------------------------
 // nb = the five neighbours in ascending (d2, index) order; sel = the query in the map frame.
 // Returns true when the residual is kept (s > min_weight); coeff = (s la, s lb, s lc, s ld2).
+// kEigenMode: compile-time copy of FitParams::eigen_mode (the hot kernels are instantiated per mode so that the
+// Eigen-style iterative solvers of the as-shipped mode stay out of the upstream-mode code).
+template <int kEigenMode>
 __device__ __forceinline__ bool corner_fit(const float nbx[5], const float nby[5], const float nbz[5], float x0,
                                            float y0, float z0, const FitParams& prm, float coeff[4]) {
   float cx = 0.f, cy = 0.f, cz = 0.f;
@@ -219,7 +222,7 @@ __device__ __forceinline__ bool corner_fit(const float nbx[5], const float nby[5
   }
   a11 /= 5.f; a12 /= 5.f; a13 /= 5.f; a22 /= 5.f; a23 /= 5.f; a33 /= 5.f;
   float ev[3], vx, vy, vz;
-  if (prm.eigen_mode == 0) {
+  if constexpr (kEigenMode == 0) {
     float Q[9];
     eig3_eigen_style(a11, a12, a13, a22, a23, a33, ev, Q);
     vx = Q[0 * 3 + 0]; vy = Q[1 * 3 + 0]; vz = Q[2 * 3 + 0];  // ROW 0: (V(0,0), V(0,1), V(0,2)) as shipped

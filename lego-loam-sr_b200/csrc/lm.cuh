@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include "fit.cuh"
 #include "map_build.cuh"
+#include "grid_inline.cuh"
 #include "solve_warp.cuh"
 
 namespace ll {
@@ -631,29 +632,6 @@ __device__ __forceinline__ void knn5_chunks(const float4* __restrict__ sorted, i
   }
 }
 
-__device__ __forceinline__ Knn5 warp_knn5(const float4* __restrict__ sorted, const int2* __restrict__ cells,
-                                          const GridGeom& g, float sx, float sy, float sz, float max_sq_dist,
-                                          int lane) {
-  const int cx = (int)floorf(sx) - g.ox, cy = (int)floorf(sy) - g.oy, cz = (int)floorf(sz) - g.oz;
-  int2 ce = make_int2(0, 0);
-  if (lane < 27) {
-    const int x = cx + (lane % 3) - 1, y = cy + ((lane / 3) % 3) - 1, z = cz + (lane / 9) - 1;
-    if (x >= 0 && x < g.dx && y >= 0 && y < g.dy && z >= 0 && z < g.dz) ce = __ldg(&cells[(z * g.dy + y) * g.dx + x]);
-  }
-  int s = (ce.y > ce.x) ? ce.x : 0x7fffffff;
-  int e = (ce.y > ce.x) ? ce.y : 0;
-  const int s1 = __shfl_down_sync(0xffffffffu, s, 1), e1 = __shfl_down_sync(0xffffffffu, e, 1);
-  const int s2 = __shfl_down_sync(0xffffffffu, s, 2), e2 = __shfl_down_sync(0xffffffffu, e, 2);
-  s = min(s, min(s1, s2));
-  e = max(e, max(e1, e2));
-  const int my_start = e > 0 ? s : 0, my_count = e > 0 ? e - s : 0;  // meaningful on lanes 0, 3, ..., 24
-  Knn5 K;  // best five so far (warp-uniform), ascending
-#pragma unroll
-  for (int k = 0; k < 5; ++k) { K.d2[k] = LM_EMPTY_D2; K.idx[k] = 0xffffffffu; K.pos[k] = 0xffffffffu; }
-  knn5_chunks(sorted, my_start, my_count, sx, sy, sz, max_sq_dist, lane, 0, K);
-  K.accept = K.d2[4] != LM_EMPTY_D2;  // five neighbours, all with d2 < max_sq_dist (:1279 / :1389)
-  return K;
-}
 
 // LM_KNN_BATCH queries of one warp searched TOGETHER: the cell descriptors of all of them are fetched in one
 // round trip, then all their candidates, and the five selection rounds of the different queries are independent
@@ -778,24 +756,39 @@ __device__ __forceinline__ void warp_knn5_batch(const float4* const (&sorted)[2]
       }
     }
   }
-  // ---- queries with more than one chunk of candidates: the remaining chunks, merged into the five found so far
-#pragma unroll
+  // ---- queries with more than one chunk of candidates: the remaining chunks, merged into the five found so far.
+  //      One copy of the chunk loop (not unrolled over q: the kernel is instruction-cache bound enough as it is).
+#pragma unroll 1
   for (int q = 0; q < NB; ++q) {
-    if (mq[q] >= 0 && total[q] > 32 * LM_CAND_UNROLL) {  // warp-uniform
-      Knn5 K;
+    bool heavy = false;
+    int m = 0, qs = 0, qc = 0;
+    float sx = 0.f, sy = 0.f, sz = 0.f;
+    uint32_t d = 0, i = 0, p = 0;
 #pragma unroll
-      for (int k = 0; k < 5; ++k) {
-        K.d2[k] = __shfl_sync(0xffffffffu, od[q], k);
-        K.idx[k] = __shfl_sync(0xffffffffu, oi[q], k);
-        K.pos[k] = __shfl_sync(0xffffffffu, op[q], k);
+    for (int t = 0; t < NB; ++t)
+      if (t == q) {
+        heavy = mq[t] >= 0 && total[t] > 32 * LM_CAND_UNROLL;
+        m = mq[t] > 0 ? 1 : 0; qs = q_start[t]; qc = q_count[t];
+        sx = sel[t].x; sy = sel[t].y; sz = sel[t].z;
+        d = od[t]; i = oi[t]; p = op[t];
       }
-      knn5_chunks(sorted[mq[q] ? 1 : 0], q_start[q], q_count[q], sel[q].x, sel[q].y, sel[q].z, max_sq_dist, lane,
-                  32 * LM_CAND_UNROLL, K);
+    if (!heavy) continue;  // warp-uniform
+    Knn5 K;
 #pragma unroll
-      for (int k = 0; k < 5; ++k)
-        if (lane == k) { od[q] = K.d2[k]; oi[q] = K.idx[k]; op[q] = K.pos[k]; }
-      acc[q] = K.d2[4] != LM_EMPTY_D2;
+    for (int k = 0; k < 5; ++k) {
+      K.d2[k] = __shfl_sync(0xffffffffu, d, k);
+      K.idx[k] = __shfl_sync(0xffffffffu, i, k);
+      K.pos[k] = __shfl_sync(0xffffffffu, p, k);
     }
+    knn5_chunks(sorted[m], qs, qc, sx, sy, sz, max_sq_dist, lane, 32 * LM_CAND_UNROLL, K);
+    d = LM_EMPTY_D2; i = 0xffffffffu; p = 0xffffffffu;
+#pragma unroll
+    for (int k = 0; k < 5; ++k)
+      if (lane == k) { d = K.d2[k]; i = K.idx[k]; p = K.pos[k]; }
+    const bool a5 = K.d2[4] != LM_EMPTY_D2;
+#pragma unroll
+    for (int t = 0; t < NB; ++t)
+      if (t == q) { od[t] = d; oi[t] = i; op[t] = p; acc[t] = a5; }
   }
 }
 #undef LL_KNN_CE
@@ -818,11 +811,16 @@ __device__ __forceinline__ float lm_term(const float sv[8], float one, int k) {
 // memory; s_red must provide at least 64 + 64 doubles. For eigen_mode = upstream the 6x6 solve runs on warp 0
 // and, at iteration 0, the eigen-decomposition runs concurrently on warp 1 (solve_warp.cuh); everything
 // else (as shipped mode, fewer than min_residuals rows) takes the single-thread path above.
+template <int kEigenMode>
 __device__ void lm_solve_block(double* s_red, const LMParams& prm, LMState* S, bool stage_mode) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = (int)(s_red[28] + 0.5);
-  if (prm.fit.eigen_mode == 0 || n < prm.min_residuals) {
+  if constexpr (kEigenMode == 0) {
     if (tid == 0) lm_solve(s_red, prm, S, stage_mode);
+    return;
+  }
+  if (n < prm.min_residuals) {  // LMOptimization returns false before computing anything (:1453)
+    if (tid == 0) lm_apply_and_control(nullptr, n, s_red[27], nullptr, nullptr, prm, S, stage_mode);
     return;
   }
   float* sh = reinterpret_cast<float*>(s_red + 64);
@@ -973,6 +971,7 @@ __device__ void lm_solve_block(double* s_red, const LMParams& prm, LMState* S, b
 }
 
 // Sum the block partials in a fixed order (deterministic regardless of which block arrives last).
+template <int kEigenMode>
 __device__ void reduce_partials_and_solve(const float* partials, int nblocks, const LMParams& prm, LMState* S,
                                           bool stage_mode, double* s_red /* [nwarps][32] shared */) {
   const int lane = threadIdx.x & 31, sub = threadIdx.x >> 5, nsub = blockDim.x >> 5;
@@ -997,7 +996,7 @@ __device__ void reduce_partials_and_solve(const float* partials, int nblocks, co
     s_red[lane] = t;
   }
   __syncthreads();
-  lm_solve_block(s_red, prm, S, stage_mode);
+  lm_solve_block<kEigenMode>(s_red, prm, S, stage_mode);
 }
 
 // Phases 1 and 2 of one LM iteration over queries [q_begin, q_end) of the concatenated query list (corner
@@ -1007,6 +1006,7 @@ __device__ void reduce_partials_and_solve(const float* partials, int nblocks, co
 //   phase 2  one thread per query: line / plane fit, Jacobian row, then a shuffle-tree reduction of the 29
 //            sums over the block (fixed order => bitwise repeatable).
 // Returns, on threads 0..28, this block's total of sum `tid`.
+template <int kEigenMode>
 __device__ __forceinline__ float lm_block_pass(const LMArgs& A, const Trig& trig, const RotTrig& rt,
                                                const GridGeom (&geom)[2], float* s_slot, float (*s_wacc)[32],
                                                int q_begin, int q_end) {
@@ -1083,7 +1083,7 @@ __device__ __forceinline__ float lm_block_pass(const LMArgs& A, const Trig& trig
           float nbx[5], nby[5], nbz[5];
 #pragma unroll
           for (int k = 0; k < 5; ++k) { nbx[k] = slot[4 + 3 * k]; nby[k] = slot[5 + 3 * k]; nbz[k] = slot[6 + 3 * k]; }
-          keep = m == 0 ? corner_fit(nbx, nby, nbz, slot[0], slot[1], slot[2], A.prm.fit, coeff)
+          keep = m == 0 ? corner_fit<kEigenMode>(nbx, nby, nbz, slot[0], slot[1], slot[2], A.prm.fit, coeff)
                         : surf_fit(nbx, nby, nbz, slot[0], slot[1], slot[2], A.prm.fit, coeff);
         }
         if (A.mode != 0) {
@@ -1139,15 +1139,18 @@ __device__ __forceinline__ void lm_partition(const LMArgs& A, int b, int nb, int
 __device__ __forceinline__ void lm_load_geom(const LMArgs& A, GridGeom (&geom)[2]) {
 #pragma unroll
   for (int m = 0; m < 2; ++m) {
+    // __ldcg: in the persistent kernel these fields may have been written by another block moments ago, and this
+    // block's L1 can still hold the MapState line from reading the bounding box
     const MapState* ms = A.mst[m];
-    geom[m].ox = ms->gox; geom[m].oy = ms->goy; geom[m].oz = ms->goz;
-    geom[m].dx = ms->gdx; geom[m].dy = ms->gdy; geom[m].dz = ms->gdz;
+    geom[m].ox = __ldcg(&ms->gox); geom[m].oy = __ldcg(&ms->goy); geom[m].oz = __ldcg(&ms->goz);
+    geom[m].dx = __ldcg(&ms->gdx); geom[m].dy = __ldcg(&ms->gdy); geom[m].dz = __ldcg(&ms->gdz);
   }
 }
 
 // One LM iteration per launch (stage-level entry points, and scan2map when persistent_lm = 0). Each block owns
 // a contiguous chunk of the query list; block partial -> global; the last block to arrive adds all partials in
 // a fixed order and solves.
+template <int kEigenMode>
 __global__ void __launch_bounds__(LM_THREADS, LM_MIN_BLOCKS) lm_iter_kernel(const __grid_constant__ LMArgs A) {
   LMState* S = A.st;
   // Programmatic dependent launch (see enqueue_iterations): wait for the previous grid's results, then let the
@@ -1164,7 +1167,7 @@ __global__ void __launch_bounds__(LM_THREADS, LM_MIN_BLOCKS) lm_iter_kernel(cons
   lm_load_geom(A, geom);
   int q_begin, q_end;
   lm_partition(A, (int)blockIdx.x, (int)gridDim.x, q_begin, q_end);
-  const float run_sum = lm_block_pass(A, trig, rt, geom, s_slot, s_wacc, q_begin, q_end);
+  const float run_sum = lm_block_pass<kEigenMode>(A, trig, rt, geom, s_slot, s_wacc, q_begin, q_end);
   if (A.mode != 0) return;
   if (tid < 32) {
     A.partials[blockIdx.x * 32 + tid] = tid < LM_NSUM ? run_sum : 0.f;
@@ -1179,7 +1182,7 @@ __global__ void __launch_bounds__(LM_THREADS, LM_MIN_BLOCKS) lm_iter_kernel(cons
   if (!s_last) return;
   __threadfence();
   if (tid == 0) S->ticket = 0;
-  reduce_partials_and_solve(A.partials, gridDim.x, A.prm, S, false, reinterpret_cast<double*>(s_slot));
+  reduce_partials_and_solve<kEigenMode>(A.partials, gridDim.x, A.prm, S, false, reinterpret_cast<double*>(s_slot));
 }
 
 // The map-size guard and loop state of scan2MapOptimization (:1573), applied to *S by one thread.
@@ -1194,23 +1197,18 @@ __device__ __forceinline__ void lm_begin_state(LMState* S, const MapState* corne
   S->sel_num = 0;
   S->lm_ret = 0;
   S->ticket = 0;
-  S->corner_map_ds = corner->n_ds;
-  S->surf_map_ds = surf->n_ds;
+  const int n_corner = __ldcg(&corner->n_ds), n_surf = __ldcg(&surf->n_ds);
+  S->corner_map_ds = n_corner;
+  S->surf_map_ds = n_surf;
   int flags = 0;
-  if (corner->voxel_overflow) flags |= 1;
-  if (surf->voxel_overflow) flags |= 2;
-  if (corner->grid_too_large || surf->grid_too_large) flags |= 4;
+  if (__ldcg(&corner->voxel_overflow)) flags |= 1;
+  if (__ldcg(&surf->voxel_overflow)) flags |= 2;
+  if (__ldcg(&corner->grid_too_large) || __ldcg(&surf->grid_too_large)) flags |= 4;
   S->flags = flags;
-  const bool ok = corner->n_ds > prm.min_corner_map && surf->n_ds > prm.min_surf_map && !(flags & 4);
+  const bool ok = n_corner > prm.min_corner_map && n_surf > prm.min_surf_map && !(flags & 4);
   S->status = ok ? 0 : 1;
   S->done = ok ? 0 : 1;
   if (prm.iter_count_thres <= 0) S->done = 1;
-}
-
-__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
 }
 
 // The whole loop of scan2MapOptimization (:1572-1610) in ONE cooperative launch (persistent_lm = 1): one block
@@ -1221,9 +1219,11 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
 // bit-identical new poses without a publish / observe round trip, and nothing waits for a kernel boundary.
 // Block 0 writes the final state back.  barrier: this scan's arrive counter (zero on entry); barrier_clear: the
 // counter a later scan will use (ring of counters in the handle, re-armed 32 scans ahead).
+template <int kEigenMode>
 __global__ void __launch_bounds__(LM_THREADS, 1) lm_persistent_kernel(const __grid_constant__ LMArgs A, float p0, float p1,
                                                                       float p2, float p3, float p4, float p5,
-                                                                      unsigned* barrier, unsigned* barrier_clear) {
+                                                                      unsigned* barrier, unsigned* barrier_clear,
+                                                                      const __grid_constant__ MapBatch GB, int build_grid) {
   __shared__ __align__(16) float s_slot[LM_THREADS * LM_SLOT];
   __shared__ float s_wacc[LM_WARPS][32];
   __shared__ __align__(16) LMState s_st;
@@ -1234,6 +1234,10 @@ __global__ void __launch_bounds__(LM_THREADS, 1) lm_persistent_kernel(const __gr
     uint32_t* dst = reinterpret_cast<uint32_t*>(&s_st);
     if (tid < (int)(sizeof(LMState) / 4)) dst[tid] = __ldcg(src + tid);
   }
+  unsigned epoch = 0;  // grid barriers passed so far
+  static_assert(GI_SMEM_WORDS <= LM_THREADS * LM_SLOT && GI_THREADS == LM_THREADS, "grid_build_inline borrows the staging slots");
+  // a4: the search grids of the local map, when ll_build_local_map left them to this launch (grid_inline.cuh)
+  if (build_grid) grid_build_inline(GB, barrier, epoch, reinterpret_cast<uint32_t*>(s_slot));
   __syncthreads();
   if (tid == 0) {
     const float pose6[6] = {p0, p1, p2, p3, p4, p5};
@@ -1248,20 +1252,14 @@ __global__ void __launch_bounds__(LM_THREADS, 1) lm_persistent_kernel(const __gr
     if (s_st.done) break;  // block-uniform, and the same decision in every block
     const Trig trig = s_st.trig;
     const RotTrig rt = s_st.rtrig;
-    const float run_sum = lm_block_pass(A, trig, rt, geom, s_slot, s_wacc, q_begin, q_end);
+    const float run_sum = lm_block_pass<kEigenMode>(A, trig, rt, geom, s_slot, s_wacc, q_begin, q_end);
     float* part = A.partials + (size_t)(it & 1u) * gridDim.x * 32;
     if (tid < 32) {
       part[blockIdx.x * 32 + tid] = tid < LM_NSUM ? run_sum : 0.f;
       __threadfence();
     }
-    __syncthreads();
-    if (tid == 0) {
-      atomicAdd(barrier, 1u);
-      const unsigned target = (it + 1u) * gridDim.x;
-      while (ld_acquire_u32(barrier) < target) {}
-    }
-    __syncthreads();
-    reduce_partials_and_solve(part, gridDim.x, A.prm, &s_st, false, reinterpret_cast<double*>(s_slot));
+    coop_barrier(barrier, epoch);
+    reduce_partials_and_solve<kEigenMode>(part, gridDim.x, A.prm, &s_st, false, reinterpret_cast<double*>(s_slot));
   }
   if (blockIdx.x == 0) {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(&s_st);
@@ -1328,7 +1326,8 @@ __global__ void __launch_bounds__(LM_THREADS) lm_rows_kernel(const float4* __res
   if (!s_last) return;
   __threadfence();
   if (tid == 0) S->ticket = 0;
-  reduce_partials_and_solve(partials, gridDim.x, prm, S, true, s_red);
+  if (prm.fit.eigen_mode == 0) reduce_partials_and_solve<0>(partials, gridDim.x, prm, S, true, s_red);
+  else reduce_partials_and_solve<1>(partials, gridDim.x, prm, S, true, s_red);
 }
 
 }  // namespace ll
