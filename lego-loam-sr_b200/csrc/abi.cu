@@ -32,7 +32,7 @@ constexpr int kPinSlots = 4;                 // pinned staging buffers in flight
 constexpr int kFirstChunk = 12;              // LM iterations enqueued before the first look at `done`
 constexpr int kNextChunk = 16;
 constexpr int kBarrierSlots = 64;
-constexpr long kInlineGridMaxPoints = 1L << 20;  // raw points up to which the persistent kernel may build the grids itself
+constexpr long kInlineMapMaxPoints = 1L << 20;  // raw points (both maps) up to which the persistent kernel assembles the map itself
 
 struct Keyframe {
   float4* d[3] = {nullptr, nullptr, nullptr};  // corner, surf, outlier (device, packed float4, sensor frame)
@@ -86,6 +86,8 @@ struct ll_handle_s {
   // the search grids of the current local map are still to be built: either inside the persistent scan kernel
   // (grid_inline.cuh) or, for any other consumer, by run_grid_build()
   bool grid_deferred = false;
+  bool map_deferred = false;  // likewise rows a2-a3 (transform, VoxelGrid): map_inline.cuh or run_voxel_build()
+  int n_jobs = 0;             // transform jobs of the segment table uploaded last
   struct { int sa, sb; float leaf_a, leaf_b; int ds_a, ds_b; } grid_cfg = {0, 1, 0.2f, 0.4f, 1, 1};
   bool cells_given_up = false;
 
@@ -418,41 +420,73 @@ MapBatch make_map_batch(const ll_handle h, bool grid_phase) {
   return B;
 }
 
+int ensure_map(ll_handle h);
+int ensure_grid(ll_handle h);
+int run_voxel_build(ll_handle h, bool want_member);
+
 // Run the map pipeline on slots (sa, sb) (sb < 0: single problem). The raw clouds are described by L.
+// With persistent_lm the work on the two surrounding maps is only PREPARED here (segment table uploaded, MapState
+// zeroed) and left to the next scan2map launch, which runs rows a2-a4 and the LM loop in one cooperative kernel
+// (map_inline.cuh); any other consumer of the map first calls ensure_map() / ensure_grid(), which run the stand-alone
+// kernels.
 int run_map_pipeline(ll_handle h, int sa, int sb, const SegList& L, float leaf_a, float leaf_b, int ds_a, int ds_b,
                      bool build_grid, bool want_member) {
-  const int ny = sb >= 0 ? 2 : 1;
-  MapBatch B;
-  std::memset(&B, 0, sizeof(B));
-  B.m[0] = slot_buffers(h, sa, leaf_a, ds_a, want_member);
-  B.sort[0] = slot_sort(h, sa, false);
-  if (sb >= 0) {
-    B.m[1] = slot_buffers(h, sb, leaf_b, ds_b, false);
-    B.sort[1] = slot_sort(h, sb, false);
-  } else {
-    B.m[1] = B.m[0];
-    B.m[1].n_raw = 0;
-    B.sort[1] = B.sort[0];
+  if (h->map_deferred || h->grid_deferred) {
+    if (sa == h->grid_cfg.sa && sb == h->grid_cfg.sb) {  // a new local map replaces the one that was never built
+      h->map_deferred = h->grid_deferred = false;
+    } else {  // another problem (ll_voxel_downsample) shares the segment table: finish the pending map first
+      LL_TRY(ensure_map(h));
+      LL_TRY(ensure_grid(h));
+    }
   }
-  B.count = ny;
+  const int ny = sb >= 0 ? 2 : 1;
+  h->grid_cfg = {sa, sb, leaf_a, leaf_b, ds_a, ds_b};
+  const int slots[2] = {sa, sb};
+  for (int k = 0; k < ny; ++k)  // MapState (bounding box, counts): zero before every build
+    LL_CUDA(h, cudaMemsetAsync(h->slot[slots[k]].scratch, 0, 256, h->stream));
+  LL_TRY(upload_seglist(h, L));
+  h->n_jobs = (int)L.jobs.size();
+  // The persistent kernel sorts one tile of <= 16 * 512 points per block, both maps together, on one block per SM.
+  const long pts = (long)h->slot[sa].n_raw + (sb >= 0 ? (long)h->slot[sb].n_raw : 0);
+  static const bool no_inline = std::getenv("LLB200_NO_INLINE_MAP") != nullptr;  // A/B switch for measurements
+  if (!no_inline && build_grid && h->prm.persistent_lm && sb >= 0 && !want_member && pts <= kInlineMapMaxPoints) {
+    h->map_deferred = true;
+    h->grid_deferred = true;
+    return LL_OK;
+  }
+  LL_TRY(run_voxel_build(h, want_member));
+  if (!build_grid) return LL_OK;
+  static const bool no_inline_grid = std::getenv("LLB200_NO_INLINE_GRID") != nullptr;
+  if (!no_inline_grid && h->prm.persistent_lm && sb >= 0 && !want_member && pts <= kInlineMapMaxPoints) {
+    h->grid_deferred = true;  // the next persistent scan kernel builds the grids; any other consumer calls ensure_grid()
+    return LL_OK;
+  }
+  return run_grid_build(h);
+}
+
+// a2 + a3 as separate launches: transform + bounding box, voxel keys, <= 4 radix passes, voxel reduce.
+int run_voxel_build(ll_handle h, bool want_member) {
+  const int sa = h->grid_cfg.sa, sb = h->grid_cfg.sb;
+  const int ny = sb >= 0 ? 2 : 1;
+  MapBatch B = make_map_batch(h, false);
+  if (want_member) B.m[0].member = h->slot[sa].member;
   const int slots[2] = {sa, sb};
   int maxn = 0;
-  for (int k = 0; k < ny; ++k) {
+  for (int k = 0; k < ny; ++k) {  // sort scratch (everything behind MapState)
     MapSlot& S = h->slot[slots[k]];
-    LL_CUDA(h, cudaMemsetAsync(S.scratch, 0, scratch_bytes_in_use(S), h->stream));
+    LL_CUDA(h, cudaMemsetAsync(S.scratch + 256, 0, scratch_bytes_in_use(S) - 256, h->stream));
     maxn = std::max(maxn, S.n_raw);
   }
-  LL_TRY(upload_seglist(h, L));
-  if (!L.jobs.empty()) {
+  if (h->n_jobs > 0) {
     LL_PROF(h, 0);
-    LL_CUDA(h, launch_pdl(h->stream, transform_minmax_kernel, dim3((unsigned)L.jobs.size()), dim3(MB_THREADS), B,
+    LL_CUDA(h, launch_pdl(h->stream, transform_minmax_kernel, dim3((unsigned)h->n_jobs), dim3(MB_THREADS), B,
                           (const Segment*)h->d_segs, (const BlockJob*)h->d_jobs));
     LL_LAUNCHED(h);
   }
   if (maxn == 0) return LL_OK;
   const unsigned gx_pts = (unsigned)((maxn + MB_TILE - 1) / MB_TILE);
   const unsigned gx_sort = (unsigned)((maxn + RS_TILE - 1) / RS_TILE);
-  if (ds_a || (sb >= 0 && ds_b)) {
+  if (h->grid_cfg.ds_a || (sb >= 0 && h->grid_cfg.ds_b)) {
     LL_PROF(h, 1);
     LL_CUDA(h, launch_pdl(h->stream, voxel_keys_kernel, dim3(gx_pts, ny), dim3(MB_THREADS), B));
     LL_LAUNCHED(h);
@@ -468,18 +502,13 @@ int run_map_pipeline(ll_handle h, int sa, int sb, const SegList& L, float leaf_a
     LL_CUDA(h, launch_pdl(h->stream, voxel_reduce_kernel, dim3(gx_pts, ny), dim3(MB_THREADS), B));
     LL_LAUNCHED(h);
   }
-  if (!build_grid) return LL_OK;
-  h->grid_cfg = {sa, sb, leaf_a, leaf_b, ds_a, ds_b};
-  // the persistent kernel sorts one tile of <= 16 * 512 points per block, both maps together; its grid may be as small
-  // as one block per 16 queries, so bound the raw size (>= the downsampled size) by what the smallest useful grid holds
-  const long pts = (long)h->slot[sa].n_raw + (sb >= 0 ? (long)h->slot[sb].n_raw : 0);
-  static const bool no_inline = std::getenv("LLB200_NO_INLINE_GRID") != nullptr;  // A/B switch for measurements
-  if (!no_inline && h->prm.persistent_lm && sb >= 0 && !want_member && pts <= kInlineGridMaxPoints) {
-    h->grid_deferred = true;  // the next persistent scan kernel builds them; any other consumer calls ensure_grid()
-    return LL_OK;
-  }
-  h->grid_deferred = false;
-  return run_grid_build(h);
+  return LL_OK;
+}
+
+int ensure_map(ll_handle h) {
+  if (!h->map_deferred) return LL_OK;
+  h->map_deferred = false;
+  return run_voxel_build(h, false);
 }
 
 // a4 as five separate launches: cell keys, <= 3 radix passes, cell-ordered points + cell table.
@@ -516,6 +545,7 @@ int run_grid_build(ll_handle h) {
 }
 
 int ensure_grid(ll_handle h) {
+  LL_TRY(ensure_map(h));
   if (!h->grid_deferred) return LL_OK;
   h->grid_deferred = false;
   return run_grid_build(h);
@@ -627,7 +657,7 @@ int scan2map_enqueue(ll_handle h, const float pose6[6]) {
   if (!pose6) return fail(h, LL_ERR_INVALID_ARG, "pose6 is NULL");
   const int nq = h->nq[0] + h->nq[1];
   h->lm_blocks = lm_grid_blocks(h, nq);
-  if (h->prm.persistent_lm && h->grid_deferred) h->lm_blocks = h->num_sms;  // the grid build wants every SM (one tile per block)
+  if (h->prm.persistent_lm && (h->grid_deferred || h->map_deferred)) h->lm_blocks = h->num_sms;  // one tile per block
   LL_TRY(ensure_partials(h, h->lm_blocks));
   if (!h->prm.persistent_lm) LL_TRY(ensure_grid(h));
   if (h->prm.persistent_lm) {
@@ -638,9 +668,13 @@ int scan2map_enqueue(ll_handle h, const float pose6[6]) {
     unsigned* bar_clear = h->d_barriers + ((h->scan_seq + kBarrierSlots / 2) % kBarrierSlots);
     h->scan_seq++;
     MapBatch GB = make_map_batch(h, true);
-    int build_grid = h->grid_deferred ? 1 : 0;
-    h->grid_deferred = false;
-    void* args[] = {&A, &p[0], &p[1], &p[2], &p[3], &p[4], &p[5], &bar, &bar_clear, &GB, &build_grid};
+    int build_map = h->map_deferred ? 1 : 0, build_grid = h->grid_deferred ? 1 : 0;
+    h->map_deferred = h->grid_deferred = false;
+    const Segment* segs = h->d_segs;
+    const BlockJob* jobs = h->d_jobs;
+    int n_jobs = h->n_jobs;
+    void* args[] = {&A, &p[0], &p[1], &p[2], &p[3], &p[4], &p[5], &bar, &bar_clear, &GB, &build_map, &build_grid,
+                    &segs, &jobs, &n_jobs};
     LL_PROF(h, 8);
     LL_CUDA(h, cudaLaunchCooperativeKernel(h->prm.eigen_mode ? reinterpret_cast<const void*>(lm_persistent_kernel<1>)
                                                              : reinterpret_cast<const void*>(lm_persistent_kernel<0>),
@@ -972,6 +1006,7 @@ int ll_get_map_ds(ll_handle h, int which, void* out, size_t cap_points, size_t s
   if (!h->map_ready) return fail(h, LL_ERR_STATE, "no local map");
   if (!stride_ok(stride_bytes)) return fail(h, LL_ERR_INVALID_ARG, "bad stride");
   LL_CUDA(h, cudaSetDevice(h->device));
+  LL_TRY(ensure_map(h));
   MapSlot& S = h->slot[which];
   MapState st;
   LL_CUDA(h, cudaMemcpyAsync(&st, S.st(), sizeof(st), cudaMemcpyDeviceToHost, h->stream));

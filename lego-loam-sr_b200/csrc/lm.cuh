@@ -17,7 +17,7 @@
 #include "common.cuh"
 #include "fit.cuh"
 #include "map_build.cuh"
-#include "grid_inline.cuh"
+#include "map_inline.cuh"
 #include "solve_warp.cuh"
 
 namespace ll {
@@ -1223,7 +1223,9 @@ template <int kEigenMode>
 __global__ void __launch_bounds__(LM_THREADS, 1) lm_persistent_kernel(const __grid_constant__ LMArgs A, float p0, float p1,
                                                                       float p2, float p3, float p4, float p5,
                                                                       unsigned* barrier, unsigned* barrier_clear,
-                                                                      const __grid_constant__ MapBatch GB, int build_grid) {
+                                                                      const __grid_constant__ MapBatch GB, int build_map,
+                                                                      int build_grid, const Segment* segs,
+                                                                      const BlockJob* jobs, int n_jobs) {
   __shared__ __align__(16) float s_slot[LM_THREADS * LM_SLOT];
   __shared__ float s_wacc[LM_WARPS][32];
   __shared__ __align__(16) LMState s_st;
@@ -1235,8 +1237,11 @@ __global__ void __launch_bounds__(LM_THREADS, 1) lm_persistent_kernel(const __gr
     if (tid < (int)(sizeof(LMState) / 4)) dst[tid] = __ldcg(src + tid);
   }
   unsigned epoch = 0;  // grid barriers passed so far
-  static_assert(GI_SMEM_WORDS <= LM_THREADS * LM_SLOT && GI_THREADS == LM_THREADS, "grid_build_inline borrows the staging slots");
+  static_assert(GI_SMEM_WORDS <= LM_THREADS * LM_SLOT && GI_SMEM_WORDS_REDUCE <= LM_THREADS * LM_SLOT && GI_THREADS == LM_THREADS,
+                "the inline map build borrows the staging slots");
   // a4: the search grids of the local map, when ll_build_local_map left them to this launch (grid_inline.cuh)
+  // a1-a3: the local map itself, when ll_build_local_map only prepared it (map_inline.cuh)
+  if (build_map) map_build_inline(GB, segs, jobs, n_jobs, barrier, epoch, reinterpret_cast<uint32_t*>(s_slot));
   if (build_grid) grid_build_inline(GB, barrier, epoch, reinterpret_cast<uint32_t*>(s_slot));
   __syncthreads();
   if (tid == 0) {

@@ -152,13 +152,14 @@ struct VoxelMeta {
 
 __device__ __forceinline__ VoxelMeta voxel_meta(const MapState* st, float inv) {
   VoxelMeta v;
-  const uint32_t e0 = st->mm[0];
+  // __ldcg: in the single-kernel scan (map_inline.cuh) the box is produced by atomics of the same launch
+  const uint32_t e0 = __ldcg(&st->mm[0]);
   v.empty = (e0 == 0u);  // no finite point seen
   float mn[3], mx[3];
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
-    mn[a] = ordered_to_float(~st->mm[a]);
-    mx[a] = ordered_to_float(st->mm[3 + a]);
+    mn[a] = ordered_to_float(~__ldcg(&st->mm[a]));
+    mx[a] = ordered_to_float(__ldcg(&st->mm[3 + a]));
   }
   if (v.empty) {
 #pragma unroll

@@ -284,6 +284,10 @@ def test_scan2map_pose_within_tolerance(abi, orc, single_problem, single_maps, l
         load_map(h, d)
         pose, res = h.scan2map(d["query"]["corner_scan_ds"], d["query"]["surf_total_ds"], d["prior"])
         pose2, res2 = h.scan2map(d["query"]["corner_scan_ds"], d["query"]["surf_total_ds"], d["prior"])
+        # with persistent_lm = 1 the local map was assembled INSIDE the scan kernel (map_inline.cuh): same bits
+        cds_gpu, sds_gpu = h.get_map_ds(0), h.get_map_ds(1)
+    assert np.array_equal(bits(cds_gpu), bits(single_maps["corner_ds"]))
+    assert np.array_equal(bits(sds_gpu), bits(single_maps["surf_ds"]))
     ores, opose, _ = orc.scan2map(single_maps["corner_ds"], single_maps["surf_ds"], d["query"]["corner_scan_ds"],
                                   d["query"]["surf_total_ds"], d["prior"], upstream_params(orc))
     assert res.status == 0 and res.iter_num == ores.iter_num == 10
