@@ -94,6 +94,10 @@ struct ll_handle_s {
   Segment* d_segs = nullptr;
   BlockJob* d_jobs = nullptr;
   size_t segs_cap = 0, jobs_cap = 0;
+  uint8_t* seg_host = nullptr;  // pinned staging of the segment table uploaded last (stage_seglist)
+  size_t seg_bytes = 0, job_bytes = 0;
+  int seg_slot = 0;
+  bool seg_staged = false;
 
   float4* dq[2] = {nullptr, nullptr};
   size_t dq_cap[2] = {0, 0};
@@ -209,6 +213,7 @@ int ensure_bytes(ll_handle h, void** p, size_t* cap, size_t need) {
 // h->pinned always points at the slot acquired last.
 int pinned_acquire(ll_handle h, size_t need) {
   h->pin_cur = (h->pin_cur + 1) % kPinSlots;
+  if (h->seg_staged && h->pin_cur == h->seg_slot) h->pin_cur = (h->pin_cur + 1) % kPinSlots;  // still holds a segment table
   const int s = h->pin_cur;
   LL_CUDA(h, cudaEventSynchronize(h->pin_evt[s]));
   if (h->pin_bytes[s] < need) {
@@ -386,17 +391,36 @@ struct SegList {
   }
 };
 
-int upload_seglist(ll_handle h, const SegList& L) {
+// The segment table is staged in a pinned slot. The single-kernel scan reads it from there directly (zero copy: ~15 KB,
+// a few PCIe round trips spread over the blocks, against two stream-ordered copies in front of the kernel); the
+// stand-alone kernels get a device copy (seglist_to_device). The slot is released after whichever consumer was enqueued.
+int stage_seglist(ll_handle h, const SegList& L) {
   const size_t sb = L.segs.size() * sizeof(Segment), jb = L.jobs.size() * sizeof(BlockJob);
+  h->seg_bytes = sb;
+  h->job_bytes = jb;
+  h->seg_staged = false;
   if (sb == 0) return LL_OK;
-  LL_TRY(ensure_bytes(h, reinterpret_cast<void**>(&h->d_segs), &h->segs_cap, sb));
-  LL_TRY(ensure_bytes(h, reinterpret_cast<void**>(&h->d_jobs), &h->jobs_cap, jb));
   LL_TRY(pinned_acquire(h, sb + jb));
   std::memcpy(h->pinned, L.segs.data(), sb);
   std::memcpy(h->pinned + sb, L.jobs.data(), jb);
-  LL_CUDA(h, cudaMemcpyAsync(h->d_segs, h->pinned, sb, cudaMemcpyHostToDevice, h->stream));
-  LL_CUDA(h, cudaMemcpyAsync(h->d_jobs, h->pinned + sb, jb, cudaMemcpyHostToDevice, h->stream));
-  return pinned_release(h);
+  h->seg_host = h->pinned;
+  h->seg_slot = h->pin_cur;
+  h->seg_staged = true;
+  return LL_OK;
+}
+int seglist_release(ll_handle h) {
+  if (!h->seg_staged) return LL_OK;
+  h->seg_staged = false;
+  LL_CUDA(h, cudaEventRecord(h->pin_evt[h->seg_slot], h->stream));
+  return LL_OK;
+}
+int seglist_to_device(ll_handle h) {
+  if (!h->seg_staged) return LL_OK;
+  LL_TRY(ensure_bytes(h, reinterpret_cast<void**>(&h->d_segs), &h->segs_cap, h->seg_bytes));
+  LL_TRY(ensure_bytes(h, reinterpret_cast<void**>(&h->d_jobs), &h->jobs_cap, h->job_bytes));
+  LL_CUDA(h, cudaMemcpyAsync(h->d_segs, h->seg_host, h->seg_bytes, cudaMemcpyHostToDevice, h->stream));
+  LL_CUDA(h, cudaMemcpyAsync(h->d_jobs, h->seg_host + h->seg_bytes, h->job_bytes, cudaMemcpyHostToDevice, h->stream));
+  return seglist_release(h);
 }
 
 int run_grid_build(ll_handle h);
@@ -441,15 +465,17 @@ int run_map_pipeline(ll_handle h, int sa, int sb, const SegList& L, float leaf_a
   }
   const int ny = sb >= 0 ? 2 : 1;
   h->grid_cfg = {sa, sb, leaf_a, leaf_b, ds_a, ds_b};
-  const int slots[2] = {sa, sb};
-  for (int k = 0; k < ny; ++k)  // MapState (bounding box, counts): zero before every build
-    LL_CUDA(h, cudaMemsetAsync(h->slot[slots[k]].scratch, 0, 256, h->stream));
-  LL_TRY(upload_seglist(h, L));
+  LL_TRY(seglist_release(h));  // (a table staged for a map that was never built)
+  LL_TRY(stage_seglist(h, L));
   h->n_jobs = (int)L.jobs.size();
   // The persistent kernel sorts one tile of <= 16 * 512 points per block, both maps together, on one block per SM.
   const long pts = (long)h->slot[sa].n_raw + (sb >= 0 ? (long)h->slot[sb].n_raw : 0);
   static const bool no_inline = std::getenv("LLB200_NO_INLINE_MAP") != nullptr;  // A/B switch for measurements
   if (!no_inline && build_grid && h->prm.persistent_lm && sb >= 0 && !want_member && pts <= kInlineMapMaxPoints) {
+    // (the kernel zeroes MapState itself.) Zero-copy reads of the staged table from the kernel were measured: +15 us
+    // of PCIe round trips inside the transform stage against ~8 us for the two copies here.
+    static const bool zero_copy = std::getenv("LLB200_SEG_ZERO_COPY") != nullptr;
+    if (!zero_copy) LL_TRY(seglist_to_device(h));
     h->map_deferred = true;
     h->grid_deferred = true;
     return LL_OK;
@@ -472,11 +498,12 @@ int run_voxel_build(ll_handle h, bool want_member) {
   if (want_member) B.m[0].member = h->slot[sa].member;
   const int slots[2] = {sa, sb};
   int maxn = 0;
-  for (int k = 0; k < ny; ++k) {  // sort scratch (everything behind MapState)
+  for (int k = 0; k < ny; ++k) {  // MapState (bounding box, counts) and the sort scratch behind it
     MapSlot& S = h->slot[slots[k]];
-    LL_CUDA(h, cudaMemsetAsync(S.scratch + 256, 0, scratch_bytes_in_use(S) - 256, h->stream));
+    LL_CUDA(h, cudaMemsetAsync(S.scratch, 0, scratch_bytes_in_use(S), h->stream));
     maxn = std::max(maxn, S.n_raw);
   }
+  LL_TRY(seglist_to_device(h));
   if (h->n_jobs > 0) {
     LL_PROF(h, 0);
     LL_CUDA(h, launch_pdl(h->stream, transform_minmax_kernel, dim3((unsigned)h->n_jobs), dim3(MB_THREADS), B,
@@ -672,7 +699,12 @@ int scan2map_enqueue(ll_handle h, const float pose6[6]) {
     h->map_deferred = h->grid_deferred = false;
     const Segment* segs = h->d_segs;
     const BlockJob* jobs = h->d_jobs;
+    if (build_map && h->seg_staged) {  // read the segment table where it was staged (pinned, device-accessible)
+      segs = reinterpret_cast<const Segment*>(h->seg_host);
+      jobs = reinterpret_cast<const BlockJob*>(h->seg_host + h->seg_bytes);
+    }
     int n_jobs = h->n_jobs;
+    A.st_host = h->h_state;  // block 0 writes the result straight into the pinned mirror
     void* args[] = {&A, &p[0], &p[1], &p[2], &p[3], &p[4], &p[5], &bar, &bar_clear, &GB, &build_map, &build_grid,
                     &segs, &jobs, &n_jobs};
     LL_PROF(h, 8);
@@ -681,8 +713,8 @@ int scan2map_enqueue(ll_handle h, const float pose6[6]) {
                                            dim3((unsigned)h->lm_blocks),
                                            dim3(LM_THREADS), args, 0, h->stream));
     LL_LAUNCHED(h);
+    LL_TRY(seglist_release(h));
     h->iters_enqueued = h->prm.iter_count_thres;
-    LL_CUDA(h, cudaMemcpyAsync(h->h_state, h->d_state, sizeof(LMState), cudaMemcpyDeviceToHost, h->stream));
     h->scan_pending = true;
     return LL_OK;
   }

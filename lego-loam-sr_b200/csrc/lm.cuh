@@ -79,6 +79,7 @@ struct LMArgs {
   int nq[2];
   LMParams prm;
   LMState* st;
+  LMState* st_host;  // optional pinned mirror of *st, written by the persistent kernel (saves the copy behind it)
   float* partials;  // [gridDim.x][32]
   int mode;         // 0 = LM iteration; 1 = residuals only (emit); 2 = k-NN only (emit, queries in map frame)
   int w_corner, w_surf;  // relative cost of a corner / surf query (lm_partition)
@@ -1241,7 +1242,12 @@ __global__ void __launch_bounds__(LM_THREADS, 1) lm_persistent_kernel(const __gr
                 "the inline map build borrows the staging slots");
   // a4: the search grids of the local map, when ll_build_local_map left them to this launch (grid_inline.cuh)
   // a1-a3: the local map itself, when ll_build_local_map only prepared it (map_inline.cuh)
-  if (build_map) map_build_inline(GB, segs, jobs, n_jobs, barrier, epoch, reinterpret_cast<uint32_t*>(s_slot));
+  if (build_map) {
+    if (blockIdx.x == 0 && tid < 128)  // MapState of both maps (bounding box, counts): zero before the build
+      reinterpret_cast<uint32_t*>(GB.m[tid >> 6].st)[tid & 63] = 0u;
+    coop_barrier(barrier, epoch);
+    map_build_inline(GB, segs, jobs, n_jobs, barrier, epoch, reinterpret_cast<uint32_t*>(s_slot));
+  }
   if (build_grid) grid_build_inline(GB, barrier, epoch, reinterpret_cast<uint32_t*>(s_slot));
   __syncthreads();
   if (tid == 0) {
@@ -1269,7 +1275,10 @@ __global__ void __launch_bounds__(LM_THREADS, 1) lm_persistent_kernel(const __gr
   if (blockIdx.x == 0) {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(&s_st);
     uint32_t* dst = reinterpret_cast<uint32_t*>(A.st);
-    if (tid < (int)(sizeof(LMState) / 4)) dst[tid] = src[tid];
+    if (tid < (int)(sizeof(LMState) / 4)) {
+      dst[tid] = src[tid];
+      if (A.st_host) reinterpret_cast<uint32_t*>(A.st_host)[tid] = src[tid];
+    }
     if (tid == 0) *barrier_clear = 0u;
   }
 }
