@@ -7,7 +7,7 @@
 //   a3  VoxelGrid                       every block owns ONE tile of 4/8/16 x 512 raw points (both maps share the
 //                                       grid) and keeps its (voxel key, index) pairs in registers:
 //         per 8-bit pass                rank the digits (warp match_any in memory order => stable), publish the
-//                                       tile's 256-bin histogram                                      | barrier
+//                                       tile's 512-bin histogram                                      | barrier
 //                                       sum the histograms of the tiles before this one / of all tiles, exclusive
 //                                       digit prefix, scatter                                          | barrier
 //         reduce                        segment heads per tile                                         | barrier
@@ -29,7 +29,9 @@ constexpr int GI_THREADS = 512;
 constexpr int GI_WARPS = GI_THREADS / 32;
 constexpr int GI_MAX_ITEMS = 16;                 // points per thread: 4, 8 or 16 (one tile per block)
 constexpr int GI_TILE = GI_THREADS * 4;          // host-side unit for the capacity bound
-constexpr int GI_SMEM_WORDS = GI_WARPS * RS_RADIX + RS_RADIX + 16;
+constexpr int GI_DIGIT_BITS = 9;                 // 512 bins = one per thread: a 26-bit voxel key takes 3 passes, not 4
+constexpr int GI_RADIX = 1 << GI_DIGIT_BITS;
+constexpr int GI_SMEM_WORDS = GI_WARPS * GI_RADIX + GI_RADIX + 16;
 constexpr int GI_SMEM_WORDS_REDUCE = 4 * 2 * GI_THREADS + 2 * GI_THREADS + 8 + 64 + 8;  // inline voxel reduce (gi_voxel)
 
 struct GridDims {
@@ -87,38 +89,38 @@ __device__ __forceinline__ TileJob gi_tile(int n0, int n1) {
   return J;
 }
 
-// Stable LSD radix sort of the tiles' (key, value) pairs, 8 bits per pass; key / val hold this block's tile (item k of
+// Stable LSD radix sort of the tiles' (key, value) pairs, GI_DIGIT_BITS bits per pass; key / val hold this block's tile (item k of
 // lane l of warp w = element warp_base + k*32 + l). `active_map` = this block has a tile and its map takes part;
 // bits = significant key bits of this block's map, max_bits = the larger of the two maps (grid-uniform).
-// kCells = false: the result is in S.keys / S.vals[(passes & 1)] (passes = ceil(bits / 8)).
+// kCells = false: the result is in S.keys / S.vals[(passes & 1)] (passes = ceil(bits / GI_DIGIT_BITS)).
 // kCells = true : the last pass writes M.sorted and M.cells instead (the cell sort of the search grid).
 template <int ITEMS, bool kCells>
 __device__ __forceinline__ void gi_sort_core(const MapBatch& B, const TileJob& J, bool active_map, int bits, int max_bits,
                                              uint32_t (&key)[ITEMS], uint32_t (&val)[ITEMS], unsigned* barrier,
                                              unsigned& epoch, uint32_t* smem) {
-  uint32_t (*warp_hist)[RS_RADIX] = reinterpret_cast<uint32_t (*)[RS_RADIX]>(smem);
-  uint32_t* gbase = smem + GI_WARPS * RS_RADIX;
-  uint32_t* wsum = gbase + RS_RADIX;
+  uint32_t (*warp_hist)[GI_RADIX] = reinterpret_cast<uint32_t (*)[GI_RADIX]>(smem);
+  uint32_t* gbase = smem + GI_WARPS * GI_RADIX;
+  uint32_t* wsum = gbase + GI_RADIX;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const MapBuffers& M = B.m[J.m];
   const SortProblem& S = B.sort[J.m];
   const int nm = J.n, warp_base = J.warp_base, tile = J.tile, ntiles = J.ntiles;
   uint32_t rank[ITEMS];
   const uint32_t lt_mask = (1u << lane) - 1u;
-  for (int pass = 0; pass * 8 < max_bits; ++pass) {
-    const int shift = pass * 8;
+  for (int pass = 0; pass * GI_DIGIT_BITS < max_bits; ++pass) {
+    const int shift = pass * GI_DIGIT_BITS;
     const bool active = active_map && shift < bits;  // block-uniform
-    const bool last = shift + 8 >= bits;
+    const bool last = shift + GI_DIGIT_BITS >= bits;
     if (active) {
 #pragma unroll
-      for (int j = 0; j < RS_RADIX / 32; ++j) warp_hist[warp][j * 32 + lane] = 0;
+      for (int j = 0; j < GI_RADIX / 32; ++j) warp_hist[warp][j * 32 + lane] = 0;
       __syncwarp();
 #pragma unroll
       for (int k = 0; k < ITEMS; ++k) {
         const bool valid = (warp_base + k * 32 + lane) < nm;
-        const uint32_t d = (key[k] >> shift) & 255u;
+        const uint32_t d = (key[k] >> shift) & (uint32_t)(GI_RADIX - 1);
         // (eight ballots instead of match.any were measured: no faster here, slower in rs_onesweep_kernel)
-        const unsigned peers = __match_any_sync(0xffffffffu, valid ? d : 256u);
+        const unsigned peers = __match_any_sync(0xffffffffu, valid ? d : (uint32_t)GI_RADIX);
         const int leader = __ffs(peers) - 1;
         uint32_t old = 0;
         if (lane == leader && valid) {
@@ -130,7 +132,7 @@ __device__ __forceinline__ void gi_sort_core(const MapBatch& B, const TileJob& J
         __syncwarp();
       }
       __syncthreads();
-      if (tid < RS_RADIX) {
+      if (tid < GI_RADIX) {
         uint32_t run = 0;
 #pragma unroll
         for (int w = 0; w < GI_WARPS; ++w) {
@@ -138,7 +140,7 @@ __device__ __forceinline__ void gi_sort_core(const MapBatch& B, const TileJob& J
           warp_hist[w][tid] = run;
           run += c;
         }
-        S.status[(size_t)tile * RS_RADIX + tid] = run;
+        S.status[(size_t)tile * GI_RADIX + tid] = run;
       }
     }
     coop_barrier(barrier, epoch);
@@ -151,12 +153,12 @@ __device__ __forceinline__ void gi_sort_core(const MapBatch& B, const TileJob& J
           pt[k] = (warp_base + k * 32 + lane) < nm ? __ldcg(&M.ds[val[k]]) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
       uint32_t before = 0, total = 0;
-      if (tid < RS_RADIX) {
+      if (tid < GI_RADIX) {
         const uint32_t* hist = S.status + tid;
         for (int tt = 0; tt < ntiles; tt += 16) {  // sixteen loads in flight
           uint32_t hv[16];
 #pragma unroll
-          for (int u = 0; u < 16; ++u) hv[u] = tt + u < ntiles ? __ldcg(hist + (size_t)(tt + u) * RS_RADIX) : 0u;
+          for (int u = 0; u < 16; ++u) hv[u] = tt + u < ntiles ? __ldcg(hist + (size_t)(tt + u) * GI_RADIX) : 0u;
 #pragma unroll
           for (int u = 0; u < 16; ++u) {
             total += hv[u];
@@ -164,18 +166,18 @@ __device__ __forceinline__ void gi_sort_core(const MapBatch& B, const TileJob& J
           }
         }
       }
-      uint32_t incl = total;  // exclusive scan of `total` over the 256 digits (threads 0..255 = warps 0..7)
+      uint32_t incl = total;  // exclusive scan of `total` over the digits (thread d = digit d)
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
         const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
         if (lane >= o) incl += up;
       }
-      if (lane == 31 && warp < RS_RADIX / 32) wsum[warp] = incl;
+      if (lane == 31 && warp < GI_RADIX / 32) wsum[warp] = incl;
       __syncthreads();
-      if (tid < RS_RADIX) {
+      if (tid < GI_RADIX) {
         uint32_t woff = 0;
 #pragma unroll
-        for (int w = 0; w < RS_RADIX / 32; ++w) woff += (w < warp) ? wsum[w] : 0u;
+        for (int w = 0; w < GI_RADIX / 32; ++w) woff += (w < warp) ? wsum[w] : 0u;
         gbase[tid] = woff + incl - total + before;
       }
       __syncthreads();
@@ -184,7 +186,7 @@ __device__ __forceinline__ void gi_sort_core(const MapBatch& B, const TileJob& J
 #pragma unroll
       for (int k = 0; k < ITEMS; ++k) {
         if (warp_base + k * 32 + lane < nm) {
-          const uint32_t d = (key[k] >> shift) & 255u;
+          const uint32_t d = (key[k] >> shift) & (uint32_t)(GI_RADIX - 1);
           const uint32_t pos = gbase[d] + warp_hist[warp][d] + rank[k];
           if (kCells && last) {
             const float4 pk = kPrefetch ? pt[kPrefetch ? k : 0] : __ldcg(&M.ds[val[k]]);
@@ -352,7 +354,7 @@ __device__ __forceinline__ void gi_voxel(const MapBatch& B, unsigned* barrier, u
   const int max_bits = max(n[0] ? bits[0] : 0, n[1] ? bits[1] : 0);
   gi_sort_core<ITEMS, false>(B, J, mine, bits[J.m], max_bits, key, val, barrier, epoch, smem);
   // ---- one centroid per voxel, in ascending voxel index. The sorted pairs are in buffer (passes & 1).
-  const int fin = ((bits[J.m] + 7) >> 3) & 1;
+  const int fin = ((bits[J.m] + GI_DIGIT_BITS - 1) / GI_DIGIT_BITS) & 1;
   const uint32_t* __restrict__ keys = S.keys[fin];
   const uint32_t* __restrict__ vals = S.vals[fin];
   uint32_t* s_w = smem;  // [GI_WARPS] heads per warp, then scratch for the block sums
