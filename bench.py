@@ -342,8 +342,12 @@ def run_at_scale(device, peaks):
                                                  ("c3_like_with_voxelgrid", 1, 2_500_000, 200_000, 8_000, 32_000)):
         surf, corner = world(n_surf), world(n_corner)
         prm = headline_params(abi, map_downsample=ds)
-        cq = corner[rng.choice(len(corner), nqc, replace=False)].copy()
-        sq = surf[rng.choice(len(surf), nqs, replace=False)].copy()
+        def vox_order(q, leaf):  # downsampleCurrentScan's VoxelGrid emits points in ascending voxel index (z-major)
+            k = np.floor(q[:, :3] / leaf).astype(np.int64)
+            return np.ascontiguousarray(q[np.lexsort((k[:, 0], k[:, 1], k[:, 2]))])
+
+        cq = vox_order(corner[rng.choice(len(corner), nqc, replace=False)], 0.2)
+        sq = vox_order(surf[rng.choice(len(surf), nqs, replace=False)], 0.4)
         pose = np.array([0.002, -0.003, 0.002, 0.03, -0.02, 0.03], np.float32)
         with abi.Handle(prm, device=device) as h:
             for r in range(4):

@@ -14,7 +14,10 @@ def world(n):
 for ds in (0, 1):
     surf = world(2_000_000 if ds == 0 else 2_500_000); corner = world(200_000)
     prm = abi.default_params(apply_update=1, eigen_mode=1, iter_count_thres=10, stop_thres=0.0, map_downsample=ds)
-    cq = corner[rng.choice(len(corner), 20_000, replace=False)].copy(); sq = surf[rng.choice(len(surf), 80_000, replace=False)].copy()
+    def vox_order(q, leaf):  # the scan-side VoxelGrid emits its points in ascending voxel index (z-major)
+        k = np.floor(q[:, :3] / leaf).astype(np.int64)
+        return q[np.lexsort((k[:, 0], k[:, 1], k[:, 2]))]
+    cq = vox_order(corner[rng.choice(len(corner), 20_000, replace=False)], 0.2).copy(); sq = vox_order(surf[rng.choice(len(surf), 80_000, replace=False)], 0.4).copy()
     pose = np.array([0.002, -0.003, 0.002, 0.03, -0.02, 0.03], np.float32)
     with abi.Handle(prm) as h:
         for r in range(4):
