@@ -293,28 +293,33 @@ def roofline_from_profile(prof, run, peaks):
     q = sum(run["queries"]) / n
     total_ms = sum(ms for ms, _ in prof.values()) or 1e-9
     table = {}
+    # single-kernel scan: the map assembly ran inside the one launch of the step, so that launch moves B_scan =
+    # B_voxel + B_grid + iterations * B_iter, not just the LM part
+    whole_scan = not prof.get("voxel_keys", (0, 0))[1]
     for cls, (ms, cnt) in prof.items():
         if not cnt:
             continue
         per_launch_us = ms * 1e3 / cnt
         b = algorithmic_bytes(cls, n_raw, n_ds, q)
+        if cls == "lm_iter" and whole_scan:
+            b += (16 * n_raw + 16 * n_ds) + 32 * n_ds
         table[cls] = dict(launches_per_step=cnt / n, us_per_launch=round(per_launch_us, 3), share=round(ms / total_ms, 4),
                           gbs=round(b / (per_launch_us * 1e-6) / 1e9, 2) if per_launch_us > 0 else None)
     top = max(table, key=lambda c: table[c]["share"])
     peak = peaks.get("hbm_gbs", 6650.0)
     achieved = table[top]["gbs"]
     traffic = None  # dram__bytes_read + dram__bytes_write per launch from the committed ncu --set full capture
-    for name in ("r01b_ncu_lm_persistent_full.json" if top == "lm_iter" else "", "r01_ncu_%s_full.json" % top):
+    for name in ("r01c_ncu_scan_kernel_full.json" if top == "lm_iter" else "", "r01_ncu_%s_full.json" % top):
         try:
             cap = json.load(open(os.path.join(ROOT, "profiles", name)))
             traffic = int(cap["traffic_bytes_per_launch"])
             break
         except Exception:
             pass
-    roof = {"kernel": "lm_persistent_kernel (all %d LM iterations of a scan)" % ITERS if top == "lm_iter" else top, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roof = {"kernel": "lm_persistent_kernel (the whole scan: transform, VoxelGrid, search grids, %d LM iterations)" % ITERS if top == "lm_iter" else top, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
             "frac": round(achieved / peak, 5), "traffic": traffic,
             "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if "hbm_gbs" in peaks else "fallback 6650 (B200_PROFILING.md)",
-            "algorithmic_bytes_per_launch": int(algorithmic_bytes(top, n_raw, n_ds, q)),
+            "algorithmic_bytes_per_launch": int(round(achieved * 1e9 * table[top]["us_per_launch"] * 1e-6)),
             "us_per_launch": table[top]["us_per_launch"], "share_of_step": table[top]["share"],
             "note": "one scan is latency-bound (10 dependent iterations, ~7 k queries): see DESIGN.md §5 and profiles/"}
     return roof, table, dict(n_raw=round(n_raw), n_ds=round(n_ds), queries=round(q))
