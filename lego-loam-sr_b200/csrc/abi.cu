@@ -38,6 +38,8 @@ struct Keyframe {
   float4* d[3] = {nullptr, nullptr, nullptr};  // corner, surf, outlier (device, packed float4, sensor frame)
   int n[3] = {0, 0, 0};
   float pose[6] = {0, 0, 0, 0, 0, 0};
+  Trig trig = {};      // sin / cos of pose, cached when the pose is set (the pose of a keyframe rarely changes)
+  bool trig_valid = false;
 };
 
 // One map's worth of device buffers. Slots 0 / 1 are the corner / surf surrounding maps; slot 2 serves
@@ -367,7 +369,16 @@ SortProblem slot_sort(const ll_handle h, int s, bool grid_phase) {
 struct SegList {
   std::vector<Segment> segs;
   std::vector<BlockJob> jobs;
-  void add(const float4* src, int count, int dst_off, int map, const float pose6[6]) {
+  // updateTransformPointCloudSinCos (mapOptmization.cpp:622-635): double trig rounded to float
+  static Trig pose_trig(const float pose6[6]) {
+    Trig t;
+    t.cr = (float)std::cos((double)pose6[0]); t.sr = (float)std::sin((double)pose6[0]);
+    t.cp = (float)std::cos((double)pose6[1]); t.sp = (float)std::sin((double)pose6[1]);
+    t.cy = (float)std::cos((double)pose6[2]); t.sy = (float)std::sin((double)pose6[2]);
+    t.tx = pose6[3]; t.ty = pose6[4]; t.tz = pose6[5];
+    return t;
+  }
+  void add(const float4* src, int count, int dst_off, int map, const Trig* trig) {
     if (count <= 0) return;
     Segment s;
     std::memset(&s, 0, sizeof(s));
@@ -375,12 +386,8 @@ struct SegList {
     s.count = count;
     s.dst_off = dst_off;
     s.map = map;
-    if (pose6) {
-      // updateTransformPointCloudSinCos (mapOptmization.cpp:622-635): double trig rounded to float
-      s.t.cr = (float)std::cos((double)pose6[0]); s.t.sr = (float)std::sin((double)pose6[0]);
-      s.t.cp = (float)std::cos((double)pose6[1]); s.t.sp = (float)std::sin((double)pose6[1]);
-      s.t.cy = (float)std::cos((double)pose6[2]); s.t.sy = (float)std::sin((double)pose6[2]);
-      s.t.tx = pose6[3]; s.t.ty = pose6[4]; s.t.tz = pose6[5];
+    if (trig) {
+      s.t = *trig;
       s.identity = 0;
     } else {
       s.identity = 1;
@@ -941,17 +948,25 @@ static int add_keyframe_impl(ll_handle h, int id, const void* c[3], const size_t
   LL_CUDA(h, cudaSetDevice(h->device));
   Keyframe kf;
   std::memcpy(kf.pose, pose6, sizeof(kf.pose));
+  // the three clouds of a keyframe share one arena block (256-byte aligned parts); host clouds are packed into one
+  // pinned slot and travel in ONE copy
+  size_t off[3], total = 0;
   for (int k = 0; k < 3; ++k) {
     kf.n[k] = (int)n[k];
-    void* p = nullptr;
-    LL_TRY(arena_alloc(h, n[k] * sizeof(float4), &p));
-    kf.d[k] = static_cast<float4*>(p);
-    if (n[k] == 0) continue;
-    if (dev) {
-      LL_CUDA(h, cudaMemcpyAsync(kf.d[k], c[k], n[k] * sizeof(float4), cudaMemcpyDeviceToDevice, h->stream));
-    } else {
-      LL_TRY(upload_points(h, kf.d[k], c[k], n[k], stride));
-    }
+    off[k] = total;
+    total += (n[k] * sizeof(float4) + 255) & ~size_t(255);
+  }
+  void* base = nullptr;
+  LL_TRY(arena_alloc(h, total, &base));
+  for (int k = 0; k < 3; ++k) kf.d[k] = reinterpret_cast<float4*>(static_cast<uint8_t*>(base) + off[k]);
+  if (dev) {
+    for (int k = 0; k < 3; ++k)
+      if (n[k]) LL_CUDA(h, cudaMemcpyAsync(kf.d[k], c[k], n[k] * sizeof(float4), cudaMemcpyDeviceToDevice, h->stream));
+  } else if (n[0] + n[1] + n[2] > 0) {
+    LL_TRY(pinned_acquire(h, total));
+    for (int k = 0; k < 3; ++k) pack_points(reinterpret_cast<float4*>(h->pinned + off[k]), c[k], n[k], stride);
+    LL_CUDA(h, cudaMemcpyAsync(base, h->pinned, total, cudaMemcpyHostToDevice, h->stream));
+    LL_TRY(pinned_release(h));
   }
   h->kfs[id] = kf;  // re-adding an id replaces the entry (the old slab space is not reclaimed)
   return LL_OK;
@@ -976,6 +991,7 @@ int ll_set_keyframe_pose(ll_handle h, int id, const float pose6[6]) {
   auto it = h->kfs.find(id);
   if (it == h->kfs.end()) return fail(h, LL_ERR_NOT_FOUND, "unknown keyframe id " + std::to_string(id));
   std::memcpy(it->second.pose, pose6, 6 * sizeof(float));
+  it->second.trig_valid = false;
   return LL_OK;
 }
 
@@ -996,10 +1012,14 @@ int ll_build_local_map(ll_handle h, const int* ids, int n_ids) {
   SegList L;
   int oc = 0, os = 0;
   for (int i = 0; i < n_ids; ++i) {  // cache order = ids order; per keyframe corner | surf, outlier (:1147-1151)
-    const Keyframe& kf = h->kfs[ids[i]];
-    L.add(kf.d[0], kf.n[0], oc, 0, kf.pose); oc += kf.n[0];
-    L.add(kf.d[1], kf.n[1], os, 1, kf.pose); os += kf.n[1];
-    L.add(kf.d[2], kf.n[2], os, 1, kf.pose); os += kf.n[2];
+    Keyframe& kf = h->kfs[ids[i]];
+    if (!kf.trig_valid) {
+      kf.trig = SegList::pose_trig(kf.pose);
+      kf.trig_valid = true;
+    }
+    L.add(kf.d[0], kf.n[0], oc, 0, &kf.trig); oc += kf.n[0];
+    L.add(kf.d[1], kf.n[1], os, 1, &kf.trig); os += kf.n[1];
+    L.add(kf.d[2], kf.n[2], os, 1, &kf.trig); os += kf.n[2];
   }
   h->slot[0].n_raw = (int)nc;
   h->slot[1].n_raw = (int)ns;
