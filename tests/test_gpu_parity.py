@@ -303,6 +303,59 @@ def test_scan2map_pose_within_tolerance(abi, orc, single_problem, single_maps, l
     print("scan2map: |dt| %.2e m, |dr| %.2e rad vs oracle; sel %d vs %d" % (trans_err(pose, opose), rot_err(pose, opose), res.sel_num, ores.sel_num))
 
 
+def _scan_both_ways(abi, corner, surf, cq, sq, prior, **kw):
+    """The same scan through the single-kernel path (persistent_lm = 1: map assembly, search grids and the LM loop in one
+    cooperative launch, map_inline.cuh) and through the stand-alone kernels (persistent_lm = 0)."""
+    out = []
+    for persistent in (1, 0):
+        with abi.Handle(upstream_params(abi, persistent_lm=persistent, **kw)) as h:
+            h.set_local_map_raw(corner, surf)
+            pose, res = h.scan2map(cq, sq, prior)
+            pose2, res2 = h.scan2map(cq, sq, prior)  # the map is built: the second scan only runs the LM loop
+            out.append((pose, res, pose2, res2, h.get_map_ds(0), h.get_map_ds(1)))
+    return out
+
+
+def test_single_kernel_scan_equals_stand_alone_kernels(abi, orc, single_problem, single_maps):
+    """Bit-for-bit: maps, poses and statistics of the two execution paths, on ordinary and on degenerate inputs."""
+    d = single_problem
+    rng = np.random.default_rng(11)
+    kf = d["keyframes"]
+    raw_c = np.concatenate([f["corner_scan"] for f in kf[:6]]).astype(np.float32)
+    raw_s = np.concatenate([np.concatenate([f["surf_last_ds"], f["outlier_last_ds"]]) for f in kf[:6]]).astype(np.float32)
+    cq, sq, prior = d["query"]["corner_scan_ds"], d["query"]["surf_total_ds"], np.zeros(6, np.float32)
+    nan_s = raw_s.copy()
+    nan_s[rng.choice(len(nan_s), 50, replace=False), 1] = np.nan           # non-finite points are dropped by VoxelGrid
+    nan_s[rng.choice(len(nan_s), 7, replace=False), 0] = np.inf
+    one_cell_c = (raw_c[:300] * np.float32(1e-3) + np.float32(0.5)).astype(np.float32)   # everything inside one 1 m cell
+    one_cell_c[:, 3] = raw_c[:300, 3]
+    cases = {
+        "ordinary": (raw_c, raw_s, {}),
+        "non-finite points": (raw_c, nan_s, {}),
+        "tiny corner map (guard :1573)": (raw_c[:8], raw_s, {}),
+        "empty corner map": (raw_c[:0], raw_s, {}),
+        "single-cell corner map": (one_cell_c, raw_s, {}),
+        "no map downsampling": (raw_c, raw_s, dict(map_downsample=0)),
+        "voxel index overflow (PCL pass-through)": (raw_c, raw_s, dict(corner_leaf=1e-4, surf_leaf=1e-4)),
+        "as shipped": (raw_c, raw_s, dict(apply_update=0, eigen_mode=0, iter_count_thres=200)),
+    }
+    for name, (c, s_, kw) in cases.items():
+        (p1, r1, p1b, r1b, c1, s1), (p0, r0, p0b, r0b, c0, s0) = _scan_both_ways(abi, c, s_, cq, sq, prior, **kw)
+        assert np.array_equal(bits(c1), bits(c0)) and np.array_equal(bits(s1), bits(s0)), name
+        for (pa, ra), (pb, rb) in (((p1, r1), (p0, r0)), ((p1b, r1b), (p0b, r0b)), ((p1, r1), (p1b, r1b))):
+            assert np.array_equal(bits(pa), bits(pb)), (name, pa, pb)
+            assert (ra.status, ra.iter_num, ra.sel_num, ra.flags, ra.corner_map_ds, ra.surf_map_ds, ra.is_degenerate) == \
+                   (rb.status, rb.iter_num, rb.sel_num, rb.flags, rb.corner_map_ds, rb.surf_map_ds, rb.is_degenerate), name
+            assert bits(np.float32(ra.min_lambda)) == bits(np.float32(rb.min_lambda)) and \
+                   bits(np.float32(ra.cf_mean)) == bits(np.float32(rb.cf_mean)), name
+    # and against the oracle for the ordinary case
+    prm = upstream_params(orc)
+    ocd = orc.voxel_downsample(raw_c, prm.corner_leaf)[0]
+    osd = orc.voxel_downsample(raw_s, prm.surf_leaf)[0]
+    (p1, r1, _, _, c1, s1), _ = _scan_both_ways(abi, raw_c, raw_s, cq, sq, prior)
+    assert np.array_equal(bits(c1), bits(ocd)) and np.array_equal(bits(s1), bits(osd))
+
+
 def test_scan2map_early_exit_and_thresholds(abi, orc, single_problem, single_maps):
     d = single_problem
     for kw in (dict(stop_thres=0.05, iter_count_thres=30), dict(stop_thres=0.05, iter_count_thres=200),
