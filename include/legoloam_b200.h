@@ -116,6 +116,13 @@ int ll_add_keyframe(ll_handle h, int id, const void* corner, size_t n_corner, co
                     const float pose6[6]);
 int ll_add_keyframe_dev(ll_handle h, int id, const void* d_corner, size_t n_corner, const void* d_surf,
                         size_t n_surf, const void* d_outlier, size_t n_outlier, const float pose6[6]);
+/* Optional overlap of the keyframe upload with the scan in flight: the three clouds saveKeyFramesAndFactor will store
+ * (:1744-1752) are inputs of the frame, only their pose comes out of scan2MapOptimization. Called between
+ * ll_scan2map_async and ll_scan2map_wait, this packs and uploads them on the handle's copy stream while the scan
+ * kernel runs; the following ll_add_keyframe with the same id then only attaches the pose (its cloud arguments are
+ * ignored). Without it ll_add_keyframe uploads as before. */
+int ll_prefetch_keyframe(ll_handle h, int id, const void* corner, size_t n_corner, const void* surf, size_t n_surf,
+                         const void* outlier, size_t n_outlier, size_t stride_bytes);
 /* correctPoses (mapOptmization.cpp:1757-1785) */
 int ll_set_keyframe_pose(ll_handle h, int id, const float pose6[6]);
 

@@ -73,6 +73,11 @@ struct ll_handle_s {
   std::string err;
   uint64_t launches = 0;
 
+  cudaStream_t copy_stream = nullptr;  // keyframe prefetch (ll_prefetch_keyframe) overlaps the scan on `stream`
+  cudaEvent_t kf_evt = nullptr;
+  int prefetched_id = -1;
+  Keyframe prefetched_kf;
+
   std::vector<void*> arena;
   size_t arena_off = 0, arena_cap = 0;
   std::unordered_map<int, Keyframe> kfs;
@@ -859,6 +864,8 @@ int ll_create(const ll_params* p, int device_id, ll_handle* out) {
   for (int i = 0; i < kPinSlots; ++i)
     ev_ok = ev_ok && cudaEventCreateWithFlags(&h->pin_evt[i], cudaEventDisableTiming) == cudaSuccess;
   bool ok = ev_ok && cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaEventCreateWithFlags(&h->kf_evt, cudaEventDisableTiming) == cudaSuccess &&
             cudaMalloc(reinterpret_cast<void**>(&h->d_state), sizeof(LMState)) == cudaSuccess &&
             cudaMalloc(reinterpret_cast<void**>(&h->d_barriers), sizeof(unsigned) * kBarrierSlots) == cudaSuccess &&
             cudaMemsetAsync(h->d_barriers, 0, sizeof(unsigned) * kBarrierSlots, h->stream) == cudaSuccess &&
@@ -877,6 +884,8 @@ int ll_create(const ll_params* p, int device_id, ll_handle* out) {
 int ll_destroy(ll_handle h) {
   if (!h) return LL_OK;
   cudaSetDevice(h->device);
+  if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
+  if (h->kf_evt) cudaEventDestroy(h->kf_evt);
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (void* p : h->arena) cudaFree(p);
   for (MapSlot& S : h->slot) {
@@ -938,6 +947,9 @@ int ll_get_launch_count(ll_handle h, uint64_t* n) {
   return LL_OK;
 }
 
+static int store_keyframe_clouds(ll_handle h, int id, Keyframe kf, const void* c[3], const size_t n[3], size_t stride, bool dev,
+                                 cudaStream_t st);
+
 static int add_keyframe_impl(ll_handle h, int id, const void* c[3], const size_t n[3], size_t stride, bool dev,
                              const float pose6[6]) {
   if (!h) return LL_ERR_INVALID_ARG;
@@ -946,8 +958,23 @@ static int add_keyframe_impl(ll_handle h, int id, const void* c[3], const size_t
   for (int k = 0; k < 3; ++k)
     if (n[k] && !c[k]) return fail(h, LL_ERR_INVALID_ARG, "NULL cloud with non-zero count");
   LL_CUDA(h, cudaSetDevice(h->device));
+  if (!dev && id == h->prefetched_id) {  // the clouds are already on their way (ll_prefetch_keyframe): attach the pose
+    Keyframe kf = h->prefetched_kf;
+    std::memcpy(kf.pose, pose6, sizeof(kf.pose));
+    h->prefetched_id = -1;
+    LL_CUDA(h, cudaStreamWaitEvent(h->stream, h->kf_evt, 0));  // later work on the main stream sees the upload
+    h->kfs[id] = kf;
+    return LL_OK;
+  }
   Keyframe kf;
   std::memcpy(kf.pose, pose6, sizeof(kf.pose));
+  return store_keyframe_clouds(h, id, kf, c, n, stride, dev, h->stream);
+}
+
+// Device copies of a keyframe's three clouds (one arena block, 256-byte aligned parts; host clouds are packed into one
+// pinned slot and travel in ONE copy on `st`), then the keyframe is registered — or parked as the prefetched one.
+static int store_keyframe_clouds(ll_handle h, int id, Keyframe kf, const void* c[3], const size_t n[3], size_t stride, bool dev,
+                                 cudaStream_t st) {
   // the three clouds of a keyframe share one arena block (256-byte aligned parts); host clouds are packed into one
   // pinned slot and travel in ONE copy
   size_t off[3], total = 0;
@@ -961,15 +988,33 @@ static int add_keyframe_impl(ll_handle h, int id, const void* c[3], const size_t
   for (int k = 0; k < 3; ++k) kf.d[k] = reinterpret_cast<float4*>(static_cast<uint8_t*>(base) + off[k]);
   if (dev) {
     for (int k = 0; k < 3; ++k)
-      if (n[k]) LL_CUDA(h, cudaMemcpyAsync(kf.d[k], c[k], n[k] * sizeof(float4), cudaMemcpyDeviceToDevice, h->stream));
+      if (n[k]) LL_CUDA(h, cudaMemcpyAsync(kf.d[k], c[k], n[k] * sizeof(float4), cudaMemcpyDeviceToDevice, st));
   } else if (n[0] + n[1] + n[2] > 0) {
     LL_TRY(pinned_acquire(h, total));
     for (int k = 0; k < 3; ++k) pack_points(reinterpret_cast<float4*>(h->pinned + off[k]), c[k], n[k], stride);
-    LL_CUDA(h, cudaMemcpyAsync(base, h->pinned, total, cudaMemcpyHostToDevice, h->stream));
-    LL_TRY(pinned_release(h));
+    LL_CUDA(h, cudaMemcpyAsync(base, h->pinned, total, cudaMemcpyHostToDevice, st));
+    LL_CUDA(h, cudaEventRecord(h->pin_evt[h->pin_cur], st));
   }
-  h->kfs[id] = kf;  // re-adding an id replaces the entry (the old slab space is not reclaimed)
+  if (st == h->stream) {
+    h->kfs[id] = kf;  // re-adding an id replaces the entry (the old slab space is not reclaimed)
+  } else {
+    LL_CUDA(h, cudaEventRecord(h->kf_evt, st));
+    h->prefetched_kf = kf;
+    h->prefetched_id = id;
+  }
   return LL_OK;
+}
+
+int ll_prefetch_keyframe(ll_handle h, int id, const void* corner, size_t n_corner, const void* surf, size_t n_surf,
+                         const void* outlier, size_t n_outlier, size_t stride_bytes) {
+  if (!h) return LL_ERR_INVALID_ARG;
+  if (!stride_ok(stride_bytes)) return fail(h, LL_ERR_INVALID_ARG, "stride_bytes must be 16 or >= 20 and a multiple of 4");
+  const void* c[3] = {corner, surf, outlier};
+  const size_t n[3] = {n_corner, n_surf, n_outlier};
+  for (int k = 0; k < 3; ++k)
+    if (n[k] && !c[k]) return fail(h, LL_ERR_INVALID_ARG, "NULL cloud with non-zero count");
+  LL_CUDA(h, cudaSetDevice(h->device));
+  return store_keyframe_clouds(h, id, Keyframe(), c, n, stride_bytes, false, h->copy_stream);
 }
 
 int ll_add_keyframe(ll_handle h, int id, const void* corner, size_t n_corner, const void* surf, size_t n_surf,

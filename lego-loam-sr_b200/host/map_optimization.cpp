@@ -254,14 +254,27 @@ void MapOptimization::scan2MapOptimization() {  // :1572-1610
                           view_->n_surf_total_ds, transformTobeMapped, &lastResult),
           "ll_scan2map_dev");
   } else if (view_) {
-    check(ll_scan2map(h_, view_->corner_scan_ds, view_->n_corner_scan_ds, view_->surf_total_ds, view_->n_surf_total_ds,
-                      view_->stride_bytes, transformTobeMapped, &lastResult),
-          "ll_scan2map");
+    // While the scan runs on the GPU, pack and upload the three clouds saveKeyFramesAndFactor is about to store
+    // (every frame becomes a keyframe, :1622-1631; only its pose comes out of the scan).
+    check(ll_scan2map_async(h_, view_->corner_scan_ds, view_->n_corner_scan_ds, view_->surf_total_ds,
+                            view_->n_surf_total_ds, view_->stride_bytes, transformTobeMapped),
+          "ll_scan2map_async");
+    check(ll_prefetch_keyframe(h_, (int)cloudKeyPoses3D.size(), view_->corner_scan, view_->n_corner_scan,
+                               view_->surf_last_ds, view_->n_surf_last_ds, view_->outlier_last_ds,
+                               view_->n_outlier_last_ds, view_->stride_bytes),
+          "ll_prefetch_keyframe");
+    check(ll_scan2map_wait(h_, transformTobeMapped, &lastResult), "ll_scan2map_wait");
   } else {
-    check(ll_scan2map(h_, laserCloudCornerScanDS->points.data(), laserCloudCornerScanDS->size(),
-                      laserCloudSurfTotalLastDS->points.data(), laserCloudSurfTotalLastDS->size(), sizeof(PointType),
-                      transformTobeMapped, &lastResult),
-          "ll_scan2map");
+    check(ll_scan2map_async(h_, laserCloudCornerScanDS->points.data(), laserCloudCornerScanDS->size(),
+                            laserCloudSurfTotalLastDS->points.data(), laserCloudSurfTotalLastDS->size(),
+                            sizeof(PointType), transformTobeMapped),
+          "ll_scan2map_async");
+    check(ll_prefetch_keyframe(h_, (int)cloudKeyPoses3D.size(), laserCloudCornerScan->points.data(),
+                               laserCloudCornerScan->size(), laserCloudSurfLastDS->points.data(),
+                               laserCloudSurfLastDS->size(), laserCloudOutlierLastDS->points.data(),
+                               laserCloudOutlierLastDS->size(), sizeof(PointType)),
+          "ll_prefetch_keyframe");
+    check(ll_scan2map_wait(h_, transformTobeMapped, &lastResult), "ll_scan2map_wait");
   }
   laserCloudCornerFromMapDSNum = lastResult.corner_map_ds;
   laserCloudSurfFromMapDSNum = lastResult.surf_map_ds;
