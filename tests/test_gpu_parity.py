@@ -7,6 +7,8 @@ Bars (BASELINE.json north_star):
   * per-point residual records: |diff| <= 2e-5 (same masks except points within float rounding of a threshold);
   * final 6-DoF pose after 10 LM iterations: <= 1e-4 m translation, <= 1e-5 rad rotation.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -504,6 +506,25 @@ def test_full_size_properties(abi, orc):
         assert np.array_equal(idx[sample][o_acc], o_idx[o_acc])
         assert np.array_equal(bits(d2[sample][o_acc]), bits(o_d2[o_acc]))
         assert (np.diff(d2[accept == 1], axis=1) >= 0).all()
+
+
+def test_reference_recorded_maps(abi, orc):
+    """The reference's own recorded maps (tests/golden/reference_maps.npz, see make_reference_maps.py): VoxelGrid bit-exact
+    vs the oracle, 5-NN bit-exact vs the answers of the reference's vendored nanoflann stored in the fixture."""
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_maps.npz"))
+    with abi.Handle(abi.default_params()) as h:
+        for cloud, leaf in ((g["corner_map"], 0.2), (g["surf_map"], 0.4), (g["corner_map"], 0.4)):
+            out, _, flags = h.voxel_downsample(cloud, leaf)
+            o_out = orc.voxel_downsample(cloud, leaf)[0]
+            assert flags == 0 and np.array_equal(bits(out), bits(o_out)), leaf
+    cds = orc.voxel_downsample(g["corner_map"], 0.2)[0]
+    with abi.Handle(abi.default_params(map_downsample=0)) as h:
+        h.set_local_map_raw(cds, g["surf_map"])
+        idx, d2, accept = h.knn5(0, g["queries"])
+    acc = g["knn_d2"][:, 4] < 1.0
+    assert np.array_equal(accept.astype(bool), acc)
+    assert np.array_equal(bits(d2[acc]), bits(g["knn_d2"][acc]))
+    assert np.array_equal(idx[acc & g["tie_free"]], g["knn_idx"][acc & g["tie_free"]])
 
 
 # ------------------------------------------------------------------------------------------ batched replay (config 5 shape)

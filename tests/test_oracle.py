@@ -263,3 +263,24 @@ def test_golden_vectors(orc):
     res, pose, st = orc.scan2map(z["corner_map"], z["surf_map"], z["corner_q"], z["surf_q"], z["prior"], prm)
     assert np.allclose(pose, z["pose10"], atol=1e-6)
     assert res.sel_num == int(z["sel_num"])
+
+
+REF_MAPS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_maps.npz")
+
+
+def test_reference_recorded_maps_knn(orc):
+    """Real-distribution inputs: maps the reference node itself recorded (Result/0318_test/*.pcd, committed as a fixture
+    by tests/golden/make_reference_maps.py together with the answers of the reference's vendored nanoflann). The
+    oracle's uniform grid and its brute force must reproduce those neighbours and distances bit for bit."""
+    g = np.load(REF_MAPS)
+    cds = orc.voxel_downsample(g["corner_map"], 0.2)[0]
+    assert 5000 < len(cds) < len(g["corner_map"])
+    for backend in (orc.KNN_GRID, orc.KNN_BRUTE):
+        idx, d2 = orc.knn5(cds, g["queries"], backend)
+        acc = g["knn_d2"][:, 4] < 1.0  # the grid only answers within the reference's 1 m acceptance radius
+        sel = acc if backend == orc.KNN_GRID else np.ones(len(acc), bool)
+        assert np.array_equal(d2[sel].view(np.uint32), g["knn_d2"][sel].view(np.uint32))
+        assert np.array_equal(idx[sel & g["tie_free"]], g["knn_idx"][sel & g["tie_free"]])
+    # VoxelGrid on real data: idempotent membership, every output inside its voxel
+    out, member, flag = orc.voxel_downsample(g["surf_map"], 0.4)
+    assert flag == 0 and member.max() == len(out) - 1 and (np.bincount(member) > 0).all()
