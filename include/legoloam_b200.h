@@ -186,6 +186,20 @@ int ll_reset_state(ll_handle h);
 int ll_solve_normal_eq(ll_handle h, const float* rows6, const float* b, size_t n, int dof_mask, int iter,
                        float eig_thresh, float* x_out, float* matP_inout, int* is_degenerate_inout);
 
+/* ---- f-3: FeatureAssociation's correspondence search (featureAssociation.cpp:1580-1697 corner, :1699-1844 surf,
+ * TransformToStart :1389-1412 inside). which = 0 corner (two tripod points), 1 surf (three).
+ * ll_fa_set_last replaces kdtree{Corner,Surf}Last.setInputCloud(laserCloud{Corner,Surf}Last) (:2311-2312, :2715-2716):
+ * the cloud (intensity = ring + column / 10000) is uploaded once per sweep.
+ * ll_fa_find_correspondences replaces one call of findCorresponding{Corner,Surf}Features(iterCount): queries =
+ * cornerPointsSharp / surfPointsFlat; ind1/ind2/ind3 [nq] are pointSearch*Ind1/2/3 (host arrays, rewritten when
+ * iter_count % 5 == 0 and read otherwise; ind3 may be NULL for which = 0); coeff4 [nq][4] and keep [nq] describe the
+ * (laserCloudOri = queries[i], coeffSel) pair each query pushes (keep[i] = 0: none) — the caller appends the kept ones in
+ * order and hands them to ll_solve_normal_eq as today. Synchronous. */
+int ll_fa_set_last(ll_handle h, int which, const void* cloud, size_t n, size_t stride_bytes);
+int ll_fa_find_correspondences(ll_handle h, int which, const void* queries, size_t nq, size_t stride_bytes,
+                               const float transform_cur[6], int iter_count, float nearest_feature_dist_sqr,
+                               int* ind1, int* ind2, int* ind3, float* coeff4, int* keep);
+
 #ifdef __cplusplus
 }
 #endif

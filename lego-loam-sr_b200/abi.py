@@ -257,6 +257,26 @@ class Handle:
                                       _vp(d2), _vp(accept)))
         return idx[:nq], d2[:nq], accept[:nq]
 
+    # -- f-3: FeatureAssociation correspondence search ---------------------------------------------
+    def fa_set_last(self, which, cloud):
+        c, n, stride = _cloud(cloud)
+        self._check(self._lib.ll_fa_set_last(self._h, C.c_int(which), _vp(c), C.c_size_t(n), C.c_size_t(stride)))
+
+    def fa_find_correspondences(self, which, queries, transform_cur, it, nearest_feature_dist_sqr=25.0, ind=None):
+        """-> (ind1, ind2, ind3, coeff [nq,4], keep [nq]); ind = the index arrays of an earlier call (it % 5 != 0)."""
+        q, nq, stride = _cloud(queries)
+        m = max(nq, 1)
+        if ind is None:
+            ind = [np.full(m, -1, np.int32) for _ in range(3)]
+        ind = [np.ascontiguousarray(a, np.int32).copy() for a in ind]
+        coeff = np.zeros((m, 4), np.float32)
+        keep = np.zeros(m, np.int32)
+        tc = np.ascontiguousarray(transform_cur, np.float32)
+        self._check(self._lib.ll_fa_find_correspondences(self._h, C.c_int(which), _vp(q), C.c_size_t(nq), C.c_size_t(stride),
+                                                         _vp(tc), C.c_int(it), C.c_float(nearest_feature_dist_sqr),
+                                                         _vp(ind[0]), _vp(ind[1]), _vp(ind[2]), _vp(coeff), _vp(keep)))
+        return ind[0][:nq], ind[1][:nq], ind[2][:nq], coeff[:nq], keep[:nq]
+
     def _residuals(self, fn, queries, pose6):
         q, nq, stride = _cloud(queries)
         m = max(nq, 1)

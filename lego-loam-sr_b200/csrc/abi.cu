@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "fa_corr.cuh"
 #include "fit.cuh"
 #include "lm.cuh"
 #include "map_build.cuh"
@@ -122,6 +123,9 @@ struct ll_handle_s {
   int lm_blocks = 0;
 
   void* d_tmp[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // emit / stage scratch
+  float4* fa_last[2] = {nullptr, nullptr};  // laserCloudCornerLast / laserCloudSurfLast (ll_fa_set_last)
+  size_t fa_last_cap[2] = {0, 0};
+  int fa_n_last[2] = {0, 0};
 
   // optional per-kernel-class timing with CUDA events on the launching stream (bench.py roofline)
   bool prof_on = false;
@@ -893,7 +897,7 @@ int ll_destroy(ll_handle h) {
     for (void* p : ptrs)
       if (p) cudaFree(p);
   }
-  void* ptrs[] = {h->d_segs, h->d_jobs, h->dq[0], h->dq[1], h->d_state, h->d_partials, h->d_barriers,
+  void* ptrs[] = {h->d_segs, h->d_jobs, h->dq[0], h->dq[1], h->d_state, h->d_partials, h->d_barriers, h->fa_last[0], h->fa_last[1],
                   h->d_tmp[0], h->d_tmp[1], h->d_tmp[2], h->d_tmp[3], h->d_tmp[4], h->d_tmp[5]};
   for (void* p : ptrs)
     if (p) cudaFree(p);
@@ -1349,6 +1353,72 @@ int ll_reset_state(ll_handle h) {
   LL_CUDA(h, cudaStreamSynchronize(h->stream));
   std::memset(h->h_state, 0, sizeof(LMState));
   h->scan_pending = false;
+  return LL_OK;
+}
+
+
+int ll_fa_set_last(ll_handle h, int which, const void* cloud, size_t n, size_t stride_bytes) {
+  if (!h) return LL_ERR_INVALID_ARG;
+  if (which != 0 && which != 1) return fail(h, LL_ERR_INVALID_ARG, "which must be 0 (corner) or 1 (surf)");
+  if (n && (!cloud || !stride_ok(stride_bytes))) return fail(h, LL_ERR_INVALID_ARG, "bad cloud / stride");
+  if (n > 0x3fffffff) return fail(h, LL_ERR_INVALID_ARG, "cloud too large");
+  LL_CUDA(h, cudaSetDevice(h->device));
+  LL_TRY(ensure_bytes(h, reinterpret_cast<void**>(&h->fa_last[which]), &h->fa_last_cap[which], std::max<size_t>(n, 1) * sizeof(float4)));
+  LL_TRY(upload_points(h, h->fa_last[which], cloud, n, stride_bytes));
+  h->fa_n_last[which] = (int)n;
+  return LL_OK;
+}
+
+int ll_fa_find_correspondences(ll_handle h, int which, const void* queries, size_t nq, size_t stride_bytes,
+                               const float transform_cur[6], int iter_count, float nearest_feature_dist_sqr,
+                               int* ind1, int* ind2, int* ind3, float* coeff4, int* keep) {
+  if (!h) return LL_ERR_INVALID_ARG;
+  if (which != 0 && which != 1) return fail(h, LL_ERR_INVALID_ARG, "which must be 0 (corner) or 1 (surf)");
+  if (!transform_cur || iter_count < 0) return fail(h, LL_ERR_INVALID_ARG, "transform_cur is NULL / iter_count < 0");
+  if (nq && (!queries || !stride_ok(stride_bytes) || !ind1 || !ind2 || !coeff4 || !keep || (which == 1 && !ind3)))
+    return fail(h, LL_ERR_INVALID_ARG, "bad query cloud / stride / output arrays");
+  if (nq > 0x3fffffff) return fail(h, LL_ERR_INVALID_ARG, "too many queries");
+  if (nq == 0) return LL_OK;
+  if (!h->fa_last[which]) return fail(h, LL_ERR_STATE, "ll_fa_set_last has not been called for this cloud");
+  LL_CUDA(h, cudaSetDevice(h->device));
+  LL_TRY(ensure_tmp(h, 0, nq * 16));  // queries
+  LL_TRY(ensure_tmp(h, 1, nq * 16));  // coeff
+  LL_TRY(ensure_tmp(h, 2, nq * 4));   // keep
+  LL_TRY(ensure_tmp(h, 3, nq * 12));  // ind1 | ind2 | ind3
+  LL_TRY(upload_points(h, static_cast<float4*>(h->d_tmp[0]), queries, nq, stride_bytes));
+  int* d_ind = static_cast<int*>(h->d_tmp[3]);
+  const bool search = iter_count % 5 == 0;
+  if (!search) {  // the indices found at the last multiple of five come back in
+    LL_CUDA(h, cudaMemcpyAsync(d_ind, ind1, nq * 4, cudaMemcpyHostToDevice, h->stream));
+    LL_CUDA(h, cudaMemcpyAsync(d_ind + nq, ind2, nq * 4, cudaMemcpyHostToDevice, h->stream));
+    if (ind3) LL_CUDA(h, cudaMemcpyAsync(d_ind + 2 * nq, ind3, nq * 4, cudaMemcpyHostToDevice, h->stream));
+    else LL_CUDA(h, cudaMemsetAsync(d_ind + 2 * nq, 0xff, nq * 4, h->stream));
+  }
+  FaArgs A;
+  A.q = static_cast<const float4*>(h->d_tmp[0]);
+  A.last = h->fa_last[which];
+  A.nq = (int)nq;
+  A.n_last = h->fa_n_last[which];
+  for (int k = 0; k < 6; ++k) A.tc[k] = transform_cur[k];
+  A.which = which;
+  A.iter = iter_count;
+  A.dist_sqr = nearest_feature_dist_sqr;
+  A.ind1 = d_ind;
+  A.ind2 = d_ind + nq;
+  A.ind3 = d_ind + 2 * nq;
+  A.coeff = static_cast<float*>(h->d_tmp[1]);
+  A.keep = static_cast<int*>(h->d_tmp[2]);
+  const unsigned blocks = (unsigned)((nq + FA_THREADS / 32 - 1) / (FA_THREADS / 32));
+  fa_corr_kernel<<<blocks, FA_THREADS, 0, h->stream>>>(A);
+  LL_LAUNCHED(h);
+  if (search) {
+    LL_CUDA(h, cudaMemcpyAsync(ind1, d_ind, nq * 4, cudaMemcpyDeviceToHost, h->stream));
+    LL_CUDA(h, cudaMemcpyAsync(ind2, d_ind + nq, nq * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (ind3) LL_CUDA(h, cudaMemcpyAsync(ind3, d_ind + 2 * nq, nq * 4, cudaMemcpyDeviceToHost, h->stream));
+  }
+  LL_CUDA(h, cudaMemcpyAsync(coeff4, h->d_tmp[1], nq * 16, cudaMemcpyDeviceToHost, h->stream));
+  LL_CUDA(h, cudaMemcpyAsync(keep, h->d_tmp[2], nq * 4, cudaMemcpyDeviceToHost, h->stream));
+  LL_CUDA(h, cudaStreamSynchronize(h->stream));
   return LL_OK;
 }
 

@@ -899,4 +899,141 @@ void orc_replay_get_map(orc_replay* r, int which, orc_p4* out, int cap, int* n) 
   std::memcpy(out, v.data(), std::min<size_t>(cap, v.size()) * sizeof(orc_p4));
 }
 
+
+// ---- f-3: FeatureAssociation correspondence search ---------------------------------------------------------------
+// TransformToStart (featureAssociation.cpp:1389-1412). cos / sin are the unqualified C functions on float arguments:
+// taken as the double functions (repo-wide convention), so every product below is evaluated in double
+// and rounded to float on assignment.
+static orc_p4 fa_transform_to_start(const orc_p4& pi, const float* tc) {
+  const float s = 10 * (pi.i - (float)(int)pi.i);
+  const float rx = s * tc[0], ry = s * tc[1], rz = s * tc[2];
+  const float tx = s * tc[3], ty = s * tc[4], tz = s * tc[5];
+  const float x1 = (float)(std::cos((double)rz) * (double)(pi.x - tx) + std::sin((double)rz) * (double)(pi.y - ty));
+  const float y1 = (float)(-std::sin((double)rz) * (double)(pi.x - tx) + std::cos((double)rz) * (double)(pi.y - ty));
+  const float z1 = (pi.z - tz);
+  const float x2 = x1;
+  const float y2 = (float)(std::cos((double)rx) * (double)y1 + std::sin((double)rx) * (double)z1);
+  const float z2 = (float)(-std::sin((double)rx) * (double)y1 + std::cos((double)rx) * (double)z1);
+  orc_p4 po;
+  po.x = (float)(std::cos((double)ry) * (double)x2 - std::sin((double)ry) * (double)z2);
+  po.y = y2;
+  po.z = (float)(std::sin((double)ry) * (double)x2 + std::cos((double)ry) * (double)z2);
+  po.i = pi.i;
+  return po;
+}
+
+void orc_fa_transform_to_start(const orc_p4* in, int n, const float transform_cur[6], orc_p4* out) {
+  for (int i = 0; i < n; ++i) out[i] = fa_transform_to_start(in[i], transform_cur);
+}
+
+static inline float fa_sqdist(const orc_p4& a, const orc_p4& p) {
+  return (a.x - p.x) * (a.x - p.x) + (a.y - p.y) * (a.y - p.y) + (a.z - p.z) * (a.z - p.z);
+}
+
+void orc_fa_correspondences(int which, const orc_p4* q, int nq, const orc_p4* last, int n_last, const float transform_cur[6],
+                            int iter, float nearest_feature_dist_sqr, int* ind1, int* ind2, int* ind3, float* coeff,
+                            int* keep, int use_ext_knn) {
+  void* tree = nullptr;
+  if (use_ext_knn && g_ext_build && g_ext_knn5 && n_last >= 5) tree = g_ext_build(last, n_last);
+  for (int i = 0; i < nq; ++i) {
+    const orc_p4 sel = fa_transform_to_start(q[i], transform_cur);
+    keep[i] = 0;
+    coeff[4 * i] = coeff[4 * i + 1] = coeff[4 * i + 2] = coeff[4 * i + 3] = 0.f;
+    if (iter % 5 == 0) {  // :1588 / :1721
+      int closest = -1, min2 = -1, min3 = -1;
+      float best = FLT_MAX;
+      int besti = -1;
+      if (tree) {  // kdtree*Last.nearestKSearch(pointSel, 1, ...)
+        int idx5[5];
+        float d5[5];
+        const float v[3] = {sel.x, sel.y, sel.z};
+        g_ext_knn5(tree, v, idx5, d5);  // five nearest, ascending: the first is nearestKSearch(pointSel, 1)
+        besti = idx5[0];
+        best = d5[0];
+      } else {
+        for (int j = 0; j < n_last; ++j) {  // exact 1-NN, ties to the lowest index
+          float df = sel.x - last[j].x;
+          float d = df * df;
+          df = sel.y - last[j].y;
+          d += df * df;
+          df = sel.z - last[j].z;
+          d += df * df;
+          if (d < best) { best = d; besti = j; }
+        }
+      }
+      if (besti >= 0 && best < nearest_feature_dist_sqr) {
+        closest = besti;
+        const int scan = (int)last[closest].i;
+        float d2min = nearest_feature_dist_sqr, d3min = nearest_feature_dist_sqr;
+        // NB the reference bounds the forward scan by the QUERY count (:1599 / :1742), not by the size of the cloud
+        // it indexes; reproduced (and clamped to the cloud so that the restatement never reads out of bounds).
+        const int fwd_end = nq < n_last ? nq : n_last;
+        for (int j = closest + 1; j < fwd_end; ++j) {
+          if ((double)(int)last[j].i > (double)scan + 2.5) break;
+          const float d = fa_sqdist(last[j], sel);
+          if (which == 0) {
+            if ((int)last[j].i > scan && d < d2min) { d2min = d; min2 = j; }
+          } else if ((int)last[j].i <= scan) {
+            if (d < d2min) { d2min = d; min2 = j; }
+          } else if (d < d3min) {
+            d3min = d; min3 = j;
+          }
+        }
+        for (int j = closest - 1; j >= 0; --j) {
+          if ((double)(int)last[j].i < (double)scan - 2.5) break;
+          const float d = fa_sqdist(last[j], sel);
+          if (which == 0) {
+            if ((int)last[j].i < scan && d < d2min) { d2min = d; min2 = j; }
+          } else if ((int)last[j].i >= scan) {
+            if (d < d2min) { d2min = d; min2 = j; }
+          } else if (d < d3min) {
+            d3min = d; min3 = j;
+          }
+        }
+      }
+      ind1[i] = closest;
+      ind2[i] = min2;
+      if (ind3) ind3[i] = min3;
+    }
+    if (which == 0) {
+      if (ind2[i] < 0) continue;  // :1644
+      const orc_p4 t1 = last[ind1[i]], t2 = last[ind2[i]];
+      const float x0 = sel.x, y0 = sel.y, z0 = sel.z, x1 = t1.x, y1 = t1.y, z1 = t1.z, x2 = t2.x, y2 = t2.y, z2 = t2.z;
+      const float m11 = ((x0 - x1) * (y0 - y2) - (x0 - x2) * (y0 - y1));
+      const float m22 = ((x0 - x1) * (z0 - z2) - (x0 - x2) * (z0 - z1));
+      const float m33 = ((y0 - y1) * (z0 - z2) - (y0 - y2) * (z0 - z1));
+      const float a012 = (float)std::sqrt((double)(m11 * m11 + m22 * m22 + m33 * m33));
+      const float l12 = (float)std::sqrt((double)((x1 - x2) * (x1 - x2) + (y1 - y2) * (y1 - y2) + (z1 - z2) * (z1 - z2)));
+      const float la = ((y1 - y2) * m11 + (z1 - z2) * m22) / a012 / l12;
+      const float lb = -((x1 - x2) * m11 - (z1 - z2) * m33) / a012 / l12;
+      const float lc = -((x1 - x2) * m22 + (y1 - y2) * m33) / a012 / l12;
+      const float ld2 = a012 / l12;
+      float s = 1;
+      if (iter >= 5) s = (float)(1 - 1.8 * std::fabs((double)ld2));
+      if ((double)s > 0.1 && ld2 != 0) {
+        coeff[4 * i] = s * la; coeff[4 * i + 1] = s * lb; coeff[4 * i + 2] = s * lc; coeff[4 * i + 3] = s * ld2;
+        keep[i] = 1;
+      }
+    } else {
+      if (ind2[i] < 0 || ind3[i] < 0) continue;  // :1785
+      const orc_p4 t1 = last[ind1[i]], t2 = last[ind2[i]], t3 = last[ind3[i]];
+      float pa = (t2.y - t1.y) * (t3.z - t1.z) - (t3.y - t1.y) * (t2.z - t1.z);
+      float pb = (t2.z - t1.z) * (t3.x - t1.x) - (t3.z - t1.z) * (t2.x - t1.x);
+      float pc = (t2.x - t1.x) * (t3.y - t1.y) - (t3.x - t1.x) * (t2.y - t1.y);
+      float pd = -(pa * t1.x + pb * t1.y + pc * t1.z);
+      const float ps = (float)std::sqrt((double)(pa * pa + pb * pb + pc * pc));
+      pa /= ps; pb /= ps; pc /= ps; pd /= ps;
+      const float pd2 = pa * sel.x + pb * sel.y + pc * sel.z + pd;
+      float s = 1;
+      if (iter >= 5)
+        s = (float)(1 - 1.8 * std::fabs((double)pd2) / std::sqrt(std::sqrt((double)(sel.x * sel.x + sel.y * sel.y + sel.z * sel.z))));
+      if ((double)s > 0.1 && pd2 != 0) {
+        coeff[4 * i] = s * pa; coeff[4 * i + 1] = s * pb; coeff[4 * i + 2] = s * pc; coeff[4 * i + 3] = s * pd2;
+        keep[i] = 1;
+      }
+    }
+  }
+  if (tree && g_ext_free) g_ext_free(tree);
+}
+
 }  // extern "C"

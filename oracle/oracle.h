@@ -129,6 +129,18 @@ void orc_replay_get_map(orc_replay* r, int which, orc_p4* out, int cap, int* n);
  * with a column mask over [rx ry rz tx ty tz]; 3 or 6 unknowns. Returns 0, or -1 for other counts. */
 int orc_solve_normal_eq(const float* rows6, const float* b, int n, int dof_mask, int iter, float eig_thresh,
                         int eigen_mode, float* x_out, float* matP_inout, int* is_degenerate_inout);
+/* f-3: FeatureAssociation::findCorrespondingCornerFeatures / findCorrespondingSurfFeatures
+ * (featureAssociation.cpp:1580-1697, :1699-1844) with TransformToStart (:1389-1412) inside.
+ * which = 0 corner (two tripod points), 1 surf (three). q = cornerPointsSharp / surfPointsFlat, last =
+ * laserCloudCornerLast / laserCloudSurfLast (intensity = ring + column/10000). ind1/2/3 [nq] are
+ * pointSearch*Ind*: rewritten when iter % 5 == 0, read otherwise. coeff [nq][4] and keep [nq] describe the
+ * (laserCloudOri, coeffSel) pair each query would push_back (keep = 0: nothing pushed). knn_backend: 1-NN by
+ * brute force (ties: lowest index) or by the reference's nanoflann when the external backend is installed. */
+void orc_fa_correspondences(int which, const orc_p4* q, int nq, const orc_p4* last, int n_last, const float transform_cur[6],
+                            int iter, float nearest_feature_dist_sqr, int* ind1, int* ind2, int* ind3, float* coeff,
+                            int* keep, int use_ext_knn);
+void orc_fa_transform_to_start(const orc_p4* in, int n, const float transform_cur[6], orc_p4* out);
+
 void orc_test_self_adjoint_eig(const float* A, int n, float* evals, float* evecs);
 void orc_test_colpiv_qr_solve(const float* A, const float* b, int rows, int cols, float* x);
 void orc_test_inverse6(const float* A, float* inv);

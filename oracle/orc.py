@@ -289,3 +289,31 @@ class Replay:
             self.close()
         except Exception:
             pass
+
+
+def fa_correspondences(which, q, last, transform_cur, it, nearest_feature_dist_sqr=25.0, ind=None, use_nanoflann=False):
+    """f-3: FeatureAssociation::findCorrespondingCornerFeatures (which = 0) / SurfFeatures (which = 1).
+    ind = (ind1, ind2, ind3) from an earlier iteration (needed when it % 5 != 0). -> (ind1, ind2, ind3, coeff, keep)."""
+    q, last = _p4(q), _p4(last)
+    nq = len(q)
+    m = max(nq, 1)
+    if ind is None:
+        ind = [np.full(m, -1, np.int32) for _ in range(3)]
+    ind = [np.ascontiguousarray(a, np.int32).copy() for a in ind]
+    coeff = np.zeros((m, 4), np.float32)
+    keep = np.zeros(m, np.int32)
+    tc = np.ascontiguousarray(transform_cur, np.float32)
+    if use_nanoflann and not have_ref():
+        raise RuntimeError("oracle/_ref/libnanoflann_ref.so is not built")
+    lib().orc_fa_correspondences(C.c_int(which), _ptr(q), C.c_int(nq), _ptr(last), C.c_int(len(last)), _ptr(tc), C.c_int(it),
+                                 C.c_float(nearest_feature_dist_sqr), _ptr(ind[0]), _ptr(ind[1]), _ptr(ind[2]), _ptr(coeff),
+                                 _ptr(keep), C.c_int(1 if use_nanoflann else 0))
+    return ind[0][:nq], ind[1][:nq], ind[2][:nq], coeff[:nq], keep[:nq]
+
+
+def fa_transform_to_start(pts, transform_cur):
+    pts = _p4(pts)
+    out = np.empty_like(pts)
+    tc = np.ascontiguousarray(transform_cur, np.float32)
+    lib().orc_fa_transform_to_start(_ptr(pts), C.c_int(len(pts)), _ptr(tc), _ptr(out))
+    return out

@@ -527,6 +527,39 @@ def test_reference_recorded_maps(abi, orc):
     assert np.array_equal(idx[acc & g["tie_free"]], g["knn_idx"][acc & g["tie_free"]])
 
 
+# ------------------------------------------------------------------------------------------ f-3 FeatureAssociation search
+def test_fa_correspondences_parity(abi, orc, synth):
+    """findCorrespondingCornerFeatures / findCorrespondingSurfFeatures on the device vs the oracle restatement: indices,
+    keep flags and coefficient records bit for bit, over a search iteration, a reuse iteration and weighted iterations."""
+    from test_oracle import _fa_problem
+    for which in (0, 1):
+        q, last, tc = _fa_problem(synth, which)
+        with abi.Handle(abi.default_params()) as h:
+            h.fa_set_last(which, last)
+            ind_d = ind_o = None
+            for it in (0, 3, 5, 7, 10):
+                tci = (tc * np.float32(1.0 + 0.01 * it)).astype(np.float32)  # transformCur moves between iterations
+                gd = h.fa_find_correspondences(which, q, tci, it, 25.0, ind=ind_d)
+                go = orc.fa_correspondences(which, q, last, tci, it, 25.0, ind=ind_o)
+                for name, a, b in zip(("ind1", "ind2", "ind3", "coeff", "keep"), gd, go):
+                    if which == 0 and name == "ind3":
+                        continue
+                    assert np.array_equal(bits(a) if a.dtype == np.float32 else a, bits(b) if b.dtype == np.float32 else b), \
+                        (which, it, name)
+                ind_d, ind_o = gd[:3], go[:3]
+                if it < 5:  # (from iteration 5 on the weight 1 - 1.8 |d| drops most pairs of this unconverged guess)
+                    assert gd[4].sum() > len(q) // 4
+        # degenerate inputs: an empty / tiny previous cloud gives no correspondences and no error
+        with abi.Handle(abi.default_params()) as h:
+            h.fa_set_last(which, last[:0])
+            i1, i2, i3, coeff, keep = h.fa_find_correspondences(which, q, tc, 0)
+            assert (i1 == -1).all() and (keep == 0).all()
+            h.fa_set_last(which, last[:3])
+            g1 = h.fa_find_correspondences(which, q, tc, 0)
+            o1 = orc.fa_correspondences(which, q, last[:3], tc, 0)
+            assert np.array_equal(g1[0], o1[0]) and np.array_equal(g1[1], o1[1]) and np.array_equal(g1[4], o1[4])
+
+
 # ------------------------------------------------------------------------------------------ batched replay (config 5 shape)
 def test_batched_replay_is_independent_of_concurrency(abi, synth):
     """Several sequences in flight on one GPU (one handle + stream + host thread each) give bit-identical poses to

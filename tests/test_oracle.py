@@ -284,3 +284,55 @@ def test_reference_recorded_maps_knn(orc):
     # VoxelGrid on real data: idempotent membership, every output inside its voxel
     out, member, flag = orc.voxel_downsample(g["surf_map"], 0.4)
     assert flag == 0 and member.max() == len(out) - 1 and (np.bincount(member) > 0).all()
+
+
+def _fa_problem(synth, which, seed=3):
+    """Two consecutive synthetic sweeps as FeatureAssociation sees them: last = the previous sweep's feature cloud in
+    extraction order (by scan line; intensity = ring + column / 10000), queries = a subset of the next sweep's."""
+    d = synth.make_sequence(seed=seed, n_scans=3, step=0.7, world_kw=dict(n_blocks=8, n_poles=50, half_x=25, half_z=35))
+    key = "corner_scan" if which == 0 else "surf_last_ds"
+    last = np.ascontiguousarray(d["frames"][1][key], np.float32)
+    last = last[np.argsort(last[:, 3].astype(np.int32), kind="stable")]
+    cur = np.ascontiguousarray(d["frames"][2][key], np.float32)
+    q = cur[::5 if which == 0 else 9].copy()
+    tc = np.array([0.004, -0.006, 0.003, 0.05, -0.02, 0.30], np.float32)  # transformCur: a plausible sweep-to-sweep motion
+    return q, last, tc
+
+
+def test_fa_correspondences_oracle(orc, synth):
+    """f-3 restatement: 1-NN by brute force == the reference's nanoflann; structural properties of the ring-window search
+    (featureAssociation.cpp:1593-1640, :1734-1779); index reuse between multiples of five; weights."""
+    for which in (0, 1):
+        q, last, tc = _fa_problem(synth, which)
+        i1, i2, i3, coeff, keep = orc.fa_correspondences(which, q, last, tc, 0)
+        assert keep.sum() > len(q) // 4, (which, keep.sum(), len(q))
+        if orc.have_ref():
+            n1, n2, n3, ncoeff, nkeep = orc.fa_correspondences(which, q, last, tc, 0, use_nanoflann=True)
+            assert np.array_equal(i1, n1) and np.array_equal(i2, n2) and np.array_equal(i3, n3)
+            assert np.array_equal(coeff.view(np.uint32), ncoeff.view(np.uint32)) and np.array_equal(keep, nkeep)
+        sel = orc.fa_transform_to_start(q, tc)
+        ring = last[:, 3].astype(np.int32)
+        ok = i1 >= 0
+        d1 = ((last[i1[ok], :3] - sel[ok, :3]) ** 2).sum(1)
+        assert (d1 < 25.0).all()
+        brute = ((last[None, :, :3].astype(np.float64) - sel[ok, None, :3]) ** 2).sum(2).min(1)
+        assert np.allclose(d1, brute, rtol=1e-5, atol=1e-6)
+        has2 = i2 >= 0
+        assert (np.abs(ring[i2[has2]] - ring[i1[has2]]) <= 2).all()
+        if which == 0:
+            assert (ring[i2[has2]] != ring[i1[has2]]).all()       # the second line point lies on ANOTHER scan line
+            assert (i3 == -1).all()
+        else:
+            has3 = i3 >= 0
+            assert (ring[i3[has3]] != ring[i1[has3]]).all()       # the third plane point lies on another scan line
+        assert (keep[~has2] == 0).all()
+        k = keep == 1
+        assert np.allclose(np.linalg.norm(coeff[k, :3], axis=1), 1.0, atol=1e-5)   # iter < 5: s = 1
+        # iterations 1..4 reuse the indices of iteration 0; from iteration 5 on the weight s = 1 - 1.8 |d| applies
+        j1, j2, j3, c3, k3 = orc.fa_correspondences(which, q, last, tc, 3, ind=(i1, i2, i3))
+        assert np.array_equal(j1, i1) and np.array_equal(j2, i2) and np.array_equal(c3.view(np.uint32), coeff.view(np.uint32))
+        _, _, _, c5, k5 = orc.fa_correspondences(which, q, last, tc, 5)
+        kk = (k5 == 1)
+        assert (np.linalg.norm(c5[kk, :3], axis=1) <= 1.0 + 1e-6).all() and (np.linalg.norm(c5[kk, :3], axis=1) > 0.1).all()
+        # with transformCur = 0 TransformToStart is the identity
+        assert np.array_equal(orc.fa_transform_to_start(q, np.zeros(6, np.float32))[:, :3].view(np.uint32), q[:, :3].view(np.uint32))
