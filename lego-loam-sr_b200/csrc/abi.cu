@@ -102,6 +102,9 @@ struct ll_handle_s {
   Segment* d_segs = nullptr;
   BlockJob* d_jobs = nullptr;
   size_t segs_cap = 0, jobs_cap = 0;
+  Segment* d_segs_aux = nullptr;  // segment table of a problem run while a local map is pending (run_map_pipeline)
+  BlockJob* d_jobs_aux = nullptr;
+  size_t segs_aux_cap = 0, jobs_aux_cap = 0;
   uint8_t* seg_host = nullptr;  // pinned staging of the segment table uploaded last (stage_seglist)
   size_t seg_bytes = 0, job_bytes = 0;
   int seg_slot = 0;
@@ -474,7 +477,24 @@ int run_map_pipeline(ll_handle h, int sa, int sb, const SegList& L, float leaf_a
   if (h->map_deferred || h->grid_deferred) {
     if (sa == h->grid_cfg.sa && sb == h->grid_cfg.sb) {  // a new local map replaces the one that was never built
       h->map_deferred = h->grid_deferred = false;
-    } else {  // another problem (ll_voxel_downsample) shares the segment table: finish the pending map first
+    } else if (!h->seg_staged) {
+      // Another problem (ll_voxel_downsample of downsampleCurrentScan, between extractSurroundingKeyFrames and
+      // scan2MapOptimization): run it with its own segment buffers and leave the pending map exactly as it is.
+      const auto cfg = h->grid_cfg;
+      const int n_jobs = h->n_jobs;
+      const bool md = h->map_deferred, gd = h->grid_deferred;
+      std::swap(h->d_segs, h->d_segs_aux); std::swap(h->segs_cap, h->segs_aux_cap);
+      std::swap(h->d_jobs, h->d_jobs_aux); std::swap(h->jobs_cap, h->jobs_aux_cap);
+      h->map_deferred = h->grid_deferred = false;
+      const int rc = run_map_pipeline(h, sa, sb, L, leaf_a, leaf_b, ds_a, ds_b, build_grid, want_member);
+      std::swap(h->d_segs, h->d_segs_aux); std::swap(h->segs_cap, h->segs_aux_cap);
+      std::swap(h->d_jobs, h->d_jobs_aux); std::swap(h->jobs_cap, h->jobs_aux_cap);
+      h->grid_cfg = cfg;
+      h->n_jobs = n_jobs;
+      h->map_deferred = md;
+      h->grid_deferred = gd;
+      return rc;
+    } else {  // (zero-copy staging in use) finish the pending map first
       LL_TRY(ensure_map(h));
       LL_TRY(ensure_grid(h));
     }
@@ -897,7 +917,7 @@ int ll_destroy(ll_handle h) {
     for (void* p : ptrs)
       if (p) cudaFree(p);
   }
-  void* ptrs[] = {h->d_segs, h->d_jobs, h->dq[0], h->dq[1], h->d_state, h->d_partials, h->d_barriers, h->fa_last[0], h->fa_last[1],
+  void* ptrs[] = {h->d_segs, h->d_jobs, h->d_segs_aux, h->d_jobs_aux, h->dq[0], h->dq[1], h->d_state, h->d_partials, h->d_barriers, h->fa_last[0], h->fa_last[1],
                   h->d_tmp[0], h->d_tmp[1], h->d_tmp[2], h->d_tmp[3], h->d_tmp[4], h->d_tmp[5]};
   for (void* p : ptrs)
     if (p) cudaFree(p);
