@@ -150,16 +150,19 @@ struct VoxelMeta {
   bool empty;
 };
 
+// kCoherent: read the box through L2 (__ldcg) — needed in the single-kernel scan (map_inline.cuh), where it is produced
+// by atomics of the same launch; the stand-alone kernels read it through L1 like any other input.
+template <bool kCoherent = false>
 __device__ __forceinline__ VoxelMeta voxel_meta(const MapState* st, float inv) {
   VoxelMeta v;
-  // __ldcg: in the single-kernel scan (map_inline.cuh) the box is produced by atomics of the same launch
-  const uint32_t e0 = __ldcg(&st->mm[0]);
+  auto ld = [](const uint32_t* p) { return kCoherent ? __ldcg(p) : *p; };
+  const uint32_t e0 = ld(&st->mm[0]);
   v.empty = (e0 == 0u);  // no finite point seen
   float mn[3], mx[3];
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
-    mn[a] = ordered_to_float(~__ldcg(&st->mm[a]));
-    mx[a] = ordered_to_float(__ldcg(&st->mm[3 + a]));
+    mn[a] = ordered_to_float(~ld(&st->mm[a]));
+    mx[a] = ordered_to_float(ld(&st->mm[3 + a]));
   }
   if (v.empty) {
 #pragma unroll

@@ -316,7 +316,7 @@ __device__ __forceinline__ void gi_voxel(const MapBatch& B, unsigned* barrier, u
   for (int m = 0; m < 2; ++m) {
     const MapBuffers& M = B.m[m];
     n[m] = M.downsample ? M.n_raw : 0;  // a map that is not downsampled does not take part (ds aliases raw)
-    vm[m] = voxel_meta(M.st, M.inv_leaf);
+    vm[m] = voxel_meta<true>(M.st, M.inv_leaf);
     sentinel[m] = vm[m].overflow ? (uint32_t)M.n_raw : (uint32_t)vm[m].total;
     bits[m] = sentinel[m] == 0 ? 0 : 32 - __clz(sentinel[m]);
     if (blockIdx.x == 0 && tid == 0 && M.downsample) {
