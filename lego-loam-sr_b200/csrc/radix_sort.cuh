@@ -69,7 +69,9 @@ __global__ void __launch_bounds__(RS_THREADS) rs_onesweep_kernel(const __grid_co
 
   __shared__ uint32_t warp_hist[RS_WARPS][RS_RADIX];
   __shared__ uint32_t digit_base[RS_RADIX];
-  __shared__ uint32_t scan_buf[RS_RADIX];
+  __shared__ uint32_t scan_buf[2 * RS_WARPS];
+  __shared__ uint32_t tile_first[RS_RADIX];
+  __shared__ uint32_t stage_keys[RS_TILE], stage_vals[RS_TILE];
   __shared__ int s_tile;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -163,28 +165,50 @@ __global__ void __launch_bounds__(RS_THREADS) rs_onesweep_kernel(const __grid_co
     }
     status[(size_t)tile * kTileStride + tid] = (excl + tile_count) | RS_FLAG_PREFIX;
   }
-  // Exclusive prefix of the global digit histogram (256 values, Hillis-Steele in shared memory).
+  // Exclusive prefixes over the 256 digits of (a) the global digit histogram and (b) this tile's digit counts:
+  // warp-shuffle scans of the eight 32-digit groups + one pass over the eight group totals.
   const uint32_t g = P.ghist[pass * RS_RADIX + tid];
-  scan_buf[tid] = g;
-  __syncthreads();
+  uint32_t gi = g, ti = tile_count;
 #pragma unroll
-  for (int off = 1; off < RS_RADIX; off <<= 1) {
-    uint32_t v = (tid >= off) ? scan_buf[tid - off] : 0u;
-    __syncthreads();
-    scan_buf[tid] += v;
-    __syncthreads();
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t ug = __shfl_up_sync(0xffffffffu, gi, o), ut = __shfl_up_sync(0xffffffffu, ti, o);
+    if (lane >= o) { gi += ug; ti += ut; }
   }
-  digit_base[tid] = scan_buf[tid] - g + excl;
+  if (lane == 31) { scan_buf[warp] = gi; scan_buf[RS_WARPS + warp] = ti; }
+  __syncthreads();
+  uint32_t goff = 0, toff = 0;
+#pragma unroll
+  for (int w = 0; w < RS_WARPS; ++w) {
+    goff += w < warp ? scan_buf[w] : 0u;
+    toff += w < warp ? scan_buf[RS_WARPS + w] : 0u;
+  }
+  const uint32_t tile_excl = toff + ti - tile_count;   // items of this tile with a smaller digit
+  digit_base[tid] = goff + gi - g + excl - tile_excl;   // global position of tile-local position 0 ... shifted per digit:
+  tile_first[tid] = tile_excl;                          // item at tile-local position j with digit d goes to digit_base[d] + j
   __syncthreads();
 
+  // Stage the tile in digit order in shared memory, then write it out with consecutive threads on consecutive tile-local
+  // positions: runs of equal digits become contiguous global stores (full sectors instead of 4-byte scatters).
 #pragma unroll
   for (int k = 0; k < RS_ITEMS; ++k) {
     const bool valid = (warp_base + k * 32 + lane) < n;
     if (valid) {
       const uint32_t d = (key[k] >> shift) & 255u;
-      const uint32_t pos = digit_base[d] + warp_hist[warp][d] + rank[k];
-      keys_out[pos] = key[k];
-      vals_out[pos] = val[k];
+      const uint32_t lpos = tile_first[d] + warp_hist[warp][d] + rank[k];
+      stage_keys[lpos] = key[k];
+      stage_vals[lpos] = val[k];
+    }
+  }
+  __syncthreads();
+  const int tile_n = (int)min((long long)RS_TILE, (long long)n - tile_base);
+#pragma unroll
+  for (int k = 0; k < RS_ITEMS; ++k) {
+    const int j = k * RS_THREADS + tid;
+    if (j < tile_n) {
+      const uint32_t kk = stage_keys[j];
+      const uint32_t pos = digit_base[(kk >> shift) & 255u] + (uint32_t)j;
+      keys_out[pos] = kk;
+      vals_out[pos] = stage_vals[j];
     }
   }
 }
