@@ -1242,13 +1242,14 @@ __global__ void __launch_bounds__(LM_THREADS, 1) lm_persistent_kernel(const __gr
                 "the inline map build borrows the staging slots");
   // a4: the search grids of the local map, when ll_build_local_map left them to this launch (grid_inline.cuh)
   // a1-a3: the local map itself, when ll_build_local_map only prepared it (map_inline.cuh)
+  bool cells_cleared = false;
   if (build_map) {
     if (blockIdx.x == 0 && tid < 128)  // MapState of both maps (bounding box, counts): zero before the build
       reinterpret_cast<uint32_t*>(GB.m[tid >> 6].st)[tid & 63] = 0u;
     coop_barrier(barrier, epoch);
-    map_build_inline(GB, segs, jobs, n_jobs, barrier, epoch, reinterpret_cast<uint32_t*>(s_slot));
+    cells_cleared = map_build_inline(GB, segs, jobs, n_jobs, barrier, epoch, reinterpret_cast<uint32_t*>(s_slot));
   }
-  if (build_grid) grid_build_inline(GB, barrier, epoch, reinterpret_cast<uint32_t*>(s_slot));
+  if (build_grid) grid_build_inline(GB, barrier, epoch, reinterpret_cast<uint32_t*>(s_slot), cells_cleared);
   __syncthreads();
   if (tid == 0) {
     const float pose6[6] = {p0, p1, p2, p3, p4, p5};

@@ -32,7 +32,8 @@ constexpr int GI_TILE = GI_THREADS * 4;          // host-side unit for the capac
 constexpr int GI_DIGIT_BITS = 9;                 // 512 bins = one per thread: a 26-bit voxel key takes 3 passes, not 4
 constexpr int GI_RADIX = 1 << GI_DIGIT_BITS;
 constexpr int GI_SMEM_WORDS = GI_WARPS * GI_RADIX + GI_RADIX + 16;
-constexpr int GI_SMEM_WORDS_REDUCE = 4 * 2 * GI_THREADS + 2 * GI_THREADS + 8 + 64 + 8;  // inline voxel reduce (gi_voxel)
+constexpr int GI_REDUCE_ITEMS = 4;               // pairs per thread and sub-tile of the inline voxel reduce (2048-pair sub-tiles)
+constexpr int GI_SMEM_WORDS_REDUCE = 5 * GI_REDUCE_ITEMS * GI_THREADS + 8 + 64 + 8;
 
 struct GridDims {
   int o[3], d[3];
@@ -405,11 +406,12 @@ __device__ __forceinline__ void gi_voxel(const MapBatch& B, unsigned* barrier, u
 #pragma unroll
   for (int w = 0; w < GI_WARPS; ++w) { before += s_w[w]; total += s_w[GI_WARPS + w]; }
   if (J.tile == 0 && tid == 0) M.st->n_ds = (int)total;
-  // Sub-tiles of 1024 sorted pairs, as voxel_reduce_kernel: the points are gathered into shared memory by all
+  // Sub-tiles of 2048 sorted pairs, organised as voxel_reduce_kernel: the points are gathered into shared memory by all
   // threads (independent loads), then every head's thread adds its own segment up IN SORTED ORDER (= ascending
   // original index, the canonical order) from shared memory; a segment that runs past the sub-tile is finished by
   // the whole block, 512 pairs at a time.
-  constexpr int SUB = 2 * GI_THREADS;  // thread t owns the consecutive pairs 2t, 2t+1 of the sub-tile
+  constexpr int R = GI_REDUCE_ITEMS;   // thread t owns the consecutive pairs R t .. R t + R - 1 of the sub-tile
+  constexpr int SUB = R * GI_THREADS;
   float4* s_pts = reinterpret_cast<float4*>(smem);                       // [SUB]
   int* s_head_pos = reinterpret_cast<int*>(smem + 4 * SUB);              // [SUB + 1]
   uint32_t* s_wsum = smem + 4 * SUB + SUB + 8;                           // [GI_WARPS]
@@ -424,22 +426,22 @@ __device__ __forceinline__ void gi_voxel(const MapBatch& B, unsigned* barrier, u
     __syncthreads();  // (shared memory of the previous sub-tile / of the head count is reused)
     if (tid == 0) { s_misc[0] = SUB; s_misc[1] = 0; }  // [0] first sentinel-keyed pair, [1] a segment crosses the end
     __syncthreads();
-    const int l0 = 2 * tid, i0 = base + l0;
-    uint32_t k2[2], v2[2];
-    bool head[2];
+    const int l0 = R * tid, i0 = base + l0;
+    uint32_t k2[R], v2[R];
+    bool head[R];
     uint32_t prev = (i0 > 0 && l0 < sub_n) ? __ldcg(keys + i0 - 1) : 0xffffffffu;
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
+    for (int k = 0; k < R; ++k) {
       const bool in = l0 + k < sub_n;
       k2[k] = in ? __ldcg(keys + i0 + k) : 0xffffffffu;
       v2[k] = in ? __ldcg(vals + i0 + k) : 0u;
     }
 #pragma unroll
-    for (int k = 0; k < 2; ++k)
+    for (int k = 0; k < R; ++k)
       s_pts[l0 + k] = l0 + k < sub_n ? __ldcg(&M.raw[v2[k]]) : make_float4(0.f, 0.f, 0.f, 0.f);
     uint32_t cnt = 0;
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
+    for (int k = 0; k < R; ++k) {
       const bool in = l0 + k < sub_n;
       const bool boundary = in && (i0 + k == 0 || k2[k] != prev);
       head[k] = boundary && k2[k] != sent;
@@ -466,7 +468,7 @@ __device__ __forceinline__ void gi_voxel(const MapBatch& B, unsigned* barrier, u
     {
       uint32_t ls = local0;
 #pragma unroll
-      for (int k = 0; k < 2; ++k)
+      for (int k = 0; k < R; ++k)
         if (head[k]) s_head_pos[ls++] = l0 + k;
     }
     if (tid == 0) s_head_pos[sub_total] = sub_n;
@@ -474,7 +476,7 @@ __device__ __forceinline__ void gi_voxel(const MapBatch& B, unsigned* barrier, u
     const int sent_pos = s_misc[0];
     uint32_t ls = local0;
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
+    for (int k = 0; k < R; ++k) {
       if (!head[k]) continue;
       const int beg = l0 + k;
       const int end = min(s_head_pos[ls + 1], sent_pos);  // sentinel-keyed pairs only ever trail the last head
@@ -546,21 +548,38 @@ __device__ __forceinline__ void gi_voxel(const MapBatch& B, unsigned* barrier, u
 
 // Rows a1-a3 for the two maps of B: raw clouds (transformed, concatenated), VoxelGrid. Every thread of every block of
 // the co-resident grid must call; returns with a grid barrier passed.
-__device__ __forceinline__ void map_build_inline(const MapBatch& B, const Segment* segs, const BlockJob* jobs, int njobs,
+// Returns true when the cell tables of the search grids were cleared on the side (see below).
+__device__ __forceinline__ bool map_build_inline(const MapBatch& B, const Segment* segs, const BlockJob* jobs, int njobs,
                                                  unsigned* barrier, unsigned& epoch, uint32_t* smem) {
   gi_transform(B, segs, jobs, njobs, smem);
   coop_barrier(barrier, epoch);
   const int n0 = B.m[0].downsample ? B.m[0].n_raw : 0, n1 = B.m[1].downsample ? B.m[1].n_raw : 0;
   const int items = gi_items(n0, n1, (int)gridDim.x);  // > 0: the host bounds the raw size
+  // The VoxelGrid sort keeps one tile per block; blocks WITHOUT a tile (47 of 148 for a VLP-16 window) would only wait
+  // at its barriers, so they clear the cell tables of the search grids meanwhile (the geometry only needs the box).
+  const int t_ = GI_THREADS * (items > 0 ? items : GI_MAX_ITEMS);
+  const int tiles = (n0 + t_ - 1) / t_ + (n1 + t_ - 1) / t_;
+  const bool side_clear = tiles < (int)gridDim.x;  // grid-uniform
+  if (side_clear && (int)blockIdx.x >= tiles) {
+    const int idle = (int)gridDim.x - tiles, me = (int)blockIdx.x - tiles;
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+      const GridDims g = grid_dims(B.m[m].st, B.m[m].cell_cap);
+      for (int c = me * GI_THREADS + (int)threadIdx.x; c < g.ncells; c += idle * GI_THREADS)
+        B.m[m].cells[c] = make_int2(0x7fffffff, 0);
+    }
+  }
   if (items == 4) gi_voxel<4>(B, barrier, epoch, smem);
   else if (items == 8) gi_voxel<8>(B, barrier, epoch, smem);
   else if (items == 16) gi_voxel<16>(B, barrier, epoch, smem);
   coop_barrier(barrier, epoch);
+  return side_clear;
 }
 
 // Builds `sorted` and `cells` of the two maps of B. Every thread of every block of the co-resident grid must call.
 // smem: GI_SMEM_WORDS uint32. Returns with a grid barrier passed (results visible to every block).
-__device__ __forceinline__ void grid_build_inline(const MapBatch& B, unsigned* barrier, unsigned& epoch, uint32_t* smem) {
+__device__ __forceinline__ void grid_build_inline(const MapBatch& B, unsigned* barrier, unsigned& epoch, uint32_t* smem,
+                                                  bool cells_cleared = false) {
   const int gtid = blockIdx.x * GI_THREADS + threadIdx.x, gthreads = gridDim.x * GI_THREADS;
   GridDims gd[2];
   int n[2];
@@ -587,7 +606,8 @@ __device__ __forceinline__ void grid_build_inline(const MapBatch& B, unsigned* b
       st->grid_too_large = g.too_large ? 1 : 0;
       st->grid_bits = g.bits;
     }
-    for (int c = gtid; c < g.ncells; c += gthreads) M.cells[c] = make_int2(0x7fffffff, 0);
+    if (!cells_cleared)
+      for (int c = gtid; c < g.ncells; c += gthreads) M.cells[c] = make_int2(0x7fffffff, 0);
   }
   if (gd[0].bits == 0 || gd[1].bits == 0)  // (warp-, block- and grid-uniform)
     coop_barrier(barrier, epoch);  // a single-cell map writes its cell entry without an intervening pass barrier

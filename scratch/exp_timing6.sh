@@ -11,9 +11,9 @@ s=open(p).read()
 a="__device__ __forceinline__ void coop_barrier(unsigned* counter, unsigned& epoch) {\n  ++epoch;\n"
 assert s.count(a)==1
 s=s.replace(a, "__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile(\"mov.u64 %0, %globaltimer;\" : \"=l\"(t)); return t; }\n__device__ unsigned long long g_arr[48][160];\n__device__ unsigned long long g_rel[48];\n"+a+"  if (threadIdx.x == 0 && epoch < 48) g_arr[epoch][blockIdx.x] = gtime();\n")
-a="    while (ld_acquire_u32(counter) < target) {}\n  }\n  __syncthreads();\n"
+a="  }\n  __syncthreads();\n}\n\n// Streaming"
 assert s.count(a)==1
-s=s.replace(a, a+"  if (threadIdx.x == 0 && blockIdx.x == 0 && epoch < 48) g_rel[epoch] = gtime();\n")
+s=s.replace(a, "  }\n  __syncthreads();\n  if (threadIdx.x == 0 && blockIdx.x == 0 && epoch < 48) g_rel[epoch] = gtime();\n}\n\n// Streaming")
 open(p,'w').write(s)
 p='scratch/var/timing/csrc/lm.cuh'
 s=open(p).read()
