@@ -440,8 +440,12 @@ def main():
         print(json.dumps(line))
         return
 
+    # Keep NCCL's own output (the "NCCL version ..." banner is printed at every debug level from VERSION up, to stdout)
+    # off stdout: the driver reads ONE JSON line there.
+    # (NCCL honours NCCL_DEBUG_FILE only above the VERSION level, so VERSION is raised to WARN.)
     if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"  # keep "NCCL version ..." off stdout: the driver reads ONE JSON line
+        os.environ["NCCL_DEBUG"] = "WARN"
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     import torch
     import torch.distributed as dist
     if not torch.cuda.is_available():
