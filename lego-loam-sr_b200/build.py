@@ -45,7 +45,7 @@ def build_abi(force=False, verbose=False):
     os.makedirs(LIB_DIR, exist_ok=True)
     cus = [s for s in srcs if s.endswith(".cu")]
     cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", ABI_LIB] + cus
-    subprocess.check_call(cmd)
+    subprocess.check_call(cmd, stdout=sys.stderr)  # (bench.py prints exactly one line on stdout)
     return ABI_LIB
 
 
@@ -60,7 +60,7 @@ def build_host(force=False):
     cxx = os.environ.get("CXX") or shutil.which("g++") or "g++"
     cmd = [cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-I", os.path.join(ROOT, "include"), "-o", HOST_LIB] + cpps + \
           ["-L", LIB_DIR, "-llegoloam_b200", "-Wl,-rpath,$ORIGIN"]
-    subprocess.check_call(cmd)
+    subprocess.check_call(cmd, stdout=sys.stderr)  # (bench.py prints exactly one line on stdout)
     return HOST_LIB
 
 
