@@ -350,6 +350,14 @@ def test_single_kernel_scan_equals_stand_alone_kernels(abi, orc, single_problem,
                    (rb.status, rb.iter_num, rb.sel_num, rb.flags, rb.corner_map_ds, rb.surf_map_ds, rb.is_degenerate), name
             assert bits(np.float32(ra.min_lambda)) == bits(np.float32(rb.min_lambda)) and \
                    bits(np.float32(ra.cf_mean)) == bits(np.float32(rb.cf_mean)), name
+    # mixed path: asking for the map before the scan builds it with the stand-alone kernels; the scan kernel then only
+    # builds the search grids itself
+    with abi.Handle(upstream_params(abi)) as h:
+        h.set_local_map_raw(raw_c, raw_s)
+        c_first = h.get_map_ds(0)
+        p_mixed, r_mixed = h.scan2map(cq, sq, prior)
+    (p1, r1, _, _, c1, _), _ = _scan_both_ways(abi, raw_c, raw_s, cq, sq, prior)
+    assert np.array_equal(bits(c_first), bits(c1)) and np.array_equal(bits(p_mixed), bits(p1)) and r_mixed.sel_num == r1.sel_num
     # and against the oracle for the ordinary case
     prm = upstream_params(orc)
     ocd = orc.voxel_downsample(raw_c, prm.corner_leaf)[0]
