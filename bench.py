@@ -491,12 +491,12 @@ def main():
             dist.barrier()
 
     sampler = ClockSampler(device)
-    # ---- e2e leg: host clouds through the C++ mirror
+    # ---- e2e leg: host clouds through the C++ mirror (SM clocks / throttle reasons are sampled over both timed legs)
     sync_all()
+    sampler.start()
     e2e = run_gpu(data, device, prefill, args.warmup, args.steps, resident=False, flush=flush)
     # ---- value leg: inputs resident in HBM
     sync_all()
-    sampler.start()
     res = run_gpu(data, device, prefill, args.warmup, args.steps, resident=True, flush=flush)
     sync_all()
     clocks = sampler.stop()
