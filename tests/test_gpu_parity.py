@@ -366,6 +366,39 @@ def test_single_kernel_scan_equals_stand_alone_kernels(abi, orc, single_problem,
     assert np.array_equal(bits(c1), bits(ocd)) and np.array_equal(bits(s1), bits(osd))
 
 
+def test_call_sequences_around_a_pending_map(abi, orc, single_problem):
+    """ll_build_local_map only PREPARES the map when persistent_lm = 1; whatever is called between it and ll_scan2map must
+    neither disturb it nor see a half-built map."""
+    d = single_problem
+    kf = d["keyframes"]
+    raw_c = np.concatenate([f["corner_scan"] for f in kf[:6]]).astype(np.float32)
+    raw_s = np.concatenate([np.concatenate([f["surf_last_ds"], f["outlier_last_ds"]]) for f in kf[:6]]).astype(np.float32)
+    cq, sq, prior = d["query"]["corner_scan_ds"], d["query"]["surf_total_ds"], np.zeros(6, np.float32)
+    with abi.Handle(upstream_params(abi)) as h:
+        h.set_local_map_raw(raw_c, raw_s)
+        ref_pose, ref_res = h.scan2map(cq, sq, prior)
+        ref_c = h.get_map_ds(0)
+    o_small = orc.voxel_downsample(raw_s[:5000], 0.4)[0]
+    with abi.Handle(upstream_params(abi)) as h:
+        h.set_local_map_raw(raw_s[:100], raw_c[:100])      # a map that is never used ...
+        h.set_local_map_raw(raw_c, raw_s)                  # ... is replaced by the next one
+        out, _, _ = h.voxel_downsample(raw_s[:5000], 0.4)  # downsampleCurrentScan in between: own buffers
+        assert np.array_equal(bits(out), bits(o_small))
+        near = raw_s[::max(1, len(raw_s) // 64)][:64].copy()  # queries next to map points
+        near[:, :3] += np.float32(0.01)
+        idx, d2, acc = h.knn5(1, near)                      # a stage-level call builds map + grids the stand-alone way
+        assert acc.sum() > 32
+        pose, res = h.scan2map(cq, sq, prior)
+        assert np.array_equal(bits(pose), bits(ref_pose)) and res.sel_num == ref_res.sel_num
+        h.set_local_map_raw(raw_c, raw_s)
+        out, _, _ = h.voxel_downsample(raw_s[:5000], 0.4)
+        pose, res = h.scan2map(cq, sq, prior)              # pending map + aux problem in between: single-kernel path
+        assert np.array_equal(bits(out), bits(o_small))
+        assert np.array_equal(bits(pose), bits(ref_pose)) and np.array_equal(bits(h.get_map_ds(0)), bits(ref_c))
+        pose0, res0 = h.scan2map(cq[:0], sq[:0], prior)     # no queries: nothing to optimise, pose unchanged
+        assert res0.sel_num == 0 and np.array_equal(bits(pose0), bits(prior))
+
+
 def test_scan2map_early_exit_and_thresholds(abi, orc, single_problem, single_maps):
     d = single_problem
     for kw in (dict(stop_thres=0.05, iter_count_thres=30), dict(stop_thres=0.05, iter_count_thres=200),
