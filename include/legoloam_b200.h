@@ -123,6 +123,8 @@ int ll_add_keyframe_dev(ll_handle h, int id, const void* d_corner, size_t n_corn
  * ignored). Without it ll_add_keyframe uploads as before. */
 int ll_prefetch_keyframe(ll_handle h, int id, const void* corner, size_t n_corner, const void* surf, size_t n_surf,
                          const void* outlier, size_t n_outlier, size_t stride_bytes);
+int ll_prefetch_keyframe_dev(ll_handle h, int id, const void* d_corner, size_t n_corner, const void* d_surf, size_t n_surf,
+                             const void* d_outlier, size_t n_outlier);
 /* correctPoses (mapOptmization.cpp:1757-1785) */
 int ll_set_keyframe_pose(ll_handle h, int id, const float pose6[6]);
 

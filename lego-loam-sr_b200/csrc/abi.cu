@@ -982,7 +982,7 @@ static int add_keyframe_impl(ll_handle h, int id, const void* c[3], const size_t
   for (int k = 0; k < 3; ++k)
     if (n[k] && !c[k]) return fail(h, LL_ERR_INVALID_ARG, "NULL cloud with non-zero count");
   LL_CUDA(h, cudaSetDevice(h->device));
-  if (!dev && id == h->prefetched_id) {  // the clouds are already on their way (ll_prefetch_keyframe): attach the pose
+  if (id == h->prefetched_id) {  // the clouds are already on their way (ll_prefetch_keyframe): attach the pose
     Keyframe kf = h->prefetched_kf;
     std::memcpy(kf.pose, pose6, sizeof(kf.pose));
     h->prefetched_id = -1;
@@ -1039,6 +1039,17 @@ int ll_prefetch_keyframe(ll_handle h, int id, const void* corner, size_t n_corne
     if (n[k] && !c[k]) return fail(h, LL_ERR_INVALID_ARG, "NULL cloud with non-zero count");
   LL_CUDA(h, cudaSetDevice(h->device));
   return store_keyframe_clouds(h, id, Keyframe(), c, n, stride_bytes, false, h->copy_stream);
+}
+
+int ll_prefetch_keyframe_dev(ll_handle h, int id, const void* d_corner, size_t n_corner, const void* d_surf, size_t n_surf,
+                             const void* d_outlier, size_t n_outlier) {
+  if (!h) return LL_ERR_INVALID_ARG;
+  const void* c[3] = {d_corner, d_surf, d_outlier};
+  const size_t n[3] = {n_corner, n_surf, n_outlier};
+  for (int k = 0; k < 3; ++k)
+    if (n[k] && !c[k]) return fail(h, LL_ERR_INVALID_ARG, "NULL cloud with non-zero count");
+  LL_CUDA(h, cudaSetDevice(h->device));
+  return store_keyframe_clouds(h, id, Keyframe(), c, n, 16, true, h->copy_stream);
 }
 
 int ll_add_keyframe(ll_handle h, int id, const void* corner, size_t n_corner, const void* surf, size_t n_surf,

@@ -250,9 +250,14 @@ void MapOptimization::scan2MapOptimization() {  // :1572-1610
   std::memcpy(lastPrior, transformTobeMapped, sizeof(lastPrior));
   if (!mapBuilt_) return;  // first frame: laserCloud*FromMapDSNum are 0, the guard at :1573 fails
   if (view_ && view_->device) {
-    check(ll_scan2map_dev(h_, view_->corner_scan_ds, view_->n_corner_scan_ds, view_->surf_total_ds,
-                          view_->n_surf_total_ds, transformTobeMapped, &lastResult),
-          "ll_scan2map_dev");
+    check(ll_scan2map_dev_async(h_, view_->corner_scan_ds, view_->n_corner_scan_ds, view_->surf_total_ds,
+                                view_->n_surf_total_ds, transformTobeMapped),
+          "ll_scan2map_dev_async");
+    check(ll_prefetch_keyframe_dev(h_, (int)cloudKeyPoses3D.size(), view_->corner_scan, view_->n_corner_scan,
+                                   view_->surf_last_ds, view_->n_surf_last_ds, view_->outlier_last_ds,
+                                   view_->n_outlier_last_ds),
+          "ll_prefetch_keyframe_dev");
+    check(ll_scan2map_wait(h_, transformTobeMapped, &lastResult), "ll_scan2map_wait");
   } else if (view_) {
     // While the scan runs on the GPU, pack and upload the three clouds saveKeyFramesAndFactor is about to store
     // (every frame becomes a keyframe, :1622-1631; only its pose comes out of the scan).
