@@ -435,10 +435,10 @@ int seglist_release(ll_handle h) {
 }
 int seglist_to_device(ll_handle h) {
   if (!h->seg_staged) return LL_OK;
-  LL_TRY(ensure_bytes(h, reinterpret_cast<void**>(&h->d_segs), &h->segs_cap, h->seg_bytes));
-  LL_TRY(ensure_bytes(h, reinterpret_cast<void**>(&h->d_jobs), &h->jobs_cap, h->job_bytes));
-  LL_CUDA(h, cudaMemcpyAsync(h->d_segs, h->seg_host, h->seg_bytes, cudaMemcpyHostToDevice, h->stream));
-  LL_CUDA(h, cudaMemcpyAsync(h->d_jobs, h->seg_host + h->seg_bytes, h->job_bytes, cudaMemcpyHostToDevice, h->stream));
+  // one device block [segments | jobs] (d_jobs points into it), one copy
+  LL_TRY(ensure_bytes(h, reinterpret_cast<void**>(&h->d_segs), &h->segs_cap, h->seg_bytes + h->job_bytes));
+  h->d_jobs = reinterpret_cast<BlockJob*>(reinterpret_cast<uint8_t*>(h->d_segs) + h->seg_bytes);
+  LL_CUDA(h, cudaMemcpyAsync(h->d_segs, h->seg_host, h->seg_bytes + h->job_bytes, cudaMemcpyHostToDevice, h->stream));
   return seglist_release(h);
 }
 
@@ -917,7 +917,7 @@ int ll_destroy(ll_handle h) {
     for (void* p : ptrs)
       if (p) cudaFree(p);
   }
-  void* ptrs[] = {h->d_segs, h->d_jobs, h->d_segs_aux, h->d_jobs_aux, h->dq[0], h->dq[1], h->d_state, h->d_partials, h->d_barriers, h->fa_last[0], h->fa_last[1],
+  void* ptrs[] = {h->d_segs, h->d_segs_aux, h->dq[0], h->dq[1], h->d_state, h->d_partials, h->d_barriers, h->fa_last[0], h->fa_last[1],
                   h->d_tmp[0], h->d_tmp[1], h->d_tmp[2], h->d_tmp[3], h->d_tmp[4], h->d_tmp[5]};
   for (void* p : ptrs)
     if (p) cudaFree(p);
