@@ -1,6 +1,6 @@
 // Host side of the C ABI declared in include/legoloam_b200.h: handle, device memory, launch
-// sequences. Everything numerical runs in the kernels of map_build.cuh / radix_sort.cuh / lm.cuh /
-// fit.cuh; this file only marshals, launches and copies. There is no CPU fallback: a call that cannot
+// sequences. Everything numerical runs in the kernels of map_build.cuh / map_inline.cuh / radix_sort.cuh /
+// lm.cuh / fit.cuh / fa_corr.cuh / normal_eq.cuh; this file only marshals, launches and copies. There is no CPU fallback: a call that cannot
 // reach the GPU fails with LL_ERR_CUDA and ll_last_error_string() says why.
 #include "../../include/legoloam_b200.h"
 

@@ -1,18 +1,23 @@
 // The Levenberg-Marquardt loop of scan2MapOptimization (mapOptmization.cpp:1572-1610) on the device.
 //
-// One launch of lm_iter_kernel = one iteration of the reference's loop body:
-//   cornerOptimization (a7) + surfOptimization (a8), in two phases per block —
-//     phase 1, one warp per query: pointAssociateToMap (a6) -> 5-NN in the 3x3x3 cells of the 1 m grid
-//       (a5; lanes fetch the 27 cell descriptors in one round trip; the candidates of a row of three
-//       x-adjacent cells are contiguous in the cell-sorted array, so lanes read consecutive float4s)
-//       -> warp-level top-5 by (d2, map index) with redux.sync -> neighbours staged in shared memory;
+// One iteration of the reference's loop body, per block of 512 threads (lm_block_pass):
+//   cornerOptimization (a7) + surfOptimization (a8), in two phases —
+//     phase 1, one warp per query, three queries of a warp searched together (warp_knn5_batch):
+//       pointAssociateToMap (a6) -> 5-NN in the 3x3x3 cells of the 1 m grid (a5; lanes fetch the 27 cell
+//       descriptors in one round trip; the candidates of a row of three x-adjacent cells are contiguous in the
+//       cell-sorted array, so lanes read consecutive float4s) -> per-lane sorting network + warp-level top-5 by
+//       (d2, map index) with redux.sync -> neighbours staged in shared memory;
 //     phase 2, one thread per query: line / plane fit in registers (fit.cuh) -> Jacobian row ->
 //       shuffle-tree reduction of the 29 sums (21 AtA + 6 Atb + sum|d| + count) in a fixed order;
-//   LMOptimization (a9): the block partials are written to global memory and the LAST block to
-//     finish (atomic ticket) adds them in a fixed order, solves the 6x6 system, applies the
-//     degeneracy projector, updates the pose and its sin/cos, and evaluates the stop test.
-// Iterations are separate launches on one stream (the kernel boundary is the grid-wide barrier);
-// the host never reads anything back between them.
+//   LMOptimization (a9): block partials -> global memory -> added in a fixed order -> 6x6 solve, degeneracy
+//     projector, pose update and its sin/cos, stop test (lm_solve_block, solve_warp.cuh).
+// Two drivers:
+//   lm_persistent_kernel  the WHOLE scan in one cooperative launch (default): optional in-kernel map assembly
+//                         (map_inline.cuh), then all iterations, separated by grid barriers; every block adds
+//                         all partials and solves redundantly, so no pose is ever published or waited for;
+//   lm_iter_kernel        one launch per iteration (stage-level entry points, persistent_lm = 0): the last block
+//                         to finish (atomic ticket) reduces and solves; the kernel boundary is the barrier.
+// The host never reads anything back between iterations in either.
 #pragma once
 #include "common.cuh"
 #include "fit.cuh"

@@ -9,6 +9,8 @@
 //   rs_onesweep_kernel       a4  sort by cell key
 //   grid_finalize_kernel     a4  cell-ordered point array (w = map index) + per-cell [start,end)
 // The corner map and the surf map go through the same launches (blockIdx.y = map).
+// These stand-alone kernels are the general path (any size, stage-level ABI, persistent_lm = 0); a VLP-16-sized local
+// map is normally assembled inside the scan kernel instead (map_inline.cuh), with bit-identical results.
 //
 // Why a 1 m uniform grid is EXACT for this path: the reference only uses a neighbour set when
 // pointSearchSqDis[4] < 1.0 (mapOptmization.cpp:1279, :1389). cell(p) = floorf(p) is exact in float,
