@@ -57,6 +57,10 @@ def parse_args():
     ap.add_argument("--sequences", type=int, default=64)
     ap.add_argument("--scans-per-seq", type=int, default=40)
     ap.add_argument("--threads", type=int, default=8, help="concurrent sequences (host threads / streams) per GPU")
+    ap.add_argument("--batch-blocks", type=int, default=-1,
+                    help="batch workload: > 0 = every sequence runs the persistent scan kernel on at most this many SMs "
+                         "(lm_max_blocks); 0 = one launch per LM iteration (persistent_lm = 0); -1 = a quarter of the SMs "
+                         "(measured best on B200: 37 blocks x 8 sequences in flight)")
     ap.add_argument("--no-l2-flush", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-at-scale", action="store_true", help="skip the configs[2]/[3]-shaped per-kernel measurements")
@@ -242,7 +246,9 @@ def run_batch(args, rank, world, device):
 
     def make_node():
         # several handles share the GPU: one launch per LM iteration so that their kernels interleave
-        return host.MapOptimization(headline_params(abi, persistent_lm=0), device=device, loop_closure_enabled=True, search_num=WINDOW)
+        nb = args.batch_blocks if args.batch_blocks >= 0 else max(1, torch.cuda.get_device_properties(device).multi_processor_count // 4)
+        kw = dict(persistent_lm=0) if nb == 0 else dict(persistent_lm=1, lm_max_blocks=nb)
+        return host.MapOptimization(headline_params(abi, **kw), device=device, loop_closure_enabled=True, search_num=WINDOW)
 
     def feed(node, data, k):
         return node.process_frame_host(data["odom"][k], data["host"][k])
@@ -472,8 +478,8 @@ def main():
                               "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
                               "data": "synthetic",
                               "config": {"workload": "configs[4]: batched replay of %d independent VLP-16 sequences x %d scans, "
-                                                     "seq -> rank = seq mod world, %d sequences in flight per GPU, NCCL only "
-                                                     "gathers the result records" % (args.sequences, args.scans_per_seq, args.threads),
+                                                     "seq -> rank = seq mod world, %d sequences in flight per GPU (persistent scan kernels on a quarter "
+                                                     "of the SMs each unless --batch-blocks says otherwise), NCCL only gathers the result records" % (args.sequences, args.scans_per_seq, args.threads),
                                          "timing": "wall clock between device synchronisations, max over ranks (concurrent streams)"},
                               "checks": {"all_scans_optimised": ok, "records": list(allrec.shape)}}))
         return

@@ -69,6 +69,10 @@ typedef struct {
   int    persistent_lm;    /* 1 (default) = the whole iteration loop of scan2MapOptimization in one cooperative launch
                               (one block per SM, grid barrier per iteration); 0 = one launch per iteration (use this
                               when several handles share a GPU and should interleave, e.g. batched replay). */
+  int    lm_max_blocks;    /* 0 (default) = the scan kernel uses every SM. > 0: at most this many blocks (one per SM), so
+                              that several handles can keep a persistent scan kernel in flight on one GPU at the same time
+                              (batched replay: e.g. half the SMs each); maps too large for that many 8192-point tiles
+                              are assembled by the stand-alone kernels instead. */
 } ll_params;
 
 /* What scan2MapOptimization leaves behind (mapOptmization.cpp:1602-1607 and members). */

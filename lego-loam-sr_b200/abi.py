@@ -31,7 +31,7 @@ class Params(C.Structure):
         ("min_weight", C.c_double), ("min_residuals", C.c_int), ("eig_thresh", C.c_float),
         ("iter_count_thres", C.c_int), ("step_size", C.c_float), ("stop_thres", C.c_float),
         ("apply_update", C.c_int), ("eigen_mode", C.c_int), ("map_downsample", C.c_int),
-        ("min_corner_map", C.c_int), ("min_surf_map", C.c_int), ("lm_solver", C.c_int), ("persistent_lm", C.c_int),
+        ("min_corner_map", C.c_int), ("min_surf_map", C.c_int), ("lm_solver", C.c_int), ("persistent_lm", C.c_int), ("lm_max_blocks", C.c_int),
     ]
 
 

@@ -642,6 +642,7 @@ int validate_params(ll_handle h, const ll_params* p) {
   if (p->eigen_mode != 0 && p->eigen_mode != 1) return fail(h, LL_ERR_INVALID_ARG, "eigen_mode must be 0 or 1");
   if (p->lm_solver != 0 && p->lm_solver != 1) return fail(h, LL_ERR_INVALID_ARG, "lm_solver must be 0 or 1");
   if (p->persistent_lm != 0 && p->persistent_lm != 1) return fail(h, LL_ERR_INVALID_ARG, "persistent_lm must be 0 or 1");
+  if (p->lm_max_blocks < 0) return fail(h, LL_ERR_INVALID_ARG, "lm_max_blocks must be >= 0");
   return LL_OK;
 }
 
@@ -721,6 +722,15 @@ int scan2map_enqueue(ll_handle h, const float pose6[6]) {
   const int nq = h->nq[0] + h->nq[1];
   h->lm_blocks = lm_grid_blocks(h, nq);
   if (h->prm.persistent_lm && (h->grid_deferred || h->map_deferred)) h->lm_blocks = h->num_sms;  // one tile per block
+  if (h->prm.persistent_lm && h->prm.lm_max_blocks > 0) {
+    // The caller shares the GPU between several scans in flight (batched replay): a smaller co-resident grid per scan.
+    h->lm_blocks = std::min(h->lm_blocks, std::min(h->prm.lm_max_blocks, h->num_sms));
+    if (h->map_deferred || h->grid_deferred) {  // one 16 x 512 tile per block must hold both maps, else stand-alone kernels
+      const long t = 16L * LM_THREADS;
+      const long tiles = (h->slot[0].n_raw + t - 1) / t + (h->slot[1].n_raw + t - 1) / t;
+      if (tiles > h->lm_blocks) LL_TRY(ensure_grid(h));  // (builds the map first)
+    }
+  }
   LL_TRY(ensure_partials(h, h->lm_blocks));
   if (!h->prm.persistent_lm) LL_TRY(ensure_grid(h));
   if (h->prm.persistent_lm) {
@@ -865,6 +875,7 @@ int ll_default_params(ll_params* p) {
   p->min_surf_map = 100;
   p->lm_solver = 0;
   p->persistent_lm = 1;
+  p->lm_max_blocks = 0;
   return LL_OK;
 }
 

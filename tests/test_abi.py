@@ -36,18 +36,18 @@ def test_library_exports_every_declared_symbol(built):
 def test_default_params_are_the_reference_constants(built, orc):
     p = built.default_params()
     o = orc.default_params()
-    device_only = {"lm_solver", "persistent_lm"}  # execution knobs of the CUDA library; the oracle has no such choice
+    device_only = {"lm_solver", "persistent_lm", "lm_max_blocks"}  # execution knobs of the CUDA library; the oracle has no such choice
     for name, _ in built.Params._fields_:
         if name not in device_only:
             assert getattr(p, name) == getattr(o, name), name
-    assert p.lm_solver == 0 and p.persistent_lm == 1
+    assert p.lm_solver == 0 and p.persistent_lm == 1 and p.lm_max_blocks == 0
     # mapOptmization.cpp:92-94, :1279, :1325, :1416, :1363, :1370, :1453, :1519; loam_config.yaml:32-35
     assert (p.corner_leaf, p.surf_leaf) == (np.float32(0.2), np.float32(0.4))
     assert p.max_sq_dist == 1.0 and p.eig_ratio == 3.0 and p.plane_tol == 0.2 and p.weight_k == 0.9
     assert p.min_weight == 0.1 and p.min_residuals == 50 and p.eig_thresh == 100.0
     assert p.iter_count_thres == 200 and p.step_size == 1.0 and p.stop_thres == np.float32(0.05)
     assert p.apply_update == 0 and p.eigen_mode == 0 and p.map_downsample == 1
-    assert C.sizeof(built.Params) == C.sizeof(orc.Params) + 8
+    assert C.sizeof(built.Params) == C.sizeof(orc.Params) + 16  # three ints, padded to the struct's 8-byte alignment
 
 
 def test_invalid_arguments_are_rejected_without_a_device(built):

@@ -399,6 +399,22 @@ def test_call_sequences_around_a_pending_map(abi, orc, single_problem):
         assert res0.sel_num == 0 and np.array_equal(bits(pose0), bits(prior))
 
 
+@pytest.mark.parametrize("max_blocks", [74, 20, 3])
+def test_scan2map_on_part_of_the_gpu(abi, orc, single_problem, single_maps, max_blocks):
+    """lm_max_blocks: the single-kernel scan on a fraction of the SMs (batched replay keeps several in flight). 74 blocks
+    still hold the map (in-kernel assembly), 20 and 3 do not (stand-alone kernels, persistent LM loop only)."""
+    d = single_problem
+    with abi.Handle(upstream_params(abi, lm_max_blocks=max_blocks)) as h:
+        load_map(h, d)
+        pose, res = h.scan2map(d["query"]["corner_scan_ds"], d["query"]["surf_total_ds"], d["prior"])
+        cds_gpu, sds_gpu = h.get_map_ds(0), h.get_map_ds(1)
+    ores, opose, _ = orc.scan2map(single_maps["corner_ds"], single_maps["surf_ds"], d["query"]["corner_scan_ds"],
+                                  d["query"]["surf_total_ds"], d["prior"], upstream_params(orc))
+    assert np.array_equal(bits(cds_gpu), bits(single_maps["corner_ds"])) and np.array_equal(bits(sds_gpu), bits(single_maps["surf_ds"]))
+    assert res.status == 0 and res.iter_num == 10 and abs(res.sel_num - ores.sel_num) <= 3
+    assert trans_err(pose, opose) <= TOL_T and rot_err(pose, opose) <= TOL_R
+
+
 def test_scan2map_early_exit_and_thresholds(abi, orc, single_problem, single_maps):
     d = single_problem
     for kw in (dict(stop_thres=0.05, iter_count_thres=30), dict(stop_thres=0.05, iter_count_thres=200),
