@@ -135,7 +135,10 @@ int ll_set_keyframe_pose(ll_handle h, int id, const float pose6[6]);
 /* ---- a1: extractSurroundingKeyFrames tail (mapOptmization.cpp:1147-1151 / :1218-1231):
  * transform the listed keyframes by their poses, concatenate (per keyframe corner | surf, outlier),
  * VoxelGrid 0.2 / 0.4 (unless map_downsample = 0), then build the 1 m search grids that replace
- * kdtreeCornerFromMap / kdtreeSurfFromMap (:1575-1576). Asynchronous on the handle's stream. */
+ * kdtreeCornerFromMap / kdtreeSurfFromMap (:1575-1576). Asynchronous on the handle's stream. With persistent_lm = 1 and a
+ * map of up to 2^20 raw points the work is only prepared here and runs at the head of the next ll_scan2map launch (one
+ * cooperative kernel for the whole scan); any other consumer (ll_get_map_ds, ll_knn5, ...) triggers the stand-alone
+ * kernels first, so the observable results are the same either way (bit for bit; tests). */
 int ll_build_local_map(ll_handle h, const int* ids, int n_ids);
 /* Test / bench entry that skips the keyframe store: raw surrounding clouds already in the map frame. */
 int ll_set_local_map_raw(ll_handle h, const void* corner, size_t n_corner, const void* surf,
