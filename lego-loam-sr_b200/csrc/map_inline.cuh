@@ -19,6 +19,12 @@
 // A grid barrier costs ~1.3 us and a pass ~1.5 us of work, against a kernel boundary plus a decoupled look-back
 // chain (~9-15 us) per pass of the stand-alone sort. `cells` marks an empty cell as (INT_MAX, 0) instead of (0, 0) —
 // both read as "end <= start" by the search.
+// Memory-ordering notes for the in-kernel path. (1) Everything one stage writes and a later stage of ANOTHER block reads is
+// separated by a coop_barrier (release-reduction arrive, acquire poll) and read with __ldcg where the reading block may
+// hold an older copy of the line in its L1 (MapState fields, sort buffers, raw / ds). (2) The LM loop afterwards reads
+// `sorted` and `cells` through the read-only path (__ldg) although this launch wrote them: no SM touches those lines
+// with a load before the barrier that follows their last write, and L1 is invalidated between launches, so no stale
+// copy can exist — the single-kernel path is compared bit for bit with the stand-alone kernels in the tests.
 #pragma once
 #include "common.cuh"
 #include "map_build.cuh"
