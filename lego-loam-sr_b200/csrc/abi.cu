@@ -1129,13 +1129,14 @@ int ll_set_local_map_raw(ll_handle h, const void* corner, size_t n_corner, const
   LL_CUDA(h, cudaSetDevice(h->device));
   LL_TRY(ensure_slot(h, 0, n_corner, true));
   LL_TRY(ensure_slot(h, 1, n_surf, true));
-  // stage the two clouds in the `sorted` buffers (free until grid_finalize), then run the pipeline with
-  // identity segments
-  LL_TRY(upload_points(h, h->slot[0].sorted, corner, n_corner, stride_bytes));
-  LL_TRY(upload_points(h, h->slot[1].sorted, surf, n_surf, stride_bytes));
+  // Stage the two clouds in the `ds` buffers (free until the VoxelGrid reduce writes them; unused altogether when the map is
+  // not downsampled), then run the pipeline with identity segments. Not in `sorted`: the LM loop reads that array
+  // through the read-only path, and in the single-kernel scan no SM may have loaded its lines earlier in the launch.
+  LL_TRY(upload_points(h, h->slot[0].ds, corner, n_corner, stride_bytes));
+  LL_TRY(upload_points(h, h->slot[1].ds, surf, n_surf, stride_bytes));
   SegList L;
-  L.add(h->slot[0].sorted, (int)n_corner, 0, 0, nullptr);
-  L.add(h->slot[1].sorted, (int)n_surf, 0, 1, nullptr);
+  L.add(h->slot[0].ds, (int)n_corner, 0, 0, nullptr);
+  L.add(h->slot[1].ds, (int)n_surf, 0, 1, nullptr);
   h->slot[0].n_raw = (int)n_corner;
   h->slot[1].n_raw = (int)n_surf;
   const int ds = h->prm.map_downsample ? 1 : 0;
