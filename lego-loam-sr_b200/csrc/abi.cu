@@ -506,8 +506,10 @@ int run_map_pipeline(ll_handle h, int sa, int sb, const SegList& L, float leaf_a
   h->n_jobs = (int)L.jobs.size();
   // The persistent kernel sorts one tile of <= 16 * 512 points per block, both maps together, on one block per SM.
   const long pts = (long)h->slot[sa].n_raw + (sb >= 0 ? (long)h->slot[sb].n_raw : 0);
+  const long tile16 = 16L * LM_THREADS;  // the largest tile a block keeps in registers
+  const bool fits_sms = (h->slot[sa].n_raw + tile16 - 1) / tile16 + (sb >= 0 ? (h->slot[sb].n_raw + tile16 - 1) / tile16 : 0) <= h->num_sms;
   static const bool no_inline = std::getenv("LLB200_NO_INLINE_MAP") != nullptr;  // A/B switch for measurements
-  if (!no_inline && build_grid && h->prm.persistent_lm && sb >= 0 && !want_member && pts <= kInlineMapMaxPoints) {
+  if (!no_inline && build_grid && h->prm.persistent_lm && sb >= 0 && !want_member && pts <= kInlineMapMaxPoints && fits_sms) {
     // (the kernel zeroes MapState itself.) Zero-copy reads of the staged table from the kernel were measured: +15 us
     // of PCIe round trips inside the transform stage against ~8 us for the two copies here.
     static const bool zero_copy = std::getenv("LLB200_SEG_ZERO_COPY") != nullptr;
@@ -519,7 +521,7 @@ int run_map_pipeline(ll_handle h, int sa, int sb, const SegList& L, float leaf_a
   LL_TRY(run_voxel_build(h, want_member));
   if (!build_grid) return LL_OK;
   static const bool no_inline_grid = std::getenv("LLB200_NO_INLINE_GRID") != nullptr;
-  if (!no_inline_grid && h->prm.persistent_lm && sb >= 0 && !want_member && pts <= kInlineMapMaxPoints) {
+  if (!no_inline_grid && h->prm.persistent_lm && sb >= 0 && !want_member && pts <= kInlineMapMaxPoints && fits_sms) {
     h->grid_deferred = true;  // the next persistent scan kernel builds the grids; any other consumer calls ensure_grid()
     return LL_OK;
   }
