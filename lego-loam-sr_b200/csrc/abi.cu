@@ -5,6 +5,9 @@
 #include "../../include/legoloam_b200.h"
 
 #include <cmath>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -250,6 +253,23 @@ int pinned_release(ll_handle h) {
 // pcl::PointXYZI -> packed float4. stride 16: {x,y,z,intensity}; otherwise intensity sits at byte 16.
 inline void pack_points(float4* dst, const void* src, size_t n, size_t stride) {
   const uint8_t* b = static_cast<const uint8_t*>(src);
+  if (stride == 16) {  // already packed
+    std::memcpy(dst, src, n * sizeof(float4));
+    return;
+  }
+#if defined(__SSE2__)
+  {  // pcl::PointXYZI: 16 bytes {x, y, z, pad} then intensity — two loads, two shuffles, one store per point
+    float* out = reinterpret_cast<float*>(dst);
+    for (size_t i = 0; i < n; ++i) {
+      const float* f = reinterpret_cast<const float*>(b + i * stride);
+      const __m128 v = _mm_loadu_ps(f);
+      const __m128 w = _mm_load_ss(f + 4);
+      const __m128 zw = _mm_shuffle_ps(v, w, _MM_SHUFFLE(0, 0, 2, 2));               // (z, z, w, w)
+      _mm_storeu_ps(out + 4 * i, _mm_shuffle_ps(v, zw, _MM_SHUFFLE(2, 0, 1, 0)));  // (x, y, z, w)
+    }
+    return;
+  }
+#endif
   const size_t ioff = stride == 16 ? 12 : 16;
   for (size_t i = 0; i < n; ++i) {
     const float* f = reinterpret_cast<const float*>(b + i * stride);
