@@ -538,6 +538,29 @@ int run_map_pipeline(ll_handle h, int sa, int sb, const SegList& L, float leaf_a
     h->grid_deferred = true;
     return LL_OK;
   }
+  // A single cloud (ll_voxel_downsample) of moderate size: the in-kernel pipeline as one cooperative launch.
+  static const bool no_inline_voxel = std::getenv("LLB200_NO_INLINE_VOXEL") != nullptr;
+  if (!no_inline_voxel && sb < 0 && !build_grid && !want_member && ds_a && h->slot[sa].n_raw > 0 &&
+      pts <= kInlineMapMaxPoints && fits_sms) {
+    LL_TRY(seglist_to_device(h));
+    MapBatch B = make_map_batch(h, false);
+    B.m[1].downsample = 0;  // (the second entry mirrors the first with no points: it must not take part)
+    const long t4 = 4L * LM_THREADS;
+    int blocks = (int)std::min<long>(h->num_sms, std::max<long>((h->slot[sa].n_raw + t4 - 1) / t4, (long)h->n_jobs));
+    blocks = std::max(blocks, 1);
+    unsigned* bar = h->d_barriers + (h->scan_seq % kBarrierSlots);
+    unsigned* bar_clear = h->d_barriers + ((h->scan_seq + kBarrierSlots / 2) % kBarrierSlots);
+    h->scan_seq++;
+    const Segment* segs = h->d_segs;
+    const BlockJob* jobs = h->d_jobs;
+    int n_jobs = h->n_jobs;
+    void* args[] = {&B, &segs, &jobs, &n_jobs, &bar, &bar_clear};
+    LL_PROF(h, 3);
+    LL_CUDA(h, cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(voxel_inline_kernel), dim3((unsigned)blocks),
+                                           dim3(GI_THREADS), args, 0, h->stream));
+    LL_LAUNCHED(h);
+    return LL_OK;
+  }
   LL_TRY(run_voxel_build(h, want_member));
   if (!build_grid) return LL_OK;
   static const bool no_inline_grid = std::getenv("LLB200_NO_INLINE_GRID") != nullptr;

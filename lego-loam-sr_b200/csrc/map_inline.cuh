@@ -556,7 +556,8 @@ __device__ __forceinline__ void gi_voxel(const MapBatch& B, unsigned* barrier, u
 // the co-resident grid must call; returns with a grid barrier passed.
 // Returns true when the cell tables of the search grids were cleared on the side (see below).
 __device__ __forceinline__ bool map_build_inline(const MapBatch& B, const Segment* segs, const BlockJob* jobs, int njobs,
-                                                 unsigned* barrier, unsigned& epoch, uint32_t* smem) {
+                                                 unsigned* barrier, unsigned& epoch, uint32_t* smem,
+                                                 bool may_clear_cells = true) {
   gi_transform(B, segs, jobs, njobs, smem);
   coop_barrier(barrier, epoch);
   const int n0 = B.m[0].downsample ? B.m[0].n_raw : 0, n1 = B.m[1].downsample ? B.m[1].n_raw : 0;
@@ -565,7 +566,7 @@ __device__ __forceinline__ bool map_build_inline(const MapBatch& B, const Segmen
   // at its barriers, so they clear the cell tables of the search grids meanwhile (the geometry only needs the box).
   const int t_ = GI_THREADS * (items > 0 ? items : GI_MAX_ITEMS);
   const int tiles = (n0 + t_ - 1) / t_ + (n1 + t_ - 1) / t_;
-  const bool side_clear = tiles < (int)gridDim.x;  // grid-uniform
+  const bool side_clear = may_clear_cells && tiles < (int)gridDim.x;  // grid-uniform
   if (side_clear && (int)blockIdx.x >= tiles) {
     const int idle = (int)gridDim.x - tiles, me = (int)blockIdx.x - tiles;
 #pragma unroll
@@ -621,6 +622,19 @@ __device__ __forceinline__ void grid_build_inline(const MapBatch& B, unsigned* b
   else if (items == 8) gi_sort_tiles<8>(B, gd, n, barrier, epoch, smem);
   else if (items == 16) gi_sort_tiles<16>(B, gd, n, barrier, epoch, smem);
   coop_barrier(barrier, epoch);
+}
+
+// Rows a2-a3 alone (ll_voxel_downsample on a cloud of up to 2^20 points: downsampleCurrentScan's six filters): the same
+// in-kernel pipeline as the head of the scan kernel, as ONE cooperative launch instead of seven launches.
+__global__ void __launch_bounds__(GI_THREADS, 1) voxel_inline_kernel(const __grid_constant__ MapBatch B,
+                                                                     const Segment* segs, const BlockJob* jobs, int n_jobs,
+                                                                     unsigned* barrier, unsigned* barrier_clear) {
+  __shared__ __align__(16) uint32_t smem[(GI_SMEM_WORDS > GI_SMEM_WORDS_REDUCE ? GI_SMEM_WORDS : GI_SMEM_WORDS_REDUCE)];
+  unsigned epoch = 0;
+  if (blockIdx.x == 0 && threadIdx.x < 128) reinterpret_cast<uint32_t*>(B.m[threadIdx.x >> 6].st)[threadIdx.x & 63] = 0u;
+  coop_barrier(barrier, epoch);
+  map_build_inline(B, segs, jobs, n_jobs, barrier, epoch, smem, /*may_clear_cells=*/false);
+  if (blockIdx.x == 0 && threadIdx.x == 0) *barrier_clear = 0u;
 }
 
 }  // namespace ll

@@ -54,6 +54,27 @@ def test_voxel_downsample_bit_exact(abi, orc, single_problem, leaf):
     assert np.array_equal(bits(out), bits(o_out))      # centroids, accumulated in the canonical order
 
 
+def test_voxel_downsample_single_launch_path(abi, orc, single_problem):
+    """Without the membership output ll_voxel_downsample runs rows a2-a3 as ONE cooperative launch (voxel_inline_kernel,
+    what downsampleCurrentScan's six filters use): same bits as the oracle and as the stand-alone kernels."""
+    d = single_problem
+    kf = d["keyframes"]
+    big = np.concatenate([f["surf_last_ds"] for f in kf]).astype(np.float32)
+    rng = np.random.default_rng(3)
+    with_nan = big[:20000].copy()
+    with_nan[rng.choice(len(with_nan), 40, replace=False), 2] = np.nan
+    cases = [(big, 0.4), (big, 0.2), (big[:1], 0.4), (big[:37], 1.0), (with_nan, 0.4), (big[:3000], 1e-4)]
+    with abi.Handle(abi.default_params()) as h:
+        for cloud, leaf in cases:
+            out, _, flags = h.voxel_downsample(cloud, leaf, want_member=False)
+            launches0 = h.launch_count
+            out2, member, flags2 = h.voxel_downsample(cloud, leaf, want_member=True)
+            o_out, _, o_flag = orc.voxel_downsample(cloud, leaf)
+            assert flags == flags2 == o_flag
+            assert np.array_equal(bits(out), bits(o_out)) and np.array_equal(bits(out2), bits(o_out)), (len(cloud), leaf)
+            assert h.launch_count - launches0 >= 7  # (the membership variant is the seven-launch pipeline)
+
+
 def test_voxel_downsample_edge_cases(abi, orc):
     rng = np.random.default_rng(0)
     with abi.Handle() as h:
