@@ -165,6 +165,24 @@ int ll_scan2map_wait(ll_handle h, float pose6_out[6], ll_result* res);
  * member (nullable, n ints): output slot of each input point. flags bit 0 = index overflow. */
 int ll_voxel_downsample(ll_handle h, const void* in, size_t n, size_t stride_bytes, float leaf, void* out,
                         size_t cap_points, size_t out_stride_bytes, size_t* n_out, int* member, int* flags);
+/* f-2 in one call: downsampleCurrentScan (mapOptmization.cpp:1234-1267). clouds[5] = laserCloudCornerLast,
+ * laserCloudSurfLast, laserCloudCornerScan, laserCloudSurfScan, laserCloudOutlierLast (host, stride_bytes per point);
+ * the six results are, in order, laserCloudCornerLastDS, SurfLastDS, CornerScanDS, SurfScanDS, OutlierLastDS
+ * (params.corner_leaf for the corner clouds, params.surf_leaf for the others, :92-94) and SurfTotalLastDS
+ * (= VoxelGrid(SurfLastDS + OutlierLastDS), :1259-1263), bit-identical to six ll_voxel_downsample calls.
+ * *dev receives packed float4 DEVICE copies of the inputs and of the results — what ll_scan2map_dev_async and
+ * ll_prefetch_keyframe_dev / ll_add_keyframe_dev take — valid until the next ll_downsample_scan on this handle.
+ * out may be NULL (results stay on the device) or hold six host buffers (NULL entries skipped) of cap_points[k]
+ * points, out_stride_bytes per point. flags[k] = 1: PCL's "leaf size too small" case, cloud k passed through. */
+typedef struct ll_scan_clouds {
+  const void* d_raw[5];
+  size_t      n_raw[5];
+  const void* d_ds[6];
+  size_t      n_ds[6];
+  int         flags[6];
+} ll_scan_clouds;
+int ll_downsample_scan(ll_handle h, const void* const clouds[5], const size_t n[5], size_t stride_bytes,
+                       ll_scan_clouds* dev, void* const out[6], const size_t cap_points[6], size_t out_stride_bytes);
 /* a4 + a5: nearestKSearch(point, 5) against the current local map (which = 0 corner, 1 surf) for
  * queries already in the map frame. accept[i] = (5 neighbours found with d2 < max_sq_dist); for
  * accepted queries idx5/d2_5 are the exact 5-NN ascending by (d2, index). */

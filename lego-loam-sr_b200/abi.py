@@ -42,6 +42,12 @@ class Result(C.Structure):
                 ("last_x", C.c_float * 6)]
 
 
+class ScanClouds(C.Structure):
+    """ll_scan_clouds: device copies of downsampleCurrentScan's inputs and results (valid until the next call)."""
+    _fields_ = [("d_raw", C.c_void_p * 5), ("n_raw", C.c_size_t * 5), ("d_ds", C.c_void_p * 6), ("n_ds", C.c_size_t * 6),
+                ("flags", C.c_int * 6)]
+
+
 class LegoLoamError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__("%s (%d): %s" % (STATUS_NAMES.get(code, "?"), code, msg))
@@ -247,6 +253,27 @@ class Handle:
                                                   _vp(out), C.c_size_t(len(out)), C.c_size_t(16), C.byref(n_out),
                                                   _vp(member) if want_member else None, C.byref(flags)))
         return out[:n_out.value].copy(), member[:n], flags.value
+
+    def downsample_scan(self, clouds, want_host=True):
+        """downsampleCurrentScan in one call. clouds = (corner_last, surf_last, corner_scan, surf_scan, outlier_last);
+        -> (six downsampled clouds or None, ScanClouds with the device pointers / counts / flags)."""
+        packed = [_cloud(c) for c in clouds]
+        assert len(packed) == 5 and len({st for _, _, st in packed}) == 1
+        ptrs = (C.c_void_p * 5)(*[p.ctypes.data if n else None for p, n, _ in packed])
+        ns = (C.c_size_t * 5)(*[n for _, n, _ in packed])
+        dev = ScanClouds()
+        outs = None
+        out_ptrs, caps = None, None
+        if want_host:
+            cap = [packed[0][1], packed[1][1], packed[2][1], packed[3][1], packed[4][1], packed[1][1] + packed[4][1]]
+            outs = [np.empty((max(c, 1), 4), np.float32) for c in cap]
+            out_ptrs = (C.c_void_p * 6)(*[o.ctypes.data for o in outs])
+            caps = (C.c_size_t * 6)(*[len(o) for o in outs])
+        self._check(self._lib.ll_downsample_scan(self._h, ptrs, ns, C.c_size_t(packed[0][2]), C.byref(dev), out_ptrs, caps,
+                                                 C.c_size_t(16)))
+        if want_host:
+            outs = [o[:dev.n_ds[k]].copy() for k, o in enumerate(outs)]
+        return outs, dev
 
     def knn5(self, which, queries):
         q, nq, stride = _cloud(queries)

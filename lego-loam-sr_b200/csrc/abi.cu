@@ -32,6 +32,7 @@ namespace {
 constexpr size_t kArenaChunk = 256ull << 20;  // keyframe store grows in 256 MiB slabs (~1000 VLP-16 keyframes each)
 constexpr int kCellCap = 1 << 24;            // 16.7 M one-metre cells per search grid (<= 24 key bits: 3 sort passes)
 constexpr int kGridPasses = 3;
+constexpr size_t kSpeculativeD2HBytes = 256u << 10;  // ll_voxel_downsample: copy all n output slots before n_ds is known
 constexpr int kPinSlots = 4;                 // pinned staging buffers in flight
 constexpr int kFirstChunk = 12;              // LM iterations enqueued before the first look at `done`
 constexpr int kNextChunk = 16;
@@ -130,6 +131,10 @@ struct ll_handle_s {
 
   void* d_tmp[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // emit / stage scratch
   float4* fa_last[2] = {nullptr, nullptr};  // laserCloudCornerLast / laserCloudSurfLast (ll_fa_set_last)
+  float4* scan_buf = nullptr;  // ll_downsample_scan: [5 raw clouds | 6 downsampled clouds], device resident until the next call
+  size_t scan_cap = 0;
+  uint8_t* res_pin = nullptr;  // its pinned result block: [6 x 256-byte MapState | downsampled points]
+  size_t res_pin_bytes = 0;
   size_t fa_last_cap[2] = {0, 0};
   int fa_n_last[2] = {0, 0};
 
@@ -519,7 +524,6 @@ int run_map_pipeline(ll_handle h, int sa, int sb, const SegList& L, float leaf_a
       LL_TRY(ensure_grid(h));
     }
   }
-  const int ny = sb >= 0 ? 2 : 1;
   h->grid_cfg = {sa, sb, leaf_a, leaf_b, ds_a, ds_b};
   LL_TRY(seglist_release(h));  // (a table staged for a map that was never built)
   LL_TRY(stage_seglist(h, L));
@@ -982,6 +986,8 @@ int ll_destroy(ll_handle h) {
     if (h->pin_evt[i]) cudaEventDestroy(h->pin_evt[i]);
   }
   if (h->h_state) cudaFreeHost(h->h_state);
+  if (h->res_pin) cudaFreeHost(h->res_pin);
+  if (h->scan_buf) cudaFree(h->scan_buf);
   for (cudaEvent_t e : h->prof_pool) cudaEventDestroy(e);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -1288,22 +1294,149 @@ int ll_voxel_downsample(ll_handle h, const void* in, size_t n, size_t stride_byt
   L.add(S.sorted, (int)n, 0, 0, nullptr);
   S.n_raw = (int)n;
   LL_TRY(run_map_pipeline(h, 2, -1, L, leaf, leaf, 1, 1, false, member != nullptr));
-  MapState st;
-  LL_CUDA(h, cudaMemcpyAsync(&st, S.st(), sizeof(st), cudaMemcpyDeviceToHost, h->stream));
+  // Results come back through one pinned slot: [MapState | points]. A small cloud's points travel speculatively
+  // (all n slots of `ds`, of which the first n_ds are valid) behind the counters, so the call pays one
+  // synchronisation; a large one first reads n_ds and then copies exactly that many.
+  constexpr size_t kHead = 256;
+  const bool speculative = out && n * sizeof(float4) <= kSpeculativeD2HBytes;
+  LL_TRY(pinned_acquire(h, kHead + (out ? n * sizeof(float4) : 0)));
+  uint8_t* pin = h->pinned;
+  const MapState& st = *reinterpret_cast<const MapState*>(pin);
+  const float4* pts = reinterpret_cast<const float4*>(pin + kHead);
+  LL_CUDA(h, cudaMemcpyAsync(pin, S.st(), sizeof(MapState), cudaMemcpyDeviceToHost, h->stream));
+  if (speculative) LL_CUDA(h, cudaMemcpyAsync(pin + kHead, S.ds, n * sizeof(float4), cudaMemcpyDeviceToHost, h->stream));
+  if (member) LL_CUDA(h, cudaMemcpyAsync(member, S.member, n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   LL_CUDA(h, cudaStreamSynchronize(h->stream));
-  *n_out = (size_t)st.n_ds;
+  const size_t n_ds = (size_t)st.n_ds;
+  *n_out = n_ds;
   if (flags) *flags = st.voxel_overflow ? 1 : 0;
-  if (member) {
-    LL_CUDA(h, cudaMemcpyAsync(member, S.member, n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  if (!out) return pinned_release(h);
+  if (cap_points < n_ds) {
+    pinned_release(h);
+    return fail(h, LL_ERR_CAPACITY, "output buffer too small");
+  }
+  if (!speculative && n_ds) {
+    LL_CUDA(h, cudaMemcpyAsync(pin + kHead, S.ds, n_ds * sizeof(float4), cudaMemcpyDeviceToHost, h->stream));
     LL_CUDA(h, cudaStreamSynchronize(h->stream));
   }
-  if (!out) return LL_OK;
-  if (cap_points < (size_t)st.n_ds) return fail(h, LL_ERR_CAPACITY, "output buffer too small");
-  std::vector<float4> tmp((size_t)st.n_ds);
-  if (!tmp.empty()) {
-    LL_CUDA(h, cudaMemcpyAsync(tmp.data(), S.ds, tmp.size() * 16, cudaMemcpyDeviceToHost, h->stream));
+  unpack_points(out, pts, n_ds, out_stride_bytes);
+  return pinned_release(h);
+}
+
+// f-2 in one call: downsampleCurrentScan (mapOptmization.cpp:1234-1267). The five raw clouds go up in ONE copy and
+// stay where they land; each VoxelGrid reads its cloud in place (a one-segment table with the identity transform)
+// and writes its output into its own region of the same device block, so laserCloudSurfTotalLast (:1259-1260) is
+// just a two-segment table over two of those regions. The host waits twice: for the five counts, and for the sixth.
+int ll_downsample_scan(ll_handle h, const void* const clouds[5], const size_t n[5], size_t stride_bytes,
+                       ll_scan_clouds* dev, void* const out[6], const size_t cap_points[6], size_t out_stride_bytes) {
+  if (!h || !clouds || !n || !dev) return LL_ERR_INVALID_ARG;
+  if (!stride_ok(stride_bytes) || (out && (!cap_points || !stride_ok(out_stride_bytes))))
+    return fail(h, LL_ERR_INVALID_ARG, "bad stride / capacity array");
+  if (h->scan_pending) return fail(h, LL_ERR_STATE, "a scan2map is still in flight");
+  size_t raw_total = 0;
+  for (int k = 0; k < 5; ++k) {
+    if (n[k] && !clouds[k]) return fail(h, LL_ERR_INVALID_ARG, "NULL cloud with non-zero count");
+    if (n[k] > 0x1fffffff) return fail(h, LL_ERR_INVALID_ARG, "cloud too large");
+    raw_total += n[k];
+  }
+  LL_CUDA(h, cudaSetDevice(h->device));
+  std::memset(dev, 0, sizeof(*dev));
+  // downSizeFilterCorner for the corner clouds, downSizeFilterSurf / Outlier (same 0.4 leaf, :93-94) for the rest
+  const float leaf[6] = {h->prm.corner_leaf, h->prm.surf_leaf, h->prm.corner_leaf, h->prm.surf_leaf, h->prm.surf_leaf, h->prm.surf_leaf};
+  const size_t cap_ds[6] = {n[0], n[1], n[2], n[3], n[4], n[1] + n[4]};
+  auto pad = [](size_t pts) { return (pts + 15) & ~size_t(15); };  // regions start on 256-byte boundaries
+  size_t off_raw[5], off_ds[6], total = 0, max_n = 0;
+  for (int k = 0; k < 5; ++k) { off_raw[k] = total; total += pad(n[k]); }
+  const size_t raw_pts = total;
+  for (int k = 0; k < 6; ++k) { off_ds[k] = total; total += pad(cap_ds[k]); max_n = std::max(max_n, cap_ds[k]); }
+  const size_t ds_pts = total - raw_pts;
+  if (max_n == 0) return LL_OK;
+  if (h->scan_cap < total) {
     LL_CUDA(h, cudaStreamSynchronize(h->stream));
-    unpack_points(out, tmp.data(), tmp.size(), out_stride_bytes);
+    LL_CUDA(h, cudaStreamSynchronize(h->copy_stream));
+    if (h->scan_buf) LL_CUDA(h, cudaFree(h->scan_buf));
+    h->scan_buf = nullptr;
+    h->scan_cap = 0;
+    const size_t newcap = total + total / 2 + 4096;
+    LL_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&h->scan_buf), newcap * sizeof(float4)));
+    h->scan_cap = newcap;
+  }
+  constexpr size_t kHead = 256;
+  const size_t res_need = 6 * kHead + (out ? ds_pts * sizeof(float4) : 0);
+  if (h->res_pin_bytes < res_need) {
+    LL_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (h->res_pin) LL_CUDA(h, cudaFreeHost(h->res_pin));
+    h->res_pin = nullptr;
+    h->res_pin_bytes = 0;
+    const size_t newcap = res_need + res_need / 2 + 4096;
+    cudaError_t e = cudaMallocHost(reinterpret_cast<void**>(&h->res_pin), newcap);
+    if (e != cudaSuccess) return fail(h, LL_ERR_NOMEM, std::string("cudaMallocHost: ") + cudaGetErrorString(e));
+    h->res_pin_bytes = newcap;
+  }
+  LL_TRY(ensure_slot(h, 2, max_n, false));
+  float4* const buf = h->scan_buf;
+  if (raw_total) {  // the five clouds, packed, in one copy
+    LL_TRY(pinned_acquire(h, raw_pts * sizeof(float4)));
+    for (int k = 0; k < 5; ++k) pack_points(reinterpret_cast<float4*>(h->pinned) + off_raw[k], clouds[k], n[k], stride_bytes);
+    LL_CUDA(h, cudaMemcpyAsync(buf, h->pinned, raw_pts * sizeof(float4), cudaMemcpyHostToDevice, h->stream));
+    LL_TRY(pinned_release(h));
+  }
+  MapSlot& S = h->slot[2];
+  uint8_t* const pin = h->res_pin;
+  std::memset(pin, 0, 6 * kHead);
+  // One VoxelGrid over `L` (n_in points) into region k; its MapState follows it into the pinned block.
+  auto filter = [&](int k, const SegList& L, size_t n_in) -> int {
+    if (n_in == 0) return LL_OK;
+    float4* const keep = S.ds;
+    S.ds = buf + off_ds[k];
+    S.n_raw = (int)n_in;
+    const int rc = run_map_pipeline(h, 2, -1, L, leaf[k], leaf[k], 1, 1, false, false);
+    S.ds = keep;
+    if (rc != LL_OK) return rc;
+    LL_CUDA(h, cudaMemcpyAsync(pin + k * kHead, S.st(), sizeof(MapState), cudaMemcpyDeviceToHost, h->stream));
+    return LL_OK;
+  };
+  for (int k = 0; k < 5; ++k) {
+    SegList L;
+    L.add(buf + off_raw[k], (int)n[k], 0, 0, nullptr);
+    LL_TRY(filter(k, L, n[k]));
+  }
+  float4* const pin_pts = reinterpret_cast<float4*>(pin + 6 * kHead);
+  const bool speculative = out && ds_pts * sizeof(float4) <= 2 * kSpeculativeD2HBytes;
+  if (speculative)  // regions 0-4 in full behind their counters (the first n_ds points of each are valid)
+    LL_CUDA(h, cudaMemcpyAsync(pin_pts, buf + off_ds[0], (off_ds[5] - off_ds[0]) * sizeof(float4), cudaMemcpyDeviceToHost, h->stream));
+  LL_CUDA(h, cudaStreamSynchronize(h->stream));
+  auto state = [&](int k) -> const MapState& { return *reinterpret_cast<const MapState*>(pin + k * kHead); };
+  for (int k = 0; k < 5; ++k) dev->n_ds[k] = (size_t)state(k).n_ds;
+  {  // laserCloudSurfTotalLast = laserCloudSurfLastDS + laserCloudOutlierLastDS, then downSizeFilterSurf (:1259-1263)
+    SegList L;
+    L.add(buf + off_ds[1], (int)dev->n_ds[1], 0, 0, nullptr);
+    L.add(buf + off_ds[4], (int)dev->n_ds[4], (int)dev->n_ds[1], 0, nullptr);
+    LL_TRY(filter(5, L, dev->n_ds[1] + dev->n_ds[4]));
+  }
+  if (speculative) {
+    LL_CUDA(h, cudaMemcpyAsync(pin_pts + (off_ds[5] - off_ds[0]), buf + off_ds[5], pad(cap_ds[5]) * sizeof(float4), cudaMemcpyDeviceToHost, h->stream));
+  } else if (out) {
+    for (int k = 0; k < 5; ++k)
+      if (out[k] && dev->n_ds[k])
+        LL_CUDA(h, cudaMemcpyAsync(pin_pts + (off_ds[k] - off_ds[0]), buf + off_ds[k], dev->n_ds[k] * sizeof(float4), cudaMemcpyDeviceToHost, h->stream));
+  }
+  LL_CUDA(h, cudaStreamSynchronize(h->stream));
+  dev->n_ds[5] = (size_t)state(5).n_ds;
+  if (out && !speculative && out[5] && dev->n_ds[5]) {
+    LL_CUDA(h, cudaMemcpyAsync(pin_pts + (off_ds[5] - off_ds[0]), buf + off_ds[5], dev->n_ds[5] * sizeof(float4), cudaMemcpyDeviceToHost, h->stream));
+    LL_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
+  for (int k = 0; k < 5; ++k) {
+    dev->d_raw[k] = n[k] ? buf + off_raw[k] : nullptr;
+    dev->n_raw[k] = n[k];
+  }
+  for (int k = 0; k < 6; ++k) {
+    dev->d_ds[k] = dev->n_ds[k] ? buf + off_ds[k] : nullptr;
+    dev->flags[k] = state(k).voxel_overflow ? 1 : 0;
+    if (!out || !out[k]) continue;
+    if (cap_points[k] < dev->n_ds[k]) return fail(h, LL_ERR_CAPACITY, "output buffer too small");
+    unpack_points(out[k], pin_pts + (off_ds[k] - off_ds[0]), dev->n_ds[k], out_stride_bytes);
   }
   return LL_OK;
 }

@@ -155,7 +155,7 @@ __device__ __forceinline__ float qr66_warp(const float* AtA, const float* Atb, i
 // Returns false when a pivot is not safely positive (rank-deficient AtA): the caller then takes the
 // rank-revealing QR, whose behaviour in that case (zeroed components) is part of the reference's semantics.
 __device__ __forceinline__ bool ldlt6_solve(const float* AtA, const float* Atb, float x[6]) {
-  double L[6][6], W[6][6], d[6], rd[6], y[6];
+  double L[6][6], W[6][6], rd[6], y[6];
   double maxdiag = 0.0;
 #pragma unroll
   for (int i = 0; i < 6; ++i) maxdiag = fmax(maxdiag, (double)AtA[i * 6 + i]);
@@ -165,7 +165,6 @@ __device__ __forceinline__ bool ldlt6_solve(const float* AtA, const float* Atb, 
     double sj = (double)AtA[j * 6 + j];
 #pragma unroll
     for (int k = 0; k < j; ++k) sj -= L[j][k] * W[j][k];
-    d[j] = sj;
     ok = ok && (sj > 1e-12 * maxdiag);
     rd[j] = 1.0 / sj;
 #pragma unroll

@@ -180,15 +180,31 @@ void MapOptimization::extractSurroundingKeyFrames() {  // :1096-1232
 }
 
 void MapOptimization::downsampleCurrentScan() {  // :1234-1267
-  laserCloudCornerLastDS = voxel(*laserCloudCornerLast, prm_.corner_leaf);
-  laserCloudSurfLastDS = voxel(*laserCloudSurfLast, prm_.surf_leaf);
-  laserCloudCornerScanDS = voxel(*laserCloudCornerScan, prm_.corner_leaf);
-  laserCloudSurfScanDS = voxel(*laserCloudSurfScan, prm_.surf_leaf);
-  laserCloudOutlierLastDS = voxel(*laserCloudOutlierLast, prm_.surf_leaf);  // downSizeFilterOutlier :94
-  laserCloudSurfTotalLast->clear();
+  // The six filters in one call (ll_downsample_scan): the raw clouds go up once, the results come back as the
+  // reference's host members AND stay on the device for scan2MapOptimization / saveKeyFramesAndFactor.
+  const PointCloud* in[5] = {laserCloudCornerLast.get(), laserCloudSurfLast.get(), laserCloudCornerScan.get(),
+                             laserCloudSurfScan.get(), laserCloudOutlierLast.get()};
+  PointCloud::Ptr* res[6] = {&laserCloudCornerLastDS, &laserCloudSurfLastDS, &laserCloudCornerScanDS,
+                             &laserCloudSurfScanDS, &laserCloudOutlierLastDS, &laserCloudSurfTotalLastDS};
+  const void* clouds[5];
+  size_t n[5], cap[6];
+  void* out[6];
+  for (int k = 0; k < 5; ++k) {
+    clouds[k] = in[k]->points.data();
+    n[k] = in[k]->size();
+  }
+  for (int k = 0; k < 6; ++k) {
+    cap[k] = k < 5 ? n[k] : n[1] + n[4];
+    *res[k] = std::make_shared<PointCloud>();
+    (*res[k])->points.resize(cap[k]);
+    out[k] = (*res[k])->points.data();
+  }
+  check(ll_downsample_scan(h_, clouds, n, sizeof(PointType), &scanDev_, out, cap, sizeof(PointType)), "ll_downsample_scan");
+  for (int k = 0; k < 6; ++k) (*res[k])->points.resize(scanDev_.n_ds[k]);
+  scanDevValid_ = true;
+  laserCloudSurfTotalLast->clear();  // :1259-1260 (its downsampled form came out of the call above)
   *laserCloudSurfTotalLast += *laserCloudSurfLastDS;
   *laserCloudSurfTotalLast += *laserCloudOutlierLastDS;
-  laserCloudSurfTotalLastDS = voxel(*laserCloudSurfTotalLast, prm_.surf_leaf);
 }
 
 static void fill_residual_clouds(const PointCloud& q, const std::vector<float>& coeff, const std::vector<int>& mask,
@@ -269,6 +285,13 @@ void MapOptimization::scan2MapOptimization() {  // :1572-1610
                                view_->n_outlier_last_ds, view_->stride_bytes),
           "ll_prefetch_keyframe");
     check(ll_scan2map_wait(h_, transformTobeMapped, &lastResult), "ll_scan2map_wait");
+  } else if (scanDevValid_) {  // downsampleCurrentScan left everything the scan and the keyframe need on the device
+    const ll_scan_clouds& d = scanDev_;
+    check(ll_scan2map_dev_async(h_, d.d_ds[2], d.n_ds[2], d.d_ds[5], d.n_ds[5], transformTobeMapped), "ll_scan2map_dev_async");
+    check(ll_prefetch_keyframe_dev(h_, (int)cloudKeyPoses3D.size(), d.d_raw[2], d.n_raw[2], d.d_ds[1], d.n_ds[1], d.d_ds[4],
+                                   d.n_ds[4]),
+          "ll_prefetch_keyframe_dev");
+    check(ll_scan2map_wait(h_, transformTobeMapped, &lastResult), "ll_scan2map_wait");
   } else {
     check(ll_scan2map_async(h_, laserCloudCornerScanDS->points.data(), laserCloudCornerScanDS->size(),
                             laserCloudSurfTotalLastDS->points.data(), laserCloudSurfTotalLastDS->size(),
@@ -340,6 +363,13 @@ void MapOptimization::saveKeyFramesAndFactor() {  // :1612-1755, pose graph = pa
           "ll_add_keyframe");
     return;
   }
+  if (scanDevValid_) {
+    const ll_scan_clouds& d = scanDev_;
+    check(ll_add_keyframe_dev(h_, (int)cloudKeyPoses3D.size() - 1, d.d_raw[2], d.n_raw[2], d.d_ds[1], d.n_ds[1], d.d_ds[4],
+                              d.n_ds[4], pose),
+          "ll_add_keyframe_dev");
+    return;
+  }
   check(ll_add_keyframe(h_, (int)cloudKeyPoses3D.size() - 1, laserCloudCornerScan->points.data(),
                         laserCloudCornerScan->size(), laserCloudSurfLastDS->points.data(), laserCloudSurfLastDS->size(),
                         laserCloudOutlierLastDS->points.data(), laserCloudOutlierLastDS->size(), sizeof(PointType), pose),
@@ -348,6 +378,7 @@ void MapOptimization::saveKeyFramesAndFactor() {  // :1612-1755, pose graph = pa
 
 void MapOptimization::processFrameView(const float laser_odometry[6], const FrameView& frame) {
   frame_idx++;
+  scanDevValid_ = false;
   view_ = &frame;
   try {
     for (int i = 0; i < 6; ++i) transformSum[i] = laser_odometry[i];
@@ -406,6 +437,7 @@ void MapOptimization::processFrame(const AssociationOut& a, bool scan_clouds_are
   for (int i = 0; i < 6; ++i) transformSum[i] = a.laser_odometry[i];
   transformAssociateToMap();
   extractSurroundingKeyFrames();
+  scanDevValid_ = false;
   if (scan_clouds_are_downsampled) {
     laserCloudCornerScanDS = corner_scan_ds ? corner_scan_ds : a.cloud_corner_scan;
     laserCloudSurfLastDS = a.cloud_surf_last;

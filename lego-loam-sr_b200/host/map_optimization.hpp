@@ -142,6 +142,8 @@ class MapOptimization {
   std::vector<int> mapIds_;
   bool mapBuilt_ = false;
   const FrameView* view_ = nullptr;  // non-null while processFrameView runs
+  ll_scan_clouds scanDev_{};  // device copies left by downsampleCurrentScan (valid for the current frame)
+  bool scanDevValid_ = false;
 };
 
 }  // namespace lego_loam_b200

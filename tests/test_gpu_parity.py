@@ -75,6 +75,51 @@ def test_voxel_downsample_single_launch_path(abi, orc, single_problem):
             assert h.launch_count - launches0 >= 7  # (the membership variant is the seven-launch pipeline)
 
 
+def test_downsample_scan_parity(abi, orc, synth, single_problem, single_maps):
+    """f-2 as one call (ll_downsample_scan): the six clouds of downsampleCurrentScan (:1234-1267) bit-equal to the
+    oracle's VoxelGrid chain, also while a local map is pending, also with empty clouds; the device copies it leaves
+    feed ll_scan2map_dev to the same bits as the host clouds."""
+    from conftest import SMALL_WORLD
+    world = synth.World(seed=1, **SMALL_WORLD)  # single_problem's world: a raw scan at its query pose
+    raw = synth.scan(world, single_problem["gt"], seed=77)
+    z = np.zeros((0, 4), np.float32)
+    cs, sl, ol = (np.ascontiguousarray(raw[k][:, :4], np.float32) for k in ("corner_scan", "surf_last", "outlier_last"))
+    full = [cs[::2].copy(), sl, cs, sl[1::2].copy(), ol]  # corner_last, surf_last, corner_scan, surf_scan, outlier_last
+    prm = abi.default_params()
+
+    def oracle_chain(clouds):
+        leaf = (prm.corner_leaf, prm.surf_leaf, prm.corner_leaf, prm.surf_leaf, prm.surf_leaf)
+        ds = [orc.voxel_downsample(c, l)[0] if len(c) else z for c, l in zip(clouds, leaf)]
+        total = np.concatenate([ds[1], ds[4]])
+        ds.append(orc.voxel_downsample(total, prm.surf_leaf)[0] if len(total) else z)
+        return ds
+
+    d = single_problem
+    kf = d["keyframes"]
+    with abi.Handle(upstream_params(abi)) as h:
+        for i, f in enumerate(kf):
+            h.add_keyframe(i, f["corner_scan"], f["surf_last_ds"], f["outlier_last_ds"], d["key_poses"][i])
+        for case, clouds in enumerate((full, [full[0], z, full[2], full[3], z], [z, full[1], z, z, z], [z] * 5,
+                                       [full[0][:1], full[1][:3], full[2], full[3], full[4][:2]])):
+            if case == 1:
+                h.build_local_map(list(range(len(kf))))  # from here on a map is pending while the filters run
+            outs, dev = h.downsample_scan(clouds)
+            want = oracle_chain(clouds)
+            for k in range(6):
+                assert dev.n_ds[k] == len(want[k]) and dev.flags[k] == 0, (case, k)
+                assert np.array_equal(bits(outs[k]), bits(want[k])), (case, k)
+            _, dev2 = h.downsample_scan(clouds, want_host=False)
+            assert list(dev2.n_ds) == list(dev.n_ds)
+        # the device copies are what the scan consumes: same result bits as the host clouds
+        h.build_local_map(list(range(len(kf))))
+        outs, dev = h.downsample_scan(full)
+        pose_d, res_d = h.scan2map_dev(dev.d_ds[2], dev.n_ds[2], dev.d_ds[5], dev.n_ds[5], d["prior"])
+        h.build_local_map(list(range(len(kf))))
+        pose_h, res_h = h.scan2map(outs[2], outs[5], d["prior"])
+        assert res_d.status == 0 and res_d.sel_num == res_h.sel_num
+        assert np.array_equal(bits(pose_d), bits(pose_h))
+
+
 def test_voxel_downsample_edge_cases(abi, orc):
     rng = np.random.default_rng(0)
     with abi.Handle() as h:
