@@ -93,7 +93,7 @@ struct ll_handle_s {
   cudaEvent_t pin_evt[kPinSlots] = {};
   int pin_cur = 0;
 
-  MapSlot slot[3];
+  MapSlot slot[4];  // 0 / 1: the corner / surf local map; 2, 3: VoxelGrid of one or two stand-alone clouds
   bool map_ready = false;
   // the search grids of the current local map are still to be built: either inside the persistent scan kernel
   // (grid_inline.cuh) or, for any other consumer, by run_grid_build()
@@ -542,15 +542,17 @@ int run_map_pipeline(ll_handle h, int sa, int sb, const SegList& L, float leaf_a
     h->grid_deferred = true;
     return LL_OK;
   }
-  // A single cloud (ll_voxel_downsample) of moderate size: the in-kernel pipeline as one cooperative launch.
+  // One or two clouds without search grids (ll_voxel_downsample, ll_downsample_scan) of moderate size: the in-kernel
+  // pipeline as one cooperative launch.
   static const bool no_inline_voxel = std::getenv("LLB200_NO_INLINE_VOXEL") != nullptr;
-  if (!no_inline_voxel && sb < 0 && !build_grid && !want_member && ds_a && h->slot[sa].n_raw > 0 &&
-      pts <= kInlineMapMaxPoints && fits_sms) {
+  if (!no_inline_voxel && !build_grid && !want_member && ds_a && (sb < 0 || ds_b) && pts > 0 && pts <= kInlineMapMaxPoints &&
+      fits_sms) {
     LL_TRY(seglist_to_device(h));
     MapBatch B = make_map_batch(h, false);
-    B.m[1].downsample = 0;  // (the second entry mirrors the first with no points: it must not take part)
+    if (sb < 0) B.m[1].downsample = 0;  // (the second entry mirrors the first with no points: it must not take part)
     const long t4 = 4L * LM_THREADS;
-    int blocks = (int)std::min<long>(h->num_sms, std::max<long>((h->slot[sa].n_raw + t4 - 1) / t4, (long)h->n_jobs));
+    const long tiles4 = (h->slot[sa].n_raw + t4 - 1) / t4 + (sb >= 0 ? (h->slot[sb].n_raw + t4 - 1) / t4 : 0);
+    int blocks = (int)std::min<long>(h->num_sms, std::max<long>(tiles4, (long)h->n_jobs));
     blocks = std::max(blocks, 1);
     unsigned* bar = h->d_barriers + (h->scan_seq % kBarrierSlots);
     unsigned* bar_clear = h->d_barriers + ((h->scan_seq + kBarrierSlots / 2) % kBarrierSlots);
@@ -1374,6 +1376,7 @@ int ll_downsample_scan(ll_handle h, const void* const clouds[5], const size_t n[
     h->res_pin_bytes = newcap;
   }
   LL_TRY(ensure_slot(h, 2, max_n, false));
+  LL_TRY(ensure_slot(h, 3, std::max(n[2], n[3]), false));
   float4* const buf = h->scan_buf;
   if (raw_total) {  // the five clouds, packed, in one copy
     LL_TRY(pinned_acquire(h, raw_pts * sizeof(float4)));
@@ -1381,25 +1384,48 @@ int ll_downsample_scan(ll_handle h, const void* const clouds[5], const size_t n[
     LL_CUDA(h, cudaMemcpyAsync(buf, h->pinned, raw_pts * sizeof(float4), cudaMemcpyHostToDevice, h->stream));
     LL_TRY(pinned_release(h));
   }
-  MapSlot& S = h->slot[2];
   uint8_t* const pin = h->res_pin;
   std::memset(pin, 0, 6 * kHead);
-  // One VoxelGrid over `L` (n_in points) into region k; its MapState follows it into the pinned block.
-  auto filter = [&](int k, const SegList& L, size_t n_in) -> int {
-    if (n_in == 0) return LL_OK;
-    float4* const keep = S.ds;
-    S.ds = buf + off_ds[k];
-    S.n_raw = (int)n_in;
-    const int rc = run_map_pipeline(h, 2, -1, L, leaf[k], leaf[k], 1, 1, false, false);
-    S.ds = keep;
+  // VoxelGrid of one cloud (kb < 0) or of two clouds in the same launch, described by `L` (map 0 -> region ka,
+  // map 1 -> region kb); each MapState follows its cloud into the pinned block.
+  auto filter = [&](int ka, size_t na, int kb, size_t nb, const SegList& L) -> int {
+    if (na == 0 && kb >= 0) {  // only the second cloud has points: run it alone
+      ka = kb; na = nb; kb = -1; nb = 0;
+    }
+    if (na == 0) return LL_OK;
+    if (nb == 0) kb = -1;
+    MapSlot &SA = h->slot[2], &SB = h->slot[3];
+    float4* const keep_a = SA.ds;
+    float4* const keep_b = SB.ds;
+    SA.ds = buf + off_ds[ka];
+    SA.n_raw = (int)na;
+    if (kb >= 0) {
+      SB.ds = buf + off_ds[kb];
+      SB.n_raw = (int)nb;
+    }
+    const int rc = run_map_pipeline(h, 2, kb >= 0 ? 3 : -1, L, leaf[ka], kb >= 0 ? leaf[kb] : leaf[ka], 1, 1, false, false);
+    SA.ds = keep_a;
+    SB.ds = keep_b;
     if (rc != LL_OK) return rc;
-    LL_CUDA(h, cudaMemcpyAsync(pin + k * kHead, S.st(), sizeof(MapState), cudaMemcpyDeviceToHost, h->stream));
+    LL_CUDA(h, cudaMemcpyAsync(pin + ka * kHead, SA.st(), sizeof(MapState), cudaMemcpyDeviceToHost, h->stream));
+    if (kb >= 0) LL_CUDA(h, cudaMemcpyAsync(pin + kb * kHead, SB.st(), sizeof(MapState), cudaMemcpyDeviceToHost, h->stream));
     return LL_OK;
   };
-  for (int k = 0; k < 5; ++k) {
+  // Clouds of like size share a launch (its length is set by the larger one): the two surf clouds, the two corner
+  // clouds, the outliers alone.
+  auto pair = [&](int ka, int kb) -> int {
     SegList L;
-    L.add(buf + off_raw[k], (int)n[k], 0, 0, nullptr);
-    LL_TRY(filter(k, L, n[k]));
+    const bool only_b = n[ka] == 0;
+    L.add(buf + off_raw[ka], (int)n[ka], 0, 0, nullptr);
+    L.add(buf + off_raw[kb], (int)n[kb], 0, only_b ? 0 : 1, nullptr);
+    return filter(ka, n[ka], kb, n[kb], L);
+  };
+  LL_TRY(pair(1, 3));
+  LL_TRY(pair(0, 2));
+  {
+    SegList L;
+    L.add(buf + off_raw[4], (int)n[4], 0, 0, nullptr);
+    LL_TRY(filter(4, n[4], -1, 0, L));
   }
   float4* const pin_pts = reinterpret_cast<float4*>(pin + 6 * kHead);
   const bool speculative = out && ds_pts * sizeof(float4) <= 2 * kSpeculativeD2HBytes;
@@ -1412,7 +1438,7 @@ int ll_downsample_scan(ll_handle h, const void* const clouds[5], const size_t n[
     SegList L;
     L.add(buf + off_ds[1], (int)dev->n_ds[1], 0, 0, nullptr);
     L.add(buf + off_ds[4], (int)dev->n_ds[4], (int)dev->n_ds[1], 0, nullptr);
-    LL_TRY(filter(5, L, dev->n_ds[1] + dev->n_ds[4]));
+    LL_TRY(filter(5, dev->n_ds[1] + dev->n_ds[4], -1, 0, L));
   }
   if (speculative) {
     LL_CUDA(h, cudaMemcpyAsync(pin_pts + (off_ds[5] - off_ds[0]), buf + off_ds[5], pad(cap_ds[5]) * sizeof(float4), cudaMemcpyDeviceToHost, h->stream));
