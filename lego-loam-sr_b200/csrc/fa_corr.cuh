@@ -5,9 +5,9 @@
 //   * TransformToStart (de-skew by the fraction of the sweep stored behind the decimal point of `intensity`);
 //   * every fifth iteration: the exact nearest neighbour in laserCloud{Corner,Surf}Last (what kdtree*Last.nearestKSearch(.,1)
 //     returns) — the clouds hold a few thousand points, so the lanes simply stride over all of them and a redux.sync
-//     pair picks the minimum by (d2, index); the ring-window scans around it (+-2.5 scan lines, by the integer part of
-//     `intensity`) are inherently ordered (strict '<' with break) and run on lane 0 exactly as written in the
-//     reference, including the forward bound by the QUERY count (:1599, :1742 — an upstream quirk, clamped to the cloud);
+//     pair picks the minimum by (d2, index); the ring-window walks around it (+-2.5 scan lines, by the integer part of
+//     `intensity`; ordered: strict '<' with break) advance 32 points per step (fa_window_scan), with the reference's
+//     forward bound by the QUERY count (:1599, :1742 — an upstream quirk, clamped to the cloud);
 //   * the point-to-line / point-to-plane residual, weight and keep test of the (laserCloudOri, coeffSel) pair.
 // Arithmetic follows DESIGN.md §3: -fmad=false, unqualified cos / sin / sqrt / fabs on floats are the double functions.
 #pragma once
@@ -59,6 +59,63 @@ __device__ __forceinline__ float fa_sqdist(const float4 a, const float4 p) {
   return (a.x - p.x) * (a.x - p.x) + (a.y - p.y) * (a.y - p.y) + (a.z - p.z) * (a.z - p.z);
 }
 
+// One direction of the ring-window walk around the nearest neighbour (forward :1599-1616 / :1742-1762, backward
+// :1617-1633 / :1764-1784). The reference walks the cloud point by point, stops at the first point more than 2.5 scan
+// lines away, and keeps the first strict minimum per category; the running minima carry over from the forward to the
+// backward walk. The same result in warp-wide steps: 32 points per step in walking order, a ballot finds the first
+// stopping point, every lane keeps its own first strict minimum, and the warp takes the minimum by (d2, walking
+// index) — the first of the smallest, which replaces the carried minimum only if strictly smaller.
+template <bool kForward>
+__device__ __forceinline__ void fa_window_scan(const FaArgs& A, const float4 sel, const int closest, const int scan,
+                                               const int lane, float& d2min, int& min2, float& d3min, int& min3) {
+  // forward bound by the QUERY count (:1599, :1742 — an upstream quirk, clamped to the cloud)
+  const int count = kForward ? min(A.nq, A.n_last) - (closest + 1) : closest;
+  uint32_t bd2 = 0x7f800000u, be2 = 0xffffffffu, bd3 = 0x7f800000u, be3 = 0xffffffffu;
+  for (int base = 0; base < count; base += 32) {  // (warp-uniform)
+    const int e = base + lane;
+    const bool in = e < count;
+    bool stop = false;
+    float d = 0.f;
+    int sj = 0;
+    if (in) {
+      const float4 m = __ldg(A.last + (kForward ? closest + 1 + e : closest - 1 - e));
+      sj = (int)m.w;
+      stop = kForward ? ((double)sj > (double)scan + 2.5) : ((double)sj < (double)scan - 2.5);
+      d = fa_sqdist(m, sel);
+    }
+    const unsigned stops = __ballot_sync(0xffffffffu, stop);
+    const int first_stop = stops ? __ffs((int)stops) - 1 : 32;
+    if (in && lane < first_stop) {
+      const uint32_t db = __float_as_uint(d);  // d >= +0, or NaN whose bit patterns are above +inf and never win
+      bool c2, c3;
+      if (A.which == 0) {  // corner: the second line point lies on ANOTHER scan line
+        c2 = kForward ? sj > scan : sj < scan;
+        c3 = false;
+      } else {             // surf: the same or the nearer-side line -> second point, the far side -> third point
+        c2 = kForward ? sj <= scan : sj >= scan;
+        c3 = !c2;
+      }
+      if (c2 && db < bd2) { bd2 = db; be2 = (uint32_t)e; }
+      if (c3 && db < bd3) { bd3 = db; be3 = (uint32_t)e; }
+    }
+    if (stops) break;
+  }
+  const uint32_t m2 = __reduce_min_sync(0xffffffffu, bd2);
+  const uint32_t e2 = __reduce_min_sync(0xffffffffu, bd2 == m2 ? be2 : 0xffffffffu);
+  if (e2 != 0xffffffffu && __uint_as_float(m2) < d2min) {
+    d2min = __uint_as_float(m2);
+    min2 = kForward ? closest + 1 + (int)e2 : closest - 1 - (int)e2;
+  }
+  if (A.which != 0) {
+    const uint32_t m3 = __reduce_min_sync(0xffffffffu, bd3);
+    const uint32_t e3 = __reduce_min_sync(0xffffffffu, bd3 == m3 ? be3 : 0xffffffffu);
+    if (e3 != 0xffffffffu && __uint_as_float(m3) < d3min) {
+      d3min = __uint_as_float(m3);
+      min3 = kForward ? closest + 1 + (int)e3 : closest - 1 - (int)e3;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(FA_THREADS) fa_corr_kernel(const __grid_constant__ FaArgs A) {
   const int lane = threadIdx.x & 31;
   const int i = blockIdx.x * (FA_THREADS / 32) + (threadIdx.x >> 5);
@@ -82,39 +139,14 @@ __global__ void __launch_bounds__(FA_THREADS) fa_corr_kernel(const __grid_consta
     }
     const uint32_t md = __reduce_min_sync(0xffffffffu, bd);
     const uint32_t mj = __reduce_min_sync(0xffffffffu, bd == md ? bj : 0xffffffffu);
+    if (mj != 0xffffffffu && __uint_as_float(md) < A.dist_sqr) {  // (warp-uniform)
+      closest = (int)mj;
+      const int scan = (int)__ldg(A.last + closest).w;
+      float d2min = A.dist_sqr, d3min = A.dist_sqr;
+      fa_window_scan<true>(A, sel, closest, scan, lane, d2min, min2, d3min, min3);
+      fa_window_scan<false>(A, sel, closest, scan, lane, d2min, min2, d3min, min3);
+    }
     if (lane == 0) {
-      if (mj != 0xffffffffu && __uint_as_float(md) < A.dist_sqr) {
-        closest = (int)mj;
-        const int scan = (int)__ldg(A.last + closest).w;
-        float d2min = A.dist_sqr, d3min = A.dist_sqr;
-        const int fwd_end = min(A.nq, A.n_last);
-        for (int j = closest + 1; j < fwd_end; ++j) {
-          const float4 m = __ldg(A.last + j);
-          const int sj = (int)m.w;
-          if ((double)sj > (double)scan + 2.5) break;
-          const float d = fa_sqdist(m, sel);
-          if (A.which == 0) {
-            if (sj > scan && d < d2min) { d2min = d; min2 = j; }
-          } else if (sj <= scan) {
-            if (d < d2min) { d2min = d; min2 = j; }
-          } else if (d < d3min) {
-            d3min = d; min3 = j;
-          }
-        }
-        for (int j = closest - 1; j >= 0; --j) {
-          const float4 m = __ldg(A.last + j);
-          const int sj = (int)m.w;
-          if ((double)sj < (double)scan - 2.5) break;
-          const float d = fa_sqdist(m, sel);
-          if (A.which == 0) {
-            if (sj < scan && d < d2min) { d2min = d; min2 = j; }
-          } else if (sj >= scan) {
-            if (d < d2min) { d2min = d; min2 = j; }
-          } else if (d < d3min) {
-            d3min = d; min3 = j;
-          }
-        }
-      }
       A.ind1[i] = closest;
       A.ind2[i] = min2;
       if (A.ind3) A.ind3[i] = min3;

@@ -672,6 +672,29 @@ def test_fa_correspondences_parity(abi, orc, synth):
                 ind_d, ind_o = gd[:3], go[:3]
                 if it < 5:  # (from iteration 5 on the weight 1 - 1.8 |d| drops most pairs of this unconverged guess)
                     assert gd[4].sum() > len(q) // 4
+        # the walks are ORDERED (first strict minimum, stop at the first far scan line): exact ties between duplicated
+        # points and a cloud that is not sorted by scan line must come out like the point-by-point walk
+        rng = np.random.default_rng(11)
+        dup = last.copy()
+        dup[1::3] = dup[0:len(dup) - 1:3][:len(dup[1::3])]           # every third point twice: equal distances
+        mixed = dup.copy()
+        blocks = np.array_split(np.arange(len(mixed)), 40)
+        mixed = mixed[np.concatenate([blocks[k] for k in rng.permutation(40)])]  # scan lines interleaved in 40 runs
+        for cloud in (dup, mixed):
+            with abi.Handle(abi.default_params()) as h:
+                h.fa_set_last(which, cloud)
+                gd = h.fa_find_correspondences(which, q, tc, 0)
+                go = orc.fa_correspondences(which, q, cloud, tc, 0)
+                for name, a, b in zip(("ind1", "ind2", "ind3", "coeff", "keep"), gd, go):
+                    if which == 0 and name == "ind3":
+                        continue
+                    if name == "coeff":  # (a plane through a duplicated point is 0/0: NaN on both sides, payloads differ)
+                        nan = np.isnan(a)
+                        assert np.array_equal(nan, np.isnan(b)), (which, name)
+                        a, b = np.where(nan, np.float32(0), a), np.where(nan, np.float32(0), b)
+                    assert np.array_equal(bits(a) if a.dtype == np.float32 else a, bits(b) if b.dtype == np.float32 else b), \
+                        (which, name)
+                assert (gd[1] >= 0).sum() > len(q) // 8
         # degenerate inputs: an empty / tiny previous cloud gives no correspondences and no error
         with abi.Handle(abi.default_params()) as h:
             h.fa_set_last(which, last[:0])
