@@ -1548,27 +1548,33 @@ int ll_solve_normal_eq(ll_handle h, const float* rows6, const float* b, size_t n
   if (m == 0 || (dof_mask & ~63) || !x_out || !matP_inout || !is_degenerate_inout || (n && (!rows6 || !b)))
     return fail(h, LL_ERR_INVALID_ARG, "bad dof_mask / NULL argument");
   LL_CUDA(h, cudaSetDevice(h->device));
-  LL_TRY(ensure_tmp(h, 0, n * 24));
-  LL_TRY(ensure_tmp(h, 1, n * 4));
-  LL_TRY(ensure_tmp(h, 2, 256));
-  uint8_t* small = static_cast<uint8_t*>(h->d_tmp[2]);
-  float* d_x = reinterpret_cast<float*>(small);
-  float* d_P = reinterpret_cast<float*>(small + 32);
-  int* d_deg = reinterpret_cast<int*>(small + 32 + 144);
+  // One block up through a pinned slot, [x (32 B) | matP (144 B) | isDegenerate | pad to 256 | rows | b], and its first
+  // 256 bytes back: two copies and one synchronisation per solve.
+  constexpr size_t kHead = 256;
+  const size_t bytes = kHead + n * 28;
+  LL_TRY(ensure_tmp(h, 0, bytes));
+  LL_TRY(pinned_acquire(h, bytes));
+  uint8_t* const pin = h->pinned;
+  std::memset(pin, 0, kHead);
+  std::memcpy(pin + 32, matP_inout, sizeof(float) * m * m);
+  std::memcpy(pin + 32 + 144, is_degenerate_inout, sizeof(int));
   if (n) {
-    LL_CUDA(h, cudaMemcpyAsync(h->d_tmp[0], rows6, n * 24, cudaMemcpyHostToDevice, h->stream));
-    LL_CUDA(h, cudaMemcpyAsync(h->d_tmp[1], b, n * 4, cudaMemcpyHostToDevice, h->stream));
+    std::memcpy(pin + kHead, rows6, n * 24);
+    std::memcpy(pin + kHead + n * 24, b, n * 4);
   }
-  LL_CUDA(h, cudaMemcpyAsync(d_P, matP_inout, sizeof(float) * m * m, cudaMemcpyHostToDevice, h->stream));
-  LL_CUDA(h, cudaMemcpyAsync(d_deg, is_degenerate_inout, sizeof(int), cudaMemcpyHostToDevice, h->stream));
-  normal_eq_kernel<<<1, LM_THREADS, 0, h->stream>>>(static_cast<const float*>(h->d_tmp[0]),
-                                                    static_cast<const float*>(h->d_tmp[1]), (int)n, dof_mask, iter,
-                                                    eig_thresh, h->prm.eigen_mode, d_x, d_P, d_deg);
+  uint8_t* const d = static_cast<uint8_t*>(h->d_tmp[0]);
+  LL_CUDA(h, cudaMemcpyAsync(d, pin, bytes, cudaMemcpyHostToDevice, h->stream));
+  normal_eq_kernel<<<1, LM_THREADS, 0, h->stream>>>(reinterpret_cast<const float*>(d + kHead),
+                                                    reinterpret_cast<const float*>(d + kHead + n * 24), (int)n, dof_mask, iter,
+                                                    eig_thresh, h->prm.eigen_mode, reinterpret_cast<float*>(d),
+                                                    reinterpret_cast<float*>(d + 32), reinterpret_cast<int*>(d + 32 + 144));
   LL_LAUNCHED(h);
-  LL_CUDA(h, cudaMemcpyAsync(x_out, d_x, sizeof(float) * m, cudaMemcpyDeviceToHost, h->stream));
-  LL_CUDA(h, cudaMemcpyAsync(matP_inout, d_P, sizeof(float) * m * m, cudaMemcpyDeviceToHost, h->stream));
-  LL_CUDA(h, cudaMemcpyAsync(is_degenerate_inout, d_deg, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  LL_CUDA(h, cudaMemcpyAsync(pin, d, kHead, cudaMemcpyDeviceToHost, h->stream));
   LL_CUDA(h, cudaStreamSynchronize(h->stream));
+  std::memcpy(x_out, pin, sizeof(float) * m);
+  std::memcpy(matP_inout, pin + 32, sizeof(float) * m * m);
+  std::memcpy(is_degenerate_inout, pin + 32 + 144, sizeof(int));
+  LL_TRY(pinned_release(h));
   return LL_OK;
 }
 
@@ -1628,21 +1634,28 @@ int ll_fa_find_correspondences(ll_handle h, int which, const void* queries, size
   if (nq == 0) return LL_OK;
   if (!h->fa_last[which]) return fail(h, LL_ERR_STATE, "ll_fa_set_last has not been called for this cloud");
   LL_CUDA(h, cudaSetDevice(h->device));
-  LL_TRY(ensure_tmp(h, 0, nq * 16));  // queries
-  LL_TRY(ensure_tmp(h, 1, nq * 16));  // coeff
-  LL_TRY(ensure_tmp(h, 2, nq * 4));   // keep
-  LL_TRY(ensure_tmp(h, 3, nq * 12));  // ind1 | ind2 | ind3
-  LL_TRY(upload_points(h, static_cast<float4*>(h->d_tmp[0]), queries, nq, stride_bytes));
-  int* d_ind = static_cast<int*>(h->d_tmp[3]);
+  // One block each way through one pinned slot: up [queries | ind1 | ind2 | ind3 (reuse iterations only)], down
+  // [ind1 | ind2 | ind3 | keep | coeff] (search iterations) or just [keep | coeff]; one synchronisation.
   const bool search = iter_count % 5 == 0;
+  const size_t in_bytes = nq * 16 + (search ? 0 : nq * 12), out_bytes = nq * 32;
+  LL_TRY(ensure_tmp(h, 0, nq * 28));
+  LL_TRY(ensure_tmp(h, 3, out_bytes));
+  LL_TRY(pinned_acquire(h, out_bytes));
+  uint8_t* const pin = h->pinned;
+  pack_points(reinterpret_cast<float4*>(pin), queries, nq, stride_bytes);
   if (!search) {  // the indices found at the last multiple of five come back in
-    LL_CUDA(h, cudaMemcpyAsync(d_ind, ind1, nq * 4, cudaMemcpyHostToDevice, h->stream));
-    LL_CUDA(h, cudaMemcpyAsync(d_ind + nq, ind2, nq * 4, cudaMemcpyHostToDevice, h->stream));
-    if (ind3) LL_CUDA(h, cudaMemcpyAsync(d_ind + 2 * nq, ind3, nq * 4, cudaMemcpyHostToDevice, h->stream));
-    else LL_CUDA(h, cudaMemsetAsync(d_ind + 2 * nq, 0xff, nq * 4, h->stream));
+    int* pi = reinterpret_cast<int*>(pin + nq * 16);
+    std::memcpy(pi, ind1, nq * 4);
+    std::memcpy(pi + nq, ind2, nq * 4);
+    if (ind3) std::memcpy(pi + 2 * nq, ind3, nq * 4);
+    else std::memset(pi + 2 * nq, 0xff, nq * 4);
   }
+  uint8_t* const d_in = static_cast<uint8_t*>(h->d_tmp[0]);
+  uint8_t* const d_out = static_cast<uint8_t*>(h->d_tmp[3]);
+  LL_CUDA(h, cudaMemcpyAsync(d_in, pin, in_bytes, cudaMemcpyHostToDevice, h->stream));
+  int* d_ind = reinterpret_cast<int*>(search ? d_out : d_in + nq * 16);
   FaArgs A;
-  A.q = static_cast<const float4*>(h->d_tmp[0]);
+  A.q = reinterpret_cast<const float4*>(d_in);
   A.last = h->fa_last[which];
   A.nq = (int)nq;
   A.n_last = h->fa_n_last[which];
@@ -1653,19 +1666,23 @@ int ll_fa_find_correspondences(ll_handle h, int which, const void* queries, size
   A.ind1 = d_ind;
   A.ind2 = d_ind + nq;
   A.ind3 = d_ind + 2 * nq;
-  A.coeff = static_cast<float*>(h->d_tmp[1]);
-  A.keep = static_cast<int*>(h->d_tmp[2]);
+  A.keep = reinterpret_cast<int*>(d_out + nq * 12);
+  A.coeff = reinterpret_cast<float*>(d_out + nq * 16);
   const unsigned blocks = (unsigned)((nq + FA_THREADS / 32 - 1) / (FA_THREADS / 32));
   fa_corr_kernel<<<blocks, FA_THREADS, 0, h->stream>>>(A);
   LL_LAUNCHED(h);
-  if (search) {
-    LL_CUDA(h, cudaMemcpyAsync(ind1, d_ind, nq * 4, cudaMemcpyDeviceToHost, h->stream));
-    LL_CUDA(h, cudaMemcpyAsync(ind2, d_ind + nq, nq * 4, cudaMemcpyDeviceToHost, h->stream));
-    if (ind3) LL_CUDA(h, cudaMemcpyAsync(ind3, d_ind + 2 * nq, nq * 4, cudaMemcpyDeviceToHost, h->stream));
-  }
-  LL_CUDA(h, cudaMemcpyAsync(coeff4, h->d_tmp[1], nq * 16, cudaMemcpyDeviceToHost, h->stream));
-  LL_CUDA(h, cudaMemcpyAsync(keep, h->d_tmp[2], nq * 4, cudaMemcpyDeviceToHost, h->stream));
+  const size_t skip = search ? 0 : nq * 12;
+  LL_CUDA(h, cudaMemcpyAsync(pin + skip, d_out + skip, out_bytes - skip, cudaMemcpyDeviceToHost, h->stream));
   LL_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (search) {
+    const int* po = reinterpret_cast<const int*>(pin);
+    std::memcpy(ind1, po, nq * 4);
+    std::memcpy(ind2, po + nq, nq * 4);
+    if (ind3) std::memcpy(ind3, po + 2 * nq, nq * 4);
+  }
+  std::memcpy(keep, pin + nq * 12, nq * 4);
+  std::memcpy(coeff4, pin + nq * 16, nq * 16);
+  LL_TRY(pinned_release(h));
   return LL_OK;
 }
 
