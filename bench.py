@@ -382,6 +382,69 @@ def run_at_scale(device, peaks):
 
 
 # ----------------------------------------------------------------------------------------------- CPU arm
+def run_next_rows(with_cpu):
+    """SURVEY.md §8 "next" rows (not the headline): p50 microseconds per call, host buffers in, host results out, on one
+    synthetic VLP-16 frame; with_cpu adds the CPU restatement of the same call (the bench's CPU leg) beside each."""
+    from lego_loam_sr_b200 import abi, synth
+
+    def p50(fn, n=60, warm=8):
+        for _ in range(warm):
+            fn()
+        ts = []
+        for _ in range(n):
+            t0 = time.perf_counter()
+            fn()
+            ts.append(time.perf_counter() - t0)
+        return round(1e6 * statistics.median(ts), 1)
+
+    world = synth.World(seed=2)
+    gt = synth.trajectory(world, 2, step=0.7, seed=2)
+    raw = [synth.scan(world, gt[k], seed=1 + k) for k in range(2)]
+    cs, sl, ol = (np.ascontiguousarray(raw[0][k][:, :4], np.float32) for k in ("corner_scan", "surf_last", "outlier_last"))
+    clouds = [cs, sl, cs, sl, ol]
+    prm = abi.default_params()
+    leaf = (prm.corner_leaf, prm.surf_leaf, prm.corner_leaf, prm.surf_leaf, prm.surf_leaf)
+    tc = np.array([0.004, -0.006, 0.003, 0.05, -0.02, 0.30], np.float32)
+    out = {"unit": "us per call (p50), host buffers both ways"}
+    with abi.Handle(prm) as h:
+        ds = h.downsample_scan(clouds)[0]
+        out["f2_downsample_scan"] = {"points_in": [len(c) for c in clouds], "points_out": [len(d) for d in ds],
+                                     "gpu": p50(lambda: h.downsample_scan(clouds)),
+                                     "gpu_device_results": p50(lambda: h.downsample_scan(clouds, want_host=False))}
+        fa = {}
+        for which, name, cur, prev in ((0, "corner", ds[2], h.voxel_downsample(np.ascontiguousarray(raw[1]["corner_scan"][:, :4], np.float32), prm.corner_leaf, want_member=False)[0]),
+                                       (1, "surf", ds[1][::4].copy(), h.voxel_downsample(np.ascontiguousarray(raw[1]["surf_last"][:, :4], np.float32), prm.surf_leaf, want_member=False)[0])):
+            last = prev[np.argsort(prev[:, 3].astype(np.int32), kind="stable")]
+            h.fa_set_last(which, last)
+            ind = h.fa_find_correspondences(which, cur, tc, 0)[:3]
+            fa[name] = {"feature_points": len(cur), "last_points": len(last),
+                        "gpu_search_iteration": p50(lambda: h.fa_find_correspondences(which, cur, tc, 0)),
+                        "gpu_reuse_iteration": p50(lambda: h.fa_find_correspondences(which, cur, tc, 1, ind=ind)),
+                        "_inputs": (cur, last)}
+        out["f3_fa_correspondences"] = fa
+        rng = np.random.default_rng(0)
+        rows, b = rng.normal(0, 1, (1500, 6)).astype(np.float32), rng.normal(0, 0.05, 1500).astype(np.float32)
+        out["f1_solve_normal_eq"] = {"rows": 1500, "gpu_3dof": p50(lambda: h.solve_normal_eq(rows, b, 0b010101, 0, 10.0)),
+                                     "gpu_6dof": p50(lambda: h.solve_normal_eq(rows, b, 0b111111, 0, 10.0))}
+    if with_cpu:
+        import orc
+        orc.build()
+
+        def chain():
+            d = [orc.voxel_downsample(c, l)[0] for c, l in zip(clouds, leaf)]
+            orc.voxel_downsample(np.concatenate([d[1], d[4]]), prm.surf_leaf)
+        out["f2_downsample_scan"]["cpu"] = p50(chain, n=10, warm=2)
+        nf = orc.have_ref()
+        for which, name in ((0, "corner"), (1, "surf")):
+            cur, last = fa[name]["_inputs"]
+            fa[name]["cpu_search_iteration"] = p50(lambda: orc.fa_correspondences(which, cur, last, tc, 0, use_nanoflann=nf), n=10, warm=2)
+        out["f1_solve_normal_eq"]["cpu_3dof"] = p50(lambda: orc.solve_normal_eq(rows, b, 0b010101, 0, 10.0, 1), n=20, warm=2)
+        out["f1_solve_normal_eq"]["cpu_6dof"] = p50(lambda: orc.solve_normal_eq(rows, b, 0b111111, 0, 10.0, 1), n=20, warm=2)
+    for v in fa.values():
+        v.pop("_inputs", None)
+    return out
+
+
 def run_cpu(data, prefill, warmup, steps, budget_s):
     """The reference's CPU path (oracle restatement; k-NN = the reference's vendored nanoflann when oracle/_ref was
     built), single thread like the reference's _run_thread (mapOptmization.cpp:175). Times `steps` scans after
@@ -538,6 +601,11 @@ def main():
                        "resident_equals_e2e_pose": bool(np.array_equal(res["poses"], e2e["poses"]))}}
     if world == 1 and not args.no_at_scale:
         line["at_scale"] = run_at_scale(device, peaks)
+    if world == 1 and not args.no_at_scale:
+        try:
+            line["next_rows"] = run_next_rows(with_cpu=not args.no_cpu_baseline)
+        except Exception as e:  # (never lose the headline line to a side measurement)
+            line["next_rows"] = {"error": "%s: %s" % (type(e).__name__, e)}
     if world == 1 and not args.no_cpu_baseline:
         times, knn = run_cpu(data, prefill, 0, args.steps, budget_s=args.cpu_seconds)
         v = len(times) / sum(times)
