@@ -193,14 +193,16 @@ void MapOptimization::downsampleCurrentScan() {  // :1234-1267
     clouds[k] = in[k]->points.data();
     n[k] = in[k]->size();
   }
-  for (int k = 0; k < 6; ++k) {
+  for (int k = 0; k < 6; ++k) {  // landing buffers sized for the worst case (output = input); they only ever grow
     cap[k] = k < 5 ? n[k] : n[1] + n[4];
-    *res[k] = std::make_shared<PointCloud>();
-    (*res[k])->points.resize(cap[k]);
-    out[k] = (*res[k])->points.data();
+    if (scanLanding_[k].size() < cap[k]) scanLanding_[k].resize(cap[k] + cap[k] / 2);
+    out[k] = scanLanding_[k].data();
   }
   check(ll_downsample_scan(h_, clouds, n, sizeof(PointType), &scanDev_, out, cap, sizeof(PointType)), "ll_downsample_scan");
-  for (int k = 0; k < 6; ++k) (*res[k])->points.resize(scanDev_.n_ds[k]);
+  for (int k = 0; k < 6; ++k) {  // like filter(*cloudDS): the member clouds are reused, only the n_ds points are written
+    if (!*res[k] || res[k]->use_count() != 1) *res[k] = std::make_shared<PointCloud>();  // (never write into a caller's cloud)
+    (*res[k])->points.assign(scanLanding_[k].begin(), scanLanding_[k].begin() + (long)scanDev_.n_ds[k]);
+  }
   scanDevValid_ = true;
   laserCloudSurfTotalLast->clear();  // :1259-1260 (its downsampled form came out of the call above)
   *laserCloudSurfTotalLast += *laserCloudSurfLastDS;

@@ -144,6 +144,7 @@ class MapOptimization {
   const FrameView* view_ = nullptr;  // non-null while processFrameView runs
   ll_scan_clouds scanDev_{};  // device copies left by downsampleCurrentScan (valid for the current frame)
   bool scanDevValid_ = false;
+  std::vector<PointType> scanLanding_[6];  // host landing buffers of downsampleCurrentScan's six results
 };
 
 }  // namespace lego_loam_b200
