@@ -549,6 +549,16 @@ int run_map_pipeline(ll_handle h, int sa, int sb, const SegList& L, float leaf_a
       fits_sms) {
     LL_TRY(seglist_to_device(h));
     MapBatch B = make_map_batch(h, false);
+    static const bool no_small_voxel = std::getenv("LLB200_NO_SMALL_VOXEL") != nullptr;  // A/B switch for measurements
+    if (!no_small_voxel && h->slot[sa].n_raw <= VS_MAX && (sb < 0 || h->slot[sb].n_raw <= VS_MAX) && h->slot[sa].n_raw > 0 &&
+        (sb < 0 || h->slot[sb].n_raw > 0)) {
+      // small clouds: one block per cloud, everything in shared memory
+      LL_PROF(h, 3);
+      voxel_small_kernel<<<sb >= 0 ? 2 : 1, VS_THREADS, 0, h->stream>>>(B, h->d_segs, (int)L.segs.size());
+      LL_CUDA(h, cudaGetLastError());
+      LL_LAUNCHED(h);
+      return LL_OK;
+    }
     if (sb < 0) B.m[1].downsample = 0;  // (the second entry mirrors the first with no points: it must not take part)
     const long t4 = 4L * LM_THREADS;
     const long tiles4 = (h->slot[sa].n_raw + t4 - 1) / t4 + (sb >= 0 ? (h->slot[sb].n_raw + t4 - 1) / t4 : 0);

@@ -626,6 +626,157 @@ __device__ __forceinline__ void grid_build_inline(const MapBatch& B, unsigned* b
 
 // Rows a2-a3 alone (ll_voxel_downsample on a cloud of up to 2^20 points: downsampleCurrentScan's six filters): the same
 // in-kernel pipeline as the head of the scan kernel, as ONE cooperative launch instead of seven launches.
+// VoxelGrid of small clouds (<= VS_MAX points: the corner clouds and outliers of downsampleCurrentScan, the key poses
+// of extractSurroundingKeyFrames) entirely in one block's shared memory, one block per cloud: the multi-block
+// pipeline above is a chain of ~30 grid-wide round trips, which for a few hundred points is all it costs (27 us).
+// Same arithmetic, same order: bounding box of the finite points, PCL's voxel index, (voxel, original index) pairs
+// sorted — a bitonic network on the 64-bit composite, whose keys are unique, so the order is the stable one — and
+// one thread per voxel adding its points up in that order.
+constexpr int VS_THREADS = 512;
+constexpr int VS_MAX = 1024;
+
+__global__ void __launch_bounds__(VS_THREADS, 1) voxel_small_kernel(const __grid_constant__ MapBatch B,
+                                                                   const Segment* __restrict__ segs, int n_segs) {
+  const MapBuffers& M = B.m[blockIdx.x];
+  __shared__ float4 s_pts[VS_MAX];
+  __shared__ unsigned long long s_key[VS_MAX];
+  __shared__ int s_head_pos[VS_MAX + 1];
+  __shared__ MapState s_st;
+  __shared__ uint32_t s_warp_sum[VS_THREADS / 32];
+  __shared__ int s_valid;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = M.n_raw;
+  if (tid < (int)(sizeof(MapState) / 4)) reinterpret_cast<uint32_t*>(&s_st)[tid] = 0u;
+  if (tid == 0) s_valid = 0;
+  __syncthreads();
+  for (int sg = 0; sg < n_segs; ++sg) {  // a2 for this cloud's pieces (identity for clouds already in their frame)
+    const Segment& g = segs[sg];
+    if (g.map != (int)blockIdx.x) continue;
+    for (int i = tid; i < g.count; i += VS_THREADS) {
+      const float4 p = __ldg(g.src + i);
+      s_pts[g.dst_off + i] = g.identity ? p : rigid_transform(g.t, p);
+    }
+  }
+  __syncthreads();
+  {  // bounding box of the finite points (MapState encoding, see transform_minmax_kernel)
+    uint32_t lo[3] = {0u, 0u, 0u}, hi[3] = {0u, 0u, 0u};
+    int valid = 0;
+    for (int i = tid; i < n; i += VS_THREADS) {
+      const float4 q = s_pts[i];
+      if (finite3(q)) {
+        ++valid;
+        lo[0] = max(lo[0], ~float_to_ordered(q.x)); hi[0] = max(hi[0], float_to_ordered(q.x));
+        lo[1] = max(lo[1], ~float_to_ordered(q.y)); hi[1] = max(hi[1], float_to_ordered(q.y));
+        lo[2] = max(lo[2], ~float_to_ordered(q.z)); hi[2] = max(hi[2], float_to_ordered(q.z));
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      lo[a] = __reduce_max_sync(0xffffffffu, lo[a]);
+      hi[a] = __reduce_max_sync(0xffffffffu, hi[a]);
+    }
+    valid = __reduce_add_sync(0xffffffffu, valid);
+    if (lane == 0 && valid) {
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        atomicMax(&s_st.mm[a], lo[a]);
+        atomicMax(&s_st.mm[3 + a], hi[a]);
+      }
+      atomicAdd(&s_valid, valid);
+    }
+  }
+  __syncthreads();
+  const VoxelMeta v = voxel_meta(&s_st, M.inv_leaf);
+  const uint32_t sentinel = v.overflow ? (uint32_t)n : (uint32_t)v.total;
+  int N = 64;
+  while (N < n) N <<= 1;
+  {
+    const float inv = M.inv_leaf;
+    for (int i = tid; i < N; i += VS_THREADS) {
+      unsigned long long ck = 0xffffffffffffffffull;  // padding sorts behind everything
+      if (i < n) {
+        const float4 q = s_pts[i];
+        uint32_t key;
+        if (!finite3(q)) {
+          key = sentinel;  // behind every voxel, dropped (PCL skips non-finite points)
+        } else if (v.overflow) {
+          key = (uint32_t)i;  // PCL's "leaf size too small": the input passes through, every point its own voxel
+        } else {
+          const int i0 = (int)(floorf(q.x * inv) - (float)v.min_b[0]);
+          const int i1 = (int)(floorf(q.y * inv) - (float)v.min_b[1]);
+          const int i2 = (int)(floorf(q.z * inv) - (float)v.min_b[2]);
+          key = (uint32_t)(i0 * v.mul[0] + i1 * v.mul[1] + i2 * v.mul[2]);
+        }
+        ck = ((unsigned long long)key << 32) | (uint32_t)i;
+      }
+      s_key[i] = ck;
+    }
+  }
+  for (int k = 2; k <= N; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      __syncthreads();
+      for (int t = tid; t < (N >> 1); t += VS_THREADS) {
+        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        const int l = i | j;
+        const unsigned long long a = s_key[i], b = s_key[l];
+        const bool up = (i & k) == 0;
+        if ((a > b) == up) {
+          s_key[i] = b;
+          s_key[l] = a;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // segment heads -> output slots: every thread owns two consecutive sorted positions
+  const int n_valid = s_valid;  // sorted positions [0, n_valid) hold the finite points
+  bool head[2];
+  uint32_t cnt = 0;
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int pos = 2 * tid + k;
+    head[k] = pos < n_valid && (pos == 0 || (uint32_t)(s_key[pos] >> 32) != (uint32_t)(s_key[pos - 1] >> 32));
+    cnt += head[k] ? 1u : 0u;
+  }
+  uint32_t incl = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) s_warp_sum[warp] = incl;
+  __syncthreads();
+  uint32_t off = incl - cnt, total = 0;
+#pragma unroll
+  for (int w = 0; w < VS_THREADS / 32; ++w) {
+    const uint32_t c = s_warp_sum[w];
+    if (w < warp) off += c;
+    total += c;
+  }
+#pragma unroll
+  for (int k = 0; k < 2; ++k)
+    if (head[k]) s_head_pos[off++] = 2 * tid + k;
+  if (tid == 0) s_head_pos[total] = n_valid;
+  __syncthreads();
+  for (int slot = tid; slot < (int)total; slot += VS_THREADS) {  // the centroid: additions in sorted order
+    const int beg = s_head_pos[slot], end = s_head_pos[slot + 1];
+    float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
+    for (int jj = beg; jj < end; ++jj) {
+      const float4 q = s_pts[(uint32_t)s_key[jj]];
+      sx += q.x; sy += q.y; sz += q.z; si += q.w;
+    }
+    const float fc = (float)(end - beg);
+    M.ds[slot] = make_float4(sx / fc, sy / fc, sz / fc, si / fc);
+  }
+  if (tid == 0) {
+    s_st.n_raw = n;
+    s_st.n_ds = (int)total;
+    s_st.voxel_bits = sentinel == 0 ? 0 : 32 - __clz(sentinel);
+    s_st.voxel_overflow = v.overflow ? 1 : 0;
+    *M.st = s_st;
+  }
+}
+
 __global__ void __launch_bounds__(GI_THREADS, 1) voxel_inline_kernel(const __grid_constant__ MapBatch B,
                                                                      const Segment* segs, const BlockJob* jobs, int n_jobs,
                                                                      unsigned* barrier, unsigned* barrier_clear) {

@@ -63,7 +63,12 @@ def test_voxel_downsample_single_launch_path(abi, orc, single_problem):
     rng = np.random.default_rng(3)
     with_nan = big[:20000].copy()
     with_nan[rng.choice(len(with_nan), 40, replace=False), 2] = np.nan
-    cases = [(big, 0.4), (big, 0.2), (big[:1], 0.4), (big[:37], 1.0), (with_nan, 0.4), (big[:3000], 1e-4)]
+    all_nan = np.full((5, 4), np.nan, np.float32)
+    one_voxel = np.tile(big[:1], (900, 1)) + np.float32(1e-3) * rng.random((900, 4)).astype(np.float32)
+    cases = [(big, 0.4), (big, 0.2), (big[:1], 0.4), (big[:37], 1.0), (with_nan, 0.4), (big[:3000], 1e-4),
+             # <= 1024 points: the one-block shared-memory kernel (voxel_small_kernel)
+             (big[:1024], 0.4), (big[:1025], 0.4), (big[5000:5700], 0.2), (with_nan[:1000], 0.4), (big[:900], 1e-4),
+             (all_nan, 0.4), (one_voxel, 2.0), (big[:65], 0.4), (big[:64], 0.4)]
     with abi.Handle(abi.default_params()) as h:
         for cloud, leaf in cases:
             out, _, flags = h.voxel_downsample(cloud, leaf, want_member=False)
