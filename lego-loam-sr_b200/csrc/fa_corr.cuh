@@ -126,8 +126,7 @@ __global__ void __launch_bounds__(FA_THREADS) fa_corr_kernel(const __grid_consta
     // exact 1-NN: distance as nanoflann's L2_Simple_Adaptor (((dx^2) + dy^2) + dz^2), ties to the lowest index
     uint32_t bd = 0x7f800000u;  // +inf
     uint32_t bj = 0xffffffffu;
-    for (int j = lane; j < A.n_last; j += 32) {
-      const float4 m = __ldg(A.last + j);
+    auto consider = [&](const float4 m, const int j) {
       float df = sel.x - m.x;
       float d = df * df;
       df = sel.y - m.y;
@@ -136,7 +135,16 @@ __global__ void __launch_bounds__(FA_THREADS) fa_corr_kernel(const __grid_consta
       d += df * df;
       const uint32_t db = __float_as_uint(d);
       if (db < bd) { bd = db; bj = (uint32_t)j; }  // (NaN distances have bit patterns above +inf and never win)
+    };
+    int j = lane;
+    for (; j + 96 < A.n_last; j += 128) {  // four loads in flight, candidates taken in ascending index order
+      const float4 m0 = __ldg(A.last + j), m1 = __ldg(A.last + j + 32), m2 = __ldg(A.last + j + 64), m3 = __ldg(A.last + j + 96);
+      consider(m0, j);
+      consider(m1, j + 32);
+      consider(m2, j + 64);
+      consider(m3, j + 96);
     }
+    for (; j < A.n_last; j += 32) consider(__ldg(A.last + j), j);
     const uint32_t md = __reduce_min_sync(0xffffffffu, bd);
     const uint32_t mj = __reduce_min_sync(0xffffffffu, bd == md ? bj : 0xffffffffu);
     if (mj != 0xffffffffu && __uint_as_float(md) < A.dist_sqr) {  // (warp-uniform)
