@@ -7,6 +7,8 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 abi = importlib.import_module("lego-loam-sr_b200.abi")
 synth = importlib.import_module("lego-loam-sr_b200.synth")
+if os.environ.get("LLB200_LIB"):  # A/B against another build of the library
+    abi.LIB_PATH = os.environ["LLB200_LIB"]
 import orc
 
 def p50(fn, n=100, warm=10):
