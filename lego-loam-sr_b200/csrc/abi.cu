@@ -1387,6 +1387,8 @@ int ll_downsample_scan(ll_handle h, const void* const clouds[5], const size_t n[
   }
   LL_TRY(ensure_slot(h, 2, max_n, false));
   LL_TRY(ensure_slot(h, 3, std::max(n[2], n[3]), false));
+  // a keyframe prefetch still reading the previous call's device clouds on the copy stream finishes first
+  if (h->prefetched_id >= 0) LL_CUDA(h, cudaStreamWaitEvent(h->stream, h->kf_evt, 0));
   float4* const buf = h->scan_buf;
   if (raw_total) {  // the five clouds, packed, in one copy
     LL_TRY(pinned_acquire(h, raw_pts * sizeof(float4)));
