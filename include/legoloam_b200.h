@@ -77,7 +77,10 @@ typedef struct {
 
 /* What scan2MapOptimization leaves behind (mapOptmization.cpp:1602-1607 and members). */
 typedef struct {
-  int   status;        /* 0 = optimised; 1 = skipped by the map-size guard (:1573), pose unchanged */
+  int   status;        /* 0 = optimised; 1 = skipped by the map-size guard (:1573), pose unchanged; 2 = NOT registered
+                          because the 1 m search grid over the map's bounding box exceeds the cell budget (2^24 cells,
+                          flags bit 2) — the reference's KD-tree has no such limit, so callers must treat 2 as a failure
+                          of this library, not as the reference's skip (the C++ mirror counts and reports it) */
   int   iter_num;      /* iterations executed (localInfo.x) */
   float min_lambda;    /* smallest eigenvalue of AtA at iteration 0 (localInfo.y) */
   float cf_mean;       /* mean |residual| of the last iteration (localInfo.z) */
@@ -123,14 +126,27 @@ int ll_add_keyframe_dev(ll_handle h, int id, const void* d_corner, size_t n_corn
 /* Optional overlap of the keyframe upload with the scan in flight: the three clouds saveKeyFramesAndFactor will store
  * (:1744-1752) are inputs of the frame, only their pose comes out of scan2MapOptimization. Called between
  * ll_scan2map_async and ll_scan2map_wait, this packs and uploads them on the handle's copy stream while the scan
- * kernel runs; the following ll_add_keyframe with the same id then only attaches the pose (its cloud arguments are
- * ignored). Without it ll_add_keyframe uploads as before. */
+ * kernel runs; the following ll_add_keyframe with the same id AND the same three point counts then only attaches the
+ * pose (its cloud pointers are not read again); with different counts the prefetch is dropped and the clouds passed
+ * to ll_add_keyframe are stored. A second prefetch before the add replaces the first (its block is reclaimed).
+ * Without a prefetch ll_add_keyframe uploads as before.
+ * _dev variant: the device clouds are copied on the handle's COPY stream, which is not ordered after the stream that
+ * produced them — they must be complete when the call is made (true for ll_downsample_scan's results, which
+ * synchronises before it returns; a caller with its own producer stream synchronises it first). */
 int ll_prefetch_keyframe(ll_handle h, int id, const void* corner, size_t n_corner, const void* surf, size_t n_surf,
                          const void* outlier, size_t n_outlier, size_t stride_bytes);
 int ll_prefetch_keyframe_dev(ll_handle h, int id, const void* d_corner, size_t n_corner, const void* d_surf, size_t n_surf,
                              const void* d_outlier, size_t n_outlier);
 /* correctPoses (mapOptmization.cpp:1757-1785) */
 int ll_set_keyframe_pose(ll_handle h, int id, const float pose6[6]);
+/* Memory management of the store. The reference keeps every keyframe cloud for the whole run (:1750-1752); on the
+ * device that is ~240 KB per VLP-16 keyframe, 256-byte-aligned blocks in 256 MiB slabs that only grow. A caller that
+ * knows a keyframe will not be listed in ll_build_local_map again (e.g. it left the sliding window and loop closure
+ * is off) may remove it: its block goes to a free list and is reused by later keyframes (first fit). Re-adding an
+ * existing id and dropping an unattached prefetch reclaim their blocks the same way. ll_get_memory_info reports the
+ * number of stored keyframes, the arena bytes handed out so far and the bytes waiting in the free list. */
+int ll_remove_keyframe(ll_handle h, int id);
+int ll_get_memory_info(ll_handle h, size_t* keyframes, size_t* arena_bytes, size_t* free_list_bytes);
 
 /* ---- a1: extractSurroundingKeyFrames tail (mapOptmization.cpp:1147-1151 / :1218-1231):
  * transform the listed keyframes by their poses, concatenate (per keyframe corner | surf, outlier),

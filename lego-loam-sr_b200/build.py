@@ -59,7 +59,7 @@ def build_host(force=False):
         return HOST_LIB
     cxx = os.environ.get("CXX") or shutil.which("g++") or "g++"
     cmd = [cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-I", os.path.join(ROOT, "include"), "-o", HOST_LIB] + cpps + \
-          ["-L", LIB_DIR, "-llegoloam_b200", "-Wl,-rpath,$ORIGIN"]
+          ["-L", LIB_DIR, "-llegoloam_b200", "-Wl,-rpath,$ORIGIN", "-pthread"]
     subprocess.check_call(cmd, stdout=sys.stderr)  # (bench.py prints exactly one line on stdout)
     return HOST_LIB
 

@@ -45,6 +45,8 @@ struct Keyframe {
   float pose[6] = {0, 0, 0, 0, 0, 0};
   Trig trig = {};      // sin / cos of pose, cached when the pose is set (the pose of a keyframe rarely changes)
   bool trig_valid = false;
+  void* base = nullptr;  // the arena block holding the three clouds, and its size (returned to the free list on removal)
+  size_t bytes = 0;
 };
 
 // One map's worth of device buffers. Slots 0 / 1 are the corner / surf surrounding maps; slot 2 serves
@@ -86,6 +88,7 @@ struct ll_handle_s {
   std::vector<void*> arena;
   size_t arena_off = 0, arena_cap = 0;
   std::unordered_map<int, Keyframe> kfs;
+  std::vector<std::pair<void*, size_t>> free_blocks;  // arena blocks of removed / replaced keyframes (first fit)
 
   uint8_t* pinned = nullptr;  // the staging slot acquired last
   uint8_t* pin_buf[kPinSlots] = {};
@@ -307,9 +310,18 @@ int upload_points(ll_handle h, float4* d_dst, const void* src, size_t n, size_t 
   return pinned_release(h);
 }
 
-int arena_alloc(ll_handle h, size_t bytes, void** out) {
+int arena_alloc(ll_handle h, size_t bytes, void** out, size_t* got = nullptr) {
   bytes = (bytes + 255) & ~size_t(255);
   if (bytes == 0) bytes = 256;
+  for (size_t i = 0; i < h->free_blocks.size(); ++i) {  // a block of a removed keyframe that is not wastefully large
+    if (h->free_blocks[i].second >= bytes && h->free_blocks[i].second <= 2 * bytes + 4096) {
+      *out = h->free_blocks[i].first;
+      if (got) *got = h->free_blocks[i].second;
+      h->free_blocks.erase(h->free_blocks.begin() + (long)i);
+      return LL_OK;
+    }
+  }
+  if (got) *got = bytes;
   if (h->arena.empty() || h->arena_off + bytes > h->arena_cap) {
     size_t chunk = bytes > kArenaChunk ? bytes : kArenaChunk;
     void* p = nullptr;
@@ -815,9 +827,13 @@ int scan2map_enqueue(ll_handle h, const float pose6[6]) {
     void* args[] = {&A, &p[0], &p[1], &p[2], &p[3], &p[4], &p[5], &bar, &bar_clear, &GB, &build_map, &build_grid,
                     &segs, &jobs, &n_jobs};
     LL_PROF(h, 8);
-    LL_CUDA(h, cudaLaunchCooperativeKernel(h->prm.eigen_mode ? reinterpret_cast<const void*>(lm_persistent_kernel<1>)
-                                                             : reinterpret_cast<const void*>(lm_persistent_kernel<0>),
-                                           dim3((unsigned)h->lm_blocks),
+    // kFresh: this launch writes `sorted` / `cells` itself, so the LM loop must not read them through ld.global.nc
+    const bool fresh = build_map || build_grid;
+    const void* kern = h->prm.eigen_mode ? (fresh ? reinterpret_cast<const void*>(lm_persistent_kernel<1, true>)
+                                                  : reinterpret_cast<const void*>(lm_persistent_kernel<1, false>))
+                                         : (fresh ? reinterpret_cast<const void*>(lm_persistent_kernel<0, true>)
+                                                  : reinterpret_cast<const void*>(lm_persistent_kernel<0, false>));
+    LL_CUDA(h, cudaLaunchCooperativeKernel(kern, dim3((unsigned)h->lm_blocks),
                                            dim3(LM_THREADS), args, 0, h->stream));
     LL_LAUNCHED(h);
     LL_TRY(seglist_release(h));
@@ -874,6 +890,7 @@ int ensure_tmp(ll_handle h, int k, size_t bytes) {
 int emit_queries(ll_handle h, int which, int mode, const void* queries, size_t nq, size_t stride, const float pose6[6],
                  float* coeff4, int* mask, int* accept, int* idx5, float* d2_5) {
   if (!h) return LL_ERR_INVALID_ARG;
+  if (h->scan_pending) return fail(h, LL_ERR_STATE, "a scan2map is still in flight: call ll_scan2map_wait first");
   if (!h->map_ready) return fail(h, LL_ERR_STATE, "no local map: call ll_build_local_map / ll_set_local_map_raw first");
   if (which != 0 && which != 1) return fail(h, LL_ERR_INVALID_ARG, "which must be 0 (corner) or 1 (surf)");
   if (nq && (!queries || !stride_ok(stride))) return fail(h, LL_ERR_INVALID_ARG, "bad query cloud / stride");
@@ -1026,6 +1043,7 @@ int ll_reserve(ll_handle h, size_t max_corner_raw, size_t max_surf_raw, size_t m
 
 int ll_set_params(ll_handle h, const ll_params* p) {
   if (!h) return LL_ERR_INVALID_ARG;
+  if (h->scan_pending) return fail(h, LL_ERR_STATE, "a scan2map is still in flight: call ll_scan2map_wait first");
   LL_TRY(validate_params(h, p));
   h->prm = *p;
   return LL_OK;
@@ -1056,11 +1074,23 @@ static int add_keyframe_impl(ll_handle h, int id, const void* c[3], const size_t
   for (int k = 0; k < 3; ++k)
     if (n[k] && !c[k]) return fail(h, LL_ERR_INVALID_ARG, "NULL cloud with non-zero count");
   LL_CUDA(h, cudaSetDevice(h->device));
+  if (id == h->prefetched_id && ((size_t)h->prefetched_kf.n[0] != n[0] || (size_t)h->prefetched_kf.n[1] != n[1] ||
+                                 (size_t)h->prefetched_kf.n[2] != n[2])) {
+    // not the clouds that were prefetched under this id: drop the prefetch (block back to the free list once its copy
+    // has finished) and store what the caller passes now
+    LL_CUDA(h, cudaEventSynchronize(h->kf_evt));
+    if (h->prefetched_kf.base) h->free_blocks.emplace_back(h->prefetched_kf.base, h->prefetched_kf.bytes);
+    h->prefetched_id = -1;
+    h->prefetched_kf = Keyframe();
+  }
   if (id == h->prefetched_id) {  // the clouds are already on their way (ll_prefetch_keyframe): attach the pose
     Keyframe kf = h->prefetched_kf;
     std::memcpy(kf.pose, pose6, sizeof(kf.pose));
     h->prefetched_id = -1;
     LL_CUDA(h, cudaStreamWaitEvent(h->stream, h->kf_evt, 0));  // later work on the main stream sees the upload
+    auto old = h->kfs.find(id);
+    if (old != h->kfs.end() && old->second.base) h->free_blocks.emplace_back(old->second.base, old->second.bytes);
+    h->prefetched_kf = Keyframe();
     h->kfs[id] = kf;
     return LL_OK;
   }
@@ -1082,7 +1112,17 @@ static int store_keyframe_clouds(ll_handle h, int id, Keyframe kf, const void* c
     total += (n[k] * sizeof(float4) + 255) & ~size_t(255);
   }
   void* base = nullptr;
-  LL_TRY(arena_alloc(h, total, &base));
+  size_t got = 0;
+  if (st != h->stream && h->prefetched_id >= 0) {
+    // A prefetch that was never attached (its ll_add_keyframe did not come): wait for its copy, then reclaim its block.
+    LL_CUDA(h, cudaEventSynchronize(h->kf_evt));
+    if (h->prefetched_kf.base) h->free_blocks.emplace_back(h->prefetched_kf.base, h->prefetched_kf.bytes);
+    h->prefetched_id = -1;
+    h->prefetched_kf = Keyframe();
+  }
+  LL_TRY(arena_alloc(h, total, &base, &got));
+  kf.base = base;
+  kf.bytes = got;
   for (int k = 0; k < 3; ++k) kf.d[k] = reinterpret_cast<float4*>(static_cast<uint8_t*>(base) + off[k]);
   if (dev) {
     for (int k = 0; k < 3; ++k)
@@ -1094,7 +1134,11 @@ static int store_keyframe_clouds(ll_handle h, int id, Keyframe kf, const void* c
     LL_CUDA(h, cudaEventRecord(h->pin_evt[h->pin_cur], st));
   }
   if (st == h->stream) {
-    h->kfs[id] = kf;  // re-adding an id replaces the entry (the old slab space is not reclaimed)
+    auto old = h->kfs.find(id);  // re-adding an id replaces the entry; the old block is reused by later keyframes. Work
+    // already enqueued on the stream that reads the old block runs before anything a later keyframe copies into it
+    // (same stream), so handing it back immediately is safe.
+    if (old != h->kfs.end() && old->second.base) h->free_blocks.emplace_back(old->second.base, old->second.bytes);
+    h->kfs[id] = kf;
   } else {
     LL_CUDA(h, cudaEventRecord(h->kf_evt, st));
     h->prefetched_kf = kf;
@@ -1146,6 +1190,31 @@ int ll_set_keyframe_pose(ll_handle h, int id, const float pose6[6]) {
   if (it == h->kfs.end()) return fail(h, LL_ERR_NOT_FOUND, "unknown keyframe id " + std::to_string(id));
   std::memcpy(it->second.pose, pose6, 6 * sizeof(float));
   it->second.trig_valid = false;
+  return LL_OK;
+}
+
+int ll_remove_keyframe(ll_handle h, int id) {
+  if (!h) return LL_ERR_INVALID_ARG;
+  if (h->scan_pending) return fail(h, LL_ERR_STATE, "a scan2map is still in flight: call ll_scan2map_wait first");
+  auto it = h->kfs.find(id);
+  if (it == h->kfs.end()) return fail(h, LL_ERR_NOT_FOUND, "unknown keyframe id " + std::to_string(id));
+  // a local map that was only prepared (single-kernel scan) still points at this keyframe's clouds: build it now
+  if (h->map_deferred) {
+    LL_CUDA(h, cudaSetDevice(h->device));
+    LL_TRY(ensure_map(h));
+  }
+  if (it->second.base) h->free_blocks.emplace_back(it->second.base, it->second.bytes);
+  h->kfs.erase(it);
+  return LL_OK;
+}
+
+int ll_get_memory_info(ll_handle h, size_t* keyframes, size_t* arena_bytes, size_t* free_list_bytes) {
+  if (!h) return LL_ERR_INVALID_ARG;
+  if (keyframes) *keyframes = h->kfs.size();
+  if (arena_bytes) *arena_bytes = h->arena.empty() ? 0 : (h->arena.size() - 1) * kArenaChunk + h->arena_off;
+  size_t fb = 0;
+  for (const auto& b : h->free_blocks) fb += b.second;
+  if (free_list_bytes) *free_list_bytes = fb;
   return LL_OK;
 }
 
@@ -1514,6 +1583,7 @@ int ll_lm_step(ll_handle h, const void* ori, const float* coeff4, size_t n, size
                float pose6_inout[6], float* AtA36, float* Atb6, float* x6, float* deltaR, float* deltaT, int* ret) {
   if (!h || !pose6_inout) return LL_ERR_INVALID_ARG;
   if (!stride_ok(stride_bytes) || (n && (!ori || !coeff4))) return fail(h, LL_ERR_INVALID_ARG, "bad records / stride");
+  if (h->scan_pending) return fail(h, LL_ERR_STATE, "a scan2map is still in flight: call ll_scan2map_wait first");
   LL_CUDA(h, cudaSetDevice(h->device));
   LL_TRY(ensure_tmp(h, 0, n * 16));
   LL_TRY(ensure_tmp(h, 5, n * 16));
@@ -1544,6 +1614,7 @@ int ll_lm_step(ll_handle h, const void* ori, const float* coeff4, size_t n, size
 
 int ll_get_degeneracy(ll_handle h, int* is_degenerate, float* matP36) {
   if (!h) return LL_ERR_INVALID_ARG;
+  if (h->scan_pending) return fail(h, LL_ERR_STATE, "a scan2map is still in flight: call ll_scan2map_wait first");
   LL_CUDA(h, cudaSetDevice(h->device));
   LL_CUDA(h, cudaMemcpyAsync(h->h_state, h->d_state, sizeof(LMState), cudaMemcpyDeviceToHost, h->stream));
   LL_CUDA(h, cudaStreamSynchronize(h->stream));
@@ -1613,11 +1684,11 @@ int ll_profile_read(ll_handle h, double* ms_per_class, uint64_t* launches_per_cl
 
 int ll_reset_state(ll_handle h) {
   if (!h) return LL_ERR_INVALID_ARG;
+  if (h->scan_pending) return fail(h, LL_ERR_STATE, "a scan2map is still in flight: call ll_scan2map_wait first");
   LL_CUDA(h, cudaSetDevice(h->device));
   LL_CUDA(h, cudaMemsetAsync(h->d_state, 0, sizeof(LMState), h->stream));
   LL_CUDA(h, cudaStreamSynchronize(h->stream));
   std::memset(h->h_state, 0, sizeof(LMState));
-  h->scan_pending = false;
   return LL_OK;
 }
 

@@ -27,6 +27,39 @@
 
 namespace ll {
 
+// ---- optional in-kernel timeline (scratch/build_timeline.sh compiles a copy of the library with -DLL_TIMELINE):
+// thread 0 of every block stamps clock64() at the sub-phases of each LM iteration and %globaltimer at the grid
+// barrier; block 0 prints the per-iteration summary at the end of the launch (profiles/r02_lm_iteration_timeline.txt).
+#ifdef LL_TIMELINE
+constexpr int TL_ITERS = 12, TL_EVENTS = 12, TL_BLOCKS = 160;
+__device__ long long g_tl[TL_ITERS][TL_EVENTS][TL_BLOCKS];
+__device__ unsigned long long g_tl_gt[TL_ITERS][2][TL_BLOCKS];  // %globaltimer: [0] barrier arrive, [1] barrier release
+__device__ long long g_tl_warp[TL_ITERS][8][16];                // block TL_WATCH's warps: sub-stamps of phase 1
+__device__ int g_tl_it;
+constexpr int TL_WATCH = 100;
+__device__ __forceinline__ unsigned long long tl_gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define LL_TL(it, ev)                                                                                        \
+  do {                                                                                                       \
+    if (threadIdx.x == 0 && (it) < TL_ITERS && blockIdx.x < TL_BLOCKS) g_tl[(it)][(ev)][blockIdx.x] = clock64(); \
+  } while (0)
+#define LL_TL_GT(it, k)                                                                                          \
+  do {                                                                                                           \
+    if (threadIdx.x == 0 && (it) < TL_ITERS && blockIdx.x < TL_BLOCKS) g_tl_gt[(it)][(k)][blockIdx.x] = tl_gtime(); \
+  } while (0)
+#define LL_TL_WARP(ev)                                                                                                         \
+  do {                                                                                                                         \
+    if ((threadIdx.x & 31) == 0 && blockIdx.x == TL_WATCH && g_tl_it < TL_ITERS) g_tl_warp[g_tl_it][(ev)][threadIdx.x >> 5] = clock64(); \
+  } while (0)
+#else
+#define LL_TL(it, ev) do {} while (0)
+#define LL_TL_GT(it, k) do {} while (0)
+#define LL_TL_WARP(ev) do {} while (0)
+#endif
+
 constexpr int LM_THREADS = 512;
 constexpr int LM_WARPS = LM_THREADS / 32;
 constexpr int LM_MIN_BLOCKS = 1;         // resident blocks per SM the register budget is sized for
@@ -58,7 +91,7 @@ struct LMState {
   RotTrig rtrig;  // the six values LMOptimization recomputes (:1445-1450)
   int iter;       // iterCount of the next launch
   int done;       // loop has ended (break, threshold, or nothing can change any more)
-  int status;     // 0 optimised, 1 skipped by the map-size guard
+  int status;     // 0 optimised, 1 skipped by the map-size guard, 2 search grid too large (scan not registered)
   int iter_num;
   int converged;
   int sel_num;
@@ -524,6 +557,16 @@ struct Knn5 {
   bool accept;
 };
 
+// Loads of the search structures (`sorted`, `cells`). kFresh = the arrays were written EARLIER IN THIS LAUNCH (the
+// single-kernel scan builds the map and its grids before the LM loop): the read-only path (ld.global.nc) is defined
+// only for data that is constant for the whole kernel, so those launches use plain weak loads, which the grid
+// barrier's release / acquire pair orders after the writes (PTX memory model) and which still allocate in L1.
+template <bool kFresh, typename T>
+__device__ __forceinline__ T map_ld(const T* p) {
+  if constexpr (kFresh) return *p;
+  else return __ldg(p);
+}
+
 __device__ __forceinline__ bool pair_less(uint32_t da, uint32_t ia, uint32_t db, uint32_t ib) {
   return da < db || (da == db && ia < ib);
 }
@@ -551,7 +594,8 @@ __device__ __forceinline__ bool pair_less(uint32_t da, uint32_t ia, uint32_t db,
 
 // Chunks j0_begin, j0_begin + 128, ... of the candidate list described by (my_start, my_count) on lanes 0, 3, ..., 24,
 // merged into K (the best five of the chunks before j0_begin; all empty when j0_begin == 0).
-__device__ __forceinline__ void knn5_chunks(const float4* __restrict__ sorted, int my_start, int my_count, float sx,
+template <bool kFresh>
+__device__ __forceinline__ void knn5_chunks(const float4* sorted, int my_start, int my_count, float sx,
                                             float sy, float sz, float max_sq_dist, int lane, int j0_begin, Knn5& K) {
   // pr[k] = candidates before range k, bs[k] = (start of range k) - pr[k]: candidate j of the concatenation
   // lives at sorted[j + bs[k]] for the last k with pr[k] <= j. Range order: centre row first.
@@ -585,7 +629,7 @@ __device__ __forceinline__ void knn5_chunks(const float4* __restrict__ sorted, i
     }
 #pragma unroll
     for (int u = 0; u < LM_CAND_UNROLL; ++u)
-      ms[u] = srcs[u] >= 0 ? __ldg(&sorted[srcs[u]]) : make_float4(0.f, 0.f, 0.f, 0.f);
+      ms[u] = srcs[u] >= 0 ? map_ld<kFresh>(&sorted[srcs[u]]) : make_float4(0.f, 0.f, 0.f, 0.f);
     uint32_t cd[LM_CAND_UNROLL], ci[LM_CAND_UNROLL], cp[LM_CAND_UNROLL];
     bool any = false;
 #pragma unroll
@@ -648,6 +692,7 @@ __device__ __forceinline__ void knn5_chunks(const float4* __restrict__ sorted, i
 // LM_EMPTY_D2 / 0xffffffff), and acc[q] (warp-uniform) says whether five neighbours within range exist.
 constexpr int LM_KNN_BATCH = 3;
 
+template <bool kFresh>
 __device__ __forceinline__ void warp_knn5_batch(const float4* const (&sorted)[2], const int2* const (&cells)[2],
                                                 const GridGeom (&geom)[2], const int (&mq)[LM_KNN_BATCH],
                                                 const float4 (&sel)[LM_KNN_BATCH], float max_sq_dist, int lane,
@@ -666,9 +711,10 @@ __device__ __forceinline__ void warp_knn5_batch(const float4* const (&sorted)[2]
       const int x = (int)floorf(sel[q].x) - g.ox + (lane % 3) - 1, y = (int)floorf(sel[q].y) - g.oy + ((lane / 3) % 3) - 1,
                 z = (int)floorf(sel[q].z) - g.oz + (lane / 9) - 1;
       if (x >= 0 && x < g.dx && y >= 0 && y < g.dy && z >= 0 && z < g.dz)
-        ce[q] = __ldg(&cells[mq[q] ? 1 : 0][(z * g.dy + y) * g.dx + x]);
+        ce[q] = map_ld<kFresh>(&cells[mq[q] ? 1 : 0][(z * g.dy + y) * g.dx + x]);
     }
   }
+  LL_TL_WARP(1);
   // ---- stage 2: ranges -> candidate addresses -> candidate loads (all queries' loads in flight together)
   int total[NB], q_start[NB], q_count[NB];
   int srcs[NB][LM_CAND_UNROLL];
@@ -706,9 +752,10 @@ __device__ __forceinline__ void warp_knn5_batch(const float4* const (&sorted)[2]
           if (j >= pr[k]) b = bs[k];
         if (j < tot) srcs[q][u] = j + b;
       }
-      ms[q][u] = srcs[q][u] >= 0 ? __ldg(&sorted[mq[q] > 0 ? 1 : 0][srcs[q][u]]) : make_float4(0.f, 0.f, 0.f, 0.f);
+      ms[q][u] = srcs[q][u] >= 0 ? map_ld<kFresh>(&sorted[mq[q] > 0 ? 1 : 0][srcs[q][u]]) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
+  LL_TL_WARP(2);
   // ---- stage 3: distances and the per-lane sorting network
   uint32_t cdq[NB][LM_CAND_UNROLL], ciq[NB][LM_CAND_UNROLL], cpq[NB][LM_CAND_UNROLL];
 #pragma unroll
@@ -733,6 +780,7 @@ __device__ __forceinline__ void warp_knn5_batch(const float4* const (&sorted)[2]
     }
     LL_KNN_CE(0, 1) LL_KNN_CE(2, 3) LL_KNN_CE(0, 2) LL_KNN_CE(1, 3) LL_KNN_CE(1, 2)
   }
+  LL_TL_WARP(3);
   // ---- stage 4: five selection rounds, the queries' chains interleaved. One redux.sync finds the smallest d2;
   //      a ballot names the lane(s) holding it; only an exact d2 tie between lanes needs the index redux.
 #pragma unroll
@@ -786,7 +834,7 @@ __device__ __forceinline__ void warp_knn5_batch(const float4* const (&sorted)[2]
       K.idx[k] = __shfl_sync(0xffffffffu, i, k);
       K.pos[k] = __shfl_sync(0xffffffffu, p, k);
     }
-    knn5_chunks(sorted[m], qs, qc, sx, sy, sz, max_sq_dist, lane, 32 * LM_CAND_UNROLL, K);
+    knn5_chunks<kFresh>(sorted[m], qs, qc, sx, sy, sz, max_sq_dist, lane, 32 * LM_CAND_UNROLL, K);
     d = LM_EMPTY_D2; i = 0xffffffffu; p = 0xffffffffu;
 #pragma unroll
     for (int k = 0; k < 5; ++k)
@@ -1002,6 +1050,7 @@ __device__ void reduce_partials_and_solve(const float* partials, int nblocks, co
     s_red[lane] = t;
   }
   __syncthreads();
+  LL_TL(S->iter, 8);
   lm_solve_block<kEigenMode>(s_red, prm, S, stage_mode);
 }
 
@@ -1012,11 +1061,12 @@ __device__ void reduce_partials_and_solve(const float* partials, int nblocks, co
 //   phase 2  one thread per query: line / plane fit, Jacobian row, then a shuffle-tree reduction of the 29
 //            sums over the block (fixed order => bitwise repeatable).
 // Returns, on threads 0..28, this block's total of sum `tid`.
-template <int kEigenMode>
+template <int kEigenMode, bool kFresh>
 __device__ __forceinline__ float lm_block_pass(const LMArgs& A, const Trig& trig, const RotTrig& rt,
                                                const GridGeom (&geom)[2], float* s_slot, float (*s_wacc)[32],
-                                               int q_begin, int q_end) {
+                                               int q_begin, int q_end, int tl_it = 0) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  (void)tl_it;
   float run_sum = 0.f;  // threads 0..28: this block's running total of sum `tid`
   for (int c0 = q_begin; c0 < q_end; c0 += LM_CHUNK) {
     const int cn = min(LM_CHUNK, q_end - c0);
@@ -1045,7 +1095,9 @@ __device__ __forceinline__ float lm_block_pass(const LMArgs& A, const Trig& trig
         if (A.mode != 2) sel[b] = rigid_transform(trig, sel[b]);
       uint32_t od[LM_KNN_BATCH], oi[LM_KNN_BATCH], op[LM_KNN_BATCH];
       bool acc[LM_KNN_BATCH];
-      warp_knn5_batch(A.sorted, A.cells, geom, mq, sel, A.prm.fit.max_sq_dist, lane, od, oi, op, acc);
+      LL_TL_WARP(0);
+      warp_knn5_batch<kFresh>(A.sorted, A.cells, geom, mq, sel, A.prm.fit.max_sq_dist, lane, od, oi, op, acc);
+      LL_TL_WARP(4);
 #pragma unroll
       for (int b = 0; b < LM_KNN_BATCH; ++b) {
         const int i = i0 + b * LM_WARPS;
@@ -1054,7 +1106,7 @@ __device__ __forceinline__ float lm_block_pass(const LMArgs& A, const Trig& trig
         float* slot = &s_slot[(i < nc ? i : nc_pad + (i - nc)) * LM_SLOT];
         if (lane < 5) {
           if (acc[b]) {
-            const float4 nb = __ldg(&A.sorted[mq[b]][op[b]]);
+            const float4 nb = map_ld<kFresh>(&A.sorted[mq[b]][op[b]]);
             slot[4 + 3 * lane] = nb.x;
             slot[5 + 3 * lane] = nb.y;
             slot[6 + 3 * lane] = nb.z;
@@ -1073,7 +1125,10 @@ __device__ __forceinline__ float lm_block_pass(const LMArgs& A, const Trig& trig
         }
       }
     }
+    LL_TL_WARP(5);
+    LL_TL(tl_it, 1);
     __syncthreads();
+    LL_TL(tl_it, 2);
     // ---- phase 2: fit + Jacobian row, one thread per query
     if (A.mode != 2) {
       float sv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -1106,6 +1161,7 @@ __device__ __forceinline__ float lm_block_pass(const LMArgs& A, const Trig& trig
           one = 1.f;
         }
       }
+      LL_TL(tl_it, 3);
       if (A.mode == 0) {
         if (warp * 32 < nslots) {  // warp-uniform
 #pragma unroll
@@ -1116,6 +1172,7 @@ __device__ __forceinline__ float lm_block_pass(const LMArgs& A, const Trig& trig
             if (lane == 0) s_wacc[warp][k] = v;
           }
         }
+        LL_TL(tl_it, 4);
         __syncthreads();
         if (tid < LM_NSUM) {
           const int nw = (nslots + 31) >> 5;
@@ -1173,7 +1230,7 @@ __global__ void __launch_bounds__(LM_THREADS, LM_MIN_BLOCKS) lm_iter_kernel(cons
   lm_load_geom(A, geom);
   int q_begin, q_end;
   lm_partition(A, (int)blockIdx.x, (int)gridDim.x, q_begin, q_end);
-  const float run_sum = lm_block_pass<kEigenMode>(A, trig, rt, geom, s_slot, s_wacc, q_begin, q_end);
+  const float run_sum = lm_block_pass<kEigenMode, false>(A, trig, rt, geom, s_slot, s_wacc, q_begin, q_end);
   if (A.mode != 0) return;
   if (tid < 32) {
     A.partials[blockIdx.x * 32 + tid] = tid < LM_NSUM ? run_sum : 0.f;
@@ -1212,7 +1269,9 @@ __device__ __forceinline__ void lm_begin_state(LMState* S, const MapState* corne
   if (__ldcg(&corner->grid_too_large) || __ldcg(&surf->grid_too_large)) flags |= 4;
   S->flags = flags;
   const bool ok = n_corner > prm.min_corner_map && n_surf > prm.min_surf_map && !(flags & 4);
-  S->status = ok ? 0 : 1;
+  // 1 = the reference's own skip (:1573); 2 = NOT a reference behaviour: the 1 m search grid over this map's bounding
+  // box exceeds the cell budget, so the scan could not be registered here although the reference's KD-tree would
+  S->status = ok ? 0 : ((flags & 4) ? 2 : 1);
   S->done = ok ? 0 : 1;
   if (prm.iter_count_thres <= 0) S->done = 1;
 }
@@ -1225,7 +1284,7 @@ __device__ __forceinline__ void lm_begin_state(LMState* S, const MapState* corne
 // bit-identical new poses without a publish / observe round trip, and nothing waits for a kernel boundary.
 // Block 0 writes the final state back.  barrier: this scan's arrive counter (zero on entry); barrier_clear: the
 // counter a later scan will use (ring of counters in the handle, re-armed 32 scans ahead).
-template <int kEigenMode>
+template <int kEigenMode, bool kFresh>
 __global__ void __launch_bounds__(LM_THREADS, 1) lm_persistent_kernel(const __grid_constant__ LMArgs A, float p0, float p1,
                                                                       float p2, float p3, float p4, float p5,
                                                                       unsigned* barrier, unsigned* barrier_clear,
@@ -1269,15 +1328,68 @@ __global__ void __launch_bounds__(LM_THREADS, 1) lm_persistent_kernel(const __gr
     if (s_st.done) break;  // block-uniform, and the same decision in every block
     const Trig trig = s_st.trig;
     const RotTrig rt = s_st.rtrig;
-    const float run_sum = lm_block_pass<kEigenMode>(A, trig, rt, geom, s_slot, s_wacc, q_begin, q_end);
+#ifdef LL_TIMELINE
+    if (tid == 0 && blockIdx.x == TL_WATCH) g_tl_it = (int)it;
+#endif
+    LL_TL(it, 0);
+    const float run_sum = lm_block_pass<kEigenMode, kFresh>(A, trig, rt, geom, s_slot, s_wacc, q_begin, q_end, (int)it);
+    LL_TL(it, 5);
     float* part = A.partials + (size_t)(it & 1u) * gridDim.x * 32;
     if (tid < 32) {
       part[blockIdx.x * 32 + tid] = tid < LM_NSUM ? run_sum : 0.f;
       __threadfence();
     }
+    LL_TL(it, 6);
+    LL_TL_GT(it, 0);
     coop_barrier(barrier, epoch);
+    LL_TL_GT(it, 1);
+    LL_TL(it, 7);
     reduce_partials_and_solve<kEigenMode>(part, gridDim.x, A.prm, &s_st, false, reinterpret_cast<double*>(s_slot));
+    LL_TL(it, 9);
   }
+#ifdef LL_TIMELINE
+  __syncthreads();
+  if (blockIdx.x == 0 && tid == 0) {
+    const int nb = min((int)gridDim.x, TL_BLOCKS);
+    const double us = 1e-3 / 1.965;  // cycles -> us at the 1965 MHz the box runs at under load
+    const char* names[9] = {"phase1 5-NN (to block barrier)", "block barrier after phase 1", "phase2 fit + Jacobian row", "shuffle reduce 29 sums",
+                            "sum warp partials + barrier", "partial -> global + fence", "grid barrier (arrive..release)",
+                            "sum all blocks' partials", "6x6 solve + pose update"};
+    const int ea[9] = {0, 1, 2, 3, 4, 5, 6, 7, 8}, eb[9] = {1, 2, 3, 4, 5, 6, 7, 8, 9};
+    printf("LM iteration timeline, %d blocks x %d threads; per phase: mean / max over blocks, microseconds at 1965 MHz\n", nb, LM_THREADS);
+    for (int itx = 0; itx < TL_ITERS && itx < s_st.iter_num; ++itx) {
+      double tot_mean = 0.0;
+      printf(" iter %d\n", itx);
+      for (int p = 0; p < 9; ++p) {
+        double sum = 0.0, mx = 0.0;
+        for (int b = 0; b < nb; ++b) {
+          const double d = (double)(g_tl[itx][eb[p]][b] - g_tl[itx][ea[p]][b]) * us;
+          sum += d;
+          if (d > mx) mx = d;
+        }
+        tot_mean += sum / nb;
+        printf("   %-34s %7.2f / %7.2f\n", names[p], sum / nb, mx);
+      }
+      unsigned long long first = ~0ull, last = 0, rel = 0;
+      for (int b = 0; b < nb; ++b) {
+        const unsigned long long t = g_tl_gt[itx][0][b];
+        if (t < first) first = t;
+        if (t > last) last = t;
+        if (g_tl_gt[itx][1][b] > rel) rel = g_tl_gt[itx][1][b];
+      }
+      printf("   %-34s %7.2f   (globaltimer: first arrival -> last arrival %.2f us, last arrival -> last release %.2f us)\n",
+             "iteration total (mean of blocks)", tot_mean, (last - first) * 1e-3, (rel - last) * 1e-3);
+      if (itx == 1 || itx == 5) {
+        printf("   block %d phase-1 sub-stamps per warp (us from the warp's first batch start): cells fetched / candidates fetched / sorted / selected / staged\n", TL_WATCH);
+        for (int w = 0; w < 16; ++w) {
+          const long long t0 = g_tl_warp[itx][0][w];
+          printf("     warp %2d: %6.2f %6.2f %6.2f %6.2f %6.2f\n", w, (g_tl_warp[itx][1][w] - t0) * us, (g_tl_warp[itx][2][w] - t0) * us,
+                 (g_tl_warp[itx][3][w] - t0) * us, (g_tl_warp[itx][4][w] - t0) * us, (g_tl_warp[itx][5][w] - t0) * us);
+        }
+      }
+    }
+  }
+#endif
   if (blockIdx.x == 0) {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(&s_st);
     uint32_t* dst = reinterpret_cast<uint32_t*>(A.st);

@@ -25,6 +25,7 @@ def load():
             raise RuntimeError("%s is missing: run __graft_entry__.build()" % HOST_LIB_PATH)
         lib = C.CDLL(HOST_LIB_PATH)
         lib.llh_create.restype = C.c_void_p
+        lib.llh_create2.restype = C.c_void_p
         lib.llh_abi_handle.restype = C.c_void_p
         _lib = lib
     return _lib
@@ -48,16 +49,63 @@ def transform_associate_to_map(tsum, bef, aft):
     return out
 
 
+class _Frame(C.Structure):
+    """llh_frame (host/batch_replay.cpp)."""
+    _fields_ = [("odom6", C.c_void_p), ("cloud", C.c_void_p * 5), ("n", C.c_size_t * 5)]
+
+
+def batch_replay(nodes, sequences, first, count, n_threads, cpu_ids=None):
+    """Batched replay (BASELINE configs[4]) through the C++ driver host/batch_replay.cpp: frames [first, first + count) of
+    every sequence through its own node, `n_threads` host threads (std::thread, optionally pinned to cpu_ids).
+
+    nodes: list of MapOptimization; sequences: list of dict(odom=[n, 6] float32, clouds=[per frame: five arrays, all
+    [m, 8] (pcl::PointXYZI layout) or all [m, 4]]). -> (records [n_seq, count, 16] float32, seconds)."""
+    lib = load()
+    n_seq = len(nodes)
+    assert len(sequences) == n_seq
+    keep = []
+    stride = None
+    frame_arrays = []
+    for seq in sequences:
+        odom = np.ascontiguousarray(seq["odom"], np.float32)
+        keep.append(odom)
+        fr = (_Frame * len(seq["clouds"]))()
+        for k, clouds in enumerate(seq["clouds"]):
+            fr[k].odom6 = odom[k].ctypes.data
+            for j, c in enumerate(clouds):
+                assert c.dtype == np.float32 and c.flags["C_CONTIGUOUS"]
+                st = c.shape[1] * 4
+                stride = st if stride is None else stride
+                assert st == stride, "all clouds of a batch must share one layout"
+                fr[k].cloud[j] = c.ctypes.data if c.size else None
+                fr[k].n[j] = c.shape[0]
+        frame_arrays.append(fr)
+    node_ptrs = (C.c_void_p * max(n_seq, 1))(*[n._mo for n in nodes])
+    frame_ptrs = (C.c_void_p * max(n_seq, 1))(*[C.cast(f, C.c_void_p) for f in frame_arrays])
+    records = np.zeros((n_seq, count, 16), np.float32)
+    secs = C.c_double(0.0)
+    err = C.create_string_buffer(512)
+    cpus = np.ascontiguousarray(cpu_ids if cpu_ids is not None else [], np.int32)
+    rc = lib.llh_batch_replay(node_ptrs, C.c_int(n_seq), frame_ptrs, C.c_int(first), C.c_int(count), C.c_size_t(stride or 16),
+                              C.c_int(n_threads), _vp(cpus) if len(cpus) else None, C.c_int(len(cpus)), _vp(records),
+                              C.byref(secs), err, C.c_size_t(512))
+    if rc != 0:
+        raise RuntimeError(err.value.decode("utf-8", "replace") or "llh_batch_replay failed")
+    return records, secs.value
+
+
 class MapOptimization:
     """One MapOptimization node's hot path: feed frames with process_frame()."""
 
-    def __init__(self, params=None, device=0, loop_closure_enabled=True, search_num=50, search_radius=50.0):
+    def __init__(self, params=None, device=0, loop_closure_enabled=True, search_num=50, search_radius=50.0,
+                 reserve=(1 << 20, 1 << 21, 1 << 17)):
         self._lib = load()
         self.params = params if params is not None else abi.default_params()
         err = C.create_string_buffer(512)
-        self._mo = C.c_void_p(self._lib.llh_create(C.byref(self.params), C.c_int(device),
-                                                   C.c_int(1 if loop_closure_enabled else 0), C.c_int(search_num),
-                                                   C.c_float(search_radius), err, C.c_size_t(512)))
+        self._mo = C.c_void_p(self._lib.llh_create2(C.byref(self.params), C.c_int(device),
+                                                    C.c_int(1 if loop_closure_enabled else 0), C.c_int(search_num),
+                                                    C.c_float(search_radius), C.c_size_t(reserve[0]), C.c_size_t(reserve[1]),
+                                                    C.c_size_t(reserve[2]), err, C.c_size_t(512)))
         if not self._mo:
             raise RuntimeError(err.value.decode("utf-8", "replace") or "llh_create failed")
 
@@ -123,6 +171,23 @@ class MapOptimization:
         p = np.zeros(6, np.float32)
         self._lib.llh_get_last_prior(self._mo, _vp(p))
         return p
+
+    @property
+    def map_ids(self):
+        """Keyframe ids the last extractSurroundingKeyFrames concatenated into the local map, in order."""
+        ids = np.zeros(max(self.num_keyframes, 1), np.int32)
+        n = self._lib.llh_get_map_ids(self._mo, _vp(ids), C.c_int(len(ids)))
+        return ids[:n].copy()
+
+    @property
+    def last_frame_ms(self):
+        """Wall milliseconds of the last frame body, measured inside the mirror (as the reference times mapt.txt)."""
+        self._lib.llh_last_frame_ms.restype = C.c_double
+        return self._lib.llh_last_frame_ms(self._mo)
+
+    @property
+    def grid_overflow_scans(self):
+        return self._lib.llh_grid_overflow_scans(self._mo)
 
     def abi_handle(self):
         """Non-owning abi.Handle view of the ll_handle the mirror drives (for inspection in tests)."""

@@ -4,6 +4,7 @@
 #include "map_optimization.hpp"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -68,7 +69,8 @@ void associateToMap(const float sum[6], const float bef[6], const float aft[6], 
 }
 
 MapOptimization::MapOptimization(const ll_params& params, int device_id, bool loop_closure_enabled,
-                                 int surrounding_keyframe_search_num, float surrounding_keyframe_search_radius)
+                                 int surrounding_keyframe_search_num, float surrounding_keyframe_search_radius,
+                                 size_t reserve_corner_raw, size_t reserve_surf_raw, size_t reserve_queries)
     : prm_(params),
       loop_closure_enabled_(loop_closure_enabled),
       search_num_(surrounding_keyframe_search_num),
@@ -84,8 +86,8 @@ MapOptimization::MapOptimization(const ll_params& params, int device_id, bool lo
   std::memset(&lastResult, 0, sizeof(lastResult));
   const int rc = ll_create(&prm_, device_id, &h_);
   if (rc != LL_OK) throw std::runtime_error("ll_create failed (" + std::to_string(rc) + "): no usable CUDA device; there is no CPU fallback");
-  // A 50-keyframe VLP-16 window is ~0.1 M corner + ~0.3 M surf raw points; reserve well above that once.
-  check(ll_reserve(h_, 1u << 20, 1u << 21, 1u << 17), "ll_reserve");
+  // A 50-keyframe VLP-16 window is ~0.15 M corner + ~0.45 M surf raw points; the defaults reserve well above that once.
+  check(ll_reserve(h_, reserve_corner_raw, reserve_surf_raw, reserve_queries), "ll_reserve");
 }
 
 MapOptimization::~MapOptimization() { ll_destroy(h_); }
@@ -308,6 +310,12 @@ void MapOptimization::scan2MapOptimization() {  // :1572-1610
   }
   laserCloudCornerFromMapDSNum = lastResult.corner_map_ds;
   laserCloudSurfFromMapDSNum = lastResult.surf_map_ds;
+  if (lastResult.status == 2) {  // not the reference's skip: the search grid did not fit (see gridOverflowScans)
+    if (gridOverflowScans++ == 0)
+      std::fprintf(stderr, "legoloam_b200: frame %d NOT registered: the 1 m search grid over the local map exceeds the cell "
+                           "budget (map bounding box too large); pose left at the odometry prior\n", frame_idx);
+    err_ = "scan2MapOptimization: search grid too large, scan not registered";
+  }
   if (lastResult.status != 0) return;
   iter_num = lastResult.iter_num;
   min_lambda = lastResult.min_lambda;
@@ -379,6 +387,7 @@ void MapOptimization::saveKeyFramesAndFactor() {  // :1612-1755, pose graph = pa
 }
 
 void MapOptimization::processFrameView(const float laser_odometry[6], const FrameView& frame) {
+  const auto t_frame = std::chrono::steady_clock::now();
   frame_idx++;
   scanDevValid_ = false;
   view_ = &frame;
@@ -395,6 +404,7 @@ void MapOptimization::processFrameView(const float laser_odometry[6], const Fram
     throw;
   }
   view_ = nullptr;
+  lastFrameMs = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_frame).count();
 }
 
 void MapOptimization::correctPoses() {  // :1757-1785
@@ -430,6 +440,7 @@ PointCloud::Ptr MapOptimization::getLaserCloudSurfFromMapDS() {
 
 void MapOptimization::processFrame(const AssociationOut& a, bool scan_clouds_are_downsampled,
                                    PointCloud::Ptr corner_scan_ds) {  // run(): :1866-1896
+  const auto t_frame = std::chrono::steady_clock::now();
   frame_idx++;
   laserCloudCornerLast = a.cloud_corner_last;
   laserCloudSurfLast = a.cloud_surf_last;
@@ -452,6 +463,7 @@ void MapOptimization::processFrame(const AssociationOut& a, bool scan_clouds_are
   saveKeyFramesAndFactor();
   correctPoses();
   clearCloud();
+  lastFrameMs = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_frame).count();
 }
 
 }  // namespace lego_loam_b200
@@ -489,6 +501,17 @@ void* llh_create(const ll_params* prm, int device, int loop_closure_enabled, int
                  char* err, size_t err_cap) {
   try {
     return new MapOptimization(*prm, device, loop_closure_enabled != 0, search_num, search_radius);
+  } catch (const std::exception& e) {
+    if (err && err_cap) std::snprintf(err, err_cap, "%s", e.what());
+    return nullptr;
+  }
+}
+
+void* llh_create2(const ll_params* prm, int device, int loop_closure_enabled, int search_num, float search_radius,
+                  size_t reserve_corner_raw, size_t reserve_surf_raw, size_t reserve_queries, char* err, size_t err_cap) {
+  try {
+    return new MapOptimization(*prm, device, loop_closure_enabled != 0, search_num, search_radius, reserve_corner_raw,
+                               reserve_surf_raw, reserve_queries);
   } catch (const std::exception& e) {
     if (err && err_cap) std::snprintf(err, err_cap, "%s", e.what());
     return nullptr;
@@ -562,5 +585,16 @@ void llh_get_last_prior(void* mo, float pose6[6]) {
 }
 
 void* llh_abi_handle(void* mo) { return static_cast<MapOptimization*>(mo)->handle(); }
+
+// keyframe ids selected by the last extractSurroundingKeyFrames, in concatenation order; returns their number
+int llh_get_map_ids(void* mo, int* ids, int cap) {
+  const auto& v = static_cast<MapOptimization*>(mo)->mapIds();
+  for (int i = 0; i < (int)v.size() && i < cap; ++i) ids[i] = v[(size_t)i];
+  return (int)v.size();
+}
+
+int llh_grid_overflow_scans(void* mo) { return static_cast<MapOptimization*>(mo)->gridOverflowScans; }
+
+double llh_last_frame_ms(void* mo) { return static_cast<MapOptimization*>(mo)->lastFrameMs; }
 
 }  // extern "C"

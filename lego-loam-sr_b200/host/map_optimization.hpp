@@ -53,8 +53,12 @@ struct AssociationOut {
 class MapOptimization {
  public:
   // loop_closure_enabled / surrounding_keyframe_search_* : loam_config.yaml:23,26,27
+  // reserve_*: points of the raw surrounding corner / surf clouds and queries per scan the device buffers are
+  // pre-sized for (ll_reserve; they still grow on demand). The defaults hold a 50-keyframe VLP-16 window several
+  // times over (~0.5 GB per handle, cell tables included); batched replay with many handles per GPU passes less.
   MapOptimization(const ll_params& params, int device_id, bool loop_closure_enabled = true,
-                  int surrounding_keyframe_search_num = 50, float surrounding_keyframe_search_radius = 50.0f);
+                  int surrounding_keyframe_search_num = 50, float surrounding_keyframe_search_radius = 50.0f,
+                  size_t reserve_corner_raw = 1u << 20, size_t reserve_surf_raw = 1u << 21, size_t reserve_queries = 1u << 17);
   ~MapOptimization();
   MapOptimization(const MapOptimization&) = delete;
   MapOptimization& operator=(const MapOptimization&) = delete;
@@ -116,6 +120,14 @@ class MapOptimization {
   std::vector<PointType> localInfo;  // (iter_num, min_lambda, CF_mean, frame_idx), :1602-1607
   ll_result lastResult;
   float lastPrior[6] = {0, 0, 0, 0, 0, 0};  // transformTobeMapped on entry to the last scan2MapOptimization
+  // Scans this library could NOT register because the 1 m search grid over the map's bounding box exceeded the cell
+  // budget (ll_result.status == 2). The reference's KD-tree has no such limit: this is a failure to report, not the
+  // reference's map-size skip (:1573). The first occurrence is also written to stderr.
+  int gridOverflowScans = 0;
+  // Wall time of the last processFrame / processFrameView body, milliseconds (steady_clock, the way the reference
+  // times the same body for mapt.txt, mapOptmization.cpp:1877,1900-1903).
+  double lastFrameMs = 0.0;
+  const std::vector<int>& mapIds() const { return mapIds_; }  // keyframe ids of the last extractSurroundingKeyFrames
 
   // laserCloud{Corner,Surf}FromMapDS on request (publishKeyPosesAndFrames reads the surf one, :746-752)
   PointCloud::Ptr getLaserCloudCornerFromMapDS();

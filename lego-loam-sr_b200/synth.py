@@ -251,15 +251,20 @@ def voxel_np(pts, leaf):
     return (sums / cnt).astype(np.float32)
 
 
-def frame_inputs(raw, corner_leaf=0.2, surf_leaf=0.4):
-    """The five clouds one MapOptimization frame consumes after downsampleCurrentScan."""
+def frame_inputs(raw, corner_leaf=0.2, surf_leaf=0.4, keep_raw=False):
+    """The five clouds one MapOptimization frame consumes after downsampleCurrentScan (keep_raw: plus the raw surf and
+    outlier clouds, for the legs that run downsampleCurrentScan on the device)."""
     corner_scan_ds = voxel_np(raw["corner_scan"], corner_leaf)
     surf_last_ds = voxel_np(raw["surf_last"], surf_leaf)
     outlier_last_ds = voxel_np(raw["outlier_last"], surf_leaf)
     surf_total_ds = voxel_np(np.concatenate([surf_last_ds, outlier_last_ds]), surf_leaf)
-    return dict(corner_scan=np.ascontiguousarray(raw["corner_scan"], np.float32),
-                corner_scan_ds=corner_scan_ds, surf_last_ds=surf_last_ds,
-                outlier_last_ds=outlier_last_ds, surf_total_ds=surf_total_ds)
+    out = dict(corner_scan=np.ascontiguousarray(raw["corner_scan"], np.float32),
+               corner_scan_ds=corner_scan_ds, surf_last_ds=surf_last_ds,
+               outlier_last_ds=outlier_last_ds, surf_total_ds=surf_total_ds)
+    if keep_raw:
+        out["surf_last"] = np.ascontiguousarray(raw["surf_last"], np.float32)
+        out["outlier_last"] = np.ascontiguousarray(raw["outlier_last"], np.float32)
+    return out
 
 
 def noisy_odometry(gt_poses, seed=0, rot_sigma_deg=0.05, trans_sigma=0.01):
@@ -279,11 +284,12 @@ def noisy_odometry(gt_poses, seed=0, rot_sigma_deg=0.05, trans_sigma=0.01):
     return np.array(odom, np.float32)
 
 
-def make_sequence(seed=2, n_scans=100, step=0.5, sensor="vlp16", world_kw=None, cache_dir=None):
+def make_sequence(seed=2, n_scans=100, step=0.5, sensor="vlp16", world_kw=None, cache_dir=None, keep_raw=False):
     """A trajectory replay problem (BASELINE config 2 shape): per scan the five input clouds, the
-    odometry pose and the ground-truth pose."""
-    key = "seq_s%d_n%d_st%.3f_%s_%s.npz" % (seed, n_scans, step, sensor,
-                                            "-".join("%s%s" % kv for kv in sorted((world_kw or {}).items())))
+    odometry pose and the ground-truth pose. The first n scans are the same for every n_scans >= n."""
+    key = "seq_s%d_n%d_st%.3f_%s_%s%s.npz" % (seed, n_scans, step, sensor,
+                                              "-".join("%s%s" % kv for kv in sorted((world_kw or {}).items())),
+                                              "_raw" if keep_raw else "")
     if cache_dir:
         path = os.path.join(cache_dir, key)
         if os.path.exists(path):
@@ -291,7 +297,7 @@ def make_sequence(seed=2, n_scans=100, step=0.5, sensor="vlp16", world_kw=None, 
             return dict(frames=list(z["frames"]), odom=z["odom"], gt=z["gt"])
     world = World(seed=seed, **(world_kw or {}))
     gt = trajectory(world, n_scans, step=step, seed=seed)
-    frames = [frame_inputs(scan(world, gt[k], sensor=sensor, seed=seed * 100003 + k)) for k in range(n_scans)]
+    frames = [frame_inputs(scan(world, gt[k], sensor=sensor, seed=seed * 100003 + k), keep_raw=keep_raw) for k in range(n_scans)]
     odom = noisy_odometry(gt, seed=seed)
     out = dict(frames=frames, odom=odom, gt=gt.astype(np.float32))
     if cache_dir:
@@ -300,12 +306,22 @@ def make_sequence(seed=2, n_scans=100, step=0.5, sensor="vlp16", world_kw=None, 
     return out
 
 
-def make_single(seed=1, n_map_scans=50, step=0.5, sensor="vlp16", rot_deg=0.5, trans=0.05, world_kw=None):
+def make_single(seed=1, n_map_scans=50, step=0.5, sensor="vlp16", rot_deg=0.5, trans=0.05, world_kw=None, cache_dir=None):
     """BASELINE config 1/3 shape: one query scan against a local map assembled from n_map_scans prior
     scans at their ground-truth poses; the prior is the ground truth perturbed by (rot_deg, trans)."""
     world = World(seed=seed, **(world_kw or {}))
     gt = trajectory(world, n_map_scans + 1, step=step, seed=seed)
-    frames = [frame_inputs(scan(world, gt[k], sensor=sensor, seed=seed * 100003 + k)) for k in range(n_map_scans + 1)]
+    path = None
+    if cache_dir:
+        path = os.path.join(cache_dir, "single_s%d_n%d_st%.3f_%s_%s.npz" % (
+            seed, n_map_scans, step, sensor, "-".join("%s%s" % kv for kv in sorted((world_kw or {}).items()))))
+    if path and os.path.exists(path):
+        frames = list(np.load(path, allow_pickle=True)["frames"])
+    else:
+        frames = [frame_inputs(scan(world, gt[k], sensor=sensor, seed=seed * 100003 + k)) for k in range(n_map_scans + 1)]
+        if path:
+            os.makedirs(cache_dir, exist_ok=True)
+            np.savez(path, frames=np.array(frames, dtype=object))
     q = frames[-1]
     rng = np.random.default_rng(seed)
     prior = perturb(gt[-1], rot_deg, trans, rng).astype(np.float32)

@@ -9,7 +9,10 @@
 // nanoflann_pcl.h itself cannot be used: it includes PCL headers (:45-46), which are not installed.
 #include <nanoflann.hpp>
 
+#include <algorithm>
 #include <cstddef>
+#include <utility>
+#include <vector>
 
 namespace {
 
@@ -49,6 +52,23 @@ void ref_kdtree_knn5(void* tree, const float q[3], int* idx5, float* d2_5) {
   rs.init(idx5, d2_5);
   ix->tree.findNeighbors(rs, q, nanoflann::SearchParams());
   for (size_t k = rs.size(); k < 5; ++k) { idx5[k] = -1; }
+}
+
+// Body of KdTreeFLANN::radiusSearch (nanoflann_pcl.h:154-174) with its default _params (sorted = true).
+int ref_kdtree_radius(void* tree, const float q[3], double radius, int* idx, float* d2, int cap) {
+  Index* ix = (Index*)tree;
+  std::vector<std::pair<int, float>> indices_dist;
+  indices_dist.reserve(128);
+  nanoflann::RadiusResultSet<float, int> resultSet(static_cast<float>(radius * radius), indices_dist);
+  nanoflann::SearchParams params;
+  ix->tree.findNeighbors(resultSet, q, params);
+  const size_t nFound = resultSet.size();
+  if (params.sorted) std::sort(indices_dist.begin(), indices_dist.end(), nanoflann::IndexDist_Sorter());
+  for (size_t i = 0; i < nFound && (int)i < cap; i++) {
+    idx[i] = indices_dist[i].first;
+    d2[i] = indices_dist[i].second;
+  }
+  return (int)nFound;
 }
 
 void ref_kdtree_free(void* tree) { delete (Index*)tree; }

@@ -522,11 +522,47 @@ struct orc_replay {
   orc_params prm;
   orc_state st;
   int window;
+  bool loop_closure = true;   // _loop_closure_enabled (loam_config.yaml:23; the VLP-16 block ships false)
+  float search_radius = 50.f; // _surrounding_keyframe_search_radius (loam_config.yaml:26)
+  float cur_pos[3] = {0.f, 0.f, 0.f};  // currentRobotPosPoint (set at :1613-1615)
+  std::vector<int> existing_ids;       // surroundingExistingKeyPosesID (:1171-1216)
+  std::vector<int> map_ids;            // keyframes concatenated into the last local map, in order
   float sum[6], bef[6], aft[6], tobe[6];
   std::vector<std::vector<orc_p4>> kf_corner, kf_surf, kf_outlier;
   std::vector<float> kf_pose;  // 6 per keyframe
   std::vector<orc_p4> cds, sds;
 };
+
+// kdtreeSurroundingKeyPoses.radiusSearch (nanoflann_pcl.h:154-174 over nanoflann.hpp RadiusResultSet): every point
+// with squared distance (float, ((dx^2)+dy^2)+dz^2, query minus point) STRICTLY below radius^2 (the double product
+// rounded to float), sorted ascending by distance. The reference sorts with std::sort (IndexDist_Sorter compares the
+// distance only), so the order among exactly equal distances is unspecified there; here it is ascending index.
+static orc_ext_radius_fn g_ext_radius = nullptr;
+static void radius_search(const std::vector<orc_p4>& pts, const float q[3], float radius, std::vector<int>& idx, bool use_ext) {
+  idx.clear();
+  if (use_ext && g_ext_radius && g_ext_build && g_ext_free && !pts.empty()) {
+    void* tree = g_ext_build(pts.data(), (int)pts.size());
+    std::vector<int> tmp(pts.size());
+    std::vector<float> d2(pts.size());
+    const int n = g_ext_radius(tree, q, (double)radius, tmp.data(), d2.data(), (int)pts.size());
+    g_ext_free(tree);
+    idx.assign(tmp.begin(), tmp.begin() + n);
+    return;
+  }
+  const float r2 = static_cast<float>((double)radius * (double)radius);
+  std::vector<std::pair<float, int>> hits;
+  for (int i = 0; i < (int)pts.size(); ++i) {
+    float df = q[0] - pts[i].x;
+    float d = df * df;
+    df = q[1] - pts[i].y;
+    d += df * df;
+    df = q[2] - pts[i].z;
+    d += df * df;
+    if (d < r2) hits.emplace_back(d, i);
+  }
+  std::stable_sort(hits.begin(), hits.end(), [](const std::pair<float, int>& a, const std::pair<float, int>& b) { return a.first < b.first; });
+  for (const auto& h : hits) idx.push_back(h.second);
+}
 
 extern "C" {
 
@@ -840,7 +876,56 @@ orc_replay* orc_replay_create(const orc_params* prm, int window) {
   return r;
 }
 
+// loop_closure_enabled = 0 selects the reference's DEFAULT local-map branch (:1152-1223): key poses within
+// search_radius of currentRobotPosPoint, thinned by a 1 m VoxelGrid, cached set updated by erase / add.
+orc_replay* orc_replay_create2(const orc_params* prm, int window, int loop_closure_enabled, float search_radius) {
+  orc_replay* r = orc_replay_create(prm, window);
+  r->loop_closure = loop_closure_enabled != 0;
+  r->search_radius = search_radius;
+  return r;
+}
+
+void orc_set_ext_radius(orc_ext_radius_fn f) { g_ext_radius = f; }
+
+int orc_replay_get_map_ids(orc_replay* r, int* ids, int cap) {
+  for (int i = 0; i < (int)r->map_ids.size() && i < cap; ++i) ids[i] = r->map_ids[(size_t)i];
+  return (int)r->map_ids.size();
+}
+
+// Stand-alone form of the selection of :1152-1216 for tests: key poses (x, y, z, intensity = index) -> the updated
+// surroundingExistingKeyPosesID. existing_inout holds n_existing ids on entry and the new list on return (capacity
+// cap); returns the new count.
+int orc_select_surrounding(const orc_p4* key_poses, int n, const float cur_pos[3], float radius, int* existing_inout,
+                           int n_existing, int cap, int use_ext_radius) {
+  orc_replay tmp;
+  tmp.existing_ids.assign(existing_inout, existing_inout + n_existing);
+  std::vector<orc_p4> kp(key_poses, key_poses + n);
+  std::vector<int> hit;
+  radius_search(kp, cur_pos, radius, hit, use_ext_radius != 0);
+  std::vector<orc_p4> sur, sur_ds(hit.size());
+  for (int i : hit) sur.push_back(kp[(size_t)i]);
+  int n_ds = 0;
+  if (!sur.empty()) orc_voxel_downsample(sur.data(), (int)sur.size(), 1.0f, sur_ds.data(), &n_ds, nullptr);
+  std::vector<int>& ex = tmp.existing_ids;
+  for (size_t i = 0; i < ex.size(); ++i) {
+    bool existing = false;
+    for (int j = 0; j < n_ds; ++j)
+      if (ex[i] == (int)sur_ds[(size_t)j].i) { existing = true; break; }
+    if (!existing) { ex.erase(ex.begin() + (long)i); --i; }
+  }
+  for (int i = 0; i < n_ds; ++i) {
+    const int id = (int)sur_ds[(size_t)i].i;
+    if (std::find(ex.begin(), ex.end(), id) == ex.end()) ex.push_back(id);
+  }
+  for (int i = 0; i < (int)ex.size() && i < cap; ++i) existing_inout[i] = ex[(size_t)i];
+  return (int)ex.size();
+}
+
 void orc_replay_destroy(orc_replay* r) { delete r; }
+
+// (bench: the as-shipped replay fills its window with iter_count_thres = 1 — same state, the pose never moves — then
+// switches to the shipped 200 for the timed scans)
+void orc_replay_set_params(orc_replay* r, const orc_params* prm) { r->prm = *prm; }
 
 // The body of MapOptimization::run for one frame (:1878-1888) with loop closure enabled so the
 // local map is the last `window` keyframes (:1101-1151), every frame a keyframe (:1622-1631) and
@@ -854,12 +939,26 @@ void orc_replay_step(orc_replay* r, const float odom6[6], const orc_p4* corner_s
   r->cds.clear();
   r->sds.clear();
   const int nkf = (int)r->kf_corner.size();
-  if (nkf > 0) {  // :1097, :1101-1151
-    int first = std::max(0, nkf - r->window);
+  r->map_ids.clear();
+  if (nkf > 0 && r->loop_closure) {  // :1097, :1101-1151
+    for (int k = std::max(0, nkf - r->window); k < nkf; ++k) r->map_ids.push_back(k);
+  } else if (nkf > 0) {  // :1152-1216, the default branch
+    std::vector<orc_p4> kp((size_t)nkf);
+    for (int k = 0; k < nkf; ++k)  // cloudKeyPoses3D: position + intensity = index (:1692-1697)
+      kp[(size_t)k] = orc_p4{r->kf_pose[6 * k + 3], r->kf_pose[6 * k + 4], r->kf_pose[6 * k + 5], (float)k};
+    std::vector<int> ex = r->existing_ids;
+    ex.resize((size_t)nkf + ex.size());
+    const int n_ex = orc_select_surrounding(kp.data(), nkf, r->cur_pos, r->search_radius, ex.data(), (int)r->existing_ids.size(),
+                                            (int)ex.size(), g_ext_radius != nullptr);
+    ex.resize((size_t)n_ex);
+    r->existing_ids = ex;
+    r->map_ids = ex;
+  }
+  if (!r->map_ids.empty()) {
     std::vector<orc_p4> c, s, o;
     std::vector<int> co{0}, so{0}, oo{0};
     std::vector<float> poses;
-    for (int k = first; k < nkf; ++k) {
+    for (int k : r->map_ids) {
       c.insert(c.end(), r->kf_corner[k].begin(), r->kf_corner[k].end());
       s.insert(s.end(), r->kf_surf[k].begin(), r->kf_surf[k].end());
       o.insert(o.end(), r->kf_outlier[k].begin(), r->kf_outlier[k].end());
@@ -868,7 +967,7 @@ void orc_replay_step(orc_replay* r, const float odom6[6], const orc_p4* corner_s
       oo.push_back((int)o.size());
       poses.insert(poses.end(), &r->kf_pose[6 * k], &r->kf_pose[6 * k] + 6);
     }
-    build_local_map(nkf - first, poses.data(), c.data(), co.data(), s.data(), so.data(), o.data(), oo.data(),
+    build_local_map((int)r->map_ids.size(), poses.data(), c.data(), co.data(), s.data(), so.data(), o.data(), oo.data(),
                     r->prm, r->cds, r->sds, nullptr, nullptr);
   }
   if (n_corner_map_ds) *n_corner_map_ds = (int)r->cds.size();
@@ -878,6 +977,7 @@ void orc_replay_step(orc_replay* r, const float odom6[6], const orc_p4* corner_s
   if (res->status == 0) {                                                     // transformUpdate :583-589
     for (int i = 0; i < 6; ++i) { r->bef[i] = r->sum[i]; r->aft[i] = r->tobe[i]; }
   }
+  for (int i = 0; i < 3; ++i) r->cur_pos[i] = r->aft[3 + i];  // currentRobotPosPoint, :1613-1615
   // saveKeyFramesAndFactor :1612-1755 with the pose graph as pass-through: the key pose is
   // transformAftMapped; the keyframe clouds are corner_scan (un-downsampled, :1746),
   // surf_last_ds (:1744) and outlier_last_ds (:1745).

@@ -61,6 +61,9 @@ typedef void  (*orc_ext_knn5_fn)(void* tree, const float q[3], int* idx5, float*
 typedef void  (*orc_ext_free_fn)(void* tree);
 void orc_set_knn_backend(int kind);
 void orc_set_ext_knn(orc_ext_build_fn b, orc_ext_knn5_fn q, orc_ext_free_fn f);
+/* radius search of the external tree (the reference's nanoflann): indices sorted by distance; returns the count */
+typedef int (*orc_ext_radius_fn)(void* tree, const float q[3], double radius, int* idx, float* d2, int cap);
+void orc_set_ext_radius(orc_ext_radius_fn f);
 
 /* a2  transformPointCloud  mapOptmization.cpp:637-667; pose6 = [rx ry rz tx ty tz]. */
 void orc_transform_cloud(const orc_p4* in, int n, const float pose6[6], orc_p4* out);
@@ -115,7 +118,15 @@ void orc_transform_associate_to_map(const float sum[6], const float bef[6], cons
  * graph as pass-through. */
 typedef struct orc_replay orc_replay;
 orc_replay* orc_replay_create(const orc_params* prm, int window);
+/* loop_closure_enabled = 0: the reference's DEFAULT local-map branch (mapOptmization.cpp:1152-1223,
+ * loam_config.yaml:23): radius search on the key poses around currentRobotPosPoint, 1 m VoxelGrid on the hits (the
+ * keyframe id is the (int) of the AVERAGED intensity, :1175/:1197/:1205), cached id list updated by erase / add. */
+orc_replay* orc_replay_create2(const orc_params* prm, int window, int loop_closure_enabled, float search_radius);
+int orc_replay_get_map_ids(orc_replay* r, int* ids, int cap);
+int orc_select_surrounding(const orc_p4* key_poses, int n, const float cur_pos[3], float radius, int* existing_inout,
+                           int n_existing, int cap, int use_ext_radius);
 void orc_replay_destroy(orc_replay* r);
+void orc_replay_set_params(orc_replay* r, const orc_params* prm);
 /* One frame: clouds as the reference receives them after downsampleCurrentScan
  * (corner_scan raw = keyframe corner cloud, corner_scan_ds = corner queries, surf_last_ds and
  * outlier_last_ds = keyframe surf/outlier clouds, surf_total_ds = surf queries). odom = transformSum. */

@@ -47,7 +47,8 @@ def build(force=False):
             os.path.getmtime(os.path.join(_HERE, f)) > os.path.getmtime(_LIB)
             for f in ("oracle.cpp", "oracle.h", "eigen_restate.hpp")):
         subprocess.check_call(["make", "-C", _HERE, "all"], stdout=subprocess.DEVNULL)
-    if os.path.isdir("/root/reference/LeGO-LOAM/include/lego_loam") and (force or not os.path.exists(_REF)):
+    if os.path.isdir("/root/reference/LeGO-LOAM/include/lego_loam") and (
+            force or not os.path.exists(_REF) or os.path.getmtime(os.path.join(_HERE, "nanoflann_ref.cpp")) > os.path.getmtime(_REF)):
         subprocess.check_call(["make", "-C", _HERE, "ref"], stdout=subprocess.DEVNULL)
 
 
@@ -72,6 +73,7 @@ def lib():
         build()
         _lib = C.CDLL(_LIB)
         _lib.orc_replay_create.restype = C.c_void_p
+        _lib.orc_replay_create2.restype = C.c_void_p
         _lib.orc_lm_step.restype = C.c_int
         _lib.orc_voxel_downsample.restype = C.c_int
         if os.path.exists(_REF):
@@ -107,6 +109,35 @@ def set_knn_backend(kind):
     if kind == KNN_NANOFLANN and not have_ref():
         raise RuntimeError("oracle/_ref/libnanoflann_ref.so is not built")
     lib().orc_set_knn_backend(C.c_int(kind))
+
+
+def set_radius_backend(use_nanoflann):
+    """Radius search of the default local-map branch (mapOptmization.cpp:1157): brute force (ties by index) or the
+    reference's own nanoflann radiusSearch (oracle/_ref)."""
+    if use_nanoflann:
+        if not have_ref() or not hasattr(_ref, "ref_kdtree_radius"):
+            raise RuntimeError("oracle/_ref/libnanoflann_ref.so is not built (or predates ref_kdtree_radius)")
+        lib().orc_set_ext_radius(C.cast(_ref.ref_kdtree_radius, C.c_void_p))
+    else:
+        lib().orc_set_ext_radius(C.c_void_p(0))
+
+
+def select_surrounding(key_poses, cur_pos, radius, existing, use_nanoflann=False):
+    """The id selection of extractSurroundingKeyFrames' default branch (:1152-1216) -> new surroundingExistingKeyPosesID."""
+    kp = _p4(key_poses)
+    cap = len(kp) + len(existing) + 1
+    ex = np.zeros(cap, np.int32)
+    ex[:len(existing)] = existing
+    cur = np.ascontiguousarray(cur_pos, np.float32)
+    if use_nanoflann:
+        set_radius_backend(True)
+    try:
+        n = lib().orc_select_surrounding(_ptr(kp), C.c_int(len(kp)), _ptr(cur), C.c_float(radius), _ptr(ex), C.c_int(len(existing)),
+                                         C.c_int(cap), C.c_int(1 if use_nanoflann else 0))
+    finally:
+        if use_nanoflann:
+            set_radius_backend(False)
+    return ex[:n].copy()
 
 
 def transform_cloud(pts, pose6):
@@ -260,8 +291,17 @@ def solve_normal_eq(rows6, b, dof_mask, it, eig_thresh, eigen_mode, matP=None, i
 
 
 class Replay:
-    def __init__(self, prm, window=50):
-        self._h = C.c_void_p(lib().orc_replay_create(C.byref(prm), C.c_int(window)))
+    def __init__(self, prm, window=50, loop_closure_enabled=True, search_radius=50.0):
+        self._h = C.c_void_p(lib().orc_replay_create2(C.byref(prm), C.c_int(window), C.c_int(1 if loop_closure_enabled else 0),
+                                                      C.c_float(search_radius)))
+
+    def set_params(self, prm):
+        lib().orc_replay_set_params(self._h, C.byref(prm))
+
+    def map_ids(self, cap=100000):
+        ids = np.zeros(cap, np.int32)
+        n = lib().orc_replay_get_map_ids(self._h, _ptr(ids), C.c_int(cap))
+        return ids[:n].copy()
 
     def step(self, odom6, corner_scan, corner_scan_ds, surf_last_ds, outlier_last_ds, surf_total_ds):
         a = [_p4(v) for v in (corner_scan, corner_scan_ds, surf_last_ds, outlier_last_ds, surf_total_ds)]

@@ -1,0 +1,178 @@
+"""Parity at BASELINE.json's STATED sizes and on the benchmarked workload (B200 box; `pytest -m gpu`).
+
+tests/test_gpu_parity.py runs every stage on a reduced world so that the brute-force oracle stays cheap; this file
+repeats the end-to-end checks where the sizes are the ones BASELINE.json names:
+
+  configs[0]  one VLP-16 scan (~2 k corner + ~8 k surf queries) against a ~60 k-point local map, 10 LM iterations
+  configs[1]  bench.py's own replay (BENCH_WORLD, 50-keyframe window ~ 100 k points): every checked frame's pose against
+              the oracle registering the same scan on the device's map and prior (bench.py `checks.parity` is this code)
+  configs[2]  HDL-64E scans (64 x 1800) against a ~500 k-point local map (stand-alone kernels: the raw map is > 2^20 points)
+  configs[3]  ~2 M surrounding-map points WITHOUT map downsampling, ~100 k feature queries taken from a real (raw) scan
+  a1 default  the reference's default local-map branch (loop closure off, mapOptmization.cpp:1152-1223): the mirror's
+              keyframe-id sequence against the oracle's restatement of that branch over a long replay
+
+The oracle uses its uniform-grid 5-NN here (pinned to brute force and to the reference's nanoflann in test_oracle.py).
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import rot_err, trans_err, upstream_params
+
+pytestmark = pytest.mark.gpu
+
+TOL_T = 1e-4   # metres, BASELINE.json
+TOL_R = 1e-5   # radians, BASELINE.json
+CACHE = os.environ.get("LLB200_CACHE", "/tmp/llb200_cache")
+
+
+@pytest.fixture(scope="module")
+def abi():
+    import __graft_entry__ as ge
+    ge.build()
+    from lego_loam_sr_b200 import abi as _abi
+    return _abi
+
+
+@pytest.fixture(scope="module")
+def bench():
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    import bench as _b
+    return _b
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def _oracle_map(orc, d, prm):
+    kf = d["keyframes"]
+    return orc.build_local_map(d["key_poses"], [f["corner_scan"] for f in kf], [f["surf_last_ds"] for f in kf],
+                               [f["outlier_last_ds"] for f in kf], prm)
+
+
+def _full_check(abi, orc, d, cq, sq, map_downsample=1, knn_sample=4000, label=""):
+    """Maps bit-exact, 5-NN bit-exact on a query sample, residual records, pose after 10 iterations."""
+    kw = dict(map_downsample=map_downsample)
+    oprm = upstream_params(orc, **kw)
+    cds, sds, ncr, nsr = _oracle_map(orc, d, oprm)
+    kf = d["keyframes"]
+    with abi.Handle(upstream_params(abi, lm_solver=1, **kw)) as h:
+        for i, f in enumerate(kf):
+            h.add_keyframe(i, f["corner_scan"], f["surf_last_ds"], f["outlier_last_ds"], d["key_poses"][i])
+        h.build_local_map(list(range(len(kf))))
+        pose, res = h.scan2map(cq, sq, d["prior"])
+        gc, gs = h.get_map_ds(0), h.get_map_ds(1)
+        assert np.array_equal(bits(gc), bits(cds)), "corner map differs from the oracle"
+        assert np.array_equal(bits(gs), bits(sds)), "surf map differs from the oracle"
+        # 5-NN of the (prior-transformed) queries: indices and squared distances, bit for bit
+        rng = np.random.default_rng(5)
+        for which, q, m in ((0, cq, cds), (1, sq, sds)):
+            qs = q[rng.choice(len(q), min(knn_sample, len(q)), replace=False)]
+            qm = orc.transform_cloud(qs, d["prior"])
+            idx, d2, acc = h.knn5(which, qm)
+            oidx, od2 = orc.knn5(m, qm, backend=orc.KNN_GRID)
+            oacc = (oidx[:, 4] >= 0) & (od2[:, 4] < 1.0)
+            assert np.array_equal(acc.astype(bool), oacc)
+            assert np.array_equal(idx[oacc], oidx[oacc]) and np.array_equal(bits(d2[oacc]), bits(od2[oacc]))
+        # residual records at the prior
+        for name, q, m in (("corner", cq, cds), ("surf", sq, sds)):
+            g = getattr(h, name + "_residuals")(q, d["prior"])
+            o = getattr(orc, name + "_residuals")(m, q, d["prior"], oprm)
+            assert np.array_equal(g["accept"], o["accept"]), name
+            assert (g["mask"] != o["mask"]).sum() <= max(3, len(q) // 2000), name
+            both = (g["mask"] != 0) & (o["mask"] != 0)
+            assert np.abs(g["coeff"][both] - o["coeff"][both]).max() <= 2e-5, name
+    ores, opose, _ = orc.scan2map(cds, sds, cq, sq, d["prior"], oprm)
+    assert res.status == 0 and res.iter_num == ores.iter_num == 10
+    assert abs(res.sel_num - ores.sel_num) <= max(3, ores.sel_num // 2000)
+    dt, dr = trans_err(pose, opose), rot_err(pose, opose)
+    print("%s: map %d + %d points (raw %d + %d), queries %d + %d, residuals %d; pose |dt| %.2e m |dr| %.2e rad vs oracle"
+          % (label, len(cds), len(sds), ncr, nsr, len(cq), len(sq), res.sel_num, dt, dr))
+    assert dt <= TOL_T and dr <= TOL_R, (dt, dr)
+    return pose, res
+
+
+def test_config0_stated_size(abi, orc, synth, bench):
+    """configs[0]: ~2 k corner + ~8 k surf queries against a ~60 k-point local map."""
+    d = synth.make_single(seed=1, n_map_scans=24, step=bench.BENCH_STEP_M, world_kw=bench.BENCH_WORLD)
+    q = d["query"]
+    assert 1200 <= len(q["corner_scan_ds"]) <= 3000 and 6000 <= len(q["surf_total_ds"]) <= 10000
+    _, res = _full_check(abi, orc, d, q["corner_scan_ds"], q["surf_total_ds"], label="configs[0]")
+    assert 45_000 <= res.corner_map_ds + res.surf_map_ds <= 80_000, (res.corner_map_ds, res.surf_map_ds)
+
+
+def test_bench_replay_parity(abi, orc, bench):
+    """configs[1] on bench.py's own workload: the frames bench.py times, checked by the code behind its `checks.parity`."""
+    n_check = 12
+    data = bench.make_data(2, bench.WINDOW + n_check)
+    par = bench.replay_parity(data, device=0, prefill=bench.WINDOW, steps=n_check, every=1)
+    print("bench replay parity:", par)
+    assert par["frames_checked"] == n_check
+    assert par["max_dt_m"] <= TOL_T and par["max_dr_rad"] <= TOL_R, par
+    assert par["ok"]
+    assert 80_000 <= par["map_points_mean"] <= 160_000 and 8_000 <= par["queries_mean"] <= 12_000, par
+
+
+def test_config2_hdl64_500k_map(abi, orc, bench):
+    """configs[2]: HDL-64E-shaped scans against a ~500 k-point local map (grid build + 5-NN at scale)."""
+    d = bench.make_hdl64_problem("c2")
+    q = d["query"]
+    _, res = _full_check(abi, orc, d, q["corner_scan_ds"], q["surf_total_ds"], label="configs[2]")
+    assert 400_000 <= res.corner_map_ds + res.surf_map_ds <= 700_000, (res.corner_map_ds, res.surf_map_ds)
+    assert len(q["corner_scan_ds"]) + len(q["surf_total_ds"]) >= 12_000
+
+
+def test_config3_dense_map_no_downsampling(abi, orc, bench):
+    """configs[3]: ~2 M surrounding-map points, map_downsample = 0, ~100 k feature queries = one RAW HDL-64E scan's
+    corner and surf clouds (not map samples)."""
+    d = bench.make_hdl64_problem("c3")
+    cq, sq = d["raw_query"]
+    assert len(cq) + len(sq) >= 80_000
+    _, res = _full_check(abi, orc, d, cq, sq, map_downsample=0, label="configs[3]")
+    assert res.corner_map_ds + res.surf_map_ds >= 1_800_000, (res.corner_map_ds, res.surf_map_ds)
+
+
+def test_default_local_map_branch_matches_oracle(abi, orc, synth):
+    """a1, the reference's DEFAULT branch (loop closure off): radius search on key poses, 1 m VoxelGrid on them, the
+    (int) of the averaged intensity as keyframe id, erase / add of the cached set (mapOptmization.cpp:1152-1223).
+    The mirror's keyframe-id list must equal the oracle's restatement frame by frame, and so must the poses."""
+    from conftest import SMALL_WORLD
+    from lego_loam_sr_b200 import host
+    n, radius = 200, 25.0
+    seq = synth.make_sequence(seed=5, n_scans=n, step=0.8, world_kw=SMALL_WORLD, cache_dir=CACHE)
+    kw = dict(iter_count_thres=10, stop_thres=0.0)
+    mo = host.MapOptimization(upstream_params(abi, lm_solver=1, **kw), loop_closure_enabled=False, search_num=50, search_radius=radius)
+    rp = orc.Replay(upstream_params(orc, **kw), window=50, loop_closure_enabled=False, search_radius=radius)
+    view = mo.abi_handle()
+    oprm = upstream_params(orc, **kw)
+    removed = thinned = 0
+    worst_t = worst_r = 0.0
+    prev = np.zeros(0, np.int32)
+    for k, f in enumerate(seq["frames"]):
+        pose, res = mo.process_frame(seq["odom"][k], f, pre_downsampled=True)
+        ores, nc, ns = rp.step(seq["odom"][k], f["corner_scan"], f["corner_scan_ds"], f["surf_last_ds"], f["outlier_last_ds"],
+                               f["surf_total_ds"])
+        if k == 0:
+            continue
+        ids, oids = mo.map_ids, rp.map_ids()
+        assert np.array_equal(ids, oids), (k, ids, oids)
+        removed += len(set(prev.tolist()) - set(ids.tolist()))
+        thinned += int(len(ids) < k and k <= 20)
+        prev = ids
+        assert res.status == ores.status == 0, k
+        if k % 10 == 0 or k == n - 1:  # strict: the oracle on the device's own map and prior
+            gc, gs = view.get_map_ds(0), view.get_map_ds(1)
+            fres, fpose, _ = orc.scan2map(gc, gs, f["corner_scan_ds"], f["surf_total_ds"], mo.last_prior, oprm)
+            worst_t, worst_r = max(worst_t, trans_err(pose, fpose)), max(worst_r, rot_err(pose, fpose))
+        assert trans_err(pose, ores.pose) <= 5e-3 and rot_err(pose, ores.pose) <= 5e-4, k  # two independent replays
+    assert removed > 0, "the replay never dropped a keyframe from the surrounding set: the erase path went untested"
+    assert len(prev) < n - 1
+    assert worst_t <= TOL_T and worst_r <= TOL_R, (worst_t, worst_r)
+    print("default branch: %d frames, final set %d keyframes, %d removals; worst |dt| %.2e m |dr| %.2e rad" % (n, len(prev), removed, worst_t, worst_r))
+    mo.close()
+    rp.close()

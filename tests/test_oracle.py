@@ -336,3 +336,17 @@ def test_fa_correspondences_oracle(orc, synth):
         assert (np.linalg.norm(c5[kk, :3], axis=1) <= 1.0 + 1e-6).all() and (np.linalg.norm(c5[kk, :3], axis=1) > 0.1).all()
         # with transformCur = 0 TransformToStart is the identity
         assert np.array_equal(orc.fa_transform_to_start(q, np.zeros(6, np.float32))[:, :3].view(np.uint32), q[:, :3].view(np.uint32))
+
+
+def test_default_branch_selection_against_reference_radius_search(orc):
+    """The id selection with brute-force radius search equals the same with the reference's nanoflann radiusSearch."""
+    if not orc.have_ref():
+        pytest.skip("oracle/_ref not built")
+    n = 400
+    t = np.linspace(0, 1, n)
+    kp = np.stack([60 * np.sin(4 * np.pi * t), 0.02 * np.sin(30 * t), 90 * np.sin(2 * np.pi * t), np.arange(n)], 1).astype(np.float32)
+    a = b = np.zeros(0, np.int32)
+    for k in range(3, n, 5):
+        a = orc.select_surrounding(kp[:k], kp[k - 1, :3], 50.0, a)
+        b = orc.select_surrounding(kp[:k], kp[k - 1, :3], 50.0, b, use_nanoflann=True)
+        assert np.array_equal(a, b), k
