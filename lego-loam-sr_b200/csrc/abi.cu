@@ -4,6 +4,7 @@
 // reach the GPU fails with LL_ERR_CUDA and ll_last_error_string() says why.
 #include "../../include/legoloam_b200.h"
 
+#include <algorithm>
 #include <cmath>
 #if defined(__SSE2__)
 #include <emmintrin.h>
@@ -129,6 +130,24 @@ struct ll_handle_s {
   uint64_t scan_seq = 0;
   int partial_blocks = 0;
   bool scan_pending = false;
+  bool smem_opt_in[4] = {false, false, false, false};
+
+  // ---- incremental local map (map_incremental.cuh): the device-resident window of the two surrounding maps
+  struct Window {
+    bool valid = false;             // the window arrays hold exactly the keyframes `ids`, in this order
+    std::vector<int> ids;           // keyframes in the window
+    std::vector<int> last_ids;      // ids of the previous ll_build_local_map, whatever path it took (stream detection)
+    int cur = 0;                    // buffer index of the current window
+    int n[2] = {0, 0};              // entries per map
+    size_t cap[2] = {0, 0};
+    WindowBuffers wb[2] = {};
+    bool job_pending = false;       // the last merge of the current build is left to the next scan kernel / ensure_map()
+    IncJob job = {};
+    bool inc_opt_in = false;        // map_inc_kernel's dynamic shared memory attribute set
+  } win;
+  bool scan_used_inc = false;       // the scan in flight assembled its map incrementally (retry in full on inc_fail)
+  bool retried = false;
+  float pose_in[6] = {0, 0, 0, 0, 0, 0};
   int iters_enqueued = 0;
   int lm_blocks = 0;
 
@@ -480,6 +499,7 @@ int seglist_to_device(ll_handle h) {
 }
 
 int run_grid_build(ll_handle h);
+int plan_incremental_restart(ll_handle h, const int* ids, int n_ids, bool* used);
 
 // The MapBatch of the slots in h->grid_cfg, with the sort problems of the voxel phase or of the grid phase.
 MapBatch make_map_batch(const ll_handle h, bool grid_phase) {
@@ -503,6 +523,270 @@ MapBatch make_map_batch(const ll_handle h, bool grid_phase) {
 int ensure_map(ll_handle h);
 int ensure_grid(ll_handle h);
 int run_voxel_build(ll_handle h, bool want_member);
+
+// ---- incremental local map: host side --------------------------------------------------------------------------
+void window_invalidate(ll_handle h) {
+  h->win.valid = false;
+  h->win.job_pending = false;
+  h->win.ids.clear();
+  h->win.n[0] = h->win.n[1] = 0;
+}
+
+void window_free(ll_handle h) {
+  for (int m = 0; m < 2; ++m) {
+    WindowBuffers& W = h->win.wb[m];
+    void* ptrs[] = {W.pts[0], W.pts[1], W.key[0], W.key[1], W.tag[0], W.tag[1], W.run_pts, W.run_key, W.run_tag,
+                    W.stage_pts, W.stage_tag, W.counts};
+    for (void* p : ptrs)
+      if (p) cudaFree(p);
+    W = WindowBuffers();
+    h->win.cap[m] = 0;
+  }
+  window_invalidate(h);
+}
+
+// Window arrays of map m for at least `need` entries. Growing them drops the window (the next build starts it afresh).
+int ensure_window(ll_handle h, int m, size_t need) {
+  WindowBuffers& W = h->win.wb[m];
+  if (h->win.cap[m] >= need && W.pts[0]) return LL_OK;
+  LL_CUDA(h, cudaStreamSynchronize(h->stream));
+  {
+    void* ptrs[] = {W.pts[0], W.pts[1], W.key[0], W.key[1], W.tag[0], W.tag[1]};
+    for (void* p : ptrs)
+      if (p) LL_CUDA(h, cudaFree(p));
+  }
+  window_invalidate(h);
+  const size_t cap = std::max<size_t>(need + need / 2 + 4096, h->slot[m].cap);
+  auto A = [&](void** p, size_t bytes) -> int {
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e != cudaSuccess) return fail(h, LL_ERR_NOMEM, std::string("cudaMalloc(window): ") + cudaGetErrorString(e));
+    return LL_OK;
+  };
+  for (int k = 0; k < 2; ++k) {
+    W.pts[k] = nullptr; W.key[k] = nullptr; W.tag[k] = nullptr;
+    LL_TRY(A(reinterpret_cast<void**>(&W.pts[k]), cap * sizeof(float4)));
+    LL_TRY(A(reinterpret_cast<void**>(&W.key[k]), cap * sizeof(unsigned long long)));
+    LL_TRY(A(reinterpret_cast<void**>(&W.tag[k]), cap * sizeof(uint32_t)));
+  }
+  if (!W.run_pts) {
+    LL_TRY(A(reinterpret_cast<void**>(&W.run_pts), INC_RUN_MAX * sizeof(float4)));
+    LL_TRY(A(reinterpret_cast<void**>(&W.run_key), INC_RUN_MAX * sizeof(unsigned long long)));
+    LL_TRY(A(reinterpret_cast<void**>(&W.run_tag), INC_RUN_MAX * sizeof(uint32_t)));
+    LL_TRY(A(reinterpret_cast<void**>(&W.stage_pts), INC_RUN_MAX * sizeof(float4)));
+    LL_TRY(A(reinterpret_cast<void**>(&W.stage_tag), INC_RUN_MAX * sizeof(uint32_t)));
+    LL_TRY(A(reinterpret_cast<void**>(&W.counts), 2 * INC_MAX_BLOCKS * sizeof(uint32_t)));
+  }
+  h->win.cap[m] = cap;
+  return LL_OK;
+}
+
+// new = (old with some members dropped, order kept) + appended members that are not in old?
+bool sliding_relation(const std::vector<int>& old_ids, const int* ids, int n_ids, std::vector<int>& removed, int& n_kept) {
+  removed.clear();
+  int i = 0;
+  for (int id : old_ids) {
+    if (i < n_ids && ids[i] == id) ++i;
+    else removed.push_back(id);
+  }
+  n_kept = i;
+  for (int k = i; k < n_ids; ++k) {  // an appended id must be new (a dropped member coming back changes its position)
+    for (int id : old_ids)
+      if (id == ids[k]) return false;
+    for (int j = i; j < k; ++j)
+      if (ids[j] == ids[k]) return false;
+  }
+  return true;
+}
+
+int blocks_for_inc(ll_handle h) {
+  int nb = h->num_sms;
+  if (h->prm.lm_max_blocks > 0) nb = std::min(nb, h->prm.lm_max_blocks);
+  return std::max(1, std::min(nb, INC_MAX_BLOCKS));
+}
+
+int launch_inc_step(ll_handle h, const IncJob& J) {
+  if (!h->win.inc_opt_in) {
+    LL_CUDA(h, cudaFuncSetAttribute(map_inc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, INC_SMEM_BYTES));
+    h->win.inc_opt_in = true;
+  }
+  MapBatch B = make_map_batch(h, false);
+  unsigned* bar = h->d_barriers + (h->scan_seq % kBarrierSlots);
+  unsigned* bar_clear = h->d_barriers + ((h->scan_seq + kBarrierSlots / 2) % kBarrierSlots);
+  h->scan_seq++;
+  IncJob Jc = J;
+  void* args[] = {&Jc, &B, &bar, &bar_clear};
+  LL_PROF(h, 3);
+  LL_CUDA(h, cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(map_inc_kernel), dim3((unsigned)blocks_for_inc(h)),
+                                         dim3(GI_THREADS), args, (size_t)INC_SMEM_BYTES, h->stream));
+  LL_LAUNCHED(h);
+  return LL_OK;
+}
+
+// Tries to bring the window from its current content to `ids` by merges (map_incremental.cuh). *used = false: the
+// caller takes the full path. All merges but the last are launched here; the last one (which also computes
+// laserCloud*FromMapDS) is left pending for the next scan kernel (or ensure_map()).
+int plan_incremental(ll_handle h, const int* ids, int n_ids, bool* used) {
+  *used = false;
+  static const bool disabled = std::getenv("LLB200_NO_INCREMENTAL_MAP") != nullptr;  // A/B switch for measurements
+  auto& win = h->win;
+  std::vector<int> last = win.last_ids;
+  win.last_ids.assign(ids, ids + n_ids);
+  if (disabled || !h->prm.map_downsample || !h->prm.persistent_lm || n_ids == 0) return LL_OK;
+  std::vector<int> removed;
+  int n_kept = 0;
+  if (win.job_pending) {
+    // the previous build's last merge was never executed (no scan, no other consumer in between)
+    if (win.valid && (int)win.ids.size() == n_ids && std::equal(win.ids.begin(), win.ids.end(), ids)) {
+      *used = true;  // the same list again: that merge is still exactly what is needed
+      return LL_OK;
+    }
+    win.job_pending = false;  // a different list: the merge runs now, as the base of the next one
+    h->map_deferred = false;
+    LL_TRY(launch_inc_step(h, win.job));
+  }
+  bool from_window = win.valid && sliding_relation(win.ids, ids, n_ids, removed, n_kept);
+  if (!from_window) {
+    // Start a window only for a list that ADVANCED from the previous call's (a sliding set of keyframes); a list built
+    // once, or rebuilt identically, is cheaper through the full path.
+    std::vector<int> rem2;
+    int kept2 = 0;
+    const bool advanced = sliding_relation(last, ids, n_ids, rem2, kept2) && n_ids - kept2 >= 1 && n_ids - kept2 <= 2;
+    if (!advanced) {
+      window_invalidate(h);
+      return LL_OK;
+    }
+    window_invalidate(h);
+    removed.clear();
+    n_kept = 0;
+  }
+  // group the appended keyframes: <= INC_RUN_MAX points per map and <= INC_MAX_SEGS / 3 keyframes per merge
+  struct Step { std::vector<int> add; std::vector<int> dead; };
+  std::vector<Step> steps;
+  {
+    Step cur;
+    int pc = 0, ps = 0;
+    for (int k = n_kept; k < n_ids; ++k) {
+      const Keyframe& kf = h->kfs[ids[k]];
+      const int c = kf.n[0], sfo = kf.n[1] + kf.n[2];
+      if (c > INC_RUN_MAX || sfo > INC_RUN_MAX) {  // a single keyframe too large for one run: full path
+        window_invalidate(h);
+        return LL_OK;
+      }
+      if (!cur.add.empty() && (pc + c > INC_RUN_MAX || ps + sfo > INC_RUN_MAX || (int)cur.add.size() >= INC_MAX_SEGS / 3)) {
+        steps.push_back(cur);
+        cur = Step();
+        pc = ps = 0;
+      }
+      cur.add.push_back(ids[k]);
+      pc += c;
+      ps += sfo;
+    }
+    if (!cur.add.empty()) steps.push_back(cur);
+  }
+  {  // spread the dropped keyframes over the steps, INC_MAX_DEAD per merge (extra merges without additions if needed)
+    size_t si = 0;
+    for (size_t r = 0; r < removed.size(); ++r) {
+      while (si < steps.size() && (int)steps[si].dead.size() >= INC_MAX_DEAD) ++si;
+      if (si == steps.size()) steps.push_back(Step());
+      steps[si].dead.push_back(removed[r]);
+    }
+  }
+  if (steps.empty()) {  // the same keyframes as last time: the maps on the device are current
+    *used = true;
+    win.job_pending = false;
+    return LL_OK;
+  }
+  if (from_window && steps.size() > 3) {  // a large change: cheaper in full (and the window is rebuilt when the list advances again)
+    window_invalidate(h);
+    return LL_OK;
+  }
+  // sizes after every step must fit the window arrays
+  size_t need[2] = {0, 0};
+  for (int k = 0; k < n_ids; ++k) {
+    const Keyframe& kf = h->kfs[ids[k]];
+    need[0] += (size_t)kf.n[0];
+    need[1] += (size_t)kf.n[1] + kf.n[2];
+  }
+  size_t peak[2] = {std::max<size_t>(need[0], (size_t)win.n[0]) + INC_RUN_MAX, std::max<size_t>(need[1], (size_t)win.n[1]) + INC_RUN_MAX};
+  const bool had_window = win.valid;
+  for (int m = 0; m < 2; ++m) LL_TRY(ensure_window(h, m, peak[m]));
+  if (had_window && !win.valid) {  // the arrays had to grow: what they held is gone — start over from an empty window
+    return plan_incremental_restart(h, ids, n_ids, used);
+  }
+  h->grid_cfg = {0, 1, h->prm.corner_leaf, h->prm.surf_leaf, 1, 1};
+  std::vector<int> cur_ids = win.valid ? win.ids : std::vector<int>();
+  for (size_t si = 0; si < steps.size(); ++si) {
+    const Step& st = steps[si];
+    IncJob J;
+    std::memset(&J, 0, sizeof(J));
+    J.w[0] = win.wb[0];
+    J.w[1] = win.wb[1];
+    J.cur = win.cur;
+    J.n_old[0] = win.n[0];
+    J.n_old[1] = win.n[1];
+    int out[2] = {win.n[0], win.n[1]};
+    J.n_dead = (int)st.dead.size();
+    for (int k = 0; k < J.n_dead; ++k) {
+      J.dead[k] = (uint32_t)st.dead[k];
+      const Keyframe& kf = h->kfs[st.dead[k]];
+      out[0] -= kf.n[0];
+      out[1] -= kf.n[1] + kf.n[2];
+      cur_ids.erase(std::find(cur_ids.begin(), cur_ids.end(), st.dead[k]));
+    }
+    int oc = 0, os = 0, ns = 0;
+    for (int id : st.add) {
+      Keyframe& kf = h->kfs[id];
+      if (!kf.trig_valid) {
+        kf.trig = SegList::pose_trig(kf.pose);
+        kf.trig_valid = true;
+      }
+      const float4* src[3] = {kf.d[0], kf.d[1], kf.d[2]};
+      const int cnt[3] = {kf.n[0], kf.n[1], kf.n[2]};
+      for (int c = 0; c < 3; ++c) {
+        if (cnt[c] <= 0) continue;
+        Segment& g = J.segs[ns++];
+        std::memset(&g, 0, sizeof(g));
+        g.src = src[c];
+        g.count = cnt[c];
+        g.map = c == 0 ? 0 : 1;
+        g.dst_off = c == 0 ? oc : os;
+        g.identity = 0;
+        g.t = kf.trig;
+        g.pad[0] = id;
+        (c == 0 ? oc : os) += cnt[c];
+      }
+      cur_ids.push_back(id);
+    }
+    J.n_segs = ns;
+    J.n_new[0] = oc;
+    J.n_new[1] = os;
+    J.n_out[0] = out[0] + oc;
+    J.n_out[1] = out[1] + os;
+    J.final_step = si + 1 == steps.size() ? 1 : 0;
+    win.cur ^= 1;  // (as enqueued: everything below is stream-ordered)
+    win.n[0] = J.n_out[0];
+    win.n[1] = J.n_out[1];
+    if (J.final_step) {
+      win.job = J;
+      win.job_pending = true;
+    } else {
+      LL_TRY(launch_inc_step(h, J));
+    }
+  }
+  win.ids = cur_ids;
+  win.valid = true;
+  h->slot[0].n_raw = win.n[0];
+  h->slot[1].n_raw = win.n[1];
+  *used = true;
+  return LL_OK;
+}
+
+int plan_incremental_restart(ll_handle h, const int* ids, int n_ids, bool* used) {
+  // (window arrays reallocated: the previous list must look like the one before this call for stream detection)
+  std::vector<int> prev(ids, ids + std::max(0, n_ids - 1));
+  h->win.last_ids = prev;
+  return plan_incremental(h, ids, n_ids, used);
+}
 
 // Run the map pipeline on slots (sa, sb) (sb < 0: single problem). The raw clouds are described by L.
 // With persistent_lm the work on the two surrounding maps is only PREPARED here (segment table uploaded, MapState
@@ -641,9 +925,29 @@ int run_voxel_build(ll_handle h, bool want_member) {
   return LL_OK;
 }
 
+int build_local_map_full(ll_handle h, const int* ids, int n_ids);
+
 int ensure_map(ll_handle h) {
   if (!h->map_deferred) return LL_OK;
   h->map_deferred = false;
+  if (h->win.job_pending) {  // the last merge of an incremental build, as its own launch; then look at its verdict
+    h->win.job_pending = false;
+    LL_TRY(launch_inc_step(h, h->win.job));
+    int fail_flag[2] = {0, 0};
+    for (int m = 0; m < 2; ++m)
+      LL_CUDA(h, cudaMemcpyAsync(&fail_flag[m], &h->slot[m].st()->inc_fail, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    LL_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (fail_flag[0] || fail_flag[1]) {  // not representable incrementally: the same keyframes through the full path
+      const std::vector<int> ids = h->win.ids;
+      window_invalidate(h);
+      LL_TRY(build_local_map_full(h, ids.data(), (int)ids.size()));
+      if (h->map_deferred) {
+        h->map_deferred = false;
+        return run_voxel_build(h, false);
+      }
+    }
+    return LL_OK;
+  }
   return run_voxel_build(h, false);
 }
 
@@ -793,12 +1097,23 @@ int scan2map_enqueue(ll_handle h, const float pose6[6]) {
   if (!h->map_ready) return fail(h, LL_ERR_STATE, "scan2map called before ll_build_local_map / ll_set_local_map_raw");
   if (!pose6) return fail(h, LL_ERR_INVALID_ARG, "pose6 is NULL");
   const int nq = h->nq[0] + h->nq[1];
+  std::memcpy(h->pose_in, pose6, sizeof(h->pose_in));
   h->lm_blocks = lm_grid_blocks(h, nq);
   if (h->prm.persistent_lm && (h->grid_deferred || h->map_deferred)) h->lm_blocks = h->num_sms;  // one tile per block
+  const bool inc_pending = h->map_deferred && h->win.job_pending;
+  if (inc_pending) h->lm_blocks = std::min(h->lm_blocks, INC_MAX_BLOCKS);
   if (h->prm.persistent_lm && h->prm.lm_max_blocks > 0) {
     // The caller shares the GPU between several scans in flight (batched replay): a smaller co-resident grid per scan.
     h->lm_blocks = std::min(h->lm_blocks, std::min(h->prm.lm_max_blocks, h->num_sms));
-    if (h->map_deferred || h->grid_deferred) {  // one 16 x 512 tile per block must hold both maps, else stand-alone kernels
+    if (inc_pending) {
+      // the merge works with any number of blocks; the search grids need one 16 x 512 tile per block for the
+      // DOWNSAMPLED maps, whose sizes the host only knows from the previous scan: estimate with a margin, and the
+      // scan is rerun on stand-alone grids should the kernel find that they do not fit (flags bit 2, see collect)
+      const long t = 16L * LM_THREADS;
+      const long est0 = std::max<long>(h->h_state->corner_map_ds, 1) * 5 / 4 + 4096, est1 = std::max<long>(h->h_state->surf_map_ds, 1) * 5 / 4 + 4096;
+      const long tiles = (std::min<long>(est0, h->slot[0].n_raw) + t - 1) / t + (std::min<long>(est1, h->slot[1].n_raw) + t - 1) / t;
+      if (tiles > h->lm_blocks) LL_TRY(ensure_grid(h));
+    } else if (h->map_deferred || h->grid_deferred) {  // one 16 x 512 tile per block must hold both maps, else stand-alone kernels
       const long t = 16L * LM_THREADS;
       const long tiles = (h->slot[0].n_raw + t - 1) / t + (h->slot[1].n_raw + t - 1) / t;
       if (tiles > h->lm_blocks) LL_TRY(ensure_grid(h));  // (builds the map first)
@@ -814,8 +1129,12 @@ int scan2map_enqueue(ll_handle h, const float pose6[6]) {
     unsigned* bar_clear = h->d_barriers + ((h->scan_seq + kBarrierSlots / 2) % kBarrierSlots);
     h->scan_seq++;
     MapBatch GB = make_map_batch(h, true);
-    int build_map = h->map_deferred ? 1 : 0, build_grid = h->grid_deferred ? 1 : 0;
+    int build_map = h->map_deferred ? (h->win.job_pending ? 2 : 1) : 0, build_grid = h->grid_deferred ? 1 : 0;
     h->map_deferred = h->grid_deferred = false;
+    h->scan_used_inc = build_map == 2;
+    static IncJob no_job = {};
+    IncJob job = build_map == 2 ? h->win.job : no_job;
+    h->win.job_pending = false;
     const Segment* segs = h->d_segs;
     const BlockJob* jobs = h->d_jobs;
     if (build_map && h->seg_staged) {  // read the segment table where it was staged (pinned, device-accessible)
@@ -825,7 +1144,7 @@ int scan2map_enqueue(ll_handle h, const float pose6[6]) {
     int n_jobs = h->n_jobs;
     A.st_host = h->h_state;  // block 0 writes the result straight into the pinned mirror
     void* args[] = {&A, &p[0], &p[1], &p[2], &p[3], &p[4], &p[5], &bar, &bar_clear, &GB, &build_map, &build_grid,
-                    &segs, &jobs, &n_jobs};
+                    &segs, &jobs, &n_jobs, &job};
     LL_PROF(h, 8);
     // kFresh: this launch writes `sorted` / `cells` itself, so the LM loop must not read them through ld.global.nc
     const bool fresh = build_map || build_grid;
@@ -833,8 +1152,13 @@ int scan2map_enqueue(ll_handle h, const float pose6[6]) {
                                                   : reinterpret_cast<const void*>(lm_persistent_kernel<1, false>))
                                          : (fresh ? reinterpret_cast<const void*>(lm_persistent_kernel<0, true>)
                                                   : reinterpret_cast<const void*>(lm_persistent_kernel<0, false>));
+    const int ki = (h->prm.eigen_mode ? 2 : 0) + (fresh ? 1 : 0);
+    if (!h->smem_opt_in[ki]) {  // opt in to > 48 KB of dynamic shared memory, once per kernel (and device: per handle)
+      LL_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, LM_PERSISTENT_SMEM));
+      h->smem_opt_in[ki] = true;
+    }
     LL_CUDA(h, cudaLaunchCooperativeKernel(kern, dim3((unsigned)h->lm_blocks),
-                                           dim3(LM_THREADS), args, 0, h->stream));
+                                           dim3(LM_THREADS), args, (size_t)LM_PERSISTENT_SMEM, h->stream));
     LL_LAUNCHED(h);
     LL_TRY(seglist_release(h));
     h->iters_enqueued = h->prm.iter_count_thres;
@@ -877,6 +1201,28 @@ int scan2map_collect(ll_handle h, float pose6_out[6], ll_result* res) {
     LL_TRY(enqueue_iterations(h, more));
   }
   h->scan_pending = false;
+  if (h->scan_used_inc && !h->retried && (h->h_state->flags & (8 | 4))) {
+    // The incremental assembly met a case it cannot represent (flags bit 3), or the in-kernel search grids did not fit
+    // the blocks this scan was given (bit 2 on a size estimate): the same keyframes through the full path / the
+    // stand-alone grid kernels, and the scan again. (A grid that is genuinely too large comes back with bit 2 again.)
+    const bool inc_failed = (h->h_state->flags & 8) != 0;
+    const std::vector<int> ids = h->win.ids;
+    h->scan_used_inc = false;
+    h->retried = true;
+    int rc = LL_OK;
+    if (inc_failed) {
+      window_invalidate(h);
+      rc = build_local_map_full(h, ids.data(), (int)ids.size());
+    } else {
+      h->grid_deferred = true;
+      rc = ensure_grid(h);
+    }
+    if (rc == LL_OK) rc = scan2map_enqueue(h, h->pose_in);
+    if (rc == LL_OK) rc = scan2map_collect(h, pose6_out, res);
+    h->retried = false;
+    return rc;
+  }
+  h->scan_used_inc = false;
   if (pose6_out) std::memcpy(pose6_out, h->h_state->pose, 6 * sizeof(float));
   if (res) fill_result(*h->h_state, res);
   return LL_OK;
@@ -1014,6 +1360,7 @@ int ll_destroy(ll_handle h) {
     if (h->pin_buf[i]) cudaFreeHost(h->pin_buf[i]);
     if (h->pin_evt[i]) cudaEventDestroy(h->pin_evt[i]);
   }
+  window_free(h);
   if (h->h_state) cudaFreeHost(h->h_state);
   if (h->res_pin) cudaFreeHost(h->res_pin);
   if (h->scan_buf) cudaFree(h->scan_buf);
@@ -1045,6 +1392,11 @@ int ll_set_params(ll_handle h, const ll_params* p) {
   if (!h) return LL_ERR_INVALID_ARG;
   if (h->scan_pending) return fail(h, LL_ERR_STATE, "a scan2map is still in flight: call ll_scan2map_wait first");
   LL_TRY(validate_params(h, p));
+  if (p->corner_leaf != h->prm.corner_leaf || p->surf_leaf != h->prm.surf_leaf || p->map_downsample != h->prm.map_downsample ||
+      p->persistent_lm != h->prm.persistent_lm) {
+    if (h->win.job_pending) LL_TRY(ensure_map(h));  // (finish a prepared merge under the parameters it was planned with)
+    window_invalidate(h);
+  }
   h->prm = *p;
   return LL_OK;
 }
@@ -1134,6 +1486,10 @@ static int store_keyframe_clouds(ll_handle h, int id, Keyframe kf, const void* c
     LL_CUDA(h, cudaEventRecord(h->pin_evt[h->pin_cur], st));
   }
   if (st == h->stream) {
+    if (std::find(h->win.ids.begin(), h->win.ids.end(), id) != h->win.ids.end()) {  // its old points are in the window
+      if (h->win.job_pending) LL_TRY(ensure_map(h));
+      window_invalidate(h);
+    }
     auto old = h->kfs.find(id);  // re-adding an id replaces the entry; the old block is reused by later keyframes. Work
     // already enqueued on the stream that reads the old block runs before anything a later keyframe copies into it
     // (same stream), so handing it back immediately is safe.
@@ -1190,6 +1546,14 @@ int ll_set_keyframe_pose(ll_handle h, int id, const float pose6[6]) {
   if (it == h->kfs.end()) return fail(h, LL_ERR_NOT_FOUND, "unknown keyframe id " + std::to_string(id));
   std::memcpy(it->second.pose, pose6, 6 * sizeof(float));
   it->second.trig_valid = false;
+  // the window holds this keyframe's points transformed by its OLD pose: drop it (the next build starts a new one)
+  if (std::find(h->win.ids.begin(), h->win.ids.end(), id) != h->win.ids.end()) {
+    if (h->win.job_pending) {  // (a prepared but unexecuted merge: the map it would have produced is obsolete anyway)
+      h->map_deferred = h->grid_deferred = false;
+      h->map_ready = false;
+    }
+    window_invalidate(h);
+  }
   return LL_OK;
 }
 
@@ -1232,6 +1596,30 @@ int ll_build_local_map(ll_handle h, const int* ids, int n_ids) {
   if (nc > 0x3fffffff || ns > 0x3fffffff) return fail(h, LL_ERR_INVALID_ARG, "surrounding cloud too large");
   LL_TRY(ensure_slot(h, 0, nc, true));
   LL_TRY(ensure_slot(h, 1, ns, true));
+  // A sliding set of keyframes is assembled incrementally (map_incremental.cuh); anything else in full below.
+  bool inc = false;
+  LL_TRY(plan_incremental(h, ids, n_ids, &inc));
+  if (inc) {
+    if (h->win.job_pending) {
+      h->map_deferred = true;   // the last merge runs at the head of the next scan kernel (or in ensure_map())
+      h->grid_deferred = true;
+    }
+    h->map_ready = true;
+    return LL_OK;
+  }
+  return build_local_map_full(h, ids, n_ids);
+}
+
+}  // extern "C"
+
+namespace {
+int build_local_map_full(ll_handle h, const int* ids, int n_ids) {
+  size_t nc = 0, ns = 0;
+  for (int i = 0; i < n_ids; ++i) {
+    const Keyframe& kf = h->kfs[ids[i]];
+    nc += kf.n[0];
+    ns += (size_t)kf.n[1] + kf.n[2];
+  }
   SegList L;
   int oc = 0, os = 0;
   for (int i = 0; i < n_ids; ++i) {  // cache order = ids order; per keyframe corner | surf, outlier (:1147-1151)
@@ -1251,6 +1639,9 @@ int ll_build_local_map(ll_handle h, const int* ids, int n_ids) {
   h->map_ready = true;
   return LL_OK;
 }
+}  // namespace
+
+extern "C" {
 
 int ll_set_local_map_raw(ll_handle h, const void* corner, size_t n_corner, const void* surf, size_t n_surf,
                          size_t stride_bytes) {
@@ -1261,6 +1652,8 @@ int ll_set_local_map_raw(ll_handle h, const void* corner, size_t n_corner, const
   LL_CUDA(h, cudaSetDevice(h->device));
   LL_TRY(ensure_slot(h, 0, n_corner, true));
   LL_TRY(ensure_slot(h, 1, n_surf, true));
+  window_invalidate(h);
+  h->win.last_ids.clear();
   // Stage the two clouds in the `ds` buffers (free until the VoxelGrid reduce writes them; unused altogether when the map is
   // not downsampled), then run the pipeline with identity segments. Not in `sorted`: the LM loop reads that array
   // through the read-only path, and in the single-kernel scan no SM may have loaded its lines earlier in the launch.

@@ -23,6 +23,7 @@
 #include "fit.cuh"
 #include "map_build.cuh"
 #include "map_inline.cuh"
+#include "map_incremental.cuh"
 #include "solve_warp.cuh"
 
 namespace ll {
@@ -36,6 +37,8 @@ __device__ long long g_tl[TL_ITERS][TL_EVENTS][TL_BLOCKS];
 __device__ unsigned long long g_tl_gt[TL_ITERS][2][TL_BLOCKS];  // %globaltimer: [0] barrier arrive, [1] barrier release
 __device__ long long g_tl_warp[TL_ITERS][8][16];                // block TL_WATCH's warps: sub-stamps of phase 1
 __device__ int g_tl_it;
+__device__ unsigned g_tl_cnt[TL_ITERS][8];  // [0] full searches, [1] heavy (> 128 candidates), [2] set > 32 points, [3] rejected & dense, [4] cached ok, [5] cached attempted
+#define LL_TL_COUNT(k) do { if ((threadIdx.x & 31) == 0 && g_tl_it < TL_ITERS) atomicAdd(&g_tl_cnt[g_tl_it][(k)], 1u); } while (0)
 constexpr int TL_WATCH = 100;
 __device__ __forceinline__ unsigned long long tl_gtime() {
   unsigned long long t;
@@ -58,6 +61,7 @@ __device__ __forceinline__ unsigned long long tl_gtime() {
 #define LL_TL(it, ev) do {} while (0)
 #define LL_TL_GT(it, k) do {} while (0)
 #define LL_TL_WARP(ev) do {} while (0)
+#define LL_TL_COUNT(k) do {} while (0)
 #endif
 
 constexpr int LM_THREADS = 512;
@@ -697,7 +701,11 @@ __device__ __forceinline__ void warp_knn5_batch(const float4* const (&sorted)[2]
                                                 const GridGeom (&geom)[2], const int (&mq)[LM_KNN_BATCH],
                                                 const float4 (&sel)[LM_KNN_BATCH], float max_sq_dist, int lane,
                                                 uint32_t (&od)[LM_KNN_BATCH], uint32_t (&oi)[LM_KNN_BATCH],
-                                                uint32_t (&op)[LM_KNN_BATCH], bool (&acc)[LM_KNN_BATCH]) {
+                                                uint32_t (&op)[LM_KNN_BATCH], bool (&acc)[LM_KNN_BATCH],
+                                                int (&q_start)[LM_KNN_BATCH], int (&q_count)[LM_KNN_BATCH],
+                                                int (&total)[LM_KNN_BATCH]) {
+  // q_start / q_count (per lane: the merged cell row this lane describes, valid on lanes 0, 3, ..., 24) and total (the
+  // number of candidates in the 27 cells, warp-uniform) are returned for knn_cache_fill.
   constexpr int NB = LM_KNN_BATCH;
   constexpr int kRowLane[9] = {12, 3, 9, 15, 21, 0, 6, 18, 24};
   const uint32_t max_bits = __float_as_uint(max_sq_dist);
@@ -714,9 +722,7 @@ __device__ __forceinline__ void warp_knn5_batch(const float4* const (&sorted)[2]
         ce[q] = map_ld<kFresh>(&cells[mq[q] ? 1 : 0][(z * g.dy + y) * g.dx + x]);
     }
   }
-  LL_TL_WARP(1);
   // ---- stage 2: ranges -> candidate addresses -> candidate loads (all queries' loads in flight together)
-  int total[NB], q_start[NB], q_count[NB];
   int srcs[NB][LM_CAND_UNROLL];
   float4 ms[NB][LM_CAND_UNROLL];
 #pragma unroll
@@ -755,7 +761,6 @@ __device__ __forceinline__ void warp_knn5_batch(const float4* const (&sorted)[2]
       ms[q][u] = srcs[q][u] >= 0 ? map_ld<kFresh>(&sorted[mq[q] > 0 ? 1 : 0][srcs[q][u]]) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
-  LL_TL_WARP(2);
   // ---- stage 3: distances and the per-lane sorting network
   uint32_t cdq[NB][LM_CAND_UNROLL], ciq[NB][LM_CAND_UNROLL], cpq[NB][LM_CAND_UNROLL];
 #pragma unroll
@@ -780,7 +785,6 @@ __device__ __forceinline__ void warp_knn5_batch(const float4* const (&sorted)[2]
     }
     LL_KNN_CE(0, 1) LL_KNN_CE(2, 3) LL_KNN_CE(0, 2) LL_KNN_CE(1, 3) LL_KNN_CE(1, 2)
   }
-  LL_TL_WARP(3);
   // ---- stage 4: five selection rounds, the queries' chains interleaved. One redux.sync finds the smallest d2;
   //      a ballot names the lane(s) holding it; only an exact d2 tie between lanes needs the index redux.
 #pragma unroll
@@ -847,6 +851,228 @@ __device__ __forceinline__ void warp_knn5_batch(const float4* const (&sorted)[2]
 }
 #undef LL_KNN_CE
 
+// ---- candidate cache of the single-kernel scan -------------------------------------------------------------------
+// Between two LM iterations the pose moves by millimetres, so a query's five nearest map points almost never change —
+// but "almost" is not parity. What CAN be proven cheaply: let c be the map-frame position of a query when its
+// neighbourhood was last searched in full, d5 its 5th-nearest distance then, and S the set of all map points within
+// R = min(1, d5 + margin) of c (complete, because the 27 one-metre cells around c hold every point within 1 m).
+// Later the query sits at q, delta = |q - c|. Take the five nearest points of q within S, 5th distance D. Every point
+// outside S is farther than R - delta from q, so if  D + delta + slack <= R  no outside point can enter the five
+// (not even as a tie), they are the exact answer, found among <= 32 points in shared memory instead of ~100 in L2:
+// one candidate per lane, no cell table, no address arithmetic, no sorting network. If the test fails (or S has more
+// than 32 points, or fewer than five within range) the query takes the full search again and S is rebuilt around q.
+// The arithmetic on every candidate (distance, (d2, index) order) is the same as in the full search, so the result
+// is bit-identical to it whenever the test passes; slack = 1 mm covers the rounding of the float quantities in the
+// test itself (coordinates below 1e4 m: ulp <= 1e-3 / 1000).
+constexpr int LM_QCAP = 144;               // queries per block with a cache slot (the rest always search in full)
+constexpr int LM_CACHE_CAND = 32;
+constexpr float LM_CACHE_MARGIN = 0.25f;   // metres
+constexpr float LM_CACHE_SLACK = 1e-3f;    // metres
+
+struct KnnCache {
+  float4* cand;    // [LM_QCAP][32]  x, y, z, map-index bits
+  float4* center;  // [LM_QCAP]      c and R
+  float4* qpt;     // [LM_QCAP]      the query itself (sensor frame), so that the steady state never leaves the SM
+  int* cnt;        // [LM_QCAP]      0 = no set yet, -1 = not cacheable, > 0 = points in the set
+  uint32_t* prev;  // [LM_QCAP]      lanes (= positions in cand) of the five neighbours found last time, 0 = unknown
+};
+constexpr int LM_CACHE_BYTES = LM_QCAP * (LM_CACHE_CAND * 16 + 16 + 16 + 4 + 4);
+constexpr int LM_PERSISTENT_SMEM = LM_THREADS * LM_SLOT * (int)sizeof(float) + LM_CACHE_BYTES;  // dynamic shared memory of lm_persistent_kernel
+
+// After a full search of a query around `sel` (5th distance d5bits, LM_EMPTY_D2 when it was not accepted; candidates
+// described by my_start / my_count as in knn5_chunks, at most 128 of them): collect the query's cached set. Two kinds:
+//   cell-complete (R = -1): ALL points of the 27 cells, when there are at most 32 — valid for as long as the query stays
+//     in the same one-metre cell, accepted or not (sparse parts of the map, where most rejected queries live);
+//   radius (R > 0): the points within R of the query, as described above.
+// All 32 lanes.
+template <bool kFresh>
+__device__ __noinline__ void knn_cache_fill(const float4* sorted, int my_start, int my_count, float sx, float sy, float sz,
+                                            uint32_t d5bits, float4 qsensor, int lane, float4* cand, float4* center,
+                                            float4* qpt, int* cnt_out, uint32_t* prev_out) {
+  constexpr int kRowLane[9] = {12, 3, 9, 15, 21, 0, 6, 18, 24};
+  int pr[9], bs[9];
+  int total = 0;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    const int st = __shfl_sync(0xffffffffu, my_start, kRowLane[k]);
+    const int cn = __shfl_sync(0xffffffffu, my_count, kRowLane[k]);
+    pr[k] = total;
+    bs[k] = st - total;
+    total += cn;
+  }
+  if (lane == 0) {
+    *qpt = qsensor;
+    *prev_out = 0u;
+  }
+  const bool whole = total <= LM_CACHE_CAND;
+  if (!whole && d5bits == LM_EMPTY_D2) {  // rejected in a dense neighbourhood: nothing provable to keep
+    if (lane == 0) *cnt_out = -1;
+    return;
+  }
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  // the radius set must fit 32 points: a dense neighbourhood gets a second try with a thinner shell around d5
+#pragma unroll 1
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    const float margin = attempt == 0 ? LM_CACHE_MARGIN : 0.3f * LM_CACHE_MARGIN;
+    const float R = whole ? -1.f : fminf(1.0f, sqrtf(__uint_as_float(d5bits)) + margin);
+    const float R2 = R * R;
+    int base = 0;
+#pragma unroll 1
+    for (int j0 = 0; j0 < total && base <= LM_CACHE_CAND; j0 += 32) {
+      const int j = j0 + lane;
+      int b = bs[0];
+#pragma unroll
+      for (int k = 1; k < 9; ++k)
+        if (j >= pr[k]) b = bs[k];
+      const bool have = j < total;
+      const float4 m = have ? map_ld<kFresh>(&sorted[j + b]) : make_float4(0.f, 0.f, 0.f, 0.f);
+      float df = sx - m.x;
+      float d = df * df;
+      df = sy - m.y;
+      d += df * df;
+      df = sz - m.z;
+      d += df * df;
+      const bool in = have && (whole || d <= R2);
+      const unsigned bal = __ballot_sync(0xffffffffu, in);
+      const int pos = base + __popc(bal & lt_mask);
+      if (in && pos < LM_CACHE_CAND) cand[pos] = m;
+      base += __popc(bal);
+    }
+    const bool fits = whole || (base <= LM_CACHE_CAND && base >= 5);
+    if (fits || attempt == 1) {
+      if (lane == 0) {
+        *center = make_float4(sx, sy, sz, R);
+        // (an EMPTY cell-complete set is stored as count 33: cnt must be > 0 to be used, and no lane is below 33 <= 32)
+        *cnt_out = fits ? (whole ? (base > 0 ? base : LM_CACHE_CAND + 1) : base) : -1;
+      }
+      return;
+    }
+  }
+}
+
+// The cached search of LM_CACHE_BATCH queries of one warp, interleaved. slot_c[b] = cache slot (or -1: skip). On return
+// ok[b] (warp-uniform) says whether the outcome is proven exact, acc[b] whether five neighbours within range exist; lane
+// r < 5 then holds neighbour r's coordinates in (nx, ny, nz)[b].
+constexpr int LM_CACHE_BATCH = 4;
+__device__ __forceinline__ void knn5_cached_batch(const KnnCache& C, const int (&slot_c)[LM_CACHE_BATCH],
+                                                  const float4 (&sel)[LM_CACHE_BATCH], float max_sq_dist, int lane,
+                                                  bool (&ok)[LM_CACHE_BATCH], bool (&acc)[LM_CACHE_BATCH],
+                                                  int (&rank)[LM_CACHE_BATCH], float (&nx)[LM_CACHE_BATCH],
+                                                  float (&ny)[LM_CACHE_BATCH], float (&nz)[LM_CACHE_BATCH]) {
+  // On return, for a proven and accepted query b, lane p < 5 holds ONE of the five neighbours in (nx, ny, nz)[b] and its
+  // position in the ascending (d2, index) order in rank[b] (the lanes' ranks are a permutation of 0..4).
+  constexpr int NB = LM_CACHE_BATCH;
+  const uint32_t max_bits = __float_as_uint(max_sq_dist);
+  uint32_t cd[NB], ci[NB], pm[NB], d5[NB];
+  float4 ctr[NB];
+  int src[NB];  // lane p < 5: the lane (= position in the cached set) holding "its" neighbour
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    cd[b] = LM_EMPTY_D2;
+    ci[b] = 0xffffffffu;
+    pm[b] = 0u;
+    d5[b] = LM_EMPTY_D2;
+    ctr[b] = make_float4(0.f, 0.f, 0.f, 0.f);
+    src[b] = 0;
+    rank[b] = 0;
+    ok[b] = false;
+    acc[b] = false;
+    if (slot_c[b] >= 0) {  // warp-uniform
+      const int cnt = C.cnt[slot_c[b]];
+      ctr[b] = C.center[slot_c[b]];
+      pm[b] = C.prev[slot_c[b]];
+      if (lane < cnt && cnt <= LM_CACHE_CAND) {
+        const float4 m = C.cand[slot_c[b] * LM_CACHE_CAND + lane];
+        float df = sel[b].x - m.x;  // evalMetric order, as in the full search
+        float d = df * df;
+        df = sel[b].y - m.y;
+        d += df * df;
+        df = sel[b].z - m.z;
+        d += df * df;
+        const uint32_t db = __float_as_uint(d);
+        if (db < max_bits) { cd[b] = db; ci[b] = __float_as_uint(m.w); }
+      }
+    }
+  }
+  LL_TL_WARP(2);
+  // ---- verify: are last time's five still the five smallest? (one redux + two ballots; the usual case)
+  bool verified[NB];
+  bool all_verified = true;
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    verified[b] = false;
+    if (slot_c[b] < 0) continue;
+    if (pm[b] != 0u) {
+      const bool mem = (pm[b] >> lane) & 1u;
+      const uint32_t T = __reduce_max_sync(0xffffffffu, mem ? cd[b] : 0u);  // the largest d2 among last time's five
+      const unsigned lt = __ballot_sync(0xffffffffu, cd[b] < T), eq = __ballot_sync(0xffffffffu, cd[b] == T);
+      verified[b] = T != LM_EMPTY_D2 && __popc(lt) == 4 && __popc(eq) == 1 && (lt | eq) == pm[b];
+      if (verified[b]) d5[b] = T;
+    }
+    all_verified = all_verified && verified[b];
+  }
+  if (!all_verified) {  // warp-uniform: five selection rounds for the queries whose set changed (or that have none yet)
+#pragma unroll 1
+    for (int r = 0; r < 5; ++r) {  // (not unrolled: the LM loop is instruction-fetch bound, every copy of this body costs)
+#pragma unroll
+      for (int b = 0; b < NB; ++b) {
+        if (slot_c[b] < 0 || verified[b]) continue;  // warp-uniform
+        const uint32_t m = __reduce_min_sync(0xffffffffu, cd[b]);
+        unsigned bal = __ballot_sync(0xffffffffu, cd[b] == m);
+        if (m != LM_EMPTY_D2 && (bal & (bal - 1u)) != 0u) {  // exact d2 tie between lanes: lowest map index (rare)
+          const uint32_t om = __reduce_min_sync(0xffffffffu, cd[b] == m ? ci[b] : 0xffffffffu);
+          bal = __ballot_sync(0xffffffffu, cd[b] == m && ci[b] == om);
+        }
+        const int wl = __ffs(bal) - 1;
+        if (r == 0) pm[b] = 0u;
+        if (m != LM_EMPTY_D2) pm[b] |= 1u << wl;
+        if (lane == r) { src[b] = wl; rank[b] = r; }
+        if (lane == wl && m != LM_EMPTY_D2) cd[b] = LM_EMPTY_D2;
+        d5[b] = m;
+      }
+    }
+  }
+  LL_TL_WARP(3);
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    nx[b] = ny[b] = nz[b] = 0.f;
+    if (slot_c[b] < 0) continue;  // warp-uniform
+    acc[b] = d5[b] != LM_EMPTY_D2;
+    if (ctr[b].w < 0.f) {         // cell-complete set: exact while the query stays in the cell it was collected for
+      ok[b] = floorf(sel[b].x) == floorf(ctr[b].x) && floorf(sel[b].y) == floorf(ctr[b].y) && floorf(sel[b].z) == floorf(ctr[b].z);
+    } else if (acc[b]) {
+      float df = sel[b].x - ctr[b].x;
+      float dl = df * df;
+      df = sel[b].y - ctr[b].y;
+      dl += df * df;
+      df = sel[b].z - ctr[b].z;
+      dl += df * df;
+      // sqrt by rsqrt (2 ulp): the millimetre of slack in the test dwarfs it
+      const float D = __uint_as_float(d5[b]);
+      const float sD = D > 0.f ? D * rsqrtf(D) : 0.f, sl = dl > 0.f ? dl * rsqrtf(dl) : 0.f;
+      ok[b] = sD + sl + LM_CACHE_SLACK <= ctr[b].w;
+    }
+    if (!(ok[b] && acc[b])) continue;  // warp-uniform
+    if (verified[b]) {
+      // the five are where they were; their order may have changed: rank each among the five by (d2, index)
+      src[b] = lane < 5 ? (int)__fns(pm[b], 0, lane + 1) : 0;
+      const uint32_t gd = __shfl_sync(0xffffffffu, cd[b], src[b]), gi = __shfl_sync(0xffffffffu, ci[b], src[b]);
+      int rk = 0;
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {
+        const uint32_t od = __shfl_sync(0xffffffffu, gd, k), oi = __shfl_sync(0xffffffffu, gi, k);
+        rk += pair_less(od, oi, gd, gi) ? 1 : 0;
+      }
+      rank[b] = rk;
+    }
+    if (lane < 5) {
+      const float4 m = C.cand[slot_c[b] * LM_CACHE_CAND + src[b]];
+      nx[b] = m.x; ny[b] = m.y; nz[b] = m.z;
+    }
+    if (lane == 0) C.prev[slot_c[b]] = pm[b];
+  }
+}
+
 // The 29 running sums of one LM iteration in a fixed order: 21 upper-triangular AtA entries (row-major),
 // 6 Atb entries, sum |d|, count. sv = [row0..row5, b, |d|].
 __device__ __forceinline__ float lm_term(const float sv[8], float one, int k) {
@@ -860,6 +1086,52 @@ __device__ __forceinline__ float lm_term(const float sv[8], float one, int k) {
   if (k == 27) return sv[7];
   return one;
 }
+
+// Iteration 0 of LMOptimization, upstream semantics (:1507-1531): min_lambda, the degeneracy flag and the projector,
+// by one warp. Out of line: it runs once per scan, and the LM loop around it is instruction-fetch bound.
+__device__ __noinline__ void lm_iter0_degeneracy(const float* AtA, float eig_thresh, int lane, float* Ps, float* misc) {
+  struct { float eig_thresh; } prm = {eig_thresh};
+
+  // min_lambda and "is any eigenvalue below the threshold" from Sturm counts (solve_warp.cuh); the full
+  // eigen-decomposition only when the projector needs eigenvectors
+  double w = 0.0, v[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  double wmin;
+  int n_below;
+  // (float)lambda < eig_thresh  <=>  lambda < the midpoint between eig_thresh and the float below it (ties round to
+  // eig_thresh's even mantissa for the default 100): the double shift that reproduces the float comparison
+  const double thr_mid = 0.5 * ((double)prm.eig_thresh + (double)nextafterf(prm.eig_thresh, -FLT_MAX));
+  min_eig6_multisection(AtA, thr_mid, lane, wmin, n_below);
+  unsigned mb = n_below > 0 ? 1u : 0u;
+  if (mb) {  // degenerate
+    jacobi6_warp<true>(AtA, lane, w, v);
+    mb = __ballot_sync(FULL, lane < 6 && (float)w < prm.eig_thresh);
+    double jm = lane < 6 ? w : 1.7976931348623157e308;
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) jm = fmin(jm, __shfl_xor_sync(FULL, jm, o));
+    wmin = jm;
+  }
+  const bool below = lane < 6 && (float)w < prm.eig_thresh;
+  if (lane == 0) {
+    misc[0] = mb ? 1.f : 0.f;
+    misc[1] = (float)wmin;
+  }
+  // matP = sum over kept eigenvectors v v^T (identity when nothing is dropped)
+#pragma unroll
+  for (int r = 0; r < 6; ++r)
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+      float pv = r == c ? 1.f : 0.f;
+      if (mb) {
+        double t = (lane < 6 && !below) ? v[r] * v[c] : 0.0;
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) t += __shfl_xor_sync(FULL, t, o);
+        pv = (float)t;
+      }
+      if (lane == 0) Ps[r * 6 + c] = pv;
+    }
+}
+
+__device__ __noinline__ float qr66_warp_outofline(const float* AtA, const float* Atb, int lane) { return qr66_warp(AtA, Atb, lane); }
 
 // LMOptimization on the reduced sums, executed by the whole (last) block. sums = s_red[0..28] in shared
 // memory; s_red must provide at least 64 + 64 doubles. For eigen_mode = upstream the 6x6 solve runs on warp 0
@@ -899,47 +1171,11 @@ __device__ void lm_solve_block(double* s_red, const LMParams& prm, LMState* S, b
       for (int r = 0; r < 6; ++r)
         if (lane == r) x = xv[r];
     } else {
-      x = qr66_warp(AtA, Atb, lane);
+      x = qr66_warp_outofline(AtA, Atb, lane);
     }
     if (lane < 6) xs[lane] = x;
   } else if (warp == 1 && iter == 0) {  // :1507-1531, upstream semantics
-    // min_lambda and "is any eigenvalue below the threshold" from Sturm counts (solve_warp.cuh); the full
-    // eigen-decomposition only when the projector needs eigenvectors
-    double w = 0.0, v[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-    double wmin;
-    int n_below;
-    // (float)lambda < eig_thresh  <=>  lambda < the midpoint between eig_thresh and the float below it (ties round to
-    // eig_thresh's even mantissa for the default 100): the double shift that reproduces the float comparison
-    const double thr_mid = 0.5 * ((double)prm.eig_thresh + (double)nextafterf(prm.eig_thresh, -FLT_MAX));
-    min_eig6_multisection(AtA, thr_mid, lane, wmin, n_below);
-    unsigned mb = n_below > 0 ? 1u : 0u;
-    if (mb) {  // degenerate
-      jacobi6_warp<true>(AtA, lane, w, v);
-      mb = __ballot_sync(FULL, lane < 6 && (float)w < prm.eig_thresh);
-      double jm = lane < 6 ? w : 1.7976931348623157e308;
-#pragma unroll
-      for (int o = 4; o > 0; o >>= 1) jm = fmin(jm, __shfl_xor_sync(FULL, jm, o));
-      wmin = jm;
-    }
-    const bool below = lane < 6 && (float)w < prm.eig_thresh;
-    if (lane == 0) {
-      misc[0] = mb ? 1.f : 0.f;
-      misc[1] = (float)wmin;
-    }
-    // matP = sum over kept eigenvectors v v^T (identity when nothing is dropped)
-#pragma unroll
-    for (int r = 0; r < 6; ++r)
-#pragma unroll
-      for (int c = 0; c < 6; ++c) {
-        float pv = r == c ? 1.f : 0.f;
-        if (mb) {
-          double t = (lane < 6 && !below) ? v[r] * v[c] : 0.0;
-#pragma unroll
-          for (int o = 4; o > 0; o >>= 1) t += __shfl_xor_sync(FULL, t, o);
-          pv = (float)t;
-        }
-        if (lane == 0) Ps[r * 6 + c] = pv;
-      }
+    lm_iter0_degeneracy(AtA, prm.eig_thresh, lane, Ps, misc);
   }
   __syncthreads();
   if (warp != 0) return;
@@ -1024,6 +1260,50 @@ __device__ void lm_solve_block(double* s_red, const LMParams& prm, LMState* S, b
   }
 }
 
+// The 29 sums of a block's rows, from the per-query vectors sv = [row0..row5, b, |d|] and `one` (1 for a kept row, else
+// every entry is 0). Every thread < nslots_pad parks its nine numbers in ITS staging slot (stride 21 floats: conflict
+// free), then sum k is accumulated by eight threads (8 k + j, j = 0..7), thread j taking slots j, j + 8, ... in order,
+// and the eight parts are added pairwise (xor 1, 2, 4). Fixed order => bitwise repeatable, and the same order in the
+// single-kernel scan and in lm_iter_kernel. Replaces 29 five-step shuffle trees per warp (1.65 us + 0.3 us per
+// iteration, profiles/r02_lm_iteration_timeline_before.txt). Returns sum k on thread 8 k (0 elsewhere / for k >= 29).
+// Must be called by all threads of the block; contains one __syncthreads (the caller's trailing one protects reuse).
+__device__ __forceinline__ float lm_block_sums(float* s_slot, const float (&sv)[8], float one, int nslots) {
+  const int tid = threadIdx.x;
+  if (tid < nslots) {
+    float* v = &s_slot[tid * LM_SLOT];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) v[r] = sv[r];
+    v[8] = one;
+  }
+  __syncthreads();
+  float acc = 0.f;
+  const int k = tid >> 3, j = tid & 7;
+  if (k < LM_NSUM) {
+    int ia, ib;  // term k = v[ia] * v[ib]  (|d| = v[7] * 1, count = 1 * 1: exact)
+    if (k < 21) {
+      int r = 0, rem = k;
+      while (rem >= 6 - r) { rem -= 6 - r; ++r; }
+      ia = r; ib = r + rem;
+    } else if (k < 27) {
+      ia = k - 21; ib = 6;
+    } else if (k == 27) {
+      ia = 7; ib = 8;
+    } else {
+      ia = 8; ib = 8;
+    }
+    for (int i = j; i < nslots; i += 8) {
+      const float* v = &s_slot[i * LM_SLOT];
+      acc += v[ia] * v[ib];
+    }
+  }
+  if (tid < 256) {  // (whole warps: 29 x 8 = 232 threads, rounded up)
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+  }
+  return (j == 0 && k < LM_NSUM) ? acc : 0.f;
+}
+
 // Sum the block partials in a fixed order (deterministic regardless of which block arrives last).
 template <int kEigenMode>
 __device__ void reduce_partials_and_solve(const float* partials, int nblocks, const LMParams& prm, LMState* S,
@@ -1054,25 +1334,45 @@ __device__ void reduce_partials_and_solve(const float* partials, int nblocks, co
   lm_solve_block<kEigenMode>(s_red, prm, S, stage_mode);
 }
 
+// Block b's share of the queries: an equal slice of the corner list AND an equal slice of the surf list (local order:
+// the corner slice, then the surf slice). Every block then runs one warp's worth of line fits (closed-form eigen solve in
+// double, the slowest piece of phase 2) beside its plane fits, and the corner queries in dense parts of the corner map
+// (hundreds of candidates each) are spread over all blocks instead of making a few blocks the stragglers of every
+// iteration's grid barrier.
+struct QShare {
+  int c_begin, c_end, s_begin, s_end;
+  __device__ __forceinline__ int ncb() const { return c_end - c_begin; }
+  __device__ __forceinline__ int size() const { return (c_end - c_begin) + (s_end - s_begin); }
+  // local index L -> (map, index in the concatenated query list: corner queries first)
+  __device__ __forceinline__ int qi(int L, int nq0) const { return L < ncb() ? c_begin + L : nq0 + s_begin + (L - ncb()); }
+};
+__device__ __forceinline__ QShare lm_partition(const LMArgs& A, int b, int nb) {
+  QShare sh;
+  sh.c_begin = (int)(((long long)A.nq[0] * b) / nb);
+  sh.c_end = (int)(((long long)A.nq[0] * (b + 1)) / nb);
+  sh.s_begin = (int)(((long long)A.nq[1] * b) / nb);
+  sh.s_end = (int)(((long long)A.nq[1] * (b + 1)) / nb);
+  return sh;
+}
+
 // Phases 1 and 2 of one LM iteration over queries [q_begin, q_end) of the concatenated query list (corner
 // queries first, then surf):
 //   phase 1  one warp per query: pointAssociateToMap + 5-NN; the five neighbours and the transformed query
 //            are staged in shared memory (21 floats per query, odd stride => conflict-free);
 //   phase 2  one thread per query: line / plane fit, Jacobian row, then a shuffle-tree reduction of the 29
 //            sums over the block (fixed order => bitwise repeatable).
-// Returns, on threads 0..28, this block's total of sum `tid`.
+// Returns, on thread 8 k (k < 29), this block's total of sum k.
 template <int kEigenMode, bool kFresh>
 __device__ __forceinline__ float lm_block_pass(const LMArgs& A, const Trig& trig, const RotTrig& rt,
-                                               const GridGeom (&geom)[2], float* s_slot, float (*s_wacc)[32],
-                                               int q_begin, int q_end, int tl_it = 0) {
+                                               const GridGeom (&geom)[2], float* s_slot, const QShare& sh) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  (void)tl_it;
-  float run_sum = 0.f;  // threads 0..28: this block's running total of sum `tid`
-  for (int c0 = q_begin; c0 < q_end; c0 += LM_CHUNK) {
-    const int cn = min(LM_CHUNK, q_end - c0);
+  float run_sum = 0.f;  // thread 8 k, k < 29: this block's running total of sum k (see lm_block_sums)
+  const int n_local = sh.size();
+  for (int c0 = 0; c0 < n_local; c0 += LM_CHUNK) {
+    const int cn = min(LM_CHUNK, n_local - c0);
     // Staging slot of query i of this pass = the thread that fits it in phase 2. Corner queries come first; the
     // surf queries start at the next warp boundary so that no warp runs corner_fit and surf_fit back to back.
-    const int nc = max(0, min(cn, A.nq[0] - c0));
+    const int nc = max(0, min(cn, sh.ncb() - c0));
     const int nc_pad = (nc + 31) & ~31;
     const int nslots = nc_pad + (cn - nc);
     // ---- phase 1: k-NN, one warp per query, LM_KNN_BATCH queries of a warp at a time
@@ -1085,7 +1385,7 @@ __device__ __forceinline__ float lm_block_pass(const LMArgs& A, const Trig& trig
         mq[b] = -1;
         sel[b] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (i < cn) {
-          const int qi = c0 + i;
+          const int qi = sh.qi(c0 + i, A.nq[0]);
           mq[b] = qi < A.nq[0] ? 0 : 1;
           sel[b] = __ldg(mq[b] ? &A.q[1][qi - A.nq[0]] : &A.q[0][qi]);
         }
@@ -1095,14 +1395,13 @@ __device__ __forceinline__ float lm_block_pass(const LMArgs& A, const Trig& trig
         if (A.mode != 2) sel[b] = rigid_transform(trig, sel[b]);
       uint32_t od[LM_KNN_BATCH], oi[LM_KNN_BATCH], op[LM_KNN_BATCH];
       bool acc[LM_KNN_BATCH];
-      LL_TL_WARP(0);
-      warp_knn5_batch<kFresh>(A.sorted, A.cells, geom, mq, sel, A.prm.fit.max_sq_dist, lane, od, oi, op, acc);
-      LL_TL_WARP(4);
+      int q_start[LM_KNN_BATCH], q_count[LM_KNN_BATCH], q_total[LM_KNN_BATCH];
+      warp_knn5_batch<kFresh>(A.sorted, A.cells, geom, mq, sel, A.prm.fit.max_sq_dist, lane, od, oi, op, acc, q_start, q_count, q_total);
 #pragma unroll
       for (int b = 0; b < LM_KNN_BATCH; ++b) {
         const int i = i0 + b * LM_WARPS;
         if (i >= cn) continue;  // warp-uniform
-        const int qi = c0 + i;
+        const int qi = sh.qi(c0 + i, A.nq[0]);
         float* slot = &s_slot[(i < nc ? i : nc_pad + (i - nc)) * LM_SLOT];
         if (lane < 5) {
           if (acc[b]) {
@@ -1125,17 +1424,14 @@ __device__ __forceinline__ float lm_block_pass(const LMArgs& A, const Trig& trig
         }
       }
     }
-    LL_TL_WARP(5);
-    LL_TL(tl_it, 1);
     __syncthreads();
-    LL_TL(tl_it, 2);
     // ---- phase 2: fit + Jacobian row, one thread per query
     if (A.mode != 2) {
       float sv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       float one = 0.f;
       const int my_i = tid < nc ? tid : (tid >= nc_pad && tid < nslots ? nc + (tid - nc_pad) : -1);
       if (my_i >= 0) {
-        const int qi = c0 + my_i;
+        const int qi = sh.qi(c0 + my_i, A.nq[0]);
         const int m = qi < A.nq[0] ? 0 : 1;
         const float* slot = &s_slot[tid * LM_SLOT];
         float coeff[4] = {0.f, 0.f, 0.f, 0.f};
@@ -1161,42 +1457,183 @@ __device__ __forceinline__ float lm_block_pass(const LMArgs& A, const Trig& trig
           one = 1.f;
         }
       }
-      LL_TL(tl_it, 3);
-      if (A.mode == 0) {
-        if (warp * 32 < nslots) {  // warp-uniform
-#pragma unroll
-          for (int k = 0; k < LM_NSUM; ++k) {
-            float v = lm_term(sv, one, k);
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if (lane == 0) s_wacc[warp][k] = v;
-          }
-        }
-        LL_TL(tl_it, 4);
-        __syncthreads();
-        if (tid < LM_NSUM) {
-          const int nw = (nslots + 31) >> 5;
-          for (int w = 0; w < nw; ++w) run_sum += s_wacc[w][tid];
-        }
-      }
+      if (A.mode == 0) run_sum += lm_block_sums(s_slot, sv, one, nslots);
     }
     __syncthreads();
   }
   return run_sum;
 }
 
-// Block b's share [q_begin, q_end) of the concatenated query list. An iteration ends when the slowest block
-// arrives at the barrier, and a corner query costs more than a surf query in both phases (denser map -> more
-// candidates; eigen solve in double), so the list is cut into pieces of equal WEIGHT, not equal length.
-__device__ __forceinline__ void lm_partition(const LMArgs& A, int b, int nb, int& q_begin, int& q_end) {
-  const long long wc = A.w_corner, ws = A.w_surf;
-  const long long cw = wc * A.nq[0], W = cw + ws * A.nq[1];
-  auto cut = [&](long long k) -> int {
-    const long long pos = (W * k) / nb;
-    return pos < cw ? (int)(pos / wc) : A.nq[0] + (int)((pos - cw) / ws);
-  };
-  q_begin = cut(b);
-  q_end = (b + 1 == nb) ? A.nq[0] + A.nq[1] : cut(b + 1);
+// Step (B) of lm_block_pass_cached for one warp: the full search of the queries in `need` (bit j = query warp + 16 j of
+// the chunk starting at c0), three at a time, their staging slots, and their cached sets. Out of line on purpose.
+template <bool kFresh>
+__device__ __noinline__ void lm_full_search_warp(const LMArgs* Ap, const Trig* trig_p, const GridGeom* geom_p, float* s_slot,
+                                                 KnnCache C, QShare sh, int c0, int nc, int nc_pad, unsigned need, bool first_chunk) {
+  const LMArgs& A = *Ap;
+  const Trig trig = *trig_p;
+  const GridGeom geom[2] = {geom_p[0], geom_p[1]};
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    while (need) {
+      int jb[LM_KNN_BATCH], mq[LM_KNN_BATCH];
+      float4 sel[LM_KNN_BATCH], qs[LM_KNN_BATCH];
+#pragma unroll
+      for (int b = 0; b < LM_KNN_BATCH; ++b) {
+        jb[b] = -1;
+        mq[b] = -1;
+        sel[b] = make_float4(0.f, 0.f, 0.f, 0.f);
+        qs[b] = sel[b];
+        if (need) {
+          jb[b] = __ffs(need) - 1;
+          need &= need - 1u;
+          const int qi = sh.qi(c0 + warp + LM_WARPS * jb[b], A.nq[0]);
+          mq[b] = qi < A.nq[0] ? 0 : 1;
+          qs[b] = __ldg(mq[b] ? &A.q[1][qi - A.nq[0]] : &A.q[0][qi]);
+          sel[b] = rigid_transform(trig, qs[b]);
+        }
+      }
+      uint32_t od[LM_KNN_BATCH], oi[LM_KNN_BATCH], op[LM_KNN_BATCH];
+      bool acc[LM_KNN_BATCH];
+      int q_start[LM_KNN_BATCH], q_count[LM_KNN_BATCH], q_total[LM_KNN_BATCH];
+      warp_knn5_batch<kFresh>(A.sorted, A.cells, geom, mq, sel, A.prm.fit.max_sq_dist, lane, od, oi, op, acc, q_start, q_count, q_total);
+#pragma unroll
+      for (int b = 0; b < LM_KNN_BATCH; ++b) {
+        if (jb[b] < 0) continue;  // warp-uniform
+        LL_TL_COUNT(0);
+        if (q_total[b] > 32 * LM_CAND_UNROLL) LL_TL_COUNT(1);
+        else if (!acc[b] && q_total[b] > LM_CACHE_CAND) LL_TL_COUNT(3);
+        const int i = warp + LM_WARPS * jb[b];
+        float* slot = &s_slot[(i < nc ? i : nc_pad + (i - nc)) * LM_SLOT];
+        if (lane < 5) {
+          if (acc[b]) {
+            const float4 nb = map_ld<kFresh>(&A.sorted[mq[b]][op[b]]);
+            slot[4 + 3 * lane] = nb.x;
+            slot[5 + 3 * lane] = nb.y;
+            slot[6 + 3 * lane] = nb.z;
+          }
+        } else if (lane == 5) {
+          slot[0] = sel[b].x;
+          slot[1] = sel[b].y;
+          slot[2] = sel[b].z;
+          slot[3] = acc[b] ? 1.f : 0.f;
+        }
+        if (first_chunk && i < LM_QCAP) {  // (re)build this query's cached set around where it is now
+          const uint32_t d5 = __shfl_sync(0xffffffffu, acc[b] ? od[b] : LM_EMPTY_D2, 4);
+          knn_cache_fill<kFresh>(A.sorted[mq[b]], q_start[b], q_count[b], sel[b].x, sel[b].y, sel[b].z, d5, qs[b], lane,
+                                 &C.cand[i * LM_CACHE_CAND], &C.center[i], &C.qpt[i], &C.cnt[i], &C.prev[i]);
+        }
+      }
+    }
+}
+
+// The same two phases for the single-kernel scan, with the candidate cache (KnnCache above) in front of the full search.
+// Warp w owns queries w, w + 16, ... of the block's share. Per iteration: (A) the queries with a cached set try the
+// cached search, four at a time; (B) the others — all of them in iteration 0 — take the full search three at a time
+// and (re)build their sets. Phase 2 and the sums are those of lm_block_pass, so both kernels add in the same order.
+template <int kEigenMode, bool kFresh>
+__device__ __forceinline__ float lm_block_pass_cached(const LMArgs& A, const Trig& trig_s, const RotTrig& rt,
+                                                      const GridGeom* geom_s, float* s_slot, const KnnCache& C,
+                                                      const QShare& sh, int tl_it) {
+  // trig_s / geom_s live in shared memory (the out-of-line full search takes them by address)
+  const Trig trig = trig_s;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  (void)tl_it;
+  float run_sum = 0.f;  // thread 8 k, k < 29: this block's running total of sum k
+  const int n_local = sh.size();
+  for (int c0 = 0; c0 < n_local; c0 += LM_CHUNK) {
+    const int cn = min(LM_CHUNK, n_local - c0);
+    const int nc = max(0, min(cn, sh.ncb() - c0));
+    const int nc_pad = (nc + 31) & ~31;
+    const int nslots = nc_pad + (cn - nc);
+    const bool first_chunk = c0 == 0;  // the cache slots belong to the first LM_QCAP queries of the block
+    const int nj = cn > warp ? (cn - warp + LM_WARPS - 1) / LM_WARPS : 0;  // this warp's queries (<= 30)
+    unsigned need = nj >= 32 ? 0xffffffffu : ((1u << nj) - 1u);            // bit j: query warp + 16 j still unsearched
+    LL_TL_WARP(0);
+    // ---- (A) cached search
+    if (first_chunk) {
+      for (int j0 = 0; j0 < nj && warp + LM_WARPS * j0 < LM_QCAP; j0 += LM_CACHE_BATCH) {
+        int sc[LM_CACHE_BATCH];
+        float4 sel[LM_CACHE_BATCH];
+        bool any = false;
+#pragma unroll
+        for (int b = 0; b < LM_CACHE_BATCH; ++b) {
+          const int i = warp + LM_WARPS * (j0 + b);
+          sc[b] = -1;
+          sel[b] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (j0 + b < nj && i < LM_QCAP && C.cnt[i] > 0) {  // warp-uniform
+            sc[b] = i;
+            sel[b] = rigid_transform(trig, C.qpt[i]);
+            any = true;
+          }
+        }
+        if (!any) continue;
+        bool ok[LM_CACHE_BATCH], acc[LM_CACHE_BATCH];
+        int rank[LM_CACHE_BATCH];
+        float nx[LM_CACHE_BATCH], ny[LM_CACHE_BATCH], nz[LM_CACHE_BATCH];
+        LL_TL_WARP(6);
+        knn5_cached_batch(C, sc, sel, A.prm.fit.max_sq_dist, lane, ok, acc, rank, nx, ny, nz);
+        LL_TL_WARP(4);
+#pragma unroll
+        for (int b = 0; b < LM_CACHE_BATCH; ++b) {
+          if (sc[b] >= 0) LL_TL_COUNT(5);
+          if (sc[b] < 0 || !ok[b]) continue;  // warp-uniform
+          LL_TL_COUNT(4);
+          const int i = sc[b];
+          float* slot = &s_slot[(i < nc ? i : nc_pad + (i - nc)) * LM_SLOT];
+          if (lane < 5) {
+            if (acc[b]) {
+              slot[4 + 3 * rank[b]] = nx[b];
+              slot[5 + 3 * rank[b]] = ny[b];
+              slot[6 + 3 * rank[b]] = nz[b];
+            }
+          } else if (lane == 5) {
+            slot[0] = sel[b].x;
+            slot[1] = sel[b].y;
+            slot[2] = sel[b].z;
+            slot[3] = acc[b] ? 1.f : 0.f;
+          }
+          need &= ~(1u << (j0 + b));
+        }
+      }
+    }
+    LL_TL_WARP(1);
+    // ---- (B) full search of what is left (everything in iteration 0), out of line: the steady-state loop is
+    //      instruction-fetch bound, and this is by far its largest piece of code
+    if (need) lm_full_search_warp<kFresh>(&A, &trig_s, geom_s, s_slot, C, sh, c0, nc, nc_pad, need, first_chunk);
+    LL_TL_WARP(5);
+    LL_TL(tl_it, 1);
+    __syncthreads();
+    LL_TL(tl_it, 2);
+    // ---- phase 2: fit + Jacobian row, one thread per query
+    float sv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float one = 0.f;
+    const int my_i = tid < nc ? tid : (tid >= nc_pad && tid < nslots ? nc + (tid - nc_pad) : -1);
+    if (my_i >= 0) {
+      const int qi = sh.qi(c0 + my_i, A.nq[0]);
+      const int m = qi < A.nq[0] ? 0 : 1;
+      const float* slot = &s_slot[tid * LM_SLOT];
+      float coeff[4] = {0.f, 0.f, 0.f, 0.f};
+      bool keep = false;
+      if (slot[3] != 0.f) {
+        float nbx[5], nby[5], nbz[5];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) { nbx[k] = slot[4 + 3 * k]; nby[k] = slot[5 + 3 * k]; nbz[k] = slot[6 + 3 * k]; }
+        keep = m == 0 ? corner_fit<kEigenMode>(nbx, nby, nbz, slot[0], slot[1], slot[2], A.prm.fit, coeff)
+                      : surf_fit(nbx, nby, nbz, slot[0], slot[1], slot[2], A.prm.fit, coeff);
+      }
+      if (keep) {
+        const float4 p = __ldg(&A.q[m][m ? qi - A.nq[0] : qi]);
+        jacobian_row(rt, p.x, p.y, p.z, coeff[0], coeff[1], coeff[2], sv);
+        sv[6] = -A.prm.step_size * coeff[3];  // matB (:1500)
+        sv[7] = fabsf(coeff[3]);
+        one = 1.f;
+      }
+    }
+    LL_TL(tl_it, 3);
+    run_sum += lm_block_sums(s_slot, sv, one, nslots);
+    LL_TL(tl_it, 4);
+    __syncthreads();
+  }
+  return run_sum;
 }
 
 __device__ __forceinline__ void lm_load_geom(const LMArgs& A, GridGeom (&geom)[2]) {
@@ -1221,19 +1658,17 @@ __global__ void __launch_bounds__(LM_THREADS, LM_MIN_BLOCKS) lm_iter_kernel(cons
   pdl_entry();
   if (A.mode == 0 && S->done) return;
   __shared__ __align__(16) float s_slot[LM_THREADS * LM_SLOT];
-  __shared__ float s_wacc[LM_WARPS][32];
   __shared__ int s_last;
   const int tid = threadIdx.x;
   const Trig trig = S->trig;
   const RotTrig rt = S->rtrig;
   GridGeom geom[2];
   lm_load_geom(A, geom);
-  int q_begin, q_end;
-  lm_partition(A, (int)blockIdx.x, (int)gridDim.x, q_begin, q_end);
-  const float run_sum = lm_block_pass<kEigenMode, false>(A, trig, rt, geom, s_slot, s_wacc, q_begin, q_end);
+  const QShare sh = lm_partition(A, (int)blockIdx.x, (int)gridDim.x);
+  const float run_sum = lm_block_pass<kEigenMode, false>(A, trig, rt, geom, s_slot, sh);
   if (A.mode != 0) return;
-  if (tid < 32) {
-    A.partials[blockIdx.x * 32 + tid] = tid < LM_NSUM ? run_sum : 0.f;
+  if (tid < 256 && (tid & 7) == 0) {  // thread 8 k holds sum k (k >= 29: zero)
+    A.partials[blockIdx.x * 32 + (tid >> 3)] = run_sum;
     __threadfence();
   }
   __syncthreads();
@@ -1267,11 +1702,12 @@ __device__ __forceinline__ void lm_begin_state(LMState* S, const MapState* corne
   if (__ldcg(&corner->voxel_overflow)) flags |= 1;
   if (__ldcg(&surf->voxel_overflow)) flags |= 2;
   if (__ldcg(&corner->grid_too_large) || __ldcg(&surf->grid_too_large)) flags |= 4;
+  if (__ldcg(&corner->inc_fail) || __ldcg(&surf->inc_fail)) flags |= 8;  // incremental map assembly gave up: the host rebuilds
   S->flags = flags;
-  const bool ok = n_corner > prm.min_corner_map && n_surf > prm.min_surf_map && !(flags & 4);
+  const bool ok = n_corner > prm.min_corner_map && n_surf > prm.min_surf_map && !(flags & 12);
   // 1 = the reference's own skip (:1573); 2 = NOT a reference behaviour: the 1 m search grid over this map's bounding
   // box exceeds the cell budget, so the scan could not be registered here although the reference's KD-tree would
-  S->status = ok ? 0 : ((flags & 4) ? 2 : 1);
+  S->status = ok ? 0 : ((flags & 8) ? 3 : ((flags & 4) ? 2 : 1));  // (3 never leaves the library: abi.cu rebuilds and reruns)
   S->done = ok ? 0 : 1;
   if (prm.iter_count_thres <= 0) S->done = 1;
 }
@@ -1290,9 +1726,17 @@ __global__ void __launch_bounds__(LM_THREADS, 1) lm_persistent_kernel(const __gr
                                                                       unsigned* barrier, unsigned* barrier_clear,
                                                                       const __grid_constant__ MapBatch GB, int build_map,
                                                                       int build_grid, const Segment* segs,
-                                                                      const BlockJob* jobs, int n_jobs) {
-  __shared__ __align__(16) float s_slot[LM_THREADS * LM_SLOT];
-  __shared__ float s_wacc[LM_WARPS][32];
+                                                                      const BlockJob* jobs, int n_jobs,
+                                                                      const __grid_constant__ IncJob IJ) {
+  // dynamic shared memory (LM_PERSISTENT_SMEM bytes): [staging slots / map-build scratch | candidate cache]
+  extern __shared__ __align__(16) unsigned char s_dyn[];
+  float* const s_slot = reinterpret_cast<float*>(s_dyn);
+  KnnCache C;
+  C.cand = reinterpret_cast<float4*>(s_dyn + LM_THREADS * LM_SLOT * sizeof(float));
+  C.center = C.cand + LM_QCAP * LM_CACHE_CAND;
+  C.qpt = C.center + LM_QCAP;
+  C.cnt = reinterpret_cast<int*>(C.qpt + LM_QCAP);
+  C.prev = reinterpret_cast<uint32_t*>(C.cnt + LM_QCAP);
   __shared__ __align__(16) LMState s_st;
   const int tid = threadIdx.x;
   {  // prologue: the persistent members (matP, isDegenerate, ...) come from the handle's state
@@ -1304,6 +1748,7 @@ __global__ void __launch_bounds__(LM_THREADS, 1) lm_persistent_kernel(const __gr
   unsigned epoch = 0;  // grid barriers passed so far
   static_assert(GI_SMEM_WORDS <= LM_THREADS * LM_SLOT && GI_SMEM_WORDS_REDUCE <= LM_THREADS * LM_SLOT && GI_THREADS == LM_THREADS,
                 "the inline map build borrows the staging slots");
+  static_assert((LM_THREADS * LM_SLOT * sizeof(float)) % 16 == 0, "the cache follows the staging slots, 16-byte aligned");
   // a4: the search grids of the local map, when ll_build_local_map left them to this launch (grid_inline.cuh)
   // a1-a3: the local map itself, when ll_build_local_map only prepared it (map_inline.cuh)
   bool cells_cleared = false;
@@ -1311,32 +1756,41 @@ __global__ void __launch_bounds__(LM_THREADS, 1) lm_persistent_kernel(const __gr
     if (blockIdx.x == 0 && tid < 128)  // MapState of both maps (bounding box, counts): zero before the build
       reinterpret_cast<uint32_t*>(GB.m[tid >> 6].st)[tid & 63] = 0u;
     coop_barrier(barrier, epoch);
-    cells_cleared = map_build_inline(GB, segs, jobs, n_jobs, barrier, epoch, reinterpret_cast<uint32_t*>(s_slot));
+    if (build_map == 2)  // a1-a3 incrementally: merge the added keyframes into the device-resident window (map_incremental.cuh)
+      map_incremental_inline(IJ, GB, barrier, epoch, reinterpret_cast<uint32_t*>(s_dyn));
+    else
+      cells_cleared = map_build_inline(GB, segs, jobs, n_jobs, barrier, epoch, reinterpret_cast<uint32_t*>(s_slot));
   }
   if (build_grid) grid_build_inline(GB, barrier, epoch, reinterpret_cast<uint32_t*>(s_slot), cells_cleared);
   __syncthreads();
+  static_assert(INC_SMEM_BYTES <= LM_PERSISTENT_SMEM && INC_MERGE_SMEM_WORDS * 4 <= LM_PERSISTENT_SMEM &&
+                INC_REDUCE_SMEM_WORDS * 4 <= LM_PERSISTENT_SMEM, "the incremental map build borrows the dynamic shared memory");
+  if (tid < LM_QCAP) C.cnt[tid] = 0;  // no cached sets yet (after the map build, which may use this memory as scratch)
   if (tid == 0) {
     const float pose6[6] = {p0, p1, p2, p3, p4, p5};
     lm_begin_state(&s_st, A.mst[0], A.mst[1], A.prm, pose6);
   }
-  GridGeom geom[2];
-  lm_load_geom(A, geom);
-  int q_begin, q_end;
-  lm_partition(A, (int)blockIdx.x, (int)gridDim.x, q_begin, q_end);
+  __shared__ GridGeom s_geom[2];
+  if (tid == 0) {
+    GridGeom geom[2];
+    lm_load_geom(A, geom);
+    s_geom[0] = geom[0];
+    s_geom[1] = geom[1];
+  }
+  const QShare sh = lm_partition(A, (int)blockIdx.x, (int)gridDim.x);
   for (unsigned it = 0;; ++it) {
     __syncthreads();
     if (s_st.done) break;  // block-uniform, and the same decision in every block
-    const Trig trig = s_st.trig;
     const RotTrig rt = s_st.rtrig;
 #ifdef LL_TIMELINE
     if (tid == 0 && blockIdx.x == TL_WATCH) g_tl_it = (int)it;
 #endif
     LL_TL(it, 0);
-    const float run_sum = lm_block_pass<kEigenMode, kFresh>(A, trig, rt, geom, s_slot, s_wacc, q_begin, q_end, (int)it);
+    const float run_sum = lm_block_pass_cached<kEigenMode, kFresh>(A, s_st.trig, rt, s_geom, s_slot, C, sh, (int)it);
     LL_TL(it, 5);
     float* part = A.partials + (size_t)(it & 1u) * gridDim.x * 32;
-    if (tid < 32) {
-      part[blockIdx.x * 32 + tid] = tid < LM_NSUM ? run_sum : 0.f;
+    if (tid < 256 && (tid & 7) == 0) {  // thread 8 k holds sum k (k >= 29: zero)
+      part[blockIdx.x * 32 + (tid >> 3)] = run_sum;
       __threadfence();
     }
     LL_TL(it, 6);
@@ -1379,12 +1833,15 @@ __global__ void __launch_bounds__(LM_THREADS, 1) lm_persistent_kernel(const __gr
       }
       printf("   %-34s %7.2f   (globaltimer: first arrival -> last arrival %.2f us, last arrival -> last release %.2f us)\n",
              "iteration total (mean of blocks)", tot_mean, (last - first) * 1e-3, (rel - last) * 1e-3);
-      if (itx == 1 || itx == 5) {
-        printf("   block %d phase-1 sub-stamps per warp (us from the warp's first batch start): cells fetched / candidates fetched / sorted / selected / staged\n", TL_WATCH);
+      printf("   queries: %u full searches (%u with > 128 candidates, %u rejected in a dense cell), cached: %u attempted, %u proven\n",
+             g_tl_cnt[itx][0], g_tl_cnt[itx][1], g_tl_cnt[itx][3], g_tl_cnt[itx][5], g_tl_cnt[itx][4]);
+      for (int k = 0; k < 8; ++k) g_tl_cnt[itx][k] = 0;
+      if (itx == 0 || itx == 1 || itx == 5) {
+        printf("   block %d phase 1 per warp (us from its start): queries loaded + transformed / distances / 5 rounds / proof + neighbours / cached part done / full part done\n", TL_WATCH);
         for (int w = 0; w < 16; ++w) {
           const long long t0 = g_tl_warp[itx][0][w];
-          printf("     warp %2d: %6.2f %6.2f %6.2f %6.2f %6.2f\n", w, (g_tl_warp[itx][1][w] - t0) * us, (g_tl_warp[itx][2][w] - t0) * us,
-                 (g_tl_warp[itx][3][w] - t0) * us, (g_tl_warp[itx][4][w] - t0) * us, (g_tl_warp[itx][5][w] - t0) * us);
+          printf("     warp %2d: %6.2f %6.2f %6.2f %6.2f %6.2f %6.2f\n", w, (g_tl_warp[itx][6][w] - t0) * us, (g_tl_warp[itx][2][w] - t0) * us,
+                 (g_tl_warp[itx][3][w] - t0) * us, (g_tl_warp[itx][4][w] - t0) * us, (g_tl_warp[itx][1][w] - t0) * us, (g_tl_warp[itx][5][w] - t0) * us);
         }
       }
     }

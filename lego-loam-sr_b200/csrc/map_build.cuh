@@ -40,7 +40,8 @@ struct MapState {
   int gdx, gdy, gdz;
   int ncells;
   uint32_t head_ticket;  // dynamic tile ticket of voxel_reduce_kernel
-  uint32_t pad[2];
+  int inc_fail;          // the incremental assembly (map_incremental.cuh) met a case it cannot represent: rebuild in full
+  uint32_t pad[1];
 };
 
 struct MapBuffers {
@@ -213,10 +214,10 @@ __global__ void __launch_bounds__(MB_THREADS) voxel_keys_kernel(const __grid_con
     if (i < n) {
       const float4 p = M.raw[i];
       uint32_t key;
-      if (!finite3(p)) {
+      if (v.overflow) {
+        key = (uint32_t)i;  // PCL returns the input unchanged (non-finite points included): every point its own voxel
+      } else if (!finite3(p)) {
         key = sentinel;  // sorted behind every voxel and dropped, like PCL skips non-finite points
-      } else if (v.overflow) {
-        key = (uint32_t)i;  // PCL returns the input unchanged: every point is its own voxel
       } else {
         const int i0 = (int)(floorf(p.x * inv) - (float)v.min_b[0]);
         const int i1 = (int)(floorf(p.y * inv) - (float)v.min_b[1]);

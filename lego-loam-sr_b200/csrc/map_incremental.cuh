@@ -1,0 +1,638 @@
+// Incremental assembly of the local map for a SLIDING set of keyframes.
+//
+// The reference re-filters the whole surrounding cloud every frame (mapOptmization.cpp:1218-1231) although, frame to
+// frame, the set of keyframes only loses a few members and gains the newest one (deque pop / push :1127-1144, erase /
+// push_back :1171-1216) and their transformed clouds are cached (:1124-1144, :1193-1215). What makes an incremental
+// VoxelGrid possible with BIT-IDENTICAL output:
+//   * pcl::VoxelGrid emits one centroid per occupied voxel in ascending idx = i + j*dx + k*dx*dy, i.e. in lexicographic
+//     (k, j, i) order of the voxel coordinates relative to the bounding box — which is the lexicographic order of the
+//     ABSOLUTE coordinates (floor(z/leaf), floor(y/leaf), floor(x/leaf)), whatever the box is;
+//   * the canonical accumulation order inside a voxel is the order of the points in the concatenated cloud (oracle and
+//     full path: stable sort), i.e. keyframes in list order, per keyframe corner | surf then outlier, then point index.
+// So the window W of a map is kept on the device as ONE array of (absolute voxel key, keyframe tag, point) sorted by
+// (key, list order). A frame then needs:
+//   R  the added keyframes' clouds: transform, key, sort (one block per map, bitonic network in shared memory)      ┐ one
+//   C  the old window: count the entries whose keyframe stays, per tile                                             ┘ barrier
+//   M  stable merge of the surviving entries with the new run into the other buffer (old before new on equal keys,
+//      exactly the order a rebuild would produce), bounding box of what is written                                    barrier
+//   V  segment heads per tile | barrier | ordered centroid sums -> laserCloud*FromMapDS, exactly as the full path     barrier
+// instead of transform (all 50 keyframes) + 3 radix passes over ~0.6 M pairs + reduce. Anything the scheme cannot
+// represent (PCL's int32-overflow pass-through, voxel coordinates beyond +-2^20, a new run whose own box needs more than
+// 32 key bits) raises MapState::inc_fail; the host then rebuilds through the full path (abi.cu).
+// A longer list of added keyframes (the default branch at start-up, a rebuild after a pose correction) is fed in groups
+// of <= INC_RUN_MAX points per map, one merge each (map_inc_kernel); only the last group computes the centroids.
+#pragma once
+#include "common.cuh"
+#include "map_build.cuh"
+#include "map_inline.cuh"
+
+namespace ll {
+
+constexpr int INC_RUN_MAX = 8192;   // points per map the keyframes added in one merge may hold (one bitonic network)
+constexpr int INC_MAX_DEAD = 8;     // keyframes dropped in one merge
+constexpr int INC_MAX_SEGS = 12;    // clouds of the added keyframes (three per keyframe)
+constexpr int INC_SUB = 2048;       // window entries per sub-tile of the merge
+constexpr int INC_MAX_BLOCKS = 160;
+constexpr unsigned long long INC_KEY_NONFINITE = ~0ull;
+constexpr int INC_SMEM_BYTES = INC_RUN_MAX * 8;  // the run's sort network; the other stages need less
+
+struct WindowBuffers {
+  float4* pts[2];
+  unsigned long long* key[2];
+  uint32_t* tag[2];
+  float4* run_pts;              // the added keyframes' points, sorted by (key, order) — [INC_RUN_MAX]
+  unsigned long long* run_key;
+  uint32_t* run_tag;
+  float4* stage_pts;            // their transformed points in arrival order — [INC_RUN_MAX]
+  uint32_t* stage_tag;
+  uint32_t* counts;             // [2 * INC_MAX_BLOCKS]: surviving entries per merge tile | heads per reduce tile
+};
+
+struct IncJob {
+  WindowBuffers w[2];
+  int cur;                       // buffer that holds the window now; the merged window goes to cur ^ 1
+  int n_old[2];                  // entries in the window now
+  int n_new[2];                  // points of the added keyframes
+  int n_out[2];                  // entries after the merge (host-known: every raw point stays an entry)
+  int n_dead;
+  uint32_t dead[INC_MAX_DEAD];   // tags (keyframe ids) to drop
+  int n_segs;
+  Segment segs[INC_MAX_SEGS];    // Segment::pad[0] = tag
+  int final_step;                // 1 = compute laserCloud*FromMapDS after the merge
+};
+
+// Absolute voxel coordinates of a point, packed (z | y | x, 21 bits each, offset 2^20): ascending key = VoxelGrid order.
+__device__ __forceinline__ unsigned long long inc_abs_key(const float4 p, float inv, bool& ok) {
+  if (!finite3(p)) return INC_KEY_NONFINITE;
+  const float fx = floorf(p.x * inv), fy = floorf(p.y * inv), fz = floorf(p.z * inv);
+  if (!(fabsf(fx) < 1048576.f && fabsf(fy) < 1048576.f && fabsf(fz) < 1048576.f)) {
+    ok = false;
+    return INC_KEY_NONFINITE - 1ull;
+  }
+  const unsigned long long ix = (unsigned long long)((int)fx + 1048576), iy = (unsigned long long)((int)fy + 1048576),
+                           iz = (unsigned long long)((int)fz + 1048576);
+  return (iz << 42) | (iy << 21) | ix;
+}
+
+// First index in [lo, hi) of the ascending array a whose element is >= v (kUpper: > v). kGlobal: the array is in
+// global memory and may have been written earlier in this launch by another block (read through L2).
+template <bool kUpper, bool kGlobal>
+__device__ __forceinline__ int inc_bound(const unsigned long long* a, int lo, int hi, unsigned long long v) {
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    const unsigned long long x = kGlobal ? __ldcg(a + mid) : a[mid];
+    if (kUpper ? (x <= v) : (x < v)) lo = mid + 1;
+    else hi = mid;
+  }
+  return lo;
+}
+
+// Which blocks merge which map: workers [first, nb) are split between the two maps in proportion to their windows.
+struct IncTiling {
+  int first, nw[2];
+  __device__ __forceinline__ IncTiling(int nb, const int (&n)[2], bool reserve_two) {
+    first = (reserve_two && nb >= 8) ? 2 : 0;
+    const int w = nb - first;
+    const long long tot = (long long)n[0] + n[1];
+    if (w < 2) {
+      nw[0] = nw[1] = w;  // a single block takes both maps in turn (see inc_worker)
+    } else {
+      int a = tot > 0 ? (int)(((long long)w * n[0] + tot / 2) / tot) : w / 2;
+      a = a < 1 ? 1 : (a > w - 1 ? w - 1 : a);
+      nw[0] = a;
+      nw[1] = w - a;
+    }
+  }
+};
+
+__device__ __forceinline__ bool inc_alive(uint32_t tag, const IncJob& J) {
+  bool alive = true;
+#pragma unroll
+  for (int k = 0; k < INC_MAX_DEAD; ++k) alive = alive && !(k < J.n_dead && tag == J.dead[k]);
+  return alive;
+}
+
+// ---- R: the run of the added keyframes of map m, by ONE block. smem: INC_RUN_MAX u64.
+__device__ __forceinline__ void inc_build_run(const IncJob& J, const MapBatch& B, int m, unsigned long long* s_key) {
+  const WindowBuffers& W = J.w[m];
+  const MapBuffers& M = B.m[m];
+  const int tid = threadIdx.x, n = J.n_new[m];
+  __shared__ int s_mn[3], s_mx[3], s_bad;
+  if (tid < 3) { s_mn[tid] = 0x7fffffff; s_mx[tid] = (int)0x80000000; }
+  if (tid == 0) s_bad = 0;
+  __syncthreads();
+  // transformPointCloud (:649-664) of every added cloud, in list order
+  for (int sg = 0; sg < J.n_segs; ++sg) {
+    const Segment& g = J.segs[sg];
+    if (g.map != m) continue;
+    for (int i = tid; i < g.count; i += blockDim.x) {
+      const float4 p = ld_stream(g.src + i);
+      const float4 q = g.identity ? p : rigid_transform(g.t, p);
+      W.stage_pts[g.dst_off + i] = q;
+      W.stage_tag[g.dst_off + i] = (uint32_t)g.pad[0];
+      if (finite3(q)) {
+        const float inv = M.inv_leaf;
+        const float f[3] = {floorf(q.x * inv), floorf(q.y * inv), floorf(q.z * inv)};
+        if (fabsf(f[0]) < 1048576.f && fabsf(f[1]) < 1048576.f && fabsf(f[2]) < 1048576.f) {
+#pragma unroll
+          for (int a = 0; a < 3; ++a) { atomicMin(&s_mn[a], (int)f[a]); atomicMax(&s_mx[a], (int)f[a]); }
+        } else {
+          s_bad = 1;
+        }
+      }
+    }
+  }
+  __syncthreads();  // (block-scope: the stage arrays are re-read below by other threads of this block)
+  const long long dx = (long long)s_mx[0] - s_mn[0] + 1, dy = (long long)s_mx[1] - s_mn[1] + 1, dz = (long long)s_mx[2] - s_mn[2] + 1;
+  const bool any = s_mx[0] >= s_mn[0];
+  if (any && (dx * dy * dz >= 0xffffffffLL || dx <= 0 || dy <= 0 || dz <= 0)) s_bad = 1;  // (benign race: all write 1)
+  __syncthreads();
+  if (s_bad) {
+    if (tid == 0) M.st->inc_fail = 1;
+    return;  // block-uniform
+  }
+  int N = 64;
+  while (N < n) N <<= 1;
+  for (int i = tid; i < N; i += blockDim.x) {
+    unsigned long long ck = ~0ull;
+    if (i < n) {
+      const float4 q = W.stage_pts[i];
+      unsigned long long rel = 0xffffffffull;  // non-finite points: behind every voxel, in arrival order
+      if (finite3(q)) {
+        const float inv = M.inv_leaf;
+        const long long ix = (long long)(int)floorf(q.x * inv) - s_mn[0], iy = (long long)(int)floorf(q.y * inv) - s_mn[1],
+                        iz = (long long)(int)floorf(q.z * inv) - s_mn[2];
+        rel = (unsigned long long)((iz * dy + iy) * dx + ix);
+      }
+      ck = (rel << 13) | (unsigned long long)i;  // unique => the bitonic order is the stable order
+    }
+    s_key[i] = ck;
+  }
+  for (int k = 2; k <= N; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      __syncthreads();
+      for (int t = tid; t < (N >> 1); t += blockDim.x) {
+        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        const int l = i | j;
+        const unsigned long long a = s_key[i], b = s_key[l];
+        const bool up = (i & k) == 0;
+        if ((a > b) == up) {
+          s_key[i] = b;
+          s_key[l] = a;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  bool ok = true;
+  for (int jj = tid; jj < n; jj += blockDim.x) {
+    const int i = (int)(s_key[jj] & 8191ull);
+    const float4 q = W.stage_pts[i];
+    W.run_pts[jj] = q;
+    W.run_key[jj] = inc_abs_key(q, M.inv_leaf, ok);
+    W.run_tag[jj] = W.stage_tag[i];
+  }
+  static_assert(INC_RUN_MAX == 8192, "the composite key keeps the arrival index in 13 bits");
+}
+
+// ---- C: surviving entries of this worker's tile of the old window.
+__device__ __forceinline__ void inc_count(const IncJob& J, int m, int t, int ntiles, uint32_t* out, uint32_t* s_w) {
+  const WindowBuffers& W = J.w[m];
+  const int n = J.n_old[m];
+  const int len = (n + ntiles - 1) / ntiles;
+  const int a = min(n, t * len), b = min(n, a + len);
+  uint32_t c = 0;
+  if (J.n_dead == 0) {
+    c = threadIdx.x == 0 ? (uint32_t)(b - a) : 0u;
+  } else {
+    const uint32_t* __restrict__ tag = W.tag[J.cur];
+    for (int i = a + threadIdx.x; i < b; i += blockDim.x) c += inc_alive(__ldcg(tag + i), J) ? 1u : 0u;
+  }
+  c = __reduce_add_sync(0xffffffffu, c);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) s_w[warp] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t tot = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += s_w[w];
+    *out = tot;
+  }
+}
+
+// ---- M: this worker's tile of the old window merged with its slice of the run, into buffer cur ^ 1.
+// smem (uint32 words): [keys 2 * INC_SUB | prefix INC_SUB + 1 (+ pad) | slice keys 2 * INC_SUB | 64]
+constexpr int INC_MERGE_SMEM_WORDS = 2 * INC_SUB + (INC_SUB + 8) + 2 * INC_SUB + 64;
+__device__ __forceinline__ void inc_merge(const IncJob& J, const MapBatch& B, int m, int t, int ntiles, const uint32_t* counts,
+                                          uint32_t* smem) {
+  const WindowBuffers& W = J.w[m];
+  const MapBuffers& M = B.m[m];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  unsigned long long* s_keys = reinterpret_cast<unsigned long long*>(smem);
+  uint32_t* s_pref = smem + 2 * INC_SUB;
+  unsigned long long* s_slice = reinterpret_cast<unsigned long long*>(smem + 2 * INC_SUB + INC_SUB + 8);
+  uint32_t* s_w = smem + 2 * INC_SUB + INC_SUB + 8 + 2 * INC_SUB;
+  const int n = J.n_old[m], n_new = J.n_new[m];
+  const int len = n > 0 ? (n + ntiles - 1) / ntiles : 0;
+  const int a0 = min(n, t * len), b0 = min(n, a0 + len);
+  const bool first_tile = t == 0;
+  const bool last_tile = b0 >= n;            // (also true for the tiles behind the end of a short window)
+  if (a0 >= n && !(first_tile)) return;      // nothing here; tile 0 of an EMPTY window still places the run
+  const float4* __restrict__ o_pts = W.pts[J.cur];
+  const unsigned long long* __restrict__ o_key = W.key[J.cur];
+  const uint32_t* __restrict__ o_tag = W.tag[J.cur];
+  float4* __restrict__ d_pts = W.pts[J.cur ^ 1];
+  unsigned long long* __restrict__ d_key = W.key[J.cur ^ 1];
+  uint32_t* __restrict__ d_tag = W.tag[J.cur ^ 1];
+  const unsigned long long* r_key = W.run_key;  // (written earlier in this launch: no read-only path)
+  // surviving entries in the tiles before this one
+  uint32_t before = 0;
+  for (int w = tid; w < t; w += blockDim.x) before += __ldcg(counts + w);
+  before = __reduce_add_sync(0xffffffffu, before);
+  __syncthreads();
+  if (lane == 0) s_w[warp] = before;
+  __syncthreads();
+  before = 0;
+  for (int w = 0; w < nwarps; ++w) before += s_w[w];
+  __syncthreads();
+  float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+  bool any = false;
+  auto track = [&](const float4 q) {
+    if (finite3(q)) {
+      any = true;
+      mn[0] = fminf(mn[0], q.x); mx[0] = fmaxf(mx[0], q.x);
+      mn[1] = fminf(mn[1], q.y); mx[1] = fmaxf(mx[1], q.y);
+      mn[2] = fminf(mn[2], q.z); mx[2] = fmaxf(mx[2], q.z);
+    }
+  };
+  uint32_t surv_before = before;  // surviving entries before the current sub-tile
+  // the run entries of this tile: [r_lo, r_hi) = those whose key is >= this tile's first key and < the next tile's
+  const int r_lo = first_tile ? 0 : inc_bound<false, true>(r_key, 0, n_new, __ldcg(o_key + a0));
+  const int r_hi = last_tile ? n_new : inc_bound<false, true>(r_key, 0, n_new, __ldcg(o_key + b0));
+  int sub_lo = r_lo;
+  for (int a = a0; a < b0 || (a == a0 && a0 >= b0); a += INC_SUB) {  // (one pass with an empty range when the window is empty)
+    const int b = min(b0, a + INC_SUB), cnt = max(0, b - a);
+    const int sub_hi = b >= b0 ? r_hi : inc_bound<false, true>(r_key, sub_lo, r_hi, __ldcg(o_key + b));
+    const int ns = sub_hi - sub_lo;
+    const bool slice_in_smem = ns <= INC_SUB;
+    // old entries of the sub-tile: 4 consecutive ones per thread
+    constexpr int R = INC_SUB / 512;
+    static_assert(R * 512 == INC_SUB && GI_THREADS == 512, "sub-tile = four entries per thread of a 512-thread block");
+    const int l0 = R * tid;
+    unsigned long long k4[R];
+    bool al[R];
+    uint32_t c = 0;
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      const bool in = l0 + k < cnt;
+      k4[k] = in ? __ldcg(o_key + a + l0 + k) : INC_KEY_NONFINITE;
+      al[k] = in && inc_alive(__ldcg(o_tag + a + l0 + k), J);
+      s_keys[l0 + k] = k4[k];
+      c += al[k] ? 1u : 0u;
+    }
+    if (slice_in_smem)
+      for (int j = tid; j < ns; j += blockDim.x) s_slice[j] = __ldcg(r_key + sub_lo + j);
+    uint32_t incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += up;
+    }
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    uint32_t woff = 0, sub_total = 0;
+    for (int w = 0; w < nwarps; ++w) {
+      const uint32_t cw = s_w[w];
+      woff += w < warp ? cw : 0u;
+      sub_total += cw;
+    }
+    {
+      uint32_t run = woff + incl - c;
+#pragma unroll
+      for (int k = 0; k < R; ++k) {
+        s_pref[l0 + k] = run;  // surviving entries of the sub-tile before entry l0 + k
+        run += al[k] ? 1u : 0u;
+      }
+      if (tid == blockDim.x - 1) s_pref[INC_SUB] = run;
+    }
+    __syncthreads();
+    // surviving old entries -> (surviving entries before) + (run entries with a smaller key)
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      if (!al[k]) continue;
+      const int nb = slice_in_smem ? inc_bound<false, false>(s_slice, 0, ns, k4[k]) : inc_bound<false, true>(r_key + sub_lo, 0, ns, k4[k]);
+      const size_t pos = (size_t)surv_before + s_pref[l0 + k] + (size_t)(sub_lo + nb);
+      const float4 q = __ldcg(o_pts + a + l0 + k);
+      d_pts[pos] = q;
+      d_key[pos] = k4[k];
+      d_tag[pos] = __ldcg(o_tag + a + l0 + k);
+      track(q);
+    }
+    // run entries of the slice -> (their index in the run) + (surviving old entries with a key <= theirs)
+    for (int j = tid; j < ns; j += blockDim.x) {
+      const unsigned long long kx = slice_in_smem ? s_slice[j] : __ldcg(r_key + sub_lo + j);
+      const int ub = inc_bound<true, false>(s_keys, 0, cnt, kx);
+      const uint32_t surv = ub >= INC_SUB ? s_pref[INC_SUB] : (ub < cnt ? s_pref[ub] : s_pref[INC_SUB]);
+      const size_t pos = (size_t)(sub_lo + j) + surv_before + surv;
+      const float4 q = __ldcg(W.run_pts + sub_lo + j);
+      d_pts[pos] = q;
+      d_key[pos] = kx;
+      d_tag[pos] = __ldcg(W.run_tag + sub_lo + j);
+      track(q);
+    }
+    surv_before += sub_total;
+    sub_lo = sub_hi;
+    __syncthreads();
+    if (a0 >= b0) break;
+  }
+  // bounding box of everything written (finite points), as transform_minmax_kernel
+#pragma unroll
+  for (int ax = 0; ax < 3; ++ax) {
+    const float v0 = warp_min(mn[ax]), v1 = warp_max(mx[ax]);
+    if (lane == 0 && __any_sync(0x1u, true)) {
+      if (v0 <= v1) {
+        atomicMax(&M.st->mm[ax], ~float_to_ordered(v0));
+        atomicMax(&M.st->mm[3 + ax], float_to_ordered(v1));
+      }
+    }
+  }
+  (void)any;
+}
+
+// ---- V: heads of the merged window per tile, then the centroids (the reduce of gi_voxel on keyed, already ordered points).
+constexpr int INC_REDUCE_SMEM_WORDS = 4 * INC_SUB + INC_SUB + 8 + 64 + 16;
+__device__ __forceinline__ uint32_t inc_count_heads(const IncJob& J, int m, int t, int ntiles, uint32_t* s_w) {
+  const unsigned long long* key = J.w[m].key[J.cur ^ 1];
+  const int n = J.n_out[m];
+  const int len = (n + ntiles - 1) / ntiles;
+  const int a = min(n, t * len), b = min(n, a + len);
+  uint32_t c = 0;
+  for (int i = a + threadIdx.x; i < b; i += blockDim.x) {
+    const unsigned long long k = __ldcg(key + i);
+    const bool head = k < INC_KEY_NONFINITE - 1ull && (i == 0 || __ldcg(key + i - 1) != k);
+    c += head ? 1u : 0u;
+  }
+  c = __reduce_add_sync(0xffffffffu, c);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) s_w[warp] = c;
+  __syncthreads();
+  uint32_t tot = 0;
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += s_w[w];
+  __syncthreads();
+  return tot;
+}
+
+__device__ __forceinline__ void inc_reduce(const IncJob& J, const MapBatch& B, int m, int t, int ntiles, const uint32_t* heads,
+                                           uint32_t* smem) {
+  const MapBuffers& M = B.m[m];
+  const unsigned long long* keys = J.w[m].key[J.cur ^ 1];  // (written earlier in this launch: read with __ldcg)
+  const float4* pts = J.w[m].pts[J.cur ^ 1];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  const int n = J.n_out[m];
+  const int len = (n + ntiles - 1) / ntiles;
+  const int tile_begin = min(n, t * len), tile_end = min(n, tile_begin + len);
+  float4* s_pts = reinterpret_cast<float4*>(smem);                           // [INC_SUB]
+  int* s_head_pos = reinterpret_cast<int*>(smem + 4 * INC_SUB);              // [INC_SUB + 1]
+  uint32_t* s_wsum = smem + 4 * INC_SUB + INC_SUB + 8;                       // [nwarps]
+  int* s_misc = reinterpret_cast<int*>(smem + 4 * INC_SUB + INC_SUB + 8 + 32);
+  float4* s_cross_sum = reinterpret_cast<float4*>(smem + 4 * INC_SUB + INC_SUB + 8 + 64);
+  unsigned long long* s_cross_key = reinterpret_cast<unsigned long long*>(smem + 4 * INC_SUB + INC_SUB + 8 + 64 + 4);
+  // output slots before this tile, and the size of laserCloud*FromMapDS
+  uint32_t before = 0, total = 0;
+  for (int w = tid; w < ntiles; w += blockDim.x) {
+    const uint32_t c = __ldcg(heads + w);
+    total += c;
+    before += w < t ? c : 0u;
+  }
+  before = __reduce_add_sync(0xffffffffu, before);
+  total = __reduce_add_sync(0xffffffffu, total);
+  __syncthreads();
+  if (lane == 0) { s_wsum[warp] = before; s_wsum[16 + warp] = total; }
+  __syncthreads();
+  before = 0; total = 0;
+  for (int w = 0; w < nwarps; ++w) { before += s_wsum[w]; total += s_wsum[16 + w]; }
+  if (t == 0 && tid == 0) {
+    M.st->n_ds = (int)total;
+    M.st->n_raw = n;
+  }
+  constexpr int R = INC_SUB / 512;
+  uint32_t slot_base = before;
+  for (int base = tile_begin; base < tile_end; base += INC_SUB) {
+    const int sub_n = min(INC_SUB, tile_end - base);
+    __syncthreads();
+    if (tid == 0) { s_misc[0] = INC_SUB; s_misc[1] = 0; }  // [0] first non-finite entry, [1] a segment crosses the end
+    __syncthreads();
+    const int l0 = R * tid, i0 = base + l0;
+    unsigned long long k2[R];
+    bool head[R];
+    unsigned long long prev = (i0 > 0 && l0 < sub_n) ? __ldcg(keys + i0 - 1) : INC_KEY_NONFINITE;
+#pragma unroll
+    for (int k = 0; k < R; ++k) k2[k] = l0 + k < sub_n ? __ldcg(keys + i0 + k) : INC_KEY_NONFINITE;
+#pragma unroll
+    for (int k = 0; k < R; ++k) s_pts[l0 + k] = l0 + k < sub_n ? __ldcg(pts + i0 + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+    uint32_t cnt = 0;
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      const bool in = l0 + k < sub_n;
+      const bool boundary = in && (i0 + k == 0 || k2[k] != prev);
+      const bool dropped = k2[k] >= INC_KEY_NONFINITE - 1ull;
+      head[k] = boundary && !dropped;
+      if (in && dropped && (i0 + k == 0 || prev < INC_KEY_NONFINITE - 1ull)) s_misc[0] = l0 + k;  // first trailing entry
+      prev = k2[k];
+      cnt += head[k] ? 1u : 0u;
+    }
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += up;
+    }
+    if (lane == 31) s_wsum[warp] = incl;
+    __syncthreads();
+    uint32_t woff = 0, sub_total = 0;
+    for (int w = 0; w < nwarps; ++w) {
+      const uint32_t c = s_wsum[w];
+      woff += w < warp ? c : 0u;
+      sub_total += c;
+    }
+    const uint32_t local0 = woff + incl - cnt;
+    {
+      uint32_t ls = local0;
+#pragma unroll
+      for (int k = 0; k < R; ++k)
+        if (head[k]) s_head_pos[ls++] = l0 + k;
+    }
+    if (tid == 0) s_head_pos[sub_total] = sub_n;
+    __syncthreads();
+    const int sent_pos = s_misc[0];
+    uint32_t ls = local0;
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      if (!head[k]) continue;
+      const int beg = l0 + k;
+      const int end = min(s_head_pos[ls + 1], sent_pos);
+      const uint32_t slot = slot_base + ls;
+      ++ls;
+      float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
+      int jj = beg;
+      for (; jj + 4 <= end; jj += 4) {
+        const float4 p0 = s_pts[jj], p1 = s_pts[jj + 1], p2 = s_pts[jj + 2], p3 = s_pts[jj + 3];
+        sx += p0.x; sy += p0.y; sz += p0.z; si += p0.w;
+        sx += p1.x; sy += p1.y; sz += p1.z; si += p1.w;
+        sx += p2.x; sy += p2.y; sz += p2.z; si += p2.w;
+        sx += p3.x; sy += p3.y; sz += p3.z; si += p3.w;
+      }
+      for (; jj < end; ++jj) {
+        const float4 p = s_pts[jj];
+        sx += p.x; sy += p.y; sz += p.z; si += p.w;
+      }
+      const int c = end - beg;
+      if (end == sub_n && sent_pos >= sub_n && base + sub_n < n) {
+        // the segment may continue behind this sub-tile (or tile): park the running sums, the block finishes it below
+        *s_cross_sum = make_float4(sx, sy, sz, si);
+        s_misc[2] = c;
+        s_misc[3] = (int)slot;
+        *s_cross_key = k2[k];
+        s_misc[1] = 1;
+        continue;
+      }
+      const float fc = (float)c;
+      M.ds[slot] = make_float4(sx / fc, sy / fc, sz / fc, si / fc);
+    }
+    slot_base += sub_total;
+    __syncthreads();
+    if (!s_misc[1]) continue;  // block-uniform
+    float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
+    int c = 0;
+    if (tid == 0) {
+      sx = s_cross_sum->x; sy = s_cross_sum->y; sz = s_cross_sum->z; si = s_cross_sum->w;
+      c = s_misc[2];
+    }
+    const unsigned long long ck = *s_cross_key;
+    const uint32_t cslot = (uint32_t)s_misc[3];
+    for (int g0 = base + sub_n; g0 < n; g0 += (int)blockDim.x) {
+      const int g = g0 + tid;
+      const bool match = g < n && __ldcg(keys + g) == ck;
+      if (tid == 0) s_misc[5] = (int)blockDim.x;
+      __syncthreads();
+      if (!match) atomicMin(&s_misc[5], tid);
+      __syncthreads();
+      const int mcount = s_misc[5];
+      if (tid < mcount) s_pts[tid] = __ldcg(pts + g);
+      __syncthreads();
+      if (tid == 0) {
+        for (int u = 0; u < mcount; ++u) {
+          const float4 p = s_pts[u];
+          sx += p.x; sy += p.y; sz += p.z; si += p.w;
+        }
+        c += mcount;
+      }
+      __syncthreads();
+      if (mcount < (int)blockDim.x) break;
+    }
+    if (tid == 0) {
+      const float fc = (float)c;
+      M.ds[cslot] = make_float4(sx / fc, sy / fc, sz / fc, si / fc);
+    }
+  }
+}
+
+// The whole incremental step for the two maps of B. Every thread of every block of the co-resident grid calls; the caller
+// has zeroed both MapStates and passed a barrier. Returns with a grid barrier passed. smem: INC_SMEM_BYTES.
+__device__ __forceinline__ void map_incremental_inline(const IncJob& J, const MapBatch& B, unsigned* barrier, unsigned& epoch,
+                                                       uint32_t* smem) {
+  const int nb = (int)gridDim.x, blk = (int)blockIdx.x;
+  const bool has_run = J.n_new[0] > 0 || J.n_new[1] > 0;
+  const IncTiling T(nb, J.n_old, has_run);
+  uint32_t* s_w = smem + INC_MERGE_SMEM_WORDS - 64;
+  // ---- R | C
+  if (has_run && blk < 2 && T.first == 2) {
+    if (J.n_new[blk] > 0) inc_build_run(J, B, blk, reinterpret_cast<unsigned long long*>(smem));
+  } else if (has_run && T.first == 0 && blk == 0) {
+    for (int m = 0; m < 2; ++m) {
+      if (J.n_new[m] > 0) inc_build_run(J, B, m, reinterpret_cast<unsigned long long*>(smem));
+      __syncthreads();
+    }
+  }
+  if (blk >= T.first) {
+    const int w = blk - T.first;
+    if (nb - T.first < 2) {
+      for (int m = 0; m < 2; ++m) inc_count(J, m, 0, 1, J.w[m].counts, s_w);
+    } else {
+      const int m = w < T.nw[0] ? 0 : 1, t = m ? w - T.nw[0] : w;
+      inc_count(J, m, t, T.nw[m], J.w[m].counts + t, s_w);
+    }
+  }
+  coop_barrier(barrier, epoch);
+  // ---- M
+  if (blk >= T.first) {
+    const int w = blk - T.first;
+    if (nb - T.first < 2) {
+      for (int m = 0; m < 2; ++m) {
+        inc_merge(J, B, m, 0, 1, J.w[m].counts, smem);
+        __syncthreads();
+      }
+    } else {
+      const int m = w < T.nw[0] ? 0 : 1, t = m ? w - T.nw[0] : w;
+      inc_merge(J, B, m, t, T.nw[m], J.w[m].counts, smem);
+    }
+  }
+  coop_barrier(barrier, epoch);
+  if (!J.final_step) return;
+  // ---- V: every block takes part; the tiling is over the merged windows
+  const IncTiling TV(nb, J.n_out, false);
+  bool fail = false;
+#pragma unroll
+  for (int m = 0; m < 2; ++m) {
+    const VoxelMeta v = voxel_meta<true>(B.m[m].st, B.m[m].inv_leaf);
+    fail = fail || v.overflow || __ldcg(&B.m[m].st->inc_fail) != 0;
+  }
+  if (fail) {  // grid-uniform: the centroids are not computed; lm_begin_state reports it and the host rebuilds
+    if (blk == 0 && threadIdx.x == 0) { B.m[0].st->inc_fail = 1; B.m[1].st->inc_fail = 1; }
+    coop_barrier(barrier, epoch);
+    return;
+  }
+  uint32_t* s_wr = smem + INC_REDUCE_SMEM_WORDS - 80;
+  if (nb < 2) {
+    for (int m = 0; m < 2; ++m) {
+      const uint32_t c = inc_count_heads(J, m, 0, 1, s_wr);
+      if (threadIdx.x == 0) J.w[m].counts[INC_MAX_BLOCKS] = c;
+    }
+  } else {
+    const int m = blk < TV.nw[0] ? 0 : 1, t = m ? blk - TV.nw[0] : blk;
+    const uint32_t c = inc_count_heads(J, m, t, TV.nw[m], s_wr);
+    if (threadIdx.x == 0) J.w[m].counts[INC_MAX_BLOCKS + t] = c;
+  }
+  coop_barrier(barrier, epoch);
+  if (nb < 2) {
+    for (int m = 0; m < 2; ++m) {
+      inc_reduce(J, B, m, 0, 1, J.w[m].counts + INC_MAX_BLOCKS, smem);
+      __syncthreads();
+    }
+  } else {
+    const int m = blk < TV.nw[0] ? 0 : 1, t = m ? blk - TV.nw[0] : blk;
+    inc_reduce(J, B, m, t, TV.nw[m], J.w[m].counts + INC_MAX_BLOCKS, smem);
+  }
+  if (blk == 0 && threadIdx.x == 0) {
+    for (int m = 0; m < 2; ++m) {
+      B.m[m].st->voxel_overflow = 0;
+      B.m[m].st->voxel_bits = 0;
+    }
+  }
+  coop_barrier(barrier, epoch);
+}
+
+// One merge as its own cooperative launch: the groups of a long list of added keyframes before the last, and a pending
+// step that another consumer than ll_scan2map needs finished (ensure_map in abi.cu).
+__global__ void __launch_bounds__(GI_THREADS, 1) map_inc_kernel(const __grid_constant__ IncJob J, const __grid_constant__ MapBatch B,
+                                                                unsigned* barrier, unsigned* barrier_clear) {
+  extern __shared__ __align__(16) unsigned char s_inc[];
+  unsigned epoch = 0;
+  if (blockIdx.x == 0 && threadIdx.x < 128) reinterpret_cast<uint32_t*>(B.m[threadIdx.x >> 6].st)[threadIdx.x & 63] = 0u;
+  coop_barrier(barrier, epoch);
+  map_incremental_inline(J, B, barrier, epoch, reinterpret_cast<uint32_t*>(s_inc));
+  if (blockIdx.x == 0 && threadIdx.x == 0) *barrier_clear = 0u;
+}
+
+}  // namespace ll

@@ -345,10 +345,10 @@ __device__ __forceinline__ void gi_voxel(const MapBatch& B, unsigned* barrier, u
     val[k] = (uint32_t)i;
     if (mine && i < J.n) {
       const float4 p = __ldcg(&M.raw[i]);
-      if (!finite3(p)) {
+      if (v.overflow) {
+        key[k] = (uint32_t)i;  // (PCL's pass-through keeps the non-finite points too)
+      } else if (!finite3(p)) {
         key[k] = sent;
-      } else if (v.overflow) {
-        key[k] = (uint32_t)i;
       } else {
         const float inv = M.inv_leaf;
         const int i0 = (int)(floorf(p.x * inv) - (float)v.min_b[0]);
@@ -697,10 +697,10 @@ __global__ void __launch_bounds__(VS_THREADS, 1) voxel_small_kernel(const __grid
       if (i < n) {
         const float4 q = s_pts[i];
         uint32_t key;
-        if (!finite3(q)) {
+        if (v.overflow) {
+          key = (uint32_t)i;  // PCL's "leaf size too small": the input passes through (non-finite points too)
+        } else if (!finite3(q)) {
           key = sentinel;  // behind every voxel, dropped (PCL skips non-finite points)
-        } else if (v.overflow) {
-          key = (uint32_t)i;  // PCL's "leaf size too small": the input passes through, every point its own voxel
         } else {
           const int i0 = (int)(floorf(q.x * inv) - (float)v.min_b[0]);
           const int i1 = (int)(floorf(q.y * inv) - (float)v.min_b[1]);
@@ -729,7 +729,7 @@ __global__ void __launch_bounds__(VS_THREADS, 1) voxel_small_kernel(const __grid
   }
   __syncthreads();
   // segment heads -> output slots: every thread owns two consecutive sorted positions
-  const int n_valid = s_valid;  // sorted positions [0, n_valid) hold the finite points
+  const int n_valid = v.overflow ? n : s_valid;  // sorted positions [0, n_valid) hold the finite points (pass-through: all)
   bool head[2];
   uint32_t cnt = 0;
 #pragma unroll

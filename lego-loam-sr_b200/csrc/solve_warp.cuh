@@ -165,8 +165,12 @@ __device__ __forceinline__ bool ldlt6_solve(const float* AtA, const float* Atb, 
     double sj = (double)AtA[j * 6 + j];
 #pragma unroll
     for (int k = 0; k < j; ++k) sj -= L[j][k] * W[j][k];
-    ok = ok && (sj > 1e-12 * maxdiag);
-    rd[j] = 1.0 / sj;
+    ok = ok && (sj > 1e-12 * maxdiag) && (sj < 1e37);
+    // 1 / sj by a float reciprocal and two Newton steps in double (relative error ~1e-16, i.e. that of the division
+    // itself): the six pivots are a serial chain, and a double division is ~10x the latency of this
+    double r = (double)__frcp_rn((float)sj);
+    r = r * (2.0 - sj * r);
+    rd[j] = r * (2.0 - sj * r);
 #pragma unroll
     for (int i = j + 1; i < 6; ++i) {
       double t = (double)AtA[i * 6 + j];

@@ -6,8 +6,13 @@ import numpy as np
 from lego_loam_sr_b200 import synth, abi
 if os.environ.get("LLB200_LIB"):
     abi.LIB_PATH = os.environ["LLB200_LIB"]
-WORLD = dict(n_blocks=60, n_poles=600, half_x=80, half_z=120)
-d = synth.make_single(seed=1, n_map_scans=50, step=1.0, world_kw=WORLD)
+import bench
+if os.environ.get("LLB200_R01_WORLD"):
+    d = synth.make_single(seed=1, n_map_scans=50, step=bench.R01_STEP_M, world_kw=bench.R01_WORLD)
+else:  # the benchmark's workload (~118 k-point map, ~10 k queries)
+    d = synth.make_single(seed=1, n_map_scans=50, step=bench.BENCH_STEP_M, world_kw=bench.BENCH_WORLD)
+if os.environ.get("LLB200_SMALL_PRIOR"):  # a prior as close as the replay's odometry gives (the default is 0.5 deg / 5 cm off)
+    d["prior"] = synth.perturb(d["gt"], 0.05, 0.01, np.random.default_rng(1)).astype(np.float32)
 prm = abi.default_params(apply_update=1, eigen_mode=1, iter_count_thres=10, stop_thres=0.0, lm_solver=1)
 with abi.Handle(prm) as h:
     for i, f in enumerate(d["keyframes"]):
