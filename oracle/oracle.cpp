@@ -1137,3 +1137,171 @@ void orc_fa_correspondences(int which, const orc_p4* q, int nq, const orc_p4* la
 }
 
 }  // extern "C"
+
+// ---- f-1 + f-3 together: FeatureAssociation::updateTransformation (featureAssociation.cpp:2505-2535) ----------------
+// Row of matA and entry of matB of calculateTransformationSurf (:1884-1949): unknowns [rx, rz, ty]. sin / cos are the
+// unqualified C functions on float arguments (double functions, rounded to float on assignment: DESIGN.md §3); every
+// other expression is float arithmetic as written.
+namespace {
+
+struct FaTrig {
+  float srx, crx, sry, cry, srz, crz, tx, ty, tz;
+};
+
+inline FaTrig fa_trig(const float* tc) {
+  FaTrig t;
+  t.srx = (float)std::sin((double)tc[0]);
+  t.crx = (float)std::cos((double)tc[0]);
+  t.sry = (float)std::sin((double)tc[1]);
+  t.cry = (float)std::cos((double)tc[1]);
+  t.srz = (float)std::sin((double)tc[2]);
+  t.crz = (float)std::cos((double)tc[2]);
+  t.tx = tc[3];
+  t.ty = tc[4];
+  t.tz = tc[5];
+  return t;
+}
+
+struct FaSurfConst {  // :1898-1923
+  float a1, a2, a3, a4, a5, a6, a7, a8, a9, a10, a11, b1, b2, b5, b6, c1, c2, c3, c4, c5, c6, c7, c8, c9, crx;
+};
+
+inline FaSurfConst fa_surf_const(const FaTrig& g) {
+  FaSurfConst k;
+  const float srx = g.srx, crx = g.crx, sry = g.sry, cry = g.cry, srz = g.srz, crz = g.crz, tx = g.tx, ty = g.ty, tz = g.tz;
+  k.a1 = crx * sry * srz;
+  k.a2 = crx * crz * sry;
+  k.a3 = srx * sry;
+  k.a4 = tx * k.a1 - ty * k.a2 - tz * k.a3;
+  k.a5 = srx * srz;
+  k.a6 = crz * srx;
+  k.a7 = ty * k.a6 - tz * crx - tx * k.a5;
+  k.a8 = crx * cry * srz;
+  k.a9 = crx * cry * crz;
+  k.a10 = cry * srx;
+  k.a11 = tz * k.a10 + ty * k.a9 - tx * k.a8;
+  k.b1 = -crz * sry - cry * srx * srz;
+  k.b2 = cry * crz * srx - sry * srz;
+  k.b5 = cry * crz - srx * sry * srz;
+  k.b6 = cry * srz + crz * srx * sry;
+  k.c1 = -k.b6;
+  k.c2 = k.b5;
+  k.c3 = tx * k.b6 - ty * k.b5;
+  k.c4 = -crx * crz;
+  k.c5 = crx * srz;
+  k.c6 = ty * k.c5 + tx * -k.c4;
+  k.c7 = k.b2;
+  k.c8 = -k.b1;
+  k.c9 = tx * -k.b2 - ty * -k.b1;
+  k.crx = crx;
+  return k;
+}
+
+inline void fa_surf_row(const FaSurfConst& k, const orc_p4& o, const float* c, float r[3], float& b) {  // :1926-1948
+  r[0] = (-k.a1 * o.x + k.a2 * o.y + k.a3 * o.z + k.a4) * c[0] + (k.a5 * o.x - k.a6 * o.y + k.crx * o.z + k.a7) * c[1] +
+         (k.a8 * o.x - k.a9 * o.y - k.a10 * o.z + k.a11) * c[2];
+  r[1] = (k.c1 * o.x + k.c2 * o.y + k.c3) * c[0] + (k.c4 * o.x - k.c5 * o.y + k.c6) * c[1] + (k.c7 * o.x + k.c8 * o.y + k.c9) * c[2];
+  r[2] = -k.b6 * c[0] + k.c4 * c[1] + k.b2 * c[2];
+  b = (float)(-0.05 * (double)c[3]);
+}
+
+struct FaCornerConst {  // :2034-2044
+  float b1, b2, b3, b4, b5, b6, b7, b8, c5, srx;
+};
+
+inline FaCornerConst fa_corner_const(const FaTrig& g) {
+  FaCornerConst k;
+  const float srx = g.srx, crx = g.crx, sry = g.sry, cry = g.cry, srz = g.srz, crz = g.crz, tx = g.tx, ty = g.ty, tz = g.tz;
+  k.b1 = -crz * sry - cry * srx * srz;
+  k.b2 = cry * crz * srx - sry * srz;
+  k.b3 = crx * cry;
+  k.b4 = tx * -k.b1 + ty * -k.b2 + tz * k.b3;
+  k.b5 = cry * crz - srx * sry * srz;
+  k.b6 = cry * srz + crz * srx * sry;
+  k.b7 = crx * sry;
+  k.b8 = tz * k.b7 - ty * k.b6 - tx * k.b5;
+  k.c5 = crx * srz;
+  k.srx = srx;
+  return k;
+}
+
+inline void fa_corner_row(const FaCornerConst& k, const orc_p4& o, const float* c, float r[3], float& b) {  // :2050-2066
+  r[0] = (k.b1 * o.x + k.b2 * o.y - k.b3 * o.z + k.b4) * c[0] + (k.b5 * o.x + k.b6 * o.y - k.b7 * o.z + k.b8) * c[2];
+  r[1] = -k.b5 * c[0] + k.c5 * c[1] + k.b1 * c[2];
+  r[2] = k.b7 * c[0] - k.srx * c[1] - k.b3 * c[2];
+  b = (float)(-0.05 * (double)c[3]);
+}
+
+}  // namespace
+
+extern "C" {
+
+// One of the two loops of updateTransformation (:2508-2518 surf, :2521-2530 corner). Returns the loop counter at exit.
+static int fa_loop(int which, const orc_p4* q, int nq, const orc_p4* last, int n_last, float tc[6], float dist_sqr,
+                   int eigen_mode, int use_ext_knn, orc_fa_state* st, float* trace) {
+  std::vector<int> ind1((size_t)std::max(nq, 1), -1), ind2(ind1), ind3(ind1), keep(ind1);
+  std::vector<float> coeff((size_t)std::max(nq, 1) * 4), rows, rhs;
+  float* matP = which ? st->matP_surf : st->matP_corner;
+  int it = 0;
+  for (; it < 100; ++it) {
+    orc_fa_correspondences(which, q, nq, last, n_last, tc, it, dist_sqr, ind1.data(), ind2.data(), ind3.data(), coeff.data(),
+                           keep.data(), use_ext_knn);
+    rows.clear();
+    rhs.clear();
+    const FaTrig g = fa_trig(tc);
+    const FaSurfConst ks = fa_surf_const(g);
+    const FaCornerConst kc = fa_corner_const(g);
+    for (int i = 0; i < nq; ++i) {
+      if (!keep[i]) continue;
+      float r[3], b;
+      if (which) fa_surf_row(ks, q[i], &coeff[4 * (size_t)i], r, b);
+      else fa_corner_row(kc, q[i], &coeff[4 * (size_t)i], r, b);
+      rows.insert(rows.end(), {r[0], r[1], r[2], 0.f, 0.f, 0.f});
+      rhs.push_back(b);
+    }
+    const int n = (int)rhs.size();
+    if (trace) { trace[4 * it] = trace[4 * it + 1] = trace[4 * it + 2] = 0.f; trace[4 * it + 3] = (float)n; }
+    if (n < 10) continue;  // :2514 / :2527
+    const int cols[3] = {0, 1, 2};
+    float x[3];
+    solve_normal_eq_t<3>(rows.data(), rhs.data(), n, cols, it, 10.f, eigen_mode, x, matP, &st->is_degenerate);
+    if (trace) { trace[4 * it] = x[0]; trace[4 * it + 1] = x[1]; trace[4 * it + 2] = x[2]; }
+    float deltaR, deltaT;
+    if (which) {  // :1992-2004
+      tc[0] += x[0];
+      tc[2] += x[1];
+      tc[4] += x[2];
+      const double r0 = (double)(57.29578f * x[0]), r1 = (double)(57.29578f * x[1]), t0 = (double)(x[2] * 100.f);
+      deltaR = (float)std::sqrt(r0 * r0 + r1 * r1);
+      deltaT = (float)std::sqrt(t0 * t0);
+    } else {      // :2127-2137
+      tc[1] += x[0];
+      tc[3] += x[1];
+      tc[5] += x[2];
+      const double r0 = (double)(57.29578f * x[0]), t0 = (double)(x[1] * 100.f), t1 = (double)(x[2] * 100.f);
+      deltaR = (float)std::sqrt(r0 * r0);
+      deltaT = (float)std::sqrt(t0 * t0 + t1 * t1);
+    }
+    for (int k = 0; k < 6; ++k)
+      if (std::isnan(tc[k])) tc[k] = 0.f;
+    if ((double)deltaR < 0.1 && (double)deltaT < 0.1) break;  // calculateTransformation* returned false
+  }
+  return it;
+}
+
+void orc_fa_init_state(orc_fa_state* st) {  // isDegenerate = false (:223); matP is a function-local there (see oracle.h)
+  std::memset(st, 0, sizeof(*st));
+}
+
+int orc_fa_update_transformation(const orc_p4* corner_sharp, int n_cs, const orc_p4* surf_flat, int n_sf,
+                                 const orc_p4* corner_last, int n_cl, const orc_p4* surf_last, int n_sl,
+                                 float transform_cur[6], float nearest_feature_dist_sqr, int eigen_mode, int use_ext_knn,
+                                 orc_fa_state* st, int iters[2], float* trace_surf, float* trace_corner) {
+  iters[0] = iters[1] = 0;
+  if (n_cl < 10 || n_sl < 100) return 1;  // :2506
+  iters[0] = fa_loop(1, surf_flat, n_sf, surf_last, n_sl, transform_cur, nearest_feature_dist_sqr, eigen_mode, use_ext_knn, st, trace_surf);
+  iters[1] = fa_loop(0, corner_sharp, n_cs, corner_last, n_cl, transform_cur, nearest_feature_dist_sqr, eigen_mode, use_ext_knn, st, trace_corner);
+  return 0;
+}
+
+}  // extern "C"

@@ -152,6 +152,26 @@ void orc_fa_correspondences(int which, const orc_p4* q, int nq, const orc_p4* la
                             int* keep, int use_ext_knn);
 void orc_fa_transform_to_start(const orc_p4* in, int n, const float transform_cur[6], orc_p4* out);
 
+/* f-1 + f-3 as the reference runs them: FeatureAssociation::updateTransformation (featureAssociation.cpp:2505-2535) —
+ * up to 100 iterations of findCorrespondingSurfFeatures + calculateTransformationSurf (:1846-2010; unknowns rx, rz, ty),
+ * then up to 100 of findCorrespondingCornerFeatures + calculateTransformationCorner (:2013-2143; unknowns ry, tx, tz).
+ * transform_cur is transformCur (in / out). State that outlives a call in the reference: isDegenerate (a class member,
+ * shared by both loops, :223) and — by accident of the stack — matP, a function-LOCAL that is only assigned at
+ * iterCount == 0 but read at every iteration while isDegenerate is set (:1961-1990): reading it later is undefined
+ * behaviour upstream; here it is kept per function from its last iteration 0 (zero before the first), which is what a
+ * reused stack slot gives. iters[0] / iters[1] = iterCount1 / iterCount2 at loop exit (100 = never converged).
+ * trace_* (nullable, [100][4]): matX and the row count of every iteration. Returns 1 when the :2506 guard skipped. */
+typedef struct orc_fa_state {
+  int is_degenerate;
+  float matP_surf[9];
+  float matP_corner[9];
+} orc_fa_state;
+void orc_fa_init_state(orc_fa_state* st);
+int orc_fa_update_transformation(const orc_p4* corner_sharp, int n_cs, const orc_p4* surf_flat, int n_sf,
+                                 const orc_p4* corner_last, int n_cl, const orc_p4* surf_last, int n_sl,
+                                 float transform_cur[6], float nearest_feature_dist_sqr, int eigen_mode, int use_ext_knn,
+                                 orc_fa_state* st, int iters[2], float* trace_surf, float* trace_corner);
+
 void orc_test_self_adjoint_eig(const float* A, int n, float* evals, float* evecs);
 void orc_test_colpiv_qr_solve(const float* A, const float* b, int rows, int cols, float* x);
 void orc_test_inverse6(const float* A, float* inv);

@@ -357,3 +357,31 @@ def fa_transform_to_start(pts, transform_cur):
     tc = np.ascontiguousarray(transform_cur, np.float32)
     lib().orc_fa_transform_to_start(_ptr(pts), C.c_int(len(pts)), _ptr(tc), _ptr(out))
     return out
+
+
+class FaState(C.Structure):
+    _fields_ = [("is_degenerate", C.c_int), ("matP_surf", C.c_float * 9), ("matP_corner", C.c_float * 9)]
+
+
+def fa_update_transformation(corner_sharp, surf_flat, corner_last, surf_last, transform_cur, nearest_feature_dist_sqr=25.0,
+                             eigen_mode=0, use_nanoflann=False, state=None):
+    """f-1 + f-3: FeatureAssociation::updateTransformation (featureAssociation.cpp:2505-2535). -> dict(transform_cur,
+    iters_surf, iters_corner, skipped, is_degenerate, trace_surf [iters][4], trace_corner [iters][4], state)."""
+    cs, sf, cl, sl = _p4(corner_sharp), _p4(surf_flat), _p4(corner_last), _p4(surf_last)
+    tc = np.ascontiguousarray(transform_cur, np.float32).copy()
+    st = state if state is not None else FaState()
+    if state is None:
+        lib().orc_fa_init_state(C.byref(st))
+    iters = (C.c_int * 2)(0, 0)
+    tr_s = np.zeros((100, 4), np.float32)
+    tr_c = np.zeros((100, 4), np.float32)
+    if use_nanoflann and not have_ref():
+        raise RuntimeError("oracle/_ref/libnanoflann_ref.so is not built")
+    lib().orc_fa_update_transformation.restype = C.c_int
+    skipped = lib().orc_fa_update_transformation(_ptr(cs), C.c_int(len(cs)), _ptr(sf), C.c_int(len(sf)), _ptr(cl), C.c_int(len(cl)),
+                                                 _ptr(sl), C.c_int(len(sl)), _ptr(tc), C.c_float(nearest_feature_dist_sqr),
+                                                 C.c_int(eigen_mode), C.c_int(1 if use_nanoflann else 0), C.byref(st), iters,
+                                                 _ptr(tr_s), _ptr(tr_c))
+    return dict(transform_cur=tc, iters_surf=iters[0], iters_corner=iters[1], skipped=int(skipped),
+                is_degenerate=int(st.is_degenerate), trace_surf=tr_s[:min(iters[0] + 1, 100)],
+                trace_corner=tr_c[:min(iters[1] + 1, 100)], state=st)

@@ -86,7 +86,22 @@ def _full_check(abi, orc, d, cq, sq, map_downsample=1, knn_sample=4000, label=""
             assert np.array_equal(g["accept"], o["accept"]), name
             assert (g["mask"] != o["mask"]).sum() <= max(3, len(q) // 2000), name
             both = (g["mask"] != 0) & (o["mask"] != 0)
-            assert np.abs(g["coeff"][both] - o["coeff"][both]).max() <= tol_coeff, name
+            diff = np.abs(g["coeff"][both] - o["coeff"][both]).max(axis=1)
+            allowed = np.full(len(diff), tol_coeff, np.float64)
+            if name == "corner":
+                # The line is given by the two points c +- 0.1 * v (mapOptmization.cpp:1329-1334), STORED AS FLOATS, and
+                # (la, lb, lc) is the unit perpendicular from that line to the query. The principal direction v differs
+                # by ~1e-7 between the closed form in double (here) and Eigen's float QR iteration (the oracle); that
+                # is enough to round a coordinate of c +- 0.1 v to the neighbouring float — one ulp of the map
+                # coordinate, 1.5e-5 m at 130-250 m from the origin — which turns the perpendicular by ulp / ld2. The
+                # reference's own float arithmetic has the same granularity (a float64 evaluation of the same formula
+                # differs from both by up to 1e-3 on configs[3]); the tolerance follows it.
+                ld2 = np.abs(o["coeff"][both][:, 3]).astype(np.float64)
+                qm = orc.transform_cloud(q, d["prior"])[both]
+                ulp = np.spacing(np.abs(qm[:, :3]).max(axis=1).astype(np.float32)).astype(np.float64)
+                allowed += 2.0 * ulp / np.maximum(ld2, 1e-6)
+            worst = int(np.argmax(diff - allowed))
+            assert (diff <= allowed).all(), (name, float(diff[worst]), float(allowed[worst]))
     ores, opose, _ = orc.scan2map(cds, sds, cq, sq, d["prior"], oprm)
     assert res.status == 0 and res.iter_num == ores.iter_num == 10
     assert abs(res.sel_num - ores.sel_num) <= max(3, ores.sel_num // 2000)

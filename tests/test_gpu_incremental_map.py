@@ -38,11 +38,23 @@ def oracle_maps(orc, frames, poses, ids, prm):
                                [frames[i]["surf_last_ds"] for i in ids], [frames[i]["outlier_last_ds"] for i in ids], prm)[:2]
 
 
+def same(a, b):
+    """Bit for bit, except that a NaN only has to be a NaN: the pass-through case keeps non-finite points, and a NaN born
+    in the keyframe transform (inf - inf) is 0xffc00000 on x86 and 0x7fffffff on the GPU — the payload carries nothing."""
+    if a.shape != b.shape:
+        return False
+    ba, bb = bits(a), bits(b)
+    return bool(((ba == bb) | (np.isnan(a) & np.isnan(b))).all())
+
+
 def check(h, orc, frames, poses, ids, prm, what):
     cds, sds = oracle_maps(orc, frames, poses, ids, prm)
     gc, gs = h.get_map_ds(0), h.get_map_ds(1)
-    assert gc.shape == cds.shape and np.array_equal(bits(gc), bits(cds)), "corner map differs from the oracle: " + what
-    assert gs.shape == sds.shape and np.array_equal(bits(gs), bits(sds)), "surf map differs from the oracle: " + what
+    if not same(gc, cds) and gc.shape == cds.shape:
+        bad = np.nonzero((bits(gc) != bits(cds)).any(axis=1))[0]
+        print("corner rows that differ:", bad[:10], gc[bad[:5]], cds[bad[:5]])
+    assert same(gc, cds), "corner map differs from the oracle: " + what
+    assert same(gs, sds), "surf map differs from the oracle: " + what
     return cds, sds
 
 
