@@ -243,6 +243,30 @@ int ll_fa_find_correspondences(ll_handle h, int which, const void* queries, size
                                const float transform_cur[6], int iter_count, float nearest_feature_dist_sqr,
                                int* ind1, int* ind2, int* ind3, float* coeff4, int* keep);
 
+/* ---- f-1 + f-3 as the reference runs them: FeatureAssociation::updateTransformation (featureAssociation.cpp:2505-2535),
+ * the whole of it in one call and one launch — up to 100 iterations of findCorrespondingSurfFeatures +
+ * calculateTransformationSurf (:1846-2010; unknowns rx, rz, ty), then up to 100 of findCorrespondingCornerFeatures +
+ * calculateTransformationCorner (:2013-2143; unknowns ry, tx, tz): correspondence search every fifth iteration, Jacobian
+ * rows, b = -0.05 d, 3x3 normal equations, eigen threshold 10 at iterCount == 0, NaN reset, the deltaR / deltaT < 0.1 exit.
+ * corner_sharp / surf_flat = cornerPointsSharp / surfPointsFlat of the current sweep; the previous sweep's clouds are those
+ * of ll_fa_set_last. transform_cur_inout = transformCur. isDegenerate (a class member upstream, :223) and the matP of each
+ * function persist in the handle from call to call (ll_fa_reset_state clears them); params.eigen_mode selects the
+ * as-shipped or upstream projector as for LMOptimization. trace (nullable, [2][100][4] floats): matX and the row count of
+ * every iteration, surf loop first. Synchronous. */
+typedef struct ll_fa_result {
+  float transform_cur[6];
+  int   iters_surf;     /* iterCount1 at loop exit (100: the loop ran out) */
+  int   iters_corner;   /* iterCount2 */
+  int   is_degenerate;
+  int   skipped;        /* 1: the :2506 guard (laserCloudCornerLastNum < 10 || laserCloudSurfLastNum < 100) returned */
+  int   n_sel_surf;     /* laserCloudOri size of the last iteration of each loop */
+  int   n_sel_corner;
+} ll_fa_result;
+int ll_fa_update_transformation(ll_handle h, const void* corner_sharp, size_t n_corner, const void* surf_flat, size_t n_surf,
+                                size_t stride_bytes, float transform_cur_inout[6], float nearest_feature_dist_sqr,
+                                ll_fa_result* res, float* trace);
+int ll_fa_reset_state(ll_handle h);
+
 #ifdef __cplusplus
 }
 #endif

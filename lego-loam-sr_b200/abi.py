@@ -42,6 +42,12 @@ class Result(C.Structure):
                 ("last_x", C.c_float * 6)]
 
 
+class FaResult(C.Structure):
+    """ll_fa_result (include/legoloam_b200.h)."""
+    _fields_ = [("transform_cur", C.c_float * 6), ("iters_surf", C.c_int), ("iters_corner", C.c_int), ("is_degenerate", C.c_int),
+                ("skipped", C.c_int), ("n_sel_surf", C.c_int), ("n_sel_corner", C.c_int)]
+
+
 class ScanClouds(C.Structure):
     """ll_scan_clouds: device copies of downsampleCurrentScan's inputs and results (valid until the next call)."""
     _fields_ = [("d_raw", C.c_void_p * 5), ("n_raw", C.c_size_t * 5), ("d_ds", C.c_void_p * 6), ("n_ds", C.c_size_t * 6),
@@ -303,6 +309,27 @@ class Handle:
                                                          _vp(tc), C.c_int(it), C.c_float(nearest_feature_dist_sqr),
                                                          _vp(ind[0]), _vp(ind[1]), _vp(ind[2]), _vp(coeff), _vp(keep)))
         return ind[0][:nq], ind[1][:nq], ind[2][:nq], coeff[:nq], keep[:nq]
+
+    def fa_update_transformation(self, corner_sharp, surf_flat, transform_cur, nearest_feature_dist_sqr=25.0, want_trace=False):
+        """f-1 + f-3 in one launch: FeatureAssociation::updateTransformation. -> dict(transform_cur, iters_surf,
+        iters_corner, is_degenerate, skipped, n_sel_surf, n_sel_corner[, trace_surf, trace_corner])."""
+        cs = np.ascontiguousarray(corner_sharp, np.float32).reshape(-1, 4)
+        ss = np.ascontiguousarray(surf_flat, np.float32).reshape(-1, 4)
+        tc = np.ascontiguousarray(transform_cur, np.float32).copy()
+        res = FaResult()
+        trace = np.zeros((2, 100, 4), np.float32) if want_trace else None
+        self._check(self._lib.ll_fa_update_transformation(self._h, _vp(cs), C.c_size_t(len(cs)), _vp(ss), C.c_size_t(len(ss)),
+                                                          C.c_size_t(16), _vp(tc), C.c_float(nearest_feature_dist_sqr),
+                                                          C.byref(res), _vp(trace) if want_trace else None))
+        out = dict(transform_cur=tc, iters_surf=res.iters_surf, iters_corner=res.iters_corner, is_degenerate=res.is_degenerate,
+                   skipped=res.skipped, n_sel_surf=res.n_sel_surf, n_sel_corner=res.n_sel_corner)
+        if want_trace:
+            out["trace_surf"] = trace[0, :min(res.iters_surf + 1, 100)]
+            out["trace_corner"] = trace[1, :min(res.iters_corner + 1, 100)]
+        return out
+
+    def fa_reset_state(self):
+        self._check(self._lib.ll_fa_reset_state(self._h))
 
     def _residuals(self, fn, queries, pose6):
         q, nq, stride = _cloud(queries)

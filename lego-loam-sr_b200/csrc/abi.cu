@@ -20,6 +20,7 @@
 
 #include "common.cuh"
 #include "fa_corr.cuh"
+#include "fa_loop.cuh"
 #include "fit.cuh"
 #include "lm.cuh"
 #include "map_build.cuh"
@@ -31,6 +32,7 @@ using namespace ll;
 namespace {
 
 constexpr size_t kArenaChunk = 256ull << 20;  // keyframe store grows in 256 MiB slabs (~1000 VLP-16 keyframes each)
+constexpr int kIncPlanMaxRun = 4096;         // largest keyframe cloud (points per map) the incremental map assembly is chosen for
 constexpr int kCellCap = 1 << 24;            // 16.7 M one-metre cells per search grid (<= 24 key bits: 3 sort passes)
 constexpr int kGridPasses = 3;
 constexpr size_t kSpeculativeD2HBytes = 256u << 10;  // ll_voxel_downsample: copy all n output slots before n_ds is known
@@ -57,6 +59,7 @@ struct MapSlot {
   float4 *raw = nullptr, *ds = nullptr, *sorted = nullptr;
   uint32_t *keys[2] = {nullptr, nullptr}, *vals[2] = {nullptr, nullptr};
   int2* cells = nullptr;
+  int cell_tag = 0;  // stamp of the grid build that wrote the valid entries of `cells` (0: table not initialised yet)
   uint8_t* scratch = nullptr;  // [MapState | ghist | tile counters | head status | look-back status], zeroed per build
   size_t scratch_bytes = 0;
   int max_tiles = 0, max_head_tiles = 0;
@@ -141,6 +144,7 @@ struct ll_handle_s {
     int n[2] = {0, 0};              // entries per map
     size_t cap[2] = {0, 0};
     WindowBuffers wb[2] = {};
+    bool unchecked = false;         // a merge was enqueued since the host last read a verdict (MapState::inc_fail)
     bool job_pending = false;       // the last merge of the current build is left to the next scan kernel / ensure_map()
     IncJob job = {};
     bool inc_opt_in = false;        // map_inc_kernel's dynamic shared memory attribute set
@@ -159,6 +163,12 @@ struct ll_handle_s {
   size_t res_pin_bytes = 0;
   size_t fa_last_cap[2] = {0, 0};
   int fa_n_last[2] = {0, 0};
+  // ll_fa_update_transformation (fa_loop.cuh): isDegenerate / matP / transformCur block, its pinned mirror, scratch
+  FaLoopState* d_fa_state = nullptr;
+  FaLoopState* h_fa_state = nullptr;
+  void* d_fa_work = nullptr;   // [queries corner | queries surf | ind 3 x cap | partials | trace]
+  size_t fa_work_bytes = 0;
+  bool fa_state_init = false;
 
   // optional per-kernel-class timing with CUDA events on the launching stream (bench.py roofline)
   bool prof_on = false;
@@ -414,6 +424,7 @@ MapBuffers slot_buffers(const ll_handle h, int s, float leaf, int downsample, bo
   M.member = want_member ? S.member : nullptr;
   M.n_raw = S.n_raw;
   M.cell_cap = kCellCap;
+  M.cell_tag = S.cell_tag;
   M.inv_leaf = 1.0f / leaf;
   M.downsample = downsample;
   return M;
@@ -501,6 +512,26 @@ int seglist_to_device(ll_handle h) {
 int run_grid_build(ll_handle h);
 int plan_incremental_restart(ll_handle h, const int* ids, int n_ids, bool* used);
 
+// The cell table of a slot is stamped, not cleared (map_build.cuh: cell_entry_x): every grid build takes the next stamp;
+// the table is reset to (~0, 0) once after its allocation and whenever the 8-bit stamp wraps (every 255 builds).
+__global__ void cells_reset_kernel(int2* cells, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    cells[i] = make_int2((int)0xffffffffu, 0);
+}
+
+int next_cell_tag(ll_handle h, int s) {
+  MapSlot& S = h->slot[s];
+  if (!S.cells) return LL_OK;
+  if (S.cell_tag <= 0 || S.cell_tag >= 255) {
+    cells_reset_kernel<<<(unsigned)(8 * h->num_sms), 256, 0, h->stream>>>(S.cells, (size_t)kCellCap);
+    LL_LAUNCHED(h);
+    S.cell_tag = 1;
+  } else {
+    ++S.cell_tag;
+  }
+  return LL_OK;
+}
+
 // The MapBatch of the slots in h->grid_cfg, with the sort problems of the voxel phase or of the grid phase.
 MapBatch make_map_batch(const ll_handle h, bool grid_phase) {
   const auto& c = h->grid_cfg;
@@ -527,6 +558,7 @@ int run_voxel_build(ll_handle h, bool want_member);
 // ---- incremental local map: host side --------------------------------------------------------------------------
 void window_invalidate(ll_handle h) {
   h->win.valid = false;
+  h->win.unchecked = false;
   h->win.job_pending = false;
   h->win.ids.clear();
   h->win.n[0] = h->win.n[1] = 0;
@@ -668,7 +700,11 @@ int plan_incremental(ll_handle h, const int* ids, int n_ids, bool* used) {
     for (int k = n_kept; k < n_ids; ++k) {
       const Keyframe& kf = h->kfs[ids[k]];
       const int c = kf.n[0], sfo = kf.n[1] + kf.n[2];
-      if (c > INC_RUN_MAX || sfo > INC_RUN_MAX) {  // a single keyframe too large for one run: full path
+      // A keyframe too large for one run takes the full path — and so does one whose run is large enough that sorting
+      // it costs more than the full rebuild saves: the run is sorted by ONE block (a bitonic network in shared memory,
+      // measured 92 us for 10 k points padded to 16 k, ~12 us for 4 k), while the full path's three radix passes over a
+      // 0.6 M-point window take ~55 us once the cell tables need no clearing (profiles/r02_scan_barrier_timeline.txt).
+      if (c > INC_RUN_MAX || sfo > INC_RUN_MAX || c > kIncPlanMaxRun || sfo > kIncPlanMaxRun) {
         window_invalidate(h);
         return LL_OK;
       }
@@ -763,6 +799,8 @@ int plan_incremental(ll_handle h, const int* ids, int n_ids, bool* used) {
     J.n_out[0] = out[0] + oc;
     J.n_out[1] = out[1] + os;
     J.final_step = si + 1 == steps.size() ? 1 : 0;
+    J.keep_fail = win.unchecked ? 1 : 0;  // a failed earlier merge of this chain must still be seen at its end
+    win.unchecked = true;
     win.cur ^= 1;  // (as enqueued: everything below is stream-ordered)
     win.n[0] = J.n_out[0];
     win.n[1] = J.n_out[1];
@@ -937,6 +975,7 @@ int ensure_map(ll_handle h) {
     for (int m = 0; m < 2; ++m)
       LL_CUDA(h, cudaMemcpyAsync(&fail_flag[m], &h->slot[m].st()->inc_fail, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     LL_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (!(fail_flag[0] || fail_flag[1])) h->win.unchecked = false;
     if (fail_flag[0] || fail_flag[1]) {  // not representable incrementally: the same keyframes through the full path
       const std::vector<int> ids = h->win.ids;
       window_invalidate(h);
@@ -955,6 +994,8 @@ int ensure_map(ll_handle h) {
 int run_grid_build(ll_handle h) {
   const int sa = h->grid_cfg.sa, sb = h->grid_cfg.sb;
   const int ny = sb >= 0 ? 2 : 1;
+  LL_TRY(next_cell_tag(h, sa));
+  if (sb >= 0) LL_TRY(next_cell_tag(h, sb));
   MapBatch B = make_map_batch(h, true);
   const int slots[2] = {sa, sb};
   int maxn = 0;
@@ -1128,6 +1169,10 @@ int scan2map_enqueue(ll_handle h, const float pose6[6]) {
     unsigned* bar = h->d_barriers + (h->scan_seq % kBarrierSlots);
     unsigned* bar_clear = h->d_barriers + ((h->scan_seq + kBarrierSlots / 2) % kBarrierSlots);
     h->scan_seq++;
+    if (h->grid_deferred) {  // this launch builds the search grids: their cell tables take the next stamp
+      LL_TRY(next_cell_tag(h, h->grid_cfg.sa));
+      if (h->grid_cfg.sb >= 0) LL_TRY(next_cell_tag(h, h->grid_cfg.sb));
+    }
     MapBatch GB = make_map_batch(h, true);
     int build_map = h->map_deferred ? (h->win.job_pending ? 2 : 1) : 0, build_grid = h->grid_deferred ? 1 : 0;
     h->map_deferred = h->grid_deferred = false;
@@ -1222,6 +1267,7 @@ int scan2map_collect(ll_handle h, float pose6_out[6], ll_result* res) {
     h->retried = false;
     return rc;
   }
+  if (h->scan_used_inc) h->win.unchecked = false;  // this scan's map came out of the window and carried no failure flag
   h->scan_used_inc = false;
   if (pose6_out) std::memcpy(pose6_out, h->h_state->pose, 6 * sizeof(float));
   if (res) fill_result(*h->h_state, res);
@@ -1362,6 +1408,9 @@ int ll_destroy(ll_handle h) {
   }
   window_free(h);
   if (h->h_state) cudaFreeHost(h->h_state);
+  if (h->h_fa_state) cudaFreeHost(h->h_fa_state);
+  if (h->d_fa_state) cudaFree(h->d_fa_state);
+  if (h->d_fa_work) cudaFree(h->d_fa_work);
   if (h->res_pin) cudaFreeHost(h->res_pin);
   if (h->scan_buf) cudaFree(h->scan_buf);
   for (cudaEvent_t e : h->prof_pool) cudaEventDestroy(e);
@@ -2159,6 +2208,100 @@ int ll_fa_find_correspondences(ll_handle h, int which, const void* queries, size
   std::memcpy(keep, pin + nq * 12, nq * 4);
   std::memcpy(coeff4, pin + nq * 16, nq * 16);
   LL_TRY(pinned_release(h));
+  return LL_OK;
+}
+
+int ll_fa_reset_state(ll_handle h) {
+  if (!h) return LL_ERR_INVALID_ARG;
+  h->fa_state_init = false;
+  return LL_OK;
+}
+
+int ll_fa_update_transformation(ll_handle h, const void* corner_sharp, size_t n_corner, const void* surf_flat, size_t n_surf,
+                                size_t stride_bytes, float transform_cur_inout[6], float nearest_feature_dist_sqr,
+                                ll_fa_result* res, float* trace) {
+  if (!h) return LL_ERR_INVALID_ARG;
+  if (!transform_cur_inout) return fail(h, LL_ERR_INVALID_ARG, "transform_cur is NULL");
+  if ((n_corner && !corner_sharp) || (n_surf && !surf_flat) || !stride_ok(stride_bytes))
+    return fail(h, LL_ERR_INVALID_ARG, "bad feature cloud / stride");
+  if (n_corner > 0x0fffffff || n_surf > 0x0fffffff) return fail(h, LL_ERR_INVALID_ARG, "too many feature points");
+  if (!h->fa_last[0] || !h->fa_last[1]) return fail(h, LL_ERR_STATE, "ll_fa_set_last has not been called for both clouds");
+  LL_CUDA(h, cudaSetDevice(h->device));
+  if (!h->d_fa_state) {
+    LL_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&h->d_fa_state), sizeof(FaLoopState)));
+    LL_CUDA(h, cudaMallocHost(reinterpret_cast<void**>(&h->h_fa_state), sizeof(FaLoopState)));
+    h->fa_state_init = false;
+  }
+  // a co-resident grid: one block per SM at most, and no more blocks than feature points are worth
+  int per_sm = 0;
+  LL_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fa_loop_kernel, FAL_THREADS, 0));
+  if (per_sm < 1) return fail(h, LL_ERR_CUDA, "fa_loop_kernel does not fit an SM");
+  int blocks = h->num_sms;
+  if (h->prm.lm_max_blocks > 0) blocks = std::min(blocks, h->prm.lm_max_blocks);
+  const size_t nq_max = std::max(n_corner, n_surf);
+  blocks = (int)std::max<size_t>(1, std::min<size_t>((size_t)blocks, (nq_max + 3) / 4));
+  // device scratch: [corner queries | surf queries | ind 3 x cap | partials 2 x blocks x FAL_PART doubles | trace]
+  const size_t cap = std::max<size_t>(nq_max, 1);
+  const size_t off_qc = 0, off_qs = off_qc + std::max<size_t>(n_corner, 1) * 16, off_ind = off_qs + std::max<size_t>(n_surf, 1) * 16;
+  const size_t off_part = (off_ind + 3 * cap * 4 + 255) & ~size_t(255);
+  const size_t off_trace = off_part + 2 * (size_t)blocks * FAL_PART * sizeof(double);
+  const size_t total = off_trace + 2 * FAL_MAX_ITERS * 4 * sizeof(float);
+  LL_TRY(ensure_bytes(h, &h->d_fa_work, &h->fa_work_bytes, total));
+  uint8_t* const w = static_cast<uint8_t*>(h->d_fa_work);
+  // one pinned block up: [FaLoopState | corner queries | surf queries]
+  const size_t up_bytes = 256 + (n_corner + n_surf) * 16;
+  LL_TRY(pinned_acquire(h, up_bytes));
+  uint8_t* const pin = h->pinned;
+  FaLoopState st0;
+  std::memset(&st0, 0, sizeof(st0));
+  if (h->fa_state_init) st0 = *h->h_fa_state;  // isDegenerate and the two matP carry over from the previous call
+  std::memcpy(st0.tc, transform_cur_inout, 6 * sizeof(float));
+  std::memcpy(pin, &st0, sizeof(st0));
+  pack_points(reinterpret_cast<float4*>(pin + 256), corner_sharp, n_corner, stride_bytes);
+  pack_points(reinterpret_cast<float4*>(pin + 256 + n_corner * 16), surf_flat, n_surf, stride_bytes);
+  LL_CUDA(h, cudaMemcpyAsync(h->d_fa_state, pin, sizeof(FaLoopState), cudaMemcpyHostToDevice, h->stream));
+  if (n_corner) LL_CUDA(h, cudaMemcpyAsync(w + off_qc, pin + 256, n_corner * 16, cudaMemcpyHostToDevice, h->stream));
+  if (n_surf) LL_CUDA(h, cudaMemcpyAsync(w + off_qs, pin + 256 + n_corner * 16, n_surf * 16, cudaMemcpyHostToDevice, h->stream));
+  LL_TRY(pinned_release(h));
+  FaLoopArgs A;
+  A.q[0] = reinterpret_cast<const float4*>(w + off_qc);
+  A.q[1] = reinterpret_cast<const float4*>(w + off_qs);
+  A.last[0] = h->fa_last[0];
+  A.last[1] = h->fa_last[1];
+  A.nq[0] = (int)n_corner;
+  A.nq[1] = (int)n_surf;
+  A.n_last[0] = h->fa_n_last[0];
+  A.n_last[1] = h->fa_n_last[1];
+  A.dist_sqr = nearest_feature_dist_sqr;
+  A.eigen_mode = h->prm.eigen_mode;
+  A.ind = reinterpret_cast<int*>(w + off_ind);
+  A.ind_cap = (int)cap;
+  A.partials = reinterpret_cast<double*>(w + off_part);
+  A.st = h->d_fa_state;
+  A.st_host = h->h_fa_state;
+  A.trace = trace ? reinterpret_cast<float*>(w + off_trace) : nullptr;
+  unsigned* bar = h->d_barriers + (h->scan_seq % kBarrierSlots);
+  unsigned* bar_clear = h->d_barriers + ((h->scan_seq + kBarrierSlots / 2) % kBarrierSlots);
+  h->scan_seq++;
+  if (trace) LL_CUDA(h, cudaMemsetAsync(w + off_trace, 0, 2 * FAL_MAX_ITERS * 4 * sizeof(float), h->stream));
+  void* args[] = {&A, &bar, &bar_clear};
+  LL_CUDA(h, cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(fa_loop_kernel), dim3((unsigned)blocks), dim3(FAL_THREADS),
+                                         args, 0, h->stream));
+  LL_LAUNCHED(h);
+  if (trace) LL_CUDA(h, cudaMemcpyAsync(trace, w + off_trace, 2 * FAL_MAX_ITERS * 4 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  LL_CUDA(h, cudaStreamSynchronize(h->stream));  // the kernel wrote its state straight into the pinned mirror
+  h->fa_state_init = true;
+  const FaLoopState& S = *h->h_fa_state;
+  std::memcpy(transform_cur_inout, S.tc, 6 * sizeof(float));
+  if (res) {
+    std::memcpy(res->transform_cur, S.tc, 6 * sizeof(float));
+    res->iters_surf = S.iters[0];
+    res->iters_corner = S.iters[1];
+    res->is_degenerate = S.is_degenerate;
+    res->skipped = S.skipped;
+    res->n_sel_surf = S.n_sel[0];
+    res->n_sel_corner = S.n_sel[1];
+  }
   return LL_OK;
 }
 

@@ -67,9 +67,23 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
 
 // Barrier across a co-resident grid (cooperative launch): `counter` starts at zero and only grows during the
 // launch; `epoch` counts the barriers this thread has passed (the same in every thread of the grid).
+#ifdef LL_TIMELINE
+// scratch/build_timeline.sh: block 0 stamps %globaltimer when it arrives at and when it leaves every grid barrier of a launch
+__device__ unsigned long long g_tl_bar[512][2];
+__device__ __forceinline__ unsigned long long tl_globaltimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define LL_TL_BAR(e, k) do { if (blockIdx.x == 0 && threadIdx.x == 0 && (e) < 512) g_tl_bar[(e)][(k)] = tl_globaltimer(); } while (0)
+#else
+#define LL_TL_BAR(e, k) do {} while (0)
+#endif
+
 __device__ __forceinline__ void coop_barrier(unsigned* counter, unsigned& epoch) {
   ++epoch;
   __syncthreads();
+  LL_TL_BAR(epoch, 0);
   if (threadIdx.x == 0) {
     // arrive: one release-reduction (cumulative: it orders the block's earlier writes, observed through bar.sync,
     // before the increment — what a __threadfence() + atomicAdd pair does in two round trips)
@@ -77,6 +91,7 @@ __device__ __forceinline__ void coop_barrier(unsigned* counter, unsigned& epoch)
     const unsigned target = epoch * gridDim.x;
     while (ld_acquire_u32(counter) < target) {}  // (relaxed polls + one fence at the end were measured: +6 us per scan)
   }
+  LL_TL_BAR(epoch, 1);
   __syncthreads();
 }
 

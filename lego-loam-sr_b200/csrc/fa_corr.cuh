@@ -116,56 +116,51 @@ __device__ __forceinline__ void fa_window_scan(const FaArgs& A, const float4 sel
   }
 }
 
-__global__ void __launch_bounds__(FA_THREADS) fa_corr_kernel(const __grid_constant__ FaArgs A) {
-  const int lane = threadIdx.x & 31;
-  const int i = blockIdx.x * (FA_THREADS / 32) + (threadIdx.x >> 5);
-  if (i >= A.nq) return;  // warp-uniform
-  const float4 sel = fa_transform_to_start(__ldg(A.q + i), A.tc);
-  int closest = -1, min2 = -1, min3 = -1;
-  if (A.iter % 5 == 0) {
-    // exact 1-NN: distance as nanoflann's L2_Simple_Adaptor (((dx^2) + dy^2) + dz^2), ties to the lowest index
-    uint32_t bd = 0x7f800000u;  // +inf
-    uint32_t bj = 0xffffffffu;
-    auto consider = [&](const float4 m, const int j) {
-      float df = sel.x - m.x;
-      float d = df * df;
-      df = sel.y - m.y;
-      d += df * df;
-      df = sel.z - m.z;
-      d += df * df;
-      const uint32_t db = __float_as_uint(d);
-      if (db < bd) { bd = db; bj = (uint32_t)j; }  // (NaN distances have bit patterns above +inf and never win)
-    };
-    int j = lane;
-    for (; j + 96 < A.n_last; j += 128) {  // four loads in flight, candidates taken in ascending index order
-      const float4 m0 = __ldg(A.last + j), m1 = __ldg(A.last + j + 32), m2 = __ldg(A.last + j + 64), m3 = __ldg(A.last + j + 96);
-      consider(m0, j);
-      consider(m1, j + 32);
-      consider(m2, j + 64);
-      consider(m3, j + 96);
-    }
-    for (; j < A.n_last; j += 32) consider(__ldg(A.last + j), j);
-    const uint32_t md = __reduce_min_sync(0xffffffffu, bd);
-    const uint32_t mj = __reduce_min_sync(0xffffffffu, bd == md ? bj : 0xffffffffu);
-    if (mj != 0xffffffffu && __uint_as_float(md) < A.dist_sqr) {  // (warp-uniform)
-      closest = (int)mj;
-      const int scan = (int)__ldg(A.last + closest).w;
-      float d2min = A.dist_sqr, d3min = A.dist_sqr;
-      fa_window_scan<true>(A, sel, closest, scan, lane, d2min, min2, d3min, min3);
-      fa_window_scan<false>(A, sel, closest, scan, lane, d2min, min2, d3min, min3);
-    }
-    if (lane == 0) {
-      A.ind1[i] = closest;
-      A.ind2[i] = min2;
-      if (A.ind3) A.ind3[i] = min3;
-    }
-  } else if (lane == 0) {
-    closest = A.ind1[i];
-    min2 = A.ind2[i];
-    min3 = A.ind3 ? A.ind3[i] : -1;
+// The search of one feature point by one warp (every fifth iteration): nearestKSearch(pointSel, 1) over the previous
+// sweep's cloud, then the two ring-window walks. All 32 lanes; the results are warp-uniform.
+__device__ __forceinline__ void fa_search_warp(const FaArgs& A, const float4 sel, const int lane, int& closest, int& min2,
+                                               int& min3) {
+  closest = -1;
+  min2 = -1;
+  min3 = -1;
+  // exact 1-NN: distance as nanoflann's L2_Simple_Adaptor (((dx^2) + dy^2) + dz^2), ties to the lowest index
+  uint32_t bd = 0x7f800000u;  // +inf
+  uint32_t bj = 0xffffffffu;
+  auto consider = [&](const float4 m, const int j) {
+    float df = sel.x - m.x;
+    float d = df * df;
+    df = sel.y - m.y;
+    d += df * df;
+    df = sel.z - m.z;
+    d += df * df;
+    const uint32_t db = __float_as_uint(d);
+    if (db < bd) { bd = db; bj = (uint32_t)j; }  // (NaN distances have bit patterns above +inf and never win)
+  };
+  int j = lane;
+  for (; j + 96 < A.n_last; j += 128) {  // four loads in flight, candidates taken in ascending index order
+    const float4 m0 = __ldg(A.last + j), m1 = __ldg(A.last + j + 32), m2 = __ldg(A.last + j + 64), m3 = __ldg(A.last + j + 96);
+    consider(m0, j);
+    consider(m1, j + 32);
+    consider(m2, j + 64);
+    consider(m3, j + 96);
   }
-  if (lane != 0) return;
-  float c[4] = {0.f, 0.f, 0.f, 0.f};
+  for (; j < A.n_last; j += 32) consider(__ldg(A.last + j), j);
+  const uint32_t md = __reduce_min_sync(0xffffffffu, bd);
+  const uint32_t mj = __reduce_min_sync(0xffffffffu, bd == md ? bj : 0xffffffffu);
+  if (mj != 0xffffffffu && __uint_as_float(md) < A.dist_sqr) {  // (warp-uniform)
+    closest = (int)mj;
+    const int scan = (int)__ldg(A.last + closest).w;
+    float d2min = A.dist_sqr, d3min = A.dist_sqr;
+    fa_window_scan<true>(A, sel, closest, scan, lane, d2min, min2, d3min, min3);
+    fa_window_scan<false>(A, sel, closest, scan, lane, d2min, min2, d3min, min3);
+  }
+}
+
+// The (laserCloudOri, coeffSel) pair of one feature point from its tripod (:1644-1693 corner, :1785-1840 surf), one
+// thread. Returns 1 when the pair is pushed (c = the coeffSel record), 0 otherwise (c = 0).
+__device__ __forceinline__ int fa_record(const FaArgs& A, const float4 sel, const int closest, const int min2, const int min3,
+                                         float (&c)[4]) {
+  c[0] = c[1] = c[2] = c[3] = 0.f;
   int kp = 0;
   if (A.which == 0) {
     if (min2 >= 0) {
@@ -204,6 +199,30 @@ __global__ void __launch_bounds__(FA_THREADS) fa_corr_kernel(const __grid_consta
       kp = 1;
     }
   }
+  return kp;
+}
+
+__global__ void __launch_bounds__(FA_THREADS) fa_corr_kernel(const __grid_constant__ FaArgs A) {
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * (FA_THREADS / 32) + (threadIdx.x >> 5);
+  if (i >= A.nq) return;  // warp-uniform
+  const float4 sel = fa_transform_to_start(__ldg(A.q + i), A.tc);
+  int closest = -1, min2 = -1, min3 = -1;
+  if (A.iter % 5 == 0) {
+    fa_search_warp(A, sel, lane, closest, min2, min3);
+    if (lane == 0) {
+      A.ind1[i] = closest;
+      A.ind2[i] = min2;
+      if (A.ind3) A.ind3[i] = min3;
+    }
+  } else if (lane == 0) {
+    closest = A.ind1[i];
+    min2 = A.ind2[i];
+    min3 = A.ind3 ? A.ind3[i] : -1;
+  }
+  if (lane != 0) return;
+  float c[4];
+  const int kp = fa_record(A, sel, closest, min2, min3, c);
 #pragma unroll
   for (int k = 0; k < 4; ++k) A.coeff[4 * i + k] = c[k];
   A.keep[i] = kp;

@@ -39,6 +39,7 @@ __device__ long long g_tl_warp[TL_ITERS][8][16];                // block TL_WATC
 __device__ int g_tl_it;
 __device__ unsigned g_tl_cnt[TL_ITERS][8];  // [0] full searches, [1] heavy (> 128 candidates), [2] set > 32 points, [3] rejected & dense, [4] cached ok, [5] cached attempted
 #define LL_TL_COUNT(k) do { if ((threadIdx.x & 31) == 0 && g_tl_it < TL_ITERS) atomicAdd(&g_tl_cnt[g_tl_it][(k)], 1u); } while (0)
+#define LL_TL_COUNT_THREAD(k) do { if (g_tl_it < TL_ITERS) atomicAdd(&g_tl_cnt[g_tl_it][(k)], 1u); } while (0)
 constexpr int TL_WATCH = 100;
 __device__ __forceinline__ unsigned long long tl_gtime() {
   unsigned long long t;
@@ -62,6 +63,7 @@ __device__ __forceinline__ unsigned long long tl_gtime() {
 #define LL_TL_GT(it, k) do {} while (0)
 #define LL_TL_WARP(ev) do {} while (0)
 #define LL_TL_COUNT(k) do {} while (0)
+#define LL_TL_COUNT_THREAD(k) do {} while (0)
 #endif
 
 constexpr int LM_THREADS = 512;
@@ -552,6 +554,7 @@ __device__ __noinline__ void lm_solve(const double* sums, const LMParams& prm, L
 // ---- warp-level 5-NN --------------------------------------------------------------------------------------
 struct GridGeom {
   int ox, oy, oz, dx, dy, dz;
+  int tag;  // stamp of the valid cell-table entries (map_build.cuh: cell_entry_x)
 };
 
 struct Knn5 {
@@ -719,7 +722,7 @@ __device__ __forceinline__ void warp_knn5_batch(const float4* const (&sorted)[2]
       const int x = (int)floorf(sel[q].x) - g.ox + (lane % 3) - 1, y = (int)floorf(sel[q].y) - g.oy + ((lane / 3) % 3) - 1,
                 z = (int)floorf(sel[q].z) - g.oz + (lane / 9) - 1;
       if (x >= 0 && x < g.dx && y >= 0 && y < g.dy && z >= 0 && z < g.dz)
-        ce[q] = map_ld<kFresh>(&cells[mq[q] ? 1 : 0][(z * g.dy + y) * g.dx + x]);
+        ce[q] = cell_decode(map_ld<kFresh>(&cells[mq[q] ? 1 : 0][(z * g.dy + y) * g.dx + x]), g.tag);
     }
   }
   // ---- stage 2: ranges -> candidate addresses -> candidate loads (all queries' loads in flight together)
@@ -868,16 +871,23 @@ constexpr int LM_QCAP = 144;               // queries per block with a cache slo
 constexpr int LM_CACHE_CAND = 32;
 constexpr float LM_CACHE_MARGIN = 0.25f;   // metres
 constexpr float LM_CACHE_SLACK = 1e-3f;    // metres
+// The per-thread test below compares quantities that are all computed from exact float coordinates with a relative error of
+// a few ulp (distances below 1.5 m: < 1e-6 m absolute, whatever the magnitude of the coordinates), so 2e-5 m is a wide margin.
+constexpr float LM_T1_SLACK = 2e-5f;
 
 struct KnnCache {
   float4* cand;    // [LM_QCAP][32]  x, y, z, map-index bits
-  float4* center;  // [LM_QCAP]      c and R
+  float4* center;  // [LM_QCAP]      c and R (R < 0: cell-complete set; 0 < R <= 1: radius set; R > 1: radius set of a REJECTED query)
   float4* qpt;     // [LM_QCAP]      the query itself (sensor frame), so that the steady state never leaves the SM
+  float4* t1;      // [LM_QCAP]      c' and G: where the five members were last confirmed, and a lower bound of the distance
+                   //                from c' to every map point that is NOT one of them (G <= 0: unknown)
   int* cnt;        // [LM_QCAP]      0 = no set yet, -1 = not cacheable, > 0 = points in the set
-  uint32_t* prev;  // [LM_QCAP]      lanes (= positions in cand) of the five neighbours found last time, 0 = unknown
+  uint32_t* prev;  // [LM_QCAP]      positions in cand of the five neighbours found last time (bit mask), 0 = unknown
 };
-constexpr int LM_CACHE_BYTES = LM_QCAP * (LM_CACHE_CAND * 16 + 16 + 16 + 4 + 4);
-constexpr int LM_PERSISTENT_SMEM = LM_THREADS * LM_SLOT * (int)sizeof(float) + LM_CACHE_BYTES;  // dynamic shared memory of lm_persistent_kernel
+constexpr int LM_CACHE_BYTES = LM_QCAP * (LM_CACHE_CAND * 16 + 16 + 16 + 16 + 4 + 4);
+constexpr int LM_LOOP_SMEM = LM_THREADS * LM_SLOT * (int)sizeof(float) + LM_CACHE_BYTES;
+// dynamic shared memory of lm_persistent_kernel (the incremental map assembly borrows it for the added keyframes' sort)
+constexpr int LM_PERSISTENT_SMEM = LM_LOOP_SMEM > INC_SMEM_BYTES ? LM_LOOP_SMEM : INC_SMEM_BYTES;
 
 // After a full search of a query around `sel` (5th distance d5bits, LM_EMPTY_D2 when it was not accepted; candidates
 // described by my_start / my_count as in knn5_chunks, at most 128 of them): collect the query's cached set. Two kinds:
@@ -888,7 +898,7 @@ constexpr int LM_PERSISTENT_SMEM = LM_THREADS * LM_SLOT * (int)sizeof(float) + L
 template <bool kFresh>
 __device__ __noinline__ void knn_cache_fill(const float4* sorted, int my_start, int my_count, float sx, float sy, float sz,
                                             uint32_t d5bits, float4 qsensor, int lane, float4* cand, float4* center,
-                                            float4* qpt, int* cnt_out, uint32_t* prev_out) {
+                                            float4* qpt, float4* t1, int* cnt_out, uint32_t* prev_out) {
   constexpr int kRowLane[9] = {12, 3, 9, 15, 21, 0, 6, 18, 24};
   int pr[9], bs[9];
   int total = 0;
@@ -903,18 +913,20 @@ __device__ __noinline__ void knn_cache_fill(const float4* sorted, int my_start, 
   if (lane == 0) {
     *qpt = qsensor;
     *prev_out = 0u;
+    *t1 = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   const bool whole = total <= LM_CACHE_CAND;
-  if (!whole && d5bits == LM_EMPTY_D2) {  // rejected in a dense neighbourhood: nothing provable to keep
-    if (lane == 0) *cnt_out = -1;
-    return;
-  }
+  // A query REJECTED in a dense neighbourhood (fewer than five points within 1 m, many beyond) keeps the points within
+  // 1 m + margin of it: while it stays in its one-metre cell (so that the 27 cells still hold every point within 1 m of it)
+  // and moves less than the margin, every point within 1 m of it is in that set, and the acceptance test and — should it
+  // pass — the five neighbours are decided exactly on the set.
+  const bool rejected = !whole && d5bits == LM_EMPTY_D2;
   const uint32_t lt_mask = (1u << lane) - 1u;
   // the radius set must fit 32 points: a dense neighbourhood gets a second try with a thinner shell around d5
 #pragma unroll 1
   for (int attempt = 0; attempt < 2; ++attempt) {
     const float margin = attempt == 0 ? LM_CACHE_MARGIN : 0.3f * LM_CACHE_MARGIN;
-    const float R = whole ? -1.f : fminf(1.0f, sqrtf(__uint_as_float(d5bits)) + margin);
+    const float R = whole ? -1.f : (rejected ? 1.0f + margin : fminf(1.0f, sqrtf(__uint_as_float(d5bits)) + margin));
     const float R2 = R * R;
     int base = 0;
 #pragma unroll 1
@@ -938,139 +950,150 @@ __device__ __noinline__ void knn_cache_fill(const float4* sorted, int my_start, 
       if (in && pos < LM_CACHE_CAND) cand[pos] = m;
       base += __popc(bal);
     }
-    const bool fits = whole || (base <= LM_CACHE_CAND && base >= 5);
+    const bool fits = whole || (base <= LM_CACHE_CAND && (rejected || base >= 5));
     if (fits || attempt == 1) {
       if (lane == 0) {
         *center = make_float4(sx, sy, sz, R);
         // (an EMPTY cell-complete set is stored as count 33: cnt must be > 0 to be used, and no lane is below 33 <= 32)
-        *cnt_out = fits ? (whole ? (base > 0 ? base : LM_CACHE_CAND + 1) : base) : -1;
+        *cnt_out = fits ? (base > 0 ? base : LM_CACHE_CAND + 1) : -1;
       }
       return;
     }
   }
 }
 
-// The cached search of LM_CACHE_BATCH queries of one warp, interleaved. slot_c[b] = cache slot (or -1: skip). On return
-// ok[b] (warp-uniform) says whether the outcome is proven exact, acc[b] whether five neighbours within range exist; lane
-// r < 5 then holds neighbour r's coordinates in (nx, ny, nz)[b].
-constexpr int LM_CACHE_BATCH = 4;
-__device__ __forceinline__ void knn5_cached_batch(const KnnCache& C, const int (&slot_c)[LM_CACHE_BATCH],
-                                                  const float4 (&sel)[LM_CACHE_BATCH], float max_sq_dist, int lane,
-                                                  bool (&ok)[LM_CACHE_BATCH], bool (&acc)[LM_CACHE_BATCH],
-                                                  int (&rank)[LM_CACHE_BATCH], float (&nx)[LM_CACHE_BATCH],
-                                                  float (&ny)[LM_CACHE_BATCH], float (&nz)[LM_CACHE_BATCH]) {
-  // On return, for a proven and accepted query b, lane p < 5 holds ONE of the five neighbours in (nx, ny, nz)[b] and its
-  // position in the ascending (d2, index) order in rank[b] (the lanes' ranks are a permutation of 0..4).
-  constexpr int NB = LM_CACHE_BATCH;
+// The cached search of ONE query by ONE thread — the thread that fits the query in phase 2, so a proven answer goes
+// straight into that thread's own staging slot and the steady state of the LM loop has no warp-level search at all.
+//   step 1  the five neighbours of last time + a guard distance: t1 = (c', G) says that at c' every map point other than
+//           those five was at least G away. At q (delta = |q - c'|) they are at least G - delta away, so if the largest of
+//           the five distances from q, D5, satisfies  sqrt(D5) + delta + slack <= G  the five are still the answer (their
+//           ORDER may have changed: they are re-sorted by (d2, index)). Five loads, a sorting network, one test.
+//   step 2  otherwise the whole cached set (<= 32 points, top six by insertion): the five nearest within the set, the
+//           set-level proof of knn_cache_fill's comment (radius sets: sqrt(D5) + |q - c| + slack <= R; cell-complete sets:
+//           same cell; rejected-query sets: same cell and |q - c| + slack <= R - 1), and a fresh guard for step 1:
+//           G = min(sixth distance within the set, what the set's kind guarantees about the points outside it, 1 m).
+// Returns true when the outcome is proven exact (slot filled: slot[3] = 1 with the neighbours in ascending (d2, index)
+// order, or slot[3] = 0 for a query proven to have fewer than five points within range); false: search in full.
+// Distances are evaluated exactly as in the full search, so a proven answer is bit-identical to it.
+__device__ __noinline__ bool knn5_thread(const KnnCache C, int i, const Trig* trig_p, float max_sq_dist, float* slot) {
+  const Trig trig = *trig_p;
   const uint32_t max_bits = __float_as_uint(max_sq_dist);
-  uint32_t cd[NB], ci[NB], pm[NB], d5[NB];
-  float4 ctr[NB];
-  int src[NB];  // lane p < 5: the lane (= position in the cached set) holding "its" neighbour
+  const float4 sel = rigid_transform(trig, C.qpt[i]);
+  const float4* cand = C.cand + i * LM_CACHE_CAND;
+  auto dist_bits = [&](const float4 m) {
+    float df = sel.x - m.x;  // evalMetric order (nanoflann.hpp:431-439), as in the full search
+    float d = df * df;
+    df = sel.y - m.y;
+    d += df * df;
+    df = sel.z - m.z;
+    d += df * df;
+    return __float_as_uint(d);
+  };
+  auto approx_sqrt = [](float v) { return v > 0.f ? v * rsqrtf(v) : 0.f; };  // 2 ulp: the slack dwarfs it
+  auto dist_to = [&](const float4 c) {
+    float df = sel.x - c.x;
+    float d = df * df;
+    df = sel.y - c.y;
+    d += df * df;
+    df = sel.z - c.z;
+    d += df * df;
+    return approx_sqrt(d);
+  };
+  auto emit = [&](const float4 (&nb)[5]) {
+    slot[0] = sel.x; slot[1] = sel.y; slot[2] = sel.z; slot[3] = 1.f;
 #pragma unroll
-  for (int b = 0; b < NB; ++b) {
-    cd[b] = LM_EMPTY_D2;
-    ci[b] = 0xffffffffu;
-    pm[b] = 0u;
-    d5[b] = LM_EMPTY_D2;
-    ctr[b] = make_float4(0.f, 0.f, 0.f, 0.f);
-    src[b] = 0;
-    rank[b] = 0;
-    ok[b] = false;
-    acc[b] = false;
-    if (slot_c[b] >= 0) {  // warp-uniform
-      const int cnt = C.cnt[slot_c[b]];
-      ctr[b] = C.center[slot_c[b]];
-      pm[b] = C.prev[slot_c[b]];
-      if (lane < cnt && cnt <= LM_CACHE_CAND) {
-        const float4 m = C.cand[slot_c[b] * LM_CACHE_CAND + lane];
-        float df = sel[b].x - m.x;  // evalMetric order, as in the full search
-        float d = df * df;
-        df = sel[b].y - m.y;
-        d += df * df;
-        df = sel[b].z - m.z;
-        d += df * df;
-        const uint32_t db = __float_as_uint(d);
-        if (db < max_bits) { cd[b] = db; ci[b] = __float_as_uint(m.w); }
-      }
+    for (int k = 0; k < 5; ++k) { slot[4 + 3 * k] = nb[k].x; slot[5 + 3 * k] = nb[k].y; slot[6 + 3 * k] = nb[k].z; }
+  };
+  // ---- step 1
+  const float4 t1 = C.t1[i];
+  if (t1.w > 0.f) {
+    uint32_t mask = C.prev[i];
+    float4 nb[5];
+    uint32_t d[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      const int j = __ffs(mask) - 1;
+      mask &= mask - 1u;
+      nb[k] = cand[j & (LM_CACHE_CAND - 1)];
+      d[k] = dist_bits(nb[k]);
+    }
+#define LL_T1_CE(a, b)                                                                                              \
+    {                                                                                                                 \
+      const bool sw_ = pair_less(d[b], __float_as_uint(nb[b].w), d[a], __float_as_uint(nb[a].w));                     \
+      const uint32_t td_ = sw_ ? d[b] : d[a];                                                                         \
+      const float4 tn_ = sw_ ? nb[b] : nb[a];                                                                         \
+      d[b] = sw_ ? d[a] : d[b]; nb[b] = sw_ ? nb[a] : nb[b];                                                          \
+      d[a] = td_; nb[a] = tn_;                                                                                        \
+    }
+    // 9-comparator network for five keys
+    LL_T1_CE(0, 1) LL_T1_CE(3, 4) LL_T1_CE(2, 4) LL_T1_CE(2, 3) LL_T1_CE(0, 3) LL_T1_CE(0, 2) LL_T1_CE(1, 4) LL_T1_CE(1, 3) LL_T1_CE(1, 2)
+#undef LL_T1_CE
+    if (d[4] < max_bits && approx_sqrt(__uint_as_float(d[4])) + dist_to(t1) + LM_T1_SLACK <= t1.w) {
+      emit(nb);
+      return true;
     }
   }
-  LL_TL_WARP(2);
-  // ---- verify: are last time's five still the five smallest? (one redux + two ballots; the usual case)
-  bool verified[NB];
-  bool all_verified = true;
+  // ---- step 2: the whole set, top six by (d2, index). Columns are visited rotated by the thread index: the threads of a
+  //      warp read different rows of `cand` (stride 512 bytes), and the rotation spreads them over the banks.
+  const int cnt_raw = C.cnt[i];
+  const int cnt = cnt_raw <= LM_CACHE_CAND ? cnt_raw : 0;  // (an EMPTY set is stored as count 33)
+  uint32_t td[6], ti[6];
+  int tc[6];
 #pragma unroll
-  for (int b = 0; b < NB; ++b) {
-    verified[b] = false;
-    if (slot_c[b] < 0) continue;
-    if (pm[b] != 0u) {
-      const bool mem = (pm[b] >> lane) & 1u;
-      const uint32_t T = __reduce_max_sync(0xffffffffu, mem ? cd[b] : 0u);  // the largest d2 among last time's five
-      const unsigned lt = __ballot_sync(0xffffffffu, cd[b] < T), eq = __ballot_sync(0xffffffffu, cd[b] == T);
-      verified[b] = T != LM_EMPTY_D2 && __popc(lt) == 4 && __popc(eq) == 1 && (lt | eq) == pm[b];
-      if (verified[b]) d5[b] = T;
-    }
-    all_verified = all_verified && verified[b];
-  }
-  if (!all_verified) {  // warp-uniform: five selection rounds for the queries whose set changed (or that have none yet)
-#pragma unroll 1
-    for (int r = 0; r < 5; ++r) {  // (not unrolled: the LM loop is instruction-fetch bound, every copy of this body costs)
+  for (int k = 0; k < 6; ++k) { td[k] = LM_EMPTY_D2; ti[k] = 0xffffffffu; tc[k] = 0; }
+#pragma unroll 4
+  for (int j = 0; j < LM_CACHE_CAND; ++j) {
+    const int col = (j + (int)threadIdx.x) & (LM_CACHE_CAND - 1);
+    if (col >= cnt) continue;
+    const float4 m = cand[col];
+    const uint32_t db = dist_bits(m), ib = __float_as_uint(m.w);
+    if (db < max_bits && pair_less(db, ib, td[5], ti[5])) {
+      td[5] = db; ti[5] = ib; tc[5] = col;
 #pragma unroll
-      for (int b = 0; b < NB; ++b) {
-        if (slot_c[b] < 0 || verified[b]) continue;  // warp-uniform
-        const uint32_t m = __reduce_min_sync(0xffffffffu, cd[b]);
-        unsigned bal = __ballot_sync(0xffffffffu, cd[b] == m);
-        if (m != LM_EMPTY_D2 && (bal & (bal - 1u)) != 0u) {  // exact d2 tie between lanes: lowest map index (rare)
-          const uint32_t om = __reduce_min_sync(0xffffffffu, cd[b] == m ? ci[b] : 0xffffffffu);
-          bal = __ballot_sync(0xffffffffu, cd[b] == m && ci[b] == om);
+      for (int k = 5; k > 0; --k) {
+        if (pair_less(td[k], ti[k], td[k - 1], ti[k - 1])) {
+          const uint32_t a = td[k]; td[k] = td[k - 1]; td[k - 1] = a;
+          const uint32_t b = ti[k]; ti[k] = ti[k - 1]; ti[k - 1] = b;
+          const int c = tc[k]; tc[k] = tc[k - 1]; tc[k - 1] = c;
         }
-        const int wl = __ffs(bal) - 1;
-        if (r == 0) pm[b] = 0u;
-        if (m != LM_EMPTY_D2) pm[b] |= 1u << wl;
-        if (lane == r) { src[b] = wl; rank[b] = r; }
-        if (lane == wl && m != LM_EMPTY_D2) cd[b] = LM_EMPTY_D2;
-        d5[b] = m;
       }
     }
   }
-  LL_TL_WARP(3);
-#pragma unroll
-  for (int b = 0; b < NB; ++b) {
-    nx[b] = ny[b] = nz[b] = 0.f;
-    if (slot_c[b] < 0) continue;  // warp-uniform
-    acc[b] = d5[b] != LM_EMPTY_D2;
-    if (ctr[b].w < 0.f) {         // cell-complete set: exact while the query stays in the cell it was collected for
-      ok[b] = floorf(sel[b].x) == floorf(ctr[b].x) && floorf(sel[b].y) == floorf(ctr[b].y) && floorf(sel[b].z) == floorf(ctr[b].z);
-    } else if (acc[b]) {
-      float df = sel[b].x - ctr[b].x;
-      float dl = df * df;
-      df = sel[b].y - ctr[b].y;
-      dl += df * df;
-      df = sel[b].z - ctr[b].z;
-      dl += df * df;
-      // sqrt by rsqrt (2 ulp): the millimetre of slack in the test dwarfs it
-      const float D = __uint_as_float(d5[b]);
-      const float sD = D > 0.f ? D * rsqrtf(D) : 0.f, sl = dl > 0.f ? dl * rsqrtf(dl) : 0.f;
-      ok[b] = sD + sl + LM_CACHE_SLACK <= ctr[b].w;
-    }
-    if (!(ok[b] && acc[b])) continue;  // warp-uniform
-    if (verified[b]) {
-      // the five are where they were; their order may have changed: rank each among the five by (d2, index)
-      src[b] = lane < 5 ? (int)__fns(pm[b], 0, lane + 1) : 0;
-      const uint32_t gd = __shfl_sync(0xffffffffu, cd[b], src[b]), gi = __shfl_sync(0xffffffffu, ci[b], src[b]);
-      int rk = 0;
-#pragma unroll
-      for (int k = 0; k < 5; ++k) {
-        const uint32_t od = __shfl_sync(0xffffffffu, gd, k), oi = __shfl_sync(0xffffffffu, gi, k);
-        rk += pair_less(od, oi, gd, gi) ? 1 : 0;
-      }
-      rank[b] = rk;
-    }
-    if (lane < 5) {
-      const float4 m = C.cand[slot_c[b] * LM_CACHE_CAND + src[b]];
-      nx[b] = m.x; ny[b] = m.y; nz[b] = m.z;
-    }
-    if (lane == 0) C.prev[slot_c[b]] = pm[b];
+  const bool acc = td[4] != LM_EMPTY_D2;
+  const float4 ctr = C.center[i];
+  const bool same_cell = floorf(sel.x) == floorf(ctr.x) && floorf(sel.y) == floorf(ctr.y) && floorf(sel.z) == floorf(ctr.z);
+  const float sl = dist_to(ctr);
+  const float sD = acc ? approx_sqrt(__uint_as_float(td[4])) : 0.f;
+  bool ok;
+  float outside;  // lower bound of the distance from sel to every map point that is not in the set
+  // distance from sel to the nearest face of its one-metre cell: a point outside the 27 cells is at least 1 m + that away
+  const float fx = sel.x - floorf(sel.x), fy = sel.y - floorf(sel.y), fz = sel.z - floorf(sel.z);
+  const float face = fminf(fminf(fminf(fx, 1.f - fx), fminf(fy, 1.f - fy)), fminf(fz, 1.f - fz));
+  if (ctr.w < 0.f) {          // cell-complete
+    ok = same_cell;
+    outside = 1.f + face;
+  } else if (ctr.w <= 1.f) {  // radius set of an accepted query
+    ok = acc && sD + sl + LM_CACHE_SLACK <= ctr.w;
+    outside = ctr.w - sl;
+  } else {                    // radius set of a rejected query
+    ok = same_cell && sl + LM_CACHE_SLACK <= ctr.w - 1.f;
+    outside = fminf(ctr.w - sl, 1.f + face);
   }
+  if (!ok) return false;
+  if (!acc) {
+    slot[0] = sel.x; slot[1] = sel.y; slot[2] = sel.z; slot[3] = 0.f;
+    C.t1[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    return true;
+  }
+  float4 nb[5];
+  uint32_t mask = 0u;
+#pragma unroll
+  for (int k = 0; k < 5; ++k) { nb[k] = cand[tc[k]]; mask |= 1u << tc[k]; }
+  emit(nb);
+  const float d6 = td[5] != LM_EMPTY_D2 ? approx_sqrt(__uint_as_float(td[5])) : 1.f;
+  C.prev[i] = mask;
+  C.t1[i] = make_float4(sel.x, sel.y, sel.z, fminf(fminf(d6, outside), 1.f));
+  return true;
 }
 
 // The 29 running sums of one LM iteration in a fixed order: 21 upper-triangular AtA entries (row-major),
@@ -1519,7 +1542,7 @@ __device__ __noinline__ void lm_full_search_warp(const LMArgs* Ap, const Trig* t
         if (first_chunk && i < LM_QCAP) {  // (re)build this query's cached set around where it is now
           const uint32_t d5 = __shfl_sync(0xffffffffu, acc[b] ? od[b] : LM_EMPTY_D2, 4);
           knn_cache_fill<kFresh>(A.sorted[mq[b]], q_start[b], q_count[b], sel[b].x, sel[b].y, sel[b].z, d5, qs[b], lane,
-                                 &C.cand[i * LM_CACHE_CAND], &C.center[i], &C.qpt[i], &C.cnt[i], &C.prev[i]);
+                                 &C.cand[i * LM_CACHE_CAND], &C.center[i], &C.qpt[i], &C.t1[i], &C.cnt[i], &C.prev[i]);
         }
       }
     }
@@ -1533,9 +1556,9 @@ template <int kEigenMode, bool kFresh>
 __device__ __forceinline__ float lm_block_pass_cached(const LMArgs& A, const Trig& trig_s, const RotTrig& rt,
                                                       const GridGeom* geom_s, float* s_slot, const KnnCache& C,
                                                       const QShare& sh, int tl_it) {
-  // trig_s / geom_s live in shared memory (the out-of-line full search takes them by address)
-  const Trig trig = trig_s;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // trig_s / geom_s live in shared memory (the out-of-line searches take them by address)
+  __shared__ unsigned s_need[LM_WARPS];
+  const int tid = threadIdx.x, warp = tid >> 5;
   (void)tl_it;
   float run_sum = 0.f;  // thread 8 k, k < 29: this block's running total of sum k
   const int n_local = sh.size();
@@ -1545,56 +1568,23 @@ __device__ __forceinline__ float lm_block_pass_cached(const LMArgs& A, const Tri
     const int nc_pad = (nc + 31) & ~31;
     const int nslots = nc_pad + (cn - nc);
     const bool first_chunk = c0 == 0;  // the cache slots belong to the first LM_QCAP queries of the block
-    const int nj = cn > warp ? (cn - warp + LM_WARPS - 1) / LM_WARPS : 0;  // this warp's queries (<= 30)
-    unsigned need = nj >= 32 ? 0xffffffffu : ((1u << nj) - 1u);            // bit j: query warp + 16 j still unsearched
+    // ---- (A) cached search, one THREAD per query: the thread that will fit it (knn5_thread). What it cannot prove is
+    //      flagged for its warp: bit j of s_need[w] = query w + 16 j of this chunk.
+    const int my_i = tid < nc ? tid : (tid >= nc_pad && tid < nslots ? nc + (tid - nc_pad) : -1);
+    if (tid < LM_WARPS) s_need[tid] = 0u;
+    __syncthreads();
     LL_TL_WARP(0);
-    // ---- (A) cached search
-    if (first_chunk) {
-      for (int j0 = 0; j0 < nj && warp + LM_WARPS * j0 < LM_QCAP; j0 += LM_CACHE_BATCH) {
-        int sc[LM_CACHE_BATCH];
-        float4 sel[LM_CACHE_BATCH];
-        bool any = false;
-#pragma unroll
-        for (int b = 0; b < LM_CACHE_BATCH; ++b) {
-          const int i = warp + LM_WARPS * (j0 + b);
-          sc[b] = -1;
-          sel[b] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (j0 + b < nj && i < LM_QCAP && C.cnt[i] > 0) {  // warp-uniform
-            sc[b] = i;
-            sel[b] = rigid_transform(trig, C.qpt[i]);
-            any = true;
-          }
-        }
-        if (!any) continue;
-        bool ok[LM_CACHE_BATCH], acc[LM_CACHE_BATCH];
-        int rank[LM_CACHE_BATCH];
-        float nx[LM_CACHE_BATCH], ny[LM_CACHE_BATCH], nz[LM_CACHE_BATCH];
-        LL_TL_WARP(6);
-        knn5_cached_batch(C, sc, sel, A.prm.fit.max_sq_dist, lane, ok, acc, rank, nx, ny, nz);
-        LL_TL_WARP(4);
-#pragma unroll
-        for (int b = 0; b < LM_CACHE_BATCH; ++b) {
-          if (sc[b] >= 0) LL_TL_COUNT(5);
-          if (sc[b] < 0 || !ok[b]) continue;  // warp-uniform
-          LL_TL_COUNT(4);
-          const int i = sc[b];
-          float* slot = &s_slot[(i < nc ? i : nc_pad + (i - nc)) * LM_SLOT];
-          if (lane < 5) {
-            if (acc[b]) {
-              slot[4 + 3 * rank[b]] = nx[b];
-              slot[5 + 3 * rank[b]] = ny[b];
-              slot[6 + 3 * rank[b]] = nz[b];
-            }
-          } else if (lane == 5) {
-            slot[0] = sel[b].x;
-            slot[1] = sel[b].y;
-            slot[2] = sel[b].z;
-            slot[3] = acc[b] ? 1.f : 0.f;
-          }
-          need &= ~(1u << (j0 + b));
-        }
+    if (my_i >= 0) {
+      bool proven = false;
+      if (first_chunk && my_i < LM_QCAP && C.cnt[my_i] > 0) {
+        proven = knn5_thread(C, my_i, &trig_s, A.prm.fit.max_sq_dist, &s_slot[tid * LM_SLOT]);
+        LL_TL_COUNT_THREAD(5);
+        if (proven) LL_TL_COUNT_THREAD(4);
       }
+      if (!proven) atomicOr(&s_need[my_i % LM_WARPS], 1u << (my_i / LM_WARPS));
     }
+    __syncthreads();
+    const unsigned need = s_need[warp];
     LL_TL_WARP(1);
     // ---- (B) full search of what is left (everything in iteration 0), out of line: the steady-state loop is
     //      instruction-fetch bound, and this is by far its largest piece of code
@@ -1606,7 +1596,6 @@ __device__ __forceinline__ float lm_block_pass_cached(const LMArgs& A, const Tri
     // ---- phase 2: fit + Jacobian row, one thread per query
     float sv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     float one = 0.f;
-    const int my_i = tid < nc ? tid : (tid >= nc_pad && tid < nslots ? nc + (tid - nc_pad) : -1);
     if (my_i >= 0) {
       const int qi = sh.qi(c0 + my_i, A.nq[0]);
       const int m = qi < A.nq[0] ? 0 : 1;
@@ -1644,6 +1633,7 @@ __device__ __forceinline__ void lm_load_geom(const LMArgs& A, GridGeom (&geom)[2
     const MapState* ms = A.mst[m];
     geom[m].ox = __ldcg(&ms->gox); geom[m].oy = __ldcg(&ms->goy); geom[m].oz = __ldcg(&ms->goz);
     geom[m].dx = __ldcg(&ms->gdx); geom[m].dy = __ldcg(&ms->gdy); geom[m].dz = __ldcg(&ms->gdz);
+    geom[m].tag = __ldcg(&ms->cell_tag);
   }
 }
 
@@ -1735,7 +1725,8 @@ __global__ void __launch_bounds__(LM_THREADS, 1) lm_persistent_kernel(const __gr
   C.cand = reinterpret_cast<float4*>(s_dyn + LM_THREADS * LM_SLOT * sizeof(float));
   C.center = C.cand + LM_QCAP * LM_CACHE_CAND;
   C.qpt = C.center + LM_QCAP;
-  C.cnt = reinterpret_cast<int*>(C.qpt + LM_QCAP);
+  C.t1 = C.qpt + LM_QCAP;
+  C.cnt = reinterpret_cast<int*>(C.t1 + LM_QCAP);
   C.prev = reinterpret_cast<uint32_t*>(C.cnt + LM_QCAP);
   __shared__ __align__(16) LMState s_st;
   const int tid = threadIdx.x;
@@ -1746,6 +1737,7 @@ __global__ void __launch_bounds__(LM_THREADS, 1) lm_persistent_kernel(const __gr
     if (tid < (int)(sizeof(LMState) / 4)) dst[tid] = __ldcg(src + tid);
   }
   unsigned epoch = 0;  // grid barriers passed so far
+  LL_TL_BAR(0, 1);     // (timeline builds: kernel entry)
   static_assert(GI_SMEM_WORDS <= LM_THREADS * LM_SLOT && GI_SMEM_WORDS_REDUCE <= LM_THREADS * LM_SLOT && GI_THREADS == LM_THREADS,
                 "the inline map build borrows the staging slots");
   static_assert((LM_THREADS * LM_SLOT * sizeof(float)) % 16 == 0, "the cache follows the staging slots, 16-byte aligned");
@@ -1753,8 +1745,8 @@ __global__ void __launch_bounds__(LM_THREADS, 1) lm_persistent_kernel(const __gr
   // a1-a3: the local map itself, when ll_build_local_map only prepared it (map_inline.cuh)
   bool cells_cleared = false;
   if (build_map) {
-    if (blockIdx.x == 0 && tid < 128)  // MapState of both maps (bounding box, counts): zero before the build
-      reinterpret_cast<uint32_t*>(GB.m[tid >> 6].st)[tid & 63] = 0u;
+    if (blockIdx.x == 0)  // MapState of both maps (bounding box, counts): zero before the build
+      inc_zero_map_states(GB, build_map == 2 && IJ.keep_fail != 0);
     coop_barrier(barrier, epoch);
     if (build_map == 2)  // a1-a3 incrementally: merge the added keyframes into the device-resident window (map_incremental.cuh)
       map_incremental_inline(IJ, GB, barrier, epoch, reinterpret_cast<uint32_t*>(s_dyn));
@@ -1804,6 +1796,10 @@ __global__ void __launch_bounds__(LM_THREADS, 1) lm_persistent_kernel(const __gr
 #ifdef LL_TIMELINE
   __syncthreads();
   if (blockIdx.x == 0 && tid == 0) {
+    printf("grid barriers of this launch (build_map %d, build_grid %d): microseconds from kernel entry to block 0's arrival / release\n", build_map, build_grid);
+    for (unsigned e = 1; e <= epoch && e < 512; ++e)
+      printf("   barrier %3u  arrive %8.2f  release %8.2f  (stage %6.2f)\n", e, (g_tl_bar[e][0] - g_tl_bar[0][1]) * 1e-3,
+             (g_tl_bar[e][1] - g_tl_bar[0][1]) * 1e-3, (g_tl_bar[e][1] - g_tl_bar[e - 1][1]) * 1e-3);
     const int nb = min((int)gridDim.x, TL_BLOCKS);
     const double us = 1e-3 / 1.965;  // cycles -> us at the 1965 MHz the box runs at under load
     const char* names[9] = {"phase1 5-NN (to block barrier)", "block barrier after phase 1", "phase2 fit + Jacobian row", "shuffle reduce 29 sums",
@@ -1837,7 +1833,7 @@ __global__ void __launch_bounds__(LM_THREADS, 1) lm_persistent_kernel(const __gr
              g_tl_cnt[itx][0], g_tl_cnt[itx][1], g_tl_cnt[itx][3], g_tl_cnt[itx][5], g_tl_cnt[itx][4]);
       for (int k = 0; k < 8; ++k) g_tl_cnt[itx][k] = 0;
       if (itx == 0 || itx == 1 || itx == 5) {
-        printf("   block %d phase 1 per warp (us from its start): queries loaded + transformed / distances / 5 rounds / proof + neighbours / cached part done / full part done\n", TL_WATCH);
+        printf("   block %d phase 1 per warp (us from its start): - / - / - / - / thread-level cached search done / full search done\n", TL_WATCH);
         for (int w = 0; w < 16; ++w) {
           const long long t0 = g_tl_warp[itx][0][w];
           printf("     warp %2d: %6.2f %6.2f %6.2f %6.2f %6.2f %6.2f\n", w, (g_tl_warp[itx][6][w] - t0) * us, (g_tl_warp[itx][2][w] - t0) * us,

@@ -41,19 +41,39 @@ struct MapState {
   int ncells;
   uint32_t head_ticket;  // dynamic tile ticket of voxel_reduce_kernel
   int inc_fail;          // the incremental assembly (map_incremental.cuh) met a case it cannot represent: rebuild in full
-  uint32_t pad[1];
+  int cell_tag;          // stamp of the cell-table entries this build wrote (cell_entry_* below)
 };
+
+// ---- the cell table is never cleared between builds --------------------------------------------------------------------
+// A dense table over the bounding box of a 200 x 300 m map has millions of cells of which a few ten thousand are occupied;
+// clearing it cost more than everything else in the map assembly (89 us of 240 per scan at the benchmark's sizes,
+// profiles/r02_*). Every entry therefore carries the stamp of the build that wrote it in its top byte:
+//   x = ((255 - tag) << 24) | start      y = (tag << 24) | end          (positions < 2^24)
+// An entry is valid when y's stamp is the current build's. Stamps grow from build to build, so with UNSIGNED atomics a
+// stale y is always below and a stale x always above anything the current build writes: atomicMax / atomicMin (inline
+// build) and plain stores (stand-alone build) both work on uncleared memory. The host resets the table to (~0, 0) when it
+// is allocated and every 255 builds, when the stamp wraps (abi.cu: next_cell_tag).
+constexpr uint32_t CELL_POS_MASK = 0x00ffffffu;
+constexpr int CELL_MAX_POINTS = 1 << 24;
+__device__ __forceinline__ uint32_t cell_entry_x(int tag, uint32_t start) { return ((uint32_t)(255 - tag) << 24) | start; }
+__device__ __forceinline__ uint32_t cell_entry_y(int tag, uint32_t end) { return ((uint32_t)tag << 24) | end; }
+// [start, end) of a loaded entry; (0, 0) when the entry is not of this build
+__device__ __forceinline__ int2 cell_decode(int2 e, int tag) {
+  const bool ok = ((uint32_t)e.y >> 24) == (uint32_t)tag;
+  return ok ? make_int2((int)((uint32_t)e.x & CELL_POS_MASK), (int)((uint32_t)e.y & CELL_POS_MASK)) : make_int2(0, 0);
+}
 
 struct MapBuffers {
   float4* raw;            // concatenated surrounding cloud in the map frame (laserCloud*FromMap)
   float4* ds;             // laserCloud*FromMapDS (== raw when map_downsample = 0)
   float4* sorted;         // ds reordered by cell key; w = index into ds (bit pattern)
-  int2* cells;            // per cell [start, end) into sorted; (0,0) = empty
+  int2* cells;            // per cell [start, end) into sorted, stamped (cell_entry_x / _y)
   MapState* st;
   uint32_t* head_status;  // look-back words of voxel_reduce_kernel
   int* member;            // optional: output slot per raw point (stage-level parity tests)
   int n_raw;              // host-known size of raw
   int cell_cap;           // capacity of cells
+  int cell_tag;           // stamp of the next grid build over this map
   float inv_leaf;         // 1 / leaf (computed on the host in float, like PCL)
   int downsample;
 };
@@ -462,9 +482,10 @@ __global__ void __launch_bounds__(MB_THREADS) grid_keys_kernel(const __grid_cons
     d[a] = (int)floorf(mx) - o[a] + 1;
   }
   const long long ncells64 = (long long)d[0] * d[1] * d[2];
-  const bool too_large = ncells64 > (long long)M.cell_cap;
+  const bool too_large = ncells64 > (long long)M.cell_cap || n >= CELL_MAX_POINTS;
   const int ncells = too_large ? 0 : (int)ncells64;
   if (blockIdx.x == 0 && threadIdx.x == 0) {
+    st->cell_tag = M.cell_tag;
     st->gox = o[0]; st->goy = o[1]; st->goz = o[2];
     st->gdx = d[0]; st->gdy = d[1]; st->gdz = d[2];
     st->ncells = ncells;
@@ -472,9 +493,7 @@ __global__ void __launch_bounds__(MB_THREADS) grid_keys_kernel(const __grid_cons
     st->grid_bits = ncells <= 1 ? 0 : 32 - __clz((uint32_t)(ncells - 1));
   }
   const int bits = ncells <= 1 ? 0 : 32 - __clz((uint32_t)(ncells - 1));
-  // clear the cell table (grid-stride over the cells actually in use)
-  const int total_threads = gridDim.x * MB_THREADS;
-  for (int c = blockIdx.x * MB_THREADS + threadIdx.x; c < ncells; c += total_threads) M.cells[c] = make_int2(0, 0);
+  // (no cell-table clear: entries are stamped, see cell_entry_x)
   const int base = blockIdx.x * MB_TILE;
 #pragma unroll
   for (int k = 0; k < MB_ITEMS; ++k) {
@@ -514,8 +533,8 @@ __global__ void __launch_bounds__(MB_THREADS) grid_finalize_kernel(const __grid_
       const uint32_t v = vals[i];
       const float4 p = M.ds[v];
       M.sorted[i] = make_float4(p.x, p.y, p.z, __uint_as_float(v));
-      if (i == 0 || keys[i - 1] != key) M.cells[key].x = i;
-      if (i == n - 1 || keys[i + 1] != key) M.cells[key].y = i + 1;
+      if (i == 0 || keys[i - 1] != key) M.cells[key].x = (int)cell_entry_x(M.cell_tag, (uint32_t)i);
+      if (i == n - 1 || keys[i + 1] != key) M.cells[key].y = (int)cell_entry_y(M.cell_tag, (uint32_t)(i + 1));
     }
   }
 }

@@ -28,7 +28,8 @@
 
 namespace ll {
 
-constexpr int INC_RUN_MAX = 8192;   // points per map the keyframes added in one merge may hold (one bitonic network)
+constexpr int INC_RUN_MAX = 16384;  // points per map the keyframes added in one merge may hold (one bitonic network)
+constexpr int INC_RUN_BITS = 14;
 constexpr int INC_MAX_DEAD = 8;     // keyframes dropped in one merge
 constexpr int INC_MAX_SEGS = 12;    // clouds of the added keyframes (three per keyframe)
 constexpr int INC_SUB = 2048;       // window entries per sub-tile of the merge
@@ -59,7 +60,19 @@ struct IncJob {
   int n_segs;
   Segment segs[INC_MAX_SEGS];    // Segment::pad[0] = tag
   int final_step;                // 1 = compute laserCloud*FromMapDS after the merge
+  int keep_fail;                 // 1 = the window this merge starts from comes from a merge whose verdict the host has not
+                                 //     read yet: MapState::inc_fail survives the zeroing at the head of the launch
 };
+
+// Zero both MapStates at the head of a launch that assembles the map (threads 0..127 of one block), keeping inc_fail when asked.
+__device__ __forceinline__ void inc_zero_map_states(const MapBatch& B, bool keep_fail) {
+  const int t = threadIdx.x;
+  if (t < 128) {
+    constexpr int kFailWord = (int)(offsetof(MapState, inc_fail) / 4);
+    static_assert(sizeof(MapState) <= 256 && offsetof(MapState, inc_fail) % 4 == 0, "MapState is zeroed as 64 words");
+    if (!(keep_fail && (t & 63) == kFailWord)) reinterpret_cast<uint32_t*>(B.m[t >> 6].st)[t & 63] = 0u;
+  }
+}
 
 // Absolute voxel coordinates of a point, packed (z | y | x, 21 bits each, offset 2^20): ascending key = VoxelGrid order.
 __device__ __forceinline__ unsigned long long inc_abs_key(const float4 p, float inv, bool& ok) {
@@ -164,7 +177,7 @@ __device__ __forceinline__ void inc_build_run(const IncJob& J, const MapBatch& B
                         iz = (long long)(int)floorf(q.z * inv) - s_mn[2];
         rel = (unsigned long long)((iz * dy + iy) * dx + ix);
       }
-      ck = (rel << 13) | (unsigned long long)i;  // unique => the bitonic order is the stable order
+      ck = (rel << INC_RUN_BITS) | (unsigned long long)i;  // unique => the bitonic order is the stable order
     }
     s_key[i] = ck;
   }
@@ -186,13 +199,13 @@ __device__ __forceinline__ void inc_build_run(const IncJob& J, const MapBatch& B
   __syncthreads();
   bool ok = true;
   for (int jj = tid; jj < n; jj += blockDim.x) {
-    const int i = (int)(s_key[jj] & 8191ull);
+    const int i = (int)(s_key[jj] & (unsigned long long)(INC_RUN_MAX - 1));
     const float4 q = W.stage_pts[i];
     W.run_pts[jj] = q;
     W.run_key[jj] = inc_abs_key(q, M.inv_leaf, ok);
     W.run_tag[jj] = W.stage_tag[i];
   }
-  static_assert(INC_RUN_MAX == 8192, "the composite key keeps the arrival index in 13 bits");
+  static_assert(INC_RUN_MAX == (1 << INC_RUN_BITS), "the composite key keeps the arrival index in INC_RUN_BITS bits");
 }
 
 // ---- C: surviving entries of this worker's tile of the old window.
@@ -629,7 +642,7 @@ __global__ void __launch_bounds__(GI_THREADS, 1) map_inc_kernel(const __grid_con
                                                                 unsigned* barrier, unsigned* barrier_clear) {
   extern __shared__ __align__(16) unsigned char s_inc[];
   unsigned epoch = 0;
-  if (blockIdx.x == 0 && threadIdx.x < 128) reinterpret_cast<uint32_t*>(B.m[threadIdx.x >> 6].st)[threadIdx.x & 63] = 0u;
+  if (blockIdx.x == 0) inc_zero_map_states(B, J.keep_fail != 0);
   coop_barrier(barrier, epoch);
   map_incremental_inline(J, B, barrier, epoch, reinterpret_cast<uint32_t*>(s_inc));
   if (blockIdx.x == 0 && threadIdx.x == 0) *barrier_clear = 0u;

@@ -198,8 +198,8 @@ __device__ __forceinline__ void gi_sort_core(const MapBatch& B, const TileJob& J
           if (kCells && last) {
             const float4 pk = kPrefetch ? pt[kPrefetch ? k : 0] : __ldcg(&M.ds[val[k]]);
             M.sorted[pos] = make_float4(pk.x, pk.y, pk.z, __uint_as_float(val[k]));
-            atomicMin(&M.cells[key[k]].x, (int)pos);
-            atomicMax(&M.cells[key[k]].y, (int)pos + 1);
+            atomicMin(reinterpret_cast<unsigned*>(&M.cells[key[k]].x), cell_entry_x(M.cell_tag, pos));
+            atomicMax(reinterpret_cast<unsigned*>(&M.cells[key[k]].y), cell_entry_y(M.cell_tag, pos + 1u));
           } else {
             keys_out[pos] = key[k];
             vals_out[pos] = val[k];
@@ -253,7 +253,8 @@ __device__ __forceinline__ void gi_sort_tiles(const MapBatch& B, const GridDims 
         M.sorted[i] = make_float4(p.x, p.y, p.z, __uint_as_float((uint32_t)i));
       }
     }
-    if (J.tile == 0 && threadIdx.x == 0) M.cells[0] = make_int2(0, J.n);
+    if (J.tile == 0 && threadIdx.x == 0)
+      M.cells[0] = make_int2((int)cell_entry_x(M.cell_tag, 0u), (int)cell_entry_y(M.cell_tag, (uint32_t)J.n));
   }
 }
 
@@ -562,20 +563,8 @@ __device__ __forceinline__ bool map_build_inline(const MapBatch& B, const Segmen
   coop_barrier(barrier, epoch);
   const int n0 = B.m[0].downsample ? B.m[0].n_raw : 0, n1 = B.m[1].downsample ? B.m[1].n_raw : 0;
   const int items = gi_items(n0, n1, (int)gridDim.x);  // > 0: the host bounds the raw size
-  // The VoxelGrid sort keeps one tile per block; blocks WITHOUT a tile (47 of 148 for a VLP-16 window) would only wait
-  // at its barriers, so they clear the cell tables of the search grids meanwhile (the geometry only needs the box).
-  const int t_ = GI_THREADS * (items > 0 ? items : GI_MAX_ITEMS);
-  const int tiles = (n0 + t_ - 1) / t_ + (n1 + t_ - 1) / t_;
-  const bool side_clear = may_clear_cells && tiles < (int)gridDim.x;  // grid-uniform
-  if (side_clear && (int)blockIdx.x >= tiles) {
-    const int idle = (int)gridDim.x - tiles, me = (int)blockIdx.x - tiles;
-#pragma unroll
-    for (int m = 0; m < 2; ++m) {
-      const GridDims g = grid_dims(B.m[m].st, B.m[m].cell_cap);
-      for (int c = me * GI_THREADS + (int)threadIdx.x; c < g.ncells; c += idle * GI_THREADS)
-        B.m[m].cells[c] = make_int2(0x7fffffff, 0);
-    }
-  }
+  (void)may_clear_cells;  // (the cell tables are stamped, not cleared: map_build.cuh)
+  const bool side_clear = false;
   if (items == 4) gi_voxel<4>(B, barrier, epoch, smem);
   else if (items == 8) gi_voxel<8>(B, barrier, epoch, smem);
   else if (items == 16) gi_voxel<16>(B, barrier, epoch, smem);
@@ -587,7 +576,7 @@ __device__ __forceinline__ bool map_build_inline(const MapBatch& B, const Segmen
 // smem: GI_SMEM_WORDS uint32. Returns with a grid barrier passed (results visible to every block).
 __device__ __forceinline__ void grid_build_inline(const MapBatch& B, unsigned* barrier, unsigned& epoch, uint32_t* smem,
                                                   bool cells_cleared = false) {
-  const int gtid = blockIdx.x * GI_THREADS + threadIdx.x, gthreads = gridDim.x * GI_THREADS;
+  const int gtid = blockIdx.x * GI_THREADS + threadIdx.x;
   GridDims gd[2];
   int n[2];
 #pragma unroll
@@ -612,9 +601,9 @@ __device__ __forceinline__ void grid_build_inline(const MapBatch& B, unsigned* b
       st->ncells = g.ncells;
       st->grid_too_large = g.too_large ? 1 : 0;
       st->grid_bits = g.bits;
+      st->cell_tag = M.cell_tag;
     }
-    if (!cells_cleared)
-      for (int c = gtid; c < g.ncells; c += gthreads) M.cells[c] = make_int2(0x7fffffff, 0);
+    (void)cells_cleared;  // (no clear: stamped entries)
   }
   if (gd[0].bits == 0 || gd[1].bits == 0)  // (warp-, block- and grid-uniform)
     coop_barrier(barrier, epoch);  // a single-cell map writes its cell entry without an intervening pass barrier

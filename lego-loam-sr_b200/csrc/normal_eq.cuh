@@ -25,48 +25,12 @@ __device__ inline void inverse3_cofactor(const float* M, float* inv) {
 #undef MM
 }
 
-__global__ void __launch_bounds__(LM_THREADS) normal_eq_kernel(const float* __restrict__ rows6,
-                                                               const float* __restrict__ b, int n, int dof_mask,
-                                                               int iter, float eig_thresh, int eigen_mode,
-                                                               float* x_out, float* matP, int* is_degenerate) {
-  __shared__ double s_part[LM_WARPS][28];
-  __shared__ int s_cols[6];
-  __shared__ int s_m;
-  if (threadIdx.x == 0) {
-    int m = 0;
-    for (int k = 0; k < 6; ++k)
-      if (dof_mask & (1 << k)) s_cols[m++] = k;
-    s_m = m;
-  }
-  __syncthreads();
-  const int m = s_m;
-  const int nsum = m * (m + 1) / 2 + m;
-  double acc[27];
-  for (int k = 0; k < 27; ++k) acc[k] = 0.0;
-  for (int i = threadIdx.x; i < n; i += LM_THREADS) {
-    float r[6];
-    for (int k = 0; k < m; ++k) r[k] = rows6[6 * i + s_cols[k]];
-    const float bi = b[i];
-    int k = 0;
-    for (int a = 0; a < m; ++a)
-      for (int c = a; c < m; ++c) acc[k++] += (double)(r[a] * r[c]);
-    for (int a = 0; a < m; ++a) acc[k++] += (double)(r[a] * bi);
-  }
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int k = 0; k < nsum; ++k) {
-    double v = acc[k];
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane == 0) s_part[warp][k] = v;
-  }
-  __syncthreads();
-  if (threadIdx.x != 0) return;
-  double sums[27];
-  for (int k = 0; k < nsum; ++k) {
-    double t = 0.0;
-    for (int w = 0; w < LM_WARPS; ++w) t += s_part[w][k];
-    sums[k] = t;
-  }
-  float AtA[36], Atb[6], x[6];
+// The solve of calculateTransformation* once matAtA / matAtB are known (featureAssociation.cpp:1953-1990): column-pivoted
+// QR, on iterCount == 0 the eigen / degeneracy projector, then matX = matP * matX2 while isDegenerate. One thread.
+// sums: the m (m + 1) / 2 upper-triangular entries of AtA (row-major order), then the m entries of AtB. x: [m].
+__device__ __noinline__ void neq_solve_small(const double* sums, int m, int iter, float eig_thresh, int eigen_mode, float* x,
+                                             float* matP, int* is_degenerate) {
+  float AtA[36], Atb[6];
   int k = 0;
   for (int a = 0; a < m; ++a)
     for (int c = a; c < m; ++c) {
@@ -128,6 +92,51 @@ __global__ void __launch_bounds__(LM_THREADS) normal_eq_kernel(const float* __re
     }
     for (int r = 0; r < m; ++r) x[r] = x2[r];
   }
+}
+
+__global__ void __launch_bounds__(LM_THREADS) normal_eq_kernel(const float* __restrict__ rows6,
+                                                               const float* __restrict__ b, int n, int dof_mask,
+                                                               int iter, float eig_thresh, int eigen_mode,
+                                                               float* x_out, float* matP, int* is_degenerate) {
+  __shared__ double s_part[LM_WARPS][28];
+  __shared__ int s_cols[6];
+  __shared__ int s_m;
+  if (threadIdx.x == 0) {
+    int m = 0;
+    for (int k = 0; k < 6; ++k)
+      if (dof_mask & (1 << k)) s_cols[m++] = k;
+    s_m = m;
+  }
+  __syncthreads();
+  const int m = s_m;
+  const int nsum = m * (m + 1) / 2 + m;
+  double acc[27];
+  for (int k = 0; k < 27; ++k) acc[k] = 0.0;
+  for (int i = threadIdx.x; i < n; i += LM_THREADS) {
+    float r[6];
+    for (int k = 0; k < m; ++k) r[k] = rows6[6 * i + s_cols[k]];
+    const float bi = b[i];
+    int k = 0;
+    for (int a = 0; a < m; ++a)
+      for (int c = a; c < m; ++c) acc[k++] += (double)(r[a] * r[c]);
+    for (int a = 0; a < m; ++a) acc[k++] += (double)(r[a] * bi);
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int k = 0; k < nsum; ++k) {
+    double v = acc[k];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) s_part[warp][k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  double sums[27];
+  for (int k = 0; k < nsum; ++k) {
+    double t = 0.0;
+    for (int w = 0; w < LM_WARPS; ++w) t += s_part[w][k];
+    sums[k] = t;
+  }
+  float x[6];
+  neq_solve_small(sums, m, iter, eig_thresh, eigen_mode, x, matP, is_degenerate);
   for (int r = 0; r < m; ++r) x_out[r] = x[r];
 }
 
