@@ -1006,7 +1006,14 @@ __device__ __noinline__ bool knn5_thread(const KnnCache C, int i, const Trig* tr
   };
   // ---- step 1
   const float4 t1 = C.t1[i];
-  if (t1.w > 0.f) {
+  if (t1.w < 0.f) {
+    // a REJECTED query's guard: at c' the fifth-nearest map point was H = -t1.w > 1 m away, so it is still farther than
+    // 1 m from q when |q - c'| + slack <= H - 1: fewer than five points within range, as before.
+    if (dist_to(t1) + LM_T1_SLACK <= -t1.w - 1.f) {
+      slot[0] = sel.x; slot[1] = sel.y; slot[2] = sel.z; slot[3] = 0.f;
+      return true;
+    }
+  } else if (t1.w > 0.f) {
     uint32_t mask = C.prev[i];
     float4 nb[5];
     uint32_t d[5];
@@ -1033,6 +1040,8 @@ __device__ __noinline__ bool knn5_thread(const KnnCache C, int i, const Trig* tr
       return true;
     }
   }
+  LL_TL_COUNT_THREAD(6);
+  if (t1.w == 0.f) LL_TL_COUNT_THREAD(7);
   // ---- step 2: the whole set, top six by (d2, index). Columns are visited rotated by the thread index: the threads of a
   //      warp read different rows of `cand` (stride 512 bytes), and the rotation spreads them over the banks.
   const int cnt_raw = C.cnt[i];
@@ -1047,7 +1056,7 @@ __device__ __noinline__ bool knn5_thread(const KnnCache C, int i, const Trig* tr
     if (col >= cnt) continue;
     const float4 m = cand[col];
     const uint32_t db = dist_bits(m), ib = __float_as_uint(m.w);
-    if (db < max_bits && pair_less(db, ib, td[5], ti[5])) {
+    if (pair_less(db, ib, td[5], ti[5])) {  // (all candidates: a rejected query's guard needs the distances beyond 1 m too)
       td[5] = db; ti[5] = ib; tc[5] = col;
 #pragma unroll
       for (int k = 5; k > 0; --k) {
@@ -1059,11 +1068,11 @@ __device__ __noinline__ bool knn5_thread(const KnnCache C, int i, const Trig* tr
       }
     }
   }
-  const bool acc = td[4] != LM_EMPTY_D2;
+  const bool acc = td[4] < max_bits;  // five points within range
   const float4 ctr = C.center[i];
   const bool same_cell = floorf(sel.x) == floorf(ctr.x) && floorf(sel.y) == floorf(ctr.y) && floorf(sel.z) == floorf(ctr.z);
   const float sl = dist_to(ctr);
-  const float sD = acc ? approx_sqrt(__uint_as_float(td[4])) : 0.f;
+  const float sD = td[4] != LM_EMPTY_D2 ? approx_sqrt(__uint_as_float(td[4])) : 3.f;  // (no fifth point in the set at all: any bound above 2 m serves)
   bool ok;
   float outside;  // lower bound of the distance from sel to every map point that is not in the set
   // distance from sel to the nearest face of its one-metre cell: a point outside the 27 cells is at least 1 m + that away
@@ -1082,7 +1091,9 @@ __device__ __noinline__ bool knn5_thread(const KnnCache C, int i, const Trig* tr
   if (!ok) return false;
   if (!acc) {
     slot[0] = sel.x; slot[1] = sel.y; slot[2] = sel.z; slot[3] = 0.f;
-    C.t1[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    // guard for step 1: the fifth-nearest point overall is at least H away (within the set: sD; outside it: `outside`)
+    const float H = fminf(sD, outside);
+    C.t1[i] = H > 1.f ? make_float4(sel.x, sel.y, sel.z, -H) : make_float4(0.f, 0.f, 0.f, 0.f);
     return true;
   }
   float4 nb[5];
@@ -1090,7 +1101,7 @@ __device__ __noinline__ bool knn5_thread(const KnnCache C, int i, const Trig* tr
 #pragma unroll
   for (int k = 0; k < 5; ++k) { nb[k] = cand[tc[k]]; mask |= 1u << tc[k]; }
   emit(nb);
-  const float d6 = td[5] != LM_EMPTY_D2 ? approx_sqrt(__uint_as_float(td[5])) : 1.f;
+  const float d6 = td[5] != LM_EMPTY_D2 ? approx_sqrt(__uint_as_float(td[5])) : 1.f;  // (capped at 1 m below)
   C.prev[i] = mask;
   C.t1[i] = make_float4(sel.x, sel.y, sel.z, fminf(fminf(d6, outside), 1.f));
   return true;
@@ -1829,8 +1840,8 @@ __global__ void __launch_bounds__(LM_THREADS, 1) lm_persistent_kernel(const __gr
       }
       printf("   %-34s %7.2f   (globaltimer: first arrival -> last arrival %.2f us, last arrival -> last release %.2f us)\n",
              "iteration total (mean of blocks)", tot_mean, (last - first) * 1e-3, (rel - last) * 1e-3);
-      printf("   queries: %u full searches (%u with > 128 candidates, %u rejected in a dense cell), cached: %u attempted, %u proven\n",
-             g_tl_cnt[itx][0], g_tl_cnt[itx][1], g_tl_cnt[itx][3], g_tl_cnt[itx][5], g_tl_cnt[itx][4]);
+      printf("   queries: %u full searches (%u with > 128 candidates, %u rejected in a dense cell), cached: %u attempted, %u proven; %u went to step 2 (%u of them without a guard)\n",
+             g_tl_cnt[itx][0], g_tl_cnt[itx][1], g_tl_cnt[itx][3], g_tl_cnt[itx][5], g_tl_cnt[itx][4], g_tl_cnt[itx][6], g_tl_cnt[itx][7]);
       for (int k = 0; k < 8; ++k) g_tl_cnt[itx][k] = 0;
       if (itx == 0 || itx == 1 || itx == 5) {
         printf("   block %d phase 1 per warp (us from its start): - / - / - / - / thread-level cached search done / full search done\n", TL_WATCH);
