@@ -877,7 +877,7 @@ constexpr float LM_T1_SLACK = 2e-5f;
 
 struct KnnCache {
   float4* cand;    // [LM_QCAP][32]  x, y, z, map-index bits
-  float4* center;  // [LM_QCAP]      c and R (R < 0: cell-complete set; 0 < R <= 1: radius set; R > 1: radius set of a REJECTED query)
+  float4* center;  // [LM_QCAP]      c and R (R < 0: cell-complete set; 0 < R <= 1: radius set; R > 1: radius set usable only inside the cell of c)
   float4* qpt;     // [LM_QCAP]      the query itself (sensor frame), so that the steady state never leaves the SM
   float4* t1;      // [LM_QCAP]      c' and G: where the five members were last confirmed, and a lower bound of the distance
                    //                from c' to every map point that is NOT one of them (G <= 0: unknown)
@@ -897,8 +897,8 @@ constexpr int LM_PERSISTENT_SMEM = LM_LOOP_SMEM > INC_SMEM_BYTES ? LM_LOOP_SMEM 
 // All 32 lanes.
 template <bool kFresh>
 __device__ __noinline__ void knn_cache_fill(const float4* sorted, int my_start, int my_count, float sx, float sy, float sz,
-                                            uint32_t d5bits, float4 qsensor, int lane, float4* cand, float4* center,
-                                            float4* qpt, float4* t1, int* cnt_out, uint32_t* prev_out) {
+                                            uint32_t d5bits, uint32_t i5bits, float4 qsensor, int lane, float4* cand,
+                                            float4* center, float4* qpt, float4* t1, int* cnt_out, uint32_t* prev_out) {
   constexpr int kRowLane[9] = {12, 3, 9, 15, 21, 0, 6, 18, 24};
   int pr[9], bs[9];
   int total = 0;
@@ -926,9 +926,12 @@ __device__ __noinline__ void knn_cache_fill(const float4* sorted, int my_start, 
 #pragma unroll 1
   for (int attempt = 0; attempt < 2; ++attempt) {
     const float margin = attempt == 0 ? LM_CACHE_MARGIN : 0.3f * LM_CACHE_MARGIN;
-    const float R = whole ? -1.f : (rejected ? 1.0f + margin : fminf(1.0f, sqrtf(__uint_as_float(d5bits)) + margin));
+    // (R may exceed 1 m — a fifth neighbour near the acceptance limit, or a rejected query: the set is then only usable
+    //  while the query stays in its cell, knn5_thread)
+    const float R = whole ? -1.f : (rejected ? 1.0f + margin : sqrtf(__uint_as_float(d5bits)) + margin);
     const float R2 = R * R;
     int base = 0;
+    uint32_t members = 0u, d6 = LM_EMPTY_D2;  // positions of the five neighbours in the set; nearest point that is not one of them
 #pragma unroll 1
     for (int j0 = 0; j0 < total && base <= LM_CACHE_CAND; j0 += 32) {
       const int j = j0 + lane;
@@ -949,6 +952,10 @@ __device__ __noinline__ void knn_cache_fill(const float4* sorted, int my_start, 
       const int pos = base + __popc(bal & lt_mask);
       if (in && pos < LM_CACHE_CAND) cand[pos] = m;
       base += __popc(bal);
+      // one of the five found by the search <=> (d2, index) <= the fifth's
+      const bool member = have && d5bits != LM_EMPTY_D2 && !pair_less(d5bits, i5bits, __float_as_uint(d), __float_as_uint(m.w));
+      members |= __reduce_or_sync(0xffffffffu, (member && in && pos < LM_CACHE_CAND) ? (1u << pos) : 0u);
+      d6 = min(d6, __reduce_min_sync(0xffffffffu, (have && !member) ? __float_as_uint(d) : LM_EMPTY_D2));
     }
     const bool fits = whole || (base <= LM_CACHE_CAND && (rejected || base >= 5));
     if (fits || attempt == 1) {
@@ -956,6 +963,17 @@ __device__ __noinline__ void knn_cache_fill(const float4* sorted, int my_start, 
         *center = make_float4(sx, sy, sz, R);
         // (an EMPTY cell-complete set is stored as count 33: cnt must be > 0 to be used, and no lane is below 33 <= 32)
         *cnt_out = fits ? (base > 0 ? base : LM_CACHE_CAND + 1) : -1;
+        if (fits && __popc(members) == 5) {
+          // the guard of knn5_thread's step 1, straight from this scan: it covered every point of the 27 cells, so the
+          // nearest point that is not one of the five is at distance sqrt(d6) or beyond the 27 cells (>= 1 m + the distance
+          // to the nearest face of the query's cell)
+          const float fx = sx - floorf(sx), fy = sy - floorf(sy), fz = sz - floorf(sz);
+          const float face = fminf(fminf(fminf(fx, 1.f - fx), fminf(fy, 1.f - fy)), fminf(fz, 1.f - fz));
+          const float v6 = __uint_as_float(d6);
+          const float s6 = d6 != LM_EMPTY_D2 ? (v6 > 0.f ? v6 * rsqrtf(v6) : 0.f) : 1.f;
+          *prev_out = members;
+          *t1 = make_float4(sx, sy, sz, fminf(fminf(s6, 1.f + face), 1.f));
+        }
       }
       return;
     }
@@ -1014,29 +1032,40 @@ __device__ __noinline__ bool knn5_thread(const KnnCache C, int i, const Trig* tr
       return true;
     }
   } else if (t1.w > 0.f) {
+    // the members of last time: five, or six when the fifth and sixth were too close to call (step 2 below). Each member's
+    // rank among them by (d2, index) is counted directly — fifteen independent comparisons instead of a sorting network's
+    // dependent layers — and the members of rank 0..4 go to their places in the slot.
     uint32_t mask = C.prev[i];
-    float4 nb[5];
-    uint32_t d[5];
+    float4 nb[6];
+    uint32_t d[6], ix[6];
 #pragma unroll
-    for (int k = 0; k < 5; ++k) {
-      const int j = __ffs(mask) - 1;
+    for (int k = 0; k < 6; ++k) {
+      const bool have = mask != 0u;
+      const int j = have ? __ffs(mask) - 1 : 0;
       mask &= mask - 1u;
-      nb[k] = cand[j & (LM_CACHE_CAND - 1)];
-      d[k] = dist_bits(nb[k]);
+      nb[k] = cand[j];
+      d[k] = have ? dist_bits(nb[k]) : LM_EMPTY_D2;
+      ix[k] = have ? __float_as_uint(nb[k].w) : 0xffffffffu;
     }
-#define LL_T1_CE(a, b)                                                                                              \
-    {                                                                                                                 \
-      const bool sw_ = pair_less(d[b], __float_as_uint(nb[b].w), d[a], __float_as_uint(nb[a].w));                     \
-      const uint32_t td_ = sw_ ? d[b] : d[a];                                                                         \
-      const float4 tn_ = sw_ ? nb[b] : nb[a];                                                                         \
-      d[b] = sw_ ? d[a] : d[b]; nb[b] = sw_ ? nb[a] : nb[b];                                                          \
-      d[a] = td_; nb[a] = tn_;                                                                                        \
-    }
-    // 9-comparator network for five keys
-    LL_T1_CE(0, 1) LL_T1_CE(3, 4) LL_T1_CE(2, 4) LL_T1_CE(2, 3) LL_T1_CE(0, 3) LL_T1_CE(0, 2) LL_T1_CE(1, 4) LL_T1_CE(1, 3) LL_T1_CE(1, 2)
-#undef LL_T1_CE
-    if (d[4] < max_bits && approx_sqrt(__uint_as_float(d[4])) + dist_to(t1) + LM_T1_SLACK <= t1.w) {
-      emit(nb);
+    int rank[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) rank[k] = 0;
+#pragma unroll
+    for (int a = 0; a < 6; ++a)
+#pragma unroll
+      for (int b = a + 1; b < 6; ++b) {
+        const bool lt = pair_less(d[b], ix[b], d[a], ix[a]);  // b before a (keys are distinct: map indices differ)
+        rank[a] += lt ? 1 : 0;
+        rank[b] += lt ? 0 : 1;
+      }
+    uint32_t d5 = 0u;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) d5 = rank[k] == 4 ? d[k] : d5;
+    if (d5 < max_bits && approx_sqrt(__uint_as_float(d5)) + dist_to(t1) + LM_T1_SLACK <= t1.w) {
+      slot[0] = sel.x; slot[1] = sel.y; slot[2] = sel.z; slot[3] = 1.f;
+#pragma unroll
+      for (int k = 0; k < 6; ++k)
+        if (rank[k] < 5) { slot[4 + 3 * rank[k]] = nb[k].x; slot[5 + 3 * rank[k]] = nb[k].y; slot[6 + 3 * rank[k]] = nb[k].z; }
       return true;
     }
   }
@@ -1046,20 +1075,21 @@ __device__ __noinline__ bool knn5_thread(const KnnCache C, int i, const Trig* tr
   //      warp read different rows of `cand` (stride 512 bytes), and the rotation spreads them over the banks.
   const int cnt_raw = C.cnt[i];
   const int cnt = cnt_raw <= LM_CACHE_CAND ? cnt_raw : 0;  // (an EMPTY set is stored as count 33)
-  uint32_t td[6], ti[6];
-  int tc[6];
+  constexpr int NT = 7;  // five neighbours, the sixth for the guard, the seventh for the guard of a six-member set
+  uint32_t td[NT], ti[NT];
+  int tc[NT];
 #pragma unroll
-  for (int k = 0; k < 6; ++k) { td[k] = LM_EMPTY_D2; ti[k] = 0xffffffffu; tc[k] = 0; }
+  for (int k = 0; k < NT; ++k) { td[k] = LM_EMPTY_D2; ti[k] = 0xffffffffu; tc[k] = 0; }
 #pragma unroll 4
   for (int j = 0; j < LM_CACHE_CAND; ++j) {
     const int col = (j + (int)threadIdx.x) & (LM_CACHE_CAND - 1);
     if (col >= cnt) continue;
     const float4 m = cand[col];
     const uint32_t db = dist_bits(m), ib = __float_as_uint(m.w);
-    if (pair_less(db, ib, td[5], ti[5])) {  // (all candidates: a rejected query's guard needs the distances beyond 1 m too)
-      td[5] = db; ti[5] = ib; tc[5] = col;
+    if (pair_less(db, ib, td[NT - 1], ti[NT - 1])) {  // (all candidates: a rejected query's guard needs the distances beyond 1 m too)
+      td[NT - 1] = db; ti[NT - 1] = ib; tc[NT - 1] = col;
 #pragma unroll
-      for (int k = 5; k > 0; --k) {
+      for (int k = NT - 1; k > 0; --k) {
         if (pair_less(td[k], ti[k], td[k - 1], ti[k - 1])) {
           const uint32_t a = td[k]; td[k] = td[k - 1]; td[k - 1] = a;
           const uint32_t b = ti[k]; ti[k] = ti[k - 1]; ti[k - 1] = b;
@@ -1081,11 +1111,12 @@ __device__ __noinline__ bool knn5_thread(const KnnCache C, int i, const Trig* tr
   if (ctr.w < 0.f) {          // cell-complete
     ok = same_cell;
     outside = 1.f + face;
-  } else if (ctr.w <= 1.f) {  // radius set of an accepted query
+  } else if (ctr.w <= 1.f) {  // radius set within 1 m: the ball is inside the 27 cells wherever the query goes
     ok = acc && sD + sl + LM_CACHE_SLACK <= ctr.w;
     outside = ctr.w - sl;
-  } else {                    // radius set of a rejected query
-    ok = same_cell && sl + LM_CACHE_SLACK <= ctr.w - 1.f;
+  } else {                    // radius set beyond 1 m (fifth neighbour near the limit, or a rejected query): complete only
+                              // for points within 1 m of a query that is still in the cell the set was collected for
+    ok = same_cell && (acc ? sD + sl + LM_CACHE_SLACK <= ctr.w : sl + LM_CACHE_SLACK <= ctr.w - 1.f);
     outside = fminf(ctr.w - sl, 1.f + face);
   }
   if (!ok) return false;
@@ -1101,7 +1132,13 @@ __device__ __noinline__ bool knn5_thread(const KnnCache C, int i, const Trig* tr
 #pragma unroll
   for (int k = 0; k < 5; ++k) { nb[k] = cand[tc[k]]; mask |= 1u << tc[k]; }
   emit(nb);
-  const float d6 = td[5] != LM_EMPTY_D2 ? approx_sqrt(__uint_as_float(td[5])) : 1.f;  // (capped at 1 m below)
+  // the guard of step 1: the nearest point that is not a member. When the sixth is within a millimetre of the fifth (a
+  // few queries per scan: the guard would never hold) the sixth joins the members and the seventh bounds the rest.
+  float d6 = td[5] != LM_EMPTY_D2 ? approx_sqrt(__uint_as_float(td[5])) : 1.f;  // (capped at 1 m below)
+  if (d6 - sD < 1e-3f && td[5] != LM_EMPTY_D2) {
+    mask |= 1u << tc[5];
+    d6 = td[6] != LM_EMPTY_D2 ? approx_sqrt(__uint_as_float(td[6])) : 1.f;
+  }
   C.prev[i] = mask;
   C.t1[i] = make_float4(sel.x, sel.y, sel.z, fminf(fminf(d6, outside), 1.f));
   return true;
@@ -1552,7 +1589,8 @@ __device__ __noinline__ void lm_full_search_warp(const LMArgs* Ap, const Trig* t
         }
         if (first_chunk && i < LM_QCAP) {  // (re)build this query's cached set around where it is now
           const uint32_t d5 = __shfl_sync(0xffffffffu, acc[b] ? od[b] : LM_EMPTY_D2, 4);
-          knn_cache_fill<kFresh>(A.sorted[mq[b]], q_start[b], q_count[b], sel[b].x, sel[b].y, sel[b].z, d5, qs[b], lane,
+          const uint32_t i5 = __shfl_sync(0xffffffffu, oi[b], 4);
+          knn_cache_fill<kFresh>(A.sorted[mq[b]], q_start[b], q_count[b], sel[b].x, sel[b].y, sel[b].z, d5, i5, qs[b], lane,
                                  &C.cand[i * LM_CACHE_CAND], &C.center[i], &C.qpt[i], &C.t1[i], &C.cnt[i], &C.prev[i]);
         }
       }
