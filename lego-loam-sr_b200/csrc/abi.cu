@@ -129,6 +129,8 @@ struct ll_handle_s {
   LMState* d_state = nullptr;
   LMState* h_state = nullptr;  // pinned mirror
   float* d_partials = nullptr;   // [2][partial_blocks][32] (double-buffered by iteration parity in the persistent kernel)
+  void* d_guard = nullptr;       // LMArgs::g_guard: 576 bytes per query, only for scans with more queries than cache slots
+  size_t guard_bytes = 0;
   unsigned* d_barriers = nullptr;  // ring of kBarrierSlots grid-barrier counters, one per scan, re-armed 32 scans ahead
   uint64_t scan_seq = 0;
   int partial_blocks = 0;
@@ -1165,6 +1167,10 @@ int scan2map_enqueue(ll_handle h, const float pose6[6]) {
   if (h->prm.persistent_lm) {
     // the whole loop in one cooperative launch (all blocks co-resident: lm_blocks <= number of SMs, one block per SM)
     LMArgs A = make_lm_args(h, 0);
+    if ((long)nq > (long)h->lm_blocks * LM_QCAP) {  // more queries than the blocks have cache slots: cache records in global memory
+      LL_TRY(ensure_bytes(h, &h->d_guard, &h->guard_bytes, (size_t)nq * LM_GUARD_STRIDE * sizeof(float4)));
+      A.g_guard = static_cast<float4*>(h->d_guard);
+    }
     float p[6] = {pose6[0], pose6[1], pose6[2], pose6[3], pose6[4], pose6[5]};
     unsigned* bar = h->d_barriers + (h->scan_seq % kBarrierSlots);
     unsigned* bar_clear = h->d_barriers + ((h->scan_seq + kBarrierSlots / 2) % kBarrierSlots);
@@ -1398,7 +1404,7 @@ int ll_destroy(ll_handle h) {
     for (void* p : ptrs)
       if (p) cudaFree(p);
   }
-  void* ptrs[] = {h->d_segs, h->d_segs_aux, h->dq[0], h->dq[1], h->d_state, h->d_partials, h->d_barriers, h->fa_last[0], h->fa_last[1],
+  void* ptrs[] = {h->d_segs, h->d_segs_aux, h->dq[0], h->dq[1], h->d_state, h->d_partials, h->d_guard, h->d_barriers, h->fa_last[0], h->fa_last[1],
                   h->d_tmp[0], h->d_tmp[1], h->d_tmp[2], h->d_tmp[3], h->d_tmp[4], h->d_tmp[5]};
   for (void* p : ptrs)
     if (p) cudaFree(p);

@@ -133,7 +133,12 @@ struct LMArgs {
   int* e_accept;
   int* e_idx;
   float* e_d2;
+  // cache records of the queries beyond a block's LM_QCAP shared-memory slots (dense scans: hundreds of queries per
+  // block), indexed by query (corner queries first), LM_GUARD_STRIDE float4 each: the same fields as a KnnCache slot —
+  // [0..31] cand, [32] center, [33] qpt, [34] t1, [35] = {cnt, prev, -, -}. nullptr: not used.
+  float4* g_guard;
 };
+constexpr int LM_GUARD_STRIDE = 36;
 
 // ---- 6x6 dense helpers (one thread; column-major like Eigen) -------------------------------------------
 struct Mat6 {
@@ -884,6 +889,17 @@ struct KnnCache {
   int* cnt;        // [LM_QCAP]      0 = no set yet, -1 = not cacheable, > 0 = points in the set
   uint32_t* prev;  // [LM_QCAP]      positions in cand of the five neighbours found last time (bit mask), 0 = unknown
 };
+// A query's record in global memory (LMArgs::g_guard) seen as slot 0 of a KnnCache: the searches below work on either.
+__device__ __forceinline__ KnnCache knn_cache_of_record(float4* rec) {
+  KnnCache G;
+  G.cand = rec;
+  G.center = rec + LM_CACHE_CAND;
+  G.qpt = rec + LM_CACHE_CAND + 1;
+  G.t1 = rec + LM_CACHE_CAND + 2;
+  G.cnt = reinterpret_cast<int*>(rec + LM_CACHE_CAND + 3);
+  G.prev = reinterpret_cast<uint32_t*>(rec + LM_CACHE_CAND + 3) + 1;
+  return G;
+}
 constexpr int LM_CACHE_BYTES = LM_QCAP * (LM_CACHE_CAND * 16 + 16 + 16 + 16 + 4 + 4);
 constexpr int LM_LOOP_SMEM = LM_THREADS * LM_SLOT * (int)sizeof(float) + LM_CACHE_BYTES;
 // dynamic shared memory of lm_persistent_kernel (the incremental map assembly borrows it for the added keyframes' sort)
@@ -927,8 +943,11 @@ __device__ __noinline__ void knn_cache_fill(const float4* sorted, int my_start, 
   for (int attempt = 0; attempt < 2; ++attempt) {
     const float margin = attempt == 0 ? LM_CACHE_MARGIN : 0.3f * LM_CACHE_MARGIN;
     // (R may exceed 1 m — a fifth neighbour near the acceptance limit, or a rejected query: the set is then only usable
-    //  while the query stays in its cell, knn5_thread)
-    const float R = whole ? -1.f : (rejected ? 1.0f + margin : sqrtf(__uint_as_float(d5bits)) + margin);
+    //  while the query stays in its cell, knn5_thread.) In a dense map — un-downsampled: the fifth neighbour centimetres
+    //  away — a quarter of a metre around it holds hundreds of points, so the radius is also bounded relative to d5: with
+    //  N(r) ~ r^2..r^3 a factor 1.7 (then 1.3) keeps the set near 20 points, still far more margin than a query moves.
+    const float s5 = rejected ? 0.f : sqrtf(__uint_as_float(d5bits));
+    const float R = whole ? -1.f : (rejected ? 1.0f + margin : fminf(s5 + margin, (attempt == 0 ? 1.7f : 1.3f) * s5 + 0.004f));
     const float R2 = R * R;
     int base = 0;
     uint32_t members = 0u, d6 = LM_EMPTY_D2;  // positions of the five neighbours in the set; nearest point that is not one of them
@@ -978,6 +997,54 @@ __device__ __noinline__ void knn_cache_fill(const float4* sorted, int my_start, 
       return;
     }
   }
+}
+
+// Step 1 of the per-thread cached search (see knn5_thread): up to six member points (absent: d = LM_EMPTY_D2), the guard
+// t1 = (c', G). Returns true and fills the slot when the members still hold the five nearest points of sel.
+__device__ __forceinline__ bool knn5_guard_check(const float4 sel, const float4 (&nb)[6], const bool (&have)[6], const float4 t1,
+                                                 uint32_t max_bits, float* slot) {
+  uint32_t d[6], ix[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    float df = sel.x - nb[k].x;  // evalMetric order (nanoflann.hpp:431-439), as in the full search
+    float dd = df * df;
+    df = sel.y - nb[k].y;
+    dd += df * df;
+    df = sel.z - nb[k].z;
+    dd += df * df;
+    d[k] = have[k] ? __float_as_uint(dd) : LM_EMPTY_D2;
+    ix[k] = have[k] ? __float_as_uint(nb[k].w) : 0xffffffffu;
+  }
+  // each member's rank among them by (d2, index), counted directly: fifteen independent comparisons instead of a sorting
+  // network's dependent layers
+  int rank[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) rank[k] = 0;
+#pragma unroll
+  for (int a = 0; a < 6; ++a)
+#pragma unroll
+    for (int b = a + 1; b < 6; ++b) {
+      const bool lt = pair_less(d[b], ix[b], d[a], ix[a]);  // b before a (keys are distinct: map indices differ)
+      rank[a] += lt ? 1 : 0;
+      rank[b] += lt ? 0 : 1;
+    }
+  uint32_t d5 = 0u;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) d5 = rank[k] == 4 ? d[k] : d5;
+  float df = sel.x - t1.x;
+  float dl = df * df;
+  df = sel.y - t1.y;
+  dl += df * df;
+  df = sel.z - t1.z;
+  dl += df * df;
+  const float D = __uint_as_float(d5);
+  const float sD = D > 0.f ? D * rsqrtf(D) : 0.f, sl = dl > 0.f ? dl * rsqrtf(dl) : 0.f;  // 2 ulp: the slack dwarfs it
+  if (!(d5 < max_bits && sD + sl + LM_T1_SLACK <= t1.w)) return false;
+  slot[0] = sel.x; slot[1] = sel.y; slot[2] = sel.z; slot[3] = 1.f;
+#pragma unroll
+  for (int k = 0; k < 6; ++k)
+    if (rank[k] < 5) { slot[4 + 3 * rank[k]] = nb[k].x; slot[5 + 3 * rank[k]] = nb[k].y; slot[6 + 3 * rank[k]] = nb[k].z; }
+  return true;
 }
 
 // The cached search of ONE query by ONE thread — the thread that fits the query in phase 2, so a proven answer goes
@@ -1032,42 +1099,18 @@ __device__ __noinline__ bool knn5_thread(const KnnCache C, int i, const Trig* tr
       return true;
     }
   } else if (t1.w > 0.f) {
-    // the members of last time: five, or six when the fifth and sixth were too close to call (step 2 below). Each member's
-    // rank among them by (d2, index) is counted directly — fifteen independent comparisons instead of a sorting network's
-    // dependent layers — and the members of rank 0..4 go to their places in the slot.
+    // the members of last time: five, or six when the fifth and sixth were too close to call (step 2 below)
     uint32_t mask = C.prev[i];
     float4 nb[6];
-    uint32_t d[6], ix[6];
+    bool have[6];
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
-      const bool have = mask != 0u;
-      const int j = have ? __ffs(mask) - 1 : 0;
+      have[k] = mask != 0u;
+      const int j = have[k] ? __ffs(mask) - 1 : 0;
       mask &= mask - 1u;
       nb[k] = cand[j];
-      d[k] = have ? dist_bits(nb[k]) : LM_EMPTY_D2;
-      ix[k] = have ? __float_as_uint(nb[k].w) : 0xffffffffu;
     }
-    int rank[6];
-#pragma unroll
-    for (int k = 0; k < 6; ++k) rank[k] = 0;
-#pragma unroll
-    for (int a = 0; a < 6; ++a)
-#pragma unroll
-      for (int b = a + 1; b < 6; ++b) {
-        const bool lt = pair_less(d[b], ix[b], d[a], ix[a]);  // b before a (keys are distinct: map indices differ)
-        rank[a] += lt ? 1 : 0;
-        rank[b] += lt ? 0 : 1;
-      }
-    uint32_t d5 = 0u;
-#pragma unroll
-    for (int k = 0; k < 6; ++k) d5 = rank[k] == 4 ? d[k] : d5;
-    if (d5 < max_bits && approx_sqrt(__uint_as_float(d5)) + dist_to(t1) + LM_T1_SLACK <= t1.w) {
-      slot[0] = sel.x; slot[1] = sel.y; slot[2] = sel.z; slot[3] = 1.f;
-#pragma unroll
-      for (int k = 0; k < 6; ++k)
-        if (rank[k] < 5) { slot[4 + 3 * rank[k]] = nb[k].x; slot[5 + 3 * rank[k]] = nb[k].y; slot[6 + 3 * rank[k]] = nb[k].z; }
-      return true;
-    }
+    if (knn5_guard_check(sel, nb, have, t1, max_bits, slot)) return true;
   }
   LL_TL_COUNT_THREAD(6);
   if (t1.w == 0.f) LL_TL_COUNT_THREAD(7);
@@ -1587,11 +1630,14 @@ __device__ __noinline__ void lm_full_search_warp(const LMArgs* Ap, const Trig* t
           slot[2] = sel[b].z;
           slot[3] = acc[b] ? 1.f : 0.f;
         }
-        if (first_chunk && i < LM_QCAP) {  // (re)build this query's cached set around where it is now
+        const bool has_slot = first_chunk && i < LM_QCAP;
+        if (has_slot || A.g_guard) {  // (re)build this query's cached set around where it is now
+          const KnnCache Cq = has_slot ? C : knn_cache_of_record(A.g_guard + (size_t)sh.qi(c0 + i, A.nq[0]) * LM_GUARD_STRIDE);
+          const int ci = has_slot ? i : 0;
           const uint32_t d5 = __shfl_sync(0xffffffffu, acc[b] ? od[b] : LM_EMPTY_D2, 4);
           const uint32_t i5 = __shfl_sync(0xffffffffu, oi[b], 4);
           knn_cache_fill<kFresh>(A.sorted[mq[b]], q_start[b], q_count[b], sel[b].x, sel[b].y, sel[b].z, d5, i5, qs[b], lane,
-                                 &C.cand[i * LM_CACHE_CAND], &C.center[i], &C.qpt[i], &C.t1[i], &C.cnt[i], &C.prev[i]);
+                                 &Cq.cand[ci * LM_CACHE_CAND], &Cq.center[ci], &Cq.qpt[ci], &Cq.t1[ci], &Cq.cnt[ci], &Cq.prev[ci]);
         }
       }
     }
@@ -1625,10 +1671,15 @@ __device__ __forceinline__ float lm_block_pass_cached(const LMArgs& A, const Tri
     LL_TL_WARP(0);
     if (my_i >= 0) {
       bool proven = false;
-      if (first_chunk && my_i < LM_QCAP && C.cnt[my_i] > 0) {
-        proven = knn5_thread(C, my_i, &trig_s, A.prm.fit.max_sq_dist, &s_slot[tid * LM_SLOT]);
-        LL_TL_COUNT_THREAD(5);
-        if (proven) LL_TL_COUNT_THREAD(4);
+      if (first_chunk && my_i < LM_QCAP) {
+        if (C.cnt[my_i] > 0) {
+          proven = knn5_thread(C, my_i, &trig_s, A.prm.fit.max_sq_dist, &s_slot[tid * LM_SLOT]);
+          LL_TL_COUNT_THREAD(5);
+          if (proven) LL_TL_COUNT_THREAD(4);
+        }
+      } else if (A.g_guard) {
+        const KnnCache G = knn_cache_of_record(A.g_guard + (size_t)sh.qi(c0 + my_i, A.nq[0]) * LM_GUARD_STRIDE);
+        if (G.cnt[0] > 0) proven = knn5_thread(G, 0, &trig_s, A.prm.fit.max_sq_dist, &s_slot[tid * LM_SLOT]);
       }
       if (!proven) atomicOr(&s_need[my_i % LM_WARPS], 1u << (my_i / LM_WARPS));
     }
@@ -1807,6 +1858,11 @@ __global__ void __launch_bounds__(LM_THREADS, 1) lm_persistent_kernel(const __gr
   static_assert(INC_SMEM_BYTES <= LM_PERSISTENT_SMEM && INC_MERGE_SMEM_WORDS * 4 <= LM_PERSISTENT_SMEM &&
                 INC_REDUCE_SMEM_WORDS * 4 <= LM_PERSISTENT_SMEM, "the incremental map build borrows the dynamic shared memory");
   if (tid < LM_QCAP) C.cnt[tid] = 0;  // no cached sets yet (after the map build, which may use this memory as scratch)
+  if (A.g_guard) {  // no guards yet for this block's queries beyond its cache slots (only this block ever touches them)
+    const QShare sh0 = lm_partition(A, (int)blockIdx.x, (int)gridDim.x);
+    for (int L = LM_QCAP + tid; L < sh0.size(); L += LM_THREADS)
+      A.g_guard[(size_t)sh0.qi(L, A.nq[0]) * LM_GUARD_STRIDE + LM_CACHE_CAND + 3] = make_float4(0.f, 0.f, 0.f, 0.f);  // cnt = 0
+  }
   if (tid == 0) {
     const float pose6[6] = {p0, p1, p2, p3, p4, p5};
     lm_begin_state(&s_st, A.mst[0], A.mst[1], A.prm, pose6);
