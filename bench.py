@@ -640,7 +640,10 @@ def run_next_rows(with_cpu):
         out["f1_solve_normal_eq"] = {"rows": 1500, "gpu_3dof": p50(lambda: h.solve_normal_eq(rows, b, 0b010101, 0, 10.0)),
                                      "gpu_6dof": p50(lambda: h.solve_normal_eq(rows, b, 0b111111, 0, 10.0))}
         if hasattr(h, "fa_update_transformation"):
-            out["f1_f3_fa_update_transformation"] = run_fa_loop_row(h, fa, tc, p50, with_cpu)
+            out["f1_f3_fa_update_transformation"] = run_fa_loop_row(h, fa, np.zeros(6, np.float32), p50, with_cpu)
+            # the same call from a poor initial guess: both loops run tens of iterations, the surf loop's search iterations
+            # (1.4 k feature points against 5.5 k) included
+            out["f1_f3_fa_update_transformation_far"] = run_fa_loop_row(h, fa, np.array([0.01, -0.012, 0.008, 0.15, -0.05, 0.5], np.float32), p50, with_cpu)
     if with_cpu:
         import orc
         orc.build()
@@ -660,12 +663,12 @@ def run_next_rows(with_cpu):
     return out
 
 
-def run_fa_loop_row(h, fa, tc, p50, with_cpu):
+def run_fa_loop_row(h, fa, t0, p50, with_cpu):
     """f-1 + f-3 as ONE device-resident call: FeatureAssociation::updateTransformation (featureAssociation.cpp:2505-2535)."""
     cs, cl = fa["corner"]["_inputs"]
     ss, sl = fa["surf"]["_inputs"]
-    t0 = np.zeros(6, np.float32)
     out = {"gpu": p50(lambda: h.fa_update_transformation(cs, ss, t0), n=30, warm=4)}
+    h.fa_reset_state()
     res = h.fa_update_transformation(cs, ss, t0)
     out["iterations"] = [int(res["iters_surf"]), int(res["iters_corner"])]
     if with_cpu:

@@ -2239,9 +2239,16 @@ int ll_fa_update_transformation(ll_handle h, const void* corner_sharp, size_t n_
     h->fa_state_init = false;
   }
   // a co-resident grid: one block per SM at most, and no more blocks than feature points are worth
-  int per_sm = 0;
-  LL_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fa_loop_kernel, FAL_THREADS, 0));
-  if (per_sm < 1) return fail(h, LL_ERR_CUDA, "fa_loop_kernel does not fit an SM");
+  // LLB200_FA_STAGE=1: the previous sweep's clouds are staged in shared memory by TMA bulk copies when they fit
+  // (fa_loop.cuh). Measured on B200 (profiles/r02_fa_loop_staging_ab.txt): 1476 us staged vs 1445 us from global memory
+  // through the read-only path per call of 100 iterations — the clouds are L1-resident either way and the staged variant
+  // pays for the copy and for generic loads — so the default reads global memory.
+  static const bool stage_allowed = std::getenv("LLB200_FA_STAGE") && std::atoi(std::getenv("LLB200_FA_STAGE")) == 1;
+  const size_t stage_bytes = ((size_t)std::max(h->fa_n_last[0], h->fa_n_last[1]) * 16 + 127) & ~size_t(127);
+  const bool stage = stage_allowed && stage_bytes > 0 && stage_bytes <= 200 * 1024;
+  const void* kern = stage ? reinterpret_cast<const void*>(fa_loop_kernel<true>) : reinterpret_cast<const void*>(fa_loop_kernel<false>);
+  const size_t dyn_smem = stage ? stage_bytes : 0;
+  if (stage) LL_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
   int blocks = h->num_sms;
   if (h->prm.lm_max_blocks > 0) blocks = std::min(blocks, h->prm.lm_max_blocks);
   const size_t nq_max = std::max(n_corner, n_surf);
@@ -2291,8 +2298,7 @@ int ll_fa_update_transformation(ll_handle h, const void* corner_sharp, size_t n_
   h->scan_seq++;
   if (trace) LL_CUDA(h, cudaMemsetAsync(w + off_trace, 0, 2 * FAL_MAX_ITERS * 4 * sizeof(float), h->stream));
   void* args[] = {&A, &bar, &bar_clear};
-  LL_CUDA(h, cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(fa_loop_kernel), dim3((unsigned)blocks), dim3(FAL_THREADS),
-                                         args, 0, h->stream));
+  LL_CUDA(h, cudaLaunchCooperativeKernel(kern, dim3((unsigned)blocks), dim3(FAL_THREADS), args, dyn_smem, h->stream));
   LL_LAUNCHED(h);
   if (trace) LL_CUDA(h, cudaMemcpyAsync(trace, w + off_trace, 2 * FAL_MAX_ITERS * 4 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
   LL_CUDA(h, cudaStreamSynchronize(h->stream));  // the kernel wrote its state straight into the pinned mirror

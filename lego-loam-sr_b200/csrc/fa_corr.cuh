@@ -65,7 +65,14 @@ __device__ __forceinline__ float fa_sqdist(const float4 a, const float4 p) {
 // backward walk. The same result in warp-wide steps: 32 points per step in walking order, a ballot finds the first
 // stopping point, every lane keeps its own first strict minimum, and the warp takes the minimum by (d2, walking
 // index) — the first of the smallest, which replaces the carried minimum only if strictly smaller.
-template <bool kForward>
+// Loads of the previous sweep's cloud: the read-only global path, or plain loads when the cloud was staged in shared memory.
+template <bool kSmem>
+__device__ __forceinline__ float4 fa_ld(const float4* p) {
+  if constexpr (kSmem) return *p;
+  else return __ldg(p);
+}
+
+template <bool kForward, bool kSmem = false>
 __device__ __forceinline__ void fa_window_scan(const FaArgs& A, const float4 sel, const int closest, const int scan,
                                                const int lane, float& d2min, int& min2, float& d3min, int& min3) {
   // forward bound by the QUERY count (:1599, :1742 — an upstream quirk, clamped to the cloud)
@@ -78,7 +85,7 @@ __device__ __forceinline__ void fa_window_scan(const FaArgs& A, const float4 sel
     float d = 0.f;
     int sj = 0;
     if (in) {
-      const float4 m = __ldg(A.last + (kForward ? closest + 1 + e : closest - 1 - e));
+      const float4 m = fa_ld<kSmem>(A.last + (kForward ? closest + 1 + e : closest - 1 - e));
       sj = (int)m.w;
       stop = kForward ? ((double)sj > (double)scan + 2.5) : ((double)sj < (double)scan - 2.5);
       d = fa_sqdist(m, sel);
@@ -118,6 +125,7 @@ __device__ __forceinline__ void fa_window_scan(const FaArgs& A, const float4 sel
 
 // The search of one feature point by one warp (every fifth iteration): nearestKSearch(pointSel, 1) over the previous
 // sweep's cloud, then the two ring-window walks. All 32 lanes; the results are warp-uniform.
+template <bool kSmem = false>
 __device__ __forceinline__ void fa_search_warp(const FaArgs& A, const float4 sel, const int lane, int& closest, int& min2,
                                                int& min3) {
   closest = -1;
@@ -138,33 +146,35 @@ __device__ __forceinline__ void fa_search_warp(const FaArgs& A, const float4 sel
   };
   int j = lane;
   for (; j + 96 < A.n_last; j += 128) {  // four loads in flight, candidates taken in ascending index order
-    const float4 m0 = __ldg(A.last + j), m1 = __ldg(A.last + j + 32), m2 = __ldg(A.last + j + 64), m3 = __ldg(A.last + j + 96);
+    const float4 m0 = fa_ld<kSmem>(A.last + j), m1 = fa_ld<kSmem>(A.last + j + 32), m2 = fa_ld<kSmem>(A.last + j + 64),
+                 m3 = fa_ld<kSmem>(A.last + j + 96);
     consider(m0, j);
     consider(m1, j + 32);
     consider(m2, j + 64);
     consider(m3, j + 96);
   }
-  for (; j < A.n_last; j += 32) consider(__ldg(A.last + j), j);
+  for (; j < A.n_last; j += 32) consider(fa_ld<kSmem>(A.last + j), j);
   const uint32_t md = __reduce_min_sync(0xffffffffu, bd);
   const uint32_t mj = __reduce_min_sync(0xffffffffu, bd == md ? bj : 0xffffffffu);
   if (mj != 0xffffffffu && __uint_as_float(md) < A.dist_sqr) {  // (warp-uniform)
     closest = (int)mj;
-    const int scan = (int)__ldg(A.last + closest).w;
+    const int scan = (int)fa_ld<kSmem>(A.last + closest).w;
     float d2min = A.dist_sqr, d3min = A.dist_sqr;
-    fa_window_scan<true>(A, sel, closest, scan, lane, d2min, min2, d3min, min3);
-    fa_window_scan<false>(A, sel, closest, scan, lane, d2min, min2, d3min, min3);
+    fa_window_scan<true, kSmem>(A, sel, closest, scan, lane, d2min, min2, d3min, min3);
+    fa_window_scan<false, kSmem>(A, sel, closest, scan, lane, d2min, min2, d3min, min3);
   }
 }
 
 // The (laserCloudOri, coeffSel) pair of one feature point from its tripod (:1644-1693 corner, :1785-1840 surf), one
 // thread. Returns 1 when the pair is pushed (c = the coeffSel record), 0 otherwise (c = 0).
+template <bool kSmem = false>
 __device__ __forceinline__ int fa_record(const FaArgs& A, const float4 sel, const int closest, const int min2, const int min3,
                                          float (&c)[4]) {
   c[0] = c[1] = c[2] = c[3] = 0.f;
   int kp = 0;
   if (A.which == 0) {
     if (min2 >= 0) {
-      const float4 t1 = __ldg(A.last + closest), t2 = __ldg(A.last + min2);
+      const float4 t1 = fa_ld<kSmem>(A.last + closest), t2 = fa_ld<kSmem>(A.last + min2);
       const float x0 = sel.x, y0 = sel.y, z0 = sel.z, x1 = t1.x, y1 = t1.y, z1 = t1.z, x2 = t2.x, y2 = t2.y, z2 = t2.z;
       const float m11 = ((x0 - x1) * (y0 - y2) - (x0 - x2) * (y0 - y1));
       const float m22 = ((x0 - x1) * (z0 - z2) - (x0 - x2) * (z0 - z1));
@@ -183,7 +193,7 @@ __device__ __forceinline__ int fa_record(const FaArgs& A, const float4 sel, cons
       }
     }
   } else if (min2 >= 0 && min3 >= 0) {
-    const float4 t1 = __ldg(A.last + closest), t2 = __ldg(A.last + min2), t3 = __ldg(A.last + min3);
+    const float4 t1 = fa_ld<kSmem>(A.last + closest), t2 = fa_ld<kSmem>(A.last + min2), t3 = fa_ld<kSmem>(A.last + min3);
     float pa = (t2.y - t1.y) * (t3.z - t1.z) - (t3.y - t1.y) * (t2.z - t1.z);
     float pb = (t2.z - t1.z) * (t3.x - t1.x) - (t3.z - t1.z) * (t2.x - t1.x);
     float pc = (t2.x - t1.x) * (t3.y - t1.y) - (t3.x - t1.x) * (t2.y - t1.y);

@@ -163,8 +163,44 @@ __device__ __forceinline__ bool fa_apply(int which, const float* x, float* tc) {
   return (double)deltaR < 0.1 && (double)deltaT < 0.1;
 }
 
+// ---- staging of the previous sweep's cloud: a regular, contiguous tile that every block reads in full at every search
+// iteration — the case BASELINE.json's north_star names for TMA bulk copies. One thread arms an mbarrier with the byte count
+// and issues cp.async.bulk (global -> shared, completion counted on the mbarrier); everybody waits on the phase bit.
+__device__ __forceinline__ uint32_t fal_smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void fal_mbar_init(uint64_t* mbar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(fal_smem_addr(mbar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fal_stage_issue(float4* dst, const float4* src, uint32_t bytes, uint64_t* mbar) {
+  // generic-proxy accesses of the destination (the other cloud was read from it) are ordered before the async-proxy writes
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fal_smem_addr(mbar)), "r"(bytes) : "memory");
+  constexpr uint32_t kChunk = 65536;
+  for (uint32_t off = 0; off < bytes; off += kChunk) {
+    const uint32_t n = min(kChunk, bytes - off);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+                     "r"(fal_smem_addr(reinterpret_cast<const char*>(dst) + off)), "l"(reinterpret_cast<const char*>(src) + off), "r"(n),
+                 "r"(fal_smem_addr(mbar))
+                 : "memory");
+  }
+}
+__device__ __forceinline__ void fal_mbar_wait(uint64_t* mbar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@!p bra WAIT_%=;\n"
+      "}\n" ::"r"(fal_smem_addr(mbar)),
+      "r"(parity)
+      : "memory");
+}
+
+template <bool kStage>
 __global__ void __launch_bounds__(FAL_THREADS) fa_loop_kernel(const __grid_constant__ FaLoopArgs A, unsigned* barrier,
                                                               unsigned* barrier_clear) {
+  extern __shared__ __align__(128) unsigned char s_stage[];  // kStage: the cloud of the loop in progress
+  __shared__ __align__(8) uint64_t s_mbar;
   __shared__ FaLoopState s_st;
   __shared__ FaRowConst s_k;
   __shared__ double s_w[FAL_WARPS][FAL_NSUM];
@@ -186,11 +222,18 @@ __global__ void __launch_bounds__(FAL_THREADS) fa_loop_kernel(const __grid_const
     s_st.iters[0] = s_st.iters[1] = 0;
     s_st.n_sel[0] = s_st.n_sel[1] = 0;
   }
+  if (kStage && tid == 0) fal_mbar_init(&s_mbar, 1);
   for (int loop = 0; loop < 2 && !guard; ++loop) {
     const int which = loop == 0 ? 1 : 0;
     FaArgs F;
     F.q = A.q[which];
     F.last = A.last[which];
+    if constexpr (kStage) {
+      __syncthreads();  // (the mbarrier is initialised; nobody reads the previous loop's cloud any more)
+      if (tid == 0) fal_stage_issue(reinterpret_cast<float4*>(s_stage), A.last[which], (uint32_t)A.n_last[which] * 16u, &s_mbar);
+      fal_mbar_wait(&s_mbar, (uint32_t)(loop & 1));
+      F.last = reinterpret_cast<const float4*>(s_stage);
+    }
     F.nq = A.nq[which];
     F.n_last = A.n_last[which];
     F.which = which;
@@ -218,13 +261,13 @@ __global__ void __launch_bounds__(FAL_THREADS) fa_loop_kernel(const __grid_const
           const float4 p = __ldg(F.q + i);
           const float4 sel = fa_transform_to_start(p, F.tc);
           int closest, min2, min3;
-          fa_search_warp(F, sel, lane, closest, min2, min3);
+          fa_search_warp<kStage>(F, sel, lane, closest, min2, min3);
           if (lane == 0) {
             F.ind1[i] = closest;
             F.ind2[i] = min2;
             F.ind3[i] = min3;
             float c[4], r[3], b;
-            if (fa_record(F, sel, closest, min2, min3, c)) {
+            if (fa_record<kStage>(F, sel, closest, min2, min3, c)) {
               fa_row(s_k, which, p, c, r, b);
               fa_accumulate(r, b, acc);
             }
@@ -237,7 +280,7 @@ __global__ void __launch_bounds__(FAL_THREADS) fa_loop_kernel(const __grid_const
           const float4 sel = fa_transform_to_start(p, F.tc);
           const int closest = __ldcg(F.ind1 + i), min2 = __ldcg(F.ind2 + i), min3 = __ldcg(F.ind3 + i);
           float c[4], r[3], b;
-          if (fa_record(F, sel, closest, min2, min3, c)) {
+          if (fa_record<kStage>(F, sel, closest, min2, min3, c)) {
             fa_row(s_k, which, p, c, r, b);
             fa_accumulate(r, b, acc);
           }

@@ -940,14 +940,14 @@ __device__ __noinline__ void knn_cache_fill(const float4* sorted, int my_start, 
   const uint32_t lt_mask = (1u << lane) - 1u;
   // the radius set must fit 32 points: a dense neighbourhood gets a second try with a thinner shell around d5
 #pragma unroll 1
-  for (int attempt = 0; attempt < 2; ++attempt) {
+  for (int attempt = 0; attempt < 3; ++attempt) {
     const float margin = attempt == 0 ? LM_CACHE_MARGIN : 0.3f * LM_CACHE_MARGIN;
     // (R may exceed 1 m — a fifth neighbour near the acceptance limit, or a rejected query: the set is then only usable
     //  while the query stays in its cell, knn5_thread.) In a dense map — un-downsampled: the fifth neighbour centimetres
     //  away — a quarter of a metre around it holds hundreds of points, so the radius is also bounded relative to d5: with
-    //  N(r) ~ r^2..r^3 a factor 1.7 (then 1.3) keeps the set near 20 points, still far more margin than a query moves.
+    //  N(r) ~ r^2..r^3 a factor 1.7 (then 1.3, then 1.1) keeps the set near 20 points, still far more margin than a query moves.
     const float s5 = rejected ? 0.f : sqrtf(__uint_as_float(d5bits));
-    const float R = whole ? -1.f : (rejected ? 1.0f + margin : fminf(s5 + margin, (attempt == 0 ? 1.7f : 1.3f) * s5 + 0.004f));
+    const float R = whole ? -1.f : (rejected ? 1.0f + margin : fminf(s5 + margin, (attempt == 0 ? 1.7f : (attempt == 1 ? 1.3f : 1.1f)) * s5 + 0.004f));
     const float R2 = R * R;
     int base = 0;
     uint32_t members = 0u, d6 = LM_EMPTY_D2;  // positions of the five neighbours in the set; nearest point that is not one of them
@@ -973,11 +973,13 @@ __device__ __noinline__ void knn_cache_fill(const float4* sorted, int my_start, 
       base += __popc(bal);
       // one of the five found by the search <=> (d2, index) <= the fifth's
       const bool member = have && d5bits != LM_EMPTY_D2 && !pair_less(d5bits, i5bits, __float_as_uint(d), __float_as_uint(m.w));
-      members |= __reduce_or_sync(0xffffffffu, (member && in && pos < LM_CACHE_CAND) ? (1u << pos) : 0u);
-      d6 = min(d6, __reduce_min_sync(0xffffffffu, (have && !member) ? __float_as_uint(d) : LM_EMPTY_D2));
+      members |= (member && in && pos < LM_CACHE_CAND) ? (1u << pos) : 0u;   // (per lane: reduced after the loop)
+      d6 = min(d6, (have && !member) ? __float_as_uint(d) : LM_EMPTY_D2);
     }
+    members = __reduce_or_sync(0xffffffffu, members);
+    d6 = __reduce_min_sync(0xffffffffu, d6);
     const bool fits = whole || (base <= LM_CACHE_CAND && (rejected || base >= 5));
-    if (fits || attempt == 1) {
+    if (fits || attempt == 2) {
       if (lane == 0) {
         *center = make_float4(sx, sy, sz, R);
         // (an EMPTY cell-complete set is stored as count 33: cnt must be > 0 to be used, and no lane is below 33 <= 32)
@@ -1448,24 +1450,36 @@ __device__ void reduce_partials_and_solve(const float* partials, int nblocks, co
   lm_solve_block<kEigenMode>(s_red, prm, S, stage_mode);
 }
 
-// Block b's share of the queries: an equal slice of the corner list AND an equal slice of the surf list (local order:
-// the corner slice, then the surf slice). Every block then runs one warp's worth of line fits (closed-form eigen solve in
-// double, the slowest piece of phase 2) beside its plane fits, and the corner queries in dense parts of the corner map
-// (hundreds of candidates each) are spread over all blocks instead of making a few blocks the stragglers of every
-// iteration's grid barrier.
+// Block b's share of the queries: groups of LM_QGROUP consecutive corner queries dealt round-robin to the blocks, and the
+// same for the surf queries (local order: the corner queries, then the surf queries). Neighbouring queries of a scan fall
+// into map regions of similar density: contiguous per-block slices made a few blocks the stragglers of every iteration's
+// grid barrier on a dense map (configs[3], hundreds of candidates per query: first arrival -> last arrival 500 us of a
+// 780 us iteration), while dealing single queries gives up the L1 / L2 locality of neighbouring queries' candidate rows
+// (+1.6 % on the VLP-16 replay). Every block also runs one warp's worth of line fits (closed-form eigen solve in double,
+// the slowest piece of phase 2) beside its plane fits.
+constexpr int LM_QGROUP = 16;
 struct QShare {
-  int c_begin, c_end, s_begin, s_end;
-  __device__ __forceinline__ int ncb() const { return c_end - c_begin; }
-  __device__ __forceinline__ int size() const { return (c_end - c_begin) + (s_end - s_begin); }
-  // local index L -> (map, index in the concatenated query list: corner queries first)
-  __device__ __forceinline__ int qi(int L, int nq0) const { return L < ncb() ? c_begin + L : nq0 + s_begin + (L - ncb()); }
+  int b, nb, n_c, n_s;
+  __device__ __forceinline__ int ncb() const { return n_c; }
+  __device__ __forceinline__ int size() const { return n_c + n_s; }
+  __device__ __forceinline__ int deal(int L) const { return ((L / LM_QGROUP) * nb + b) * LM_QGROUP + (L % LM_QGROUP); }
+  // local index L -> index in the concatenated query list (corner queries first)
+  __device__ __forceinline__ int qi(int L, int nq0) const { return L < n_c ? deal(L) : nq0 + deal(L - n_c); }
 };
+// queries of a list of n that block b of nb owns
+__device__ __forceinline__ int lm_share_count(int n, int b, int nb) {
+  const int groups = (n + LM_QGROUP - 1) / LM_QGROUP;              // the last one may be partial
+  if (groups <= b) return 0;
+  const int mine = (groups - b + nb - 1) / nb;                     // groups b, b + nb, ...
+  const bool owns_last = (groups - 1 - b) % nb == 0;
+  return mine * LM_QGROUP - (owns_last ? groups * LM_QGROUP - n : 0);
+}
 __device__ __forceinline__ QShare lm_partition(const LMArgs& A, int b, int nb) {
   QShare sh;
-  sh.c_begin = (int)(((long long)A.nq[0] * b) / nb);
-  sh.c_end = (int)(((long long)A.nq[0] * (b + 1)) / nb);
-  sh.s_begin = (int)(((long long)A.nq[1] * b) / nb);
-  sh.s_end = (int)(((long long)A.nq[1] * (b + 1)) / nb);
+  sh.b = b;
+  sh.nb = nb;
+  sh.n_c = lm_share_count(A.nq[0], b, nb);
+  sh.n_s = lm_share_count(A.nq[1], b, nb);
   return sh;
 }
 
