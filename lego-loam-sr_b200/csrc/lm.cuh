@@ -940,7 +940,7 @@ __device__ __noinline__ void knn_cache_fill(const float4* sorted, int my_start, 
   const uint32_t lt_mask = (1u << lane) - 1u;
   // the radius set must fit 32 points: a dense neighbourhood gets a second try with a thinner shell around d5
 #pragma unroll 1
-  for (int attempt = 0; attempt < 3; ++attempt) {
+  for (int attempt = (total > 256 && !rejected) ? 1 : 0; attempt < 3; ++attempt) {
     const float margin = attempt == 0 ? LM_CACHE_MARGIN : 0.3f * LM_CACHE_MARGIN;
     // (R may exceed 1 m — a fifth neighbour near the acceptance limit, or a rejected query: the set is then only usable
     //  while the query stays in its cell, knn5_thread.) In a dense map — un-downsampled: the fifth neighbour centimetres
@@ -951,30 +951,43 @@ __device__ __noinline__ void knn_cache_fill(const float4* sorted, int my_start, 
     const float R2 = R * R;
     int base = 0;
     uint32_t members = 0u, d6 = LM_EMPTY_D2;  // positions of the five neighbours in the set; nearest point that is not one of them
+    // four candidate loads in flight per lane (the loop is otherwise one exposed L1 / L2 latency per 32 candidates: a dense
+    // map's 600-candidate query spent more time here than in its search)
 #pragma unroll 1
-    for (int j0 = 0; j0 < total && base <= LM_CACHE_CAND; j0 += 32) {
-      const int j = j0 + lane;
-      int b = bs[0];
+    for (int j0 = 0; j0 < total && base <= LM_CACHE_CAND; j0 += 128) {
+      float4 mv[4];
+      bool hv[4];
 #pragma unroll
-      for (int k = 1; k < 9; ++k)
-        if (j >= pr[k]) b = bs[k];
-      const bool have = j < total;
-      const float4 m = have ? map_ld<kFresh>(&sorted[j + b]) : make_float4(0.f, 0.f, 0.f, 0.f);
-      float df = sx - m.x;
-      float d = df * df;
-      df = sy - m.y;
-      d += df * df;
-      df = sz - m.z;
-      d += df * df;
-      const bool in = have && (whole || d <= R2);
-      const unsigned bal = __ballot_sync(0xffffffffu, in);
-      const int pos = base + __popc(bal & lt_mask);
-      if (in && pos < LM_CACHE_CAND) cand[pos] = m;
-      base += __popc(bal);
-      // one of the five found by the search <=> (d2, index) <= the fifth's
-      const bool member = have && d5bits != LM_EMPTY_D2 && !pair_less(d5bits, i5bits, __float_as_uint(d), __float_as_uint(m.w));
-      members |= (member && in && pos < LM_CACHE_CAND) ? (1u << pos) : 0u;   // (per lane: reduced after the loop)
-      d6 = min(d6, (have && !member) ? __float_as_uint(d) : LM_EMPTY_D2);
+      for (int u = 0; u < 4; ++u) {
+        const int j = j0 + 32 * u + lane;
+        int b = bs[0];
+#pragma unroll
+        for (int k = 1; k < 9; ++k)
+          if (j >= pr[k]) b = bs[k];
+        hv[u] = j < total;
+        mv[u] = hv[u] ? map_ld<kFresh>(&sorted[j + b]) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (j0 + 32 * u >= total) break;  // warp-uniform
+        const bool have = hv[u];
+        const float4 m = mv[u];
+        float df = sx - m.x;
+        float d = df * df;
+        df = sy - m.y;
+        d += df * df;
+        df = sz - m.z;
+        d += df * df;
+        const bool in = have && (whole || d <= R2);
+        const unsigned bal = __ballot_sync(0xffffffffu, in);
+        const int pos = base + __popc(bal & lt_mask);
+        if (in && pos < LM_CACHE_CAND) cand[pos] = m;
+        base += __popc(bal);
+        // one of the five found by the search <=> (d2, index) <= the fifth's
+        const bool member = have && d5bits != LM_EMPTY_D2 && !pair_less(d5bits, i5bits, __float_as_uint(d), __float_as_uint(m.w));
+        members |= (member && in && pos < LM_CACHE_CAND) ? (1u << pos) : 0u;   // (per lane: reduced after the loop)
+        d6 = min(d6, (have && !member) ? __float_as_uint(d) : LM_EMPTY_D2);
+      }
     }
     members = __reduce_or_sync(0xffffffffu, members);
     d6 = __reduce_min_sync(0xffffffffu, d6);
