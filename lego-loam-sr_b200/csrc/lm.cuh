@@ -614,17 +614,34 @@ __device__ __forceinline__ void knn5_chunks(const float4* sorted, int my_start, 
   constexpr int kRowLane[9] = {12, 3, 9, 15, 21, 0, 6, 18, 24};
   int pr[9], bs[9];
   int total = 0;
+  // Row pruning (dense maps: hundreds of candidates in the 27 cells, the five nearest within centimetres): once the chunks
+  // before j0_begin have left a fifth-best distance, a row of cells whose nearest possible point — by its (y, z) cell
+  // offsets and the query's position inside its own cell — is farther than that cannot contribute, and its candidates
+  // are never loaded. The margin keeps rounding (3 ulp on a float-evaluated d2) and exact ties out of the argument.
+  const float fy = sy - floorf(sy), fz = sz - floorf(sz);
+  const bool prune = j0_begin > 0 && K.d2[4] != LM_EMPTY_D2;
+  const float bound = __uint_as_float(K.d2[4]) * 1.00001f + 1e-12f;
+  int consumed = j0_begin;  // candidates of the un-pruned concatenation the earlier chunks have taken
 #pragma unroll
   for (int k = 0; k < 9; ++k) {
-    const int st = __shfl_sync(0xffffffffu, my_start, kRowLane[k]);
-    const int cn = __shfl_sync(0xffffffffu, my_count, kRowLane[k]);
+    int st = __shfl_sync(0xffffffffu, my_start, kRowLane[k]);
+    int cn = __shfl_sync(0xffffffffu, my_count, kRowLane[k]);
+    const int used = min(consumed, cn);  // this row's share of what is already done (rows are taken in this order)
+    consumed -= used;
+    st += used;
+    cn -= used;
+    if (prune) {
+      const int oy = (kRowLane[k] / 3) % 3 - 1, oz = kRowLane[k] / 9 - 1;
+      const float dy = oy == 0 ? 0.f : (oy < 0 ? fy : 1.f - fy), dz = oz == 0 ? 0.f : (oz < 0 ? fz : 1.f - fz);
+      if (dy * dy + dz * dz > bound) cn = 0;
+    }
     pr[k] = total;
     bs[k] = st - total;
     total += cn;
   }
   const uint32_t max_bits = __float_as_uint(max_sq_dist);
-  for (int j0 = j0_begin; j0 < total; j0 += 32 * LM_CAND_UNROLL) {
-    const bool first = j0 == 0;
+  for (int j0 = 0; j0 < total; j0 += 32 * LM_CAND_UNROLL) {
+    const bool first = j0 == 0 && j0_begin == 0;  // nothing carried yet
     int srcs[LM_CAND_UNROLL];
     float4 ms[LM_CAND_UNROLL];
 #pragma unroll
@@ -932,6 +949,7 @@ __device__ __noinline__ void knn_cache_fill(const float4* sorted, int my_start, 
     *t1 = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   const bool whole = total <= LM_CACHE_CAND;
+  const bool heavy = total > 32 * LM_CAND_UNROLL;
   // A query REJECTED in a dense neighbourhood (fewer than five points within 1 m, many beyond) keeps the points within
   // 1 m + margin of it: while it stays in its one-metre cell (so that the 27 cells still hold every point within 1 m of it)
   // and moves less than the margin, every point within 1 m of it is in that set, and the acceptance test and — should it
@@ -939,8 +957,9 @@ __device__ __noinline__ void knn_cache_fill(const float4* sorted, int my_start, 
   const bool rejected = !whole && d5bits == LM_EMPTY_D2;
   const uint32_t lt_mask = (1u << lane) - 1u;
   // the radius set must fit 32 points: a dense neighbourhood gets a second try with a thinner shell around d5
+  const int first_attempt = (total > 256 && !rejected) ? 1 : 0;
 #pragma unroll 1
-  for (int attempt = (total > 256 && !rejected) ? 1 : 0; attempt < 3; ++attempt) {
+  for (int attempt = first_attempt; attempt < 3; ++attempt) {
     const float margin = attempt == 0 ? LM_CACHE_MARGIN : 0.3f * LM_CACHE_MARGIN;
     // (R may exceed 1 m — a fifth neighbour near the acceptance limit, or a rejected query: the set is then only usable
     //  while the query stays in its cell, knn5_thread.) In a dense map — un-downsampled: the fifth neighbour centimetres
@@ -951,6 +970,27 @@ __device__ __noinline__ void knn_cache_fill(const float4* sorted, int my_start, 
     const float R2 = R * R;
     int base = 0;
     uint32_t members = 0u, d6 = LM_EMPTY_D2;  // positions of the five neighbours in the set; nearest point that is not one of them
+    // rows of cells that lie entirely beyond R hold no point of the set: they are not read, and the nearest point one of
+    // them could hold bounds d6 from below (conservative: the guard only gets tighter)
+    if (heavy) {  // (only where it pays: a sparse neighbourhood's few dozen candidates are read faster than tested)
+      const float fy = sy - floorf(sy), fz = sz - floorf(sz);
+      total = 0;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) {
+        const int st = __shfl_sync(0xffffffffu, my_start, kRowLane[k]);
+        int cn = __shfl_sync(0xffffffffu, my_count, kRowLane[k]);
+        const int oy = (kRowLane[k] / 3) % 3 - 1, oz = kRowLane[k] / 9 - 1;
+        const float dy = oy == 0 ? 0.f : (oy < 0 ? fy : 1.f - fy), dz = oz == 0 ? 0.f : (oz < 0 ? fz : 1.f - fz);
+        const float rowmin2 = dy * dy + dz * dz;
+        if (cn > 0 && rowmin2 * 0.99999f > R2 + 1e-12f) {
+          d6 = min(d6, __float_as_uint(rowmin2 * 0.99999f));
+          cn = 0;
+        }
+        pr[k] = total;
+        bs[k] = st - total;
+        total += cn;
+      }
+    }
     // four candidate loads in flight per lane (the loop is otherwise one exposed L1 / L2 latency per 32 candidates: a dense
     // map's 600-candidate query spent more time here than in its search)
 #pragma unroll 1
