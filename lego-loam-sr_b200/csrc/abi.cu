@@ -32,7 +32,7 @@ using namespace ll;
 namespace {
 
 constexpr size_t kArenaChunk = 256ull << 20;  // keyframe store grows in 256 MiB slabs (~1000 VLP-16 keyframes each)
-constexpr int kIncPlanMaxRun = 4096;         // largest keyframe cloud (points per map) the incremental map assembly is chosen for
+constexpr double kIncRankBudget = 1.5e6;     // comparisons per block the incremental map assembly may spend ranking a run
 constexpr int kCellCap = 1 << 24;            // 16.7 M one-metre cells per search grid (<= 24 key bits: 3 sort passes)
 constexpr int kGridPasses = 3;
 constexpr size_t kSpeculativeD2HBytes = 256u << 10;  // ll_voxel_downsample: copy all n output slots before n_ds is known
@@ -693,7 +693,8 @@ int plan_incremental(ll_handle h, const int* ids, int n_ids, bool* used) {
     removed.clear();
     n_kept = 0;
   }
-  // group the appended keyframes: <= INC_RUN_MAX points per map and <= INC_MAX_SEGS / 3 keyframes per merge
+  // group the appended keyframes: <= run_cap points per map and <= INC_MAX_SEGS / 3 keyframes per merge
+  const int run_cap = std::min<long>(INC_RUN_MAX, (long)std::sqrt(kIncRankBudget * (double)blocks_for_inc(h)));
   struct Step { std::vector<int> add; std::vector<int> dead; };
   std::vector<Step> steps;
   {
@@ -702,15 +703,14 @@ int plan_incremental(ll_handle h, const int* ids, int n_ids, bool* used) {
     for (int k = n_kept; k < n_ids; ++k) {
       const Keyframe& kf = h->kfs[ids[k]];
       const int c = kf.n[0], sfo = kf.n[1] + kf.n[2];
-      // A keyframe too large for one run takes the full path — and so does one whose run is large enough that sorting
-      // it costs more than the full rebuild saves: the run is sorted by ONE block (a bitonic network in shared memory,
-      // measured 92 us for 10 k points padded to 16 k, ~12 us for 4 k), while the full path's three radix passes over a
-      // 0.6 M-point window take ~55 us once the cell tables need no clearing (profiles/r02_scan_barrier_timeline.txt).
-      if (c > INC_RUN_MAX || sfo > INC_RUN_MAX || c > kIncPlanMaxRun || sfo > kIncPlanMaxRun) {
+      // A keyframe too large for one run takes the full path — and so does one whose run costs more to rank than the
+      // full rebuild saves: the run is ranked by counting, n^2 / blocks comparisons (map_incremental.cuh: ~6 us for 10 k
+      // points on 148 blocks), so a scan kernel on a few SMs (batched replay) only takes small keyframes this way.
+      if (c > run_cap || sfo > run_cap) {
         window_invalidate(h);
         return LL_OK;
       }
-      if (!cur.add.empty() && (pc + c > INC_RUN_MAX || ps + sfo > INC_RUN_MAX || (int)cur.add.size() >= INC_MAX_SEGS / 3)) {
+      if (!cur.add.empty() && (pc + c > run_cap || ps + sfo > run_cap || (int)cur.add.size() >= INC_MAX_SEGS / 3)) {
         steps.push_back(cur);
         cur = Step();
         pc = ps = 0;

@@ -125,26 +125,32 @@ __device__ __forceinline__ bool inc_alive(uint32_t tag, const IncJob& J) {
   return alive;
 }
 
-// ---- R: the run of the added keyframes of map m, by ONE block. smem: INC_RUN_MAX u64.
+// ---- R: the run of the added keyframes of map m = their points sorted by (voxel key, arrival order), by ALL blocks.
+// A sorting network in one block's shared memory took 92 us for a 10 k-point keyframe (profiles/r02_*): the run is instead
+// RANKED. Every block transforms all the added points itself (a few thousand: cheaper than a grid barrier between a
+// transform stage and a sort stage) and keeps their 64-bit composites (voxel index relative to the run's own box, arrival
+// index: unique, so the order is the stable one) in shared memory; it then owns a contiguous slice of the points and
+// counts, for each of them, the composites below its own — four points per pass over the keys, one warp per four points —
+// which is its position in the run. n^2 / blocks comparisons: ~6 us for 10 k points on 148 blocks; the host takes the
+// full path when that budget is exceeded (few blocks, abi.cu). smem: INC_RUN_MAX u64.
 __device__ __forceinline__ void inc_build_run(const IncJob& J, const MapBatch& B, int m, unsigned long long* s_key) {
   const WindowBuffers& W = J.w[m];
   const MapBuffers& M = B.m[m];
-  const int tid = threadIdx.x, n = J.n_new[m];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5, n = J.n_new[m];
   __shared__ int s_mn[3], s_mx[3], s_bad;
+  __syncthreads();  // (the previous map's pass is over: its keys and box may be overwritten)
   if (tid < 3) { s_mn[tid] = 0x7fffffff; s_mx[tid] = (int)0x80000000; }
   if (tid == 0) s_bad = 0;
   __syncthreads();
-  // transformPointCloud (:649-664) of every added cloud, in list order
+  const float inv = M.inv_leaf;
+  // pass 1: the box of the run in voxel coordinates (transformPointCloud :649-664 of every added cloud, in list order)
   for (int sg = 0; sg < J.n_segs; ++sg) {
     const Segment& g = J.segs[sg];
     if (g.map != m) continue;
     for (int i = tid; i < g.count; i += blockDim.x) {
-      const float4 p = ld_stream(g.src + i);
+      const float4 p = __ldg(g.src + i);
       const float4 q = g.identity ? p : rigid_transform(g.t, p);
-      W.stage_pts[g.dst_off + i] = q;
-      W.stage_tag[g.dst_off + i] = (uint32_t)g.pad[0];
       if (finite3(q)) {
-        const float inv = M.inv_leaf;
         const float f[3] = {floorf(q.x * inv), floorf(q.y * inv), floorf(q.z * inv)};
         if (fabsf(f[0]) < 1048576.f && fabsf(f[1]) < 1048576.f && fabsf(f[2]) < 1048576.f) {
 #pragma unroll
@@ -155,57 +161,70 @@ __device__ __forceinline__ void inc_build_run(const IncJob& J, const MapBatch& B
       }
     }
   }
-  __syncthreads();  // (block-scope: the stage arrays are re-read below by other threads of this block)
+  __syncthreads();
   const long long dx = (long long)s_mx[0] - s_mn[0] + 1, dy = (long long)s_mx[1] - s_mn[1] + 1, dz = (long long)s_mx[2] - s_mn[2] + 1;
   const bool any = s_mx[0] >= s_mn[0];
-  if (any && (dx * dy * dz >= 0xffffffffLL || dx <= 0 || dy <= 0 || dz <= 0)) s_bad = 1;  // (benign race: all write 1)
-  __syncthreads();
-  if (s_bad) {
-    if (tid == 0) M.st->inc_fail = 1;
-    return;  // block-uniform
+  const bool bad = s_bad != 0 || (any && (dx * dy * dz >= 0xffffffffLL || dx <= 0 || dy <= 0 || dz <= 0));
+  if (bad) {  // (the same verdict in every block: they all looked at the same points)
+    if (tid == 0 && blockIdx.x == 0) M.st->inc_fail = 1;
+    return;
   }
-  int N = 64;
-  while (N < n) N <<= 1;
-  for (int i = tid; i < N; i += blockDim.x) {
-    unsigned long long ck = ~0ull;
-    if (i < n) {
-      const float4 q = W.stage_pts[i];
+  // pass 2: the composites of ALL added points
+  for (int sg = 0; sg < J.n_segs; ++sg) {
+    const Segment& g = J.segs[sg];
+    if (g.map != m) continue;
+    for (int i = tid; i < g.count; i += blockDim.x) {
+      const float4 p = __ldg(g.src + i);
+      const float4 q = g.identity ? p : rigid_transform(g.t, p);
       unsigned long long rel = 0xffffffffull;  // non-finite points: behind every voxel, in arrival order
       if (finite3(q)) {
-        const float inv = M.inv_leaf;
         const long long ix = (long long)(int)floorf(q.x * inv) - s_mn[0], iy = (long long)(int)floorf(q.y * inv) - s_mn[1],
                         iz = (long long)(int)floorf(q.z * inv) - s_mn[2];
         rel = (unsigned long long)((iz * dy + iy) * dx + ix);
       }
-      ck = (rel << INC_RUN_BITS) | (unsigned long long)i;  // unique => the bitonic order is the stable order
-    }
-    s_key[i] = ck;
-  }
-  for (int k = 2; k <= N; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      __syncthreads();
-      for (int t = tid; t < (N >> 1); t += blockDim.x) {
-        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-        const int l = i | j;
-        const unsigned long long a = s_key[i], b = s_key[l];
-        const bool up = (i & k) == 0;
-        if ((a > b) == up) {
-          s_key[i] = b;
-          s_key[l] = a;
-        }
-      }
+      const int e = g.dst_off + i;
+      s_key[e] = (rel << INC_RUN_BITS) | (unsigned long long)e;  // unique => the rank order is the stable order
     }
   }
   __syncthreads();
-  bool ok = true;
-  for (int jj = tid; jj < n; jj += blockDim.x) {
-    const int i = (int)(s_key[jj] & (unsigned long long)(INC_RUN_MAX - 1));
-    const float4 q = W.stage_pts[i];
-    W.run_pts[jj] = q;
-    W.run_key[jj] = inc_abs_key(q, M.inv_leaf, ok);
-    W.run_tag[jj] = W.stage_tag[i];
-  }
   static_assert(INC_RUN_MAX == (1 << INC_RUN_BITS), "the composite key keeps the arrival index in INC_RUN_BITS bits");
+  // ranks of this block's slice [lo, hi) of the added points: four points per pass over the keys, one warp per four
+  const int per = (n + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int lo = min(n, (int)blockIdx.x * per), hi = min(n, lo + per);
+  for (int e0 = lo + 4 * warp; e0 < hi; e0 += 4 * nwarps) {
+    unsigned long long ke[4];
+    int cnt[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int u = 0; u < 4; ++u) ke[u] = e0 + u < hi ? s_key[e0 + u] : 0ull;
+    for (int j = lane; j < n; j += 32) {
+      const unsigned long long k = s_key[j];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) cnt[u] += k < ke[u] ? 1 : 0;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) cnt[u] = __reduce_add_sync(0xffffffffu, cnt[u]);
+    if (lane < 4 && e0 + lane < hi) {
+      const int e = e0 + lane;
+      int rank = cnt[0];
+#pragma unroll
+      for (int u = 1; u < 4; ++u) rank = lane == u ? cnt[u] : rank;
+      // the point itself again (its cloud and offset from the segment table), to its place in the run
+      float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+      uint32_t tag = 0u;
+      for (int sg = 0; sg < J.n_segs; ++sg) {
+        const Segment& g = J.segs[sg];
+        if (g.map == m && e >= g.dst_off && e < g.dst_off + g.count) {
+          const float4 p = __ldg(g.src + (e - g.dst_off));
+          q = g.identity ? p : rigid_transform(g.t, p);
+          tag = (uint32_t)g.pad[0];
+        }
+      }
+      bool ok = true;
+      W.run_pts[rank] = q;
+      W.run_key[rank] = inc_abs_key(q, inv, ok);
+      W.run_tag[rank] = tag;
+    }
+  }
 }
 
 // ---- C: surviving entries of this worker's tile of the old window.
@@ -556,18 +575,12 @@ __device__ __forceinline__ void inc_reduce(const IncJob& J, const MapBatch& B, i
 __device__ __forceinline__ void map_incremental_inline(const IncJob& J, const MapBatch& B, unsigned* barrier, unsigned& epoch,
                                                        uint32_t* smem) {
   const int nb = (int)gridDim.x, blk = (int)blockIdx.x;
-  const bool has_run = J.n_new[0] > 0 || J.n_new[1] > 0;
-  const IncTiling T(nb, J.n_old, has_run);
+  const IncTiling T(nb, J.n_old, false);
   uint32_t* s_w = smem + INC_MERGE_SMEM_WORDS - 64;
   // ---- R | C
-  if (has_run && blk < 2 && T.first == 2) {
-    if (J.n_new[blk] > 0) inc_build_run(J, B, blk, reinterpret_cast<unsigned long long*>(smem));
-  } else if (has_run && T.first == 0 && blk == 0) {
-    for (int m = 0; m < 2; ++m) {
-      if (J.n_new[m] > 0) inc_build_run(J, B, m, reinterpret_cast<unsigned long long*>(smem));
-      __syncthreads();
-    }
-  }
+  for (int m = 0; m < 2; ++m)
+    if (J.n_new[m] > 0) inc_build_run(J, B, m, reinterpret_cast<unsigned long long*>(smem));
+  __syncthreads();
   if (blk >= T.first) {
     const int w = blk - T.first;
     if (nb - T.first < 2) {
