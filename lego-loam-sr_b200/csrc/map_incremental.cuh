@@ -143,6 +143,7 @@ __device__ __forceinline__ void inc_build_run(const IncJob& J, const MapBatch& B
   if (tid == 0) s_bad = 0;
   __syncthreads();
   const float inv = M.inv_leaf;
+  int t_mn[3] = {0x7fffffff, 0x7fffffff, 0x7fffffff}, t_mx[3] = {(int)0x80000000, (int)0x80000000, (int)0x80000000};
   // pass 1: the box of the run in voxel coordinates (transformPointCloud :649-664 of every added cloud, in list order)
   for (int sg = 0; sg < J.n_segs; ++sg) {
     const Segment& g = J.segs[sg];
@@ -154,12 +155,17 @@ __device__ __forceinline__ void inc_build_run(const IncJob& J, const MapBatch& B
         const float f[3] = {floorf(q.x * inv), floorf(q.y * inv), floorf(q.z * inv)};
         if (fabsf(f[0]) < 1048576.f && fabsf(f[1]) < 1048576.f && fabsf(f[2]) < 1048576.f) {
 #pragma unroll
-          for (int a = 0; a < 3; ++a) { atomicMin(&s_mn[a], (int)f[a]); atomicMax(&s_mx[a], (int)f[a]); }
+          for (int a = 0; a < 3; ++a) { t_mn[a] = min(t_mn[a], (int)f[a]); t_mx[a] = max(t_mx[a], (int)f[a]); }
         } else {
           s_bad = 1;
         }
       }
     }
+  }
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {  // one shared-memory atomic per warp and bound (every block runs this pass)
+    const int wmn = __reduce_min_sync(0xffffffffu, t_mn[a]), wmx = __reduce_max_sync(0xffffffffu, t_mx[a]);
+    if (lane == 0) { atomicMin(&s_mn[a], wmn); atomicMax(&s_mx[a], wmx); }
   }
   __syncthreads();
   const long long dx = (long long)s_mx[0] - s_mn[0] + 1, dy = (long long)s_mx[1] - s_mn[1] + 1, dz = (long long)s_mx[2] - s_mn[2] + 1;
@@ -196,7 +202,14 @@ __device__ __forceinline__ void inc_build_run(const IncJob& J, const MapBatch& B
     int cnt[4] = {0, 0, 0, 0};
 #pragma unroll
     for (int u = 0; u < 4; ++u) ke[u] = e0 + u < hi ? s_key[e0 + u] : 0ull;
-    for (int j = lane; j < n; j += 32) {
+    int j = lane;
+    for (; j + 96 < n; j += 128) {  // four key loads in flight
+      const unsigned long long k0 = s_key[j], k1 = s_key[j + 32], k2 = s_key[j + 64], k3 = s_key[j + 96];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        cnt[u] += (k0 < ke[u] ? 1 : 0) + (k1 < ke[u] ? 1 : 0) + (k2 < ke[u] ? 1 : 0) + (k3 < ke[u] ? 1 : 0);
+    }
+    for (; j < n; j += 32) {
       const unsigned long long k = s_key[j];
 #pragma unroll
       for (int u = 0; u < 4; ++u) cnt[u] += k < ke[u] ? 1 : 0;
