@@ -62,14 +62,9 @@ struct FaRowConst {
   float kb1, kb2, kb3, kb4, kb5, kb6, kb7, kb8, kc5, srx;
 };
 
-__device__ __forceinline__ void fa_row_const(const float* tc, FaRowConst& k) {
-  double s, c;
-  sincos((double)tc[0], &s, &c);
-  const float srx = (float)s, crx = (float)c;
-  sincos((double)tc[1], &s, &c);
-  const float sry = (float)s, cry = (float)c;
-  sincos((double)tc[2], &s, &c);
-  const float srz = (float)s, crz = (float)c;
+// sc = {sin rx, cos rx, sin ry, cos ry, sin rz, cos rz} of transformCur
+__device__ __forceinline__ void fa_row_const(const float* tc, const float* sc, FaRowConst& k) {
+  const float srx = sc[0], crx = sc[1], sry = sc[2], cry = sc[3], srz = sc[4], crz = sc[5];
   const float tx = tc[3], ty = tc[4], tz = tc[5];
   k.a1 = crx * sry * srz;
   k.a2 = crx * crz * sry;
@@ -203,6 +198,7 @@ __global__ void __launch_bounds__(FAL_THREADS) fa_loop_kernel(const __grid_const
   __shared__ __align__(8) uint64_t s_mbar;
   __shared__ FaLoopState s_st;
   __shared__ FaRowConst s_k;
+  __shared__ float s_sc[6];
   __shared__ double s_w[FAL_WARPS][FAL_NSUM];
   __shared__ double s_sum[FAL_NSUM];
   __shared__ int s_break;
@@ -247,10 +243,17 @@ __global__ void __launch_bounds__(FAL_THREADS) fa_loop_kernel(const __grid_const
     int it = 0;
     for (; it < FAL_MAX_ITERS; ++it) {
       __syncthreads();
-      if (tid == 0) fa_row_const(s_st.tc, s_k);
+      if (tid < 3) {  // sin / cos of the three angles side by side (double precision, rounded to float: DESIGN.md §3)
+        double sn, cs;
+        sincos((double)s_st.tc[tid], &sn, &cs);
+        s_sc[2 * tid] = (float)sn;
+        s_sc[2 * tid + 1] = (float)cs;
+      }
 #pragma unroll
       for (int k = 0; k < 6; ++k) F.tc[k] = s_st.tc[k];
       F.iter = it;
+      __syncthreads();
+      if (tid == 0) fa_row_const(s_st.tc, s_sc, s_k);
       __syncthreads();
       double acc[FAL_NSUM];
 #pragma unroll
@@ -307,7 +310,13 @@ __global__ void __launch_bounds__(FAL_THREADS) fa_loop_kernel(const __grid_const
       if (tid < FAL_NSUM * 16) {
         const int k = tid >> 4, j = tid & 15;
         double t = 0.0;
-        for (int b = j; b < nb; b += 16) t += __ldcg(part + b * FAL_PART + k);
+        for (int b0 = j; b0 < nb; b0 += 16 * 8) {  // eight partials in flight per thread, added in block order
+          double v[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) v[u] = b0 + 16 * u < nb ? __ldcg(part + (b0 + 16 * u) * FAL_PART + k) : 0.0;
+#pragma unroll
+          for (int u = 0; u < 8; ++u) t += v[u];
+        }
         t += __shfl_xor_sync(0xffffffffu, t, 8, 16);
         t += __shfl_xor_sync(0xffffffffu, t, 4, 16);
         t += __shfl_xor_sync(0xffffffffu, t, 2, 16);
