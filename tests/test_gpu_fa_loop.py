@@ -115,3 +115,16 @@ def test_update_transformation_on_part_of_the_gpu(abi, orc, synth, max_blocks):
         g = h.fa_update_transformation(cur_c, cur_s, np.zeros(6, np.float32), want_trace=True)
         o = orc.fa_update_transformation(cur_c, cur_s, last_c, last_s, np.zeros(6, np.float32), eigen_mode=1)
         _compare(g, o, "%d blocks" % max_blocks)
+
+
+def test_update_transformation_with_staged_cloud():
+    """The cp.async.bulk staging of the previous sweep's cloud (LLB200_FA_STAGE=1, off by default: profiles/r02_ab_records.txt)
+    is read once per process, so the parity test above is run again in a child process with the switch on."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, LLB200_FA_STAGE="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", os.path.abspath(__file__),
+                        "-k", "matches_oracle or on_part_of_the_gpu"], env=env, capture_output=True, text=True, timeout=900,
+                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]

@@ -245,6 +245,35 @@ def test_knn5_exact_ties_and_small_maps(abi, orc):
         assert accept.tolist() == [0, 0, 0]
 
 
+def test_cell_table_stamps_survive_many_builds(abi, orc):
+    """The cell tables are stamped, not cleared (csrc/map_build.cuh: cell_entry_x): 8-bit stamps, table reset every 255
+    builds. More than 255 grid builds on ONE handle, over maps that move and shrink (so stale entries of earlier builds lie
+    in cells the current map does not touch, and inside its box), through the stand-alone grid kernels (ll_knn5) and, every
+    few builds, through the grid built inside the scan kernel: neighbours stay bit-exact across the wrap."""
+    rng = np.random.default_rng(11)
+    base = np.concatenate([rng.uniform(-6, 6, (4000, 3)), np.zeros((4000, 1))], 1).astype(np.float32)
+    base[:, 1] *= 0.2
+    prm = abi.default_params(map_downsample=0, apply_update=1, eigen_mode=1, iter_count_thres=2, stop_thres=0.0)
+    with abi.Handle(prm) as h:
+        for k in range(300):
+            n = 4000 - 13 * (k % 50)
+            shift = np.array([0.37 * (k % 7), 0.0, -0.41 * (k % 5), 0.0], np.float32)
+            corner = (base[:n] + shift).astype(np.float32)
+            surf = (base[::-1][:n] * np.float32(1.3) + shift).astype(np.float32)
+            h.set_local_map_raw(corner, surf)
+            if k % 4 == 3:   # the grid of this build is made inside the single-kernel scan
+                h.scan2map(corner[::40], surf[::10], np.zeros(6, np.float32))
+            if k < 250 and k % 25:
+                continue     # (every build counts; only some are checked — all of them around the wrap)
+            q = (corner[rng.choice(n, 200, replace=False)] + np.float32(0.05)).astype(np.float32)
+            for which, m in ((0, corner), (1, surf)):
+                idx, d2, acc = h.knn5(which, q)
+                oidx, od2 = orc.knn5(m, q, orc.KNN_GRID)
+                oacc = (oidx[:, 4] >= 0) & (od2[:, 4] < 1.0)
+                assert np.array_equal(acc.astype(bool), oacc), (k, which)
+                assert np.array_equal(idx[oacc], oidx[oacc]) and np.array_equal(bits(d2[oacc]), bits(od2[oacc])), (k, which)
+
+
 # ------------------------------------------------------------------------------------------ a6/a7/a8 residuals
 @pytest.mark.parametrize("eigen_mode", [1, 0])
 def test_residuals_parity(abi, orc, single_problem, single_maps, eigen_mode):
