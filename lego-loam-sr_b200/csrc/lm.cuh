@@ -167,7 +167,11 @@ __device__ inline void make_householder(float* v, int n, float& tau, float& beta
 
 // matAtA.colPivHouseholderQr().solve(matAtB) (mapOptmization.cpp:1505) for an n x n system, n <= 6.
 // Same step sequence as Eigen 3.3.7 ColPivHouseholderQR::computeInPlace + _solve_impl.
-__device__ __noinline__ void colpiv_qr_solve_n(const float* Ain /* col-major n x n */, const float* b, float* x, int n) {
+// kN > 0: the size is a compile-time constant (everything unrolls into registers: the 3 x 3 solves of fa_loop.cuh);
+// kN = 0: the size is the run-time argument n.
+template <int kN>
+__device__ __forceinline__ void colpiv_qr_solve_core(const float* Ain /* col-major n x n */, const float* b, float* x, int n_rt) {
+  const int n = kN > 0 ? kN : n_rt;
   float qr[36], hC[6], nU[6], nD[6], c[6], col[6];
   int transp[6], perm[6];
   for (int i = 0; i < n * n; ++i) qr[i] = Ain[i];
@@ -256,6 +260,12 @@ __device__ __noinline__ void colpiv_qr_solve_n(const float* Ain /* col-major n x
   }
   for (int i = 0; i < nonzero; ++i) x[perm[i]] = c[i];
 #undef QR
+}
+__device__ __noinline__ void colpiv_qr_solve_n(const float* Ain /* col-major n x n */, const float* b, float* x, int n) {
+  colpiv_qr_solve_core<0>(Ain, b, x, n);
+}
+__device__ __noinline__ void colpiv_qr_solve_3(const float* Ain /* col-major 3 x 3 */, const float* b, float* x) {
+  colpiv_qr_solve_core<3>(Ain, b, x, 3);
 }
 
 // Cyclic Jacobi eigen-decomposition of a symmetric n x n matrix (n <= 6) in double: eigenvalues

@@ -39,7 +39,8 @@ __device__ __noinline__ void neq_solve_small(const double* sums, int m, int iter
       AtA[a * m + c] = v;
     }
   for (int a = 0; a < m; ++a) Atb[a] = (float)sums[k++];
-  colpiv_qr_solve_n(AtA, Atb, x, m);
+  if (m == 3) colpiv_qr_solve_3(AtA, Atb, x);  // (same step sequence, unrolled: every iteration of fa_loop_kernel pays for it)
+  else colpiv_qr_solve_n(AtA, Atb, x, m);
   if (iter == 0) {
     int deg = 0;
     float P[36];

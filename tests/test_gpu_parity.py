@@ -599,19 +599,47 @@ def test_replay_matches_oracle(abi, orc, sequence):
 
 
 def test_replay_scan_side_downsample_on_device(abi, orc, synth, sequence):
-    """downsampleCurrentScan (:1234-1267) through ll_voxel_downsample: raw clouds in, same frame products."""
+    """The raw-frame path — downsampleCurrentScan (:1234-1267) on the device as part of the frame, loop-closure-off mirror —
+    against the SAME replay fed with the oracle's VoxelGrid chain of the same raw clouds (the reference's six filters,
+    :1236-1265): the two pose streams, the keyframe-id lists and the downsampled maps must be identical bit for bit (the
+    device filters are bit-exact, so everything downstream sees the same numbers), and every frame's pose must match the
+    oracle registering that scan on the device's map and prior."""
     from conftest import SMALL_WORLD
     from lego_loam_sr_b200 import host
     world = synth.World(seed=2, **SMALL_WORLD)
-    gt = synth.trajectory(world, 4, step=0.7, seed=2)
-    mo = host.MapOptimization(upstream_params(abi), loop_closure_enabled=False, search_num=50, search_radius=50.0)
-    for k in range(4):
+    n = 12
+    gt = synth.trajectory(world, n, step=0.7, seed=2)
+    kw = dict(iter_count_thres=10, stop_thres=0.0)
+    prm, oprm = upstream_params(abi, lm_solver=1, **kw), upstream_params(orc, **kw)
+    mo = host.MapOptimization(prm, loop_closure_enabled=False, search_num=50, search_radius=50.0)
+    ref = host.MapOptimization(prm, loop_closure_enabled=False, search_num=50, search_radius=50.0)
+    view = mo.abi_handle()
+    worst_t = worst_r = 0.0
+    for k in range(n):
         raw = synth.scan(world, gt[k], seed=2 * 100003 + k)
         pose, res = mo.process_frame(gt[k].astype(np.float32), raw, pre_downsampled=False)
-        assert res.status == (1 if k == 0 else 0)
+        # the reference's chain on the CPU: corner clouds 0.2, the others 0.4, SurfTotal = VoxelGrid(SurfLastDS + OutlierLastDS)
+        cs = np.ascontiguousarray(raw["corner_scan"][:, :4], np.float32)
+        sl = np.ascontiguousarray(raw["surf_last"][:, :4], np.float32)
+        ol = np.ascontiguousarray(raw["outlier_last"][:, :4], np.float32)
+        csd = orc.voxel_downsample(cs, oprm.corner_leaf)[0]
+        sld = orc.voxel_downsample(sl, oprm.surf_leaf)[0]
+        old = orc.voxel_downsample(ol, oprm.surf_leaf)[0]
+        std = orc.voxel_downsample(np.concatenate([sld, old]), oprm.surf_leaf)[0]
+        frame = dict(corner_scan=cs, corner_scan_ds=csd, surf_last_ds=sld, outlier_last_ds=old, surf_total_ds=std)
+        pose2, res2 = ref.process_frame(gt[k].astype(np.float32), frame, pre_downsampled=True)
+        assert res.status == res2.status == (1 if k == 0 else 0), k
+        assert np.array_equal(pose.view(np.uint32), pose2.view(np.uint32)), (k, pose, pose2)
+        assert np.array_equal(mo.map_ids, ref.map_ids), k
         if k:
+            assert (res.iter_num, res.sel_num, res.corner_map_ds, res.surf_map_ds) == (res2.iter_num, res2.sel_num, res2.corner_map_ds, res2.surf_map_ds)
+            gc, gs = view.get_map_ds(0), view.get_map_ds(1)
+            fres, fpose, _ = orc.scan2map(gc, gs, csd, std, mo.last_prior, oprm)
+            worst_t, worst_r = max(worst_t, trans_err(pose, fpose)), max(worst_r, rot_err(pose, fpose))
             assert trans_err(pose, gt[k]) < 0.05
+    assert worst_t <= 1e-4 and worst_r <= 1e-5, (worst_t, worst_r)
     mo.close()
+    ref.close()
 
 
 # ------------------------------------------------------------------------------------------ full-size properties
