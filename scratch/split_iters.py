@@ -11,6 +11,8 @@ if os.environ.get("LLB200_LIB"):
 import bench
 steps = int(os.environ.get("NSTEPS", "40"))
 flush = not os.environ.get("NOFLUSH")
+if os.environ.get("LEGACY_WORLD"):  # round 1's smaller workload (~62 k-point map, ~6.7 k queries)
+    bench._WORLD, bench._STEP = bench.R01_WORLD, bench.R01_STEP_M
 data = bench.make_data(2, bench.WINDOW + 5 + steps)
 out = {}
 for it in [int(v) for v in os.environ.get("ITERS", "1,2,4,10").split(",")]:
