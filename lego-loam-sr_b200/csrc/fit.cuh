@@ -201,14 +201,18 @@ __device__ void eig3_eigen_style(float a11, float a12, float a13, float a22, flo
   ev[0] = diag[0] * scale; ev[1] = diag[1] * scale; ev[2] = diag[2] * scale;
 }
 
-// ---- a7: corner residual ------------------------------------------------------------------------------
-// nb = the five neighbours in ascending (d2, index) order; sel = the query in the map frame.
-// Returns true when the residual is kept (s > min_weight); coeff = (s la, s lb, s lc, s ld2).
-// kEigenMode: compile-time copy of FitParams::eigen_mode (the hot kernels are instantiated per mode so that the
-// Eigen-style iterative solvers of the as-shipped mode stay out of the upstream-mode code).
+// The fit is split where the query enters: the GEOMETRY (the two points of the line / the plane) depends on the five
+// neighbours and their order only, so the LM loop keeps it from one iteration to the next while the neighbours stay the
+// same (lm.cuh); the RESIDUAL is what the query adds. corner_fit / surf_fit are the two halves back to back: the same
+// operations in the same order as before the split.
+struct FitGeom {
+  float g[6];  // corner: x1, y1, z1, x2, y2, z2 (:1329-1334)   surf: pa, pb, pc, pd (normalised, :1400-1409), -, -
+  bool ok;     // corner: the line test (:1325) passed          surf: the plane is valid (:1411-1420)
+};
+
 template <int kEigenMode>
-__device__ __forceinline__ bool corner_fit(const float nbx[5], const float nby[5], const float nbz[5], float x0,
-                                           float y0, float z0, const FitParams& prm, float coeff[4]) {
+__device__ __forceinline__ void corner_geometry(const float nbx[5], const float nby[5], const float nbz[5], const FitParams& prm,
+                                                FitGeom& G) {
   float cx = 0.f, cy = 0.f, cz = 0.f;
 #pragma unroll
   for (int j = 0; j < 5; ++j) { cx += nbx[j]; cy += nby[j]; cz += nbz[j]; }
@@ -231,11 +235,17 @@ __device__ __forceinline__ bool corner_fit(const float nbx[5], const float nby[5
     eig3_closed_form(a11, a12, a13, a22, a23, a33, ev, v);
     vx = v[0]; vy = v[1]; vz = v[2];
   }
-  if (!(ev[2] > prm.eig_ratio * ev[1])) return false;
-  float x1 = (float)((double)cx + 0.1 * (double)vx), y1 = (float)((double)cy + 0.1 * (double)vy),
-        z1 = (float)((double)cz + 0.1 * (double)vz);
-  float x2 = (float)((double)cx - 0.1 * (double)vx), y2 = (float)((double)cy - 0.1 * (double)vy),
-        z2 = (float)((double)cz - 0.1 * (double)vz);
+  G.ok = ev[2] > prm.eig_ratio * ev[1];
+  G.g[0] = (float)((double)cx + 0.1 * (double)vx); G.g[1] = (float)((double)cy + 0.1 * (double)vy);
+  G.g[2] = (float)((double)cz + 0.1 * (double)vz);
+  G.g[3] = (float)((double)cx - 0.1 * (double)vx); G.g[4] = (float)((double)cy - 0.1 * (double)vy);
+  G.g[5] = (float)((double)cz - 0.1 * (double)vz);
+}
+
+__device__ __forceinline__ bool corner_residual(const FitGeom& G, float x0, float y0, float z0, const FitParams& prm,
+                                                float coeff[4]) {
+  if (!G.ok) return false;
+  const float x1 = G.g[0], y1 = G.g[1], z1 = G.g[2], x2 = G.g[3], y2 = G.g[4], z2 = G.g[5];
   float cxy = (x0 - x1) * (y0 - y2) - (x0 - x2) * (y0 - y1);
   float cxz = (x0 - x1) * (z0 - z2) - (x0 - x2) * (z0 - z1);
   float cyz = (y0 - y1) * (z0 - z2) - (y0 - y2) * (z0 - z1);
@@ -251,6 +261,19 @@ __device__ __forceinline__ bool corner_fit(const float nbx[5], const float nby[5
   coeff[2] = s * lc;
   coeff[3] = s * ld2;
   return (double)s > prm.min_weight;
+}
+
+// ---- a7: corner residual ------------------------------------------------------------------------------
+// nb = the five neighbours in ascending (d2, index) order; sel = the query in the map frame.
+// Returns true when the residual is kept (s > min_weight); coeff = (s la, s lb, s lc, s ld2).
+// kEigenMode: compile-time copy of FitParams::eigen_mode (the hot kernels are instantiated per mode so that the
+// Eigen-style iterative solvers of the as-shipped mode stay out of the upstream-mode code).
+template <int kEigenMode>
+__device__ __forceinline__ bool corner_fit(const float nbx[5], const float nby[5], const float nbz[5], float x0,
+                                           float y0, float z0, const FitParams& prm, float coeff[4]) {
+  FitGeom G;
+  corner_geometry<kEigenMode>(nbx, nby, nbz, prm, G);
+  return corner_residual(G, x0, y0, z0, prm, coeff);
 }
 
 // ---- a8: surf residual ----------------------------------------------------------------------------------
@@ -376,8 +399,8 @@ __device__ __forceinline__ void qr53_solve_minus_one(float a[3][5], float x[3]) 
   }
 }
 
-__device__ __forceinline__ bool surf_fit(const float nbx[5], const float nby[5], const float nbz[5], float x0, float y0,
-                                         float z0, const FitParams& prm, float coeff[4]) {
+__device__ __forceinline__ void surf_geometry(const float nbx[5], const float nby[5], const float nbz[5], const FitParams& prm,
+                                              FitGeom& G) {
   float a[3][5];
 #pragma unroll
   for (int j = 0; j < 5; ++j) { a[0][j] = nbx[j]; a[1][j] = nby[j]; a[2][j] = nbz[j]; }
@@ -390,7 +413,13 @@ __device__ __forceinline__ bool surf_fit(const float nbx[5], const float nby[5],
 #pragma unroll
   for (int j = 0; j < 5; ++j)
     if ((double)fabsf(pa * nbx[j] + pb * nby[j] + pc * nbz[j] + pd) > prm.plane_tol) valid = false;
-  if (!valid) return false;
+  G.g[0] = pa; G.g[1] = pb; G.g[2] = pc; G.g[3] = pd; G.g[4] = 0.f; G.g[5] = 0.f;
+  G.ok = valid;
+}
+
+__device__ __forceinline__ bool surf_residual(const FitGeom& G, float x0, float y0, float z0, const FitParams& prm, float coeff[4]) {
+  if (!G.ok) return false;
+  const float pa = G.g[0], pb = G.g[1], pc = G.g[2], pd = G.g[3];
   float pd2 = pa * x0 + pb * y0 + pc * z0 + pd;
   float nrm2 = x0 * x0 + y0 * y0 + z0 * z0;
   float s = (float)(1.0 - prm.weight_k * fabs((double)pd2) / sqrt(sqrt((double)nrm2)));
@@ -399,6 +428,13 @@ __device__ __forceinline__ bool surf_fit(const float nbx[5], const float nby[5],
   coeff[2] = s * pc;
   coeff[3] = s * pd2;
   return (double)s > prm.min_weight;
+}
+
+__device__ __forceinline__ bool surf_fit(const float nbx[5], const float nby[5], const float nbz[5], float x0, float y0,
+                                         float z0, const FitParams& prm, float coeff[4]) {
+  FitGeom G;
+  surf_geometry(nbx, nby, nbz, prm, G);
+  return surf_residual(G, x0, y0, z0, prm, coeff);
 }
 
 // ---- a9: one row of matA and matB (mapOptmization.cpp:1464-1501) ---------------------------------------

@@ -135,10 +135,10 @@ struct LMArgs {
   float* e_d2;
   // cache records of the queries beyond a block's LM_QCAP shared-memory slots (dense scans: hundreds of queries per
   // block), indexed by query (corner queries first), LM_GUARD_STRIDE float4 each: the same fields as a KnnCache slot —
-  // [0..31] cand, [32] center, [33] qpt, [34] t1, [35] = {cnt, prev, -, -}. nullptr: not used.
+  // [0..31] cand, [32] center, [33] qpt, [34] t1, [35] = {cnt, prev, -, -}, [36..37] geo. nullptr: not used.
   float4* g_guard;
 };
-constexpr int LM_GUARD_STRIDE = 36;
+constexpr int LM_GUARD_STRIDE = 38;
 
 // ---- 6x6 dense helpers (one thread; column-major like Eigen) -------------------------------------------
 struct Mat6 {
@@ -915,7 +915,10 @@ struct KnnCache {
                    //                from c' to every map point that is NOT one of them (G <= 0: unknown)
   int* cnt;        // [LM_QCAP]      0 = no set yet, -1 = not cacheable, > 0 = points in the set
   uint32_t* prev;  // [LM_QCAP]      positions in cand of the five neighbours found last time (bit mask), 0 = unknown
+  float4* geo;     // [LM_QCAP][2]   the fit's geometry (fit.cuh: FitGeom: g[0..5], ok) and the signature of the neighbour
+                   //                order it was computed for (0xffffffff: none) — see lm_block_pass_cached, phase 2
 };
+constexpr uint32_t LM_GEO_NONE = 0xffffffffu;
 // A query's record in global memory (LMArgs::g_guard) seen as slot 0 of a KnnCache: the searches below work on either.
 __device__ __forceinline__ KnnCache knn_cache_of_record(float4* rec) {
   KnnCache G;
@@ -925,9 +928,10 @@ __device__ __forceinline__ KnnCache knn_cache_of_record(float4* rec) {
   G.t1 = rec + LM_CACHE_CAND + 2;
   G.cnt = reinterpret_cast<int*>(rec + LM_CACHE_CAND + 3);
   G.prev = reinterpret_cast<uint32_t*>(rec + LM_CACHE_CAND + 3) + 1;
+  G.geo = rec + LM_CACHE_CAND + 4;
   return G;
 }
-constexpr int LM_CACHE_BYTES = LM_QCAP * (LM_CACHE_CAND * 16 + 16 + 16 + 16 + 4 + 4);
+constexpr int LM_CACHE_BYTES = LM_QCAP * (LM_CACHE_CAND * 16 + 16 + 16 + 16 + 4 + 4 + 32);
 constexpr int LM_LOOP_SMEM = LM_THREADS * LM_SLOT * (int)sizeof(float) + LM_CACHE_BYTES;
 // dynamic shared memory of lm_persistent_kernel (the incremental map assembly borrows it for the added keyframes' sort)
 constexpr int LM_PERSISTENT_SMEM = LM_LOOP_SMEM > INC_SMEM_BYTES ? LM_LOOP_SMEM : INC_SMEM_BYTES;
@@ -1067,7 +1071,7 @@ __device__ __noinline__ void knn_cache_fill(const float4* sorted, int my_start, 
 // Step 1 of the per-thread cached search (see knn5_thread): up to six member points (absent: d = LM_EMPTY_D2), the guard
 // t1 = (c', G). Returns true and fills the slot when the members still hold the five nearest points of sel.
 __device__ __forceinline__ bool knn5_guard_check(const float4 sel, const float4 (&nb)[6], const bool (&have)[6], const float4 t1,
-                                                 uint32_t max_bits, float* slot) {
+                                                 uint32_t max_bits, uint32_t geo_sig, float* slot) {
   uint32_t d[6], ix[6];
 #pragma unroll
   for (int k = 0; k < 6; ++k) {
@@ -1109,6 +1113,13 @@ __device__ __forceinline__ bool knn5_guard_check(const float4 sel, const float4 
 #pragma unroll
   for (int k = 0; k < 6; ++k)
     if (rank[k] < 5) { slot[4 + 3 * rank[k]] = nb[k].x; slot[5 + 3 * rank[k]] = nb[k].y; slot[6 + 3 * rank[k]] = nb[k].z; }
+  // the order of the members (their ranks, three bits each) names the neighbour list: the same signature as when the
+  // fit's geometry was stored = the same five points in the same order = the same geometry, bit for bit
+  uint32_t sig = 0u;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) sig |= (uint32_t)rank[k] << (3 * k);
+  slot[19] = sig == geo_sig ? 1.f : 0.f;
+  slot[20] = __uint_as_float(sig);
   return true;
 }
 
@@ -1175,8 +1186,10 @@ __device__ __noinline__ bool knn5_thread(const KnnCache C, int i, const Trig* tr
       mask &= mask - 1u;
       nb[k] = cand[j];
     }
-    if (knn5_guard_check(sel, nb, have, t1, max_bits, slot)) return true;
+    if (knn5_guard_check(sel, nb, have, t1, max_bits, __float_as_uint(C.geo[2 * i + 1].w), slot)) return true;
   }
+  slot[19] = 0.f;                          // (everything below changes the neighbour list: the stored geometry is void)
+  slot[20] = __uint_as_float(LM_GEO_NONE);
   LL_TL_COUNT_THREAD(6);
   if (t1.w == 0.f) LL_TL_COUNT_THREAD(7);
   // ---- step 2: the whole set, top six by (d2, index). Columns are visited rotated by the thread index: the threads of a
@@ -1706,6 +1719,8 @@ __device__ __noinline__ void lm_full_search_warp(const LMArgs* Ap, const Trig* t
           slot[1] = sel[b].y;
           slot[2] = sel[b].z;
           slot[3] = acc[b] ? 1.f : 0.f;
+          slot[19] = 0.f;  // a new neighbour list: no stored geometry applies
+          slot[20] = __uint_as_float(LM_GEO_NONE);
         }
         const bool has_slot = first_chunk && i < LM_QCAP;
         if (has_slot || A.g_guard) {  // (re)build this query's cached set around where it is now
@@ -1780,11 +1795,31 @@ __device__ __forceinline__ float lm_block_pass_cached(const LMArgs& A, const Tri
       float coeff[4] = {0.f, 0.f, 0.f, 0.f};
       bool keep = false;
       if (slot[3] != 0.f) {
-        float nbx[5], nby[5], nbz[5];
+        // The geometry of the fit (line points / plane) depends on the neighbour list only: when the guard test of phase A
+        // confirmed the SAME five points in the SAME order as when it was last computed (signature in slot[20]), it is
+        // taken from the query's record instead of running the eigen solve / QR again — the same numbers, bit for bit.
+        const bool has_slot = first_chunk && my_i < LM_QCAP;
+        const bool has_rec = has_slot || A.g_guard != nullptr;
+        float4* geo = nullptr;
+        if (has_rec) geo = has_slot ? C.geo + 2 * my_i : A.g_guard + (size_t)qi * LM_GUARD_STRIDE + LM_CACHE_CAND + 4;
+        FitGeom G;
+        if (has_rec && slot[19] != 0.f) {
+          const float4 g0 = geo[0], g1 = geo[1];
+          G.g[0] = g0.x; G.g[1] = g0.y; G.g[2] = g0.z; G.g[3] = g0.w; G.g[4] = g1.x; G.g[5] = g1.y;
+          G.ok = g1.z != 0.f;
+        } else {
+          float nbx[5], nby[5], nbz[5];
 #pragma unroll
-        for (int k = 0; k < 5; ++k) { nbx[k] = slot[4 + 3 * k]; nby[k] = slot[5 + 3 * k]; nbz[k] = slot[6 + 3 * k]; }
-        keep = m == 0 ? corner_fit<kEigenMode>(nbx, nby, nbz, slot[0], slot[1], slot[2], A.prm.fit, coeff)
-                      : surf_fit(nbx, nby, nbz, slot[0], slot[1], slot[2], A.prm.fit, coeff);
+          for (int k = 0; k < 5; ++k) { nbx[k] = slot[4 + 3 * k]; nby[k] = slot[5 + 3 * k]; nbz[k] = slot[6 + 3 * k]; }
+          if (m == 0) corner_geometry<kEigenMode>(nbx, nby, nbz, A.prm.fit, G);
+          else surf_geometry(nbx, nby, nbz, A.prm.fit, G);
+          if (has_rec) {
+            geo[0] = make_float4(G.g[0], G.g[1], G.g[2], G.g[3]);
+            geo[1] = make_float4(G.g[4], G.g[5], G.ok ? 1.f : 0.f, slot[20]);
+          }
+        }
+        keep = m == 0 ? corner_residual(G, slot[0], slot[1], slot[2], A.prm.fit, coeff)
+                      : surf_residual(G, slot[0], slot[1], slot[2], A.prm.fit, coeff);
       }
       if (keep) {
         const float4 p = __ldg(&A.q[m][m ? qi - A.nq[0] : qi]);
@@ -1903,7 +1938,8 @@ __global__ void __launch_bounds__(LM_THREADS, 1) lm_persistent_kernel(const __gr
   C.center = C.cand + LM_QCAP * LM_CACHE_CAND;
   C.qpt = C.center + LM_QCAP;
   C.t1 = C.qpt + LM_QCAP;
-  C.cnt = reinterpret_cast<int*>(C.t1 + LM_QCAP);
+  C.geo = C.t1 + LM_QCAP;
+  C.cnt = reinterpret_cast<int*>(C.geo + 2 * LM_QCAP);
   C.prev = reinterpret_cast<uint32_t*>(C.cnt + LM_QCAP);
   __shared__ __align__(16) LMState s_st;
   const int tid = threadIdx.x;
