@@ -100,6 +100,28 @@ __device__ __forceinline__ int inc_bound(const unsigned long long* a, int lo, in
   return lo;
 }
 
+// lower_bound over an ascending array in global memory by the WHOLE block: every thread probes one position per round
+// (two rounds cover 2^18 entries with 512 threads) and __syncthreads_count tells how many probes lie below v — two L2
+// round trips instead of the fourteen dependent ones of a one-thread binary search (three such searches sat at the head
+// of every merge tile). All threads of the block must call; the result is block-uniform.
+__device__ __forceinline__ int inc_bound_block(const unsigned long long* a, int lo, int hi, unsigned long long v) {
+  const int nt = (int)blockDim.x, tid = (int)threadIdx.x;
+#pragma unroll 1
+  while (hi - lo > 0) {
+    const int len = hi - lo;
+    // probe positions split [lo, hi) into nt + 1 nearly equal pieces; with len <= nt every element is probed
+    const int p = len <= nt ? lo + tid : lo + (int)(((long long)len * (tid + 1)) / (nt + 1));
+    const bool below = p < hi && __ldcg(a + p) < v;
+    const int c = __syncthreads_count(below);  // probes are ascending, so the first c of them are the ones below v
+    if (len <= nt) return lo + c;
+    const int new_lo = c == 0 ? lo : lo + (int)(((long long)len * c) / (nt + 1)) + 1;
+    const int new_hi = c == nt ? hi : lo + (int)(((long long)len * (c + 1)) / (nt + 1));
+    lo = new_lo;
+    hi = new_hi;
+  }
+  return lo;
+}
+
 // Which blocks merge which map: workers [first, nb) are split between the two maps in proportion to their windows.
 struct IncTiling {
   int first, nw[2];
@@ -312,12 +334,12 @@ __device__ __forceinline__ void inc_merge(const IncJob& J, const MapBatch& B, in
   };
   uint32_t surv_before = before;  // surviving entries before the current sub-tile
   // the run entries of this tile: [r_lo, r_hi) = those whose key is >= this tile's first key and < the next tile's
-  const int r_lo = first_tile ? 0 : inc_bound<false, true>(r_key, 0, n_new, __ldcg(o_key + a0));
-  const int r_hi = last_tile ? n_new : inc_bound<false, true>(r_key, 0, n_new, __ldcg(o_key + b0));
+  const int r_lo = first_tile ? 0 : inc_bound_block(r_key, 0, n_new, __ldcg(o_key + a0));
+  const int r_hi = last_tile ? n_new : inc_bound_block(r_key, 0, n_new, __ldcg(o_key + b0));
   int sub_lo = r_lo;
   for (int a = a0; a < b0 || (a == a0 && a0 >= b0); a += INC_SUB) {  // (one pass with an empty range when the window is empty)
     const int b = min(b0, a + INC_SUB), cnt = max(0, b - a);
-    const int sub_hi = b >= b0 ? r_hi : inc_bound<false, true>(r_key, sub_lo, r_hi, __ldcg(o_key + b));
+    const int sub_hi = b >= b0 ? r_hi : inc_bound_block(r_key, sub_lo, r_hi, __ldcg(o_key + b));
     const int ns = sub_hi - sub_lo;
     const bool slice_in_smem = ns <= INC_SUB;
     // old entries of the sub-tile: 4 consecutive ones per thread
