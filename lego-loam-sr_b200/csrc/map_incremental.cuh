@@ -170,16 +170,25 @@ __device__ __forceinline__ void inc_build_run(const IncJob& J, const MapBatch& B
   for (int sg = 0; sg < J.n_segs; ++sg) {
     const Segment& g = J.segs[sg];
     if (g.map != m) continue;
-    for (int i = tid; i < g.count; i += blockDim.x) {
-      const float4 p = __ldg(g.src + i);
-      const float4 q = g.identity ? p : rigid_transform(g.t, p);
-      if (finite3(q)) {
-        const float f[3] = {floorf(q.x * inv), floorf(q.y * inv), floorf(q.z * inv)};
-        if (fabsf(f[0]) < 1048576.f && fabsf(f[1]) < 1048576.f && fabsf(f[2]) < 1048576.f) {
+    for (int i0 = tid; i0 < g.count; i0 += 4 * blockDim.x) {  // four loads in flight (the clouds are cold: fresh from the host)
+      float4 pv[4];
 #pragma unroll
-          for (int a = 0; a < 3; ++a) { t_mn[a] = min(t_mn[a], (int)f[a]); t_mx[a] = max(t_mx[a], (int)f[a]); }
-        } else {
-          s_bad = 1;
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * (int)blockDim.x;
+        pv[u] = i < g.count ? __ldg(g.src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (i0 + u * (int)blockDim.x >= g.count) continue;
+        const float4 q = g.identity ? pv[u] : rigid_transform(g.t, pv[u]);
+        if (finite3(q)) {
+          const float f[3] = {floorf(q.x * inv), floorf(q.y * inv), floorf(q.z * inv)};
+          if (fabsf(f[0]) < 1048576.f && fabsf(f[1]) < 1048576.f && fabsf(f[2]) < 1048576.f) {
+#pragma unroll
+            for (int a = 0; a < 3; ++a) { t_mn[a] = min(t_mn[a], (int)f[a]); t_mx[a] = max(t_mx[a], (int)f[a]); }
+          } else {
+            s_bad = 1;
+          }
         }
       }
     }
@@ -201,17 +210,27 @@ __device__ __forceinline__ void inc_build_run(const IncJob& J, const MapBatch& B
   for (int sg = 0; sg < J.n_segs; ++sg) {
     const Segment& g = J.segs[sg];
     if (g.map != m) continue;
-    for (int i = tid; i < g.count; i += blockDim.x) {
-      const float4 p = __ldg(g.src + i);
-      const float4 q = g.identity ? p : rigid_transform(g.t, p);
-      unsigned long long rel = 0xffffffffull;  // non-finite points: behind every voxel, in arrival order
-      if (finite3(q)) {
-        const long long ix = (long long)(int)floorf(q.x * inv) - s_mn[0], iy = (long long)(int)floorf(q.y * inv) - s_mn[1],
-                        iz = (long long)(int)floorf(q.z * inv) - s_mn[2];
-        rel = (unsigned long long)((iz * dy + iy) * dx + ix);
+    for (int i0 = tid; i0 < g.count; i0 += 4 * blockDim.x) {
+      float4 pv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * (int)blockDim.x;
+        pv[u] = i < g.count ? __ldg(g.src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      const int e = g.dst_off + i;
-      s_key[e] = (rel << INC_RUN_BITS) | (unsigned long long)e;  // unique => the rank order is the stable order
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * (int)blockDim.x;
+        if (i >= g.count) continue;
+        const float4 q = g.identity ? pv[u] : rigid_transform(g.t, pv[u]);
+        unsigned long long rel = 0xffffffffull;  // non-finite points: behind every voxel, in arrival order
+        if (finite3(q)) {
+          const long long ix = (long long)(int)floorf(q.x * inv) - s_mn[0], iy = (long long)(int)floorf(q.y * inv) - s_mn[1],
+                          iz = (long long)(int)floorf(q.z * inv) - s_mn[2];
+          rel = (unsigned long long)((iz * dy + iy) * dx + ix);
+        }
+        const int e = g.dst_off + i;
+        s_key[e] = (rel << INC_RUN_BITS) | (unsigned long long)e;  // unique => the rank order is the stable order
+      }
     }
   }
   __syncthreads();
