@@ -292,7 +292,13 @@ __device__ __forceinline__ void inc_count(const IncJob& J, int m, int t, int nti
     c = threadIdx.x == 0 ? (uint32_t)(b - a) : 0u;
   } else {
     const uint32_t* __restrict__ tag = W.tag[J.cur];
-    for (int i = a + threadIdx.x; i < b; i += blockDim.x) c += inc_alive(__ldcg(tag + i), J) ? 1u : 0u;
+    for (int i0 = a + (int)threadIdx.x; i0 < b; i0 += 4 * (int)blockDim.x) {  // four loads in flight
+      uint32_t tv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) tv[u] = i0 + u * (int)blockDim.x < b ? __ldcg(tag + i0 + u * (int)blockDim.x) : 0u;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) c += (i0 + u * (int)blockDim.x < b && inc_alive(tv[u], J)) ? 1u : 0u;
+    }
   }
   c = __reduce_add_sync(0xffffffffu, c);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -453,10 +459,20 @@ __device__ __forceinline__ uint32_t inc_count_heads(const IncJob& J, int m, int 
   const int len = (n + ntiles - 1) / ntiles;
   const int a = min(n, t * len), b = min(n, a + len);
   uint32_t c = 0;
-  for (int i = a + threadIdx.x; i < b; i += blockDim.x) {
-    const unsigned long long k = __ldcg(key + i);
-    const bool head = k < INC_KEY_NONFINITE - 1ull && (i == 0 || __ldcg(key + i - 1) != k);
-    c += head ? 1u : 0u;
+  for (int i0 = a + (int)threadIdx.x; i0 < b; i0 += 4 * (int)blockDim.x) {  // eight loads in flight
+    unsigned long long kv[4], pv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * (int)blockDim.x;
+      kv[u] = i < b ? __ldcg(key + i) : INC_KEY_NONFINITE;
+      pv[u] = (i < b && i > 0) ? __ldcg(key + i - 1) : INC_KEY_NONFINITE;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * (int)blockDim.x;
+      const bool head = i < b && kv[u] < INC_KEY_NONFINITE - 1ull && (i == 0 || pv[u] != kv[u]);
+      c += head ? 1u : 0u;
+    }
   }
   c = __reduce_add_sync(0xffffffffu, c);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
