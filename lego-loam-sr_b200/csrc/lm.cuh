@@ -1999,10 +1999,9 @@ __global__ void __launch_bounds__(LM_THREADS, 1) lm_persistent_kernel(const __gr
     const float run_sum = lm_block_pass_cached<kEigenMode, kFresh>(A, s_st.trig, rt, s_geom, s_slot, C, sh, (int)it);
     LL_TL(it, 5);
     float* part = A.partials + (size_t)(it & 1u) * gridDim.x * 32;
-    if (tid < 256 && (tid & 7) == 0) {  // thread 8 k holds sum k (k >= 29: zero)
-      part[blockIdx.x * 32 + (tid >> 3)] = run_sum;
-      __threadfence();
-    }
+    // (no __threadfence: the grid barrier's release-reduction is cumulative — it orders these writes, observed by thread 0
+    //  through the barrier's bar.sync, before the arrival that the other blocks acquire; the map stages rely on the same)
+    if (tid < 256 && (tid & 7) == 0) part[blockIdx.x * 32 + (tid >> 3)] = run_sum;  // thread 8 k holds sum k (k >= 29: zero)
     LL_TL(it, 6);
     LL_TL_GT(it, 0);
     coop_barrier(barrier, epoch);
