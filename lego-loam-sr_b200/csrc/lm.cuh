@@ -1672,7 +1672,8 @@ __device__ __forceinline__ float lm_block_pass(const LMArgs& A, const Trig& trig
 // the chunk starting at c0), three at a time, their staging slots, and their cached sets. Out of line on purpose.
 template <bool kFresh>
 __device__ __noinline__ void lm_full_search_warp(const LMArgs* Ap, const Trig* trig_p, const GridGeom* geom_p, float* s_slot,
-                                                 KnnCache C, QShare sh, int c0, int nc, int nc_pad, unsigned need, bool first_chunk) {
+                                                 KnnCache C, QShare sh, int c0, int nc, int nc_pad, unsigned need, bool first_chunk,
+                                                 bool do_fill) {
   const LMArgs& A = *Ap;
   const Trig trig = *trig_p;
   const GridGeom geom[2] = {geom_p[0], geom_p[1]};
@@ -1723,7 +1724,7 @@ __device__ __noinline__ void lm_full_search_warp(const LMArgs* Ap, const Trig* t
           slot[20] = __uint_as_float(LM_GEO_NONE);
         }
         const bool has_slot = first_chunk && i < LM_QCAP;
-        if (has_slot || A.g_guard) {  // (re)build this query's cached set around where it is now
+        if (do_fill && (has_slot || A.g_guard)) {  // (re)build this query's cached set around where it is now
           const KnnCache Cq = has_slot ? C : knn_cache_of_record(A.g_guard + (size_t)sh.qi(c0 + i, A.nq[0]) * LM_GUARD_STRIDE);
           const int ci = has_slot ? i : 0;
           const uint32_t d5 = __shfl_sync(0xffffffffu, acc[b] ? od[b] : LM_EMPTY_D2, 4);
@@ -1746,7 +1747,6 @@ __device__ __forceinline__ float lm_block_pass_cached(const LMArgs& A, const Tri
   // trig_s / geom_s live in shared memory (the out-of-line searches take them by address)
   __shared__ unsigned s_need[LM_WARPS];
   const int tid = threadIdx.x, warp = tid >> 5;
-  (void)tl_it;
   float run_sum = 0.f;  // thread 8 k, k < 29: this block's running total of sum k
   const int n_local = sh.size();
   for (int c0 = 0; c0 < n_local; c0 += LM_CHUNK) {
@@ -1780,7 +1780,11 @@ __device__ __forceinline__ float lm_block_pass_cached(const LMArgs& A, const Tri
     LL_TL_WARP(1);
     // ---- (B) full search of what is left (everything in iteration 0), out of line: the steady-state loop is
     //      instruction-fetch bound, and this is by far its largest piece of code
-    if (need) lm_full_search_warp<kFresh>(&A, &trig_s, geom_s, s_slot, C, sh, c0, nc, nc_pad, need, first_chunk);
+    // The cached sets are first collected in iteration 1: iteration 0 starts from the prior, its pose step is by far the
+    // largest, and sets collected around the prior's positions mostly failed their proofs one iteration later (55 % of the
+    // queries re-scanned their sets and 1-2 % searched again and refilled; profiles/r02_scan_timeline_*.txt) — so
+    // iteration 0 only searches, iteration 1 searches again from nearly converged positions and fills.
+    if (need) lm_full_search_warp<kFresh>(&A, &trig_s, geom_s, s_slot, C, sh, c0, nc, nc_pad, need, first_chunk, tl_it >= 1);
     LL_TL_WARP(5);
     LL_TL(tl_it, 1);
     __syncthreads();
