@@ -919,6 +919,9 @@ struct KnnCache {
                    //                order it was computed for (0xffffffff: none) — see lm_block_pass_cached, phase 2
 };
 constexpr uint32_t LM_GEO_NONE = 0xffffffffu;
+#ifndef LM_FILL_FROM
+#define LM_FILL_FROM 1  // first LM iteration whose full searches also collect the cached sets (0 and 2 measured: profiles/r02_ab_records.txt)
+#endif
 // A query's record in global memory (LMArgs::g_guard) seen as slot 0 of a KnnCache: the searches below work on either.
 __device__ __forceinline__ KnnCache knn_cache_of_record(float4* rec) {
   KnnCache G;
@@ -1784,7 +1787,7 @@ __device__ __forceinline__ float lm_block_pass_cached(const LMArgs& A, const Tri
     // largest, and sets collected around the prior's positions mostly failed their proofs one iteration later (55 % of the
     // queries re-scanned their sets and 1-2 % searched again and refilled; profiles/r02_scan_timeline_*.txt) — so
     // iteration 0 only searches, iteration 1 searches again from nearly converged positions and fills.
-    if (need) lm_full_search_warp<kFresh>(&A, &trig_s, geom_s, s_slot, C, sh, c0, nc, nc_pad, need, first_chunk, tl_it >= 1);
+    if (need) lm_full_search_warp<kFresh>(&A, &trig_s, geom_s, s_slot, C, sh, c0, nc, nc_pad, need, first_chunk, tl_it >= LM_FILL_FROM);
     LL_TL_WARP(5);
     LL_TL(tl_it, 1);
     __syncthreads();
