@@ -1282,9 +1282,34 @@ __device__ __forceinline__ float lm_term(const float sv[8], float one, int k) {
   return one;
 }
 
+// min_lambda is an OUTPUT of the scan (localInfo, :1602-1607), not an input of the loop: when iteration 0's Sturm count at
+// the threshold says that nothing is degenerate, the six multisection rounds that pin the smallest eigenvalue down to float
+// resolution leave the critical path of iteration 0 (18 us with cold code) and run one per iteration on warp 1, beside
+// warp 0's 6x6 solve of iterations 1..6 (single-kernel scan only: the job lives in shared memory). The same rounds on the
+// same matrix in the same order: the same number, bit for bit. A loop that ends early finishes the rounds at its exit.
+struct MinLambdaJob {
+  float A[36];
+  double lo, hi;
+  int rounds_left;
+};
+__device__ __forceinline__ void lm_min_lambda_step(MinLambdaJob* J, LMState* S, int lane, int max_rounds) {
+  double lo = J->lo, hi = J->hi;
+  int left = J->rounds_left;
+  for (int r = 0; r < max_rounds && left > 0; ++r, --left) min_eig6_round(J->A, lane, lo, hi);
+  __syncwarp();
+  if (lane == 0) {
+    J->lo = lo;
+    J->hi = hi;
+    J->rounds_left = left;
+    if (left == 0) S->min_lambda = (float)(0.5 * (lo + hi));
+  }
+  __syncwarp();
+}
+
 // Iteration 0 of LMOptimization, upstream semantics (:1507-1531): min_lambda, the degeneracy flag and the projector,
 // by one warp. Out of line: it runs once per scan, and the LM loop around it is instruction-fetch bound.
-__device__ __noinline__ void lm_iter0_degeneracy(const float* AtA, float eig_thresh, int lane, float* Ps, float* misc) {
+__device__ __noinline__ void lm_iter0_degeneracy(const float* AtA, float eig_thresh, int lane, float* Ps, float* misc,
+                                                 MinLambdaJob* defer) {
   struct { float eig_thresh; } prm = {eig_thresh};
 
   // min_lambda and "is any eigenvalue below the threshold" from Sturm counts (solve_warp.cuh); the full
@@ -1295,6 +1320,23 @@ __device__ __noinline__ void lm_iter0_degeneracy(const float* AtA, float eig_thr
   // (float)lambda < eig_thresh  <=>  lambda < the midpoint between eig_thresh and the float below it (ties round to
   // eig_thresh's even mantissa for the default 100): the double shift that reproduces the float comparison
   const double thr_mid = 0.5 * ((double)prm.eig_thresh + (double)nextafterf(prm.eig_thresh, -FLT_MAX));
+  if (defer && sturm_count6(AtA, thr_mid) == 0) {  // (warp-uniform) nothing below the threshold: identity projector now,
+    for (int i = lane; i < 36; i += 32) {          // min_lambda later (lm_min_lambda_step)
+      defer->A[i] = AtA[i];
+      Ps[i] = (i / 6 == i % 6) ? 1.f : 0.f;
+    }
+    if (lane == 0) {
+      double lo, hi;
+      min_eig6_bracket(AtA, lo, hi);
+      defer->lo = lo;
+      defer->hi = hi;
+      defer->rounds_left = MIN_EIG6_ROUNDS;
+      misc[0] = 0.f;
+      misc[1] = 0.f;  // (placeholder until the rounds are done)
+    }
+    __syncwarp();
+    return;
+  }
   min_eig6_multisection(AtA, thr_mid, lane, wmin, n_below);
   unsigned mb = n_below > 0 ? 1u : 0u;
   if (mb) {  // degenerate
@@ -1333,7 +1375,7 @@ __device__ __noinline__ float qr66_warp_outofline(const float* AtA, const float*
 // and, at iteration 0, the eigen-decomposition runs concurrently on warp 1 (solve_warp.cuh); everything
 // else (as shipped mode, fewer than min_residuals rows) takes the single-thread path above.
 template <int kEigenMode>
-__device__ void lm_solve_block(double* s_red, const LMParams& prm, LMState* S, bool stage_mode) {
+__device__ void lm_solve_block(double* s_red, const LMParams& prm, LMState* S, bool stage_mode, MinLambdaJob* defer = nullptr) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = (int)(s_red[28] + 0.5);
   if constexpr (kEigenMode == 0) {
@@ -1370,7 +1412,9 @@ __device__ void lm_solve_block(double* s_red, const LMParams& prm, LMState* S, b
     }
     if (lane < 6) xs[lane] = x;
   } else if (warp == 1 && iter == 0) {  // :1507-1531, upstream semantics
-    lm_iter0_degeneracy(AtA, prm.eig_thresh, lane, Ps, misc);
+    lm_iter0_degeneracy(AtA, prm.eig_thresh, lane, Ps, misc, defer);
+  } else if (warp == 1 && defer && defer->rounds_left > 0) {
+    lm_min_lambda_step(defer, S, lane, 1);  // one deferred multisection round beside warp 0's solve
   }
   __syncthreads();
   if (warp != 0) return;
@@ -1502,7 +1546,7 @@ __device__ __forceinline__ float lm_block_sums(float* s_slot, const float (&sv)[
 // Sum the block partials in a fixed order (deterministic regardless of which block arrives last).
 template <int kEigenMode>
 __device__ void reduce_partials_and_solve(const float* partials, int nblocks, const LMParams& prm, LMState* S,
-                                          bool stage_mode, double* s_red /* [nwarps][32] shared */) {
+                                          bool stage_mode, double* s_red /* [nwarps][32] shared */, MinLambdaJob* defer = nullptr) {
   const int lane = threadIdx.x & 31, sub = threadIdx.x >> 5, nsub = blockDim.x >> 5;
   double acc = 0.0;
   constexpr int kInFlight = 10;  // 148 blocks / 16 warps: every partial of a warp's share is fetched in one round trip
@@ -1526,7 +1570,7 @@ __device__ void reduce_partials_and_solve(const float* partials, int nblocks, co
   }
   __syncthreads();
   LL_TL(S->iter, 8);
-  lm_solve_block<kEigenMode>(s_red, prm, S, stage_mode);
+  lm_solve_block<kEigenMode>(s_red, prm, S, stage_mode, defer);
 }
 
 // Block b's share of the queries: groups of LM_QGROUP consecutive corner queries dealt round-robin to the blocks, and the
@@ -1949,7 +1993,9 @@ __global__ void __launch_bounds__(LM_THREADS, 1) lm_persistent_kernel(const __gr
   C.cnt = reinterpret_cast<int*>(C.geo + 2 * LM_QCAP);
   C.prev = reinterpret_cast<uint32_t*>(C.cnt + LM_QCAP);
   __shared__ __align__(16) LMState s_st;
+  __shared__ __align__(8) MinLambdaJob s_ml;
   const int tid = threadIdx.x;
+  if (tid == 0) s_ml.rounds_left = 0;
   {  // prologue: the persistent members (matP, isDegenerate, ...) come from the handle's state
     static_assert(sizeof(LMState) % 4 == 0, "LMState is copied word by word");
     const uint32_t* src = reinterpret_cast<const uint32_t*>(A.st);
@@ -2014,9 +2060,12 @@ __global__ void __launch_bounds__(LM_THREADS, 1) lm_persistent_kernel(const __gr
     coop_barrier(barrier, epoch);
     LL_TL_GT(it, 1);
     LL_TL(it, 7);
-    reduce_partials_and_solve<kEigenMode>(part, gridDim.x, A.prm, &s_st, false, reinterpret_cast<double*>(s_slot));
+    reduce_partials_and_solve<kEigenMode>(part, gridDim.x, A.prm, &s_st, false, reinterpret_cast<double*>(s_slot), &s_ml);
     LL_TL(it, 9);
   }
+  if (blockIdx.x == 0 && (tid >> 5) == 1 && s_ml.rounds_left > 0)  // the loop ended before the deferred rounds did
+    lm_min_lambda_step(&s_ml, &s_st, tid & 31, MIN_EIG6_ROUNDS);
+  __syncthreads();
 #ifdef LL_TIMELINE
   __syncthreads();
   if (blockIdx.x == 0 && tid == 0) {

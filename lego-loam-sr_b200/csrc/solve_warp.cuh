@@ -238,28 +238,37 @@ __device__ __forceinline__ int sturm_count6(const float* A, double sigma) {
 // This replaces the full Jacobi eigen-decomposition on the critical path of iteration 0 whenever no eigenvalue
 // is below the threshold (the usual case); the eigenvectors are only needed for the degenerate projector.
 // All 32 lanes must call; results are warp-uniform.
-__device__ __forceinline__ void min_eig6_multisection(const float* A, double thresh, int lane, double& min_lambda,
-                                                      int& n_below) {
-  double tr = 0.0, hi = 1.7976931348623157e308;
+// The bracket the multisection starts from, and one of its rounds (32 shifts, one per lane; results warp-uniform).
+__device__ __forceinline__ void min_eig6_bracket(const float* A, double& lo, double& hi) {
+  double tr = 0.0;
+  hi = 1.7976931348623157e308;
 #pragma unroll
   for (int i = 0; i < 6; ++i) {
     tr += fabs((double)A[i * 6 + i]);
     hi = fmin(hi, (double)A[i * 6 + i]);  // lambda_min <= every diagonal entry
   }
-  double lo = -1e-6 * tr - 1e-30;         // AtA is positive semi-definite up to rounding
+  lo = -1e-6 * tr - 1e-30;                // AtA is positive semi-definite up to rounding
   hi += 1e-12 * tr + 1e-30;
+}
+__device__ __forceinline__ void min_eig6_round(const float* A, int lane, double& lo, double& hi) {
+  const double step = (hi - lo) / 33.0;
+  const double sigma = lo + step * (double)(lane + 1);
+  const unsigned has = __ballot_sync(FULL, sturm_count6(A, sigma) >= 1);
+  // counts are monotone in sigma: the first lane whose shift is above lambda_min
+  const int first = has ? __ffs(has) - 1 : 32;
+  const double new_lo = lo + step * (double)first;
+  hi = first < 32 ? lo + step * (double)(first + 1) : hi;
+  lo = new_lo;
+}
+constexpr int MIN_EIG6_ROUNDS = 6;
+
+__device__ __forceinline__ void min_eig6_multisection(const float* A, double thresh, int lane, double& min_lambda,
+                                                      int& n_below) {
+  double lo, hi;
+  min_eig6_bracket(A, lo, hi);
   n_below = sturm_count6(A, thresh);
 #pragma unroll 1
-  for (int round = 0; round < 6; ++round) {
-    const double step = (hi - lo) / 33.0;
-    const double sigma = lo + step * (double)(lane + 1);
-    const unsigned has = __ballot_sync(FULL, sturm_count6(A, sigma) >= 1);
-    // counts are monotone in sigma: the first lane whose shift is above lambda_min
-    const int first = has ? __ffs(has) - 1 : 32;
-    const double new_lo = lo + step * (double)first;
-    hi = first < 32 ? lo + step * (double)(first + 1) : hi;
-    lo = new_lo;
-  }
+  for (int round = 0; round < MIN_EIG6_ROUNDS; ++round) min_eig6_round(A, lane, lo, hi);
   min_lambda = 0.5 * (lo + hi);
 }
 
