@@ -5,6 +5,7 @@
 #include "../../include/legoloam_b200.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #if defined(__SSE2__)
 #include <emmintrin.h>
@@ -129,6 +130,11 @@ struct ll_handle_s {
   LMState* d_state = nullptr;
   LMState* h_state = nullptr;  // pinned mirror
   float* d_partials = nullptr;   // [2][partial_blocks][32] (double-buffered by iteration parity in the persistent kernel)
+  unsigned* d_qsync = nullptr;   // LMArgs::q_sync: [0] arrival stamp of the query upload, [1] block 0's verdict
+  unsigned q_seq = 0;
+  bool q_overlap = false;        // the scan being enqueued gets its queries from a copy queued behind the launch
+  bool counted = false;          // this handle is in g_live_handles
+  bool q_overlap_off = false;    // this handle met a scan whose overlapped upload never arrived: stream order from then on
   void* d_guard = nullptr;       // LMArgs::g_guard: 576 bytes per query, only for scans with more queries than cache slots
   size_t guard_bytes = 0;
   unsigned* d_barriers = nullptr;  // ring of kBarrierSlots grid-barrier counters, one per scan, re-armed 32 scans ahead
@@ -184,6 +190,8 @@ struct ll_handle_s {
 };
 
 namespace {
+
+std::atomic<int> g_live_handles{0};
 
 int fail(ll_handle h, int code, const std::string& msg) {
   if (h) h->err = msg;
@@ -1171,6 +1179,10 @@ int scan2map_enqueue(ll_handle h, const float pose6[6]) {
       LL_TRY(ensure_bytes(h, &h->d_guard, &h->guard_bytes, (size_t)nq * LM_GUARD_STRIDE * sizeof(float4)));
       A.g_guard = static_cast<float4*>(h->d_guard);
     }
+    if (h->q_overlap) {
+      A.q_sync = h->d_qsync;
+      A.q_seq = h->q_seq;
+    }
     float p[6] = {pose6[0], pose6[1], pose6[2], pose6[3], pose6[4], pose6[5]};
     unsigned* bar = h->d_barriers + (h->scan_seq % kBarrierSlots);
     unsigned* bar_clear = h->d_barriers + ((h->scan_seq + kBarrierSlots / 2) % kBarrierSlots);
@@ -1252,6 +1264,20 @@ int scan2map_collect(ll_handle h, float pose6_out[6], ll_result* res) {
     LL_TRY(enqueue_iterations(h, more));
   }
   h->scan_pending = false;
+  if (h->h_state->status == 4) {
+    // The kernel gave up waiting for the query clouds (uploaded beside it on the copy stream): streams of MANY handles can
+    // share a hardware work queue, and a copy queued behind another handle's not-yet-resident kernel never runs while this
+    // kernel holds the SMs. The clouds are on the device by now: run the scan again in stream order, and keep this handle
+    // off the overlapped path from here on.
+    h->q_overlap_off = true;
+    LL_CUDA(h, cudaStreamSynchronize(h->copy_stream));
+    if (h->retried) return fail(h, LL_ERR_CUDA, "the query clouds' upload never reached the scan kernel");
+    h->retried = true;
+    int rc = scan2map_enqueue(h, h->pose_in);
+    if (rc == LL_OK) rc = scan2map_collect(h, pose6_out, res);
+    h->retried = false;
+    return rc;
+  }
   if (h->scan_used_inc && !h->retried && (h->h_state->flags & (8 | 4))) {
     // The incremental assembly met a case it cannot represent (flags bit 3), or the in-kernel search grids did not fit
     // the blocks this scan was given (bit 2 on a size estimate): the same keyframes through the full path / the
@@ -1379,6 +1405,8 @@ int ll_create(const ll_params* p, int device_id, ll_handle* out) {
             cudaEventCreateWithFlags(&h->kf_evt, cudaEventDisableTiming) == cudaSuccess &&
             cudaMalloc(reinterpret_cast<void**>(&h->d_state), sizeof(LMState)) == cudaSuccess &&
             cudaMalloc(reinterpret_cast<void**>(&h->d_barriers), sizeof(unsigned) * kBarrierSlots) == cudaSuccess &&
+            cudaMalloc(reinterpret_cast<void**>(&h->d_qsync), sizeof(unsigned) * 4) == cudaSuccess &&
+            cudaMemsetAsync(h->d_qsync, 0, sizeof(unsigned) * 4, h->stream) == cudaSuccess &&
             cudaMemsetAsync(h->d_barriers, 0, sizeof(unsigned) * kBarrierSlots, h->stream) == cudaSuccess &&
             cudaMallocHost(reinterpret_cast<void**>(&h->h_state), sizeof(LMState)) == cudaSuccess &&
             cudaMemsetAsync(h->d_state, 0, sizeof(LMState), h->stream) == cudaSuccess &&
@@ -1388,12 +1416,15 @@ int ll_create(const ll_params* p, int device_id, ll_handle* out) {
     return LL_ERR_CUDA;
   }
   std::memset(h->h_state, 0, sizeof(LMState));
+  h->counted = true;
+  g_live_handles.fetch_add(1);
   *out = h;
   return LL_OK;
 }
 
 int ll_destroy(ll_handle h) {
   if (!h) return LL_OK;
+  if (h->counted) g_live_handles.fetch_sub(1);
   cudaSetDevice(h->device);
   if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
   if (h->kf_evt) cudaEventDestroy(h->kf_evt);
@@ -1404,7 +1435,7 @@ int ll_destroy(ll_handle h) {
     for (void* p : ptrs)
       if (p) cudaFree(p);
   }
-  void* ptrs[] = {h->d_segs, h->d_segs_aux, h->dq[0], h->dq[1], h->d_state, h->d_partials, h->d_guard, h->d_barriers, h->fa_last[0], h->fa_last[1],
+  void* ptrs[] = {h->d_segs, h->d_segs_aux, h->dq[0], h->dq[1], h->d_state, h->d_partials, h->d_guard, h->d_qsync, h->d_barriers, h->fa_last[0], h->fa_last[1],
                   h->d_tmp[0], h->d_tmp[1], h->d_tmp[2], h->d_tmp[3], h->d_tmp[4], h->d_tmp[5]};
   for (void* p : ptrs)
     if (p) cudaFree(p);
@@ -1757,6 +1788,41 @@ int ll_scan2map_async(ll_handle h, const void* corner_scan_ds, size_t n_corner, 
   // one staging pass for both query clouds
   const size_t nt = n_corner + n_surf;
   LL_TRY(ensure_bytes(h, reinterpret_cast<void**>(&h->dq[0]), &h->dq_cap[0], std::max<size_t>(nt, 1) * sizeof(float4)));
+  h->q_overlap = false;
+  // OFF by default (LLB200_QUERY_OVERLAP=1 enables): measured on the benchmarked replay it hides ~2 us of a 28 us gap
+  // between host and resident clouds — the gap is the CPU reading 345 KB of cache-cold 32-byte records while packing, not
+  // the DMA — and it is only safe for a handle that owns the GPU (see below); profiles/r02_ab_records.txt.
+  static const bool overlap_allowed = std::getenv("LLB200_QUERY_OVERLAP") && std::atoi(std::getenv("LLB200_QUERY_OVERLAP")) == 1;
+  // Only for a handle that has the GPU to itself: whole-GPU scan kernels (lm_max_blocks = 0) and no other live handle in
+  // the process — with many handles their streams share hardware work queues (CUDA_DEVICE_MAX_CONNECTIONS), and a copy
+  // queued behind another handle's waiting kernel would never reach a kernel that is spinning for it (measured: the
+  // batched replay of 8 handles ran into exactly that; the kernel's 2 s timeout and the rerun in scan2map_collect caught it).
+  if (overlap_allowed && !h->q_overlap_off && g_live_handles.load() == 1 && h->prm.lm_max_blocks == 0 && nt && h->prm.persistent_lm &&
+      h->map_ready && (h->map_deferred || h->grid_deferred)) {
+    // The single-kernel scan assembles the map (~150 us) before it looks at a query: launch it first and upload the
+    // clouds beside it on the copy stream, with a 4-byte arrival stamp queued behind them (lm.cuh: LMArgs::q_sync).
+    LL_TRY(pinned_acquire(h, nt * sizeof(float4) + 16));
+    float4* st = reinterpret_cast<float4*>(h->pinned);
+    pack_points(st, corner_scan_ds, n_corner, stride_bytes);
+    pack_points(st + n_corner, surf_total_ds, n_surf, stride_bytes);
+    unsigned* stamp = reinterpret_cast<unsigned*>(st + nt);
+    *stamp = ++h->q_seq;
+    h->q_ptr[0] = h->dq[0];
+    h->q_ptr[1] = h->dq[0] + n_corner;
+    h->nq[0] = (int)n_corner;
+    h->nq[1] = (int)n_surf;
+    h->q_overlap = true;
+    const int rc = scan2map_enqueue(h, pose6_in);
+    h->q_overlap = false;
+    // (whatever the launch said, the copies go out: a launched kernel waits for the stamp)
+    cudaError_t e1 = cudaMemcpyAsync(h->dq[0], st, nt * sizeof(float4), cudaMemcpyHostToDevice, h->copy_stream);
+    cudaError_t e2 = cudaMemcpyAsync(h->d_qsync, stamp, sizeof(unsigned), cudaMemcpyHostToDevice, h->copy_stream);
+    cudaError_t e3 = cudaEventRecord(h->pin_evt[h->pin_cur], h->copy_stream);
+    if (rc != LL_OK) return rc;
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess)
+      return fail(h, LL_ERR_CUDA, std::string("query upload: ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3)));
+    return LL_OK;
+  }
   if (nt) {
     LL_TRY(pinned_acquire(h, nt * sizeof(float4)));
     float4* st = reinterpret_cast<float4*>(h->pinned);

@@ -65,6 +65,12 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
   return v;
 }
 
+__device__ __forceinline__ unsigned ld_acquire_sys_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
 // Barrier across a co-resident grid (cooperative launch): `counter` starts at zero and only grows during the
 // launch; `epoch` counts the barriers this thread has passed (the same in every thread of the grid).
 #ifdef LL_TIMELINE

@@ -137,6 +137,13 @@ struct LMArgs {
   // block), indexed by query (corner queries first), LM_GUARD_STRIDE float4 each: the same fields as a KnnCache slot —
   // [0..31] cand, [32] center, [33] qpt, [34] t1, [35] = {cnt, prev, -, -}, [36..37] geo. nullptr: not used.
   float4* g_guard;
+  // The query clouds may still be on their way when the launch starts (ll_scan2map_async with host clouds: the upload runs
+  // on the copy stream while this kernel assembles the map, which does not need them). q_sync[0] is written by a 4-byte
+  // copy queued BEHIND the clouds on that stream (value q_seq); block 0 waits for it before the LM loop and tells the other
+  // blocks through q_sync[1] and a grid barrier whether it arrived (a copy that never comes must not hang the GPU).
+  // nullptr: the queries were resident before the launch.
+  unsigned* q_sync;
+  unsigned q_seq;
 };
 constexpr int LM_GUARD_STRIDE = 38;
 
@@ -1739,7 +1746,7 @@ __device__ __noinline__ void lm_full_search_warp(const LMArgs* Ap, const Trig* t
           need &= need - 1u;
           const int qi = sh.qi(c0 + warp + LM_WARPS * jb[b], A.nq[0]);
           mq[b] = qi < A.nq[0] ? 0 : 1;
-          qs[b] = __ldg(mq[b] ? &A.q[1][qi - A.nq[0]] : &A.q[0][qi]);
+          qs[b] = __ldcg(mq[b] ? &A.q[1][qi - A.nq[0]] : &A.q[0][qi]);  // (L2: the clouds may arrive during the launch)
           sel[b] = rigid_transform(trig, qs[b]);
         }
       }
@@ -1873,7 +1880,7 @@ __device__ __forceinline__ float lm_block_pass_cached(const LMArgs& A, const Tri
                       : surf_residual(G, slot[0], slot[1], slot[2], A.prm.fit, coeff);
       }
       if (keep) {
-        const float4 p = __ldg(&A.q[m][m ? qi - A.nq[0] : qi]);
+        const float4 p = __ldcg(&A.q[m][m ? qi - A.nq[0] : qi]);
         jacobian_row(rt, p.x, p.y, p.z, coeff[0], coeff[1], coeff[2], sv);
         sv[6] = -A.prm.step_size * coeff[3];  // matB (:1500)
         sv[7] = fabsf(coeff[3]);
@@ -2023,6 +2030,19 @@ __global__ void __launch_bounds__(LM_THREADS, 1) lm_persistent_kernel(const __gr
   __syncthreads();
   static_assert(INC_SMEM_BYTES <= LM_PERSISTENT_SMEM && INC_MERGE_SMEM_WORDS * 4 <= LM_PERSISTENT_SMEM &&
                 INC_REDUCE_SMEM_WORDS * 4 <= LM_PERSISTENT_SMEM, "the incremental map build borrows the dynamic shared memory");
+  bool queries_missing = false;
+  if (A.q_sync) {  // the query clouds were uploaded beside the map assembly: make sure they have landed
+    if (blockIdx.x == 0 && tid == 0) {
+      const long long t0 = clock64();
+      unsigned arrived = 1u;
+      while (ld_acquire_sys_u32(A.q_sync) != A.q_seq) {
+        if (clock64() - t0 > 4000000000LL) { arrived = 0u; break; }  // ~2 s: the copy is never coming
+      }
+      A.q_sync[1] = arrived;
+    }
+    coop_barrier(barrier, epoch);
+    queries_missing = __ldcg(A.q_sync + 1) == 0u;
+  }
   if (tid < LM_QCAP) C.cnt[tid] = 0;  // no cached sets yet (after the map build, which may use this memory as scratch)
   if (A.g_guard) {  // no guards yet for this block's queries beyond its cache slots (only this block ever touches them)
     const QShare sh0 = lm_partition(A, (int)blockIdx.x, (int)gridDim.x);
@@ -2032,6 +2052,10 @@ __global__ void __launch_bounds__(LM_THREADS, 1) lm_persistent_kernel(const __gr
   if (tid == 0) {
     const float pose6[6] = {p0, p1, p2, p3, p4, p5};
     lm_begin_state(&s_st, A.mst[0], A.mst[1], A.prm, pose6);
+    if (queries_missing) {  // (grid-uniform) not a reference behaviour: reported as status 4, the scan is not registered
+      s_st.status = 4;
+      s_st.done = 1;
+    }
   }
   __shared__ GridGeom s_geom[2];
   if (tid == 0) {
