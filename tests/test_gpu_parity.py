@@ -8,6 +8,7 @@ Bars (BASELINE.json north_star):
   * final 6-DoF pose after 10 LM iterations: <= 1e-4 m translation, <= 1e-5 rad rotation.
 """
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -791,3 +792,16 @@ def test_batched_replay_is_independent_of_concurrency(abi, synth):
     assert np.array_equal(a, b)
     assert (a[:, 1:, batch.RECORD_FIELDS.index("status")] == 0).all()
     assert (a[:, 1:, batch.RECORD_FIELDS.index("iter_num")] == 6).all()
+
+
+def test_scan2map_with_overlapped_query_upload():
+    """LLB200_QUERY_OVERLAP=1 (off by default: profiles/r02_ab_records.txt) launches the scan kernel before the query clouds
+    are uploaded and lets it wait for their arrival stamp; the switch is read once per process, so the scan-level parity
+    tests are run again in a child process with it on."""
+    import subprocess
+    env = dict(os.environ, LLB200_QUERY_OVERLAP="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", os.path.abspath(__file__), "-k",
+                        "scan2map_pose_within_tolerance or replay_matches_oracle or single_kernel_scan_equals"],
+                       env=env, capture_output=True, text=True, timeout=900,
+                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
