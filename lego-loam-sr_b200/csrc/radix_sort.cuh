@@ -20,7 +20,7 @@ namespace ll {
 
 constexpr int RS_THREADS = 256;
 constexpr int RS_WARPS = RS_THREADS / 32;
-constexpr int RS_ITEMS = 8;
+constexpr int RS_ITEMS = 16;
 constexpr int RS_TILE = RS_THREADS * RS_ITEMS;  // 2048 pairs per tile
 constexpr int RS_RADIX = 256;
 constexpr int RS_MAX_PASSES = 4;
