@@ -147,6 +147,58 @@ __device__ __forceinline__ bool inc_alive(uint32_t tag, const IncJob& J) {
   return alive;
 }
 
+// Ranks of the added points [lo, hi) of map m among all n composites in s_key (shared memory), and the points to their
+// places in the run. One warp per E points: the lanes stride over the keys (four loads in flight), every key is compared
+// with the E composites, the counts are reduced over the warp.
+template <int E>
+__device__ __forceinline__ void inc_rank_slice(const IncJob& J, const MapBatch& B, int m, const unsigned long long* s_key, int n,
+                                               int lo, int hi) {
+  const WindowBuffers& W = J.w[m];
+  const float inv = B.m[m].inv_leaf;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int e0 = lo + E * warp; e0 < hi; e0 += E * nwarps) {
+    unsigned long long ke[E];
+    int cnt[E];
+#pragma unroll
+    for (int u = 0; u < E; ++u) { ke[u] = e0 + u < hi ? s_key[e0 + u] : 0ull; cnt[u] = 0; }
+    int j = lane;
+    for (; j + 96 < n; j += 128) {  // four key loads in flight
+      const unsigned long long k0 = s_key[j], k1 = s_key[j + 32], k2 = s_key[j + 64], k3 = s_key[j + 96];
+#pragma unroll
+      for (int u = 0; u < E; ++u)
+        cnt[u] += (k0 < ke[u] ? 1 : 0) + (k1 < ke[u] ? 1 : 0) + (k2 < ke[u] ? 1 : 0) + (k3 < ke[u] ? 1 : 0);
+    }
+    for (; j < n; j += 32) {
+      const unsigned long long k = s_key[j];
+#pragma unroll
+      for (int u = 0; u < E; ++u) cnt[u] += k < ke[u] ? 1 : 0;
+    }
+#pragma unroll
+    for (int u = 0; u < E; ++u) cnt[u] = __reduce_add_sync(0xffffffffu, cnt[u]);
+    if (lane < E && e0 + lane < hi) {
+      const int e = e0 + lane;
+      int rank = cnt[0];
+#pragma unroll
+      for (int u = 1; u < E; ++u) rank = lane == u ? cnt[u] : rank;
+      // the point itself again (its cloud and offset from the segment table), to its place in the run
+      float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+      uint32_t tag = 0u;
+      for (int sg = 0; sg < J.n_segs; ++sg) {
+        const Segment& g = J.segs[sg];
+        if (g.map == m && e >= g.dst_off && e < g.dst_off + g.count) {
+          const float4 p = __ldg(g.src + (e - g.dst_off));
+          q = g.identity ? p : rigid_transform(g.t, p);
+          tag = (uint32_t)g.pad[0];
+        }
+      }
+      bool ok = true;
+      W.run_pts[rank] = q;
+      W.run_key[rank] = inc_abs_key(q, inv, ok);
+      W.run_tag[rank] = tag;
+    }
+  }
+}
+
 // ---- R: the run of the added keyframes of map m = their points sorted by (voxel key, arrival order), by ALL blocks.
 // A sorting network in one block's shared memory took 92 us for a 10 k-point keyframe (profiles/r02_*): the run is instead
 // RANKED. Every block transforms all the added points itself (a few thousand: cheaper than a grid barrier between a
@@ -235,50 +287,14 @@ __device__ __forceinline__ void inc_build_run(const IncJob& J, const MapBatch& B
   }
   __syncthreads();
   static_assert(INC_RUN_MAX == (1 << INC_RUN_BITS), "the composite key keeps the arrival index in INC_RUN_BITS bits");
-  // ranks of this block's slice [lo, hi) of the added points: four points per pass over the keys, one warp per four
+  // ranks of this block's slice [lo, hi) of the added points: E points per pass over the keys, one warp per E points, E
+  // chosen so that the slice is one round of the block's warps (69 points per block at 10 k: E = 5, not two rounds of 4)
   const int per = (n + (int)gridDim.x - 1) / (int)gridDim.x;
   const int lo = min(n, (int)blockIdx.x * per), hi = min(n, lo + per);
-  for (int e0 = lo + 4 * warp; e0 < hi; e0 += 4 * nwarps) {
-    unsigned long long ke[4];
-    int cnt[4] = {0, 0, 0, 0};
-#pragma unroll
-    for (int u = 0; u < 4; ++u) ke[u] = e0 + u < hi ? s_key[e0 + u] : 0ull;
-    int j = lane;
-    for (; j + 96 < n; j += 128) {  // four key loads in flight
-      const unsigned long long k0 = s_key[j], k1 = s_key[j + 32], k2 = s_key[j + 64], k3 = s_key[j + 96];
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-        cnt[u] += (k0 < ke[u] ? 1 : 0) + (k1 < ke[u] ? 1 : 0) + (k2 < ke[u] ? 1 : 0) + (k3 < ke[u] ? 1 : 0);
-    }
-    for (; j < n; j += 32) {
-      const unsigned long long k = s_key[j];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) cnt[u] += k < ke[u] ? 1 : 0;
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) cnt[u] = __reduce_add_sync(0xffffffffu, cnt[u]);
-    if (lane < 4 && e0 + lane < hi) {
-      const int e = e0 + lane;
-      int rank = cnt[0];
-#pragma unroll
-      for (int u = 1; u < 4; ++u) rank = lane == u ? cnt[u] : rank;
-      // the point itself again (its cloud and offset from the segment table), to its place in the run
-      float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-      uint32_t tag = 0u;
-      for (int sg = 0; sg < J.n_segs; ++sg) {
-        const Segment& g = J.segs[sg];
-        if (g.map == m && e >= g.dst_off && e < g.dst_off + g.count) {
-          const float4 p = __ldg(g.src + (e - g.dst_off));
-          q = g.identity ? p : rigid_transform(g.t, p);
-          tag = (uint32_t)g.pad[0];
-        }
-      }
-      bool ok = true;
-      W.run_pts[rank] = q;
-      W.run_key[rank] = inc_abs_key(q, inv, ok);
-      W.run_tag[rank] = tag;
-    }
-  }
+  const int want = (hi - lo + nwarps - 1) / nwarps;
+  if (want <= 4) inc_rank_slice<4>(J, B, m, s_key, n, lo, hi);
+  else if (want <= 6) inc_rank_slice<6>(J, B, m, s_key, n, lo, hi);
+  else inc_rank_slice<8>(J, B, m, s_key, n, lo, hi);
 }
 
 // ---- C: surviving entries of this worker's tile of the old window.
