@@ -806,6 +806,15 @@ int plan_incremental(ll_handle h, const int* ids, int n_ids, bool* used) {
     J.n_segs = ns;
     J.n_new[0] = oc;
     J.n_new[1] = os;
+    if (!st.add.empty()) {  // origin of the run's voxel cube: the first added keyframe's position, 2048 voxels back per axis
+      const Keyframe& k0 = h->kfs[st.add.front()];
+      const float leaf[2] = {h->prm.corner_leaf, h->prm.surf_leaf};
+      for (int m = 0; m < 2; ++m)
+        for (int a = 0; a < 3; ++a) {
+          const float v = std::floor(k0.pose[3 + a] * (1.0f / leaf[m]));
+          J.run_org[m][a] = (std::fabs(v) < 1.0e6f ? (int)v : 0) - 2048;
+        }
+    }
     J.n_out[0] = out[0] + oc;
     J.n_out[1] = out[1] + os;
     J.final_step = si + 1 == steps.size() ? 1 : 0;

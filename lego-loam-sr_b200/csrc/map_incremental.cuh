@@ -59,6 +59,7 @@ struct IncJob {
   uint32_t dead[INC_MAX_DEAD];   // tags (keyframe ids) to drop
   int n_segs;
   Segment segs[INC_MAX_SEGS];    // Segment::pad[0] = tag
+  int run_org[2][3];             // per map: voxel coordinates the added points' composites are relative to (inc_build_run)
   int final_step;                // 1 = compute laserCloud*FromMapDS after the merge
   int keep_fail;                 // 1 = the window this merge starts from comes from a merge whose verdict the host has not
                                  //     read yet: MapState::inc_fail survives the zeroing at the head of the launch
@@ -202,23 +203,24 @@ __device__ __forceinline__ void inc_rank_slice(const IncJob& J, const MapBatch& 
 // ---- R: the run of the added keyframes of map m = their points sorted by (voxel key, arrival order), by ALL blocks.
 // A sorting network in one block's shared memory took 92 us for a 10 k-point keyframe (profiles/r02_*): the run is instead
 // RANKED. Every block transforms all the added points itself (a few thousand: cheaper than a grid barrier between a
-// transform stage and a sort stage) and keeps their 64-bit composites (voxel index relative to the run's own box, arrival
-// index: unique, so the order is the stable one) in shared memory; it then owns a contiguous slice of the points and
+// transform stage and a sort stage) and keeps their 64-bit composites (voxel coordinates relative to a host-given origin,
+// arrival index: unique, so the order is the stable one) in shared memory; it then owns a contiguous slice of the points and
 // counts, for each of them, the composites below its own — four points per pass over the keys, one warp per four points —
 // which is its position in the run. n^2 / blocks comparisons: ~6 us for 10 k points on 148 blocks; the host takes the
 // full path when that budget is exceeded (few blocks, abi.cu). smem: INC_RUN_MAX u64.
 __device__ __forceinline__ void inc_build_run(const IncJob& J, const MapBatch& B, int m, unsigned long long* s_key) {
-  const WindowBuffers& W = J.w[m];
   const MapBuffers& M = B.m[m];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5, n = J.n_new[m];
-  __shared__ int s_mn[3], s_mx[3], s_bad;
-  __syncthreads();  // (the previous map's pass is over: its keys and box may be overwritten)
-  if (tid < 3) { s_mn[tid] = 0x7fffffff; s_mx[tid] = (int)0x80000000; }
+  const int tid = threadIdx.x, nwarps = blockDim.x >> 5, n = J.n_new[m];
+  __shared__ int s_bad;
+  __syncthreads();  // (the previous map's pass is over: its keys may be overwritten)
   if (tid == 0) s_bad = 0;
   __syncthreads();
   const float inv = M.inv_leaf;
-  int t_mn[3] = {0x7fffffff, 0x7fffffff, 0x7fffffff}, t_mx[3] = {(int)0x80000000, (int)0x80000000, (int)0x80000000};
-  // pass 1: the box of the run in voxel coordinates (transformPointCloud :649-664 of every added cloud, in list order)
+  // The composites of ALL added points: voxel coordinates relative to an origin the HOST derives from the first added
+  // keyframe's position (IncJob::run_org: its voxel minus 2048 per axis), twelve bits per axis — a cloud reaches at most
+  // ~130 m from its sensor, 650 voxels of 0.2 m — so that no pass over the points is needed to find their box first. A
+  // point outside that cube (or beyond +-2^20 voxels) gives the merge up: the host rebuilds in full.
+  const int ox = J.run_org[m][0], oy = J.run_org[m][1], oz = J.run_org[m][2];
   for (int sg = 0; sg < J.n_segs; ++sg) {
     const Segment& g = J.segs[sg];
     if (g.map != m) continue;
@@ -231,54 +233,17 @@ __device__ __forceinline__ void inc_build_run(const IncJob& J, const MapBatch& B
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        if (i0 + u * (int)blockDim.x >= g.count) continue;
-        const float4 q = g.identity ? pv[u] : rigid_transform(g.t, pv[u]);
-        if (finite3(q)) {
-          const float f[3] = {floorf(q.x * inv), floorf(q.y * inv), floorf(q.z * inv)};
-          if (fabsf(f[0]) < 1048576.f && fabsf(f[1]) < 1048576.f && fabsf(f[2]) < 1048576.f) {
-#pragma unroll
-            for (int a = 0; a < 3; ++a) { t_mn[a] = min(t_mn[a], (int)f[a]); t_mx[a] = max(t_mx[a], (int)f[a]); }
-          } else {
-            s_bad = 1;
-          }
-        }
-      }
-    }
-  }
-#pragma unroll
-  for (int a = 0; a < 3; ++a) {  // one shared-memory atomic per warp and bound (every block runs this pass)
-    const int wmn = __reduce_min_sync(0xffffffffu, t_mn[a]), wmx = __reduce_max_sync(0xffffffffu, t_mx[a]);
-    if (lane == 0) { atomicMin(&s_mn[a], wmn); atomicMax(&s_mx[a], wmx); }
-  }
-  __syncthreads();
-  const long long dx = (long long)s_mx[0] - s_mn[0] + 1, dy = (long long)s_mx[1] - s_mn[1] + 1, dz = (long long)s_mx[2] - s_mn[2] + 1;
-  const bool any = s_mx[0] >= s_mn[0];
-  const bool bad = s_bad != 0 || (any && (dx * dy * dz >= 0xffffffffLL || dx <= 0 || dy <= 0 || dz <= 0));
-  if (bad) {  // (the same verdict in every block: they all looked at the same points)
-    if (tid == 0 && blockIdx.x == 0) M.st->inc_fail = 1;
-    return;
-  }
-  // pass 2: the composites of ALL added points
-  for (int sg = 0; sg < J.n_segs; ++sg) {
-    const Segment& g = J.segs[sg];
-    if (g.map != m) continue;
-    for (int i0 = tid; i0 < g.count; i0 += 4 * blockDim.x) {
-      float4 pv[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int i = i0 + u * (int)blockDim.x;
-        pv[u] = i < g.count ? __ldg(g.src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
         const int i = i0 + u * (int)blockDim.x;
         if (i >= g.count) continue;
         const float4 q = g.identity ? pv[u] : rigid_transform(g.t, pv[u]);
-        unsigned long long rel = 0xffffffffull;  // non-finite points: behind every voxel, in arrival order
+        unsigned long long rel = 0xfffffffffull;  // non-finite points: behind every voxel (36 bits), in arrival order
         if (finite3(q)) {
-          const long long ix = (long long)(int)floorf(q.x * inv) - s_mn[0], iy = (long long)(int)floorf(q.y * inv) - s_mn[1],
-                          iz = (long long)(int)floorf(q.z * inv) - s_mn[2];
-          rel = (unsigned long long)((iz * dy + iy) * dx + ix);
+          const float f[3] = {floorf(q.x * inv), floorf(q.y * inv), floorf(q.z * inv)};
+          bool in = fabsf(f[0]) < 1048576.f && fabsf(f[1]) < 1048576.f && fabsf(f[2]) < 1048576.f;
+          const int ix = (int)f[0] - ox, iy = (int)f[1] - oy, iz = (int)f[2] - oz;
+          in = in && ix >= 0 && ix < 4096 && iy >= 0 && iy < 4096 && iz >= 0 && iz < 4095;  // (z = 4095 is kept for the sentinel)
+          if (!in) s_bad = 1;
+          rel = ((unsigned long long)(unsigned)iz << 24) | ((unsigned long long)(unsigned)iy << 12) | (unsigned long long)(unsigned)ix;
         }
         const int e = g.dst_off + i;
         s_key[e] = (rel << INC_RUN_BITS) | (unsigned long long)e;  // unique => the rank order is the stable order
@@ -286,6 +251,10 @@ __device__ __forceinline__ void inc_build_run(const IncJob& J, const MapBatch& B
     }
   }
   __syncthreads();
+  if (s_bad) {  // (the same verdict in every block: they all looked at the same points)
+    if (tid == 0 && blockIdx.x == 0) M.st->inc_fail = 1;
+    return;
+  }
   static_assert(INC_RUN_MAX == (1 << INC_RUN_BITS), "the composite key keeps the arrival index in INC_RUN_BITS bits");
   // ranks of this block's slice [lo, hi) of the added points: E points per pass over the keys, one warp per E points, E
   // chosen so that the slice is one round of the block's warps (69 points per block at 10 k: E = 5, not two rounds of 4)
