@@ -169,7 +169,11 @@ int ll_scan2map(ll_handle h, const void* corner_scan_ds, size_t n_corner, const 
                 size_t n_surf, size_t stride_bytes, float pose6_inout[6], ll_result* res);
 int ll_scan2map_dev(ll_handle h, const void* d_corner_scan_ds, size_t n_corner, const void* d_surf_total_ds,
                     size_t n_surf, float pose6_inout[6], ll_result* res);
-/* Asynchronous pair: enqueue, then collect. Between the two the caller may drive other handles. */
+/* Asynchronous pair: enqueue, then collect. Between the two the caller may drive other handles.
+ * Host clouds are normally packed into the library's own staging memory before the call returns. Clouds that lie in
+ * PAGE-LOCKED host memory (cudaHostAlloc / cudaHostRegister by the caller) with a stride that is a multiple of 16 bytes
+ * (pcl::PointXYZI: 32) are instead copied by DMA straight from the caller's buffers, which must then stay untouched until
+ * ll_scan2map_wait returns (ll_scan2map: until it returns). Same results either way (tests). */
 int ll_scan2map_async(ll_handle h, const void* corner_scan_ds, size_t n_corner, const void* surf_total_ds,
                       size_t n_surf, size_t stride_bytes, const float pose6_in[6]);
 int ll_scan2map_dev_async(ll_handle h, const void* d_corner_scan_ds, size_t n_corner,

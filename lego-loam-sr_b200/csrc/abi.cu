@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #if defined(__SSE2__)
 #include <emmintrin.h>
@@ -74,6 +75,10 @@ struct MapSlot {
 };
 static_assert(sizeof(MapState) <= 256, "MapState must fit the first 256 bytes of the scratch block");
 static_assert(sizeof(LMState) == 484, "bench.py reports sizeof(LMState) as the per-scan device-to-host bytes");
+// The pinned mirror of LMState is followed by the persistent scan kernel's completion stamp (LMArgs::done_host): the host
+// waits for a scan by polling it instead of synchronising the stream (scan2map_collect).
+constexpr size_t kHostStateBytes = 512, kDoneStampOffset = 496;
+static_assert(sizeof(LMState) <= kDoneStampOffset, "the completion stamp sits behind the LMState mirror");
 
 }  // namespace
 
@@ -126,6 +131,9 @@ struct ll_handle_s {
   size_t dq_cap[2] = {0, 0};
   const float4* q_ptr[2] = {nullptr, nullptr};
   int nq[2] = {0, 0};
+  unsigned done_seq = 0;     // LMArgs::done_seq of the scan in flight
+  bool done_polled = false;  // ... which ends with a completion stamp in pinned host memory
+  int q_step = 1;  // LMArgs::q_step of the queries q_ptr points at (2: pcl::PointXYZI records uploaded as they are)
 
   LMState* d_state = nullptr;
   LMState* h_state = nullptr;  // pinned mirror
@@ -340,6 +348,16 @@ inline void unpack_points(void* dst, const float4* src, size_t n, size_t stride)
 }
 
 bool stride_ok(size_t s) { return s == 16 || (s >= 20 && s % 4 == 0); }
+
+// Is p inside a page-locked host allocation (cudaHostAlloc / cudaMallocHost / cudaHostRegister)?
+bool host_ptr_is_pinned(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost;
+}
 
 int upload_points(ll_handle h, float4* d_dst, const void* src, size_t n, size_t stride) {
   if (n == 0) return LL_OK;
@@ -1091,6 +1109,7 @@ LMArgs make_lm_args(ll_handle h, int mode) {
     A.cells[m] = h->slot[m].cells;
     A.mst[m] = h->slot[m].st();
     A.q[m] = h->q_ptr[m];
+    A.q_step = h->q_step;
     A.nq[m] = h->nq[m];
   }
   A.prm = make_lm_params(h->prm);
@@ -1134,6 +1153,7 @@ int set_queries_host(ll_handle h, int m, const void* pts, size_t n, size_t strid
   LL_TRY(ensure_bytes(h, reinterpret_cast<void**>(&h->dq[m]), &h->dq_cap[m], bytes));
   LL_TRY(upload_points(h, h->dq[m], pts, n, stride));
   h->q_ptr[m] = h->dq[m];
+  h->q_step = 1;
   h->nq[m] = (int)n;
   return LL_OK;
 }
@@ -1215,6 +1235,13 @@ int scan2map_enqueue(ll_handle h, const float pose6[6]) {
     }
     int n_jobs = h->n_jobs;
     A.st_host = h->h_state;  // block 0 writes the result straight into the pinned mirror
+    static const bool no_poll = std::getenv("LLB200_NO_DONE_POLL") != nullptr;  // A/B switch for measurements
+    h->done_polled = !no_poll;
+    if (h->done_polled) {
+      A.done_host = reinterpret_cast<unsigned*>(reinterpret_cast<uint8_t*>(h->h_state) + kDoneStampOffset);
+      A.done_seq = ++h->done_seq;
+      if (A.done_seq == 0u) A.done_seq = ++h->done_seq;
+    }
     void* args[] = {&A, &p[0], &p[1], &p[2], &p[3], &p[4], &p[5], &bar, &bar_clear, &GB, &build_map, &build_grid,
                     &segs, &jobs, &n_jobs, &job};
     LL_PROF(h, 8);
@@ -1267,7 +1294,24 @@ void fill_result(const LMState& s, ll_result* r) {
 int scan2map_collect(ll_handle h, float pose6_out[6], ll_result* res) {
   if (!h->scan_pending) return fail(h, LL_ERR_STATE, "no scan2map in flight");
   while (true) {
-    LL_CUDA(h, cudaStreamSynchronize(h->stream));
+    bool seen = false;
+    if (h->done_polled) {
+      // The single-kernel scan ends by writing its result and then a stamp into pinned host memory: poll the stamp instead
+      // of synchronising the stream (the kernel's retirement and the driver's completion path come off the frame). A kernel
+      // that fails never writes it: after a bounded spin the stream is synchronised as before, which reports the error.
+      const volatile unsigned* stamp = reinterpret_cast<const volatile unsigned*>(reinterpret_cast<uint8_t*>(h->h_state) + kDoneStampOffset);
+      const auto t0 = std::chrono::steady_clock::now();
+      for (unsigned spins = 0;; ++spins) {
+        if (*stamp == h->done_seq) { seen = true; break; }
+        if ((spins & 0xfffu) == 0xfffu) {
+          if (cudaStreamQuery(h->stream) != cudaErrorNotReady) break;  // finished (the stamp is there by now) or failed
+          if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(10)) break;
+        }
+      }
+      std::atomic_thread_fence(std::memory_order_acquire);
+      h->done_polled = false;
+    }
+    if (!seen) LL_CUDA(h, cudaStreamSynchronize(h->stream));
     if (h->h_state->done || h->iters_enqueued >= h->prm.iter_count_thres) break;
     const int more = std::min(h->prm.iter_count_thres - h->iters_enqueued, kNextChunk);
     LL_TRY(enqueue_iterations(h, more));
@@ -1417,14 +1461,14 @@ int ll_create(const ll_params* p, int device_id, ll_handle* out) {
             cudaMalloc(reinterpret_cast<void**>(&h->d_qsync), sizeof(unsigned) * 4) == cudaSuccess &&
             cudaMemsetAsync(h->d_qsync, 0, sizeof(unsigned) * 4, h->stream) == cudaSuccess &&
             cudaMemsetAsync(h->d_barriers, 0, sizeof(unsigned) * kBarrierSlots, h->stream) == cudaSuccess &&
-            cudaMallocHost(reinterpret_cast<void**>(&h->h_state), sizeof(LMState)) == cudaSuccess &&
+            cudaMallocHost(reinterpret_cast<void**>(&h->h_state), kHostStateBytes) == cudaSuccess &&
             cudaMemsetAsync(h->d_state, 0, sizeof(LMState), h->stream) == cudaSuccess &&
             cudaStreamSynchronize(h->stream) == cudaSuccess;
   if (!ok) {
     ll_destroy(h);
     return LL_ERR_CUDA;
   }
-  std::memset(h->h_state, 0, sizeof(LMState));
+  std::memset(h->h_state, 0, kHostStateBytes);
   h->counted = true;
   g_live_handles.fetch_add(1);
   *out = h;
@@ -1818,6 +1862,7 @@ int ll_scan2map_async(ll_handle h, const void* corner_scan_ds, size_t n_corner, 
     *stamp = ++h->q_seq;
     h->q_ptr[0] = h->dq[0];
     h->q_ptr[1] = h->dq[0] + n_corner;
+    h->q_step = 1;
     h->nq[0] = (int)n_corner;
     h->nq[1] = (int)n_surf;
     h->q_overlap = true;
@@ -1832,6 +1877,27 @@ int ll_scan2map_async(ll_handle h, const void* corner_scan_ds, size_t n_corner, 
       return fail(h, LL_ERR_CUDA, std::string("query upload: ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3)));
     return LL_OK;
   }
+  // Clouds in PAGE-LOCKED host memory (cudaHostAlloc / cudaHostRegister by the caller) whose records are a whole number of
+  // float4s (pcl::PointXYZI: 32 bytes, {x, y, z, pad} first) go up as they are, one DMA per cloud straight from the caller's
+  // buffer, and the kernel steps over them with LMArgs::q_step — the path only reads x, y, z of a query. That takes the
+  // CPU's packing pass (28 us for 345 KB of cache-cold records on the benchmarked replay, profiles/r02_ab_records.txt)
+  // out of the frame. The buffers must stay untouched until ll_scan2map_wait returns (include/legoloam_b200.h).
+  static const bool no_direct = std::getenv("LLB200_NO_PINNED_DIRECT") != nullptr;  // A/B switch for measurements
+  const bool direct = !no_direct && nt && stride_bytes % 16 == 0 && stride_bytes <= 64 && h->prm.persistent_lm &&
+                      (!n_corner || host_ptr_is_pinned(corner_scan_ds)) && (!n_surf || host_ptr_is_pinned(surf_total_ds));
+  if (direct) {
+    const size_t step = stride_bytes / 16;
+    LL_TRY(ensure_bytes(h, reinterpret_cast<void**>(&h->dq[0]), &h->dq_cap[0], nt * stride_bytes));
+    if (n_corner) LL_CUDA(h, cudaMemcpyAsync(h->dq[0], corner_scan_ds, n_corner * stride_bytes, cudaMemcpyHostToDevice, h->stream));
+    if (n_surf)
+      LL_CUDA(h, cudaMemcpyAsync(h->dq[0] + n_corner * step, surf_total_ds, n_surf * stride_bytes, cudaMemcpyHostToDevice, h->stream));
+    h->q_ptr[0] = h->dq[0];
+    h->q_ptr[1] = h->dq[0] + n_corner * step;
+    h->q_step = (int)step;
+    h->nq[0] = (int)n_corner;
+    h->nq[1] = (int)n_surf;
+    return scan2map_enqueue(h, pose6_in);
+  }
   if (nt) {
     LL_TRY(pinned_acquire(h, nt * sizeof(float4)));
     float4* st = reinterpret_cast<float4*>(h->pinned);
@@ -1842,6 +1908,7 @@ int ll_scan2map_async(ll_handle h, const void* corner_scan_ds, size_t n_corner, 
   }
   h->q_ptr[0] = h->dq[0];
   h->q_ptr[1] = h->dq[0] + n_corner;
+  h->q_step = 1;
   h->nq[0] = (int)n_corner;
   h->nq[1] = (int)n_surf;
   return scan2map_enqueue(h, pose6_in);
@@ -1853,6 +1920,7 @@ int ll_scan2map_dev_async(ll_handle h, const void* d_corner_scan_ds, size_t n_co
   if ((n_corner && !d_corner_scan_ds) || (n_surf && !d_surf_total_ds)) return fail(h, LL_ERR_INVALID_ARG, "NULL query cloud");
   if (h->scan_pending) return fail(h, LL_ERR_STATE, "a scan2map is already in flight");
   LL_CUDA(h, cudaSetDevice(h->device));
+  h->q_step = 1;
   h->q_ptr[0] = static_cast<const float4*>(d_corner_scan_ds);
   h->q_ptr[1] = static_cast<const float4*>(d_surf_total_ds);
   if (!h->q_ptr[0]) h->q_ptr[0] = h->q_ptr[1];

@@ -82,8 +82,12 @@ __device__ __forceinline__ unsigned long long tl_globaltimer() {
   return t;
 }
 #define LL_TL_BAR(e, k) do { if (blockIdx.x == 0 && threadIdx.x == 0 && (e) < 512) g_tl_bar[(e)][(k)] = tl_globaltimer(); } while (0)
+// ... and thread 0 of block 0 at named points between the barriers of the map assembly (printed with the barrier list)
+__device__ unsigned long long g_tl_sub[64];
+#define LL_TL_SUB(id) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_tl_sub[(id)] = tl_globaltimer(); } while (0)
 #else
 #define LL_TL_BAR(e, k) do {} while (0)
+#define LL_TL_SUB(id) do {} while (0)
 #endif
 
 __device__ __forceinline__ void coop_barrier(unsigned* counter, unsigned& epoch) {

@@ -121,6 +121,8 @@ struct LMArgs {
   const MapState* mst[2];
   const float4* q[2];  // corner queries, surf queries (sensor frame)
   int nq[2];
+  int q_step;  // distance between two queries in float4 units: 1 = packed {x, y, z, intensity}; 2 = pcl::PointXYZI records
+               // uploaded as they are (32 bytes, {x, y, z, pad} first: the path only reads x, y, z of a query)
   LMParams prm;
   LMState* st;
   LMState* st_host;  // optional pinned mirror of *st, written by the persistent kernel (saves the copy behind it)
@@ -144,8 +146,18 @@ struct LMArgs {
   // nullptr: the queries were resident before the launch.
   unsigned* q_sync;
   unsigned q_seq;
+  // Completion stamp of the persistent scan kernel in pinned host memory: done_seq is stored (release, system scope) after
+  // the result has been written to st_host, so a host that polls it reads a complete LMState. nullptr: not used.
+  unsigned* done_host;
+  unsigned done_seq;
 };
 constexpr int LM_GUARD_STRIDE = 38;
+
+// Address of query qi of the concatenated list (corner queries first).
+__device__ __forceinline__ const float4* lm_query(const LMArgs& A, int qi) {
+  const bool surf = qi >= A.nq[0];
+  return (surf ? A.q[1] : A.q[0]) + (size_t)(surf ? qi - A.nq[0] : qi) * (size_t)A.q_step;
+}
 
 // ---- 6x6 dense helpers (one thread; column-major like Eigen) -------------------------------------------
 struct Mat6 {
@@ -1645,7 +1657,7 @@ __device__ __forceinline__ float lm_block_pass(const LMArgs& A, const Trig& trig
         if (i < cn) {
           const int qi = sh.qi(c0 + i, A.nq[0]);
           mq[b] = qi < A.nq[0] ? 0 : 1;
-          sel[b] = __ldg(mq[b] ? &A.q[1][qi - A.nq[0]] : &A.q[0][qi]);
+          sel[b] = __ldg(lm_query(A, qi));
         }
       }
 #pragma unroll
@@ -1708,7 +1720,7 @@ __device__ __forceinline__ float lm_block_pass(const LMArgs& A, const Trig& trig
             for (int k = 0; k < 4; ++k) A.e_coeff[4 * qi + k] = keep ? coeff[k] : 0.f;
           }
         } else if (keep) {
-          const float4 p = __ldg(&A.q[m][m ? qi - A.nq[0] : qi]);
+          const float4 p = __ldg(lm_query(A, qi));
           jacobian_row(rt, p.x, p.y, p.z, coeff[0], coeff[1], coeff[2], sv);
           sv[6] = -A.prm.step_size * coeff[3];  // matB (:1500)
           sv[7] = fabsf(coeff[3]);
@@ -1746,7 +1758,7 @@ __device__ __noinline__ void lm_full_search_warp(const LMArgs* Ap, const Trig* t
           need &= need - 1u;
           const int qi = sh.qi(c0 + warp + LM_WARPS * jb[b], A.nq[0]);
           mq[b] = qi < A.nq[0] ? 0 : 1;
-          qs[b] = __ldcg(mq[b] ? &A.q[1][qi - A.nq[0]] : &A.q[0][qi]);  // (L2: the clouds may arrive during the launch)
+          qs[b] = __ldcg(lm_query(A, qi));  // (L2: the clouds may arrive during the launch)
           sel[b] = rigid_transform(trig, qs[b]);
         }
       }
@@ -1880,7 +1892,7 @@ __device__ __forceinline__ float lm_block_pass_cached(const LMArgs& A, const Tri
                       : surf_residual(G, slot[0], slot[1], slot[2], A.prm.fit, coeff);
       }
       if (keep) {
-        const float4 p = __ldcg(&A.q[m][m ? qi - A.nq[0] : qi]);
+        const float4 p = __ldcg(lm_query(A, qi));
         jacobian_row(rt, p.x, p.y, p.z, coeff[0], coeff[1], coeff[2], sv);
         sv[6] = -A.prm.step_size * coeff[3];  // matB (:1500)
         sv[7] = fabsf(coeff[3]);
@@ -2097,6 +2109,11 @@ __global__ void __launch_bounds__(LM_THREADS, 1) lm_persistent_kernel(const __gr
     for (unsigned e = 1; e <= epoch && e < 512; ++e)
       printf("   barrier %3u  arrive %8.2f  release %8.2f  (stage %6.2f)\n", e, (g_tl_bar[e][0] - g_tl_bar[0][1]) * 1e-3,
              (g_tl_bar[e][1] - g_tl_bar[0][1]) * 1e-3, (g_tl_bar[e][1] - g_tl_bar[e - 1][1]) * 1e-3);
+    printf("sub-stage stamps of block 0 (microseconds from kernel entry):");
+    for (int k = 0; k < 64; ++k)
+      if (g_tl_sub[k] > g_tl_bar[0][1]) printf("  [%d] %.2f", k, (g_tl_sub[k] - g_tl_bar[0][1]) * 1e-3);
+    printf("\n");
+    for (int k = 0; k < 64; ++k) g_tl_sub[k] = 0ull;
     const int nb = min((int)gridDim.x, TL_BLOCKS);
     const double us = 1e-3 / 1.965;  // cycles -> us at the 1965 MHz the box runs at under load
     const char* names[9] = {"phase1 5-NN (to block barrier)", "block barrier after phase 1", "phase2 fit + Jacobian row", "shuffle reduce 29 sums",
@@ -2148,6 +2165,11 @@ __global__ void __launch_bounds__(LM_THREADS, 1) lm_persistent_kernel(const __gr
       if (A.st_host) reinterpret_cast<uint32_t*>(A.st_host)[tid] = src[tid];
     }
     if (tid == 0) *barrier_clear = 0u;
+    if (A.st_host && A.done_host) {  // block-uniform
+      __threadfence_system();
+      __syncthreads();
+      if (tid == 0) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(A.done_host), "r"(A.done_seq) : "memory");
+    }
   }
 }
 

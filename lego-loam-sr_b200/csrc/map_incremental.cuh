@@ -251,6 +251,7 @@ __device__ __forceinline__ void inc_build_run(const IncJob& J, const MapBatch& B
     }
   }
   __syncthreads();
+  LL_TL_SUB(2 + 2 * m);  // composites of the added points in shared memory
   if (s_bad) {  // (the same verdict in every block: they all looked at the same points)
     if (tid == 0 && blockIdx.x == 0) M.st->inc_fail = 1;
     return;
@@ -347,6 +348,7 @@ __device__ __forceinline__ void inc_merge(const IncJob& J, const MapBatch& B, in
   const int r_lo = first_tile ? 0 : inc_bound_block(r_key, 0, n_new, __ldcg(o_key + a0));
   const int r_hi = last_tile ? n_new : inc_bound_block(r_key, 0, n_new, __ldcg(o_key + b0));
   int sub_lo = r_lo;
+  LL_TL_SUB(10);  // merge: tile offsets and run bounds known
   for (int a = a0; a < b0 || (a == a0 && a0 >= b0); a += INC_SUB) {  // (one pass with an empty range when the window is empty)
     const int b = min(b0, a + INC_SUB), cnt = max(0, b - a);
     const int sub_hi = b >= b0 ? r_hi : inc_bound_block(r_key, sub_lo, r_hi, __ldcg(o_key + b));
@@ -420,6 +422,7 @@ __device__ __forceinline__ void inc_merge(const IncJob& J, const MapBatch& B, in
     surv_before += sub_total;
     sub_lo = sub_hi;
     __syncthreads();
+    LL_TL_SUB(11 + min(4, (a - a0) / INC_SUB));  // merge: sub-tile written
     if (a0 >= b0) break;
   }
   // bounding box of everything written (finite points), as transform_minmax_kernel
@@ -505,6 +508,7 @@ __device__ __forceinline__ void inc_reduce(const IncJob& J, const MapBatch& B, i
   }
   constexpr int R = INC_SUB / 512;
   uint32_t slot_base = before;
+  LL_TL_SUB(20);  // centroids: output offsets known
   for (int base = tile_begin; base < tile_end; base += INC_SUB) {
     const int sub_n = min(INC_SUB, tile_end - base);
     __syncthreads();
@@ -589,6 +593,7 @@ __device__ __forceinline__ void inc_reduce(const IncJob& J, const MapBatch& B, i
     }
     slot_base += sub_total;
     __syncthreads();
+    LL_TL_SUB(21 + min(4, (base - tile_begin) / INC_SUB));  // centroids: sub-tile done
     if (!s_misc[1]) continue;  // block-uniform
     float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
     int c = 0;
@@ -633,9 +638,13 @@ __device__ __forceinline__ void map_incremental_inline(const IncJob& J, const Ma
   const IncTiling T(nb, J.n_old, false);
   uint32_t* s_w = smem + INC_MERGE_SMEM_WORDS - 64;
   // ---- R | C
-  for (int m = 0; m < 2; ++m)
+  LL_TL_SUB(1);
+  for (int m = 0; m < 2; ++m) {
     if (J.n_new[m] > 0) inc_build_run(J, B, m, reinterpret_cast<unsigned long long*>(smem));
+    LL_TL_SUB(3 + 2 * m);  // ... ranked and placed
+  }
   __syncthreads();
+  LL_TL_SUB(6);
   if (blk >= T.first) {
     const int w = blk - T.first;
     if (nb - T.first < 2) {
@@ -645,6 +654,7 @@ __device__ __forceinline__ void map_incremental_inline(const IncJob& J, const Ma
       inc_count(J, m, t, T.nw[m], J.w[m].counts + t, s_w);
     }
   }
+  LL_TL_SUB(7);  // surviving entries counted
   coop_barrier(barrier, epoch);
   // ---- M
   if (blk >= T.first) {
