@@ -6,7 +6,6 @@
 
 #include <algorithm>
 #include <atomic>
-#include <chrono>
 #include <cmath>
 #if defined(__SSE2__)
 #include <emmintrin.h>
@@ -75,10 +74,6 @@ struct MapSlot {
 };
 static_assert(sizeof(MapState) <= 256, "MapState must fit the first 256 bytes of the scratch block");
 static_assert(sizeof(LMState) == 484, "bench.py reports sizeof(LMState) as the per-scan device-to-host bytes");
-// The pinned mirror of LMState is followed by the persistent scan kernel's completion stamp (LMArgs::done_host): the host
-// waits for a scan by polling it instead of synchronising the stream (scan2map_collect).
-constexpr size_t kHostStateBytes = 512, kDoneStampOffset = 496;
-static_assert(sizeof(LMState) <= kDoneStampOffset, "the completion stamp sits behind the LMState mirror");
 
 }  // namespace
 
@@ -131,8 +126,6 @@ struct ll_handle_s {
   size_t dq_cap[2] = {0, 0};
   const float4* q_ptr[2] = {nullptr, nullptr};
   int nq[2] = {0, 0};
-  unsigned done_seq = 0;     // LMArgs::done_seq of the scan in flight
-  bool done_polled = false;  // ... which ends with a completion stamp in pinned host memory
   int q_step = 1;  // LMArgs::q_step of the queries q_ptr points at (2: pcl::PointXYZI records uploaded as they are)
 
   LMState* d_state = nullptr;
@@ -1235,13 +1228,6 @@ int scan2map_enqueue(ll_handle h, const float pose6[6]) {
     }
     int n_jobs = h->n_jobs;
     A.st_host = h->h_state;  // block 0 writes the result straight into the pinned mirror
-    static const bool no_poll = std::getenv("LLB200_NO_DONE_POLL") != nullptr;  // A/B switch for measurements
-    h->done_polled = !no_poll;
-    if (h->done_polled) {
-      A.done_host = reinterpret_cast<unsigned*>(reinterpret_cast<uint8_t*>(h->h_state) + kDoneStampOffset);
-      A.done_seq = ++h->done_seq;
-      if (A.done_seq == 0u) A.done_seq = ++h->done_seq;
-    }
     void* args[] = {&A, &p[0], &p[1], &p[2], &p[3], &p[4], &p[5], &bar, &bar_clear, &GB, &build_map, &build_grid,
                     &segs, &jobs, &n_jobs, &job};
     LL_PROF(h, 8);
@@ -1294,24 +1280,7 @@ void fill_result(const LMState& s, ll_result* r) {
 int scan2map_collect(ll_handle h, float pose6_out[6], ll_result* res) {
   if (!h->scan_pending) return fail(h, LL_ERR_STATE, "no scan2map in flight");
   while (true) {
-    bool seen = false;
-    if (h->done_polled) {
-      // The single-kernel scan ends by writing its result and then a stamp into pinned host memory: poll the stamp instead
-      // of synchronising the stream (the kernel's retirement and the driver's completion path come off the frame). A kernel
-      // that fails never writes it: after a bounded spin the stream is synchronised as before, which reports the error.
-      const volatile unsigned* stamp = reinterpret_cast<const volatile unsigned*>(reinterpret_cast<uint8_t*>(h->h_state) + kDoneStampOffset);
-      const auto t0 = std::chrono::steady_clock::now();
-      for (unsigned spins = 0;; ++spins) {
-        if (*stamp == h->done_seq) { seen = true; break; }
-        if ((spins & 0xfffu) == 0xfffu) {
-          if (cudaStreamQuery(h->stream) != cudaErrorNotReady) break;  // finished (the stamp is there by now) or failed
-          if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(10)) break;
-        }
-      }
-      std::atomic_thread_fence(std::memory_order_acquire);
-      h->done_polled = false;
-    }
-    if (!seen) LL_CUDA(h, cudaStreamSynchronize(h->stream));
+    LL_CUDA(h, cudaStreamSynchronize(h->stream));
     if (h->h_state->done || h->iters_enqueued >= h->prm.iter_count_thres) break;
     const int more = std::min(h->prm.iter_count_thres - h->iters_enqueued, kNextChunk);
     LL_TRY(enqueue_iterations(h, more));
@@ -1461,14 +1430,14 @@ int ll_create(const ll_params* p, int device_id, ll_handle* out) {
             cudaMalloc(reinterpret_cast<void**>(&h->d_qsync), sizeof(unsigned) * 4) == cudaSuccess &&
             cudaMemsetAsync(h->d_qsync, 0, sizeof(unsigned) * 4, h->stream) == cudaSuccess &&
             cudaMemsetAsync(h->d_barriers, 0, sizeof(unsigned) * kBarrierSlots, h->stream) == cudaSuccess &&
-            cudaMallocHost(reinterpret_cast<void**>(&h->h_state), kHostStateBytes) == cudaSuccess &&
+            cudaMallocHost(reinterpret_cast<void**>(&h->h_state), sizeof(LMState)) == cudaSuccess &&
             cudaMemsetAsync(h->d_state, 0, sizeof(LMState), h->stream) == cudaSuccess &&
             cudaStreamSynchronize(h->stream) == cudaSuccess;
   if (!ok) {
     ll_destroy(h);
     return LL_ERR_CUDA;
   }
-  std::memset(h->h_state, 0, kHostStateBytes);
+  std::memset(h->h_state, 0, sizeof(LMState));
   h->counted = true;
   g_live_handles.fetch_add(1);
   *out = h;

@@ -146,10 +146,6 @@ struct LMArgs {
   // nullptr: the queries were resident before the launch.
   unsigned* q_sync;
   unsigned q_seq;
-  // Completion stamp of the persistent scan kernel in pinned host memory: done_seq is stored (release, system scope) after
-  // the result has been written to st_host, so a host that polls it reads a complete LMState. nullptr: not used.
-  unsigned* done_host;
-  unsigned done_seq;
 };
 constexpr int LM_GUARD_STRIDE = 38;
 
@@ -964,8 +960,11 @@ constexpr int LM_PERSISTENT_SMEM = LM_LOOP_SMEM > INC_SMEM_BYTES ? LM_LOOP_SMEM 
 //     in the same one-metre cell, accepted or not (sparse parts of the map, where most rejected queries live);
 //   radius (R > 0): the points within R of the query, as described above.
 // All 32 lanes.
+// Returns (warp-uniform) the signature of the five neighbours' order as knn5_guard_check computes it — the name under which
+// phase 2 stores the fit's geometry of THIS iteration, so that the next iteration's guard test can already reuse it — or
+// LM_GEO_NONE when no guard was set up.
 template <bool kFresh>
-__device__ __noinline__ void knn_cache_fill(const float4* sorted, int my_start, int my_count, float sx, float sy, float sz,
+__device__ __noinline__ uint32_t knn_cache_fill(const float4* sorted, int my_start, int my_count, float sx, float sy, float sz,
                                             uint32_t d5bits, uint32_t i5bits, float4 qsensor, int lane, float4* cand,
                                             float4* center, float4* qpt, float4* t1, int* cnt_out, uint32_t* prev_out) {
   constexpr int kRowLane[9] = {12, 3, 9, 15, 21, 0, 6, 18, 24};
@@ -1069,6 +1068,26 @@ __device__ __noinline__ void knn_cache_fill(const float4* sorted, int my_start, 
     d6 = __reduce_min_sync(0xffffffffu, d6);
     const bool fits = whole || (base <= LM_CACHE_CAND && (rejected || base >= 5));
     if (fits || attempt == 2) {
+      uint32_t sig = LM_GEO_NONE;
+      if (fits && __popc(members) == 5) {  // (warp-uniform) rank of each member, in ascending position, by (d2, index)
+        __syncwarp();  // the set was written by all lanes
+        const int pos = (int)__fns(members, 0u, (lane < 5 ? lane : 0) + 1);
+        const float4 m = cand[pos];
+        float df = sx - m.x;  // evalMetric order, as everywhere
+        float d = df * df;
+        df = sy - m.y;
+        d += df * df;
+        df = sz - m.z;
+        d += df * df;
+        const uint32_t db = __float_as_uint(d), ib = __float_as_uint(m.w);
+        int rank = 0;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+          const uint32_t dk = __shfl_sync(0xffffffffu, db, k), ik = __shfl_sync(0xffffffffu, ib, k);
+          rank += (k != lane && pair_less(dk, ik, db, ib)) ? 1 : 0;
+        }
+        sig = __reduce_or_sync(0xffffffffu, lane < 5 ? (uint32_t)rank << (3 * lane) : 0u) | (5u << 15);  // (no sixth member: rank 5)
+      }
       if (lane == 0) {
         *center = make_float4(sx, sy, sz, R);
         // (an EMPTY cell-complete set is stored as count 33: cnt must be > 0 to be used, and no lane is below 33 <= 32)
@@ -1085,9 +1104,10 @@ __device__ __noinline__ void knn_cache_fill(const float4* sorted, int my_start, 
           *t1 = make_float4(sx, sy, sz, fminf(fminf(s6, 1.f + face), 1.f));
         }
       }
-      return;
+      return sig;
     }
   }
+  return LM_GEO_NONE;
 }
 
 // Step 1 of the per-thread cached search (see knn5_thread): up to six member points (absent: d = LM_EMPTY_D2), the guard
@@ -1151,50 +1171,37 @@ __device__ __forceinline__ bool knn5_guard_check(const float4 sel, const float4 
 //           those five was at least G away. At q (delta = |q - c'|) they are at least G - delta away, so if the largest of
 //           the five distances from q, D5, satisfies  sqrt(D5) + delta + slack <= G  the five are still the answer (their
 //           ORDER may have changed: they are re-sorted by (d2, index)). Five loads, a sorting network, one test.
-//   step 2  otherwise the whole cached set (<= 32 points, top six by insertion): the five nearest within the set, the
-//           set-level proof of knn_cache_fill's comment (radius sets: sqrt(D5) + |q - c| + slack <= R; cell-complete sets:
-//           same cell; rejected-query sets: same cell and |q - c| + slack <= R - 1), and a fresh guard for step 1:
-//           G = min(sixth distance within the set, what the set's kind guarantees about the points outside it, 1 m).
-// Returns true when the outcome is proven exact (slot filled: slot[3] = 1 with the neighbours in ascending (d2, index)
-// order, or slot[3] = 0 for a query proven to have fewer than five points within range); false: search in full.
+//   step 2  otherwise the whole cached set (<= 32 points): its seven nearest by (d2, index), found by the WARP — one
+//           candidate per lane, seven arg-min rounds (knn5_warp_step2; one thread inserting 32 candidates into a sorted
+//           list took 4 us, and the grid barrier made every block wait for the one thread of the scan that had to) —
+//           then, by the thread again: the set-level proof of knn_cache_fill's comment (radius sets: sqrt(D5) + |q - c| +
+//           slack <= R; cell-complete sets: same cell; rejected-query sets: same cell and |q - c| + slack <= R - 1), and
+//           a fresh guard for step 1: G = min(sixth distance within the set, what the set's kind guarantees about the
+//           points outside it, 1 m).
+// Proven exact: slot filled (slot[3] = 1 with the neighbours in ascending (d2, index) order, or slot[3] = 0 for a query
+// proven to have fewer than five points within range); otherwise the query is searched in full.
 // Distances are evaluated exactly as in the full search, so a proven answer is bit-identical to it.
-__device__ __noinline__ bool knn5_thread(const KnnCache C, int i, const Trig* trig_p, float max_sq_dist, float* slot) {
+// Step 1: returns 1 = proven, 2 = scan the set (step 2); sel_out = the query in the map frame.
+__device__ __noinline__ int knn5_thread_step1(const KnnCache C, int i, const Trig* trig_p, float max_sq_dist, float* slot, float4* sel_out) {
   const Trig trig = *trig_p;
   const uint32_t max_bits = __float_as_uint(max_sq_dist);
   const float4 sel = rigid_transform(trig, C.qpt[i]);
+  *sel_out = sel;
   const float4* cand = C.cand + i * LM_CACHE_CAND;
-  auto dist_bits = [&](const float4 m) {
-    float df = sel.x - m.x;  // evalMetric order (nanoflann.hpp:431-439), as in the full search
-    float d = df * df;
-    df = sel.y - m.y;
-    d += df * df;
-    df = sel.z - m.z;
-    d += df * df;
-    return __float_as_uint(d);
-  };
-  auto approx_sqrt = [](float v) { return v > 0.f ? v * rsqrtf(v) : 0.f; };  // 2 ulp: the slack dwarfs it
-  auto dist_to = [&](const float4 c) {
-    float df = sel.x - c.x;
-    float d = df * df;
-    df = sel.y - c.y;
-    d += df * df;
-    df = sel.z - c.z;
-    d += df * df;
-    return approx_sqrt(d);
-  };
-  auto emit = [&](const float4 (&nb)[5]) {
-    slot[0] = sel.x; slot[1] = sel.y; slot[2] = sel.z; slot[3] = 1.f;
-#pragma unroll
-    for (int k = 0; k < 5; ++k) { slot[4 + 3 * k] = nb[k].x; slot[5 + 3 * k] = nb[k].y; slot[6 + 3 * k] = nb[k].z; }
-  };
-  // ---- step 1
   const float4 t1 = C.t1[i];
   if (t1.w < 0.f) {
     // a REJECTED query's guard: at c' the fifth-nearest map point was H = -t1.w > 1 m away, so it is still farther than
     // 1 m from q when |q - c'| + slack <= H - 1: fewer than five points within range, as before.
-    if (dist_to(t1) + LM_T1_SLACK <= -t1.w - 1.f) {
+    float df = sel.x - t1.x;
+    float d = df * df;
+    df = sel.y - t1.y;
+    d += df * df;
+    df = sel.z - t1.z;
+    d += df * df;
+    const float dl = d > 0.f ? d * rsqrtf(d) : 0.f;  // 2 ulp: the slack dwarfs it
+    if (dl + LM_T1_SLACK <= -t1.w - 1.f) {
       slot[0] = sel.x; slot[1] = sel.y; slot[2] = sel.z; slot[3] = 0.f;
-      return true;
+      return 1;
     }
   } else if (t1.w > 0.f) {
     // the members of last time: five, or six when the fifth and sixth were too close to call (step 2 below)
@@ -1208,83 +1215,143 @@ __device__ __noinline__ bool knn5_thread(const KnnCache C, int i, const Trig* tr
       mask &= mask - 1u;
       nb[k] = cand[j];
     }
-    if (knn5_guard_check(sel, nb, have, t1, max_bits, __float_as_uint(C.geo[2 * i + 1].w), slot)) return true;
+    if (knn5_guard_check(sel, nb, have, t1, max_bits, __float_as_uint(C.geo[2 * i + 1].w), slot)) return 1;
   }
-  slot[19] = 0.f;                          // (everything below changes the neighbour list: the stored geometry is void)
-  slot[20] = __uint_as_float(LM_GEO_NONE);
   LL_TL_COUNT_THREAD(6);
   if (t1.w == 0.f) LL_TL_COUNT_THREAD(7);
-  // ---- step 2: the whole set, top six by (d2, index). Columns are visited rotated by the thread index: the threads of a
-  //      warp read different rows of `cand` (stride 512 bytes), and the rotation spreads them over the banks.
-  const int cnt_raw = C.cnt[i];
-  const int cnt = cnt_raw <= LM_CACHE_CAND ? cnt_raw : 0;  // (an EMPTY set is stored as count 33)
+  return 2;
+}
+
+// Step 2 for the lanes in `todo` (all 32 lanes call, converged): C / i / sel / slot are each lane's own query. Returns the
+// ballot of the lanes whose outcome is proven.
+__device__ __noinline__ unsigned knn5_warp_step2(unsigned todo, const KnnCache C, int i, float4 sel, float max_sq_dist, float* slot) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t max_bits = __float_as_uint(max_sq_dist);
+  const bool mine = (todo >> lane) & 1u;
   constexpr int NT = 7;  // five neighbours, the sixth for the guard, the seventh for the guard of a six-member set
   uint32_t td[NT], ti[NT];
   int tc[NT];
 #pragma unroll
   for (int k = 0; k < NT; ++k) { td[k] = LM_EMPTY_D2; ti[k] = 0xffffffffu; tc[k] = 0; }
-#pragma unroll 4
-  for (int j = 0; j < LM_CACHE_CAND; ++j) {
-    const int col = (j + (int)threadIdx.x) & (LM_CACHE_CAND - 1);
-    if (col >= cnt) continue;
-    const float4 m = cand[col];
-    const uint32_t db = dist_bits(m), ib = __float_as_uint(m.w);
-    if (pair_less(db, ib, td[NT - 1], ti[NT - 1])) {  // (all candidates: a rejected query's guard needs the distances beyond 1 m too)
-      td[NT - 1] = db; ti[NT - 1] = ib; tc[NT - 1] = col;
+  const float4* my_cand = C.cand + (mine ? i : 0) * LM_CACHE_CAND;
+  const int my_cnt_raw = mine ? C.cnt[i] : 0;
+  const int my_cnt = my_cnt_raw <= LM_CACHE_CAND ? my_cnt_raw : 0;  // (an EMPTY set is stored as count 33)
+  // ---- the seven nearest of each set by (d2, index): lane j takes candidate j, seven arg-min rounds
+#pragma unroll 1
+  for (unsigned rest = todo; rest; rest &= rest - 1u) {
+    const int src = __ffs(rest) - 1;
+    const float4* cand = reinterpret_cast<const float4*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(my_cand), src));
+    const int cnt = __shfl_sync(0xffffffffu, my_cnt, src);
+    const float qx = __shfl_sync(0xffffffffu, sel.x, src), qy = __shfl_sync(0xffffffffu, sel.y, src), qz = __shfl_sync(0xffffffffu, sel.z, src);
+    uint32_t db = LM_EMPTY_D2, ib = 0xffffffffu;
+    if (lane < cnt) {
+      const float4 m = cand[lane];
+      float df = qx - m.x;  // evalMetric order (nanoflann.hpp:431-439), as in the full search
+      float d = df * df;
+      df = qy - m.y;
+      d += df * df;
+      df = qz - m.z;
+      d += df * df;
+      db = __float_as_uint(d);  // (all candidates: a rejected query's guard needs the distances beyond 1 m too)
+      ib = __float_as_uint(m.w);
+    }
 #pragma unroll
-      for (int k = NT - 1; k > 0; --k) {
-        if (pair_less(td[k], ti[k], td[k - 1], ti[k - 1])) {
-          const uint32_t a = td[k]; td[k] = td[k - 1]; td[k - 1] = a;
-          const uint32_t b = ti[k]; ti[k] = ti[k - 1]; ti[k - 1] = b;
-          const int c = tc[k]; tc[k] = tc[k - 1]; tc[k - 1] = c;
-        }
+    for (int r = 0; r < NT; ++r) {
+      const uint32_t m = __reduce_min_sync(0xffffffffu, db);
+      unsigned bal = __ballot_sync(0xffffffffu, db == m);
+      if (m != LM_EMPTY_D2 && (bal & (bal - 1u)) != 0u) {  // warp-uniform; an exact d2 tie: the lower map index first
+        const uint32_t om = __reduce_min_sync(0xffffffffu, db == m ? ib : 0xffffffffu);
+        bal = __ballot_sync(0xffffffffu, db == m && ib == om);
       }
+      const int wl = __ffs(bal) - 1;
+      const uint32_t wi = __shfl_sync(0xffffffffu, ib, wl);
+      if (lane == src && m != LM_EMPTY_D2) { td[r] = m; ti[r] = wi; tc[r] = wl; }
+      if (lane == wl && m != LM_EMPTY_D2) { db = LM_EMPTY_D2; ib = 0xffffffffu; }
     }
   }
-  const bool acc = td[4] < max_bits;  // five points within range
-  const float4 ctr = C.center[i];
-  const bool same_cell = floorf(sel.x) == floorf(ctr.x) && floorf(sel.y) == floorf(ctr.y) && floorf(sel.z) == floorf(ctr.z);
-  const float sl = dist_to(ctr);
-  const float sD = td[4] != LM_EMPTY_D2 ? approx_sqrt(__uint_as_float(td[4])) : 3.f;  // (no fifth point in the set at all: any bound above 2 m serves)
-  bool ok;
-  float outside;  // lower bound of the distance from sel to every map point that is not in the set
-  // distance from sel to the nearest face of its one-metre cell: a point outside the 27 cells is at least 1 m + that away
-  const float fx = sel.x - floorf(sel.x), fy = sel.y - floorf(sel.y), fz = sel.z - floorf(sel.z);
-  const float face = fminf(fminf(fminf(fx, 1.f - fx), fminf(fy, 1.f - fy)), fminf(fz, 1.f - fz));
-  if (ctr.w < 0.f) {          // cell-complete
-    ok = same_cell;
-    outside = 1.f + face;
-  } else if (ctr.w <= 1.f) {  // radius set within 1 m: the ball is inside the 27 cells wherever the query goes
-    ok = acc && sD + sl + LM_CACHE_SLACK <= ctr.w;
-    outside = ctr.w - sl;
-  } else {                    // radius set beyond 1 m (fifth neighbour near the limit, or a rejected query): complete only
-                              // for points within 1 m of a query that is still in the cell the set was collected for
-    ok = same_cell && (acc ? sD + sl + LM_CACHE_SLACK <= ctr.w : sl + LM_CACHE_SLACK <= ctr.w - 1.f);
-    outside = fminf(ctr.w - sl, 1.f + face);
-  }
-  if (!ok) return false;
-  if (!acc) {
-    slot[0] = sel.x; slot[1] = sel.y; slot[2] = sel.z; slot[3] = 0.f;
-    // guard for step 1: the fifth-nearest point overall is at least H away (within the set: sD; outside it: `outside`)
-    const float H = fminf(sD, outside);
-    C.t1[i] = H > 1.f ? make_float4(sel.x, sel.y, sel.z, -H) : make_float4(0.f, 0.f, 0.f, 0.f);
-    return true;
-  }
-  float4 nb[5];
-  uint32_t mask = 0u;
+  // ---- each lane of `todo`: the proofs on its own seven
+  bool proven = false;
+  if (mine) {
+    auto approx_sqrt = [](float v) { return v > 0.f ? v * rsqrtf(v) : 0.f; };  // 2 ulp: the slack dwarfs it
+    const float4* cand = my_cand;
+    const float4 t1_old = C.t1[i];
+    const uint32_t old_mask = t1_old.w > 0.f ? C.prev[i] : 0u;
+    const bool acc = td[4] < max_bits;  // five points within range
+    const float4 ctr = C.center[i];
+    const bool same_cell = floorf(sel.x) == floorf(ctr.x) && floorf(sel.y) == floorf(ctr.y) && floorf(sel.z) == floorf(ctr.z);
+    float df = sel.x - ctr.x;
+    float dc = df * df;
+    df = sel.y - ctr.y;
+    dc += df * df;
+    df = sel.z - ctr.z;
+    dc += df * df;
+    const float sl = approx_sqrt(dc);
+    const float sD = td[4] != LM_EMPTY_D2 ? approx_sqrt(__uint_as_float(td[4])) : 3.f;  // (no fifth point in the set at all: any bound above 2 m serves)
+    bool ok;
+    float outside;  // lower bound of the distance from sel to every map point that is not in the set
+    // distance from sel to the nearest face of its one-metre cell: a point outside the 27 cells is at least 1 m + that away
+    const float fx = sel.x - floorf(sel.x), fy = sel.y - floorf(sel.y), fz = sel.z - floorf(sel.z);
+    const float face = fminf(fminf(fminf(fx, 1.f - fx), fminf(fy, 1.f - fy)), fminf(fz, 1.f - fz));
+    if (ctr.w < 0.f) {          // cell-complete
+      ok = same_cell;
+      outside = 1.f + face;
+    } else if (ctr.w <= 1.f) {  // radius set within 1 m: the ball is inside the 27 cells wherever the query goes
+      ok = acc && sD + sl + LM_CACHE_SLACK <= ctr.w;
+      outside = ctr.w - sl;
+    } else {                    // radius set beyond 1 m (fifth neighbour near the limit, or a rejected query): complete only
+                                // for points within 1 m of a query that is still in the cell the set was collected for
+      ok = same_cell && (acc ? sD + sl + LM_CACHE_SLACK <= ctr.w : sl + LM_CACHE_SLACK <= ctr.w - 1.f);
+      outside = fminf(ctr.w - sl, 1.f + face);
+    }
+    slot[19] = 0.f;  // (unless the list below turns out to be the one the stored geometry was computed for)
+    slot[20] = __uint_as_float(LM_GEO_NONE);
+    if (ok && !acc) {
+      slot[0] = sel.x; slot[1] = sel.y; slot[2] = sel.z; slot[3] = 0.f;
+      // guard for step 1: the fifth-nearest point overall is at least H away (within the set: sD; outside it: `outside`)
+      const float H = fminf(sD, outside);
+      C.t1[i] = H > 1.f ? make_float4(sel.x, sel.y, sel.z, -H) : make_float4(0.f, 0.f, 0.f, 0.f);
+      proven = true;
+    } else if (ok) {
+      uint32_t mask = 0u;
+      slot[0] = sel.x; slot[1] = sel.y; slot[2] = sel.z; slot[3] = 1.f;
 #pragma unroll
-  for (int k = 0; k < 5; ++k) { nb[k] = cand[tc[k]]; mask |= 1u << tc[k]; }
-  emit(nb);
-  // the guard of step 1: the nearest point that is not a member. When the sixth is within a millimetre of the fifth (a
-  // few queries per scan: the guard would never hold) the sixth joins the members and the seventh bounds the rest.
-  float d6 = td[5] != LM_EMPTY_D2 ? approx_sqrt(__uint_as_float(td[5])) : 1.f;  // (capped at 1 m below)
-  if (d6 - sD < 1e-3f && td[5] != LM_EMPTY_D2) {
-    mask |= 1u << tc[5];
-    d6 = td[6] != LM_EMPTY_D2 ? approx_sqrt(__uint_as_float(td[6])) : 1.f;
+      for (int k = 0; k < 5; ++k) {
+        const float4 nb = cand[tc[k]];
+        slot[4 + 3 * k] = nb.x; slot[5 + 3 * k] = nb.y; slot[6 + 3 * k] = nb.z;
+        mask |= 1u << tc[k];
+      }
+      // the guard of step 1: the nearest point that is not a member. When the sixth is within a millimetre of the fifth (a
+      // few queries per scan: the guard would never hold) the sixth joins the members and the seventh bounds the rest.
+      int nmem = 5;
+      float d6 = td[5] != LM_EMPTY_D2 ? approx_sqrt(__uint_as_float(td[5])) : 1.f;  // (capped at 1 m below)
+      if (d6 - sD < 1e-3f && td[5] != LM_EMPTY_D2) {
+        mask |= 1u << tc[5];
+        nmem = 6;
+        d6 = td[6] != LM_EMPTY_D2 ? approx_sqrt(__uint_as_float(td[6])) : 1.f;
+      }
+      // The name of this neighbour list as knn5_guard_check spells it: the members in ascending position, three bits of
+      // rank by (d2, index) each (an absent sixth: rank 5). The same members in the same order as when the fit's geometry
+      // was stored = the same geometry; and phase 2 stores what it computes now under the new name.
+      uint32_t sig = 0u, mm = mask;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        int rank = 5;
+        if (mm) {
+          const int col = __ffs(mm) - 1;
+          mm &= mm - 1u;
+#pragma unroll
+          for (int r = 0; r < 6; ++r) rank = (r < nmem && tc[r] == col) ? r : rank;
+        }
+        sig |= (uint32_t)rank << (3 * k);
+      }
+      slot[19] = (mask == old_mask && sig == __float_as_uint(C.geo[2 * i + 1].w)) ? 1.f : 0.f;
+      slot[20] = __uint_as_float(sig);
+      C.prev[i] = mask;
+      C.t1[i] = make_float4(sel.x, sel.y, sel.z, fminf(fminf(d6, outside), 1.f));
+      proven = true;
+    }
   }
-  C.prev[i] = mask;
-  C.t1[i] = make_float4(sel.x, sel.y, sel.z, fminf(fminf(d6, outside), 1.f));
-  return true;
+  return __ballot_sync(0xffffffffu, proven);
 }
 
 // The 29 running sums of one LM iteration in a fixed order: 21 upper-triangular AtA entries (row-major),
@@ -1795,8 +1862,10 @@ __device__ __noinline__ void lm_full_search_warp(const LMArgs* Ap, const Trig* t
           const int ci = has_slot ? i : 0;
           const uint32_t d5 = __shfl_sync(0xffffffffu, acc[b] ? od[b] : LM_EMPTY_D2, 4);
           const uint32_t i5 = __shfl_sync(0xffffffffu, oi[b], 4);
-          knn_cache_fill<kFresh>(A.sorted[mq[b]], q_start[b], q_count[b], sel[b].x, sel[b].y, sel[b].z, d5, i5, qs[b], lane,
-                                 &Cq.cand[ci * LM_CACHE_CAND], &Cq.center[ci], &Cq.qpt[ci], &Cq.t1[ci], &Cq.cnt[ci], &Cq.prev[ci]);
+          const uint32_t sig = knn_cache_fill<kFresh>(A.sorted[mq[b]], q_start[b], q_count[b], sel[b].x, sel[b].y, sel[b].z, d5, i5, qs[b],
+                                                      lane, &Cq.cand[ci * LM_CACHE_CAND], &Cq.center[ci], &Cq.qpt[ci], &Cq.t1[ci],
+                                                      &Cq.cnt[ci], &Cq.prev[ci]);
+          if (lane == 5) slot[20] = __uint_as_float(sig);  // phase 2 stores this iteration's geometry under that name
         }
       }
     }
@@ -1827,19 +1896,34 @@ __device__ __forceinline__ float lm_block_pass_cached(const LMArgs& A, const Tri
     if (tid < LM_WARPS) s_need[tid] = 0u;
     __syncthreads();
     LL_TL_WARP(0);
-    if (my_i >= 0) {
-      bool proven = false;
-      if (first_chunk && my_i < LM_QCAP) {
-        if (C.cnt[my_i] > 0) {
-          proven = knn5_thread(C, my_i, &trig_s, A.prm.fit.max_sq_dist, &s_slot[tid * LM_SLOT]);
-          LL_TL_COUNT_THREAD(5);
-          if (proven) LL_TL_COUNT_THREAD(4);
+    {
+      int state = 0;  // 0 = no cached set: full search; 1 = proven; 2 = the set must be scanned (by the warp, below)
+      KnnCache Cq = C;
+      int ci = 0;
+      float4 sel = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (my_i >= 0) {
+        bool cached = false;
+        if (first_chunk && my_i < LM_QCAP) {
+          ci = my_i;
+          cached = C.cnt[my_i] > 0;
+        } else if (A.g_guard) {
+          Cq = knn_cache_of_record(A.g_guard + (size_t)sh.qi(c0 + my_i, A.nq[0]) * LM_GUARD_STRIDE);
+          cached = Cq.cnt[0] > 0;
         }
-      } else if (A.g_guard) {
-        const KnnCache G = knn_cache_of_record(A.g_guard + (size_t)sh.qi(c0 + my_i, A.nq[0]) * LM_GUARD_STRIDE);
-        if (G.cnt[0] > 0) proven = knn5_thread(G, 0, &trig_s, A.prm.fit.max_sq_dist, &s_slot[tid * LM_SLOT]);
+        if (cached) {
+          state = knn5_thread_step1(Cq, ci, &trig_s, A.prm.fit.max_sq_dist, &s_slot[tid * LM_SLOT], &sel);
+          LL_TL_COUNT_THREAD(5);
+        }
       }
-      if (!proven) atomicOr(&s_need[my_i % LM_WARPS], 1u << (my_i / LM_WARPS));
+      const unsigned todo = __ballot_sync(0xffffffffu, state == 2);
+      if (todo) {  // warp-uniform
+        const unsigned done = knn5_warp_step2(todo, Cq, ci, sel, A.prm.fit.max_sq_dist, &s_slot[tid * LM_SLOT]);
+        if (state == 2) state = (done >> (tid & 31)) & 1u ? 1 : 0;
+      }
+#ifdef LL_TIMELINE
+      if (state == 1) LL_TL_COUNT_THREAD(4);
+#endif
+      if (my_i >= 0 && state != 1) atomicOr(&s_need[my_i % LM_WARPS], 1u << (my_i / LM_WARPS));
     }
     __syncthreads();
     const unsigned need = s_need[warp];
@@ -2165,11 +2249,6 @@ __global__ void __launch_bounds__(LM_THREADS, 1) lm_persistent_kernel(const __gr
       if (A.st_host) reinterpret_cast<uint32_t*>(A.st_host)[tid] = src[tid];
     }
     if (tid == 0) *barrier_clear = 0u;
-    if (A.st_host && A.done_host) {  // block-uniform
-      __threadfence_system();
-      __syncthreads();
-      if (tid == 0) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(A.done_host), "r"(A.done_seq) : "memory");
-    }
   }
 }
 

@@ -32,7 +32,7 @@ constexpr int INC_RUN_MAX = 16384;  // points per map the keyframes added in one
 constexpr int INC_RUN_BITS = 14;
 constexpr int INC_MAX_DEAD = 8;     // keyframes dropped in one merge
 constexpr int INC_MAX_SEGS = 12;    // clouds of the added keyframes (three per keyframe)
-constexpr int INC_SUB = 2048;       // window entries per sub-tile of the merge
+constexpr int INC_SUB = 2560;       // window entries per sub-tile of the merge / centroid pass (five per thread); a block cuts its tile into EQUAL sub-tiles
 constexpr int INC_MAX_BLOCKS = 160;
 constexpr unsigned long long INC_KEY_NONFINITE = ~0ull;
 constexpr int INC_SMEM_BYTES = INC_RUN_MAX * 8;  // the run's sort network; the other stages need less
@@ -349,8 +349,9 @@ __device__ __forceinline__ void inc_merge(const IncJob& J, const MapBatch& B, in
   const int r_hi = last_tile ? n_new : inc_bound_block(r_key, 0, n_new, __ldcg(o_key + b0));
   int sub_lo = r_lo;
   LL_TL_SUB(10);  // merge: tile offsets and run bounds known
-  for (int a = a0; a < b0 || (a == a0 && a0 >= b0); a += INC_SUB) {  // (one pass with an empty range when the window is empty)
-    const int b = min(b0, a + INC_SUB), cnt = max(0, b - a);
+  const int m_nsub = max(1, (b0 - a0 + INC_SUB - 1) / INC_SUB), m_step = max(1, (b0 - a0 + m_nsub - 1) / m_nsub);
+  for (int a = a0; a < b0 || (a == a0 && a0 >= b0); a += m_step) {  // (one pass with an empty range when the window is empty)
+    const int b = min(b0, a + m_step), cnt = max(0, b - a);
     const int sub_hi = b >= b0 ? r_hi : inc_bound_block(r_key, sub_lo, r_hi, __ldcg(o_key + b));
     const int ns = sub_hi - sub_lo;
     const bool slice_in_smem = ns <= INC_SUB;
@@ -422,7 +423,7 @@ __device__ __forceinline__ void inc_merge(const IncJob& J, const MapBatch& B, in
     surv_before += sub_total;
     sub_lo = sub_hi;
     __syncthreads();
-    LL_TL_SUB(11 + min(4, (a - a0) / INC_SUB));  // merge: sub-tile written
+    LL_TL_SUB(11 + min(4, (a - a0) / m_step));  // merge: sub-tile written
     if (a0 >= b0) break;
   }
   // bounding box of everything written (finite points), as transform_minmax_kernel
@@ -509,8 +510,9 @@ __device__ __forceinline__ void inc_reduce(const IncJob& J, const MapBatch& B, i
   constexpr int R = INC_SUB / 512;
   uint32_t slot_base = before;
   LL_TL_SUB(20);  // centroids: output offsets known
-  for (int base = tile_begin; base < tile_end; base += INC_SUB) {
-    const int sub_n = min(INC_SUB, tile_end - base);
+  const int r_nsub = max(1, (tile_end - tile_begin + INC_SUB - 1) / INC_SUB), r_step = max(1, (tile_end - tile_begin + r_nsub - 1) / r_nsub);
+  for (int base = tile_begin; base < tile_end; base += r_step) {
+    const int sub_n = min(r_step, tile_end - base);
     __syncthreads();
     if (tid == 0) { s_misc[0] = INC_SUB; s_misc[1] = 0; }  // [0] first non-finite entry, [1] a segment crosses the end
     __syncthreads();
@@ -593,7 +595,7 @@ __device__ __forceinline__ void inc_reduce(const IncJob& J, const MapBatch& B, i
     }
     slot_base += sub_total;
     __syncthreads();
-    LL_TL_SUB(21 + min(4, (base - tile_begin) / INC_SUB));  // centroids: sub-tile done
+    LL_TL_SUB(21 + min(4, (base - tile_begin) / r_step));  // centroids: sub-tile done
     if (!s_misc[1]) continue;  // block-uniform
     float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
     int c = 0;
