@@ -746,17 +746,19 @@ __device__ __forceinline__ void knn5_chunks(const float4* sorted, int my_start, 
 // LM_EMPTY_D2 / 0xffffffff), and acc[q] (warp-uniform) says whether five neighbours within range exist.
 constexpr int LM_KNN_BATCH = 3;
 
-template <bool kFresh>
+template <bool kFresh, int NB>
 __device__ __forceinline__ void warp_knn5_batch(const float4* const (&sorted)[2], const int2* const (&cells)[2],
-                                                const GridGeom (&geom)[2], const int (&mq)[LM_KNN_BATCH],
-                                                const float4 (&sel)[LM_KNN_BATCH], float max_sq_dist, int lane,
-                                                uint32_t (&od)[LM_KNN_BATCH], uint32_t (&oi)[LM_KNN_BATCH],
-                                                uint32_t (&op)[LM_KNN_BATCH], bool (&acc)[LM_KNN_BATCH],
-                                                int (&q_start)[LM_KNN_BATCH], int (&q_count)[LM_KNN_BATCH],
-                                                int (&total)[LM_KNN_BATCH]) {
+                                                const GridGeom (&geom)[2], const int (&mq)[NB],
+                                                const float4 (&sel)[NB], float max_sq_dist, int lane,
+                                                uint32_t (&od)[NB], uint32_t (&oi)[NB],
+                                                uint32_t (&op)[NB], bool (&acc)[NB],
+                                                int (&q_start)[NB], int (&q_count)[NB],
+                                                int (&total)[NB]) {
   // q_start / q_count (per lane: the merged cell row this lane describes, valid on lanes 0, 3, ..., 24) and total (the
   // number of candidates in the 27 cells, warp-uniform) are returned for knn_cache_fill.
-  constexpr int NB = LM_KNN_BATCH;
+  // NB = LM_KNN_BATCH in the first rounds of a warp; a single remaining query (the fourth of a warp's share in iterations
+  // 0 and 1, the odd query whose cached set failed later on) takes the NB = 1 instance: the search is instruction-fetch
+  // bound, and a third of the unrolled code is a third of the time.
   constexpr int kRowLane[9] = {12, 3, 9, 15, 21, 0, 6, 18, 24};
   const uint32_t max_bits = __float_as_uint(max_sq_dist);
   // ---- stage 1: the 27 cell descriptors of every query (one load per lane per query, all in flight together)
@@ -1229,10 +1231,10 @@ __device__ __noinline__ unsigned knn5_warp_step2(unsigned todo, const KnnCache C
   const uint32_t max_bits = __float_as_uint(max_sq_dist);
   const bool mine = (todo >> lane) & 1u;
   constexpr int NT = 7;  // five neighbours, the sixth for the guard, the seventh for the guard of a six-member set
-  uint32_t td[NT], ti[NT];
+  uint32_t td[NT];
   int tc[NT];
 #pragma unroll
-  for (int k = 0; k < NT; ++k) { td[k] = LM_EMPTY_D2; ti[k] = 0xffffffffu; tc[k] = 0; }
+  for (int k = 0; k < NT; ++k) { td[k] = LM_EMPTY_D2; tc[k] = 0; }
   const float4* my_cand = C.cand + (mine ? i : 0) * LM_CACHE_CAND;
   const int my_cnt_raw = mine ? C.cnt[i] : 0;
   const int my_cnt = my_cnt_raw <= LM_CACHE_CAND ? my_cnt_raw : 0;  // (an EMPTY set is stored as count 33)
@@ -1264,8 +1266,7 @@ __device__ __noinline__ unsigned knn5_warp_step2(unsigned todo, const KnnCache C
         bal = __ballot_sync(0xffffffffu, db == m && ib == om);
       }
       const int wl = __ffs(bal) - 1;
-      const uint32_t wi = __shfl_sync(0xffffffffu, ib, wl);
-      if (lane == src && m != LM_EMPTY_D2) { td[r] = m; ti[r] = wi; tc[r] = wl; }
+      if (lane == src && m != LM_EMPTY_D2) { td[r] = m; tc[r] = wl; }
       if (lane == wl && m != LM_EMPTY_D2) { db = LM_EMPTY_D2; ib = 0xffffffffu; }
     }
   }
@@ -1733,7 +1734,7 @@ __device__ __forceinline__ float lm_block_pass(const LMArgs& A, const Trig& trig
       uint32_t od[LM_KNN_BATCH], oi[LM_KNN_BATCH], op[LM_KNN_BATCH];
       bool acc[LM_KNN_BATCH];
       int q_start[LM_KNN_BATCH], q_count[LM_KNN_BATCH], q_total[LM_KNN_BATCH];
-      warp_knn5_batch<kFresh>(A.sorted, A.cells, geom, mq, sel, A.prm.fit.max_sq_dist, lane, od, oi, op, acc, q_start, q_count, q_total);
+      warp_knn5_batch<kFresh, LM_KNN_BATCH>(A.sorted, A.cells, geom, mq, sel, A.prm.fit.max_sq_dist, lane, od, oi, op, acc, q_start, q_count, q_total);
 #pragma unroll
       for (int b = 0; b < LM_KNN_BATCH; ++b) {
         const int i = i0 + b * LM_WARPS;
@@ -1801,8 +1802,73 @@ __device__ __forceinline__ float lm_block_pass(const LMArgs& A, const Trig& trig
   return run_sum;
 }
 
+// One round of step (B): the full search of the next NB queries in `need`, their staging slots, and their cached sets.
+template <bool kFresh, int NB>
+__device__ __forceinline__ void lm_full_search_round(const LMArgs& A, const Trig& trig, const GridGeom (&geom)[2], float* s_slot,
+                                                     const KnnCache& C, const QShare& sh, int c0, int nc, int nc_pad, unsigned& need,
+                                                     bool first_chunk, bool do_fill) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int jb[NB], mq[NB];
+  float4 sel[NB], qs[NB];
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    jb[b] = -1;
+    mq[b] = -1;
+    sel[b] = make_float4(0.f, 0.f, 0.f, 0.f);
+    qs[b] = sel[b];
+    if (need) {
+      jb[b] = __ffs(need) - 1;
+      need &= need - 1u;
+      const int qi = sh.qi(c0 + warp + LM_WARPS * jb[b], A.nq[0]);
+      mq[b] = qi < A.nq[0] ? 0 : 1;
+      qs[b] = __ldcg(lm_query(A, qi));  // (L2: the clouds may arrive during the launch)
+      sel[b] = rigid_transform(trig, qs[b]);
+    }
+  }
+  uint32_t od[NB], oi[NB], op[NB];
+  bool acc[NB];
+  int q_start[NB], q_count[NB], q_total[NB];
+  warp_knn5_batch<kFresh, NB>(A.sorted, A.cells, geom, mq, sel, A.prm.fit.max_sq_dist, lane, od, oi, op, acc, q_start, q_count, q_total);
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    if (jb[b] < 0) continue;  // warp-uniform
+    LL_TL_COUNT(0);
+    if (q_total[b] > 32 * LM_CAND_UNROLL) LL_TL_COUNT(1);
+    else if (!acc[b] && q_total[b] > LM_CACHE_CAND) LL_TL_COUNT(3);
+    const int i = warp + LM_WARPS * jb[b];
+    float* slot = &s_slot[(i < nc ? i : nc_pad + (i - nc)) * LM_SLOT];
+    if (lane < 5) {
+      if (acc[b]) {
+        const float4 nb = map_ld<kFresh>(&A.sorted[mq[b]][op[b]]);
+        slot[4 + 3 * lane] = nb.x;
+        slot[5 + 3 * lane] = nb.y;
+        slot[6 + 3 * lane] = nb.z;
+      }
+    } else if (lane == 5) {
+      slot[0] = sel[b].x;
+      slot[1] = sel[b].y;
+      slot[2] = sel[b].z;
+      slot[3] = acc[b] ? 1.f : 0.f;
+      slot[19] = 0.f;  // a new neighbour list: no stored geometry applies
+      slot[20] = __uint_as_float(LM_GEO_NONE);
+    }
+    const bool has_slot = first_chunk && i < LM_QCAP;
+    if (do_fill && (has_slot || A.g_guard)) {  // (re)build this query's cached set around where it is now
+      const KnnCache Cq = has_slot ? C : knn_cache_of_record(A.g_guard + (size_t)sh.qi(c0 + i, A.nq[0]) * LM_GUARD_STRIDE);
+      const int ci = has_slot ? i : 0;
+      const uint32_t d5 = __shfl_sync(0xffffffffu, acc[b] ? od[b] : LM_EMPTY_D2, 4);
+      const uint32_t i5 = __shfl_sync(0xffffffffu, oi[b], 4);
+      const uint32_t sig = knn_cache_fill<kFresh>(A.sorted[mq[b]], q_start[b], q_count[b], sel[b].x, sel[b].y, sel[b].z, d5, i5, qs[b],
+                                                  lane, &Cq.cand[ci * LM_CACHE_CAND], &Cq.center[ci], &Cq.qpt[ci], &Cq.t1[ci],
+                                                  &Cq.cnt[ci], &Cq.prev[ci]);
+      if (lane == 5) slot[20] = __uint_as_float(sig);  // phase 2 stores this iteration's geometry under that name
+    }
+  }
+}
+
 // Step (B) of lm_block_pass_cached for one warp: the full search of the queries in `need` (bit j = query warp + 16 j of
-// the chunk starting at c0), three at a time, their staging slots, and their cached sets. Out of line on purpose.
+// the chunk starting at c0), three at a time (a single remaining one by itself), their staging slots, and their cached
+// sets. Out of line on purpose.
 template <bool kFresh>
 __device__ __noinline__ void lm_full_search_warp(const LMArgs* Ap, const Trig* trig_p, const GridGeom* geom_p, float* s_slot,
                                                  KnnCache C, QShare sh, int c0, int nc, int nc_pad, unsigned need, bool first_chunk,
@@ -1810,65 +1876,10 @@ __device__ __noinline__ void lm_full_search_warp(const LMArgs* Ap, const Trig* t
   const LMArgs& A = *Ap;
   const Trig trig = *trig_p;
   const GridGeom geom[2] = {geom_p[0], geom_p[1]};
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    while (need) {
-      int jb[LM_KNN_BATCH], mq[LM_KNN_BATCH];
-      float4 sel[LM_KNN_BATCH], qs[LM_KNN_BATCH];
-#pragma unroll
-      for (int b = 0; b < LM_KNN_BATCH; ++b) {
-        jb[b] = -1;
-        mq[b] = -1;
-        sel[b] = make_float4(0.f, 0.f, 0.f, 0.f);
-        qs[b] = sel[b];
-        if (need) {
-          jb[b] = __ffs(need) - 1;
-          need &= need - 1u;
-          const int qi = sh.qi(c0 + warp + LM_WARPS * jb[b], A.nq[0]);
-          mq[b] = qi < A.nq[0] ? 0 : 1;
-          qs[b] = __ldcg(lm_query(A, qi));  // (L2: the clouds may arrive during the launch)
-          sel[b] = rigid_transform(trig, qs[b]);
-        }
-      }
-      uint32_t od[LM_KNN_BATCH], oi[LM_KNN_BATCH], op[LM_KNN_BATCH];
-      bool acc[LM_KNN_BATCH];
-      int q_start[LM_KNN_BATCH], q_count[LM_KNN_BATCH], q_total[LM_KNN_BATCH];
-      warp_knn5_batch<kFresh>(A.sorted, A.cells, geom, mq, sel, A.prm.fit.max_sq_dist, lane, od, oi, op, acc, q_start, q_count, q_total);
-#pragma unroll
-      for (int b = 0; b < LM_KNN_BATCH; ++b) {
-        if (jb[b] < 0) continue;  // warp-uniform
-        LL_TL_COUNT(0);
-        if (q_total[b] > 32 * LM_CAND_UNROLL) LL_TL_COUNT(1);
-        else if (!acc[b] && q_total[b] > LM_CACHE_CAND) LL_TL_COUNT(3);
-        const int i = warp + LM_WARPS * jb[b];
-        float* slot = &s_slot[(i < nc ? i : nc_pad + (i - nc)) * LM_SLOT];
-        if (lane < 5) {
-          if (acc[b]) {
-            const float4 nb = map_ld<kFresh>(&A.sorted[mq[b]][op[b]]);
-            slot[4 + 3 * lane] = nb.x;
-            slot[5 + 3 * lane] = nb.y;
-            slot[6 + 3 * lane] = nb.z;
-          }
-        } else if (lane == 5) {
-          slot[0] = sel[b].x;
-          slot[1] = sel[b].y;
-          slot[2] = sel[b].z;
-          slot[3] = acc[b] ? 1.f : 0.f;
-          slot[19] = 0.f;  // a new neighbour list: no stored geometry applies
-          slot[20] = __uint_as_float(LM_GEO_NONE);
-        }
-        const bool has_slot = first_chunk && i < LM_QCAP;
-        if (do_fill && (has_slot || A.g_guard)) {  // (re)build this query's cached set around where it is now
-          const KnnCache Cq = has_slot ? C : knn_cache_of_record(A.g_guard + (size_t)sh.qi(c0 + i, A.nq[0]) * LM_GUARD_STRIDE);
-          const int ci = has_slot ? i : 0;
-          const uint32_t d5 = __shfl_sync(0xffffffffu, acc[b] ? od[b] : LM_EMPTY_D2, 4);
-          const uint32_t i5 = __shfl_sync(0xffffffffu, oi[b], 4);
-          const uint32_t sig = knn_cache_fill<kFresh>(A.sorted[mq[b]], q_start[b], q_count[b], sel[b].x, sel[b].y, sel[b].z, d5, i5, qs[b],
-                                                      lane, &Cq.cand[ci * LM_CACHE_CAND], &Cq.center[ci], &Cq.qpt[ci], &Cq.t1[ci],
-                                                      &Cq.cnt[ci], &Cq.prev[ci]);
-          if (lane == 5) slot[20] = __uint_as_float(sig);  // phase 2 stores this iteration's geometry under that name
-        }
-      }
-    }
+  while (need) {
+    if ((need & (need - 1u)) == 0u) lm_full_search_round<kFresh, 1>(A, trig, geom, s_slot, C, sh, c0, nc, nc_pad, need, first_chunk, do_fill);
+    else lm_full_search_round<kFresh, LM_KNN_BATCH>(A, trig, geom, s_slot, C, sh, c0, nc, nc_pad, need, first_chunk, do_fill);
+  }
 }
 
 // The same two phases for the single-kernel scan, with the candidate cache (KnnCache above) in front of the full search.

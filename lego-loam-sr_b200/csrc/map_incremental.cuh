@@ -261,31 +261,18 @@ __device__ __forceinline__ void inc_build_run(const IncJob& J, const MapBatch& B
   // chosen so that the slice is one round of the block's warps (69 points per block at 10 k: E = 5, not two rounds of 4)
   const int per = (n + (int)gridDim.x - 1) / (int)gridDim.x;
   const int lo = min(n, (int)blockIdx.x * per), hi = min(n, lo + per);
-  const int want = (hi - lo + nwarps - 1) / nwarps;
+  // (E from the LARGER of the two maps' runs: both maps then go through the same instance of the loop, whose code is
+  //  fetched once — these stages run once per scan, straight after an L2 flush in the benchmark, and every instruction is a miss)
+  const int per_max = (max(J.n_new[0], J.n_new[1]) + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int want = (per_max + nwarps - 1) / nwarps;
   if (want <= 4) inc_rank_slice<4>(J, B, m, s_key, n, lo, hi);
   else if (want <= 6) inc_rank_slice<6>(J, B, m, s_key, n, lo, hi);
   else inc_rank_slice<8>(J, B, m, s_key, n, lo, hi);
 }
 
 // ---- C: surviving entries of this worker's tile of the old window.
-__device__ __forceinline__ void inc_count(const IncJob& J, int m, int t, int ntiles, uint32_t* out, uint32_t* s_w) {
-  const WindowBuffers& W = J.w[m];
-  const int n = J.n_old[m];
-  const int len = (n + ntiles - 1) / ntiles;
-  const int a = min(n, t * len), b = min(n, a + len);
-  uint32_t c = 0;
-  if (J.n_dead == 0) {
-    c = threadIdx.x == 0 ? (uint32_t)(b - a) : 0u;
-  } else {
-    const uint32_t* __restrict__ tag = W.tag[J.cur];
-    for (int i0 = a + (int)threadIdx.x; i0 < b; i0 += 4 * (int)blockDim.x) {  // four loads in flight
-      uint32_t tv[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) tv[u] = i0 + u * (int)blockDim.x < b ? __ldcg(tag + i0 + u * (int)blockDim.x) : 0u;
-#pragma unroll
-      for (int u = 0; u < 4; ++u) c += (i0 + u * (int)blockDim.x < b && inc_alive(tv[u], J)) ? 1u : 0u;
-    }
-  }
+// (block sum of the threads' counts -> *out)
+__device__ __forceinline__ void inc_count_finish(uint32_t c, uint32_t* out, uint32_t* s_w) {
   c = __reduce_add_sync(0xffffffffu, c);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   __syncthreads();
@@ -296,6 +283,26 @@ __device__ __forceinline__ void inc_count(const IncJob& J, int m, int t, int nti
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += s_w[w];
     *out = tot;
   }
+}
+__device__ __forceinline__ void inc_count(const IncJob& J, int m, int t, int ntiles, uint32_t* out, uint32_t* s_w) {
+  const WindowBuffers& W = J.w[m];
+  const int n = J.n_old[m];
+  const int len = (n + ntiles - 1) / ntiles;
+  const int a = min(n, t * len), b = min(n, a + len);
+  uint32_t c = 0;
+  if (J.n_dead == 0) {
+    c = threadIdx.x == 0 ? (uint32_t)(b - a) : 0u;
+  } else {
+    const uint32_t* __restrict__ tag = W.tag[J.cur];
+    for (int i0 = a + (int)threadIdx.x; i0 < b; i0 += 10 * (int)blockDim.x) {  // ten loads in flight: one round for a 0.62 M-entry window on 148 blocks
+      uint32_t tv[10];
+#pragma unroll
+      for (int u = 0; u < 10; ++u) tv[u] = i0 + u * (int)blockDim.x < b ? __ldcg(tag + i0 + u * (int)blockDim.x) : 0u;
+#pragma unroll
+      for (int u = 0; u < 10; ++u) c += (i0 + u * (int)blockDim.x < b && inc_alive(tv[u], J)) ? 1u : 0u;
+    }
+  }
+  inc_count_finish(c, out, s_w);
 }
 
 // ---- M: this worker's tile of the old window merged with its slice of the run, into buffer cur ^ 1.
@@ -352,21 +359,30 @@ __device__ __forceinline__ void inc_merge(const IncJob& J, const MapBatch& B, in
   const int m_nsub = max(1, (b0 - a0 + INC_SUB - 1) / INC_SUB), m_step = max(1, (b0 - a0 + m_nsub - 1) / m_nsub);
   for (int a = a0; a < b0 || (a == a0 && a0 >= b0); a += m_step) {  // (one pass with an empty range when the window is empty)
     const int b = min(b0, a + m_step), cnt = max(0, b - a);
+    // old entries of the sub-tile: R consecutive ones per thread; their keys, tags and points all go out before the search
+    // for the run's share of the sub-tile (two more round trips), so the three latencies overlap
+    constexpr int R = INC_SUB / 512;
+    static_assert(R * 512 == INC_SUB && GI_THREADS == 512, "sub-tile = R entries per thread of a 512-thread block");
+    const int l0 = R * tid;
+    unsigned long long k4[R];
+    uint32_t tg[R];
+    float4 q4[R];
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      const bool in = l0 + k < cnt;
+      k4[k] = in ? __ldcg(o_key + a + l0 + k) : INC_KEY_NONFINITE;
+      tg[k] = in ? __ldcg(o_tag + a + l0 + k) : 0u;
+      q4[k] = in ? __ldcg(o_pts + a + l0 + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     const int sub_hi = b >= b0 ? r_hi : inc_bound_block(r_key, sub_lo, r_hi, __ldcg(o_key + b));
     const int ns = sub_hi - sub_lo;
     const bool slice_in_smem = ns <= INC_SUB;
-    // old entries of the sub-tile: 4 consecutive ones per thread
-    constexpr int R = INC_SUB / 512;
-    static_assert(R * 512 == INC_SUB && GI_THREADS == 512, "sub-tile = four entries per thread of a 512-thread block");
-    const int l0 = R * tid;
-    unsigned long long k4[R];
     bool al[R];
     uint32_t c = 0;
 #pragma unroll
     for (int k = 0; k < R; ++k) {
       const bool in = l0 + k < cnt;
-      k4[k] = in ? __ldcg(o_key + a + l0 + k) : INC_KEY_NONFINITE;
-      al[k] = in && inc_alive(__ldcg(o_tag + a + l0 + k), J);
+      al[k] = in && inc_alive(tg[k], J);
       s_keys[l0 + k] = k4[k];
       c += al[k] ? 1u : 0u;
     }
@@ -402,10 +418,10 @@ __device__ __forceinline__ void inc_merge(const IncJob& J, const MapBatch& B, in
       if (!al[k]) continue;
       const int nb = slice_in_smem ? inc_bound<false, false>(s_slice, 0, ns, k4[k]) : inc_bound<false, true>(r_key + sub_lo, 0, ns, k4[k]);
       const size_t pos = (size_t)surv_before + s_pref[l0 + k] + (size_t)(sub_lo + nb);
-      const float4 q = __ldcg(o_pts + a + l0 + k);
+      const float4 q = q4[k];
       d_pts[pos] = q;
       d_key[pos] = k4[k];
-      d_tag[pos] = __ldcg(o_tag + a + l0 + k);
+      d_tag[pos] = tg[k];
       track(q);
     }
     // run entries of the slice -> (their index in the run) + (surviving old entries with a key <= theirs)
@@ -448,16 +464,16 @@ __device__ __forceinline__ uint32_t inc_count_heads(const IncJob& J, int m, int 
   const int len = (n + ntiles - 1) / ntiles;
   const int a = min(n, t * len), b = min(n, a + len);
   uint32_t c = 0;
-  for (int i0 = a + (int)threadIdx.x; i0 < b; i0 += 4 * (int)blockDim.x) {  // eight loads in flight
-    unsigned long long kv[4], pv[4];
+  for (int i0 = a + (int)threadIdx.x; i0 < b; i0 += 10 * (int)blockDim.x) {  // twenty loads in flight: one round per tile
+    unsigned long long kv[10], pv[10];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < 10; ++u) {
       const int i = i0 + u * (int)blockDim.x;
       kv[u] = i < b ? __ldcg(key + i) : INC_KEY_NONFINITE;
       pv[u] = (i < b && i > 0) ? __ldcg(key + i - 1) : INC_KEY_NONFINITE;
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < 10; ++u) {
       const int i = i0 + u * (int)blockDim.x;
       const bool head = i < b && kv[u] < INC_KEY_NONFINITE - 1ull && (i == 0 || pv[u] != kv[u]);
       c += head ? 1u : 0u;
@@ -641,6 +657,27 @@ __device__ __forceinline__ void map_incremental_inline(const IncJob& J, const Ma
   uint32_t* s_w = smem + INC_MERGE_SMEM_WORDS - 64;
   // ---- R | C
   LL_TL_SUB(1);
+  // C's loads go out first: the tags of this block's tile of the old window (cold: DRAM) are in registers by the time the
+  // run is built (one round of ten loads per thread covers a 0.62 M-entry window on 148 blocks; a longer tile counts below)
+  constexpr int kPre = 10;
+  uint32_t tv[kPre];
+  bool pre = false;
+  int c_a = 0, c_b = 0;
+  if (blk >= T.first && nb - T.first >= 2 && J.n_dead > 0) {
+    const int w = blk - T.first, m = w < T.nw[0] ? 0 : 1, t = m ? w - T.nw[0] : w;
+    const int n = J.n_old[m], len = (n + T.nw[m] - 1) / T.nw[m];
+    c_a = min(n, t * len);
+    c_b = min(n, c_a + len);
+    pre = c_b - c_a <= kPre * (int)blockDim.x;  // block-uniform
+    if (pre) {
+      const uint32_t* __restrict__ tag = J.w[m].tag[J.cur];
+#pragma unroll
+      for (int u = 0; u < kPre; ++u) {
+        const int i = c_a + (int)threadIdx.x + u * (int)blockDim.x;
+        tv[u] = i < c_b ? __ldcg(tag + i) : 0u;
+      }
+    }
+  }
   for (int m = 0; m < 2; ++m) {
     if (J.n_new[m] > 0) inc_build_run(J, B, m, reinterpret_cast<unsigned long long*>(smem));
     LL_TL_SUB(3 + 2 * m);  // ... ranked and placed
@@ -651,6 +688,12 @@ __device__ __forceinline__ void map_incremental_inline(const IncJob& J, const Ma
     const int w = blk - T.first;
     if (nb - T.first < 2) {
       for (int m = 0; m < 2; ++m) inc_count(J, m, 0, 1, J.w[m].counts, s_w);
+    } else if (pre) {
+      const int m = w < T.nw[0] ? 0 : 1, t = m ? w - T.nw[0] : w;
+      uint32_t c = 0;
+#pragma unroll
+      for (int u = 0; u < kPre; ++u) c += (c_a + (int)threadIdx.x + u * (int)blockDim.x < c_b && inc_alive(tv[u], J)) ? 1u : 0u;
+      inc_count_finish(c, J.w[m].counts + t, s_w);
     } else {
       const int m = w < T.nw[0] ? 0 : 1, t = m ? w - T.nw[0] : w;
       inc_count(J, m, t, T.nw[m], J.w[m].counts + t, s_w);
