@@ -562,12 +562,14 @@ def run_batch(args, rank, world, device, dist):
         odom = np.array([synth.mat_to_pose(G @ synth.pose_to_mat(p)) for p in d["odom"][:n_frames]], np.float32)
         seqs.append(dict(odom=odom, clouds=clouds))
     sms = torch.cuda.get_device_properties(device).multi_processor_count
-    threads = max(1, min(args.threads, len(ids)))
+    cpus = rank_cpus(int(os.environ.get("LOCAL_RANK", "0")), world)
+    # one host thread per sequence in flight, each spinning on its own core while its scan runs: never more threads than
+    # this rank has cores (a 2-GPU box with 12 cores gave each rank 6: eight threads on them ran the batch at 65 % per GPU)
+    threads = max(1, min(args.threads, len(ids), len(cpus) if cpus else args.threads))
     nb = args.batch_blocks if args.batch_blocks >= 0 else max(1, sms // threads)
     kw = dict(persistent_lm=0) if nb == 0 else dict(persistent_lm=1, lm_max_blocks=nb)
     nodes = [host.MapOptimization(headline_params(abi, **kw), device=device, loop_closure_enabled=True, search_num=WINDOW,
                                   reserve=(1 << 18, 1 << 20, 1 << 15)) for _ in ids]
-    cpus = rank_cpus(int(os.environ.get("LOCAL_RANK", "0")), world)
     host.batch_replay(nodes, seqs, 0, WINDOW, threads, cpus)          # untimed: fill the windows
     torch.cuda.synchronize(device)
     if world > 1:
