@@ -351,6 +351,11 @@ bool host_ptr_is_pinned(const void* p) {
   }
   return a.type == cudaMemoryTypeHost;
 }
+// ... the whole range [p, p + bytes)? (first and last byte: a registered range is contiguous, and a buffer that leaves one
+// registration for another is still page-locked throughout)
+bool host_range_is_pinned(const void* p, size_t bytes) {
+  return bytes == 0 || (host_ptr_is_pinned(p) && host_ptr_is_pinned(static_cast<const uint8_t*>(p) + bytes - 1));
+}
 
 int upload_points(ll_handle h, float4* d_dst, const void* src, size_t n, size_t stride) {
   if (n == 0) return LL_OK;
@@ -1853,7 +1858,7 @@ int ll_scan2map_async(ll_handle h, const void* corner_scan_ds, size_t n_corner, 
   // out of the frame. The buffers must stay untouched until ll_scan2map_wait returns (include/legoloam_b200.h).
   static const bool no_direct = std::getenv("LLB200_NO_PINNED_DIRECT") != nullptr;  // A/B switch for measurements
   const bool direct = !no_direct && nt && stride_bytes % 16 == 0 && stride_bytes <= 64 && h->prm.persistent_lm &&
-                      (!n_corner || host_ptr_is_pinned(corner_scan_ds)) && (!n_surf || host_ptr_is_pinned(surf_total_ds));
+                      host_range_is_pinned(corner_scan_ds, n_corner * stride_bytes) && host_range_is_pinned(surf_total_ds, n_surf * stride_bytes);
   if (direct) {
     const size_t step = stride_bytes / 16;
     LL_TRY(ensure_bytes(h, reinterpret_cast<void**>(&h->dq[0]), &h->dq_cap[0], nt * stride_bytes));
