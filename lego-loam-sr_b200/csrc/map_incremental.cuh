@@ -11,14 +11,15 @@
 //     full path: stable sort), i.e. keyframes in list order, per keyframe corner | surf then outlier, then point index.
 // So the window W of a map is kept on the device as ONE array of (absolute voxel key, keyframe tag, point) sorted by
 // (key, list order). A frame then needs:
-//   R  the added keyframes' clouds: transform, key, sort (one block per map, bitonic network in shared memory)      ┐ one
-//   C  the old window: count the entries whose keyframe stays, per tile                                             ┘ barrier
+//   R  the added keyframes' clouds: transform, key, RANK (every block holds all composites in shared memory and ranks  ┐ one
+//      its own slice of the points: inc_build_run)                                                                    │
+//   C  the old window: count the entries whose keyframe stays, per tile (its loads are issued before R)               ┘ barrier
 //   M  stable merge of the surviving entries with the new run into the other buffer (old before new on equal keys,
 //      exactly the order a rebuild would produce), bounding box of what is written                                    barrier
 //   V  segment heads per tile | barrier | ordered centroid sums -> laserCloud*FromMapDS, exactly as the full path     barrier
 // instead of transform (all 50 keyframes) + 3 radix passes over ~0.6 M pairs + reduce. Anything the scheme cannot
-// represent (PCL's int32-overflow pass-through, voxel coordinates beyond +-2^20, a new run whose own box needs more than
-// 32 key bits) raises MapState::inc_fail; the host then rebuilds through the full path (abi.cu).
+// represent (PCL's int32-overflow pass-through, voxel coordinates beyond +-2^20, an added point more than 2048 voxels
+// from the added keyframe's position) raises MapState::inc_fail; the host then rebuilds through the full path (abi.cu).
 // A longer list of added keyframes (the default branch at start-up, a rebuild after a pose correction) is fed in groups
 // of <= INC_RUN_MAX points per map, one merge each (map_inc_kernel); only the last group computes the centroids.
 #pragma once
@@ -205,9 +206,10 @@ __device__ __forceinline__ void inc_rank_slice(const IncJob& J, const MapBatch& 
 // RANKED. Every block transforms all the added points itself (a few thousand: cheaper than a grid barrier between a
 // transform stage and a sort stage) and keeps their 64-bit composites (voxel coordinates relative to a host-given origin,
 // arrival index: unique, so the order is the stable one) in shared memory; it then owns a contiguous slice of the points and
-// counts, for each of them, the composites below its own — four points per pass over the keys, one warp per four points —
-// which is its position in the run. n^2 / blocks comparisons: ~6 us for 10 k points on 148 blocks; the host takes the
-// full path when that budget is exceeded (few blocks, abi.cu). smem: INC_RUN_MAX u64.
+// counts, for each of them, the composites below its own — E points per pass over the keys, one warp per E points —
+// which is its position in the run. n^2 / blocks comparisons: 13-16 us for 10 k points on 148 blocks (64-bit compares, three
+// instructions each; a sample-splitter bucket ranking was built and measured: not faster, profiles/r02_ab_records.txt); the
+// host takes the full path when that budget is exceeded (few blocks, abi.cu). smem: INC_RUN_MAX u64.
 __device__ __forceinline__ void inc_build_run(const IncJob& J, const MapBatch& B, int m, unsigned long long* s_key) {
   const MapBuffers& M = B.m[m];
   const int tid = threadIdx.x, nwarps = blockDim.x >> 5, n = J.n_new[m];
