@@ -11,8 +11,10 @@ extractSurroundingKeyFrames (transform + concatenate + VoxelGrid 0.2/0.4 + searc
 registered. 50 scans are registered first to fill the window (untimed set-up), then W warm-up scans, then K timed scans.
 
   value : scans/s with every input cloud already resident in HBM (device pointers through the C ABI); CUDA events.
-  e2e   : the same through the reference-facing C++ mirror with HOST pcl::PointXYZI clouds: pack + H2D of the scan's
-          five clouds and D2H of the result inside the timed region; WALL clock per step (the call a user makes).
+  e2e   : the same through the reference-facing C++ mirror with HOST pcl::PointXYZI clouds in page-locked memory (the
+          contract's "inputs in pinned host memory"; BENCH_PAGEABLE=1 for pageable ones): H2D of the scan's five clouds
+          (the two query clouds as the 32-byte records they are, the three keyframe clouds packed) and D2H of the result
+          inside the timed region; WALL clock per step (the call a user makes).
   checks.parity : the timed frames replayed once more with the oracle registering the same scan against the device's
           own map and prior; the line is marked failed when a pose differs by more than 1e-4 m / 1e-5 rad, or when the
           checked replay's poses are not bit-identical to the timed legs'.
