@@ -530,16 +530,25 @@ def run_raw_frame(seed, device, with_cpu):
 
 
 # ----------------------------------------------------------------------------------------------- batched replay
+_RANK_CPUS = None
+
+
 def rank_cpus(local_rank, world):
-    """Disjoint slice of the host cores for this rank (its threads stay next to each other and off the other ranks')."""
+    """Disjoint slice of the host cores for this rank (its threads stay next to each other and off the other ranks').
+    Computed ONCE per process, from the affinity the process started with: main() then restricts the process to its
+    slice, and a second slicing of that slice (the batched replay asks again) left 2 of 8 cores at N = 4."""
+    global _RANK_CPUS
+    if _RANK_CPUS is not None:
+        return _RANK_CPUS
     try:
         cores = sorted(os.sched_getaffinity(0))
     except Exception:
         return []
-    if world <= 1 or len(cores) < 2 * world:
-        return cores
-    per = len(cores) // world
-    return cores[local_rank * per:(local_rank + 1) * per]
+    if world > 1 and len(cores) >= 2 * world:
+        per = len(cores) // world
+        cores = cores[local_rank * per:(local_rank + 1) * per]
+    _RANK_CPUS = cores
+    return cores
 
 
 def run_batch(args, rank, world, device, dist):
@@ -567,16 +576,22 @@ def run_batch(args, rank, world, device, dist):
     cpus = rank_cpus(int(os.environ.get("LOCAL_RANK", "0")), world)
     # one host thread per sequence in flight, each spinning on its own core while its scan runs: never more threads than
     # this rank has cores (a 2-GPU box with 12 cores gave each rank 6: eight threads on them ran the batch at 65 % per GPU)
-    threads = max(1, min(args.threads, len(ids), len(cpus) if cpus else args.threads))
-    nb = args.batch_blocks if args.batch_blocks >= 0 else max(1, sms // threads)
+    want = max(1, min(args.threads, len(ids)))                 # sequences in flight per GPU
+    threads = max(1, min(want, len(cpus) if cpus else want))   # host threads: one core each
+    # sequences each thread keeps in flight (begin the frame of each, then end them). Short of cores, aim at 1.5 x the
+    # scans in flight: measured on one GPU restricted to 4 cores (taskset), 8 x 1: 7 669 scans/s; 4 x 1: 6 258; 4 x 2: 6 995;
+    # 4 x 3: 7 309
+    group = 1 if threads >= want else (3 * want + 2 * threads - 1) // (2 * threads)
+    in_flight = min(len(ids), threads * group)
+    nb = args.batch_blocks if args.batch_blocks >= 0 else max(1, sms // in_flight)
     kw = dict(persistent_lm=0) if nb == 0 else dict(persistent_lm=1, lm_max_blocks=nb)
     nodes = [host.MapOptimization(headline_params(abi, **kw), device=device, loop_closure_enabled=True, search_num=WINDOW,
                                   reserve=(1 << 18, 1 << 20, 1 << 15)) for _ in ids]
-    host.batch_replay(nodes, seqs, 0, WINDOW, threads, cpus)          # untimed: fill the windows
+    host.batch_replay(nodes, seqs, 0, WINDOW, threads, cpus, group)   # untimed: fill the windows
     torch.cuda.synchronize(device)
     if world > 1:
         dist.barrier()
-    rec, secs = host.batch_replay(nodes, seqs, WINDOW, args.scans_per_seq, threads, cpus)
+    rec, secs = host.batch_replay(nodes, seqs, WINDOW, args.scans_per_seq, threads, cpus, group)
     torch.cuda.synchronize(device)
     for n in nodes:
         n.close()
@@ -604,8 +619,8 @@ def run_batch(args, rank, world, device, dist):
     total = args.sequences * args.scans_per_seq
     secs_max = float(dt[0])
     record = {"workload": "configs[4]: %d independent VLP-16 sequences, seq -> rank = seq mod world, windows of %d keyframes pre-filled "
-                          "untimed, then %d timed scans per sequence; %d C++ host threads (= sequences in flight) per GPU, %s"
-                          % (args.sequences, WINDOW, args.scans_per_seq, threads,
+                          "untimed, then %d timed scans per sequence; %d sequences in flight per GPU (%d C++ host threads x %d), %s"
+                          % (args.sequences, WINDOW, args.scans_per_seq, in_flight, threads, group,
                              "persistent scan kernels on <= %d SMs each" % nb if nb else "one launch per LM iteration"),
               "value": round(total / secs_max, 2), "unit": UNIT, "per_gpu": round(total / secs_max / world, 2), "n_gpus": world,
               "seconds": round(secs_max, 4), "timing": "steady_clock in the C++ driver from the threads' common start to the last result on the host, max over ranks",

@@ -54,9 +54,10 @@ class _Frame(C.Structure):
     _fields_ = [("odom6", C.c_void_p), ("cloud", C.c_void_p * 5), ("n", C.c_size_t * 5)]
 
 
-def batch_replay(nodes, sequences, first, count, n_threads, cpu_ids=None):
+def batch_replay(nodes, sequences, first, count, n_threads, cpu_ids=None, group=1):
     """Batched replay (BASELINE configs[4]) through the C++ driver host/batch_replay.cpp: frames [first, first + count) of
-    every sequence through its own node, `n_threads` host threads (std::thread, optionally pinned to cpu_ids).
+    every sequence through its own node, `n_threads` host threads (std::thread, optionally pinned to cpu_ids), each keeping
+    `group` sequences in flight (begin the frame of each, then end them).
 
     nodes: list of MapOptimization; sequences: list of dict(odom=[n, 6] float32, clouds=[per frame: five arrays, all
     [m, 8] (pcl::PointXYZI layout) or all [m, 4]]). -> (records [n_seq, count, 16] float32, seconds)."""
@@ -86,9 +87,9 @@ def batch_replay(nodes, sequences, first, count, n_threads, cpu_ids=None):
     secs = C.c_double(0.0)
     err = C.create_string_buffer(512)
     cpus = np.ascontiguousarray(cpu_ids if cpu_ids is not None else [], np.int32)
-    rc = lib.llh_batch_replay(node_ptrs, C.c_int(n_seq), frame_ptrs, C.c_int(first), C.c_int(count), C.c_size_t(stride or 16),
-                              C.c_int(n_threads), _vp(cpus) if len(cpus) else None, C.c_int(len(cpus)), _vp(records),
-                              C.byref(secs), err, C.c_size_t(512))
+    rc = lib.llh_batch_replay2(node_ptrs, C.c_int(n_seq), frame_ptrs, C.c_int(first), C.c_int(count), C.c_size_t(stride or 16),
+                               C.c_int(n_threads), C.c_int(max(1, int(group))), _vp(cpus) if len(cpus) else None, C.c_int(len(cpus)),
+                               _vp(records), C.byref(secs), err, C.c_size_t(512))
     if rc != 0:
         raise RuntimeError(err.value.decode("utf-8", "replace") or "llh_batch_replay failed")
     return records, secs.value

@@ -9,6 +9,7 @@
 #include <cstring>
 #include <exception>
 #include <string>
+#include <algorithm>
 #include <thread>
 #include <vector>
 
@@ -35,10 +36,14 @@ struct llh_frame {
 // {pose[6], status, iter_num, sel_num, corner_map_ds, surf_map_ds, min_lambda, cf_mean, is_degenerate, frame ms, 0}.
 // cpu_ids (optional): thread t is pinned to cpu_ids[t % n_cpu_ids]. *seconds = wall time from the common start of the
 // threads to the last one finishing (every result is on the host by then). Returns 0, or -1 with err filled.
-int llh_batch_replay(void* const* nodes, int n_seq, const llh_frame* const* frames, int first, int count, size_t stride,
-                     int n_threads, const int* cpu_ids, int n_cpu_ids, float* records, double* seconds, char* err,
-                     size_t err_cap) {
-  if (!nodes || !frames || n_seq < 0 || count < 0 || n_threads < 1) return -1;
+// group: sequences one thread keeps IN FLIGHT together (>= 1). A thread takes its sequences `group` at a time and, frame by
+// frame, begins the frame of each (scan kernel and keyframe upload enqueued) before it ends any of them (wait, keyframe
+// store): with fewer host cores than scans the GPU can usefully hold (an 8-GPU box with 4 cores per GPU), two or more scans
+// per thread keep the SMs busy. The results do not depend on it (every sequence is its own node, handle and stream).
+int llh_batch_replay2(void* const* nodes, int n_seq, const llh_frame* const* frames, int first, int count, size_t stride,
+                      int n_threads, int group, const int* cpu_ids, int n_cpu_ids, float* records, double* seconds, char* err,
+                      size_t err_cap) {
+  if (!nodes || !frames || n_seq < 0 || count < 0 || n_threads < 1 || group < 1) return -1;
   n_threads = n_threads > n_seq ? (n_seq > 0 ? n_seq : 1) : n_threads;
   std::atomic<int> ready{0};
   std::atomic<bool> go{false}, failed{false};
@@ -57,28 +62,38 @@ int llh_batch_replay(void* const* nodes, int n_seq, const llh_frame* const* fram
     ready.fetch_add(1);
     while (!go.load(std::memory_order_acquire)) std::this_thread::yield();
     try {
-      // frame-major over this thread's sequences: while one sequence's scan is being collected the others' host
-      // work is not pending anyway (the calls are synchronous), so the order only decides cache locality
-      for (int s = t; s < n_seq && !failed.load(); s += n_threads) {
-        MapOptimization* M = static_cast<MapOptimization*>(nodes[s]);
-        for (int k = 0; k < count; ++k) {
-          const llh_frame& f = frames[s][first + k];
-          MapOptimization::FrameView v;
-          v.corner_scan = f.cloud[0]; v.n_corner_scan = f.n[0];
-          v.corner_scan_ds = f.cloud[1]; v.n_corner_scan_ds = f.n[1];
-          v.surf_last_ds = f.cloud[2]; v.n_surf_last_ds = f.n[2];
-          v.outlier_last_ds = f.cloud[3]; v.n_outlier_last_ds = f.n[3];
-          v.surf_total_ds = f.cloud[4]; v.n_surf_total_ds = f.n[4];
-          v.device = false;
-          v.stride_bytes = stride;
-          M->processFrameView(f.odom6, v);
-          if (records) {
-            float* r = records + ((size_t)s * (size_t)count + (size_t)k) * 16;
-            const ll_result& R = M->lastResult;
-            std::memcpy(r, R.pose, 6 * sizeof(float));
-            r[6] = (float)R.status; r[7] = (float)R.iter_num; r[8] = (float)R.sel_num;
-            r[9] = (float)R.corner_map_ds; r[10] = (float)R.surf_map_ds; r[11] = R.min_lambda; r[12] = R.cf_mean;
-            r[13] = (float)R.is_degenerate; r[14] = (float)M->lastFrameMs; r[15] = 0.f;
+      // this thread's sequences t, t + n_threads, ... in groups of `group`; within a group frame-major, begin-all then end-all
+      std::vector<int> mine;
+      for (int q = t; q < n_seq; q += n_threads) mine.push_back(q);
+      std::vector<MapOptimization::FrameView> views((size_t)group);
+      for (size_t g0 = 0; g0 < mine.size() && !failed.load(); g0 += (size_t)group) {
+        const size_t ng = std::min((size_t)group, mine.size() - g0);
+        for (int k = 0; k < count && !failed.load(); ++k) {
+          for (size_t u = 0; u < ng; ++u) {
+            const int q = mine[g0 + u];
+            const llh_frame& f = frames[q][first + k];
+            MapOptimization::FrameView& v = views[u];
+            v.corner_scan = f.cloud[0]; v.n_corner_scan = f.n[0];
+            v.corner_scan_ds = f.cloud[1]; v.n_corner_scan_ds = f.n[1];
+            v.surf_last_ds = f.cloud[2]; v.n_surf_last_ds = f.n[2];
+            v.outlier_last_ds = f.cloud[3]; v.n_outlier_last_ds = f.n[3];
+            v.surf_total_ds = f.cloud[4]; v.n_surf_total_ds = f.n[4];
+            v.device = false;
+            v.stride_bytes = stride;
+            static_cast<MapOptimization*>(nodes[q])->processFrameViewBegin(f.odom6, v);
+          }
+          for (size_t u = 0; u < ng; ++u) {
+            const int q = mine[g0 + u];
+            MapOptimization* M = static_cast<MapOptimization*>(nodes[q]);
+            M->processFrameViewEnd();
+            if (records) {
+              float* r = records + ((size_t)q * (size_t)count + (size_t)k) * 16;
+              const ll_result& R = M->lastResult;
+              std::memcpy(r, R.pose, 6 * sizeof(float));
+              r[6] = (float)R.status; r[7] = (float)R.iter_num; r[8] = (float)R.sel_num;
+              r[9] = (float)R.corner_map_ds; r[10] = (float)R.surf_map_ds; r[11] = R.min_lambda; r[12] = R.cf_mean;
+              r[13] = (float)R.is_degenerate; r[14] = (float)M->lastFrameMs; r[15] = 0.f;
+            }
           }
         }
       }
@@ -101,6 +116,13 @@ int llh_batch_replay(void* const* nodes, int n_seq, const llh_frame* const* fram
     return -1;
   }
   return 0;
+}
+
+int llh_batch_replay(void* const* nodes, int n_seq, const llh_frame* const* frames, int first, int count, size_t stride,
+                     int n_threads, const int* cpu_ids, int n_cpu_ids, float* records, double* seconds, char* err,
+                     size_t err_cap) {
+  return llh_batch_replay2(nodes, n_seq, frames, first, count, stride, n_threads, 1, cpu_ids, n_cpu_ids, records, seconds, err,
+                           err_cap);
 }
 
 }  // extern "C"

@@ -264,6 +264,12 @@ bool MapOptimization::LMOptimization(int iterCount) {  // :1444-1570
 }
 
 void MapOptimization::scan2MapOptimization() {  // :1572-1610
+  scan2MapLaunch();
+  scan2MapCollect();
+}
+
+void MapOptimization::scan2MapLaunch() {
+  scanInFlight_ = false;
   std::memset(&lastResult, 0, sizeof(lastResult));
   lastResult.status = 1;
   std::memcpy(lastResult.pose, transformTobeMapped, sizeof(lastResult.pose));
@@ -277,7 +283,6 @@ void MapOptimization::scan2MapOptimization() {  // :1572-1610
                                    view_->surf_last_ds, view_->n_surf_last_ds, view_->outlier_last_ds,
                                    view_->n_outlier_last_ds),
           "ll_prefetch_keyframe_dev");
-    check(ll_scan2map_wait(h_, transformTobeMapped, &lastResult), "ll_scan2map_wait");
   } else if (view_) {
     // While the scan runs on the GPU, pack and upload the three clouds saveKeyFramesAndFactor is about to store
     // (every frame becomes a keyframe, :1622-1631; only its pose comes out of the scan).
@@ -288,14 +293,12 @@ void MapOptimization::scan2MapOptimization() {  // :1572-1610
                                view_->surf_last_ds, view_->n_surf_last_ds, view_->outlier_last_ds,
                                view_->n_outlier_last_ds, view_->stride_bytes),
           "ll_prefetch_keyframe");
-    check(ll_scan2map_wait(h_, transformTobeMapped, &lastResult), "ll_scan2map_wait");
   } else if (scanDevValid_) {  // downsampleCurrentScan left everything the scan and the keyframe need on the device
     const ll_scan_clouds& d = scanDev_;
     check(ll_scan2map_dev_async(h_, d.d_ds[2], d.n_ds[2], d.d_ds[5], d.n_ds[5], transformTobeMapped), "ll_scan2map_dev_async");
     check(ll_prefetch_keyframe_dev(h_, (int)cloudKeyPoses3D.size(), d.d_raw[2], d.n_raw[2], d.d_ds[1], d.n_ds[1], d.d_ds[4],
                                    d.n_ds[4]),
           "ll_prefetch_keyframe_dev");
-    check(ll_scan2map_wait(h_, transformTobeMapped, &lastResult), "ll_scan2map_wait");
   } else {
     check(ll_scan2map_async(h_, laserCloudCornerScanDS->points.data(), laserCloudCornerScanDS->size(),
                             laserCloudSurfTotalLastDS->points.data(), laserCloudSurfTotalLastDS->size(),
@@ -306,8 +309,14 @@ void MapOptimization::scan2MapOptimization() {  // :1572-1610
                                laserCloudSurfLastDS->size(), laserCloudOutlierLastDS->points.data(),
                                laserCloudOutlierLastDS->size(), sizeof(PointType)),
           "ll_prefetch_keyframe");
-    check(ll_scan2map_wait(h_, transformTobeMapped, &lastResult), "ll_scan2map_wait");
   }
+  scanInFlight_ = true;
+}
+
+void MapOptimization::scan2MapCollect() {
+  if (!scanInFlight_) return;  // (first frame: no map yet, nothing was launched)
+  scanInFlight_ = false;
+  check(ll_scan2map_wait(h_, transformTobeMapped, &lastResult), "ll_scan2map_wait");
   laserCloudCornerFromMapDSNum = lastResult.corner_map_ds;
   laserCloudSurfFromMapDSNum = lastResult.surf_map_ds;
   if (lastResult.status == 2) {  // not the reference's skip: the search grid did not fit (see gridOverflowScans)
@@ -387,7 +396,12 @@ void MapOptimization::saveKeyFramesAndFactor() {  // :1612-1755, pose graph = pa
 }
 
 void MapOptimization::processFrameView(const float laser_odometry[6], const FrameView& frame) {
-  const auto t_frame = std::chrono::steady_clock::now();
+  processFrameViewBegin(laser_odometry, frame);
+  processFrameViewEnd();
+}
+
+void MapOptimization::processFrameViewBegin(const float laser_odometry[6], const FrameView& frame) {
+  frameStart_ = std::chrono::steady_clock::now();
   frame_idx++;
   scanDevValid_ = false;
   view_ = &frame;
@@ -395,7 +409,16 @@ void MapOptimization::processFrameView(const float laser_odometry[6], const Fram
     for (int i = 0; i < 6; ++i) transformSum[i] = laser_odometry[i];
     transformAssociateToMap();
     extractSurroundingKeyFrames();
-    scan2MapOptimization();
+    scan2MapLaunch();
+  } catch (...) {
+    view_ = nullptr;
+    throw;
+  }
+}
+
+void MapOptimization::processFrameViewEnd() {
+  try {
+    scan2MapCollect();
     saveKeyFramesAndFactor();
     correctPoses();
     clearCloud();
@@ -404,7 +427,7 @@ void MapOptimization::processFrameView(const float laser_odometry[6], const Fram
     throw;
   }
   view_ = nullptr;
-  lastFrameMs = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_frame).count();
+  lastFrameMs = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - frameStart_).count();
 }
 
 void MapOptimization::correctPoses() {  // :1757-1785

@@ -7,6 +7,7 @@
 #pragma once
 #include <cstddef>
 #include <cstdint>
+#include <chrono>
 #include <deque>
 #include <memory>
 #include <string>
@@ -86,6 +87,11 @@ class MapOptimization {
     size_t stride_bytes = 32;  // host clouds only
   };
   void processFrameView(const float laser_odometry[6], const FrameView& frame);
+  // The same frame in two halves, for a caller that drives several nodes from one thread (host/batch_replay.cpp): Begin
+  // returns as soon as the scan kernel and the keyframe upload are enqueued, End waits for the scan and finishes the frame.
+  // `frame` must stay alive until End returns; nothing else may be called on the node in between.
+  void processFrameViewBegin(const float laser_odometry[6], const FrameView& frame);
+  void processFrameViewEnd();
 
   // ---- members with the reference's names (mapOptimization.h:311,327-333 and :458,:583) ----------------
   void transformAssociateToMap();
@@ -96,6 +102,8 @@ class MapOptimization {
   void surfOptimization();          // stage-level
   bool LMOptimization(int iterCount);  // stage-level, on laserCloudOri / coeffSel
   void scan2MapOptimization();      // the whole loop in one ABI call
+  void scan2MapLaunch();            // ... its first half: enqueue the scan and the keyframe upload
+  void scan2MapCollect();           // ... its second half: wait, then :1588-1608
   void saveKeyFramesAndFactor();
   void correctPoses();
   void clearCloud();
@@ -153,6 +161,8 @@ class MapOptimization {
   std::vector<int> surroundingExistingKeyPosesID_;
   std::vector<int> mapIds_;
   bool mapBuilt_ = false;
+  bool scanInFlight_ = false;  // between scan2MapLaunch and scan2MapCollect
+  std::chrono::steady_clock::time_point frameStart_;
   const FrameView* view_ = nullptr;  // non-null while processFrameView runs
   ll_scan_clouds scanDev_{};  // device copies left by downsampleCurrentScan (valid for the current frame)
   bool scanDevValid_ = false;
