@@ -78,6 +78,8 @@ def parse_args():
                     help="batch: > 0 = every sequence runs the persistent scan kernel on at most this many SMs "
                          "(lm_max_blocks); 0 = one launch per LM iteration (persistent_lm = 0); -1 = SMs / threads")
     ap.add_argument("--batch-dump", default="", help="batch: write the gathered records to this .npy (rank 0)")
+    ap.add_argument("--batch-group", type=int, default=0,
+                    help="batch: sequences each host thread keeps in flight (0 = 1, or more when the rank is short of cores)")
     ap.add_argument("--no-l2-flush", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-at-scale", action="store_true", help="skip configs[2]/[3], raw-frame, as-shipped and next-row records")
@@ -582,6 +584,8 @@ def run_batch(args, rank, world, device, dist):
     # scans in flight: measured on one GPU restricted to 4 cores (taskset), 8 x 1: 7 669 scans/s; 4 x 1: 6 258; 4 x 2: 6 995;
     # 4 x 3: 7 309
     group = 1 if threads >= want else (3 * want + 2 * threads - 1) // (2 * threads)
+    if args.batch_group > 0:
+        group = args.batch_group
     in_flight = min(len(ids), threads * group)
     nb = args.batch_blocks if args.batch_blocks >= 0 else max(1, sms // in_flight)
     kw = dict(persistent_lm=0) if nb == 0 else dict(persistent_lm=1, lm_max_blocks=nb)

@@ -3,7 +3,8 @@
 The batched replay (BASELINE configs[4]) is run through `bench.py --workload batch` under torch.distributed.run with
 world = 1, 2, 4, 8 (as many as the box has GPUs), one process per GPU over NCCL; the records NCCL gathers — pose, status,
 iteration count, residual count of every (sequence, scan) — must be bit-identical whatever the partition. World 1 is also
-run with a different number of host threads (sequences in flight), so the same check covers the concurrency on one GPU.
+run with a different number of host threads (sequences in flight) and with threads that each keep three sequences in
+flight, so the same check covers the concurrency on one GPU.
 Skipped below two devices; the single-GPU half runs on any box.
 """
 import os
@@ -33,13 +34,14 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _run(world, threads, out):
+def _run(world, threads, out, group=0):
     cmd = [sys.executable]
     if world > 1:
         cmd += ["-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
                 "--master-port", str(_free_port())]
     cmd += [os.path.join(ROOT, "bench.py"), "--gpus", str(world), "--workload", "batch", "--sequences", str(N_SEQ),
-            "--scans-per-seq", str(N_SCANS), "--threads", str(threads), "--batch-blocks", str(BLOCKS), "--batch-dump", out]
+            "--scans-per-seq", str(N_SCANS), "--threads", str(threads), "--batch-blocks", str(BLOCKS), "--batch-dump", out,
+            "--batch-group", str(group)]
     env = dict(os.environ)
     env.pop("RANK", None)
     env.pop("WORLD_SIZE", None)
@@ -59,6 +61,10 @@ def test_batch_records_identical_across_world_sizes(tmp_path):
     other = _run(1, 2, str(tmp_path / "w1b.npy"))
     assert np.array_equal(base[:, :, COMPARED].view(np.uint64), other[:, :, COMPARED].view(np.uint64)), \
         "records depend on the number of sequences in flight"
+    # one host thread driving several sequences at once (host/batch_replay.cpp: begin the frame of each, then end them)
+    grouped = _run(1, 2, str(tmp_path / "w1c.npy"), group=3)
+    assert np.array_equal(base[:, :, COMPARED].view(np.uint64), grouped[:, :, COMPARED].view(np.uint64)), \
+        "records depend on how many sequences a host thread keeps in flight"
     worlds = [w for w in (2, 4, 8) if w <= n_dev]
     if not worlds:
         pytest.skip("one device: world 2/4/8 not run (the world-1 concurrency check above passed)")
