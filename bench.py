@@ -553,6 +553,19 @@ def rank_cpus(local_rank, world):
     return cores
 
 
+def batch_schedule(want_in_flight, n_sequences, n_cpus, forced_group=0):
+    """How a rank drives its sequences: -> (host threads, sequences each thread keeps in flight, sequences in flight).
+    One host thread per core at most (each spins on its scan's completion). Short of cores, a thread keeps several
+    sequences in flight (host/batch_replay.cpp: begin the frame of each, then end them), aiming at 1.5 x the wanted number:
+    measured on one GPU restricted to 4 cores (taskset), 8 x 1: 7 669 scans/s; 4 x 1: 6 258; 4 x 2: 6 995; 4 x 3: 7 309."""
+    want = max(1, min(want_in_flight, n_sequences))
+    threads = max(1, min(want, n_cpus if n_cpus > 0 else want))
+    group = 1 if threads >= want else (3 * want + 2 * threads - 1) // (2 * threads)
+    if forced_group > 0:
+        group = forced_group
+    return threads, group, max(1, min(n_sequences, threads * group))
+
+
 def run_batch(args, rank, world, device, dist):
     """BASELINE configs[4]: `--sequences` independent VLP-16 sequences, seq -> rank = seq mod world, one handle + stream per
     sequence, `--threads` C++ host threads per GPU (host/batch_replay.cpp). Every sequence first registers WINDOW scans
@@ -578,15 +591,7 @@ def run_batch(args, rank, world, device, dist):
     cpus = rank_cpus(int(os.environ.get("LOCAL_RANK", "0")), world)
     # one host thread per sequence in flight, each spinning on its own core while its scan runs: never more threads than
     # this rank has cores (a 2-GPU box with 12 cores gave each rank 6: eight threads on them ran the batch at 65 % per GPU)
-    want = max(1, min(args.threads, len(ids)))                 # sequences in flight per GPU
-    threads = max(1, min(want, len(cpus) if cpus else want))   # host threads: one core each
-    # sequences each thread keeps in flight (begin the frame of each, then end them). Short of cores, aim at 1.5 x the
-    # scans in flight: measured on one GPU restricted to 4 cores (taskset), 8 x 1: 7 669 scans/s; 4 x 1: 6 258; 4 x 2: 6 995;
-    # 4 x 3: 7 309
-    group = 1 if threads >= want else (3 * want + 2 * threads - 1) // (2 * threads)
-    if args.batch_group > 0:
-        group = args.batch_group
-    in_flight = min(len(ids), threads * group)
+    threads, group, in_flight = batch_schedule(args.threads, len(ids), len(cpus), args.batch_group)
     nb = args.batch_blocks if args.batch_blocks >= 0 else max(1, sms // in_flight)
     kw = dict(persistent_lm=0) if nb == 0 else dict(persistent_lm=1, lm_max_blocks=nb)
     nodes = [host.MapOptimization(headline_params(abi, **kw), device=device, loop_closure_enabled=True, search_num=WINDOW,
