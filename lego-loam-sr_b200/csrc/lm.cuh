@@ -999,7 +999,7 @@ __device__ __noinline__ uint32_t knn_cache_fill(const float4* sorted, int my_sta
   for (int attempt = first_attempt; attempt < 3; ++attempt) {
     const float margin = attempt == 0 ? LM_CACHE_MARGIN : 0.3f * LM_CACHE_MARGIN;
     // (R may exceed 1 m — a fifth neighbour near the acceptance limit, or a rejected query: the set is then only usable
-    //  while the query stays in its cell, knn5_thread.) In a dense map — un-downsampled: the fifth neighbour centimetres
+    //  while the query stays in its cell, knn5_warp_step2.) In a dense map — un-downsampled: the fifth neighbour centimetres
     //  away — a quarter of a metre around it holds hundreds of points, so the radius is also bounded relative to d5: with
     //  N(r) ~ r^2..r^3 a factor 1.7 (then 1.3, then 1.1) keeps the set near 20 points, still far more margin than a query moves.
     const float s5 = rejected ? 0.f : sqrtf(__uint_as_float(d5bits));
@@ -1095,7 +1095,7 @@ __device__ __noinline__ uint32_t knn_cache_fill(const float4* sorted, int my_sta
         // (an EMPTY cell-complete set is stored as count 33: cnt must be > 0 to be used, and no lane is below 33 <= 32)
         *cnt_out = fits ? (base > 0 ? base : LM_CACHE_CAND + 1) : -1;
         if (fits && __popc(members) == 5) {
-          // the guard of knn5_thread's step 1, straight from this scan: it covered every point of the 27 cells, so the
+          // the guard of knn5_thread_step1, straight from this scan: it covered every point of the 27 cells, so the
           // nearest point that is not one of the five is at distance sqrt(d6) or beyond the 27 cells (>= 1 m + the distance
           // to the nearest face of the query's cell)
           const float fx = sx - floorf(sx), fy = sy - floorf(sy), fz = sz - floorf(sz);
@@ -1112,7 +1112,7 @@ __device__ __noinline__ uint32_t knn_cache_fill(const float4* sorted, int my_sta
   return LM_GEO_NONE;
 }
 
-// Step 1 of the per-thread cached search (see knn5_thread): up to six member points (absent: d = LM_EMPTY_D2), the guard
+// Step 1 of the per-thread cached search (see knn5_thread_step1): up to six member points (absent: d = LM_EMPTY_D2), the guard
 // t1 = (c', G). Returns true and fills the slot when the members still hold the five nearest points of sel.
 __device__ __forceinline__ bool knn5_guard_check(const float4 sel, const float4 (&nb)[6], const bool (&have)[6], const float4 t1,
                                                  uint32_t max_bits, uint32_t geo_sig, float* slot) {
@@ -1901,7 +1901,8 @@ __device__ __forceinline__ float lm_block_pass_cached(const LMArgs& A, const Tri
     const int nc_pad = (nc + 31) & ~31;
     const int nslots = nc_pad + (cn - nc);
     const bool first_chunk = c0 == 0;  // the cache slots belong to the first LM_QCAP queries of the block
-    // ---- (A) cached search, one THREAD per query: the thread that will fit it (knn5_thread). What it cannot prove is
+    // ---- (A) cached search, one THREAD per query: the thread that will fit it (knn5_thread_step1; a set that has to be
+    //      re-scanned is re-scanned by the warp, knn5_warp_step2). What it cannot prove is
     //      flagged for its warp: bit j of s_need[w] = query w + 16 j of this chunk.
     const int my_i = tid < nc ? tid : (tid >= nc_pad && tid < nslots ? nc + (tid - nc_pad) : -1);
     if (tid < LM_WARPS) s_need[tid] = 0u;
